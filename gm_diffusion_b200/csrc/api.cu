@@ -1,0 +1,83 @@
+// C-ABI plumbing shared by all kernels: error strings, launch accounting, TMA descriptor encoding.
+#include "common.cuh"
+#include "../../include/gmd_b200.h"
+#include <atomic>
+#include <cstdarg>
+#include <cstdio>
+#include <mutex>
+
+namespace gmd {
+
+static thread_local char g_err[512] = "";
+static std::atomic<int64_t> g_launches{0};
+
+void set_last_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+
+int check_launch(const char* what) {
+    cudaError_t e = cudaPeekAtLastError();
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        set_last_error("%s: %s", what, cudaGetErrorString(e));
+        return kErrCuda;
+    }
+    return kOk;
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode_fn() {
+    static EncodeTiledFn fn = nullptr;
+    static std::once_flag once;
+    std::call_once(once, [] {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres);
+        if (e == cudaSuccess && qres == cudaDriverEntryPointSuccess) fn = reinterpret_cast<EncodeTiledFn>(p);
+    });
+    return fn;
+}
+
+int encode_tensor_map_bf16(CUtensorMap* out, const void* base, int rank, const uint64_t* dims,
+                           const uint64_t* strides_bytes, const uint32_t* box, bool swizzle128) {
+    EncodeTiledFn fn = get_encode_fn();
+    if (!fn) {
+        set_last_error("cuTensorMapEncodeTiled entry point unavailable (no CUDA driver?)");
+        return kErrCuda;
+    }
+    cuuint64_t gdim[5];
+    cuuint64_t gstr[4];
+    cuuint32_t bx[5], es[5];
+    for (int i = 0; i < rank; ++i) {
+        gdim[i] = dims[i];
+        bx[i] = box[i];
+        es[i] = 1;
+        if (i > 0) gstr[i - 1] = strides_bytes[i];
+    }
+    CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(base), gdim, gstr, bx, es,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE,
+                    CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        set_last_error("cuTensorMapEncodeTiled failed (%d): rank=%d dims=[%llu,%llu,%llu,%llu] box=[%u,%u,%u,%u] base=%p",
+                       (int)r, rank, (unsigned long long)dims[0], (unsigned long long)(rank > 1 ? dims[1] : 0),
+                       (unsigned long long)(rank > 2 ? dims[2] : 0), (unsigned long long)(rank > 3 ? dims[3] : 0), box[0],
+                       rank > 1 ? box[1] : 0, rank > 2 ? box[2] : 0, rank > 3 ? box[3] : 0, base);
+        return kErrInvalid;
+    }
+    return kOk;
+}
+
+}  // namespace gmd
+
+extern "C" int gmd_version(void) { return GMD_VERSION; }
+extern "C" const char* gmd_last_error(void) { return gmd::g_err; }
+extern "C" int64_t gmd_launch_count(void) { return gmd::g_launches.load(); }
+extern "C" void gmd_reset_launch_count(void) { gmd::g_launches.store(0); }

@@ -1,0 +1,296 @@
+// Kernel (a): flash attention on tcgen05 + TMEM, fed by TMA.   O = softmax(Q K^T * scale) V
+//
+// One CTA owns 128 query rows of one (batch, head).  Warp 0 = TMA producer (Q once, then a ring of K/V
+// tiles of 64 keys), warp 1 = MMA issuer, warps 2-5 = softmax (one thread per query row).
+//   S = Q K^T     : tcgen05.mma  A = Q smem (K-major), B = K smem (K-major)      -> TMEM cols [0, 64)
+//   P = exp2(..)  : softmax warps read S with tcgen05.ld, write bf16 P to smem (K-major, 128B swizzle)
+//   O += P V      : tcgen05.mma  A = P smem (K-major), B = V smem (MN-major)     -> TMEM cols [64, 64+DPV)
+// O is rescaled in place in TMEM (tcgen05.ld / st) only when a row maximum of the warp moved.
+// Head dims 40/80/160 (SD1.5: 8 heads at every level) are zero-padded to a multiple of 16 for free by
+// TMA out-of-bounds fill: the tensor map's innermost dim is the true head dim, the box is 64 wide.
+// Two CTAs are co-resident per SM for d = 40/80 so one CTA's MMAs overlap the other's exponentials.
+#include "common.cuh"
+#include "../../include/gmd_b200.h"
+
+namespace gmd {
+void count_launch(int n);
+namespace {
+
+constexpr int BQ = 128;   // query rows per CTA
+constexpr int BKV = 64;   // keys per tile (one 128-byte swizzle row of P)
+
+struct AttnArgs {
+    __nv_bfloat16* o;
+    int64_t o_stride_b, o_stride_n, o_stride_h;
+    int Nq, Nk;
+    float scale_log2;
+};
+
+__device__ __forceinline__ float ex2(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+
+template <int D>
+struct Cfg {
+    static constexpr int NDB = (D + 63) / 64;            // 64-wide d blocks
+    static constexpr int DP = (D + 15) / 16 * 16;        // K extent of QK^T and N extent of PV
+    static constexpr int STAGES = D <= 40 ? 3 : 2;
+    static constexpr int Q_BYTES = NDB * BQ * 128;
+    static constexpr int KV_BLOCK_BYTES = BKV * 128;     // one d block of a K or V tile
+    static constexpr int K_BYTES = NDB * KV_BLOCK_BYTES;
+    static constexpr int STAGE_BYTES = 2 * K_BYTES;      // K then V
+    static constexpr int P_BYTES = BQ * 128;
+    static constexpr int SMEM = Q_BYTES + STAGES * STAGE_BYTES + P_BYTES + 256 + 1024;
+    static constexpr uint32_t TMEM_COLS = (BKV + DP) <= 128 ? 128 : 256;
+    static constexpr int MIN_CTAS = D <= 80 ? 2 : 1;
+};
+
+template <int D>
+__global__ void __launch_bounds__(192, Cfg<D>::MIN_CTAS)
+attn_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_k,
+            const __grid_constant__ CUtensorMap map_v, const AttnArgs args) {
+    using C = Cfg<D>;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t* q_smem = smem;
+    uint8_t* kv_smem = smem + C::Q_BYTES;
+    uint8_t* p_smem = kv_smem + C::STAGES * C::STAGE_BYTES;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(p_smem + C::P_BYTES);
+    uint64_t* q_full = bars;
+    uint64_t* kv_full = bars + 1;
+    uint64_t* kv_empty = kv_full + C::STAGES;
+    uint64_t* s_full = kv_empty + C::STAGES;
+    uint64_t* p_full = s_full + 1;
+    uint64_t* pv_done = p_full + 1;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(pv_done + 1);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int q0 = blockIdx.x * BQ, head = blockIdx.y, batch = blockIdx.z;
+    const int num_tiles = (args.Nk + BKV - 1) / BKV;
+
+    if (threadIdx.x == 0) {
+        tma_prefetch_desc(&map_q); tma_prefetch_desc(&map_k); tma_prefetch_desc(&map_v);
+        mbar_init(q_full, 1);
+        for (int s = 0; s < C::STAGES; ++s) { mbar_init(&kv_full[s], 1); mbar_init(&kv_empty[s], 1); }
+        mbar_init(s_full, 1);
+        mbar_init(p_full, 128);
+        mbar_init(pv_done, 1);
+        fence_barrier_init();
+    }
+    if (warp == 1) tmem_alloc<C::TMEM_COLS>(tmem_slot);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_s = *tmem_slot;
+    const uint32_t tmem_o = tmem_s + BKV;
+
+    if (warp == 0) {
+        if (elect_one()) {
+            mbar_expect_tx(q_full, C::Q_BYTES);
+            for (int b = 0; b < C::NDB; ++b) tma_load_4d(q_smem + b * BQ * 128, &map_q, q_full, b * 64, head, q0, batch);
+            for (int j = 0; j < num_tiles; ++j) {
+                const int st = j % C::STAGES;
+                const uint32_t ph = (j / C::STAGES) & 1;
+                mbar_wait(&kv_empty[st], ph ^ 1);
+                uint8_t* ks = kv_smem + st * C::STAGE_BYTES;
+                uint8_t* vs = ks + C::K_BYTES;
+                mbar_expect_tx(&kv_full[st], C::STAGE_BYTES);
+                for (int b = 0; b < C::NDB; ++b) {
+                    tma_load_4d(ks + b * C::KV_BLOCK_BYTES, &map_k, &kv_full[st], b * 64, head, j * BKV, batch);
+                    tma_load_4d(vs + b * C::KV_BLOCK_BYTES, &map_v, &kv_full[st], b * 64, head, j * BKV, batch);
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (elect_one()) {
+            constexpr uint32_t IDESC_S = umma_idesc_bf16(BQ, BKV, false, false);
+            constexpr uint32_t IDESC_O = umma_idesc_bf16(BQ, C::DP, false, true);  // B = V is MN-major
+            const uint32_t q_addr = smem_u32(q_smem), p_addr = smem_u32(p_smem);
+            auto issue_s = [&](int j) {
+                const int st = j % C::STAGES;
+                mbar_wait(&kv_full[st], (j / C::STAGES) & 1);
+                tc_fence_after();
+                const uint32_t k_addr = smem_u32(kv_smem + st * C::STAGE_BYTES);
+#pragma unroll
+                for (int ks = 0; ks < C::DP / 16; ++ks) {
+                    const int blk = ks >> 2, within = ks & 3;
+                    uint64_t da = umma_desc_k_sw128(q_addr + blk * (BQ * 128) + within * 32);
+                    uint64_t db = umma_desc_k_sw128(k_addr + blk * C::KV_BLOCK_BYTES + within * 32);
+                    umma_bf16_ss(tmem_s, da, db, IDESC_S, ks != 0 ? 1u : 0u);
+                }
+                umma_commit(s_full);
+            };
+            mbar_wait(q_full, 0);
+            issue_s(0);
+            for (int j = 0; j < num_tiles; ++j) {
+                const int st = j % C::STAGES;
+                mbar_wait(p_full, j & 1);
+                tc_fence_after();
+                const uint32_t v_addr = smem_u32(kv_smem + st * C::STAGE_BYTES + C::K_BYTES);
+#pragma unroll
+                for (int ks = 0; ks < BKV / 16; ++ks) {
+                    uint64_t da = umma_desc_k_sw128(p_addr + ks * 32);
+                    uint64_t db = umma_desc_mn_sw128(v_addr + ks * 16 * 128, C::KV_BLOCK_BYTES);
+                    umma_bf16_ss(tmem_o, da, db, IDESC_O, (j | ks) != 0 ? 1u : 0u);
+                }
+                umma_commit(&kv_empty[st]);
+                umma_commit(pv_done);
+                if (j + 1 < num_tiles) issue_s(j + 1);
+            }
+        }
+    } else {
+        const int lg = warp & 3;
+        const int row = lg * 32 + lane;
+        const uint32_t lane_off = static_cast<uint32_t>(lg * 32) << 16;
+        float m = -INFINITY, l = 0.0f;
+        for (int j = 0; j < num_tiles; ++j) {
+            mbar_wait(s_full, j & 1);
+            tc_fence_after();
+            uint32_t sr[64];
+            {
+                uint32_t t0[32], t1[32];
+                tmem_ld_32x32(tmem_s + lane_off, t0);
+                tmem_ld_32x32(tmem_s + lane_off + 32, t1);
+                tmem_wait_ld();
+#pragma unroll
+                for (int k = 0; k < 32; ++k) { sr[k] = t0[k]; sr[32 + k] = t1[k]; }
+            }
+            const int valid = args.Nk - j * BKV;  // columns >= valid are padding keys
+            float mj = -INFINITY;
+#pragma unroll
+            for (int k = 0; k < 64; ++k) {
+                float s = __uint_as_float(sr[k]) * args.scale_log2;
+                if (k >= valid) s = -INFINITY;
+                sr[k] = __float_as_uint(s);
+                mj = fmaxf(mj, s);
+            }
+            const float m_new = fmaxf(m, mj);
+            const float alpha = ex2(m - m_new);  // m = -inf on the first tile -> 0
+            float rowsum = 0.0f;
+            uint32_t pk[32];
+#pragma unroll
+            for (int k = 0; k < 32; ++k) {
+                float p0 = ex2(__uint_as_float(sr[2 * k]) - m_new);
+                float p1 = ex2(__uint_as_float(sr[2 * k + 1]) - m_new);
+                rowsum += p0 + p1;
+                pk[k] = pack_bf16x2(p0, p1);
+            }
+            l = l * alpha + rowsum;
+            if (j > 0) {
+                mbar_wait(pv_done, (j - 1) & 1);  // PV_{j-1} finished: P smem reusable, O stable
+                tc_fence_after();
+            }
+            // P row -> smem, K-major SWIZZLE_128B: 16-byte chunk c of row r lands at chunk (c ^ (r & 7))
+            {
+                uint8_t* prow = p_smem + row * 128;
+#pragma unroll
+                for (int c = 0; c < 8; ++c) {
+                    uint4 v = make_uint4(pk[4 * c], pk[4 * c + 1], pk[4 * c + 2], pk[4 * c + 3]);
+                    *reinterpret_cast<uint4*>(prow + ((c ^ (row & 7)) << 4)) = v;
+                }
+            }
+            if (j > 0 && __any_sync(0xffffffffu, m_new > m)) {
+#pragma unroll
+                for (int ch = 0; ch < C::DP / 16; ++ch) {
+                    uint32_t o[16];
+                    tmem_ld_32x16(tmem_o + lane_off + ch * 16, o);
+                    tmem_wait_ld();
+#pragma unroll
+                    for (int k = 0; k < 16; ++k) o[k] = __float_as_uint(__uint_as_float(o[k]) * alpha);
+                    tmem_st_32x16(tmem_o + lane_off + ch * 16, o);
+                }
+                tmem_wait_st();
+            }
+            m = m_new;
+            fence_proxy_async_smem();
+            tc_fence_before();
+            mbar_arrive(p_full);
+        }
+        mbar_wait(pv_done, (num_tiles - 1) & 1);
+        tc_fence_after();
+        const float inv_l = 1.0f / l;
+        const int q = q0 + row;
+        __nv_bfloat16* op = args.o + batch * args.o_stride_b + (int64_t)q * args.o_stride_n + head * args.o_stride_h;
+#pragma unroll
+        for (int ch = 0; ch < C::DP / 16; ++ch) {
+            uint32_t o[16];
+            tmem_ld_32x16(tmem_o + lane_off + ch * 16, o);
+            tmem_wait_ld();
+            if (q < args.Nq) {
+#pragma unroll
+                for (int h8 = 0; h8 < 2; ++h8) {
+                    const int d0 = ch * 16 + h8 * 8;
+                    if (d0 < D) {  // D is a multiple of 8
+                        uint4 v = make_uint4(pack_bf16x2(__uint_as_float(o[h8 * 8 + 0]) * inv_l, __uint_as_float(o[h8 * 8 + 1]) * inv_l),
+                                             pack_bf16x2(__uint_as_float(o[h8 * 8 + 2]) * inv_l, __uint_as_float(o[h8 * 8 + 3]) * inv_l),
+                                             pack_bf16x2(__uint_as_float(o[h8 * 8 + 4]) * inv_l, __uint_as_float(o[h8 * 8 + 5]) * inv_l),
+                                             pack_bf16x2(__uint_as_float(o[h8 * 8 + 6]) * inv_l, __uint_as_float(o[h8 * 8 + 7]) * inv_l));
+                        *reinterpret_cast<uint4*>(op + d0) = v;
+                    }
+                }
+            }
+        }
+        tc_fence_before();
+    }
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        tmem_dealloc<C::TMEM_COLS>(tmem_s);
+    }
+}
+
+template <int D>
+int launch(const gmd_attn_params* p, cudaStream_t st) {
+    using C = Cfg<D>;
+    static bool configured = false;
+    if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(attn_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM);
+        if (e != cudaSuccess) { set_last_error("attn: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return kErrCuda; }
+        configured = true;
+    }
+    CUtensorMap mq, mk, mv;
+    auto enc = [&](CUtensorMap* m, const void* base, int64_t sb, int64_t sn, int64_t sh, int n, uint32_t rows) {
+        uint64_t dims[4] = {(uint64_t)D, (uint64_t)p->H, (uint64_t)n, (uint64_t)p->B};
+        uint64_t strides[4] = {2, (uint64_t)sh * 2, (uint64_t)sn * 2, (uint64_t)sb * 2};
+        uint32_t box[4] = {64, 1, rows, 1};
+        return encode_tensor_map_bf16(m, base, 4, dims, strides, box, true);
+    };
+    int rc;
+    if ((rc = enc(&mq, p->q, p->q_stride_b, p->q_stride_n, p->q_stride_h, p->Nq, BQ))) return rc;
+    if ((rc = enc(&mk, p->k, p->k_stride_b, p->k_stride_n, p->k_stride_h, p->Nk, BKV))) return rc;
+    if ((rc = enc(&mv, p->v, p->v_stride_b, p->v_stride_n, p->v_stride_h, p->Nk, BKV))) return rc;
+    AttnArgs a;
+    a.o = static_cast<__nv_bfloat16*>(p->o);
+    a.o_stride_b = p->o_stride_b; a.o_stride_n = p->o_stride_n; a.o_stride_h = p->o_stride_h;
+    a.Nq = p->Nq; a.Nk = p->Nk;
+    a.scale_log2 = p->scale * 1.4426950408889634f;
+    dim3 grid((p->Nq + BQ - 1) / BQ, p->H, p->B);
+    attn_kernel<D><<<grid, 192, C::SMEM, st>>>(mq, mk, mv, a);
+    count_launch(1);
+    return check_launch("attn_kernel");
+}
+
+}  // namespace
+}  // namespace gmd
+
+extern "C" int gmd_attn_fwd(const gmd_attn_params* p, void* stream) {
+    using namespace gmd;
+    if (!p || !p->q || !p->k || !p->v || !p->o) { set_last_error("gmd_attn_fwd: null pointer"); return kErrInvalid; }
+    if (p->B <= 0 || p->H <= 0 || p->Nq <= 0 || p->Nk <= 0) { set_last_error("gmd_attn_fwd: empty problem"); return kErrInvalid; }
+    const int64_t strides[] = {p->q_stride_b, p->q_stride_n, p->q_stride_h, p->k_stride_b, p->k_stride_n, p->k_stride_h,
+                               p->v_stride_b, p->v_stride_n, p->v_stride_h, p->o_stride_b, p->o_stride_n, p->o_stride_h};
+    for (int64_t s : strides)
+        if (s % 8) { set_last_error("gmd_attn_fwd: strides must be multiples of 8 elements (16 bytes)"); return kErrInvalid; }
+    const void* ptrs[] = {p->q, p->k, p->v, p->o};
+    for (const void* q : ptrs)
+        if (reinterpret_cast<uintptr_t>(q) & 15) { set_last_error("gmd_attn_fwd: pointers must be 16-byte aligned"); return kErrInvalid; }
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    switch (p->d) {
+        case 40: return launch<40>(p, st);
+        case 80: return launch<80>(p, st);
+        case 160: return launch<160>(p, st);
+        default: set_last_error("gmd_attn_fwd: head dim %d not instantiated (40, 80, 160)", p->d); return kErrUnsupported;
+    }
+}

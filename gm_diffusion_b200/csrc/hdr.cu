@@ -1,0 +1,343 @@
+// Kernel (d): SDR + gain map -> HDR (Eq. 1) -> tone-mapping operator -> BT.2020->709 gamut, with min/max
+// statistics, as ONE coalesced streaming pass (HBM-bound: 2 x 12 B read + 12 B written per pixel).
+// Arithmetic follows gm_diffusion/stage1/tone_mapping.py:14-90 of the reference op for op.
+#include "common.cuh"
+#include "../../include/gmd_b200.h"
+
+namespace gmd {
+void count_launch(int n);
+
+namespace {
+
+struct HdrConsts {
+    float qmax, eps, hi;          // hi = qmax + 1
+    float inv_hi;                 // 1 / (qmax + 1)
+    float mu, inv_log1p_mu;
+    float log2_hi;                // for the optional exponential gain
+    int flags, tmo;
+};
+
+// x^2.2 on [0,1] as x*x * 2^(0.2*log2 x): the MUFU approximations only see the 0.2 exponent, so their
+// absolute error (2^-22 on lg2) is damped 11x compared with a direct 2^(2.2*log2 x): <= ~4e-7 relative.
+__device__ __forceinline__ float pow22_unit(float x) {
+    float x2 = x * x;
+    float r = exp2f(0.2f * __log2f(x));   // x = 0 -> log2 = -inf -> exp2 = 0
+    return x2 * r;
+}
+
+__device__ __forceinline__ float denorm(float v, int flags) {
+    return (flags & GMD_HDR_DENORM) ? fminf(fmaxf(v * 0.5f + 0.5f, 0.0f), 1.0f) : v;
+}
+
+// Eq.(1), tone_mapping.py:69-71
+__device__ __forceinline__ float eq1(float sdr, float gm, const HdrConsts& c) {
+    float s = fminf(fmaxf(sdr, 0.0f), 1.0f);
+    float lin = pow22_unit(s);
+    float gain = (c.flags & GMD_HDR_EXP_GAIN) ? exp2f(gm * c.log2_hi) : (1.0f + gm * c.qmax);
+    float hdr = (lin + c.eps) * gain - c.eps;
+    if (c.flags & GMD_HDR_CLAMP_OUT) hdr = fminf(fmaxf(hdr, 0.0f), c.hi);
+    return hdr;
+}
+
+// tone_mapping.py:14-47
+__device__ __forceinline__ float tmo_apply(float x, const HdrConsts& c) {
+    switch (c.tmo) {
+        case GMD_TMO_LINEAR: return x * c.inv_hi;
+        case GMD_TMO_HARD_CLIP: return fminf(fmaxf(x, 0.0f), 1.0f);
+        case GMD_TMO_MULOG: {
+            float y = x * c.inv_hi;
+            float t = log1pf(c.mu * y) * c.inv_log1p_mu;
+            return fminf(fmaxf(t, 0.0f), 1.0f);
+        }
+        case GMD_TMO_CUDA: {
+            float y = fminf(fmaxf(x * 0.1f, 0.0f), 1.0f);
+            return log1pf(c.mu * y) * c.inv_log1p_mu;
+        }
+        default: return x;
+    }
+}
+
+// tone_mapping.py:78-90 (rows of M applied to the pixel's rgb column vector, then clamp)
+__device__ __forceinline__ void gamut709(float& r, float& g, float& b) {
+    float r2 = 1.660491f * r + -0.587641f * g + -0.072850f * b;
+    float g2 = -0.124550f * r + 1.132900f * g + -0.008349f * b;
+    float b2 = -0.018151f * r + -0.100579f * g + 1.118730f * b;
+    r = fminf(fmaxf(r2, 0.0f), 1.0f);
+    g = fminf(fmaxf(g2, 0.0f), 1.0f);
+    b = fminf(fmaxf(b2, 0.0f), 1.0f);
+}
+
+__device__ __forceinline__ int32_t ordered_from_float(float f) {
+    int32_t i = __float_as_int(f);
+    return i >= 0 ? i : i ^ 0x7fffffff;
+}
+
+struct MinMax {
+    float lo = INFINITY, hi = -INFINITY;
+    __device__ __forceinline__ void add(float v) {
+        lo = fminf(lo, v); hi = fmaxf(hi, v);
+        if (v != v) hi = INFINITY;  // NaN marker (tmo_cuda's range check, tone_mapping.py:43-45)
+    }
+};
+
+__device__ __forceinline__ void minmax_commit(MinMax mm, int32_t* out) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        mm.lo = fminf(mm.lo, __shfl_xor_sync(0xffffffffu, mm.lo, o));
+        mm.hi = fmaxf(mm.hi, __shfl_xor_sync(0xffffffffu, mm.hi, o));
+    }
+    __shared__ float s_lo[32], s_hi[32];
+    int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = (blockDim.x + 31) >> 5;
+    if (lane == 0) { s_lo[warp] = mm.lo; s_hi[warp] = mm.hi; }
+    __syncthreads();
+    if (warp == 0) {
+        float lo = lane < nw ? s_lo[lane] : __int_as_float(0x7f800000);
+        float hi = lane < nw ? s_hi[lane] : __int_as_float(0xff800000);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            lo = fminf(lo, __shfl_xor_sync(0xffffffffu, lo, o));
+            hi = fmaxf(hi, __shfl_xor_sync(0xffffffffu, hi, o));
+        }
+        if (lane == 0) {
+            atomicMin(out, ordered_from_float(lo));
+            atomicMax(out + 1, ordered_from_float(hi));
+        }
+    }
+}
+
+template <typename T> struct Vec4;
+template <> struct Vec4<float> {
+    static __device__ __forceinline__ void load(const float* p, int64_t i, float* v) {
+        float4 t = __ldcs(reinterpret_cast<const float4*>(p + i));
+        v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
+    }
+    static __device__ __forceinline__ float load1(const float* p, int64_t i) { return __ldcs(p + i); }
+};
+template <> struct Vec4<__nv_bfloat16> {
+    static __device__ __forceinline__ void load(const __nv_bfloat16* p, int64_t i, float* v) {
+        uint2 t = __ldcs(reinterpret_cast<const uint2*>(p + i));
+        v[0] = bf16_lo(t.x); v[1] = bf16_hi(t.x); v[2] = bf16_lo(t.y); v[3] = bf16_hi(t.y);
+    }
+    static __device__ __forceinline__ float load1(const __nv_bfloat16* p, int64_t i) {
+        return __bfloat162float(p[i]);
+    }
+};
+
+__device__ __forceinline__ void store4(float* p, int64_t i, const float* v) {
+    __stcs(reinterpret_cast<float4*>(p + i), make_float4(v[0], v[1], v[2], v[3]));
+}
+
+// One "item" = VEC consecutive pixels of one image; CH channel planes are processed together so the gamut
+// matrix sees r,g,b of the same pixel.  CH = 1 is the flat elementwise case.
+//   plane_stride: elements between channel planes (H*W) ; img_stride = CH * plane_stride
+//   INTERLEAVED (CH == 3 only): pixel-major [n_px, 3]; VEC pixels = 3*VEC consecutive floats.
+template <typename T, int CH, int VEC, bool INTERLEAVED>
+__global__ void __launch_bounds__(256) hdr_kernel(const T* __restrict__ sdr, const T* __restrict__ gm,
+                                                  float* __restrict__ hdr_out, float* __restrict__ tmo_out,
+                                                  int32_t* __restrict__ minmax, int64_t items_per_img, int64_t n_items,
+                                                  int64_t plane_stride, HdrConsts c) {
+    MinMax mm;
+    const bool do_eq1 = c.flags & GMD_HDR_EQ1;
+    const bool do_gamut = (c.flags & GMD_HDR_GAMUT) && CH == 3;
+    for (int64_t it = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; it < n_items;
+         it += (int64_t)gridDim.x * blockDim.x) {
+        float s[CH][VEC], g[CH][VEC], h[CH][VEC];
+        int64_t off[CH];
+        if (INTERLEAVED) {
+            // 3*VEC contiguous floats, VEC == 4 -> three 16-byte vectors
+            int64_t base = it * (3 * VEC);
+            float sv[3 * VEC], gv[3 * VEC];
+            if (VEC == 4) {
+#pragma unroll
+                for (int q = 0; q < 3; ++q) {
+                    float t4[4];
+                    Vec4<T>::load(sdr, base + 4 * q, t4);
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) sv[4 * q + k] = t4[k];
+                    if (do_eq1) {
+                        Vec4<T>::load(gm, base + 4 * q, t4);
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) gv[4 * q + k] = t4[k];
+                    }
+                }
+            } else {
+#pragma unroll
+                for (int k = 0; k < 3 * VEC; ++k) {
+                    sv[k] = Vec4<T>::load1(sdr, base + k);
+                    gv[k] = do_eq1 ? Vec4<T>::load1(gm, base + k) : 0.0f;
+                }
+            }
+#pragma unroll
+            for (int v = 0; v < VEC; ++v)
+#pragma unroll
+                for (int ch = 0; ch < CH; ++ch) { s[ch][v] = sv[3 * v + ch]; g[ch][v] = gv[3 * v + ch]; }
+            off[0] = base;
+        } else {
+            int64_t img = it / items_per_img;
+            int64_t px = (it - img * items_per_img) * VEC;
+#pragma unroll
+            for (int ch = 0; ch < CH; ++ch) off[ch] = (img * CH + ch) * plane_stride + px;
+#pragma unroll
+            for (int ch = 0; ch < CH; ++ch) {
+                if (VEC == 4) {
+                    Vec4<T>::load(sdr, off[ch], s[ch]);
+                    if (do_eq1) Vec4<T>::load(gm, off[ch], g[ch]);
+                } else {
+                    s[ch][0] = Vec4<T>::load1(sdr, off[ch]);
+                    if (do_eq1) g[ch][0] = Vec4<T>::load1(gm, off[ch]);
+                }
+            }
+        }
+        // Eq.(1)
+#pragma unroll
+        for (int ch = 0; ch < CH; ++ch)
+#pragma unroll
+            for (int v = 0; v < VEC; ++v) {
+                float x = s[ch][v];
+                if (do_eq1) x = eq1(denorm(x, c.flags), denorm(g[ch][v], c.flags), c);
+                h[ch][v] = x;
+                if (minmax) mm.add(x);
+            }
+        if (hdr_out) {
+            if (INTERLEAVED) {
+                float ov[3 * VEC];
+#pragma unroll
+                for (int v = 0; v < VEC; ++v)
+#pragma unroll
+                    for (int ch = 0; ch < CH; ++ch) ov[3 * v + ch] = h[ch][v];
+                if (VEC == 4) {
+#pragma unroll
+                    for (int q = 0; q < 3; ++q) {
+                        float t4[4] = {ov[4 * q], ov[4 * q + 1], ov[4 * q + 2], ov[4 * q + 3]};
+                        store4(hdr_out, off[0] + 4 * q, t4);
+                    }
+                } else {
+#pragma unroll
+                    for (int k = 0; k < 3 * VEC; ++k) hdr_out[off[0] + k] = ov[k];
+                }
+            } else {
+#pragma unroll
+                for (int ch = 0; ch < CH; ++ch) {
+                    if (VEC == 4) store4(hdr_out, off[ch], h[ch]);
+                    else hdr_out[off[ch]] = h[ch][0];
+                }
+            }
+        }
+        if (tmo_out) {
+#pragma unroll
+            for (int v = 0; v < VEC; ++v) {
+#pragma unroll
+                for (int ch = 0; ch < CH; ++ch) h[ch][v] = tmo_apply(h[ch][v], c);
+                if (do_gamut) gamut709(h[0][v], h[CH > 1 ? 1 : 0][v], h[CH > 2 ? 2 : 0][v]);
+            }
+            if (INTERLEAVED) {
+                float ov[3 * VEC];
+#pragma unroll
+                for (int v = 0; v < VEC; ++v)
+#pragma unroll
+                    for (int ch = 0; ch < CH; ++ch) ov[3 * v + ch] = h[ch][v];
+                if (VEC == 4) {
+#pragma unroll
+                    for (int q = 0; q < 3; ++q) {
+                        float t4[4] = {ov[4 * q], ov[4 * q + 1], ov[4 * q + 2], ov[4 * q + 3]};
+                        store4(tmo_out, off[0] + 4 * q, t4);
+                    }
+                } else {
+#pragma unroll
+                    for (int k = 0; k < 3 * VEC; ++k) tmo_out[off[0] + k] = ov[k];
+                }
+            } else {
+#pragma unroll
+                for (int ch = 0; ch < CH; ++ch) {
+                    if (VEC == 4) store4(tmo_out, off[ch], h[ch]);
+                    else tmo_out[off[ch]] = h[ch][0];
+                }
+            }
+        }
+    }
+    if (minmax) minmax_commit(mm, minmax);
+}
+
+__global__ void minmax_init_kernel(int32_t* mm) {
+    mm[0] = 0x7f800000;                      // +inf (ordered encoding of a non-negative float is itself)
+    mm[1] = (int32_t)0xff800000 ^ 0x7fffffff;  // -inf
+}
+
+template <typename T, int CH, int VEC, bool INTER>
+int launch(const gmd_hdr_params* p, const HdrConsts& c, int64_t items_per_img, int64_t n_items, int64_t plane_stride,
+           cudaStream_t st) {
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    int64_t want = (n_items + 255) / 256;
+    int64_t cap = (int64_t)sms * 8;   // 8 resident CTAs of 256 threads per SM; grid-stride over the rest
+    int grid = (int)(want < cap ? (want > 0 ? want : 1) : cap);
+    hdr_kernel<T, CH, VEC, INTER><<<grid, 256, 0, st>>>(static_cast<const T*>(p->sdr), static_cast<const T*>(p->gm),
+                                                         p->hdr_out, p->tmo_out, p->minmax, items_per_img, n_items,
+                                                         plane_stride, c);
+    count_launch(1);
+    return check_launch("hdr_kernel");
+}
+
+template <typename T>
+int dispatch(const gmd_hdr_params* p, const HdrConsts& c, cudaStream_t st) {
+    auto aligned16 = [](const void* q) { return q == nullptr || (reinterpret_cast<uintptr_t>(q) & 15) == 0; };
+    const size_t in_align = sizeof(T) == 4 ? 15 : 7;
+    bool ptr_ok = (reinterpret_cast<uintptr_t>(p->sdr) & in_align) == 0 &&
+                  (p->gm == nullptr || (reinterpret_cast<uintptr_t>(p->gm) & in_align) == 0) && aligned16(p->hdr_out) &&
+                  aligned16(p->tmo_out);
+    if (p->layout == GMD_LAYOUT_PLANAR3) {
+        if (ptr_ok && p->n_px % 4 == 0)
+            return launch<T, 3, 4, false>(p, c, p->n_px / 4, p->batch * (p->n_px / 4), p->n_px, st);
+        return launch<T, 3, 1, false>(p, c, p->n_px, p->batch * p->n_px, p->n_px, st);
+    }
+    if (p->layout == GMD_LAYOUT_INTERLEAVED3) {
+        if (ptr_ok && p->n_px % 4 == 0) return launch<T, 3, 4, true>(p, c, 0, p->n_px / 4, 0, st);
+        return launch<T, 3, 1, true>(p, c, 0, p->n_px, 0, st);
+    }
+    // flat
+    int64_t n = p->n_px;
+    if (ptr_ok && n % 4 == 0) return launch<T, 1, 4, false>(p, c, n / 4, n / 4, n, st);
+    return launch<T, 1, 1, false>(p, c, n, n, n, st);
+}
+
+}  // namespace
+}  // namespace gmd
+
+extern "C" int gmd_hdr_reconstruct(const gmd_hdr_params* p, void* stream) {
+    using namespace gmd;
+    if (!p || !p->sdr) { set_last_error("gmd_hdr_reconstruct: null input"); return kErrInvalid; }
+    if ((p->flags & GMD_HDR_EQ1) && !p->gm) { set_last_error("gmd_hdr_reconstruct: Eq.(1) needs a gain map"); return kErrInvalid; }
+    if (!p->hdr_out && !p->tmo_out && !p->minmax) { set_last_error("gmd_hdr_reconstruct: no output requested"); return kErrInvalid; }
+    if (p->n_px < 0 || p->batch < 0) { set_last_error("gmd_hdr_reconstruct: negative size"); return kErrInvalid; }
+    if ((p->flags & GMD_HDR_GAMUT) && p->layout == GMD_LAYOUT_FLAT) {
+        set_last_error("gmd_hdr_reconstruct: gamut compression needs a 3-channel layout"); return kErrInvalid;
+    }
+    if (p->tmo < GMD_TMO_NONE || p->tmo > GMD_TMO_CUDA) { set_last_error("gmd_hdr_reconstruct: unknown tmo %d", p->tmo); return kErrInvalid; }
+    int64_t total = p->layout == GMD_LAYOUT_PLANAR3 ? p->n_px * p->batch : p->n_px;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (p->minmax) {
+        minmax_init_kernel<<<1, 1, 0, st>>>(p->minmax);
+        count_launch(1);
+    }
+    if (total == 0) return check_launch("hdr_reconstruct(empty)");
+    HdrConsts c;
+    c.qmax = p->qmax; c.eps = p->eps; c.hi = p->qmax + 1.0f;
+    c.inv_hi = (float)(1.0 / ((double)p->qmax + 1.0));
+    c.flags = p->flags; c.tmo = p->tmo;
+    double mu = p->tmo == GMD_TMO_CUDA ? 5000.0 : (double)p->mu;
+    c.mu = (float)mu;
+    c.inv_log1p_mu = (float)(1.0 / log1p(mu));
+    c.log2_hi = (float)log2((double)p->qmax + 1.0);
+    if (p->in_dtype == GMD_F32) return dispatch<float>(p, c, st);
+    if (p->in_dtype == GMD_BF16) return dispatch<__nv_bfloat16>(p, c, st);
+    set_last_error("gmd_hdr_reconstruct: unknown in_dtype %d", p->in_dtype);
+    return kErrInvalid;
+}
+
+extern "C" float gmd_decode_ordered(int32_t v) {
+    int32_t i = v >= 0 ? v : v ^ 0x7fffffff;
+    float f;
+    memcpy(&f, &i, sizeof(f));
+    return f;
+}

@@ -1,0 +1,281 @@
+// Memory-bound companions of the tensor-core kernels: GroupNorm(+SiLU) over NHWC bf16 (two-source aware, so
+// the up-block skip concat is materialised only once, already normalised), LayerNorm over token rows,
+// row softmax, sinusoidal timestep embedding, SiLU.  All 16-byte vectorised; fp32 statistics.
+#include "common.cuh"
+#include "../../include/gmd_b200.h"
+
+namespace gmd {
+void count_launch(int n);
+namespace {
+
+__device__ __forceinline__ void unpack8(uint4 v, float (&f)[8]) {
+    f[0] = bf16_lo(v.x); f[1] = bf16_hi(v.x); f[2] = bf16_lo(v.y); f[3] = bf16_hi(v.y);
+    f[4] = bf16_lo(v.z); f[5] = bf16_hi(v.z); f[6] = bf16_lo(v.w); f[7] = bf16_hi(v.w);
+}
+__device__ __forceinline__ uint4 pack8(const float (&f)[8]) {
+    return make_uint4(pack_bf16x2(f[0], f[1]), pack_bf16x2(f[2], f[3]), pack_bf16x2(f[4], f[5]), pack_bf16x2(f[6], f[7]));
+}
+
+// ---------------------------------------------------------------------------------------------
+// GroupNorm.  Thread t owns channel vector cv = t % (C/8) (8 consecutive channels) and pixel lane t / (C/8).
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint4 gn_load(const __nv_bfloat16* x0, int C0, const __nv_bfloat16* x1, int C1, int64_t px, int c) {
+    if (c < C0) return __ldg(reinterpret_cast<const uint4*>(x0 + px * C0 + c));
+    return __ldg(reinterpret_cast<const uint4*>(x1 + px * C1 + (c - C0)));
+}
+
+__global__ void gn_stats_kernel(const __nv_bfloat16* __restrict__ x0, int C0, const __nv_bfloat16* __restrict__ x1, int C1,
+                                float* __restrict__ stats, int HW, int groups, int px_per_cta) {
+    extern __shared__ float s_acc[];  // [groups][2]
+    const int C = C0 + C1, nvec = C / 8, cg = C / groups;
+    const int n = blockIdx.y;
+    for (int i = threadIdx.x; i < groups * 2; i += blockDim.x) s_acc[i] = 0.0f;
+    __syncthreads();
+    const int cv = threadIdx.x % nvec, pl = threadIdx.x / nvec, P = blockDim.x / nvec;
+    if (pl < P) {
+        float s[8] = {0, 0, 0, 0, 0, 0, 0, 0}, q[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+        const int p0 = blockIdx.x * px_per_cta;
+        const int p1 = min(p0 + px_per_cta, HW);
+        for (int p = p0 + pl; p < p1; p += P) {
+            float f[8];
+            unpack8(gn_load(x0, C0, x1, C1, (int64_t)n * HW + p, cv * 8), f);
+#pragma unroll
+            for (int k = 0; k < 8; ++k) { s[k] += f[k]; q[k] += f[k] * f[k]; }
+        }
+        // fold the 8 channels into (at most a few) group slots
+        int g_prev = (cv * 8) / cg;
+        float ss = 0, qq = 0;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            int g = (cv * 8 + k) / cg;
+            if (g != g_prev) { atomicAdd(&s_acc[g_prev * 2], ss); atomicAdd(&s_acc[g_prev * 2 + 1], qq); ss = qq = 0; g_prev = g; }
+            ss += s[k]; qq += q[k];
+        }
+        atomicAdd(&s_acc[g_prev * 2], ss); atomicAdd(&s_acc[g_prev * 2 + 1], qq);
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < groups * 2; i += blockDim.x) atomicAdd(stats + (int64_t)n * groups * 2 + i, s_acc[i]);
+}
+
+__global__ void gn_apply_kernel(const __nv_bfloat16* __restrict__ x0, int C0, const __nv_bfloat16* __restrict__ x1, int C1,
+                                const float* __restrict__ stats, const float* __restrict__ gamma, const float* __restrict__ beta,
+                                __nv_bfloat16* __restrict__ out, int HW, int groups, float eps, int apply_silu, int px_per_cta) {
+    const int C = C0 + C1, nvec = C / 8, cg = C / groups;
+    const int n = blockIdx.y;
+    const int cv = threadIdx.x % nvec, pl = threadIdx.x / nvec, P = blockDim.x / nvec;
+    if (pl >= P) return;
+    float sc[8], sh[8];
+    const float inv_cnt = 1.0f / ((float)cg * (float)HW);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        int c = cv * 8 + k, g = c / cg;
+        float mean = stats[((int64_t)n * groups + g) * 2] * inv_cnt;
+        float var = fmaxf(stats[((int64_t)n * groups + g) * 2 + 1] * inv_cnt - mean * mean, 0.0f);
+        float rstd = rsqrtf(var + eps);
+        float ga = gamma[c], be = beta[c];
+        sc[k] = rstd * ga; sh[k] = be - mean * rstd * ga;
+    }
+    const int p0 = blockIdx.x * px_per_cta;
+    const int p1 = min(p0 + px_per_cta, HW);
+    for (int p = p0 + pl; p < p1; p += P) {
+        float f[8];
+        const int64_t px = (int64_t)n * HW + p;
+        unpack8(gn_load(x0, C0, x1, C1, px, cv * 8), f);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            float y = f[k] * sc[k] + sh[k];
+            f[k] = apply_silu ? silu_f(y) : y;
+        }
+        *reinterpret_cast<uint4*>(out + px * C + cv * 8) = pack8(f);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// LayerNorm: one warp per token row; the row lives in registers between the two passes.
+// ---------------------------------------------------------------------------------------------
+template <int MAXV>  // vectors (of 8) per lane
+__global__ void __launch_bounds__(256) layernorm_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ gamma,
+                                                        const float* __restrict__ beta, __nv_bfloat16* __restrict__ out,
+                                                        int64_t M, int C, float eps) {
+    const int64_t row = blockIdx.x * (int64_t)(blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (row >= M) return;
+    const int lane = threadIdx.x & 31, nvec = C / 8;
+    float v[MAXV][8];
+    float s = 0.0f;
+#pragma unroll
+    for (int i = 0; i < MAXV; ++i) {
+        int vi = lane + i * 32;
+        if (vi < nvec) {
+            unpack8(__ldg(reinterpret_cast<const uint4*>(x + row * C) + vi), v[i]);
+#pragma unroll
+            for (int k = 0; k < 8; ++k) s += v[i][k];
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(~0u, s, o);
+    const float mean = s / (float)C;
+    float q = 0.0f;
+#pragma unroll
+    for (int i = 0; i < MAXV; ++i) {
+        int vi = lane + i * 32;
+        if (vi < nvec) {
+#pragma unroll
+            for (int k = 0; k < 8; ++k) { float d = v[i][k] - mean; q += d * d; }
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) q += __shfl_xor_sync(~0u, q, o);
+    const float rstd = rsqrtf(q / (float)C + eps);
+#pragma unroll
+    for (int i = 0; i < MAXV; ++i) {
+        int vi = lane + i * 32;
+        if (vi < nvec) {
+            float4 g0 = __ldg(reinterpret_cast<const float4*>(gamma) + vi * 2), g1 = __ldg(reinterpret_cast<const float4*>(gamma) + vi * 2 + 1);
+            float4 b0 = __ldg(reinterpret_cast<const float4*>(beta) + vi * 2), b1 = __ldg(reinterpret_cast<const float4*>(beta) + vi * 2 + 1);
+            float ga[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+            float be[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+            float f[8];
+#pragma unroll
+            for (int k = 0; k < 8; ++k) f[k] = (v[i][k] - mean) * rstd * ga[k] + be[k];
+            reinterpret_cast<uint4*>(out + row * C)[vi] = pack8(f);
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Row softmax (bf16 in/out, fp32 math): one CTA per row, three passes (the row stays in L1/L2).
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) softmax_rows_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ out,
+                                                           int64_t N, float scale) {
+    __shared__ float red[32];
+    const __nv_bfloat16* xr = x + blockIdx.x * N;
+    __nv_bfloat16* orow = out + blockIdx.x * N;
+    const int nvec = (int)(N / 8);
+    float mx = -INFINITY;
+    for (int i = threadIdx.x; i < nvec; i += blockDim.x) {
+        float f[8]; unpack8(__ldg(reinterpret_cast<const uint4*>(xr) + i), f);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) mx = fmaxf(mx, f[k]);
+    }
+    auto block_reduce = [&](float v, bool is_max) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) { float t = __shfl_xor_sync(~0u, v, o); v = is_max ? fmaxf(v, t) : v + t; }
+        __syncthreads();
+        if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+        __syncthreads();
+        float r = red[0];
+        for (int i = 1; i < (blockDim.x >> 5); ++i) r = is_max ? fmaxf(r, red[i]) : r + red[i];
+        return r;
+    };
+    mx = block_reduce(mx, true);
+    const float sl2 = scale * 1.4426950408889634f;
+    float sum = 0.0f;
+    for (int i = threadIdx.x; i < nvec; i += blockDim.x) {
+        float f[8]; unpack8(__ldg(reinterpret_cast<const uint4*>(xr) + i), f);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) sum += exp2f((f[k] - mx) * sl2);
+    }
+    sum = block_reduce(sum, false);
+    const float inv = 1.0f / sum;
+    for (int i = threadIdx.x; i < nvec; i += blockDim.x) {
+        float f[8]; unpack8(__ldg(reinterpret_cast<const uint4*>(xr) + i), f);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) f[k] = exp2f((f[k] - mx) * sl2) * inv;
+        reinterpret_cast<uint4*>(orow)[i] = pack8(f);
+    }
+}
+
+// diffusers get_timestep_embedding(flip_sin_to_cos=True, downscale_freq_shift=0): [cos(t f_k) | sin(t f_k)], f_k = exp(-ln(1e4) k / half)
+__global__ void timestep_embedding_kernel(float t, __nv_bfloat16* __restrict__ out, int B, int dim) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= B * dim) return;
+    int c = i % dim, half = dim / 2;
+    int k = c < half ? c : c - half;
+    float freq = expf(-9.210340371976184f * (float)k / (float)half);
+    float a = t * freq;
+    out[i] = __float2bfloat16(c < half ? cosf(a) : sinf(a));
+}
+
+__global__ void silu_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ out, int64_t n) {
+    int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i < n) out[i] = __float2bfloat16(silu_f(__bfloat162float(x[i])));
+}
+
+inline bool al16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+
+}  // namespace
+}  // namespace gmd
+
+extern "C" int gmd_groupnorm_silu(const void* x0, int32_t C0, const void* x1, int32_t C1, const float* gamma, const float* beta,
+                                  void* out, int32_t N, int32_t HW, int32_t groups, float eps, int32_t apply_silu, float* stats_ws,
+                                  void* stream) {
+    using namespace gmd;
+    if (!x0 || !gamma || !beta || !out || !stats_ws) { set_last_error("gmd_groupnorm_silu: null pointer"); return kErrInvalid; }
+    if (!x1) C1 = 0;
+    const int C = C0 + C1;
+    if (C0 % 8 || C1 % 8 || groups <= 0 || C % groups || N <= 0 || HW <= 0) { set_last_error("gmd_groupnorm_silu: bad shape C0=%d C1=%d groups=%d", C0, C1, groups); return kErrInvalid; }
+    if (!al16(x0) || !al16(x1) || !al16(out)) { set_last_error("gmd_groupnorm_silu: pointers must be 16-byte aligned"); return kErrInvalid; }
+    const int nvec = C / 8;
+    if (nvec > 1024) { set_last_error("gmd_groupnorm_silu: C=%d too large", C); return kErrUnsupported; }
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    int P = 256 / nvec; if (P < 1) P = 1;
+    int threads = nvec * P;
+    threads = (threads + 31) / 32 * 32;
+    // ~4 waves of CTAs over 148 SMs
+    int target_ctas = 148 * 4;
+    int chunks = (target_ctas + N - 1) / N;
+    int px_per_cta = (HW + chunks - 1) / chunks;
+    if (px_per_cta < P * 4) px_per_cta = P * 4;
+    chunks = (HW + px_per_cta - 1) / px_per_cta;
+    dim3 grid(chunks, N);
+    cudaMemsetAsync(stats_ws, 0, sizeof(float) * 2 * groups * N, st);
+    gn_stats_kernel<<<grid, threads, groups * 2 * sizeof(float), st>>>(static_cast<const __nv_bfloat16*>(x0), C0, static_cast<const __nv_bfloat16*>(x1), C1, stats_ws, HW, groups, px_per_cta);
+    gn_apply_kernel<<<grid, threads, 0, st>>>(static_cast<const __nv_bfloat16*>(x0), C0, static_cast<const __nv_bfloat16*>(x1), C1, stats_ws, gamma, beta,
+                                              static_cast<__nv_bfloat16*>(out), HW, groups, eps, apply_silu, px_per_cta);
+    count_launch(2);
+    return check_launch("groupnorm");
+}
+
+extern "C" int gmd_layernorm(const void* x, const float* gamma, const float* beta, void* out, int64_t M, int32_t C, float eps, void* stream) {
+    using namespace gmd;
+    if (!x || !gamma || !beta || !out) { set_last_error("gmd_layernorm: null pointer"); return kErrInvalid; }
+    if (C % 8 || C <= 0 || C > 8 * 32 * 8) { set_last_error("gmd_layernorm: C=%d unsupported (multiple of 8, <= 2048)", C); return kErrInvalid; }
+    if (!al16(x) || !al16(out) || !al16(gamma) || !al16(beta)) { set_last_error("gmd_layernorm: pointers must be 16-byte aligned"); return kErrInvalid; }
+    if (M == 0) return kOk;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    unsigned grid = (unsigned)((M + 7) / 8);
+    const int nvec = C / 8;
+    auto* xp = static_cast<const __nv_bfloat16*>(x);
+    auto* op = static_cast<__nv_bfloat16*>(out);
+    if (nvec <= 64) layernorm_kernel<2><<<grid, 256, 0, st>>>(xp, gamma, beta, op, M, C, eps);
+    else if (nvec <= 160) layernorm_kernel<5><<<grid, 256, 0, st>>>(xp, gamma, beta, op, M, C, eps);
+    else layernorm_kernel<8><<<grid, 256, 0, st>>>(xp, gamma, beta, op, M, C, eps);
+    count_launch(1);
+    return check_launch("layernorm");
+}
+
+extern "C" int gmd_softmax_rows(const void* x, void* out, int64_t M, int64_t N, float scale, void* stream) {
+    using namespace gmd;
+    if (!x || !out || N % 8 || !al16(x) || !al16(out)) { set_last_error("gmd_softmax_rows: bad arguments"); return kErrInvalid; }
+    if (M == 0 || N == 0) return kOk;
+    softmax_rows_kernel<<<(unsigned)M, 256, 0, static_cast<cudaStream_t>(stream)>>>(static_cast<const __nv_bfloat16*>(x), static_cast<__nv_bfloat16*>(out), N, scale);
+    count_launch(1);
+    return check_launch("softmax_rows");
+}
+
+extern "C" int gmd_timestep_embedding(float t, void* out, int32_t B, int32_t dim, void* stream) {
+    using namespace gmd;
+    if (!out || B <= 0 || dim <= 0 || dim % 2) { set_last_error("gmd_timestep_embedding: bad arguments"); return kErrInvalid; }
+    timestep_embedding_kernel<<<(B * dim + 255) / 256, 256, 0, static_cast<cudaStream_t>(stream)>>>(t, static_cast<__nv_bfloat16*>(out), B, dim);
+    count_launch(1);
+    return check_launch("timestep_embedding");
+}
+
+extern "C" int gmd_silu(const void* x, void* out, int64_t n, void* stream) {
+    using namespace gmd;
+    if (!x || !out) { set_last_error("gmd_silu: null pointer"); return kErrInvalid; }
+    if (n == 0) return kOk;
+    silu_kernel<<<(unsigned)((n + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(static_cast<const __nv_bfloat16*>(x), static_cast<__nv_bfloat16*>(out), n);
+    count_launch(1);
+    return check_launch("silu");
+}

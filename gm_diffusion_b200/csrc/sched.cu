@@ -1,0 +1,203 @@
+// Kernel (c): classifier-free-guidance combine + x0 prediction + PLMS / DDIM update + SDR/GM latent concat,
+// one launch per branch per step.  One thread owns one latent pixel (4 channels = one float4) so every
+// access is a 16-byte vector; outputs for the next UNet calls are written directly in the channel-padded
+// bf16 pixel-major layout the convolution kernels read.
+// Follows stable_diffusion_dual_unet.py:1045-1048,1063-1080,1093 and diffusers PNDMScheduler.step_plms /
+// DDIMScheduler.step.
+#include "common.cuh"
+#include "../../include/gmd_b200.h"
+
+namespace gmd {
+void count_launch(int n);
+namespace {
+
+__device__ __forceinline__ float4 ld4(const float* p, int64_t i) { return __ldg(reinterpret_cast<const float4*>(p) + i); }
+__device__ __forceinline__ void st4(float* p, int64_t i, float4 v) { reinterpret_cast<float4*>(p)[i] = v; }
+__device__ __forceinline__ float4 f4_axpby(float a, float4 x, float b, float4 y) {
+    return make_float4(a * x.x + b * y.x, a * x.y + b * y.y, a * x.z + b * y.z, a * x.w + b * y.w);
+}
+
+// write one pixel row of `ch` bf16 channels: ch0-3 = a, ch4-7 = b, rest zero
+__device__ __forceinline__ void store_row(void* dst, int64_t px, int ch, float4 a, float4 b) {
+    uint4* row = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(dst) + px * ch);
+    row[0] = make_uint4(pack_bf16x2(a.x, a.y), pack_bf16x2(a.z, a.w), pack_bf16x2(b.x, b.y), pack_bf16x2(b.z, b.w));
+    for (int k = 1; k < ch / 8; ++k) row[k] = make_uint4(0, 0, 0, 0);
+}
+
+// per-sample sums for guidance rescale (stable_diffusion_dual_unet.py:71-94): [B][4] = {S(c), S(c^2), S(g), S(g^2)}
+__global__ void __launch_bounds__(256) rescale_stats_kernel(const float* __restrict__ eu, const float* __restrict__ ec,
+                                                           float* __restrict__ stats, int64_t px_per_sample, float g) {
+    int64_t b = blockIdx.y;
+    float s0 = 0, s1 = 0, s2 = 0, s3 = 0;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < px_per_sample; i += (int64_t)gridDim.x * blockDim.x) {
+        float4 c = ld4(ec, b * px_per_sample + i), u = ld4(eu, b * px_per_sample + i);
+        float cv[4] = {c.x, c.y, c.z, c.w}, uv[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            float e = uv[k] + g * (cv[k] - uv[k]);
+            s0 += cv[k]; s1 += cv[k] * cv[k]; s2 += e; s3 += e * e;
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        s0 += __shfl_xor_sync(~0u, s0, o); s1 += __shfl_xor_sync(~0u, s1, o);
+        s2 += __shfl_xor_sync(~0u, s2, o); s3 += __shfl_xor_sync(~0u, s3, o);
+    }
+    if ((threadIdx.x & 31) == 0) {
+        atomicAdd(stats + b * 4 + 0, s0); atomicAdd(stats + b * 4 + 1, s1);
+        atomicAdd(stats + b * 4 + 2, s2); atomicAdd(stats + b * 4 + 3, s3);
+    }
+}
+
+__global__ void __launch_bounds__(256) sched_kernel(gmd_sched_params p) {
+    int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i >= p.n_px) return;
+    // --- CFG combine (dual_unet.py:1063-1065) ---
+    float4 e = ld4(p.eps_cond, i);
+    if (p.eps_uncond) {
+        float4 u = ld4(p.eps_uncond, i);
+        float g = p.guidance_scale;
+        float4 ec = e;
+        e = make_float4(u.x + g * (ec.x - u.x), u.y + g * (ec.y - u.y), u.z + g * (ec.z - u.z), u.w + g * (ec.w - u.w));
+        if (p.guidance_rescale > 0.0f && p.rescale_stats) {
+            // rescale_noise_cfg (dual_unet.py:71-94): unbiased std over the sample
+            const float* s = p.rescale_stats + (i / p.px_per_sample) * 4;
+            float n = (float)(p.px_per_sample * 4);
+            float var_c = (s[1] - s[0] * s[0] / n) / (n - 1.0f);
+            float var_g = (s[3] - s[2] * s[2] / n) / (n - 1.0f);
+            float ratio = sqrtf(var_c) / sqrtf(var_g);
+            float phi = p.guidance_rescale;
+            float f = phi * ratio + (1.0f - phi);
+            e = make_float4(e.x * f, e.y * f, e.z * f, e.w * f);
+        }
+    }
+    float4 x = ld4(p.x, i);
+    // --- x0 prediction from the PRE-step latents and the loop's t (dual_unet.py:1072-1075) ---
+    float4 x0;
+    {
+        float a = p.sqrt_1m_alpha_t, inv = p.sqrt_alpha_t;
+        x0 = make_float4((x.x - a * e.x) / inv, (x.y - a * e.y) / inv, (x.z - a * e.z) / inv, (x.w - a * e.w) / inv);
+    }
+    if (p.x0_out) st4(p.x0_out, i, x0);
+    if (p.stash_out) st4(p.stash_out, i, x);
+    if (p.eps_out) st4(p.eps_out, i, e);
+    // --- scheduler update ---
+    float4 xn;
+    if (p.mode == GMD_SCHED_LINEAR) {
+        // eps' = sum_k w_k e_k   (PLMS Adams-Bashforth / averaging), then x' = c_sample * x_src - c_eps * eps'
+        float4 ep = make_float4(p.w[0] * e.x, p.w[0] * e.y, p.w[0] * e.z, p.w[0] * e.w);
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            if (p.hist[k]) {
+                float4 h = ld4(p.hist[k], i);
+                float w = p.w[k + 1];
+                ep.x += w * h.x; ep.y += w * h.y; ep.z += w * h.z; ep.w += w * h.w;
+            }
+        }
+        float4 xs = p.use_stash ? ld4(p.x_stash, i) : x;
+        xn = f4_axpby(p.c_sample, xs, -p.c_eps, ep);
+    } else {
+        // DDIM: x0 = (x - sqrt(1-a_t) e)/sqrt(a_t); dir = sqrt(1-a_prev-sigma^2) e; x' = sqrt(a_prev) x0 + dir (+ sigma z)
+        float a = p.ddim_sqrt_1m_alpha_t, inv = p.ddim_sqrt_alpha_t;
+        float4 p0 = make_float4((x.x - a * e.x) / inv, (x.y - a * e.y) / inv, (x.z - a * e.z) / inv, (x.w - a * e.w) / inv);
+        float4 dir = make_float4(p.ddim_dir_coeff * e.x, p.ddim_dir_coeff * e.y, p.ddim_dir_coeff * e.z, p.ddim_dir_coeff * e.w);
+        xn = make_float4(p.ddim_sqrt_alpha_prev * p0.x + dir.x, p.ddim_sqrt_alpha_prev * p0.y + dir.y,
+                         p.ddim_sqrt_alpha_prev * p0.z + dir.z, p.ddim_sqrt_alpha_prev * p0.w + dir.w);
+        if (p.noise && p.ddim_sigma != 0.0f) {
+            float4 z = ld4(p.noise, i);
+            xn.x += p.ddim_sigma * z.x; xn.y += p.ddim_sigma * z.y; xn.z += p.ddim_sigma * z.z; xn.w += p.ddim_sigma * z.w;
+        }
+    }
+    st4(p.x_next, i, xn);
+    // --- fused layout outputs (replace torch.cat at dual_unet.py:1045,1080 / gm.py:1045) ---
+    float4 zero = make_float4(0, 0, 0, 0);
+    if (p.unet_in_next) store_row(p.unet_in_next, i, p.unet_in_ch, xn, zero);
+    if (p.concat_out) {
+        float4 lead = p.concat_lead ? ld4(p.concat_lead, i) : x0;
+        float4 tail = p.concat_tail ? ld4(p.concat_tail, i) : zero;
+        store_row(p.concat_out, i, p.unet_in_ch, lead, tail);
+    }
+}
+
+__global__ void __launch_bounds__(256) nchw_to_px_kernel(const float* __restrict__ src, float* __restrict__ dst, int64_t batch, int64_t hw) {
+    int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i >= batch * hw) return;
+    int64_t b = i / hw, p = i - b * hw;
+    const float* s = src + b * 4 * hw + p;
+    st4(dst, i, make_float4(s[0], s[hw], s[2 * hw], s[3 * hw]));
+}
+__global__ void __launch_bounds__(256) px_to_nchw_kernel(const float* __restrict__ src, float* __restrict__ dst, int64_t batch, int64_t hw) {
+    int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i >= batch * hw) return;
+    int64_t b = i / hw, p = i - b * hw;
+    float4 v = ld4(src, i);
+    float* d = dst + b * 4 * hw + p;
+    d[0] = v.x; d[hw] = v.y; d[2 * hw] = v.z; d[3 * hw] = v.w;
+}
+__global__ void __launch_bounds__(256) pack_unet_input_kernel(const float* __restrict__ lead, const float* __restrict__ tail, void* dst, int64_t n_px, int ch) {
+    int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i >= n_px) return;
+    float4 zero = make_float4(0, 0, 0, 0);
+    store_row(dst, i, ch, ld4(lead, i), tail ? ld4(tail, i) : zero);
+}
+
+inline bool al16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+
+}  // namespace
+}  // namespace gmd
+
+extern "C" int gmd_cfg_sched_step(const gmd_sched_params* p, void* stream) {
+    using namespace gmd;
+    if (!p || !p->eps_cond || !p->x || !p->x_next) { set_last_error("gmd_cfg_sched_step: null eps/x"); return kErrInvalid; }
+    if (p->n_px < 0) { set_last_error("gmd_cfg_sched_step: negative n_px"); return kErrInvalid; }
+    if (p->use_stash && !p->x_stash) { set_last_error("gmd_cfg_sched_step: use_stash without x_stash"); return kErrInvalid; }
+    if ((p->unet_in_next || p->concat_out) && (p->unet_in_ch < 8 || p->unet_in_ch % 8)) {
+        set_last_error("gmd_cfg_sched_step: unet_in_ch must be a multiple of 8 (got %d)", p->unet_in_ch); return kErrInvalid;
+    }
+    if (p->mode != GMD_SCHED_LINEAR && p->mode != GMD_SCHED_DDIM) { set_last_error("gmd_cfg_sched_step: bad mode %d", p->mode); return kErrInvalid; }
+    const void* ptrs[] = {p->eps_uncond, p->eps_cond, p->x, p->x_stash, p->hist[0], p->hist[1], p->hist[2], p->noise, p->x_next,
+                          p->stash_out, p->eps_out, p->unet_in_next, p->concat_out, p->concat_tail, p->concat_lead, p->x0_out};
+    for (const void* q : ptrs)
+        if (!al16(q)) { set_last_error("gmd_cfg_sched_step: pointers must be 16-byte aligned"); return kErrInvalid; }
+    if (p->n_px == 0) return kOk;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (p->eps_uncond && p->guidance_rescale > 0.0f) {
+        if (!p->rescale_stats || p->px_per_sample <= 0 || p->n_px % p->px_per_sample) {
+            set_last_error("gmd_cfg_sched_step: guidance_rescale needs rescale_stats and px_per_sample"); return kErrInvalid;
+        }
+        int64_t B = p->n_px / p->px_per_sample;
+        cudaMemsetAsync(p->rescale_stats, 0, sizeof(float) * 4 * B, st);
+        dim3 grid((unsigned)((p->px_per_sample + 255) / 256 < 64 ? (p->px_per_sample + 255) / 256 : 64), (unsigned)B);
+        rescale_stats_kernel<<<grid, 256, 0, st>>>(p->eps_uncond, p->eps_cond, p->rescale_stats, p->px_per_sample, p->guidance_scale);
+        count_launch(1);
+    }
+    unsigned grid = (unsigned)((p->n_px + 255) / 256);
+    sched_kernel<<<grid, 256, 0, st>>>(*p);
+    count_launch(1);
+    return check_launch("sched_kernel");
+}
+
+extern "C" int gmd_latents_nchw_to_px(const float* src, float* dst, int64_t batch, int64_t hw, void* stream) {
+    using namespace gmd;
+    if (batch * hw == 0) return kOk;
+    if (!src || !dst || !al16(dst)) { set_last_error("gmd_latents_nchw_to_px: bad pointers"); return kErrInvalid; }
+    nchw_to_px_kernel<<<(unsigned)((batch * hw + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(src, dst, batch, hw);
+    count_launch(1);
+    return check_launch("nchw_to_px");
+}
+extern "C" int gmd_latents_px_to_nchw(const float* src, float* dst, int64_t batch, int64_t hw, void* stream) {
+    using namespace gmd;
+    if (batch * hw == 0) return kOk;
+    if (!src || !dst || !al16(src)) { set_last_error("gmd_latents_px_to_nchw: bad pointers"); return kErrInvalid; }
+    px_to_nchw_kernel<<<(unsigned)((batch * hw + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(src, dst, batch, hw);
+    count_launch(1);
+    return check_launch("px_to_nchw");
+}
+extern "C" int gmd_pack_unet_input(const float* lead, const float* tail, void* dst, int64_t n_px, int32_t ch, void* stream) {
+    using namespace gmd;
+    if (n_px == 0) return kOk;
+    if (!lead || !dst || ch < 8 || ch % 8 || !al16(lead) || !al16(tail) || !al16(dst)) { set_last_error("gmd_pack_unet_input: bad arguments"); return kErrInvalid; }
+    pack_unet_input_kernel<<<(unsigned)((n_px + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(lead, tail, dst, n_px, ch);
+    count_launch(1);
+    return check_launch("pack_unet_input");
+}

@@ -1,0 +1,202 @@
+"""Thin tensor-level wrappers over the C-ABI (one C call each; no math happens in Python).
+
+Layouts: activations bf16 NHWC `[N,H,W,C]` or token-major `[M,C]`; conv weights `[Cout, kh*kw*Cin]` with
+k = (r*kw + s)*Cin + c; linear weights `[N,K]` (torch Linear layout); biases / norm affine fp32.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional
+
+import torch
+
+from . import _lib as L
+
+bf16 = torch.bfloat16
+
+
+def gemm(a: torch.Tensor, w: torch.Tensor, *, bias: Optional[torch.Tensor] = None, residual: Optional[torch.Tensor] = None,
+         row_bias: Optional[torch.Tensor] = None, rows_per_sample: int = 0, geglu: bool = False, out: Optional[torch.Tensor] = None,
+         out_f32: bool = False, alpha: Optional[float] = None) -> torch.Tensor:
+    """out[M,N] = a[M,K] @ w[N,K]^T (+bias +row_bias[sample] +residual | GEGLU).  3-D inputs are batched."""
+    L.require_cuda(a, w)
+    assert a.dtype == bf16 and w.dtype == bf16, "gemm operands must be bf16"
+    batched = a.dim() == 3
+    if batched:
+        Bt, M, K = a.shape
+        N = w.shape[1]
+        assert w.shape[0] == Bt and w.shape[2] == K
+    else:
+        M, K = a.shape
+        N = w.shape[0]
+        assert w.shape[1] == K
+        Bt = 1
+    assert a.stride(-1) == 1 and w.stride(-1) == 1
+    n_out = N // 2 if geglu else N
+    if out is None:
+        shape = (Bt, M, n_out) if batched else (M, n_out)
+        out = torch.empty(shape, dtype=torch.float32 if out_f32 else bf16, device=a.device)
+    p = L.GemmParams()
+    p.a, p.lda = a.data_ptr(), a.stride(-2)
+    p.w, p.ldw = w.data_ptr(), w.stride(-2)
+    p.out, p.ldo = out.data_ptr(), out.stride(-2)
+    p.M, p.N, p.K, p.batch = M, N, K, Bt
+    if batched:
+        p.stride_a, p.stride_w, p.stride_o = a.stride(0), w.stride(0), out.stride(0)
+    flags = 0
+    if bias is not None:
+        assert bias.dtype == torch.float32 and bias.numel() == N
+        flags |= L.EPI_BIAS
+        p.bias = bias.data_ptr()
+    if row_bias is not None:
+        assert row_bias.dtype == torch.float32 and rows_per_sample > 0
+        flags |= L.EPI_ROW_BIAS
+        p.row_bias, p.ld_row_bias, p.rows_per_sample = row_bias.data_ptr(), row_bias.stride(0), rows_per_sample
+    if residual is not None:
+        assert residual.dtype == bf16 and residual.stride(-1) == 1
+        flags |= L.EPI_RESIDUAL
+        p.residual, p.ldr = residual.data_ptr(), residual.stride(-2)
+    if geglu:
+        flags |= L.EPI_GEGLU
+    if out_f32 or out.dtype == torch.float32:
+        flags |= L.EPI_OUT_F32
+    if alpha is not None:
+        flags |= L.EPI_SCALE
+        p.alpha = float(alpha)
+    p.flags = flags
+    L.check(L.lib().gmd_gemm_fwd(C.byref(p), L.current_stream()), "gmd_gemm_fwd")
+    return out
+
+
+def conv2d(x: torch.Tensor, w: torch.Tensor, cout: int, *, ksize: int = 3, stride: int = 1, upsample: bool = False,
+           x1: Optional[torch.Tensor] = None, bias: Optional[torch.Tensor] = None, row_bias: Optional[torch.Tensor] = None,
+           residual: Optional[torch.Tensor] = None, out: Optional[torch.Tensor] = None, out_f32: bool = False) -> torch.Tensor:
+    """NHWC bf16 convolution as implicit GEMM (3x3 pad 1 stride 1/2, optional folded nearest-2x upsample)."""
+    L.require_cuda(x, w)
+    assert x.dtype == bf16 and w.dtype == bf16 and x.is_contiguous() and w.is_contiguous()
+    N, H, W, C0 = x.shape
+    C1 = 0
+    if x1 is not None:
+        assert x1.dtype == bf16 and x1.is_contiguous() and x1.shape[:3] == x.shape[:3]
+        C1 = x1.shape[3]
+    assert w.shape[1] == ksize * ksize * (C0 + C1), (w.shape, ksize, C0, C1)
+    Ho, Wo = (H // 2, W // 2) if stride == 2 else ((2 * H, 2 * W) if upsample else (H, W))
+    if out is None:
+        out = torch.empty((N, Ho, Wo, cout), dtype=torch.float32 if out_f32 else bf16, device=x.device)
+    p = L.ConvParams()
+    p.x0, p.C0 = x.data_ptr(), C0
+    p.x1, p.C1 = (x1.data_ptr(), C1) if x1 is not None else (None, 0)
+    p.w, p.out = w.data_ptr(), out.data_ptr()
+    p.N, p.H, p.W, p.Cout, p.Cout_pad = N, H, W, cout, w.shape[0]
+    p.ksize, p.stride, p.upsample = ksize, stride, int(upsample)
+    flags = 0
+    if bias is not None:
+        assert bias.dtype == torch.float32
+        flags |= L.EPI_BIAS
+        p.bias = bias.data_ptr()
+    if row_bias is not None:
+        assert row_bias.dtype == torch.float32
+        flags |= L.EPI_ROW_BIAS
+        p.row_bias, p.ld_row_bias = row_bias.data_ptr(), row_bias.stride(0)
+    if residual is not None:
+        assert residual.dtype == bf16 and residual.is_contiguous()
+        flags |= L.EPI_RESIDUAL
+        p.residual = residual.data_ptr()
+    if out.dtype == torch.float32:
+        flags |= L.EPI_OUT_F32
+    p.flags = flags
+    L.check(L.lib().gmd_conv_fwd(C.byref(p), L.current_stream()), "gmd_conv_fwd")
+    return out
+
+
+def groupnorm_silu(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, *, x1: Optional[torch.Tensor] = None, groups: int = 32,
+                   eps: float = 1e-5, silu: bool = True, out: Optional[torch.Tensor] = None, stats_ws: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """GroupNorm(+SiLU) over NHWC bf16; with `x1` the channels are [x | x1] and the output is the concatenation."""
+    L.require_cuda(x)
+    N, C0 = x.shape[0], x.shape[-1]
+    HW = x.numel() // (N * C0)
+    C1 = x1.shape[-1] if x1 is not None else 0
+    if out is None:
+        out = torch.empty(x.shape[:-1] + (C0 + C1,), dtype=bf16, device=x.device)
+    if stats_ws is None:
+        stats_ws = torch.empty(N * groups * 2, dtype=torch.float32, device=x.device)
+    L.check(L.lib().gmd_groupnorm_silu(x.data_ptr(), C0, L.ptr(x1), C1, gamma.data_ptr(), beta.data_ptr(), out.data_ptr(), N, HW,
+                                       groups, float(eps), int(silu), stats_ws.data_ptr(), L.current_stream()), "gmd_groupnorm_silu")
+    return out
+
+
+def layernorm(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, eps: float = 1e-5, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    L.require_cuda(x)
+    Cc = x.shape[-1]
+    M = x.numel() // Cc
+    if out is None:
+        out = torch.empty_like(x)
+    L.check(L.lib().gmd_layernorm(x.data_ptr(), gamma.data_ptr(), beta.data_ptr(), out.data_ptr(), M, Cc, float(eps), L.current_stream()),
+            "gmd_layernorm")
+    return out
+
+
+def softmax_rows(x: torch.Tensor, scale: float, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    L.require_cuda(x)
+    N = x.shape[-1]
+    if out is None:
+        out = torch.empty_like(x)
+    L.check(L.lib().gmd_softmax_rows(x.data_ptr(), out.data_ptr(), x.numel() // N, N, float(scale), L.current_stream()), "gmd_softmax_rows")
+    return out
+
+
+def timestep_embedding(t: float, batch: int, dim: int, device, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    if out is None:
+        out = torch.empty((batch, dim), dtype=bf16, device=device)
+    L.check(L.lib().gmd_timestep_embedding(float(t), out.data_ptr(), batch, dim, L.current_stream()), "gmd_timestep_embedding")
+    return out
+
+
+def silu(x: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    L.require_cuda(x)
+    if out is None:
+        out = torch.empty_like(x)
+    L.check(L.lib().gmd_silu(x.data_ptr(), out.data_ptr(), x.numel(), L.current_stream()), "gmd_silu")
+    return out
+
+
+def attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, heads: int, scale: Optional[float] = None,
+              out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """q: [B,Nq,H*d] view, k/v: [B,Nk,H*d] views (last dim contiguous, arbitrary row strides) -> [B,Nq,H*d]."""
+    L.require_cuda(q, k, v)
+    B, Nq, Cc = q.shape
+    Nk = k.shape[1]
+    d = Cc // heads
+    assert q.dtype == bf16 and k.dtype == bf16 and v.dtype == bf16
+    assert q.stride(2) == 1 and k.stride(2) == 1 and v.stride(2) == 1
+    if out is None:
+        out = torch.empty((B, Nq, Cc), dtype=bf16, device=q.device)
+    p = L.AttnParams()
+    p.q, p.q_stride_b, p.q_stride_n, p.q_stride_h = q.data_ptr(), q.stride(0), q.stride(1), d
+    p.k, p.k_stride_b, p.k_stride_n, p.k_stride_h = k.data_ptr(), k.stride(0), k.stride(1), d
+    p.v, p.v_stride_b, p.v_stride_n, p.v_stride_h = v.data_ptr(), v.stride(0), v.stride(1), d
+    p.o, p.o_stride_b, p.o_stride_n, p.o_stride_h = out.data_ptr(), out.stride(0), out.stride(1), d
+    p.B, p.H, p.Nq, p.Nk, p.d = B, heads, Nq, Nk, d
+    p.scale = float(scale if scale is not None else d ** -0.5)
+    L.check(L.lib().gmd_attn_fwd(C.byref(p), L.current_stream()), "gmd_attn_fwd")
+    return out
+
+
+# ---- weight repacking helpers (run once at load) ------------------------------------------------------------
+def pack_conv_weight(w_oihw: torch.Tensor, cin_pad: Optional[int] = None) -> torch.Tensor:
+    """OIHW -> [Cout, kh*kw*Cin(_pad)] bf16, k = (r*kw + s)*Cin + c."""
+    co, ci, kh, kw = w_oihw.shape
+    w = w_oihw.permute(0, 2, 3, 1)
+    if cin_pad is not None and cin_pad > ci:
+        w = torch.nn.functional.pad(w, (0, cin_pad - ci))
+    return w.reshape(co, -1).to(bf16).contiguous()
+
+
+def pack_geglu_weight(w: torch.Tensor, b: torch.Tensor, tile: int = 160):
+    """diffusers GEGLU proj [2*inner, K] (rows: value | gate) -> rows interleaved per N tile: [value half-tile | gate half-tile]."""
+    inner = w.shape[0] // 2
+    half = tile // 2
+    assert inner % half == 0, (inner, tile)
+    wv, wg = w[:inner].reshape(inner // half, half, -1), w[inner:].reshape(inner // half, half, -1)
+    wi = torch.cat([wv, wg], dim=1).reshape(2 * inner, -1)
+    return wi.to(bf16).contiguous(), b.float().contiguous()  # bias stays [value | gate]; the kernel indexes both halves

@@ -1,0 +1,238 @@
+"""Host side of kernel (c): scheduler objects with the attribute surface the reference pipelines touch
+(`set_timesteps`, `timesteps`, `order`, `init_noise_sigma`, `scale_model_input`, `alphas_cumprod`, `config`;
+stable_diffusion_dual_unet.py:151-152,717,1033,1047,1072,1077) whose `step` is not a chain of ~15 torch
+launches but a *plan*: a handful of fp32 coefficients computed on the host for the fused CUDA kernel
+`gmd_cfg_sched_step`.  Device state (latents, PLMS history ring, stash) lives in `BranchState`.
+
+Coefficient arithmetic mirrors diffusers PNDMScheduler._get_prev_sample / DDIMScheduler.step op for op in
+fp32 (torch CPU scalars) so the fused kernel lands within ~1e-6 of the unfused chain.
+"""
+from __future__ import annotations
+
+import copy
+import ctypes as C
+from dataclasses import dataclass, field
+from types import SimpleNamespace
+from typing import List, Optional
+
+import numpy as np
+import torch
+
+from . import _lib as L
+
+
+def _sd15_config(**over):
+    cfg = dict(num_train_timesteps=1000, beta_start=0.00085, beta_end=0.012, beta_schedule="scaled_linear",
+               skip_prk_steps=True, set_alpha_to_one=False, steps_offset=1, prediction_type="epsilon",
+               clip_sample=False, timestep_spacing="leading")
+    cfg.update(over)
+    return SimpleNamespace(**cfg)
+
+
+@dataclass
+class StepPlan:
+    """Everything kernel (c) needs for one scheduler update, as host scalars."""
+    mode: int = L.SCHED_LINEAR
+    w: tuple = (1.0, 0.0, 0.0, 0.0)     # eps' = w0*eps + w1*hist0 + w2*hist1 + w3*hist2
+    n_hist: int = 0                      # history tensors read
+    c_sample: float = 1.0
+    c_eps: float = 0.0
+    use_stash: bool = False              # PLMS counter 1: update from the stashed sample
+    write_stash: bool = False            # PLMS counter 0
+    push_eps: bool = True                # append the (post-CFG) eps to the history ring
+    ddim: tuple = (1.0, 0.0, 1.0, 0.0, 0.0)  # sqrt_a_t, sqrt_1m_a_t, sqrt_a_prev, dir_coeff, sigma
+    needs_noise: bool = False
+
+
+class _SchedulerBase:
+    order = 1
+    init_noise_sigma = 1.0
+
+    def __init__(self, **over):
+        self.config = _sd15_config(**over)
+        c = self.config
+        if c.beta_schedule == "scaled_linear":
+            betas = torch.linspace(c.beta_start ** 0.5, c.beta_end ** 0.5, c.num_train_timesteps, dtype=torch.float32) ** 2
+        elif c.beta_schedule == "linear":
+            betas = torch.linspace(c.beta_start, c.beta_end, c.num_train_timesteps, dtype=torch.float32)
+        else:
+            raise NotImplementedError(f"beta_schedule {c.beta_schedule}")
+        if c.prediction_type != "epsilon":
+            raise NotImplementedError("only epsilon prediction is on the reference path (SD1.5 scheduler config)")
+        self.betas = betas
+        self.alphas_cumprod = torch.cumprod(1.0 - betas, dim=0)
+        self.final_alpha_cumprod = torch.tensor(1.0) if c.set_alpha_to_one else self.alphas_cumprod[0]
+        self.timesteps: Optional[torch.Tensor] = None
+        self.num_inference_steps: Optional[int] = None
+
+    @classmethod
+    def from_config(cls, config, **over):
+        d = dict(vars(config)) if not isinstance(config, dict) else dict(config)
+        d.update(over)
+        known = vars(_sd15_config())
+        return cls(**{k: v for k, v in d.items() if k in known})
+
+    def scale_model_input(self, sample, timestep=None):
+        return sample  # identity for PNDM / DDIM / DDPM (dual_unet.py:1047-1048)
+
+    def x0_coeffs(self, t: int):
+        """sqrt(alpha_t), sqrt(1 - alpha_t) for the x0 prediction at dual_unet.py:1072-1075."""
+        a = self.alphas_cumprod[int(t)]
+        return float(a.sqrt()), float((1 - a).sqrt())
+
+    def reset(self):
+        pass
+
+
+class PNDMScheduler(_SchedulerBase):
+    """PLMS (skip_prk_steps) — diffusers PNDMScheduler.step_plms as a coefficient plan."""
+
+    def __init__(self, **over):
+        super().__init__(**over)
+        if not self.config.skip_prk_steps:
+            raise NotImplementedError("PRK warm-up steps are not on the reference path (SD1.5 config sets skip_prk_steps)")
+        self.counter = 0
+        self.n_ets = 0
+
+    def set_timesteps(self, num_inference_steps: int, device=None):
+        self.num_inference_steps = int(num_inference_steps)
+        ratio = self.config.num_train_timesteps // self.num_inference_steps
+        base = (np.arange(0, self.num_inference_steps) * ratio).round() + self.config.steps_offset
+        plms = np.concatenate([base[:-1], base[-2:-1], base[-1:]])[::-1].copy()
+        self.timesteps = torch.from_numpy(plms.astype(np.int64))
+        self.reset()
+
+    def reset(self):
+        self.counter = 0
+        self.n_ets = 0
+
+    def _prev_coeffs(self, timestep: int, prev_timestep: int):
+        a_t = self.alphas_cumprod[timestep]
+        a_p = self.alphas_cumprod[prev_timestep] if prev_timestep >= 0 else self.final_alpha_cumprod
+        b_t, b_p = 1 - a_t, 1 - a_p
+        sample_coeff = (a_p / a_t) ** 0.5
+        denom = a_t * b_p ** 0.5 + (a_t * b_t * a_p) ** 0.5
+        return float(sample_coeff), float((a_p - a_t) / denom)
+
+    def plan_step(self, timestep: int, eta: float = 0.0) -> StepPlan:
+        timestep = int(timestep)
+        ratio = self.config.num_train_timesteps // self.num_inference_steps
+        prev = timestep - ratio
+        plan = StepPlan()
+        if self.counter != 1:
+            self.n_ets = min(self.n_ets, 3) + 1
+            plan.push_eps = True
+        else:
+            prev = timestep
+            timestep = timestep + ratio
+            plan.push_eps = False
+        if self.n_ets == 1 and self.counter == 0:
+            plan.w, plan.n_hist, plan.write_stash = (1.0, 0.0, 0.0, 0.0), 0, True
+        elif self.n_ets == 1 and self.counter == 1:
+            plan.w, plan.n_hist, plan.use_stash = (0.5, 0.5, 0.0, 0.0), 1, True
+        elif self.n_ets == 2:
+            plan.w, plan.n_hist = (1.5, -0.5, 0.0, 0.0), 1
+        elif self.n_ets == 3:
+            plan.w, plan.n_hist = (23 / 12, -16 / 12, 5 / 12, 0.0), 2
+        else:
+            plan.w, plan.n_hist = (55 / 24, -59 / 24, 37 / 24, -9 / 24), 3
+        plan.c_sample, plan.c_eps = self._prev_coeffs(timestep, prev)
+        self.counter += 1
+        return plan
+
+
+class DDIMScheduler(_SchedulerBase):
+    def set_timesteps(self, num_inference_steps: int, device=None):
+        self.num_inference_steps = int(num_inference_steps)
+        ratio = self.config.num_train_timesteps // self.num_inference_steps
+        ts = (np.arange(0, self.num_inference_steps) * ratio).round()[::-1].copy().astype(np.int64) + self.config.steps_offset
+        self.timesteps = torch.from_numpy(ts)
+
+    def plan_step(self, timestep: int, eta: float = 0.0) -> StepPlan:
+        timestep = int(timestep)
+        prev = timestep - self.config.num_train_timesteps // self.num_inference_steps
+        a_t = self.alphas_cumprod[timestep]
+        a_p = self.alphas_cumprod[prev] if prev >= 0 else self.final_alpha_cumprod
+        b_t = 1 - a_t
+        variance = ((1 - a_p) / (1 - a_t)) * (1 - a_t / a_p)
+        std = eta * variance ** 0.5
+        plan = StepPlan(mode=L.SCHED_DDIM, push_eps=False)
+        plan.ddim = (float(a_t ** 0.5), float(b_t ** 0.5), float(a_p ** 0.5), float((1 - a_p - std ** 2) ** 0.5), float(std))
+        plan.needs_noise = eta > 0
+        return plan
+
+
+class BranchState:
+    """Device state of one denoising branch (SDR or GM): fp32 pixel-major latents [B*h*w, 4], a 4-slot eps ring
+    and the PLMS stash.  Allocated once; every step is in-place (CUDA-graph friendly)."""
+
+    def __init__(self, n_px: int, device):
+        f = dict(dtype=torch.float32, device=device)
+        self.n_px = n_px
+        self.x = torch.empty(n_px, 4, **f)
+        self.stash = torch.empty(n_px, 4, **f)
+        self.ring = [torch.empty(n_px, 4, **f) for _ in range(4)]
+        self.order: List[int] = []  # ring slots, most recent first
+        self.noise: Optional[torch.Tensor] = None
+
+    def reset(self):
+        self.order = []
+
+    def hist(self, k: int) -> Optional[torch.Tensor]:
+        return self.ring[self.order[k]] if k < len(self.order) else None
+
+    def free_slot(self) -> int:
+        used = set(self.order[:3])
+        for s in range(4):
+            if s not in used:
+                return s
+        raise AssertionError
+
+
+def fused_step(plan: StepPlan, state: BranchState, eps_cond: torch.Tensor, eps_uncond: Optional[torch.Tensor] = None, *,
+               guidance_scale: float = 1.0, guidance_rescale: float = 0.0, px_per_sample: int = 0, x0_coeffs=(1.0, 0.0),
+               unet_in_next: Optional[torch.Tensor] = None, concat_out: Optional[torch.Tensor] = None,
+               concat_tail: Optional[torch.Tensor] = None, concat_lead: Optional[torch.Tensor] = None,
+               x0_out: Optional[torch.Tensor] = None, rescale_ws: Optional[torch.Tensor] = None, stream: Optional[int] = None) -> None:
+    """One launch of `gmd_cfg_sched_step` (csrc/sched.cu) for one branch; updates `state` in place."""
+    p = L.SchedParams()
+    p.eps_uncond, p.eps_cond = L.ptr(eps_uncond), eps_cond.data_ptr()
+    p.x, p.x_next = state.x.data_ptr(), state.x.data_ptr()
+    p.x_stash = state.stash.data_ptr() if plan.use_stash else None
+    p.stash_out = state.stash.data_ptr() if plan.write_stash else None
+    for k in range(3):
+        h = state.hist(k) if k < plan.n_hist else None
+        p.hist[k] = L.ptr(h)
+    slot = None
+    if plan.push_eps and plan.mode == L.SCHED_LINEAR:
+        slot = state.free_slot()
+        p.eps_out = state.ring[slot].data_ptr()
+    if plan.needs_noise:
+        if state.noise is None:
+            raise ValueError("this scheduler step needs pre-drawn variance noise in BranchState.noise")
+        p.noise = state.noise.data_ptr()
+    p.unet_in_next, p.concat_out = L.ptr(unet_in_next), L.ptr(concat_out)
+    p.concat_tail, p.concat_lead, p.x0_out = L.ptr(concat_tail), L.ptr(concat_lead), L.ptr(x0_out)
+    ch = None
+    for t in (unet_in_next, concat_out):
+        if t is not None:
+            ch = t.shape[-1]
+    p.unet_in_ch = ch or 8
+    p.n_px, p.px_per_sample = state.n_px, px_per_sample or state.n_px
+    p.mode, p.use_stash = plan.mode, int(plan.use_stash)
+    p.guidance_scale, p.guidance_rescale = float(guidance_scale), float(guidance_rescale)
+    p.rescale_stats = L.ptr(rescale_ws)
+    p.sqrt_alpha_t, p.sqrt_1m_alpha_t = x0_coeffs
+    for k in range(4):
+        p.w[k] = plan.w[k]
+    p.c_sample, p.c_eps = plan.c_sample, plan.c_eps
+    (p.ddim_sqrt_alpha_t, p.ddim_sqrt_1m_alpha_t, p.ddim_sqrt_alpha_prev, p.ddim_dir_coeff, p.ddim_sigma) = plan.ddim
+    L.check(L.lib().gmd_cfg_sched_step(C.byref(p), L.current_stream() if stream is None else stream), "gmd_cfg_sched_step")
+    if slot is not None:
+        state.order.insert(0, slot)
+        del state.order[3:]
+
+
+def clone_scheduler(s):
+    """`copy.deepcopy(self.scheduler)` at dual_unet.py:1036-1037."""
+    return copy.deepcopy(s)

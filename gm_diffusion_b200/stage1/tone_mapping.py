@@ -1,0 +1,141 @@
+"""Drop-in for gm_diffusion/stage1/tone_mapping.py: same function names, argument meaning and error
+behaviour, each routed to the fused sm_100a kernel `gmd_hdr_reconstruct` (csrc/hdr.cu).  CUDA tensors only —
+there is no CPU or PyTorch fallback.  `reconstruct_hdr` exposes the whole fused chain (de-normalise ->
+Eq.(1) -> TMO -> gamut -> min/max) as ONE launch; the reference spends ~15 launches and a host round-trip on it
+(scripts/inference/generate_hdr.py:225-268)."""
+from __future__ import annotations
+
+import ctypes as C
+import random
+from typing import Optional, Tuple
+
+import torch
+
+from .. import _lib as L
+
+_TMO = {None: L.TMO_NONE, "none": L.TMO_NONE, "linear_scale": L.TMO_LINEAR, "hard_clip": L.TMO_HARD_CLIP,
+        "fix_mulog": L.TMO_MULOG, "mulog": L.TMO_MULOG, "tmo_cuda": L.TMO_CUDA}
+
+
+def _prep(t: torch.Tensor) -> Tuple[torch.Tensor, int]:
+    if t.dtype == torch.bfloat16:
+        return t.contiguous(), L.BF16
+    return t.to(torch.float32).contiguous(), L.F32
+
+
+def _run(sdr, gm, *, flags, tmo, qmax, eps, mu, want_hdr, want_tmo, want_minmax, layout=None):
+    L.require_cuda(sdr, gm)
+    sdr, dt = _prep(sdr)
+    if gm is not None:
+        gm, dt2 = _prep(gm)
+        if dt2 != dt:
+            sdr, gm, dt = sdr.float(), gm.float(), L.F32
+        if gm.shape != sdr.shape:
+            gm, sdr = (t.contiguous() for t in torch.broadcast_tensors(gm, sdr))
+    p = L.HdrParams()
+    if layout is None:
+        layout = L.LAYOUT_PLANAR3 if (sdr.dim() == 4 and sdr.shape[1] == 3 and (flags & L.HDR_GAMUT)) else L.LAYOUT_FLAT
+    if layout == L.LAYOUT_PLANAR3:
+        p.n_px, p.batch = sdr.shape[2] * sdr.shape[3], sdr.shape[0]
+    elif layout == L.LAYOUT_INTERLEAVED3:
+        p.n_px, p.batch = sdr.numel() // 3, 1
+    else:
+        p.n_px, p.batch = sdr.numel(), 1
+    hdr = torch.empty(sdr.shape, dtype=torch.float32, device=sdr.device) if want_hdr else None
+    out = torch.empty(sdr.shape, dtype=torch.float32, device=sdr.device) if want_tmo else None
+    mm = torch.empty(2, dtype=torch.int32, device=sdr.device) if want_minmax else None
+    p.sdr, p.gm, p.hdr_out, p.tmo_out, p.minmax = L.ptr(sdr), L.ptr(gm), L.ptr(hdr), L.ptr(out), L.ptr(mm)
+    p.layout, p.in_dtype, p.flags, p.tmo = layout, dt, flags, tmo
+    p.qmax, p.eps, p.mu = float(qmax), float(eps), float(mu)
+    L.check(L.lib().gmd_hdr_reconstruct(C.byref(p), L.current_stream()), "gmd_hdr_reconstruct")
+    return hdr, out, mm
+
+
+def _decode_minmax(mm: torch.Tensor) -> Tuple[float, float]:
+    lo, hi = mm.tolist()  # device -> host sync, like hdr.max()/hdr.min() at generate_hdr.py:268
+    return float(L.lib().gmd_decode_ordered(lo)), float(L.lib().gmd_decode_ordered(hi))
+
+
+def linear_scale_tmo(img: torch.Tensor, qmax: float) -> torch.Tensor:
+    """tone_mapping.py:14-18."""
+    return _run(img, None, flags=0, tmo=L.TMO_LINEAR, qmax=qmax, eps=0, mu=0, want_hdr=False, want_tmo=True,
+                want_minmax=False)[1]
+
+
+def hard_clip_tmo(hdr_img: torch.Tensor, qmax: float) -> torch.Tensor:
+    """tone_mapping.py:21-26 (qmax ignored, kept for API compatibility)."""
+    del qmax
+    return _run(hdr_img, None, flags=0, tmo=L.TMO_HARD_CLIP, qmax=0, eps=0, mu=0, want_hdr=False, want_tmo=True,
+                want_minmax=False)[1]
+
+
+def fix_mulog_tmo(hdr_img: torch.Tensor, qmax: float) -> torch.Tensor:
+    """tone_mapping.py:29-36 (mu = 500)."""
+    return _run(hdr_img, None, flags=0, tmo=L.TMO_MULOG, qmax=qmax, eps=0, mu=500.0, want_hdr=False, want_tmo=True,
+                want_minmax=False)[1]
+
+
+def tmo_cuda(hdr_img: torch.Tensor) -> torch.Tensor:
+    """tone_mapping.py:39-47; raises ValueError when the clamped image is not inside [0,1] (NaN input)."""
+    _, out, mm = _run(hdr_img, None, flags=0, tmo=L.TMO_CUDA, qmax=0, eps=0, mu=5000.0, want_hdr=False, want_tmo=True,
+                      want_minmax=True)
+    lo, hi = _decode_minmax(mm)
+    if hdr_img.numel() and not (hi < float("inf")):  # the kernel flags NaN inputs as max = +inf
+        raise ValueError("HDR image values should be in the range [0, 1]")
+    return out
+
+
+def random_tmo_cuda(hdr_img: torch.Tensor, qmax: float) -> torch.Tensor:
+    """tone_mapping.py:50-57: mu ~ U(500, 5000) from Python's `random`, as in the reference."""
+    mu = random.uniform(500, 5_000)
+    return _run(hdr_img, None, flags=0, tmo=L.TMO_MULOG, qmax=qmax, eps=0, mu=mu, want_hdr=False, want_tmo=True,
+                want_minmax=False)[1]
+
+
+def apply_gm_to_sdr(gm: torch.Tensor, sdr: torch.Tensor, qmax: float = 9, eps: float = 1 / 64) -> torch.Tensor:
+    """tone_mapping.py:60-71: hdr = clamp((clamp(sdr,0,1)^2.2 + eps) * (1 + gm*qmax) - eps, 0, qmax+1)."""
+    return _run(sdr, gm, flags=L.HDR_EQ1 | L.HDR_CLAMP_OUT, tmo=L.TMO_NONE, qmax=qmax, eps=eps, mu=0, want_hdr=True,
+                want_tmo=False, want_minmax=False)[0]
+
+
+def gamut_compress(tmo_hdr_img: torch.Tensor) -> torch.Tensor:
+    """tone_mapping.py:74-90: BT.2020 -> BT.709 matrix + clamp for [B,3,H,W]."""
+    if tmo_hdr_img.dim() != 4 or tmo_hdr_img.shape[1] != 3:
+        # the reference's permute(0,2,3,1) @ [3,3] fails on anything else
+        raise RuntimeError(f"gamut_compress expects [B,3,H,W], got {tuple(tmo_hdr_img.shape)}")
+    return _run(tmo_hdr_img, None, flags=L.HDR_GAMUT, tmo=L.TMO_NONE, qmax=0, eps=0, mu=0, want_hdr=False, want_tmo=True,
+                want_minmax=False, layout=L.LAYOUT_PLANAR3)[1]
+
+
+def reconstruct_hdr(sdr: torch.Tensor, gm: torch.Tensor, qmax: float = 99.0, eps: float = 1 / 64, *, tmo: Optional[str] = None,
+                    gamut: bool = False, denormalize: bool = False, clamp: bool = True, return_hdr: bool = True,
+                    return_minmax: bool = False, mu: float = 500.0, channels_last: bool = False, exp_gain: bool = False):
+    """The whole post-VAE chain in one launch.  Returns (hdr | None, tmo | None[, (min, max)]).
+
+    sdr, gm: [B,3,H,W] (or [...,3] with channels_last) fp32/bf16, in [0,1] or, with `denormalize`, the raw VAE
+    output in [-1,1] (generate_hdr.py:227,232).  `clamp=False` gives the numpy-twin behaviour
+    (formal_improved.py:34-45)."""
+    if tmo not in _TMO:
+        raise ValueError(f"unknown tmo {tmo!r}; choose from {sorted(k for k in _TMO if k)}")
+    flags = L.HDR_EQ1 | (L.HDR_DENORM if denormalize else 0) | (L.HDR_CLAMP_OUT if clamp else 0) | \
+        (L.HDR_GAMUT if gamut else 0) | (L.HDR_EXP_GAIN if exp_gain else 0)
+    want_tmo = tmo is not None or gamut
+    if channels_last:
+        if sdr.shape[-1] != 3:
+            raise ValueError("channels_last expects [...,3]")
+        layout = L.LAYOUT_INTERLEAVED3
+    elif sdr.dim() == 4 and sdr.shape[1] == 3:
+        layout = L.LAYOUT_PLANAR3
+    else:
+        if gamut:
+            raise ValueError("gamut compression needs [B,3,H,W] or channels_last [...,3]")
+        layout = L.LAYOUT_FLAT
+    hdr, out, mm = _run(sdr, gm, flags=flags, tmo=_TMO[tmo], qmax=qmax, eps=eps, mu=mu, want_hdr=return_hdr,
+                        want_tmo=want_tmo, want_minmax=return_minmax, layout=layout)
+    if return_minmax:
+        return hdr, out, _decode_minmax(mm)
+    return hdr, out
+
+
+__all__ = ["linear_scale_tmo", "hard_clip_tmo", "fix_mulog_tmo", "tmo_cuda", "random_tmo_cuda", "apply_gm_to_sdr",
+           "gamut_compress", "reconstruct_hdr"]

@@ -1,0 +1,219 @@
+/*
+ * gmd_b200.h — C-ABI of the B200-native GM-Diffusion Stage-3 hot path.
+ *
+ * The reference (Guanys-dar/GM-Diffusion) is pure Python and has no FFI of its own; the seam this
+ * library slots into is the set of tensor ops its pipelines and stage-1 functions execute
+ * (SURVEY.md §8b).  Every entry point below names the reference lines it replaces.  A maintainer
+ * binds these with ctypes from
+ *   gm_diffusion/stage1/tone_mapping.py            (kernel d)
+ *   gm_diffusion/pipelines/stable_diffusion_*.py   (kernels a, b, c inside the denoising loop)
+ *
+ * Conventions
+ *   - all pointers are DEVICE pointers owned by the caller (torch); `stream` is a cudaStream_t
+ *     passed as void*; functions never allocate device memory and never synchronise.
+ *   - return 0 on success, <0 on error: -1 invalid argument (binding raises ValueError),
+ *     -2 CUDA error, -3 unsupported configuration (binding raises RuntimeError /
+ *     NotImplementedError).  gmd_last_error() returns a thread-local message.
+ *   - activations are bf16 NHWC ("pixel-major": [N, H, W, C]) or token-major [M, C]; latent /
+ *     scheduler state is fp32 [N, H, W, 4]; images for kernel (d) are fp32 (or bf16) planar
+ *     [B, 3, H, W] / interleaved [.., 3] / flat.
+ */
+#ifndef GMD_B200_H_
+#define GMD_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GMD_VERSION 100
+
+int gmd_version(void);
+const char* gmd_last_error(void);
+/* number of kernels launched by this library in this process since load / last reset */
+int64_t gmd_launch_count(void);
+void gmd_reset_launch_count(void);
+
+/* ------------------------------------------------------------------------------------------ */
+/* (d) Eq.(1) HDR reconstruction + TMO + gamut + min/max                                       */
+/*     replaces gm_diffusion/stage1/tone_mapping.py:14-90 (apply_gm_to_sdr :60-71,             */
+/*     linear_scale_tmo :14-18, hard_clip_tmo :21-26, fix_mulog_tmo :29-36, tmo_cuda :39-47,   */
+/*     random_tmo_cuda :50-57, gamut_compress :74-90) and the de-normalise + numpy Eq.(1)      */
+/*     tail of scripts/inference/generate_hdr.py:225-233,256-268.                              */
+/* ------------------------------------------------------------------------------------------ */
+enum gmd_layout { GMD_LAYOUT_FLAT = 0, GMD_LAYOUT_PLANAR3 = 1 /* [B,3,H*W] */, GMD_LAYOUT_INTERLEAVED3 = 2 /* [n_px,3] */ };
+enum gmd_dtype { GMD_F32 = 0, GMD_BF16 = 1 };
+enum gmd_tmo {
+    GMD_TMO_NONE = 0,
+    GMD_TMO_LINEAR = 1,    /* x / (qmax+1) */
+    GMD_TMO_HARD_CLIP = 2, /* clamp(x, 0, 1) */
+    GMD_TMO_MULOG = 3,     /* clamp(log1p(mu * x/(qmax+1)) / log1p(mu), 0, 1); fix_mulog: mu = 500 */
+    GMD_TMO_CUDA = 4       /* y = clamp(x/10,0,1); log1p(5000 y)/log1p(5000)  (tmo_cuda) */
+};
+enum gmd_stage_flags {
+    GMD_HDR_EQ1 = 1,          /* run Eq.(1); otherwise `sdr` is taken as the HDR input of the TMO stage */
+    GMD_HDR_DENORM = 2,       /* inputs are in [-1,1]: x <- clamp(x/2 + 0.5, 0, 1) first (generate_hdr.py:227,232) */
+    GMD_HDR_CLAMP_OUT = 4,    /* clamp(hdr, 0, qmax+1) (tone_mapping.py:71; numpy twins do not clamp) */
+    GMD_HDR_GAMUT = 8,        /* BT.2020 -> BT.709 3x3 + clamp(0,1) after the TMO (needs a 3-channel layout) */
+    GMD_HDR_EXP_GAIN = 16     /* extra, never default: gain = 2^(gm * log2(qmax+1)) instead of 1 + gm*qmax */
+};
+
+typedef struct gmd_hdr_params {
+    const void* sdr;   /* SDR image (or HDR input when GMD_HDR_EQ1 is not set) */
+    const void* gm;    /* gain map; may be NULL when GMD_HDR_EQ1 is not set */
+    float* hdr_out;    /* optional: Eq.(1) output */
+    float* tmo_out;    /* optional: TMO (+gamut) output */
+    int32_t* minmax;   /* optional: 2 ordered-int32 slots {min,max} of the hdr values; decode with gmd_decode_ordered */
+    int64_t n_px;      /* PLANAR3: H*W per image plane; INTERLEAVED3: pixels; FLAT: elements */
+    int64_t batch;     /* PLANAR3: number of images (planes = 3*batch); otherwise 1 */
+    int32_t layout;    /* enum gmd_layout */
+    int32_t in_dtype;  /* enum gmd_dtype */
+    int32_t flags;     /* enum gmd_stage_flags */
+    int32_t tmo;       /* enum gmd_tmo */
+    float qmax;
+    float eps;
+    float mu;          /* GMD_TMO_MULOG only */
+} gmd_hdr_params;
+
+int gmd_hdr_reconstruct(const gmd_hdr_params* p, void* stream);
+float gmd_decode_ordered(int32_t v);
+
+/* ------------------------------------------------------------------------------------------ */
+/* (c) CFG combine + x0 prediction + PLMS/DDIM update + SDR/GM concat, one launch per branch   */
+/*     replaces gm_diffusion/pipelines/stable_diffusion_dual_unet.py:1045-1048,1063-1080,1093  */
+/*     and stable_diffusion_gm.py:1045-1048,1062-1071 plus diffusers PNDMScheduler.step_plms / */
+/*     DDIMScheduler.step (called at :1077/:1093).                                             */
+/* ------------------------------------------------------------------------------------------ */
+enum gmd_sched_mode { GMD_SCHED_LINEAR = 0 /* PLMS & friends: x' = c_sample*x_src - c_eps*eps' */, GMD_SCHED_DDIM = 1 };
+
+typedef struct gmd_sched_params {
+    /* model outputs, fp32 [n_px, 4] (pixel-major) */
+    const float* eps_uncond; /* NULL when CFG is off: eps = eps_cond */
+    const float* eps_cond;
+    /* state, fp32 [n_px, 4] */
+    const float* x;          /* current latents */
+    const float* x_stash;    /* PLMS: sample stashed at counter 0; used instead of x when use_stash */
+    const float* hist[3];    /* previous eps (most recent first); NULL where weight is 0 */
+    const float* noise;      /* optional pre-drawn variance noise (DDIM eta>0 / DDPM), fp32 [n_px,4] */
+    float* x_next;           /* updated latents (may alias x) */
+    float* stash_out;        /* optional: copy of x (PLMS counter 0) */
+    float* eps_out;          /* optional: post-CFG eps stored for the history ring */
+    /* fused layout outputs, bf16 [n_px, unet_in_ch] pixel-major, channel-padded with zeros */
+    void* unet_in_next;      /* optional: ch0-3 <- x_next (next SDR-UNet input; CFG dup is implicit) */
+    void* concat_out;        /* optional: ch0-3 <- x0 (or `concat_lead` if given), ch4-7 <- concat_tail */
+    const float* concat_tail;/* fp32 [n_px,4]: the other branch's current latents (gm_latents) */
+    const float* concat_lead;/* optional fp32 [n_px,4]: fixed leading channels (single pipeline: sdr_latent) */
+    float* x0_out;           /* optional fp32 [n_px,4]: x0 prediction */
+    int64_t n_px;            /* B*h*w */
+    int64_t px_per_sample;   /* h*w, for per-sample guidance rescale */
+    int32_t unet_in_ch;      /* channel count of unet_in_next / concat_out rows (multiple of 8, >= 8) */
+    int32_t mode;            /* enum gmd_sched_mode */
+    int32_t use_stash;
+    float guidance_scale;
+    float guidance_rescale;  /* phi; > 0 needs rescale_stats */
+    float* rescale_stats;    /* workspace fp32 [B, 4]: sums for std(eps_cond), std(eps_cfg) */
+    float sqrt_alpha_t;      /* x0 = (x - sqrt_1m_alpha_t * eps) / sqrt_alpha_t (dual_unet.py:1072-1075) */
+    float sqrt_1m_alpha_t;
+    float w[4];              /* eps' = w0*eps + w1*hist0 + w2*hist1 + w3*hist2 */
+    float c_sample;          /* LINEAR mode */
+    float c_eps;
+    float ddim_sqrt_alpha_t, ddim_sqrt_1m_alpha_t, ddim_sqrt_alpha_prev, ddim_dir_coeff, ddim_sigma; /* DDIM mode */
+} gmd_sched_params;
+
+int gmd_cfg_sched_step(const gmd_sched_params* p, void* stream);
+
+/* latents fp32 NCHW [B,4,h,w] <-> pixel-major fp32 [B,h,w,4] (pipeline entry / exit) */
+int gmd_latents_nchw_to_px(const float* src, float* dst, int64_t batch, int64_t hw, void* stream);
+int gmd_latents_px_to_nchw(const float* src, float* dst, int64_t batch, int64_t hw, void* stream);
+/* fp32 [n_px,4] -> bf16 [n_px, ch] zero-padded rows, optional second source in ch4-7 */
+int gmd_pack_unet_input(const float* lead, const float* tail, void* dst, int64_t n_px, int32_t ch, void* stream);
+
+/* ------------------------------------------------------------------------------------------ */
+/* (b) convolutions / linears as tcgen05 implicit GEMM; GroupNorm+SiLU; LayerNorm               */
+/*     replaces the diffusers UNet2DConditionModel / AutoencoderKL ops reached from            */
+/*     stable_diffusion_dual_unet.py:1052-1060,1083-1092 and generate_hdr.py:225-233.          */
+/* ------------------------------------------------------------------------------------------ */
+enum gmd_epilogue_flags {
+    GMD_EPI_BIAS = 1,       /* + bias[n] (fp32) */
+    GMD_EPI_ROW_BIAS = 2,   /* + row_bias[sample(m), n] (fp32; the time-embedding projection) */
+    GMD_EPI_RESIDUAL = 4,   /* + residual[m, n] (bf16, ld = ldr) */
+    GMD_EPI_GEGLU = 8,      /* out[m, j] = (acc[m, j] + b[j]) * gelu(acc[m, j + N/2] + b[j + N/2]); weight rows interleaved per tile */
+    GMD_EPI_OUT_F32 = 16,   /* write fp32 instead of bf16 */
+    GMD_EPI_SCALE = 32      /* acc *= alpha before everything else */
+};
+
+typedef struct gmd_gemm_params {
+    /* out[M, N] = A[M, K] * W[N, K]^T  (+ epilogue).  A, W bf16 K-contiguous. */
+    const void* a;  int64_t lda;        /* row stride in elements */
+    const void* w;  int64_t ldw;
+    void* out;      int64_t ldo;
+    const float* bias;
+    const float* row_bias; int64_t ld_row_bias; int64_t rows_per_sample;
+    const void* residual;  int64_t ldr;
+    int64_t M, N, K;
+    int64_t batch;                       /* batched: strides in elements between problems */
+    int64_t stride_a, stride_w, stride_o;
+    int32_t flags;
+    float alpha;
+} gmd_gemm_params;
+
+int gmd_gemm_fwd(const gmd_gemm_params* p, void* stream);
+
+typedef struct gmd_conv_params {
+    /* 3x3 (pad 1, stride 1 or 2) or 1x1 convolution, NHWC bf16, weights [Cout, R*S*(C0+C1)] bf16
+     * with k = (r*S + s)*(C0+C1) + c.  Two sources implement the up-block skip concat without a copy. */
+    const void* x0; int32_t C0;
+    const void* x1; int32_t C1;          /* optional second source (channels appended after x0's) */
+    const void* w;
+    void* out;                           /* [N, Ho, Wo, Cout] bf16 (or fp32 with GMD_EPI_OUT_F32) */
+    const float* bias;
+    const float* row_bias; int64_t ld_row_bias;   /* [N, Cout] time-embedding projection */
+    const void* residual;                /* [N, Ho, Wo, Cout] bf16 */
+    int32_t N, H, W;                     /* input spatial size */
+    int32_t Cout;                        /* logical output channels written */
+    int32_t Cout_pad;                    /* rows of w (multiple of the N tile; >= Cout) */
+    int32_t ksize;                       /* 1 or 3 */
+    int32_t stride;                      /* 1 or 2 */
+    int32_t upsample;                    /* 1: nearest-2x upsample of the input folded into the gather */
+    int32_t flags;
+} gmd_conv_params;
+
+int gmd_conv_fwd(const gmd_conv_params* p, void* stream);
+
+/* GroupNorm(+SiLU) over NHWC bf16 with an optional second (concatenated) source. */
+int gmd_groupnorm_silu(const void* x0, int32_t C0, const void* x1, int32_t C1, const float* gamma, const float* beta,
+                       void* out, int32_t N, int32_t HW, int32_t groups, float eps, int32_t apply_silu,
+                       float* stats_ws /* fp32 [N, groups, 2] */, void* stream);
+/* LayerNorm over the last dim of token-major bf16 [M, C]. */
+int gmd_layernorm(const void* x, const float* gamma, const float* beta, void* out, int64_t M, int32_t C, float eps,
+                  void* stream);
+/* sinusoidal timestep embedding (flip_sin_to_cos, shift 0) -> bf16 [B, dim] */
+int gmd_timestep_embedding(float t, void* out, int32_t B, int32_t dim, void* stream);
+/* y = silu(x) elementwise bf16 */
+int gmd_silu(const void* x, void* out, int64_t n, void* stream);
+/* row softmax over bf16 [M, N] with scale (VAE mid-block attention) */
+int gmd_softmax_rows(const void* x, void* out, int64_t M, int64_t N, float scale, void* stream);
+
+/* ------------------------------------------------------------------------------------------ */
+/* (a) attention: softmax(Q K^T * scale) V, tcgen05 + TMEM + TMA, streaming softmax            */
+/*     replaces F.scaled_dot_product_attention inside diffusers AttnProcessor2_0 (self- and    */
+/*     text cross-attention of the UNets called at stable_diffusion_dual_unet.py:1052,1083).   */
+/* ------------------------------------------------------------------------------------------ */
+typedef struct gmd_attn_params {
+    /* q: [B, Nq, H, d] view with element strides; k, v: [B, Nk, H, d]; o: [B, Nq, H*d] bf16 */
+    const void* q; int64_t q_stride_b, q_stride_n, q_stride_h;
+    const void* k; int64_t k_stride_b, k_stride_n, k_stride_h;
+    const void* v; int64_t v_stride_b, v_stride_n, v_stride_h;
+    void* o;       int64_t o_stride_b, o_stride_n, o_stride_h;
+    int32_t B, H, Nq, Nk, d;
+    float scale;
+} gmd_attn_params;
+
+int gmd_attn_fwd(const gmd_attn_params* p, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GMD_B200_H_ */

@@ -1,0 +1,53 @@
+"""Generate tests/golden/tm_*.npz by running the REAL reference gm_diffusion/stage1/tone_mapping.py
+(executed by file path in the build container: it is pure torch).  The vectors pin oracle/tone_mapping_oracle.py
+and kernel (d).  Run: python -m oracle.make_golden"""
+from __future__ import annotations
+
+import math
+from pathlib import Path
+
+import numpy as np
+import torch
+
+from . import tone_mapping_oracle as tmo
+
+OUT = Path(__file__).resolve().parent.parent / "tests" / "golden"
+
+
+def main():
+    ref = tmo.load_reference_tm()
+    if ref is None:
+        raise SystemExit("reference not present; golden vectors can only be generated in the build container")
+    OUT.mkdir(parents=True, exist_ok=True)
+    g = torch.Generator().manual_seed(0)
+    # domain: sdr, gm in [0,1] (train_vqgan_lora.py:1129-1131), plus out-of-range / edge values
+    sdr = torch.rand(2, 3, 24, 20, generator=g)
+    gm = torch.rand(2, 3, 24, 20, generator=g)
+    edge = torch.tensor([0.0, 1.0, 0.5, 1e-3, 1e-6, 0.999999, -0.25, 1.25])
+    sdr.view(-1)[: edge.numel()] = edge
+    gm.view(-1)[: edge.numel()] = edge.flip(0)
+    out = dict(sdr=sdr.numpy(), gm=gm.numpy())
+    for qmax in (9.0, 49.0, 99.0):
+        hdr = ref.apply_gm_to_sdr(gm, sdr, qmax=qmax, eps=1 / 64)
+        q = int(qmax)
+        out[f"hdr_q{q}"] = hdr.numpy()
+        out[f"linear_q{q}"] = ref.linear_scale_tmo(hdr, qmax).numpy()
+        out[f"hardclip_q{q}"] = ref.hard_clip_tmo(hdr, qmax).numpy()
+        out[f"mulog_q{q}"] = ref.fix_mulog_tmo(hdr, qmax).numpy()
+        out[f"mulog_gamut_q{q}"] = ref.gamut_compress(ref.fix_mulog_tmo(hdr, qmax)).numpy()
+        out[f"tmo_cuda_q{q}"] = ref.tmo_cuda(hdr).numpy()
+    out["hdr_default"] = ref.apply_gm_to_sdr(gm, sdr).numpy()  # qmax=9, eps=1/64 defaults (tone_mapping.py:63-64)
+    out["gamut_only"] = ref.gamut_compress(sdr).numpy()
+    np.savez_compressed(OUT / "tm_reference.npz", **out)
+    # the SURVEY §8c spot values (seeded [1,3,4,4])
+    torch.manual_seed(0)
+    s = torch.rand(1, 3, 4, 4); m = torch.rand(1, 3, 4, 4)
+    h = ref.apply_gm_to_sdr(m, s, qmax=99)
+    np.savez_compressed(OUT / "tm_spot.npz", sdr=s.numpy(), gm=m.numpy(), hdr=h.numpy(),
+                        mulog=ref.fix_mulog_tmo(h, 99).numpy(), mulog_gamut=ref.gamut_compress(ref.fix_mulog_tmo(h, 99)).numpy())
+    print("wrote", sorted(p.name for p in OUT.glob("tm_*.npz")), "hdr max", float(h.max()),
+          "mulog mean", float(ref.fix_mulog_tmo(h, 99).mean()))
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,170 @@
+"""Oracle for the scheduler half of kernel (c): CPU restatement of the diffusers schedulers the reference
+pipelines call (`scheduler.set_timesteps` at stable_diffusion_dual_unet.py:151-152, `scheduler.step` at
+:1077/:1093, `alphas_cumprod` at :1072).  TEST INFRASTRUCTURE ONLY.
+
+PARITY UNPINNED: diffusers (>=0.33, README.md:54) is not vendored in /root/reference and cannot be
+installed offline; the formulas below restate the published PNDMScheduler.step_plms /
+DDIMScheduler.step / DDPMScheduler.step algorithms with the SD1.5 scheduler config
+and are pinned by invariants in tests/test_schedulers_oracle.py.
+"""
+from __future__ import annotations
+
+import math
+from types import SimpleNamespace
+
+import numpy as np
+import torch
+
+
+def sd15_scheduler_config(**over):
+    cfg = dict(num_train_timesteps=1000, beta_start=0.00085, beta_end=0.012, beta_schedule="scaled_linear",
+               skip_prk_steps=True, set_alpha_to_one=False, steps_offset=1, prediction_type="epsilon",
+               clip_sample=False, timestep_spacing="leading")
+    cfg.update(over)
+    return SimpleNamespace(**cfg)
+
+
+def make_alphas_cumprod(cfg) -> torch.Tensor:
+    if cfg.beta_schedule == "scaled_linear":
+        betas = torch.linspace(cfg.beta_start ** 0.5, cfg.beta_end ** 0.5, cfg.num_train_timesteps, dtype=torch.float32) ** 2
+    elif cfg.beta_schedule == "linear":
+        betas = torch.linspace(cfg.beta_start, cfg.beta_end, cfg.num_train_timesteps, dtype=torch.float32)
+    else:
+        raise NotImplementedError(cfg.beta_schedule)
+    return torch.cumprod(1.0 - betas, dim=0)
+
+
+class _Base:
+    order = 1
+    init_noise_sigma = 1.0
+
+    def __init__(self, **over):
+        self.config = sd15_scheduler_config(**over)
+        self.alphas_cumprod = make_alphas_cumprod(self.config)
+        self.final_alpha_cumprod = torch.tensor(1.0) if self.config.set_alpha_to_one else self.alphas_cumprod[0]
+        self.timesteps = None
+        self.num_inference_steps = None
+
+    def scale_model_input(self, sample, timestep=None):
+        return sample
+
+
+class PNDMOracle(_Base):
+    """diffusers PNDMScheduler with skip_prk_steps (PLMS only)."""
+
+    def __init__(self, **over):
+        super().__init__(**over)
+        self.ets = []
+        self.counter = 0
+        self.cur_sample = None
+
+    def set_timesteps(self, num_inference_steps, device=None):
+        self.num_inference_steps = num_inference_steps
+        ratio = self.config.num_train_timesteps // num_inference_steps
+        base = (np.arange(0, num_inference_steps) * ratio).round() + self.config.steps_offset
+        assert self.config.skip_prk_steps, "PRK steps are not on the reference path (SD1.5 config skips them)"
+        plms = np.concatenate([base[:-1], base[-2:-1], base[-1:]])[::-1].copy()
+        self.timesteps = torch.from_numpy(plms.astype(np.int64))
+        self.ets = []
+        self.counter = 0
+        self.cur_sample = None
+
+    def _get_prev_sample(self, sample, timestep, prev_timestep, model_output):
+        a_t = self.alphas_cumprod[timestep]
+        a_p = self.alphas_cumprod[prev_timestep] if prev_timestep >= 0 else self.final_alpha_cumprod
+        b_t = 1 - a_t
+        b_p = 1 - a_p
+        sample_coeff = (a_p / a_t) ** 0.5
+        denom = a_t * b_p ** 0.5 + (a_t * b_t * a_p) ** 0.5
+        return sample_coeff * sample - (a_p - a_t) * model_output / denom
+
+    def step(self, model_output, timestep, sample, return_dict=False, **kw):
+        timestep = int(timestep)
+        ratio = self.config.num_train_timesteps // self.num_inference_steps
+        prev_timestep = timestep - ratio
+        if self.counter != 1:
+            self.ets = self.ets[-3:]
+            self.ets.append(model_output)
+        else:
+            prev_timestep = timestep
+            timestep = timestep + ratio
+        if len(self.ets) == 1 and self.counter == 0:
+            self.cur_sample = sample
+        elif len(self.ets) == 1 and self.counter == 1:
+            model_output = (model_output + self.ets[-1]) / 2
+            sample = self.cur_sample
+            self.cur_sample = None
+        elif len(self.ets) == 2:
+            model_output = (3 * self.ets[-1] - self.ets[-2]) / 2
+        elif len(self.ets) == 3:
+            model_output = (23 * self.ets[-1] - 16 * self.ets[-2] + 5 * self.ets[-3]) / 12
+        else:
+            model_output = (1 / 24) * (55 * self.ets[-1] - 59 * self.ets[-2] + 37 * self.ets[-3] - 9 * self.ets[-4])
+        prev = self._get_prev_sample(sample, timestep, prev_timestep, model_output)
+        self.counter += 1
+        return (prev,)
+
+
+class DDIMOracle(_Base):
+    """diffusers DDIMScheduler (epsilon prediction, clip_sample False, leading spacing)."""
+
+    def set_timesteps(self, num_inference_steps, device=None):
+        self.num_inference_steps = num_inference_steps
+        ratio = self.config.num_train_timesteps // num_inference_steps
+        ts = (np.arange(0, num_inference_steps) * ratio).round()[::-1].copy().astype(np.int64) + self.config.steps_offset
+        self.timesteps = torch.from_numpy(ts)
+
+    def step(self, model_output, timestep, sample, eta=0.0, generator=None, variance_noise=None, return_dict=False, **kw):
+        timestep = int(timestep)
+        prev_timestep = timestep - self.config.num_train_timesteps // self.num_inference_steps
+        a_t = self.alphas_cumprod[timestep]
+        a_p = self.alphas_cumprod[prev_timestep] if prev_timestep >= 0 else self.final_alpha_cumprod
+        b_t = 1 - a_t
+        pred_x0 = (sample - b_t ** 0.5 * model_output) / a_t ** 0.5
+        variance = ((1 - a_p) / (1 - a_t)) * (1 - a_t / a_p)
+        std = eta * variance ** 0.5
+        direction = (1 - a_p - std ** 2) ** 0.5 * model_output
+        prev = a_p ** 0.5 * pred_x0 + direction
+        if eta > 0:
+            if variance_noise is None:
+                variance_noise = torch.randn(model_output.shape, generator=generator, dtype=model_output.dtype)
+            prev = prev + std * variance_noise
+        return (prev,)
+
+
+class DDPMOracle(_Base):
+    """diffusers DDPMScheduler (fixed_small variance, epsilon prediction) — what the inference CLIs pass
+    (scripts/inference/generate_hdr.py:162-176).  Ancestral noise comes from the shared generator."""
+
+    def set_timesteps(self, num_inference_steps, device=None):
+        self.num_inference_steps = num_inference_steps
+        ratio = self.config.num_train_timesteps // num_inference_steps
+        ts = (np.arange(0, num_inference_steps) * ratio).round()[::-1].copy().astype(np.int64) + self.config.steps_offset
+        self.timesteps = torch.from_numpy(ts)
+
+    def step(self, model_output, timestep, sample, generator=None, variance_noise=None, return_dict=False, **kw):
+        t = int(timestep)
+        prev_t = t - self.config.num_train_timesteps // self.num_inference_steps
+        a_t = self.alphas_cumprod[t]
+        a_p = self.alphas_cumprod[prev_t] if prev_t >= 0 else torch.tensor(1.0)
+        b_t, b_p = 1 - a_t, 1 - a_p
+        cur_alpha = a_t / a_p
+        cur_beta = 1 - cur_alpha
+        pred_x0 = (sample - b_t ** 0.5 * model_output) / a_t ** 0.5
+        c_x0 = (a_p ** 0.5 * cur_beta) / b_t
+        c_xt = cur_alpha ** 0.5 * b_p / b_t
+        prev = c_x0 * pred_x0 + c_xt * sample
+        if t > 0:
+            if variance_noise is None:
+                variance_noise = torch.randn(model_output.shape, generator=generator, dtype=model_output.dtype)
+            variance = torch.clamp((1 - a_p) / (1 - a_t) * cur_beta, min=1e-20)
+            prev = prev + variance ** 0.5 * variance_noise
+        return (prev,)
+
+
+def rescale_noise_cfg(noise_cfg, noise_pred_text, guidance_rescale=0.0):
+    """stable_diffusion_dual_unet.py:71-94."""
+    std_text = noise_pred_text.std(dim=list(range(1, noise_pred_text.ndim)), keepdim=True)
+    std_cfg = noise_cfg.std(dim=list(range(1, noise_cfg.ndim)), keepdim=True)
+    rescaled = noise_cfg * (std_text / std_cfg)
+    return guidance_rescale * rescaled + (1 - guidance_rescale) * noise_cfg

@@ -1,0 +1,188 @@
+"""tcgen05 GEMM / implicit-GEMM conv / flash attention / norms (C-ABI) vs plain PyTorch fp32 references of the
+same op on the same bf16-rounded inputs.  Tolerance: bf16 output rounding (rel 2^-8) + fp32 accumulation order."""
+import math
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+bf = torch.bfloat16
+
+
+def rel_l2(a, b):
+    a, b = a.float(), b.float()
+    return float((a - b).norm() / (b.norm() + 1e-20))
+
+
+def check(got, want, tol=6e-3, what=""):
+    got, want = got.float().cpu(), want.float().cpu()
+    assert got.shape == want.shape, (got.shape, want.shape)
+    assert torch.isfinite(got).all(), f"{what}: non-finite output"
+    r = rel_l2(got, want)
+    mx = float((got - want).abs().max())
+    assert r < tol, f"{what}: rel-L2 {r:.3e} (max abs {mx:.3e}, ref rms {float(want.pow(2).mean().sqrt()):.3e})"
+    # elementwise: bf16 rounding of the output + small absolute slack
+    scale = float(want.abs().max()) + 1e-6
+    assert mx <= 2.5e-2 * scale, f"{what}: max abs err {mx:.3e} vs scale {scale:.3e}"
+
+
+@pytest.mark.parametrize("M,N,K", [(128, 160, 64), (256, 320, 320), (1000, 320, 768), (77 * 2, 640, 768), (4096, 1280, 1280),
+                                   (130, 128, 72), (64, 32, 64), (300, 512, 512), (16, 2560, 1280)])
+def test_gemm_plain(M, N, K):
+    from gm_diffusion_b200 import ops
+    g = torch.Generator().manual_seed(M + N + K)
+    a = torch.randn(M, K, generator=g).to(bf).cuda()
+    w = (torch.randn(N, K, generator=g) / math.sqrt(K)).to(bf).cuda()
+    check(ops.gemm(a, w), a.float() @ w.float().t(), what=f"gemm {M}x{N}x{K}")
+
+
+def test_gemm_epilogues():
+    from gm_diffusion_b200 import ops
+    g = torch.Generator().manual_seed(0)
+    M, N, K, S = 512, 640, 320, 128
+    a = torch.randn(M, K, generator=g).to(bf).cuda()
+    w = (torch.randn(N, K, generator=g) / math.sqrt(K)).to(bf).cuda()
+    bias = torch.randn(N, generator=g).cuda()
+    res = torch.randn(M, N, generator=g).to(bf).cuda()
+    rb = torch.randn(M // S, N, generator=g).cuda()
+    ref = a.float() @ w.float().t()
+    check(ops.gemm(a, w, bias=bias), ref + bias, what="bias")
+    check(ops.gemm(a, w, bias=bias, residual=res), ref + bias + res.float(), what="bias+residual")
+    check(ops.gemm(a, w, bias=bias, row_bias=rb, rows_per_sample=S), ref + bias + rb.repeat_interleave(S, 0), what="row_bias")
+    out = ops.gemm(a, w, bias=bias, out_f32=True)
+    assert out.dtype == torch.float32
+    check(out, ref + bias, tol=1e-3, what="fp32 out")
+    check(ops.gemm(a, w, alpha=0.125), ref * 0.125, what="alpha")
+    # strided views (QKV-style column slices) as A, and as output
+    big = torch.randn(M, 3 * K, generator=g).to(bf).cuda()
+    check(ops.gemm(big[:, K:2 * K], w), big[:, K:2 * K].float() @ w.float().t(), what="strided A")
+
+
+def test_gemm_geglu():
+    from gm_diffusion_b200 import ops
+    g = torch.Generator().manual_seed(3)
+    M, Cc = 384, 320
+    x = torch.randn(M, Cc, generator=g).to(bf).cuda()
+    w = (torch.randn(8 * Cc, Cc, generator=g) / math.sqrt(Cc)).to(bf)
+    b = torch.randn(8 * Cc, generator=g) * 0.1
+    wi, bi = ops.pack_geglu_weight(w, b)
+    got = ops.gemm(x, wi.cuda(), bias=bi.cuda(), geglu=True)
+    proj = x.float().cpu() @ w.float().t() + b
+    h, gate = proj.chunk(2, -1)
+    check(got, h * F.gelu(gate), what="geglu")
+
+
+def test_gemm_batched():
+    from gm_diffusion_b200 import ops
+    g = torch.Generator().manual_seed(4)
+    a = torch.randn(3, 256, 512, generator=g).to(bf).cuda()
+    w = (torch.randn(3, 192, 512, generator=g) / 22).to(bf).cuda()
+    check(ops.gemm(a, w), torch.bmm(a.float(), w.float().transpose(1, 2)), what="batched")
+
+
+def _conv_ref(x_nhwc, w_oihw, bias=None, stride=1, upsample=False):
+    x = x_nhwc.float().permute(0, 3, 1, 2)
+    if upsample:
+        x = F.interpolate(x, scale_factor=2.0, mode="nearest")
+    y = F.conv2d(x, w_oihw.float(), bias, stride=stride, padding=w_oihw.shape[-1] // 2)
+    return y.permute(0, 2, 3, 1)
+
+
+@pytest.mark.parametrize("N,H,W,Cin,Cout", [(2, 64, 64, 320, 320), (2, 32, 32, 640, 1280), (3, 16, 16, 1280, 640), (5, 8, 8, 1280, 1280),
+                                            (1, 64, 64, 8, 320), (2, 64, 64, 320, 4), (1, 24, 40, 64, 128), (2, 128, 128, 128, 128)])
+def test_conv3x3(N, H, W, Cin, Cout):
+    from gm_diffusion_b200 import ops
+    g = torch.Generator().manual_seed(N * H + Cin + Cout)
+    x = torch.randn(N, H, W, Cin, generator=g).to(bf)
+    w = (torch.randn(Cout, Cin, 3, 3, generator=g) / math.sqrt(9 * Cin)).to(bf)
+    b = torch.randn(Cout, generator=g)
+    got = ops.conv2d(x.cuda(), ops.pack_conv_weight(w).cuda(), Cout, bias=b.cuda(), out_f32=(Cout == 4))
+    check(got, _conv_ref(x, w, b), what=f"conv3x3 {N}x{H}x{W} {Cin}->{Cout}")
+
+
+def test_conv_stride2_upsample_concat_epilogue():
+    from gm_diffusion_b200 import ops
+    g = torch.Generator().manual_seed(9)
+    x = torch.randn(2, 32, 32, 320, generator=g).to(bf)
+    w = (torch.randn(320, 320, 3, 3, generator=g) / math.sqrt(9 * 320)).to(bf)
+    b = torch.randn(320, generator=g)
+    wp = ops.pack_conv_weight(w).cuda()
+    check(ops.conv2d(x.cuda(), wp, 320, stride=2, bias=b.cuda()), _conv_ref(x, w, b, stride=2), what="stride 2")
+    check(ops.conv2d(x.cuda(), wp, 320, upsample=True, bias=b.cuda()), _conv_ref(x, w, b, upsample=True), what="upsample fold")
+    # two-source concat + time-embedding row bias + residual
+    x1 = torch.randn(2, 32, 32, 640, generator=g).to(bf)
+    w2 = (torch.randn(320, 960, 3, 3, generator=g) / math.sqrt(9 * 960)).to(bf)
+    rb = torch.randn(2, 320, generator=g)
+    res = torch.randn(2, 32, 32, 320, generator=g).to(bf)
+    ref = _conv_ref(torch.cat([x, x1], -1), w2, b) + rb[:, None, None, :] + res.float()
+    got = ops.conv2d(x.cuda(), ops.pack_conv_weight(w2).cuda(), 320, x1=x1.cuda(), bias=b.cuda(), row_bias=rb.cuda(), residual=res.cuda())
+    check(got, ref, what="concat+temb+residual")
+
+
+@pytest.mark.parametrize("B,H,Nq,Nk,d", [(2, 8, 4096, 4096, 40), (2, 8, 1024, 1024, 80), (2, 8, 256, 256, 160), (3, 8, 64, 64, 160),
+                                         (2, 8, 4096, 77, 40), (2, 8, 1024, 77, 80), (2, 8, 256, 77, 160), (1, 8, 200, 130, 40)])
+def test_attention(B, H, Nq, Nk, d):
+    from gm_diffusion_b200 import ops
+    g = torch.Generator().manual_seed(Nq + Nk + d)
+    Cc = H * d
+    if Nq == Nk:
+        qkv = torch.randn(B, Nq, 3 * Cc, generator=g).to(bf).cuda()
+        q, k, v = qkv[..., :Cc], qkv[..., Cc:2 * Cc], qkv[..., 2 * Cc:]
+    else:
+        q = torch.randn(B, Nq, Cc, generator=g).to(bf).cuda()
+        kv = torch.randn(B, Nk, 2 * Cc, generator=g).to(bf).cuda()
+        k, v = kv[..., :Cc], kv[..., Cc:]
+    got = ops.attention(q, k, v, H)
+    qh, kh, vh = (t.float().reshape(B, -1, H, d).transpose(1, 2) for t in (q, k, v))
+    ref = torch.softmax(qh @ kh.transpose(-1, -2) * d ** -0.5, -1) @ vh
+    check(got, ref.transpose(1, 2).reshape(B, Nq, Cc), tol=1e-2, what=f"attn B{B} H{H} {Nq}x{Nk} d{d}")
+
+
+def test_attention_large_logits():
+    from gm_diffusion_b200 import ops
+    g = torch.Generator().manual_seed(2)
+    B, H, N, d = 1, 8, 512, 40
+    q = (torch.randn(B, N, H * d, generator=g) * 6).to(bf).cuda()
+    k = (torch.randn(B, N, H * d, generator=g) * 6).to(bf).cuda()
+    v = torch.randn(B, N, H * d, generator=g).to(bf).cuda()
+    got = ops.attention(q, k, v, H)
+    qh, kh, vh = (t.float().reshape(B, -1, H, d).transpose(1, 2) for t in (q, k, v))
+    ref = torch.softmax(qh @ kh.transpose(-1, -2) * d ** -0.5, -1) @ vh
+    check(got, ref.transpose(1, 2).reshape(B, N, H * d), tol=2e-2, what="peaky softmax (running-max rescale path)")
+
+
+@pytest.mark.parametrize("N,HW,C0,C1", [(2, 4096, 320, 0), (2, 1024, 1280, 640), (3, 64, 1280, 1280), (1, 256, 640, 320), (2, 4096, 128, 0), (1, 100, 512, 0)])
+def test_groupnorm(N, HW, C0, C1):
+    from gm_diffusion_b200 import ops
+    g = torch.Generator().manual_seed(HW + C0 + C1)
+    x = (torch.randn(N, HW, C0, generator=g) * 2 + 0.5).to(bf)
+    x1 = (torch.randn(N, HW, C1, generator=g) - 1).to(bf) if C1 else None
+    Cc = C0 + C1
+    ga, be = torch.randn(Cc, generator=g), torch.randn(Cc, generator=g)
+    got = ops.groupnorm_silu(x.cuda(), ga.cuda(), be.cuda(), x1=x1.cuda() if C1 else None, eps=1e-5)
+    full = torch.cat([x, x1], -1) if C1 else x
+    ref = F.silu(F.group_norm(full.float().permute(0, 2, 1), 32, ga, be, 1e-5)).permute(0, 2, 1)
+    check(got, ref, what=f"groupnorm+silu {N}x{HW}x{C0}+{C1}")
+    got = ops.groupnorm_silu(x.cuda(), ga[:C0].cuda(), be[:C0].cuda(), eps=1e-6, silu=False)
+    check(got, F.group_norm(x.float().permute(0, 2, 1), 32, ga[:C0], be[:C0], 1e-6).permute(0, 2, 1), what="groupnorm no silu")
+
+
+@pytest.mark.parametrize("M,Cc", [(8192, 320), (2048, 640), (513, 1280), (7, 512)])
+def test_layernorm(M, Cc):
+    from gm_diffusion_b200 import ops
+    g = torch.Generator().manual_seed(M + Cc)
+    x = (torch.randn(M, Cc, generator=g) * 3 + 1).to(bf)
+    ga, be = torch.randn(Cc, generator=g), torch.randn(Cc, generator=g)
+    check(ops.layernorm(x.cuda(), ga.cuda(), be.cuda()), F.layer_norm(x.float(), (Cc,), ga, be, 1e-5), what=f"layernorm {M}x{Cc}")
+
+
+def test_softmax_silu_temb():
+    from gm_diffusion_b200 import ops
+    from oracle.unet_oracle import timestep_embedding
+    g = torch.Generator().manual_seed(1)
+    x = (torch.randn(300, 4096, generator=g) * 4).to(bf)
+    check(ops.softmax_rows(x.cuda(), 0.044), torch.softmax(x.float() * 0.044, -1), what="softmax rows")
+    check(ops.silu(x.cuda()), F.silu(x.float()), what="silu")
+    for t in (981.0, 501.0, 1.0):
+        check(ops.timestep_embedding(t, 3, 320, "cuda"), timestep_embedding(torch.full((3,), t), 320), what=f"temb {t}")
