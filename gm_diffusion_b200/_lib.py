@@ -20,7 +20,7 @@ F32, BF16 = 0, 1
 TMO_NONE, TMO_LINEAR, TMO_HARD_CLIP, TMO_MULOG, TMO_CUDA = 0, 1, 2, 3, 4
 HDR_EQ1, HDR_DENORM, HDR_CLAMP_OUT, HDR_GAMUT, HDR_EXP_GAIN = 1, 2, 4, 8, 16
 SCHED_LINEAR, SCHED_DDIM = 0, 1
-EPI_BIAS, EPI_ROW_BIAS, EPI_RESIDUAL, EPI_GEGLU, EPI_OUT_F32, EPI_SCALE = 1, 2, 4, 8, 16, 32
+EPI_BIAS, EPI_ROW_BIAS, EPI_RESIDUAL, EPI_GEGLU, EPI_OUT_F32, EPI_SCALE, EPI_RESIDUAL_F32 = 1, 2, 4, 8, 16, 32, 64
 
 _vp, _i64, _i32, _f32 = C.c_void_p, C.c_int64, C.c_int32, C.c_float
 
@@ -35,10 +35,10 @@ class SchedParams(C.Structure):
     _fields_ = [("eps_uncond", _vp), ("eps_cond", _vp), ("x", _vp), ("x_stash", _vp), ("hist", _vp * 3),
                 ("noise", _vp), ("x_next", _vp), ("stash_out", _vp), ("eps_out", _vp), ("unet_in_next", _vp),
                 ("concat_out", _vp), ("concat_tail", _vp), ("concat_lead", _vp), ("x0_out", _vp),
-                ("n_px", _i64), ("px_per_sample", _i64), ("unet_in_ch", _i32), ("mode", _i32),
+                ("n_px", _i64), ("px_per_sample", _i64), ("unet_in_ch", _i32), ("unet_in_dup", _i32), ("concat_dup", _i32), ("concat_self", _i32), ("mode", _i32),
                 ("use_stash", _i32), ("guidance_scale", _f32), ("guidance_rescale", _f32),
-                ("rescale_stats", _vp), ("sqrt_alpha_t", _f32), ("sqrt_1m_alpha_t", _f32), ("w", _f32 * 4),
-                ("c_sample", _f32), ("c_eps", _f32), ("ddim_sqrt_alpha_t", _f32), ("ddim_sqrt_1m_alpha_t", _f32),
+                ("rescale_stats", _vp), ("sqrt_alpha_t", _f32), ("sqrt_1m_alpha_t", _f32), ("plms_kind", _i32),
+                ("c_sample", _f32), ("c_num", _f32), ("c_denom", _f32), ("ddim_sqrt_alpha_t", _f32), ("ddim_sqrt_1m_alpha_t", _f32),
                 ("ddim_sqrt_alpha_prev", _f32), ("ddim_dir_coeff", _f32), ("ddim_sigma", _f32)]
 
 
@@ -97,8 +97,8 @@ def lib() -> C.CDLL:
     L.gmd_pack_unet_input.argtypes = [_vp, _vp, _vp, _i64, _i32, _vp]
     L.gmd_gemm_fwd.argtypes = [C.POINTER(GemmParams), _vp]
     L.gmd_conv_fwd.argtypes = [C.POINTER(ConvParams), _vp]
-    L.gmd_groupnorm_silu.argtypes = [_vp, _i32, _vp, _i32, _vp, _vp, _vp, _i32, _i32, _i32, _f32, _i32, _vp, _vp]
-    L.gmd_layernorm.argtypes = [_vp, _vp, _vp, _vp, _i64, _i32, _f32, _vp]
+    L.gmd_groupnorm_silu.argtypes = [_vp, _i32, _vp, _i32, _vp, _vp, _vp, _i32, _i32, _i32, _f32, _i32, _i32, _vp, _vp]
+    L.gmd_layernorm.argtypes = [_vp, _vp, _vp, _vp, _i64, _i32, _f32, _i32, _vp]
     L.gmd_softmax_rows.argtypes = [_vp, _vp, _i64, _i64, _f32, _vp]
     L.gmd_timestep_embedding.argtypes = [_f32, _vp, _i32, _i32, _vp]
     L.gmd_silu.argtypes = [_vp, _vp, _i64, _vp]

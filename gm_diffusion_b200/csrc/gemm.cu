@@ -227,7 +227,18 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__ 
 #pragma unroll
                 for (int j = 0; j < 16; ++j) if (j < ncol) v[j] += __ldg(rb + j);
             }
-            if (args.residual) {
+            if (args.residual && (args.flags & GMD_EPI_RESIDUAL_F32)) {
+                const float* rp = reinterpret_cast<const float*>(args.residual) + zoff_r + out_row * args.ldr + col0;
+                if (ncol == 16 && ((reinterpret_cast<uintptr_t>(rp) & 15) == 0)) {
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        float4 a = __ldg(reinterpret_cast<const float4*>(rp) + j);
+                        v[4 * j] += a.x; v[4 * j + 1] += a.y; v[4 * j + 2] += a.z; v[4 * j + 3] += a.w;
+                    }
+                } else {
+                    for (int j = 0; j < ncol; ++j) v[j] += rp[j];
+                }
+            } else if (args.residual) {
                 const __nv_bfloat16* rp = args.residual + zoff_r + out_row * args.ldr + col0;
                 if (ncol == 16 && ((reinterpret_cast<uintptr_t>(rp) & 15) == 0)) {
                     uint4 a = __ldg(reinterpret_cast<const uint4*>(rp));

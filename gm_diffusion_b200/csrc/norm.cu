@@ -1,6 +1,10 @@
-// Memory-bound companions of the tensor-core kernels: GroupNorm(+SiLU) over NHWC bf16 (two-source aware, so
-// the up-block skip concat is materialised only once, already normalised), LayerNorm over token rows,
-// row softmax, sinusoidal timestep embedding, SiLU.  All 16-byte vectorised; fp32 statistics.
+// Memory-bound companions of the tensor-core kernels: GroupNorm(+SiLU) over NHWC (two-source aware, so the
+// up-block skip concat is materialised only once, already normalised), LayerNorm over token rows, row softmax,
+// sinusoidal timestep embedding, SiLU.  16-byte vectorised; fp32 statistics; inputs bf16 or fp32 (the fp32
+// variants read the tensors that never feed an MMA directly — conv1 outputs and the transformer token stream —
+// so those are not rounded to bf16 on their way into a normalisation).
+// Reductions are performed in a FIXED order (no atomics): results are bit-reproducible run to run and
+// independent of the batch size, which is what makes image sharding across GPUs exact.
 #include "common.cuh"
 #include "../../include/gmd_b200.h"
 
@@ -15,49 +19,63 @@ __device__ __forceinline__ void unpack8(uint4 v, float (&f)[8]) {
 __device__ __forceinline__ uint4 pack8(const float (&f)[8]) {
     return make_uint4(pack_bf16x2(f[0], f[1]), pack_bf16x2(f[2], f[3]), pack_bf16x2(f[4], f[5]), pack_bf16x2(f[6], f[7]));
 }
+// 8 consecutive channels starting at element offset `off`
+template <typename T> __device__ __forceinline__ void load8(const T* p, int64_t off, float (&f)[8]);
+template <> __device__ __forceinline__ void load8<__nv_bfloat16>(const __nv_bfloat16* p, int64_t off, float (&f)[8]) {
+    unpack8(__ldg(reinterpret_cast<const uint4*>(p + off)), f);
+}
+template <> __device__ __forceinline__ void load8<float>(const float* p, int64_t off, float (&f)[8]) {
+    float4 a = __ldg(reinterpret_cast<const float4*>(p + off)), b = __ldg(reinterpret_cast<const float4*>(p + off) + 1);
+    f[0] = a.x; f[1] = a.y; f[2] = a.z; f[3] = a.w; f[4] = b.x; f[5] = b.y; f[6] = b.z; f[7] = b.w;
+}
 
 // ---------------------------------------------------------------------------------------------
 // GroupNorm.  Thread t owns channel vector cv = t % (C/8) (8 consecutive channels) and pixel lane t / (C/8).
 // ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ uint4 gn_load(const __nv_bfloat16* x0, int C0, const __nv_bfloat16* x1, int C1, int64_t px, int c) {
-    if (c < C0) return __ldg(reinterpret_cast<const uint4*>(x0 + px * C0 + c));
-    return __ldg(reinterpret_cast<const uint4*>(x1 + px * C1 + (c - C0)));
+template <typename T>
+__device__ __forceinline__ void gn_load(const T* x0, int C0, const __nv_bfloat16* x1, int C1, int64_t px, int c, float (&f)[8]) {
+    if (c < C0) load8<T>(x0, px * C0 + c, f);
+    else load8<__nv_bfloat16>(x1, px * C1 + (c - C0), f);
 }
 
-__global__ void gn_stats_kernel(const __nv_bfloat16* __restrict__ x0, int C0, const __nv_bfloat16* __restrict__ x1, int C1,
+template <typename T>
+__global__ void gn_stats_kernel(const T* __restrict__ x0, int C0, const __nv_bfloat16* __restrict__ x1, int C1,
                                 float* __restrict__ stats, int HW, int groups, int px_per_cta) {
-    extern __shared__ float s_acc[];  // [groups][2]
+    extern __shared__ float s_part[];  // [blockDim][16]: per-thread per-channel sum / sum of squares
     const int C = C0 + C1, nvec = C / 8, cg = C / groups;
     const int n = blockIdx.y;
-    for (int i = threadIdx.x; i < groups * 2; i += blockDim.x) s_acc[i] = 0.0f;
-    __syncthreads();
     const int cv = threadIdx.x % nvec, pl = threadIdx.x / nvec, P = blockDim.x / nvec;
+    float s[8] = {0, 0, 0, 0, 0, 0, 0, 0}, q[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     if (pl < P) {
-        float s[8] = {0, 0, 0, 0, 0, 0, 0, 0}, q[8] = {0, 0, 0, 0, 0, 0, 0, 0};
         const int p0 = blockIdx.x * px_per_cta;
         const int p1 = min(p0 + px_per_cta, HW);
         for (int p = p0 + pl; p < p1; p += P) {
             float f[8];
-            unpack8(gn_load(x0, C0, x1, C1, (int64_t)n * HW + p, cv * 8), f);
+            gn_load<T>(x0, C0, x1, C1, (int64_t)n * HW + p, cv * 8, f);
 #pragma unroll
             for (int k = 0; k < 8; ++k) { s[k] += f[k]; q[k] += f[k] * f[k]; }
         }
-        // fold the 8 channels into (at most a few) group slots
-        int g_prev = (cv * 8) / cg;
-        float ss = 0, qq = 0;
-#pragma unroll
-        for (int k = 0; k < 8; ++k) {
-            int g = (cv * 8 + k) / cg;
-            if (g != g_prev) { atomicAdd(&s_acc[g_prev * 2], ss); atomicAdd(&s_acc[g_prev * 2 + 1], qq); ss = qq = 0; g_prev = g; }
-            ss += s[k]; qq += q[k];
-        }
-        atomicAdd(&s_acc[g_prev * 2], ss); atomicAdd(&s_acc[g_prev * 2 + 1], qq);
     }
+#pragma unroll
+    for (int k = 0; k < 8; ++k) { s_part[threadIdx.x * 16 + k] = s[k]; s_part[threadIdx.x * 16 + 8 + k] = q[k]; }
     __syncthreads();
-    for (int i = threadIdx.x; i < groups * 2; i += blockDim.x) atomicAdd(stats + (int64_t)n * groups * 2 + i, s_acc[i]);
+    // thread g < groups folds its group's channels over all pixel lanes in a fixed order
+    if ((int)threadIdx.x < groups) {
+        const int g = threadIdx.x;
+        float ss = 0.0f, qq = 0.0f;
+        for (int l = 0; l < P; ++l)
+            for (int c = g * cg; c < (g + 1) * cg; ++c) {
+                const int t = l * nvec + (c >> 3), k = c & 7;
+                ss += s_part[t * 16 + k];
+                qq += s_part[t * 16 + 8 + k];
+            }
+        float* dst = stats + (((int64_t)n * gridDim.x + blockIdx.x) * groups + g) * 2;
+        dst[0] = ss; dst[1] = qq;
+    }
 }
 
-__global__ void gn_apply_kernel(const __nv_bfloat16* __restrict__ x0, int C0, const __nv_bfloat16* __restrict__ x1, int C1,
+template <typename T>
+__global__ void gn_apply_kernel(const T* __restrict__ x0, int C0, const __nv_bfloat16* __restrict__ x1, int C1,
                                 const float* __restrict__ stats, const float* __restrict__ gamma, const float* __restrict__ beta,
                                 __nv_bfloat16* __restrict__ out, int HW, int groups, float eps, int apply_silu, int px_per_cta) {
     const int C = C0 + C1, nvec = C / 8, cg = C / groups;
@@ -66,11 +84,19 @@ __global__ void gn_apply_kernel(const __nv_bfloat16* __restrict__ x0, int C0, co
     if (pl >= P) return;
     float sc[8], sh[8];
     const float inv_cnt = 1.0f / ((float)cg * (float)HW);
+    int g_cached = -1;
+    float mean = 0.0f, var = 0.0f;
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
         int c = cv * 8 + k, g = c / cg;
-        float mean = stats[((int64_t)n * groups + g) * 2] * inv_cnt;
-        float var = fmaxf(stats[((int64_t)n * groups + g) * 2 + 1] * inv_cnt - mean * mean, 0.0f);
+        if (g != g_cached) {
+            float s1 = 0.0f, s2 = 0.0f;
+            const float* src = stats + (int64_t)n * gridDim.x * groups * 2 + g * 2;
+            for (int ch = 0; ch < (int)gridDim.x; ++ch) { s1 += src[(int64_t)ch * groups * 2]; s2 += src[(int64_t)ch * groups * 2 + 1]; }
+            mean = s1 * inv_cnt;
+            var = fmaxf(s2 * inv_cnt - mean * mean, 0.0f);
+            g_cached = g;
+        }
         float rstd = rsqrtf(var + eps);
         float ga = gamma[c], be = beta[c];
         sc[k] = rstd * ga; sh[k] = be - mean * rstd * ga;
@@ -80,7 +106,7 @@ __global__ void gn_apply_kernel(const __nv_bfloat16* __restrict__ x0, int C0, co
     for (int p = p0 + pl; p < p1; p += P) {
         float f[8];
         const int64_t px = (int64_t)n * HW + p;
-        unpack8(gn_load(x0, C0, x1, C1, px, cv * 8), f);
+        gn_load<T>(x0, C0, x1, C1, px, cv * 8, f);
 #pragma unroll
         for (int k = 0; k < 8; ++k) {
             float y = f[k] * sc[k] + sh[k];
@@ -93,8 +119,8 @@ __global__ void gn_apply_kernel(const __nv_bfloat16* __restrict__ x0, int C0, co
 // ---------------------------------------------------------------------------------------------
 // LayerNorm: one warp per token row; the row lives in registers between the two passes.
 // ---------------------------------------------------------------------------------------------
-template <int MAXV>  // vectors (of 8) per lane
-__global__ void __launch_bounds__(256) layernorm_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ gamma,
+template <typename T, int MAXV>  // vectors (of 8) per lane
+__global__ void __launch_bounds__(256) layernorm_kernel(const T* __restrict__ x, const float* __restrict__ gamma,
                                                         const float* __restrict__ beta, __nv_bfloat16* __restrict__ out,
                                                         int64_t M, int C, float eps) {
     const int64_t row = blockIdx.x * (int64_t)(blockDim.x >> 5) + (threadIdx.x >> 5);
@@ -106,7 +132,7 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const __nv_bfloat16* __r
     for (int i = 0; i < MAXV; ++i) {
         int vi = lane + i * 32;
         if (vi < nvec) {
-            unpack8(__ldg(reinterpret_cast<const uint4*>(x + row * C) + vi), v[i]);
+            load8<T>(x, row * C + vi * 8, v[i]);
 #pragma unroll
             for (int k = 0; k < 8; ++k) s += v[i][k];
         }
@@ -203,53 +229,64 @@ __global__ void silu_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* 
 
 inline bool al16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
 
+template <typename T>
+int gn_launch(const void* x0, int C0, const void* x1, int C1, const float* gamma, const float* beta, void* out, int N, int HW, int groups,
+              float eps, int apply_silu, float* stats_ws, cudaStream_t st) {
+    const int nvec = (C0 + C1) / 8;
+    int P = 256 / nvec; if (P < 1) P = 1;
+    int threads = (nvec * P + 31) / 32 * 32;
+    // chunking depends on (HW, C) only, never on N: a sample's statistics are bit-identical for any batch size / sharding
+    int px_per_cta = (HW + 31) / 32;
+    if (px_per_cta < P * 4) px_per_cta = P * 4;
+    int chunks = (HW + px_per_cta - 1) / px_per_cta;  // <= 32
+    dim3 grid(chunks, N);
+    gn_stats_kernel<T><<<grid, threads, threads * 16 * sizeof(float), st>>>(static_cast<const T*>(x0), C0, static_cast<const __nv_bfloat16*>(x1), C1,
+                                                                            stats_ws, HW, groups, px_per_cta);
+    gn_apply_kernel<T><<<grid, threads, 0, st>>>(static_cast<const T*>(x0), C0, static_cast<const __nv_bfloat16*>(x1), C1, stats_ws, gamma, beta,
+                                                 static_cast<__nv_bfloat16*>(out), HW, groups, eps, apply_silu, px_per_cta);
+    count_launch(2);
+    return check_launch("groupnorm");
+}
+
 }  // namespace
 }  // namespace gmd
 
 extern "C" int gmd_groupnorm_silu(const void* x0, int32_t C0, const void* x1, int32_t C1, const float* gamma, const float* beta,
-                                  void* out, int32_t N, int32_t HW, int32_t groups, float eps, int32_t apply_silu, float* stats_ws,
-                                  void* stream) {
+                                  void* out, int32_t N, int32_t HW, int32_t groups, float eps, int32_t apply_silu, int32_t in_dtype,
+                                  float* stats_ws, void* stream) {
     using namespace gmd;
     if (!x0 || !gamma || !beta || !out || !stats_ws) { set_last_error("gmd_groupnorm_silu: null pointer"); return kErrInvalid; }
     if (!x1) C1 = 0;
     const int C = C0 + C1;
     if (C0 % 8 || C1 % 8 || groups <= 0 || C % groups || N <= 0 || HW <= 0) { set_last_error("gmd_groupnorm_silu: bad shape C0=%d C1=%d groups=%d", C0, C1, groups); return kErrInvalid; }
     if (!al16(x0) || !al16(x1) || !al16(out)) { set_last_error("gmd_groupnorm_silu: pointers must be 16-byte aligned"); return kErrInvalid; }
-    const int nvec = C / 8;
-    if (nvec > 1024) { set_last_error("gmd_groupnorm_silu: C=%d too large", C); return kErrUnsupported; }
+    if (C / 8 > 1024 || groups > 256) { set_last_error("gmd_groupnorm_silu: C=%d groups=%d too large", C, groups); return kErrUnsupported; }
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    int P = 256 / nvec; if (P < 1) P = 1;
-    int threads = nvec * P;
-    threads = (threads + 31) / 32 * 32;
-    // ~4 waves of CTAs over 148 SMs
-    int target_ctas = 148 * 4;
-    int chunks = (target_ctas + N - 1) / N;
-    int px_per_cta = (HW + chunks - 1) / chunks;
-    if (px_per_cta < P * 4) px_per_cta = P * 4;
-    chunks = (HW + px_per_cta - 1) / px_per_cta;
-    dim3 grid(chunks, N);
-    cudaMemsetAsync(stats_ws, 0, sizeof(float) * 2 * groups * N, st);
-    gn_stats_kernel<<<grid, threads, groups * 2 * sizeof(float), st>>>(static_cast<const __nv_bfloat16*>(x0), C0, static_cast<const __nv_bfloat16*>(x1), C1, stats_ws, HW, groups, px_per_cta);
-    gn_apply_kernel<<<grid, threads, 0, st>>>(static_cast<const __nv_bfloat16*>(x0), C0, static_cast<const __nv_bfloat16*>(x1), C1, stats_ws, gamma, beta,
-                                              static_cast<__nv_bfloat16*>(out), HW, groups, eps, apply_silu, px_per_cta);
-    count_launch(2);
-    return check_launch("groupnorm");
+    if (in_dtype == GMD_BF16) return gn_launch<__nv_bfloat16>(x0, C0, x1, C1, gamma, beta, out, N, HW, groups, eps, apply_silu, stats_ws, st);
+    if (in_dtype == GMD_F32) return gn_launch<float>(x0, C0, x1, C1, gamma, beta, out, N, HW, groups, eps, apply_silu, stats_ws, st);
+    set_last_error("gmd_groupnorm_silu: unknown in_dtype %d", in_dtype);
+    return kErrInvalid;
 }
 
-extern "C" int gmd_layernorm(const void* x, const float* gamma, const float* beta, void* out, int64_t M, int32_t C, float eps, void* stream) {
+extern "C" int gmd_layernorm(const void* x, const float* gamma, const float* beta, void* out, int64_t M, int32_t C, float eps,
+                             int32_t in_dtype, void* stream) {
     using namespace gmd;
     if (!x || !gamma || !beta || !out) { set_last_error("gmd_layernorm: null pointer"); return kErrInvalid; }
     if (C % 8 || C <= 0 || C > 8 * 32 * 8) { set_last_error("gmd_layernorm: C=%d unsupported (multiple of 8, <= 2048)", C); return kErrInvalid; }
     if (!al16(x) || !al16(out) || !al16(gamma) || !al16(beta)) { set_last_error("gmd_layernorm: pointers must be 16-byte aligned"); return kErrInvalid; }
+    if (in_dtype != GMD_BF16 && in_dtype != GMD_F32) { set_last_error("gmd_layernorm: unknown in_dtype %d", in_dtype); return kErrInvalid; }
     if (M == 0) return kOk;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     unsigned grid = (unsigned)((M + 7) / 8);
     const int nvec = C / 8;
-    auto* xp = static_cast<const __nv_bfloat16*>(x);
     auto* op = static_cast<__nv_bfloat16*>(out);
-    if (nvec <= 64) layernorm_kernel<2><<<grid, 256, 0, st>>>(xp, gamma, beta, op, M, C, eps);
-    else if (nvec <= 160) layernorm_kernel<5><<<grid, 256, 0, st>>>(xp, gamma, beta, op, M, C, eps);
-    else layernorm_kernel<8><<<grid, 256, 0, st>>>(xp, gamma, beta, op, M, C, eps);
+#define GMD_LN(T, V) layernorm_kernel<T, V><<<grid, 256, 0, st>>>(static_cast<const T*>(x), gamma, beta, op, M, C, eps)
+    if (in_dtype == GMD_BF16) {
+        if (nvec <= 64) GMD_LN(__nv_bfloat16, 2); else if (nvec <= 160) GMD_LN(__nv_bfloat16, 5); else GMD_LN(__nv_bfloat16, 8);
+    } else {
+        if (nvec <= 64) GMD_LN(float, 2); else if (nvec <= 160) GMD_LN(float, 5); else GMD_LN(float, 8);
+    }
+#undef GMD_LN
     count_launch(1);
     return check_launch("layernorm");
 }

@@ -13,9 +13,6 @@ namespace {
 
 __device__ __forceinline__ float4 ld4(const float* p, int64_t i) { return __ldg(reinterpret_cast<const float4*>(p) + i); }
 __device__ __forceinline__ void st4(float* p, int64_t i, float4 v) { reinterpret_cast<float4*>(p)[i] = v; }
-__device__ __forceinline__ float4 f4_axpby(float a, float4 x, float b, float4 y) {
-    return make_float4(a * x.x + b * y.x, a * x.y + b * y.y, a * x.z + b * y.z, a * x.w + b * y.w);
-}
 
 // write one pixel row of `ch` bf16 channels: ch0-3 = a, ch4-7 = b, rest zero
 __device__ __forceinline__ void store_row(void* dst, int64_t px, int ch, float4 a, float4 b) {
@@ -49,73 +46,108 @@ __global__ void __launch_bounds__(256) rescale_stats_kernel(const float* __restr
     }
 }
 
+// All arithmetic below uses explicit round-to-nearest intrinsics in the SAME association order as the torch
+// expressions it replaces, so that nvcc cannot contract mul+add into FMA: the fused step is then bit-identical
+// to the unfused fp32 chain (except the guidance-rescale reduction, whose summation order differs).
+#define MUL(a, b) __fmul_rn(a, b)
+#define ADD(a, b) __fadd_rn(a, b)
+#define SUB(a, b) __fsub_rn(a, b)
+#define DIV(a, b) __fdiv_rn(a, b)
+
+struct F4 { float v[4]; };
+__device__ __forceinline__ F4 ld(const float* p, int64_t i) { float4 t = ld4(p, i); return {{t.x, t.y, t.z, t.w}}; }
+__device__ __forceinline__ float4 f4(const F4& a) { return make_float4(a.v[0], a.v[1], a.v[2], a.v[3]); }
+
 __global__ void __launch_bounds__(256) sched_kernel(gmd_sched_params p) {
     int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (i >= p.n_px) return;
-    // --- CFG combine (dual_unet.py:1063-1065) ---
-    float4 e = ld4(p.eps_cond, i);
+    // --- CFG combine: u + g * (c - u)   (dual_unet.py:1063-1065) ---
+    F4 e = ld(p.eps_cond, i);
     if (p.eps_uncond) {
-        float4 u = ld4(p.eps_uncond, i);
-        float g = p.guidance_scale;
-        float4 ec = e;
-        e = make_float4(u.x + g * (ec.x - u.x), u.y + g * (ec.y - u.y), u.z + g * (ec.z - u.z), u.w + g * (ec.w - u.w));
-        if (p.guidance_rescale > 0.0f && p.rescale_stats) {
+        F4 u = ld(p.eps_uncond, i);
+        const float g = p.guidance_scale;
+        const bool rescale = p.guidance_rescale > 0.0f && p.rescale_stats;
+        float ratio = 1.0f;
+        if (rescale) {
             // rescale_noise_cfg (dual_unet.py:71-94): unbiased std over the sample
             const float* s = p.rescale_stats + (i / p.px_per_sample) * 4;
             float n = (float)(p.px_per_sample * 4);
             float var_c = (s[1] - s[0] * s[0] / n) / (n - 1.0f);
             float var_g = (s[3] - s[2] * s[2] / n) / (n - 1.0f);
-            float ratio = sqrtf(var_c) / sqrtf(var_g);
-            float phi = p.guidance_rescale;
-            float f = phi * ratio + (1.0f - phi);
-            e = make_float4(e.x * f, e.y * f, e.z * f, e.w * f);
+            ratio = DIV(sqrtf(var_c), sqrtf(var_g));
         }
-    }
-    float4 x = ld4(p.x, i);
-    // --- x0 prediction from the PRE-step latents and the loop's t (dual_unet.py:1072-1075) ---
-    float4 x0;
-    {
-        float a = p.sqrt_1m_alpha_t, inv = p.sqrt_alpha_t;
-        x0 = make_float4((x.x - a * e.x) / inv, (x.y - a * e.y) / inv, (x.z - a * e.z) / inv, (x.w - a * e.w) / inv);
-    }
-    if (p.x0_out) st4(p.x0_out, i, x0);
-    if (p.stash_out) st4(p.stash_out, i, x);
-    if (p.eps_out) st4(p.eps_out, i, e);
-    // --- scheduler update ---
-    float4 xn;
-    if (p.mode == GMD_SCHED_LINEAR) {
-        // eps' = sum_k w_k e_k   (PLMS Adams-Bashforth / averaging), then x' = c_sample * x_src - c_eps * eps'
-        float4 ep = make_float4(p.w[0] * e.x, p.w[0] * e.y, p.w[0] * e.z, p.w[0] * e.w);
 #pragma unroll
-        for (int k = 0; k < 3; ++k) {
-            if (p.hist[k]) {
-                float4 h = ld4(p.hist[k], i);
-                float w = p.w[k + 1];
-                ep.x += w * h.x; ep.y += w * h.y; ep.z += w * h.z; ep.w += w * h.w;
+        for (int k = 0; k < 4; ++k) {
+            float c = e.v[k];
+            float cfg = ADD(u.v[k], MUL(g, SUB(c, u.v[k])));
+            if (rescale) {
+                // phi * (cfg * (std_text/std_cfg)) + (1 - phi) * cfg
+                float phi = p.guidance_rescale;
+                cfg = ADD(MUL(phi, MUL(cfg, ratio)), MUL(SUB(1.0f, phi), cfg));
             }
-        }
-        float4 xs = p.use_stash ? ld4(p.x_stash, i) : x;
-        xn = f4_axpby(p.c_sample, xs, -p.c_eps, ep);
-    } else {
-        // DDIM: x0 = (x - sqrt(1-a_t) e)/sqrt(a_t); dir = sqrt(1-a_prev-sigma^2) e; x' = sqrt(a_prev) x0 + dir (+ sigma z)
-        float a = p.ddim_sqrt_1m_alpha_t, inv = p.ddim_sqrt_alpha_t;
-        float4 p0 = make_float4((x.x - a * e.x) / inv, (x.y - a * e.y) / inv, (x.z - a * e.z) / inv, (x.w - a * e.w) / inv);
-        float4 dir = make_float4(p.ddim_dir_coeff * e.x, p.ddim_dir_coeff * e.y, p.ddim_dir_coeff * e.z, p.ddim_dir_coeff * e.w);
-        xn = make_float4(p.ddim_sqrt_alpha_prev * p0.x + dir.x, p.ddim_sqrt_alpha_prev * p0.y + dir.y,
-                         p.ddim_sqrt_alpha_prev * p0.z + dir.z, p.ddim_sqrt_alpha_prev * p0.w + dir.w);
-        if (p.noise && p.ddim_sigma != 0.0f) {
-            float4 z = ld4(p.noise, i);
-            xn.x += p.ddim_sigma * z.x; xn.y += p.ddim_sigma * z.y; xn.z += p.ddim_sigma * z.z; xn.w += p.ddim_sigma * z.w;
+            e.v[k] = cfg;
         }
     }
-    st4(p.x_next, i, xn);
+    F4 x = ld(p.x, i);
+    // --- x0 = (x - sqrt(1-a_t) * eps) / sqrt(a_t) from the PRE-step latents and the loop's t (dual_unet.py:1072-1075) ---
+    F4 x0;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) x0.v[k] = DIV(SUB(x.v[k], MUL(p.sqrt_1m_alpha_t, e.v[k])), p.sqrt_alpha_t);
+    if (p.x0_out) st4(p.x0_out, i, f4(x0));
+    if (p.stash_out) st4(p.stash_out, i, f4(x));
+    if (p.eps_out) st4(p.eps_out, i, f4(e));
+    // --- scheduler update ---
+    F4 xn;
+    if (p.mode == GMD_SCHED_LINEAR) {
+        // diffusers PNDMScheduler.step_plms: the multistep combination, written exactly as the reference expressions
+        F4 h0, h1, h2, ep;
+        if (p.hist[0]) h0 = ld(p.hist[0], i);
+        if (p.hist[1]) h1 = ld(p.hist[1], i);
+        if (p.hist[2]) h2 = ld(p.hist[2], i);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            float m = e.v[k];
+            switch (p.plms_kind) {
+                case 1: m = DIV(ADD(m, h0.v[k]), 2.0f); break;                                          // (eps + ets[-1]) / 2
+                case 2: m = DIV(SUB(MUL(3.0f, m), h0.v[k]), 2.0f); break;                                // (3 e1 - e2) / 2
+                case 3: m = DIV(ADD(SUB(MUL(23.0f, m), MUL(16.0f, h0.v[k])), MUL(5.0f, h1.v[k])), 12.0f); break;
+                case 4: m = MUL(0.041666666666666664f,
+                                SUB(ADD(SUB(MUL(55.0f, m), MUL(59.0f, h0.v[k])), MUL(37.0f, h1.v[k])), MUL(9.0f, h2.v[k])));
+                        break;
+                default: break;
+            }
+            ep.v[k] = m;
+        }
+        F4 xs = p.use_stash ? ld(p.x_stash, i) : x;
+        // sample_coeff * sample - (a_prev - a_t) * model_output / denom
+#pragma unroll
+        for (int k = 0; k < 4; ++k) xn.v[k] = SUB(MUL(p.c_sample, xs.v[k]), DIV(MUL(p.c_num, ep.v[k]), p.c_denom));
+    } else {
+        // diffusers DDIMScheduler.step: pred_x0, direction, prev (+ sigma * noise)
+        F4 z;
+        const bool noisy = p.noise && p.ddim_sigma != 0.0f;
+        if (noisy) z = ld(p.noise, i);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            float p0 = DIV(SUB(x.v[k], MUL(p.ddim_sqrt_1m_alpha_t, e.v[k])), p.ddim_sqrt_alpha_t);
+            float dir = MUL(p.ddim_dir_coeff, e.v[k]);
+            float v = ADD(MUL(p.ddim_sqrt_alpha_prev, p0), dir);
+            if (noisy) v = ADD(v, MUL(p.ddim_sigma, z.v[k]));
+            xn.v[k] = v;
+        }
+    }
+    st4(p.x_next, i, f4(xn));
     // --- fused layout outputs (replace torch.cat at dual_unet.py:1045,1080 / gm.py:1045) ---
     float4 zero = make_float4(0, 0, 0, 0);
-    if (p.unet_in_next) store_row(p.unet_in_next, i, p.unet_in_ch, xn, zero);
+    if (p.unet_in_next) {
+        store_row(p.unet_in_next, i, p.unet_in_ch, f4(xn), zero);
+        if (p.unet_in_dup == 2) store_row(p.unet_in_next, i + p.n_px, p.unet_in_ch, f4(xn), zero);
+    }
     if (p.concat_out) {
-        float4 lead = p.concat_lead ? ld4(p.concat_lead, i) : x0;
-        float4 tail = p.concat_tail ? ld4(p.concat_tail, i) : zero;
+        float4 lead = p.concat_lead ? ld4(p.concat_lead, i) : f4(x0);
+        float4 tail = p.concat_self ? f4(xn) : (p.concat_tail ? ld4(p.concat_tail, i) : zero);
         store_row(p.concat_out, i, p.unet_in_ch, lead, tail);
+        if (p.concat_dup == 2) store_row(p.concat_out, i + p.n_px, p.unet_in_ch, lead, tail);
     }
 }
 
@@ -148,7 +180,9 @@ inline bool al16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) =
 
 extern "C" int gmd_cfg_sched_step(const gmd_sched_params* p, void* stream) {
     using namespace gmd;
-    if (!p || !p->eps_cond || !p->x || !p->x_next) { set_last_error("gmd_cfg_sched_step: null eps/x"); return kErrInvalid; }
+    if (!p) { set_last_error("gmd_cfg_sched_step: null params"); return kErrInvalid; }
+    if (p->n_px == 0) return kOk;
+    if (!p->eps_cond || !p->x || !p->x_next) { set_last_error("gmd_cfg_sched_step: null eps/x"); return kErrInvalid; }
     if (p->n_px < 0) { set_last_error("gmd_cfg_sched_step: negative n_px"); return kErrInvalid; }
     if (p->use_stash && !p->x_stash) { set_last_error("gmd_cfg_sched_step: use_stash without x_stash"); return kErrInvalid; }
     if ((p->unet_in_next || p->concat_out) && (p->unet_in_ch < 8 || p->unet_in_ch % 8)) {
@@ -159,7 +193,12 @@ extern "C" int gmd_cfg_sched_step(const gmd_sched_params* p, void* stream) {
                           p->stash_out, p->eps_out, p->unet_in_next, p->concat_out, p->concat_tail, p->concat_lead, p->x0_out};
     for (const void* q : ptrs)
         if (!al16(q)) { set_last_error("gmd_cfg_sched_step: pointers must be 16-byte aligned"); return kErrInvalid; }
-    if (p->n_px == 0) return kOk;
+    if (p->mode == GMD_SCHED_LINEAR) {
+        if (p->plms_kind < 0 || p->plms_kind > 4) { set_last_error("gmd_cfg_sched_step: plms_kind %d out of range", p->plms_kind); return kErrInvalid; }
+        const int need = p->plms_kind == 0 ? 0 : p->plms_kind <= 2 ? 1 : p->plms_kind - 1;
+        for (int k = 0; k < need; ++k)
+            if (!p->hist[k]) { set_last_error("gmd_cfg_sched_step: plms_kind %d needs %d history tensors", p->plms_kind, need); return kErrInvalid; }
+    }
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     if (p->eps_uncond && p->guidance_rescale > 0.0f) {
         if (!p->rescale_stats || p->px_per_sample <= 0 || p->n_px % p->px_per_sample) {

@@ -53,8 +53,8 @@ def gemm(a: torch.Tensor, w: torch.Tensor, *, bias: Optional[torch.Tensor] = Non
         flags |= L.EPI_ROW_BIAS
         p.row_bias, p.ld_row_bias, p.rows_per_sample = row_bias.data_ptr(), row_bias.stride(0), rows_per_sample
     if residual is not None:
-        assert residual.dtype == bf16 and residual.stride(-1) == 1
-        flags |= L.EPI_RESIDUAL
+        assert residual.dtype in (bf16, torch.float32) and residual.stride(-1) == 1
+        flags |= L.EPI_RESIDUAL | (L.EPI_RESIDUAL_F32 if residual.dtype == torch.float32 else 0)
         p.residual, p.ldr = residual.data_ptr(), residual.stride(-2)
     if geglu:
         flags |= L.EPI_GEGLU
@@ -99,8 +99,8 @@ def conv2d(x: torch.Tensor, w: torch.Tensor, cout: int, *, ksize: int = 3, strid
         flags |= L.EPI_ROW_BIAS
         p.row_bias, p.ld_row_bias = row_bias.data_ptr(), row_bias.stride(0)
     if residual is not None:
-        assert residual.dtype == bf16 and residual.is_contiguous()
-        flags |= L.EPI_RESIDUAL
+        assert residual.dtype in (bf16, torch.float32) and residual.is_contiguous()
+        flags |= L.EPI_RESIDUAL | (L.EPI_RESIDUAL_F32 if residual.dtype == torch.float32 else 0)
         p.residual = residual.data_ptr()
     if out.dtype == torch.float32:
         flags |= L.EPI_OUT_F32
@@ -119,9 +119,11 @@ def groupnorm_silu(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, *, 
     if out is None:
         out = torch.empty(x.shape[:-1] + (C0 + C1,), dtype=bf16, device=x.device)
     if stats_ws is None:
-        stats_ws = torch.empty(N * groups * 2, dtype=torch.float32, device=x.device)
+        stats_ws = torch.empty(N * 32 * groups * 2, dtype=torch.float32, device=x.device)
+    assert stats_ws.numel() >= N * 32 * groups * 2, "groupnorm workspace too small"
     L.check(L.lib().gmd_groupnorm_silu(x.data_ptr(), C0, L.ptr(x1), C1, gamma.data_ptr(), beta.data_ptr(), out.data_ptr(), N, HW,
-                                       groups, float(eps), int(silu), stats_ws.data_ptr(), L.current_stream()), "gmd_groupnorm_silu")
+                                       groups, float(eps), int(silu), L.F32 if x.dtype == torch.float32 else L.BF16, stats_ws.data_ptr(),
+                                       L.current_stream()), "gmd_groupnorm_silu")
     return out
 
 
@@ -130,9 +132,9 @@ def layernorm(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, eps: flo
     Cc = x.shape[-1]
     M = x.numel() // Cc
     if out is None:
-        out = torch.empty_like(x)
-    L.check(L.lib().gmd_layernorm(x.data_ptr(), gamma.data_ptr(), beta.data_ptr(), out.data_ptr(), M, Cc, float(eps), L.current_stream()),
-            "gmd_layernorm")
+        out = torch.empty(x.shape, dtype=bf16, device=x.device)
+    L.check(L.lib().gmd_layernorm(x.data_ptr(), gamma.data_ptr(), beta.data_ptr(), out.data_ptr(), M, Cc, float(eps),
+                                  L.F32 if x.dtype == torch.float32 else L.BF16, L.current_stream()), "gmd_layernorm")
     return out
 
 

@@ -1,0 +1,241 @@
+"""Drop-in for gm_diffusion/pipelines/stable_diffusion_dual_unet.py: `StableDiffusionDualUNetPipeline` with the
+reference's `__call__` signature (:784-812) and return convention (:1122-1132), executing the joint SDR /
+gain-map denoising loop (:1040-1093) on hand-written sm_100a kernels:
+
+    per step:  SDR UNet (2B under CFG)  ->  fused CFG + x0 + PLMS/DDIM + concat  ->  GM UNet (B)  ->  fused step
+
+Differences from the reference, all deliberate:
+  * GM-branch text conditioning uses the batch-correct conditional slice
+    (`prompt_embeds[negative_prompt_embeds.shape[0]:]`, visualize_latents.py:274); identical to the reference's
+    `prompt_embeds[1:]` (:1086) at batch 1, and the only form that works for batch > 1.
+  * `output_type="latent"` returns `(latents, gm_latents)` exactly like the reference.  Other output types are broken in
+    the reference (:1118-1131 index the batch of a single SDR decode); here they decode BOTH latents:
+    "pt"/"np"/"pil" -> `(sdr_images, gm_images)`, and "hdr" additionally applies Eq.(1) on the GPU and returns
+    `(hdr [B,H,W,3] fp32, sdr, gm)`.
+  * cross-attention K/V and the timestep-embedding MLP are hoisted out of the loop; latents / PLMS history / CFG math
+    stay in fp32 regardless of the UNet compute dtype (bf16).
+"""
+from __future__ import annotations
+
+from typing import Any, Callable, Dict, List, Optional, Union
+
+import torch
+
+from .. import _lib as L
+from .. import schedulers as S
+from ..stage1 import tone_mapping as TM
+from ._common import (PipelineBase, StableDiffusionPipelineOutput, as_b200_unet, bf16, randn_tensor, retrieve_timesteps)
+
+
+class _Workspace:
+    """Static device buffers for one (batch, h, w): everything the loop touches has a fixed address (CUDA graphs)."""
+
+    def __init__(self, B, h, w, cfg_mult, device, temb_cols_sdr, temb_cols_gm):
+        n_px = B * h * w
+        self.B, self.h, self.w, self.n_px = B, h, w, n_px
+        self.sdr = S.BranchState(n_px, device)
+        self.gm = S.BranchState(n_px, device)
+        self.unet_in = torch.zeros((cfg_mult * B, h, w, 8), dtype=bf16, device=device)
+        self.gm_in = torch.zeros((B, h, w, 8), dtype=bf16, device=device)
+        self.eps_sdr = torch.empty((cfg_mult * B, h, w, 4), dtype=torch.float32, device=device)
+        self.eps_gm = torch.empty((B, h, w, 4), dtype=torch.float32, device=device)
+        self.temb_sdr = torch.empty((1, temb_cols_sdr), dtype=torch.float32, device=device)
+        self.temb_gm = torch.empty((1, temb_cols_gm), dtype=torch.float32, device=device)
+        self.rescale_ws = torch.zeros(B * 4, dtype=torch.float32, device=device)
+        self.kv_sdr: Optional[List[torch.Tensor]] = None
+        self.kv_gm: Optional[List[torch.Tensor]] = None
+
+    def set_context(self, which: str, kv: List[torch.Tensor]):
+        cur = getattr(self, which)
+        if cur is None or any(a.shape != b.shape for a, b in zip(cur, kv)):
+            setattr(self, which, kv)
+        else:
+            for a, b in zip(cur, kv):
+                a.copy_(b)
+
+
+class StableDiffusionDualUNetPipeline(PipelineBase):
+    model_cpu_offload_seq = "text_encoder->image_encoder->unet->vae"
+
+    def __init__(self, vae, text_encoder, tokenizer, unet, gm_unet, scheduler, safety_checker=None, feature_extractor=None,
+                 image_encoder=None, requires_safety_checker: bool = True, device="cuda"):
+        """Constructor kwargs as stable_diffusion_dual_unet.py:202-214.  `unet` / `gm_unet` may be `B200UNet` objects or
+        any module exposing a diffusers UNet2DConditionModel state_dict (repacked once, here)."""
+        self._init_common(vae, text_encoder, tokenizer, scheduler, safety_checker, feature_extractor, image_encoder,
+                          requires_safety_checker, device)
+        self.unet = as_b200_unet(unet, self.device)
+        self.gm_unet = as_b200_unet(gm_unet, self.device)
+        if self.unet.in_channels != 4 or self.gm_unet.in_channels != 8:
+            raise ValueError(f"dual pipeline expects a 4-channel SDR UNet and an 8-channel GM UNet, got "
+                             f"{self.unet.in_channels} / {self.gm_unet.in_channels}")
+        self.gm_scheduler = None
+        self._ws: Dict[Any, _Workspace] = {}
+
+    # ------------------------------------------------------------------------------------------------------------
+    @torch.no_grad()
+    def __call__(
+        self,
+        prompt: Union[str, List[str]] = None,
+        height: Optional[int] = None,
+        width: Optional[int] = None,
+        num_inference_steps: int = 50,
+        timesteps: List[int] = None,
+        sigmas: List[float] = None,
+        guidance_scale: float = 7.5,
+        negative_prompt: Optional[Union[str, List[str]]] = None,
+        num_images_per_prompt: Optional[int] = 1,
+        eta: float = 0.0,
+        generator: Optional[Union[torch.Generator, List[torch.Generator]]] = None,
+        latents: Optional[torch.Tensor] = None,
+        prompt_embeds: Optional[torch.Tensor] = None,
+        negative_prompt_embeds: Optional[torch.Tensor] = None,
+        ip_adapter_image=None,
+        ip_adapter_image_embeds: Optional[List[torch.Tensor]] = None,
+        output_type: Optional[str] = "pil",
+        return_dict: bool = True,
+        cross_attention_kwargs: Optional[Dict[str, Any]] = None,
+        guidance_rescale: float = 0.0,
+        clip_skip: Optional[int] = None,
+        callback_on_step_end: Optional[Callable] = None,
+        callback_on_step_end_tensor_inputs: List[str] = ["latents"],
+        **kwargs,
+    ):
+        callback = kwargs.pop("callback", None)          # legacy callback(step, t, latents), dual_unet.py:1108-1110
+        callback_steps = kwargs.pop("callback_steps", None)
+        qmax = kwargs.pop("qmax", 99.0)                  # only used by the output_type="hdr" extension
+        hdr_eps = kwargs.pop("hdr_eps", 1 / 64)
+        # unknown kwargs (e.g. noise_level=0.0, formal_baseline.py:221) are swallowed like the reference's **kwargs (:811)
+
+        # 0. defaults (:930-932): unet.config.sample_size (64) * vae_scale_factor
+        height = height or 64 * self.vae_scale_factor
+        width = width or 64 * self.vae_scale_factor
+        # 1. check inputs (:934-945)
+        self.check_inputs(prompt, height, width, callback_steps, negative_prompt, prompt_embeds, negative_prompt_embeds,
+                          ip_adapter_image, ip_adapter_image_embeds, callback_on_step_end_tensor_inputs)
+        if cross_attention_kwargs:
+            raise NotImplementedError("cross_attention_kwargs (LoRA scale) are accepted at the signature level only")
+        self._guidance_scale = guidance_scale
+        self._guidance_rescale = guidance_rescale
+        self._clip_skip = clip_skip
+        self._cross_attention_kwargs = cross_attention_kwargs
+        self._interrupt = False
+        # 2. batch size (:953-959)
+        if prompt is not None and isinstance(prompt, str):
+            batch_size = 1
+        elif prompt is not None and isinstance(prompt, list):
+            batch_size = len(prompt)
+        else:
+            batch_size = prompt_embeds.shape[0]
+        device = self.device
+        # 3. encode prompt (:968-984)
+        prompt_embeds, negative_prompt_embeds = self.encode_prompt(
+            prompt, device, num_images_per_prompt, self.do_classifier_free_guidance, negative_prompt,
+            prompt_embeds=prompt_embeds, negative_prompt_embeds=negative_prompt_embeds, clip_skip=self.clip_skip)
+        out_dtype = prompt_embeds.dtype
+        do_cfg = self.do_classifier_free_guidance
+        B = batch_size * num_images_per_prompt
+        # 4. timesteps (:996-998)
+        timesteps, num_inference_steps = retrieve_timesteps(self.scheduler, num_inference_steps, device, timesteps, sigmas)
+        # 5. latents (:1002-1012); gm_latents starts as a clone of the SDR noise
+        latents = self.prepare_latents(B, 4, height, width, torch.float32, device, generator, latents)
+        h, w = latents.shape[-2:]
+        self._num_timesteps = len(timesteps)
+        self.gm_scheduler = S.clone_scheduler(self.scheduler)  # :1036-1037
+
+        ws = self._workspace(B, h, w, 2 if do_cfg else 1)
+        stream = L.current_stream()
+        lat32 = latents.to(device=device, dtype=torch.float32).contiguous()
+        L.check(L.lib().gmd_latents_nchw_to_px(lat32.data_ptr(), ws.sdr.x.data_ptr(), B, h * w, stream), "gmd_latents_nchw_to_px")
+        ws.gm.x.copy_(ws.sdr.x)
+        ws.sdr.reset(); ws.gm.reset()
+        L.check(L.lib().gmd_pack_unet_input(ws.sdr.x.data_ptr(), None, ws.unet_in.data_ptr(), ws.n_px, 8, stream), "gmd_pack_unet_input")
+        if do_cfg:
+            ws.unet_in[B:].copy_(ws.unet_in[:B])  # :1045 torch.cat([latents] * 2); later steps: the fused kernel writes both halves
+        # step-invariant work hoisted out of the loop: text K/V per layer, timestep-embedding tables
+        sdr_ctx = torch.cat([negative_prompt_embeds, prompt_embeds]) if do_cfg else prompt_embeds  # :983-984
+        gm_ctx = prompt_embeds  # conditional half only, no CFG on the GM branch (:1086; batch-correct form VIS:274)
+        ws.set_context("kv_sdr", self.unet.project_context(sdr_ctx))
+        ws.set_context("kv_gm", self.gm_unet.project_context(gm_ctx))
+        ts = [int(t) for t in timesteps]
+        table_sdr = self.unet.timestep_table(ts)
+        table_gm = self.gm_unet.timestep_table(ts)
+        run_sdr = self._unet_runner(("sdr", B, h, w, do_cfg), self.unet, ws.unet_in, ws.temb_sdr, ws.kv_sdr, ws.eps_sdr)
+        run_gm = self._unet_runner(("gm", B, h, w), self.gm_unet, ws.gm_in, ws.temb_gm, ws.kv_gm, ws.eps_gm)
+        extra = self.prepare_extra_step_kwargs(generator, eta)
+        eps_u = ws.eps_sdr[:B].reshape(-1, 4) if do_cfg else None
+        eps_c = (ws.eps_sdr[B:] if do_cfg else ws.eps_sdr).reshape(-1, 4)
+        eps_g = ws.eps_gm.reshape(-1, 4)
+
+        # 7. denoising loop (:1040-1113)
+        with self.progress_bar(total=num_inference_steps) as progress_bar:
+            for i, t in enumerate(ts):
+                if self.interrupt:
+                    continue
+                ws.temb_sdr.copy_(table_sdr[i:i + 1])
+                ws.temb_gm.copy_(table_gm[i:i + 1])
+                run_sdr()                                                       # :1052-1060  SDR eps (uncond | cond)
+                plan = self.scheduler.plan_step(t, extra["eta"])
+                if plan.needs_noise:                                            # DDIM eta > 0: SDR draw first, then GM (§8a-Q7)
+                    ws.sdr.noise = self._draw_noise(B, h, w, generator)
+                S.fused_step(plan, ws.sdr, eps_c, eps_u, guidance_scale=guidance_scale,        # :1063-1080
+                             guidance_rescale=guidance_rescale if do_cfg else 0.0, px_per_sample=h * w,
+                             x0_coeffs=self.scheduler.x0_coeffs(t), unet_in_next=ws.unet_in, unet_in_dup=2 if do_cfg else 1,
+                             concat_out=ws.gm_in, concat_tail=ws.gm.x, rescale_ws=ws.rescale_ws)
+                run_gm()                                                        # :1083-1092  GM eps, no CFG
+                gplan = self.gm_scheduler.plan_step(t, extra["eta"])
+                if gplan.needs_noise:
+                    ws.gm.noise = self._draw_noise(B, h, w, generator)
+                S.fused_step(gplan, ws.gm, eps_g, x0_coeffs=self.gm_scheduler.x0_coeffs(t))    # :1093
+                progress_bar.update()
+                if callback is not None and callback_steps and i % callback_steps == 0:
+                    callback(i, t, self._latents_nchw(ws.sdr.x, B, h, w))
+
+        sdr_lat = self._latents_nchw(ws.sdr.x, B, h, w)
+        gm_lat = self._latents_nchw(ws.gm.x, B, h, w)
+        if output_type == "latent":
+            return (sdr_lat.to(out_dtype), gm_lat.to(out_dtype))  # :1122-1132
+        return self._decode_outputs(ws, B, h, w, output_type, qmax, hdr_eps)
+
+    # ------------------------------------------------------------------------------------------------------------
+    def _workspace(self, B, h, w, cfg_mult) -> _Workspace:
+        key = (B, h, w, cfg_mult)
+        ws = self._ws.get(key)
+        if ws is None:
+            ws = _Workspace(B, h, w, cfg_mult, self.device, self.unet.w_temb.shape[0], self.gm_unet.w_temb.shape[0])
+            self._ws[key] = ws
+        return ws
+
+    def _draw_noise(self, B, h, w, generator):
+        z = randn_tensor((B, 4, h, w), generator=generator, device=self.device, dtype=torch.float32)
+        out = torch.empty((B * h * w, 4), dtype=torch.float32, device=self.device)
+        L.check(L.lib().gmd_latents_nchw_to_px(z.contiguous().data_ptr(), out.data_ptr(), B, h * w, L.current_stream()))
+        return out
+
+    def _latents_nchw(self, x_px, B, h, w):
+        out = torch.empty((B, 4, h, w), dtype=torch.float32, device=self.device)
+        L.check(L.lib().gmd_latents_px_to_nchw(x_px.data_ptr(), out.data_ptr(), B, h * w, L.current_stream()), "gmd_latents_px_to_nchw")
+        return out
+
+    def _decode_outputs(self, ws, B, h, w, output_type, qmax, hdr_eps):
+        if self.vae is None:
+            raise ValueError(f"output_type={output_type!r} needs a VAE; pass output_type='latent' or construct the pipeline with one")
+        sdr_img = self.vae.decode_px(ws.sdr.x, B, h, w)   # bf16 NHWC in [-1,1]
+        gm_img = self.vae.decode_px(ws.gm.x, B, h, w)
+        if output_type == "hdr":
+            # de-normalise + Eq.(1) in ONE kernel (generate_hdr.py:227,232,256-265 run this on the host in numpy; no clamp there)
+            hdr, _ = TM.reconstruct_hdr(sdr_img, gm_img, qmax=qmax, eps=hdr_eps, denormalize=True, clamp=False, channels_last=True)
+            return hdr, sdr_img, gm_img
+        outs = []
+        for img in (sdr_img, gm_img):
+            x = (img.float() / 2 + 0.5).clamp(0, 1)       # VaeImageProcessor.postprocess de-normalise
+            if output_type == "pt":
+                outs.append(x.permute(0, 3, 1, 2))
+            elif output_type == "np":
+                outs.append(x.cpu().numpy())
+            elif output_type == "pil":
+                from PIL import Image
+                arr = (x.cpu().numpy() * 255).round().astype("uint8")
+                outs.append([Image.fromarray(a) for a in arr])
+            else:
+                raise ValueError(f"unknown output_type {output_type!r}")
+        return tuple(outs)

@@ -33,10 +33,11 @@ def _sd15_config(**over):
 class StepPlan:
     """Everything kernel (c) needs for one scheduler update, as host scalars."""
     mode: int = L.SCHED_LINEAR
-    w: tuple = (1.0, 0.0, 0.0, 0.0)     # eps' = w0*eps + w1*hist0 + w2*hist1 + w3*hist2
+    plms_kind: int = 0                   # multistep combination (include/gmd_b200.h)
     n_hist: int = 0                      # history tensors read
     c_sample: float = 1.0
-    c_eps: float = 0.0
+    c_num: float = 0.0
+    c_denom: float = 1.0
     use_stash: bool = False              # PLMS counter 1: update from the stashed sample
     write_stash: bool = False            # PLMS counter 0
     push_eps: bool = True                # append the (post-CFG) eps to the history ring
@@ -112,7 +113,7 @@ class PNDMScheduler(_SchedulerBase):
         b_t, b_p = 1 - a_t, 1 - a_p
         sample_coeff = (a_p / a_t) ** 0.5
         denom = a_t * b_p ** 0.5 + (a_t * b_t * a_p) ** 0.5
-        return float(sample_coeff), float((a_p - a_t) / denom)
+        return float(sample_coeff), float(a_p - a_t), float(denom)
 
     def plan_step(self, timestep: int, eta: float = 0.0) -> StepPlan:
         timestep = int(timestep)
@@ -127,16 +128,16 @@ class PNDMScheduler(_SchedulerBase):
             timestep = timestep + ratio
             plan.push_eps = False
         if self.n_ets == 1 and self.counter == 0:
-            plan.w, plan.n_hist, plan.write_stash = (1.0, 0.0, 0.0, 0.0), 0, True
+            plan.plms_kind, plan.n_hist, plan.write_stash = 0, 0, True
         elif self.n_ets == 1 and self.counter == 1:
-            plan.w, plan.n_hist, plan.use_stash = (0.5, 0.5, 0.0, 0.0), 1, True
+            plan.plms_kind, plan.n_hist, plan.use_stash = 1, 1, True
         elif self.n_ets == 2:
-            plan.w, plan.n_hist = (1.5, -0.5, 0.0, 0.0), 1
+            plan.plms_kind, plan.n_hist = 2, 1
         elif self.n_ets == 3:
-            plan.w, plan.n_hist = (23 / 12, -16 / 12, 5 / 12, 0.0), 2
+            plan.plms_kind, plan.n_hist = 3, 2
         else:
-            plan.w, plan.n_hist = (55 / 24, -59 / 24, 37 / 24, -9 / 24), 3
-        plan.c_sample, plan.c_eps = self._prev_coeffs(timestep, prev)
+            plan.plms_kind, plan.n_hist = 4, 3
+        plan.c_sample, plan.c_num, plan.c_denom = self._prev_coeffs(timestep, prev)
         self.counter += 1
         return plan
 
@@ -193,7 +194,7 @@ def fused_step(plan: StepPlan, state: BranchState, eps_cond: torch.Tensor, eps_u
                guidance_scale: float = 1.0, guidance_rescale: float = 0.0, px_per_sample: int = 0, x0_coeffs=(1.0, 0.0),
                unet_in_next: Optional[torch.Tensor] = None, concat_out: Optional[torch.Tensor] = None,
                concat_tail: Optional[torch.Tensor] = None, concat_lead: Optional[torch.Tensor] = None,
-               x0_out: Optional[torch.Tensor] = None, rescale_ws: Optional[torch.Tensor] = None, stream: Optional[int] = None) -> None:
+               x0_out: Optional[torch.Tensor] = None, unet_in_dup: int = 1, concat_dup: int = 1, concat_self: bool = False, rescale_ws: Optional[torch.Tensor] = None, stream: Optional[int] = None) -> None:
     """One launch of `gmd_cfg_sched_step` (csrc/sched.cu) for one branch; updates `state` in place."""
     p = L.SchedParams()
     p.eps_uncond, p.eps_cond = L.ptr(eps_uncond), eps_cond.data_ptr()
@@ -218,14 +219,14 @@ def fused_step(plan: StepPlan, state: BranchState, eps_cond: torch.Tensor, eps_u
         if t is not None:
             ch = t.shape[-1]
     p.unet_in_ch = ch or 8
+    p.unet_in_dup, p.concat_dup, p.concat_self = unet_in_dup, concat_dup, int(concat_self)
     p.n_px, p.px_per_sample = state.n_px, px_per_sample or state.n_px
     p.mode, p.use_stash = plan.mode, int(plan.use_stash)
     p.guidance_scale, p.guidance_rescale = float(guidance_scale), float(guidance_rescale)
     p.rescale_stats = L.ptr(rescale_ws)
     p.sqrt_alpha_t, p.sqrt_1m_alpha_t = x0_coeffs
-    for k in range(4):
-        p.w[k] = plan.w[k]
-    p.c_sample, p.c_eps = plan.c_sample, plan.c_eps
+    p.plms_kind = plan.plms_kind
+    p.c_sample, p.c_num, p.c_denom = plan.c_sample, plan.c_num, plan.c_denom
     (p.ddim_sqrt_alpha_t, p.ddim_sqrt_1m_alpha_t, p.ddim_sqrt_alpha_prev, p.ddim_dir_coeff, p.ddim_sigma) = plan.ddim
     L.check(L.lib().gmd_cfg_sched_step(C.byref(p), L.current_stream() if stream is None else stream), "gmd_cfg_sched_step")
     if slot is not None:

@@ -41,6 +41,10 @@ def _run(sdr, gm, *, flags, tmo, qmax, eps, mu, want_hdr, want_tmo, want_minmax,
         p.n_px, p.batch = sdr.numel() // 3, 1
     else:
         p.n_px, p.batch = sdr.numel(), 1
+    if sdr.numel() == 0:  # empty input: nothing to launch
+        e = torch.empty(sdr.shape, dtype=torch.float32, device=sdr.device)
+        mm0 = torch.tensor([0x7F800000, -2139095041], dtype=torch.int32, device=sdr.device) if want_minmax else None  # (+inf, -inf)
+        return (e if want_hdr else None), (e.clone() if want_tmo else None), mm0
     hdr = torch.empty(sdr.shape, dtype=torch.float32, device=sdr.device) if want_hdr else None
     out = torch.empty(sdr.shape, dtype=torch.float32, device=sdr.device) if want_tmo else None
     mm = torch.empty(2, dtype=torch.int32, device=sdr.device) if want_minmax else None

@@ -1,0 +1,249 @@
+"""B200 executor for the SD1.5-architecture UNets the reference pipelines call
+(`self.unet(...)` stable_diffusion_dual_unet.py:1052-1060, `self.gm_unet(...)` :1083-1092; architecture =
+diffusers UNet2DConditionModel with the config literal scripts/inference/generate_hdr.py:116-135).
+
+Weights are ingested from a diffusers-style state_dict (OIHW convs, [out,in] linears) and repacked ONCE into
+the layouts the sm_100a kernels read: bf16, NHWC / K-major, QKV fused, cross-attention K/V fused, GEGLU rows
+interleaved per N tile, every time_emb_proj of the 22 resnets concatenated into one GEMM.  The forward pass is
+a flat sequence of C-ABI calls (no torch math); text-conditioning K/V projections and the whole timestep-MLP
+chain are hoisted out of the denoising loop because they do not depend on the latents.
+"""
+from __future__ import annotations
+
+from typing import Dict, List, Optional, Tuple
+
+import torch
+
+from . import ops
+
+bf16 = torch.bfloat16
+
+
+def _f32(t, dev):
+    return t.detach().to(device=dev, dtype=torch.float32).contiguous()
+
+
+def _w(t, dev):
+    return t.detach().to(device=dev, dtype=bf16).contiguous()
+
+
+class _Resnet:
+    def __init__(self, sd, prefix, dev, temb_slices: Optional[list], eps=1e-5):
+        g = lambda k: sd[prefix + k]
+        self.eps = eps
+        self.n1 = (_f32(g("norm1.weight"), dev), _f32(g("norm1.bias"), dev))
+        self.n2 = (_f32(g("norm2.weight"), dev), _f32(g("norm2.bias"), dev))
+        self.w1 = ops.pack_conv_weight(g("conv1.weight")).to(dev)
+        self.b1 = _f32(g("conv1.bias"), dev)
+        self.w2 = ops.pack_conv_weight(g("conv2.weight")).to(dev)
+        self.b2 = _f32(g("conv2.bias"), dev)
+        self.cout = self.w1.shape[0]
+        self.cin = g("conv1.weight").shape[1]
+        self.temb_off = None
+        if temb_slices is not None and (prefix + "time_emb_proj.weight") in sd:
+            off = sum(w.shape[0] for w, _ in temb_slices)
+            temb_slices.append((g("time_emb_proj.weight"), g("time_emb_proj.bias")))
+            self.temb_off = off
+        self.wsc = self.bsc = None
+        if (prefix + "conv_shortcut.weight") in sd:
+            self.wsc = _w(g("conv_shortcut.weight").reshape(self.cout, self.cin), dev)
+            self.bsc = _f32(g("conv_shortcut.bias"), dev)
+
+    def __call__(self, x, skip, temb_all, ws):
+        # GN+SiLU also materialises the [hidden | skip] concat, already normalised (dual source read)
+        h = ops.groupnorm_silu(x, *self.n1, x1=skip, eps=self.eps, stats_ws=ws)
+        rb = temb_all[:, self.temb_off:self.temb_off + self.cout] if self.temb_off is not None else None
+        # conv1's output only feeds GroupNorm (never an MMA): keep it fp32 so it is not rounded on the way in
+        h = ops.conv2d(h, self.w1, self.cout, bias=self.b1, row_bias=rb, out_f32=True)
+        h = ops.groupnorm_silu(h, *self.n2, eps=self.eps, stats_ws=ws)
+        if self.wsc is not None:
+            res = ops.conv2d(x, self.wsc, self.cout, ksize=1, x1=skip, bias=self.bsc)
+        else:
+            res = x
+        return ops.conv2d(h, self.w2, self.cout, bias=self.b2, residual=res)
+
+
+class _Transformer:
+    def __init__(self, sd, prefix, dev, heads=8):
+        g = lambda k: sd[prefix + k]
+        t = "transformer_blocks.0."
+        self.heads = heads
+        self.norm = (_f32(g("norm.weight"), dev), _f32(g("norm.bias"), dev))
+        c = g("proj_in.weight").shape[0]
+        self.c = c
+        self.w_in, self.b_in = _w(g("proj_in.weight").reshape(c, c), dev), _f32(g("proj_in.bias"), dev)
+        self.w_out, self.b_out = _w(g("proj_out.weight").reshape(c, c), dev), _f32(g("proj_out.bias"), dev)
+        self.ln = [(_f32(g(t + f"norm{i}.weight"), dev), _f32(g(t + f"norm{i}.bias"), dev)) for i in (1, 2, 3)]
+        self.w_qkv = _w(torch.cat([g(t + "attn1.to_q.weight"), g(t + "attn1.to_k.weight"), g(t + "attn1.to_v.weight")], 0), dev)
+        self.w_o1, self.b_o1 = _w(g(t + "attn1.to_out.0.weight"), dev), _f32(g(t + "attn1.to_out.0.bias"), dev)
+        self.w_q2 = _w(g(t + "attn2.to_q.weight"), dev)
+        self.w_kv2 = _w(torch.cat([g(t + "attn2.to_k.weight"), g(t + "attn2.to_v.weight")], 0), dev)
+        self.w_o2, self.b_o2 = _w(g(t + "attn2.to_out.0.weight"), dev), _f32(g(t + "attn2.to_out.0.bias"), dev)
+        wff, bff = ops.pack_geglu_weight(g(t + "ff.net.0.proj.weight"), g(t + "ff.net.0.proj.bias"))
+        self.w_ff1, self.b_ff1 = wff.to(dev), bff.to(dev)
+        self.w_ff2, self.b_ff2 = _w(g(t + "ff.net.2.weight"), dev), _f32(g(t + "ff.net.2.bias"), dev)
+
+    def project_context(self, ctx2d):
+        """Step-invariant text K/V: Linear(768 -> C) of the CLIP states, fused [K | V]."""
+        return ops.gemm(ctx2d, self.w_kv2)
+
+    def __call__(self, x, kv, ws):
+        B, H, W, c = x.shape
+        n, m = H * W, B * H * W
+        y = ops.groupnorm_silu(x, *self.norm, eps=1e-6, silu=False, stats_ws=ws)
+        # the token stream y is consumed only by LayerNorms and residual adds (never an MMA operand): it stays fp32,
+        # which removes 4 of the 5 full-magnitude bf16 roundings per transformer block
+        y = ops.gemm(y.view(m, c), self.w_in, bias=self.b_in, out_f32=True)
+        # self-attention
+        h = ops.layernorm(y, *self.ln[0])
+        qkv = ops.gemm(h, self.w_qkv).view(B, n, 3 * c)
+        a = ops.attention(qkv[..., :c], qkv[..., c:2 * c], qkv[..., 2 * c:], self.heads)
+        y = ops.gemm(a.view(m, c), self.w_o1, bias=self.b_o1, residual=y, out_f32=True)
+        # text cross-attention (K/V hoisted)
+        h = ops.layernorm(y, *self.ln[1])
+        q = ops.gemm(h, self.w_q2).view(B, n, c)
+        kv3 = kv.view(B, -1, 2 * c)
+        a = ops.attention(q, kv3[..., :c], kv3[..., c:], self.heads)
+        y = ops.gemm(a.view(m, c), self.w_o2, bias=self.b_o2, residual=y, out_f32=True)
+        # GEGLU feed-forward
+        h = ops.layernorm(y, *self.ln[2])
+        h = ops.gemm(h, self.w_ff1, bias=self.b_ff1, geglu=True)
+        y = ops.gemm(h, self.w_ff2, bias=self.b_ff2, residual=y, out_f32=False)  # proj_out's MMA reads it: bf16
+        return ops.gemm(y, self.w_out, bias=self.b_out, residual=x.view(m, c)).view(B, H, W, c)
+
+
+class B200UNet:
+    """`forward(sample_nhwc_bf16, temb_all, context_kv) -> eps fp32 [B,h,w,4]` on hand-written sm_100a kernels."""
+
+    IN_PAD = 8  # conv_in channels padded to 8 (16-byte TMA rows): 4 -> 8 for the SDR UNet, 8 for the GM UNet
+
+    def __init__(self, state_dict: Dict[str, torch.Tensor], device="cuda", heads: int = 8):
+        sd = state_dict
+        dev = torch.device(device)
+        self.device = dev
+        self.in_channels = sd["conv_in.weight"].shape[1]
+        self.out_channels = sd["conv_out.weight"].shape[0]
+        self.ch0 = sd["conv_in.weight"].shape[0]
+        self.cross_dim = sd["down_blocks.0.attentions.0.transformer_blocks.0.attn2.to_k.weight"].shape[1]
+        if self.in_channels > self.IN_PAD:
+            raise NotImplementedError("in_channels > 8")
+        self.w_in = ops.pack_conv_weight(sd["conv_in.weight"], cin_pad=self.IN_PAD).to(dev)
+        self.b_in = _f32(sd["conv_in.bias"], dev)
+        self.t1 = (_w(sd["time_embedding.linear_1.weight"], dev), _f32(sd["time_embedding.linear_1.bias"], dev))
+        self.t2 = (_w(sd["time_embedding.linear_2.weight"], dev), _f32(sd["time_embedding.linear_2.bias"], dev))
+        temb_slices: list = []
+        self.down: List[Tuple[List[_Resnet], List[Optional[_Transformer]], Optional[tuple]]] = []
+        i = 0
+        while f"down_blocks.{i}.resnets.0.conv1.weight" in sd:
+            res, att = [], []
+            j = 0
+            while f"down_blocks.{i}.resnets.{j}.conv1.weight" in sd:
+                res.append(_Resnet(sd, f"down_blocks.{i}.resnets.{j}.", dev, temb_slices))
+                has = f"down_blocks.{i}.attentions.{j}.norm.weight" in sd
+                att.append(_Transformer(sd, f"down_blocks.{i}.attentions.{j}.", dev, heads) if has else None)
+                j += 1
+            ds = None
+            if f"down_blocks.{i}.downsamplers.0.conv.weight" in sd:
+                ds = (ops.pack_conv_weight(sd[f"down_blocks.{i}.downsamplers.0.conv.weight"]).to(dev),
+                      _f32(sd[f"down_blocks.{i}.downsamplers.0.conv.bias"], dev))
+            self.down.append((res, att, ds))
+            i += 1
+        self.mid_res = [_Resnet(sd, f"mid_block.resnets.{j}.", dev, temb_slices) for j in range(2)]
+        self.mid_att = _Transformer(sd, "mid_block.attentions.0.", dev, heads)
+        self.up = []
+        i = 0
+        while f"up_blocks.{i}.resnets.0.conv1.weight" in sd:
+            res, att = [], []
+            j = 0
+            while f"up_blocks.{i}.resnets.{j}.conv1.weight" in sd:
+                res.append(_Resnet(sd, f"up_blocks.{i}.resnets.{j}.", dev, temb_slices))
+                has = f"up_blocks.{i}.attentions.{j}.norm.weight" in sd
+                att.append(_Transformer(sd, f"up_blocks.{i}.attentions.{j}.", dev, heads) if has else None)
+                j += 1
+            us = None
+            if f"up_blocks.{i}.upsamplers.0.conv.weight" in sd:
+                us = (ops.pack_conv_weight(sd[f"up_blocks.{i}.upsamplers.0.conv.weight"]).to(dev),
+                      _f32(sd[f"up_blocks.{i}.upsamplers.0.conv.bias"], dev))
+            self.up.append((res, att, us))
+            i += 1
+        self.n_out = (_f32(sd["conv_norm_out.weight"], dev), _f32(sd["conv_norm_out.bias"], dev))
+        self.w_out = ops.pack_conv_weight(sd["conv_out.weight"]).to(dev)
+        self.b_out = _f32(sd["conv_out.bias"], dev)
+        # all 22 time_emb_proj linears as ONE GEMM: [sum(Cout), 1280]
+        self.w_temb = _w(torch.cat([w for w, _ in temb_slices], 0), dev)
+        self.b_temb = _f32(torch.cat([b for _, b in temb_slices], 0), dev)
+        self._gn_ws = torch.empty(64 * 32 * 32 * 2, dtype=torch.float32, device=dev)  # up to 64 samples per forward
+        self.transformers: List[_Transformer] = [a for _, att, _ in self.down for a in att if a is not None] + [self.mid_att] + \
+            [a for _, att, _ in self.up for a in att if a is not None]
+
+    # ---- construction helpers -----------------------------------------------------------------------------
+    @classmethod
+    def from_module(cls, module, device="cuda", **kw) -> "B200UNet":
+        """Accepts anything exposing a diffusers-style `state_dict()` (a real UNet2DConditionModel or the oracle)."""
+        return cls({k: v for k, v in module.state_dict().items()}, device=device, **kw)
+
+    # ---- step-invariant work, hoisted out of the loop --------------------------------------------------------
+    def timestep_table(self, timesteps) -> torch.Tensor:
+        """Rows of SiLU(temb) projected through every resnet's time_emb_proj, for ALL timesteps at once:
+        fp32 [len(timesteps), sum(Cout)].  (diffusers: get_timestep_embedding -> TimestepEmbedding ->
+        per-resnet Linear(SiLU(temb)); depends on t only.)"""
+        ts = [float(t) for t in timesteps]
+        emb = torch.empty((len(ts), self.ch0), dtype=bf16, device=self.device)
+        for i, t in enumerate(ts):
+            ops.timestep_embedding(t, 1, self.ch0, self.device, out=emb[i:i + 1])
+        h = ops.silu(ops.gemm(emb, self.t1[0], bias=self.t1[1]))
+        temb = ops.silu(ops.gemm(h, self.t2[0], bias=self.t2[1]))
+        return ops.gemm(temb, self.w_temb, bias=self.b_temb, out_f32=True)
+
+    def project_context(self, encoder_hidden_states: torch.Tensor) -> List[torch.Tensor]:
+        """Cross-attention K/V of every transformer layer for `encoder_hidden_states` [B,77,768]; identical at
+        every denoising step, so computed once per call instead of 51x."""
+        B, n, c = encoder_hidden_states.shape
+        ctx = encoder_hidden_states.to(device=self.device, dtype=bf16).reshape(B * n, c).contiguous()
+        return [t.project_context(ctx) for t in self.transformers]
+
+    # ---- the forward pass ------------------------------------------------------------------------------------
+    def forward(self, sample: torch.Tensor, temb_row: torch.Tensor, context_kv: List[torch.Tensor],
+                out: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """sample: bf16 [B,h,w,8] (channel-padded NHWC, written by kernel (c)); temb_row: fp32 [1 or B, sum(Cout)]
+        row(s) of `timestep_table`; context_kv: `project_context` output.  Returns eps fp32 [B,h,w,out_channels]."""
+        B = sample.shape[0]
+        temb_all = temb_row if temb_row.shape[0] == B else temb_row.expand(B, -1)
+        ws = self._gn_ws
+        kv = iter(context_kv)
+        x = ops.conv2d(sample, self.w_in, self.ch0, bias=self.b_in)
+        skips = [x]
+        for res, att, ds in self.down:
+            for r, a in zip(res, att):
+                x = r(x, None, temb_all, ws)
+                if a is not None:
+                    x = a(x, next(kv), ws)
+                skips.append(x)
+            if ds is not None:
+                x = ops.conv2d(x, ds[0], ds[0].shape[0], stride=2, bias=ds[1])
+                skips.append(x)
+        x = self.mid_res[0](x, None, temb_all, ws)
+        x = self.mid_att(x, next(kv), ws)
+        x = self.mid_res[1](x, None, temb_all, ws)
+        for res, att, us in self.up:
+            for r, a in zip(res, att):
+                x = r(x, skips.pop(), temb_all, ws)
+                if a is not None:
+                    x = a(x, next(kv), ws)
+            if us is not None:
+                x = ops.conv2d(x, us[0], us[0].shape[0], upsample=True, bias=us[1])
+        x = ops.groupnorm_silu(x, *self.n_out, eps=1e-5, stats_ws=ws)
+        return ops.conv2d(x, self.w_out, self.out_channels, bias=self.b_out, out=out, out_f32=True)
+
+    __call__ = forward
+
+    # ---- convenience: the diffusers call convention (used by tests and by eager callers) -----------------------
+    @torch.no_grad()
+    def forward_nchw(self, sample_nchw: torch.Tensor, timestep, encoder_hidden_states: torch.Tensor) -> torch.Tensor:
+        """`unet(sample, t, encoder_hidden_states=...)[0]` convention: NCHW in, NCHW fp32 eps out."""
+        B, c, h, w = sample_nchw.shape
+        x = torch.zeros((B, h, w, self.IN_PAD), dtype=bf16, device=self.device)
+        x[..., :c] = sample_nchw.to(self.device).permute(0, 2, 3, 1)
+        table = self.timestep_table([float(timestep)])
+        eps = self.forward(x, table, self.project_context(encoder_hidden_states))
+        return eps.permute(0, 3, 1, 2).contiguous()

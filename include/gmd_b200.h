@@ -86,7 +86,9 @@ float gmd_decode_ordered(int32_t v);
 /*     and stable_diffusion_gm.py:1045-1048,1062-1071 plus diffusers PNDMScheduler.step_plms / */
 /*     DDIMScheduler.step (called at :1077/:1093).                                             */
 /* ------------------------------------------------------------------------------------------ */
-enum gmd_sched_mode { GMD_SCHED_LINEAR = 0 /* PLMS & friends: x' = c_sample*x_src - c_eps*eps' */, GMD_SCHED_DDIM = 1 };
+enum gmd_sched_mode { GMD_SCHED_LINEAR = 0 /* PLMS: x' = c_sample*x_src - c_num*eps'/c_denom */, GMD_SCHED_DDIM = 1 };
+/* PLMS multistep combination eps' (diffusers PNDMScheduler.step_plms):
+ *   0: eps   1: (eps + h0)/2   2: (3 eps - h0)/2   3: (23 eps - 16 h0 + 5 h1)/12   4: (55 eps - 59 h0 + 37 h1 - 9 h2)/24 */
 
 typedef struct gmd_sched_params {
     /* model outputs, fp32 [n_px, 4] (pixel-major) */
@@ -109,6 +111,9 @@ typedef struct gmd_sched_params {
     int64_t n_px;            /* B*h*w */
     int64_t px_per_sample;   /* h*w, for per-sample guidance rescale */
     int32_t unet_in_ch;      /* channel count of unet_in_next / concat_out rows (multiple of 8, >= 8) */
+    int32_t unet_in_dup;     /* 1 or 2: write unet_in_next twice (rows i and i + n_px) = the CFG batch duplication of dual_unet.py:1045 */
+    int32_t concat_dup;      /* 1 or 2: same duplication for concat_out (single pipeline under CFG, gm.py:1045-1047) */
+    int32_t concat_self;     /* 1: concat_out ch4-7 <- x_next of THIS branch (single pipeline) instead of concat_tail */
     int32_t mode;            /* enum gmd_sched_mode */
     int32_t use_stash;
     float guidance_scale;
@@ -116,9 +121,10 @@ typedef struct gmd_sched_params {
     float* rescale_stats;    /* workspace fp32 [B, 4]: sums for std(eps_cond), std(eps_cfg) */
     float sqrt_alpha_t;      /* x0 = (x - sqrt_1m_alpha_t * eps) / sqrt_alpha_t (dual_unet.py:1072-1075) */
     float sqrt_1m_alpha_t;
-    float w[4];              /* eps' = w0*eps + w1*hist0 + w2*hist1 + w3*hist2 */
-    float c_sample;          /* LINEAR mode */
-    float c_eps;
+    int32_t plms_kind;       /* LINEAR mode: which multistep combination (see above) */
+    float c_sample;          /* LINEAR mode: (a_prev/a_t)^0.5 */
+    float c_num;             /*              a_prev - a_t */
+    float c_denom;           /*              a_t*(1-a_prev)^0.5 + (a_t*(1-a_t)*a_prev)^0.5 */
     float ddim_sqrt_alpha_t, ddim_sqrt_1m_alpha_t, ddim_sqrt_alpha_prev, ddim_dir_coeff, ddim_sigma; /* DDIM mode */
 } gmd_sched_params;
 
@@ -141,7 +147,8 @@ enum gmd_epilogue_flags {
     GMD_EPI_RESIDUAL = 4,   /* + residual[m, n] (bf16, ld = ldr) */
     GMD_EPI_GEGLU = 8,      /* out[m, j] = (acc[m, j] + b[j]) * gelu(acc[m, j + N/2] + b[j + N/2]); weight rows interleaved per tile */
     GMD_EPI_OUT_F32 = 16,   /* write fp32 instead of bf16 */
-    GMD_EPI_SCALE = 32      /* acc *= alpha before everything else */
+    GMD_EPI_SCALE = 32,     /* acc *= alpha before everything else */
+    GMD_EPI_RESIDUAL_F32 = 64 /* the residual tensor is fp32 (the transformer token stream is kept in fp32) */
 };
 
 typedef struct gmd_gemm_params {
@@ -182,13 +189,14 @@ typedef struct gmd_conv_params {
 
 int gmd_conv_fwd(const gmd_conv_params* p, void* stream);
 
-/* GroupNorm(+SiLU) over NHWC bf16 with an optional second (concatenated) source. */
+/* GroupNorm(+SiLU) over NHWC with an optional second (concatenated, bf16) source; x0 is bf16 or fp32 (in_dtype =
+ * enum gmd_dtype), output bf16.  Deterministic fixed-order reductions. */
 int gmd_groupnorm_silu(const void* x0, int32_t C0, const void* x1, int32_t C1, const float* gamma, const float* beta,
-                       void* out, int32_t N, int32_t HW, int32_t groups, float eps, int32_t apply_silu,
-                       float* stats_ws /* fp32 [N, groups, 2] */, void* stream);
-/* LayerNorm over the last dim of token-major bf16 [M, C]. */
+                       void* out, int32_t N, int32_t HW, int32_t groups, float eps, int32_t apply_silu, int32_t in_dtype,
+                       float* stats_ws /* fp32 workspace, N * 32 * groups * 2 floats */, void* stream);
+/* LayerNorm over the last dim of token-major [M, C] (bf16 or fp32 in, bf16 out). */
 int gmd_layernorm(const void* x, const float* gamma, const float* beta, void* out, int64_t M, int32_t C, float eps,
-                  void* stream);
+                  int32_t in_dtype, void* stream);
 /* sinusoidal timestep embedding (flip_sin_to_cos, shift 0) -> bf16 [B, dim] */
 int gmd_timestep_embedding(float t, void* out, int32_t B, int32_t dim, void* stream);
 /* y = silu(x) elementwise bf16 */

@@ -38,23 +38,25 @@ def dual_unet_loop(unet, gm_unet, scheduler, prompt_embeds, negative_prompt_embe
     if "generator" in scheduler.step.__code__.co_varnames:
         extra["generator"] = generator
     for i, t in enumerate(timesteps):
+        latents_in = latents
         latent_model_input = torch.cat([latents] * 2) if do_cfg else latents  # :1045
         latent_model_input = scheduler.scale_model_input(latent_model_input, t)  # :1047
         gm_latents = gm_scheduler.scale_model_input(gm_latents, t)  # :1048
         sdr_noise_pred = unet(latent_model_input, t, encoder_hidden_states=embeds)  # :1052-1060
+        raw_sdr = sdr_noise_pred
         if do_cfg:
             u, c = sdr_noise_pred.chunk(2)  # :1064
             sdr_noise_pred = u + guidance_scale * (c - u)  # :1065
             if guidance_rescale > 0.0:
                 sdr_noise_pred = rescale_noise_cfg(sdr_noise_pred, c, guidance_rescale)  # :1067-1069
-        a = scheduler.alphas_cumprod[t].view(-1, 1, 1, 1)  # :1072
+        a = scheduler.alphas_cumprod.to(sdr_noise_pred.device)[t].view(-1, 1, 1, 1)  # :1072
         x0_latent = (latents - (1 - a).sqrt() * sdr_noise_pred) / a.sqrt()  # :1073-1075
         latents = scheduler.step(sdr_noise_pred, t, latents, **extra)[0]  # :1077
         gm_latent_input = torch.cat([x0_latent, gm_latents], dim=1)  # :1080
         gm_noise_pred = gm_unet(gm_latent_input, t, encoder_hidden_states=gm_embeds)  # :1083-1092 (no CFG)
         gm_latents = gm_scheduler.step(gm_noise_pred, t, gm_latents, **extra)[0]  # :1093
         if trace is not None:
-            trace.append(dict(t=int(t), sdr_eps=sdr_noise_pred.clone(), gm_eps=gm_noise_pred.clone(),
+            trace.append(dict(t=int(t), x_in=latents_in.clone(), sdr_raw=raw_sdr.clone(), sdr_eps=sdr_noise_pred.clone(), gm_eps=gm_noise_pred.clone(),
                               latents=latents.clone(), gm_latents=gm_latents.clone(), x0=x0_latent.clone()))
     return latents, gm_latents
 

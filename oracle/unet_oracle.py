@@ -159,9 +159,9 @@ class Upsample2D(nn.Module):
 
 
 class DownBlock(nn.Module):
-    def __init__(self, cin, cout, attn, ctx_dim, heads, add_down):
+    def __init__(self, cin, cout, attn, ctx_dim, heads, add_down, temb=1280):
         super().__init__()
-        self.resnets = nn.ModuleList([ResnetBlock2D(cin if i == 0 else cout, cout) for i in range(2)])
+        self.resnets = nn.ModuleList([ResnetBlock2D(cin if i == 0 else cout, cout, temb) for i in range(2)])
         if attn:
             self.attentions = nn.ModuleList([Transformer2DModel(cout, ctx_dim, heads) for _ in range(2)])
         else:
@@ -182,9 +182,9 @@ class DownBlock(nn.Module):
 
 
 class MidBlock(nn.Module):
-    def __init__(self, c, ctx_dim, heads):
+    def __init__(self, c, ctx_dim, heads, temb=1280):
         super().__init__()
-        self.resnets = nn.ModuleList([ResnetBlock2D(c, c), ResnetBlock2D(c, c)])
+        self.resnets = nn.ModuleList([ResnetBlock2D(c, c, temb), ResnetBlock2D(c, c, temb)])
         self.attentions = nn.ModuleList([Transformer2DModel(c, ctx_dim, heads)])
 
     def forward(self, x, temb, ctx):
@@ -194,13 +194,13 @@ class MidBlock(nn.Module):
 
 
 class UpBlock(nn.Module):
-    def __init__(self, cin, cout, cprev, attn, ctx_dim, heads, add_up):
+    def __init__(self, cin, cout, cprev, attn, ctx_dim, heads, add_up, temb=1280):
         super().__init__()
         res = []
         for i in range(3):
             skip = cin if i == 2 else cout
             rin = cprev if i == 0 else cout
-            res.append(ResnetBlock2D(rin + skip, cout))
+            res.append(ResnetBlock2D(rin + skip, cout, temb))
         self.resnets = nn.ModuleList(res)
         self.attentions = nn.ModuleList([Transformer2DModel(cout, ctx_dim, heads) for _ in range(3)]) if attn else None
         self.upsamplers = nn.ModuleList([Upsample2D(cout)]) if add_up else None
@@ -234,9 +234,9 @@ class UNet2DConditionOracle(nn.Module):
         cout = ch[0]
         for i in range(4):
             cin, cout = cout, ch[i]
-            downs.append(DownBlock(cin, cout, attn=i < 3, ctx_dim=cross_attention_dim, heads=heads, add_down=i < 3))
+            downs.append(DownBlock(cin, cout, attn=i < 3, ctx_dim=cross_attention_dim, heads=heads, add_down=i < 3, temb=temb))
         self.down_blocks = nn.ModuleList(downs)
-        self.mid_block = MidBlock(ch[-1], cross_attention_dim, heads)
+        self.mid_block = MidBlock(ch[-1], cross_attention_dim, heads, temb)
         rev = list(reversed(ch))
         ups = []
         cout = rev[0]
@@ -244,7 +244,7 @@ class UNet2DConditionOracle(nn.Module):
             cprev = cout
             cout = rev[i]
             cin = rev[min(i + 1, 3)]
-            ups.append(UpBlock(cin, cout, cprev, attn=i > 0, ctx_dim=cross_attention_dim, heads=heads, add_up=i < 3))
+            ups.append(UpBlock(cin, cout, cprev, attn=i > 0, ctx_dim=cross_attention_dim, heads=heads, add_up=i < 3, temb=temb))
         self.up_blocks = nn.ModuleList(ups)
         self.conv_norm_out = nn.GroupNorm(32, ch[0], eps=1e-5)
         self.conv_out = nn.Conv2d(ch[0], out_channels, 3, padding=1)

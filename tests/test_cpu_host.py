@@ -1,0 +1,177 @@
+"""CPU suite, part 2: host logic of the product (no compute calls): the C-ABI library loads and exports every symbol the
+header declares, struct layouts match, scheduler plans equal the oracle's coefficients, argument checking mirrors the
+reference, sharding arithmetic, and a world_size-2 gloo run of the gather path."""
+import ctypes as C
+import os
+import subprocess
+import sys
+from pathlib import Path
+
+import pytest
+import torch
+
+ROOT = Path(__file__).resolve().parent.parent
+
+
+@pytest.fixture(scope="module")
+def lib():
+    from gm_diffusion_b200 import build
+    build.build()
+    from gm_diffusion_b200 import _lib
+    return _lib
+
+
+def test_library_exports_every_declared_symbol(lib):
+    L = lib.lib()
+    names = lib.declared_symbols()
+    assert len(names) >= 17 and "gmd_attn_fwd" in names and "gmd_hdr_reconstruct" in names
+    for n in names:
+        assert hasattr(L, n), f"{n} declared in include/gmd_b200.h but not exported"
+    assert L.gmd_version() == 100
+    assert abs(L.gmd_decode_ordered(0x3F800000) - 1.0) == 0.0 and L.gmd_decode_ordered(-2139095041) == float("-inf")
+
+
+def test_struct_layouts_match_header(lib):
+    src = r'''
+    #include <stdio.h>
+    #include "gmd_b200.h"
+    int main(void){ printf("%zu %zu %zu %zu %zu\n", sizeof(gmd_hdr_params), sizeof(gmd_sched_params), sizeof(gmd_gemm_params),
+                            sizeof(gmd_conv_params), sizeof(gmd_attn_params)); return 0; }'''
+    tmp = ROOT / "gm_diffusion_b200" / "_C"
+    (tmp / "sizes.c").write_text(src)
+    subprocess.run(["gcc", "-I", str(ROOT / "include"), str(tmp / "sizes.c"), "-o", str(tmp / "sizes")], check=True)
+    out = subprocess.run([str(tmp / "sizes")], check=True, capture_output=True, text=True).stdout.split()
+    want = [C.sizeof(lib.HdrParams), C.sizeof(lib.SchedParams), C.sizeof(lib.GemmParams), C.sizeof(lib.ConvParams), C.sizeof(lib.AttnParams)]
+    assert [int(x) for x in out] == want
+
+
+def test_argument_errors_without_gpu(lib):
+    L = lib.lib()
+    p = lib.HdrParams()
+    assert L.gmd_hdr_reconstruct(C.byref(p), None) == -1 and b"null input" in L.gmd_last_error()
+    with pytest.raises(ValueError):
+        lib.check(-1, "x")
+    with pytest.raises(NotImplementedError):
+        lib.check(-3, "x")
+    with pytest.raises(RuntimeError):
+        lib.check(-2, "x")
+    a = lib.AttnParams()
+    assert L.gmd_attn_fwd(C.byref(a), None) == -1
+    g = lib.GemmParams()
+    assert L.gmd_gemm_fwd(C.byref(g), None) == -1
+
+
+@pytest.mark.skipif(torch.cuda.is_available(), reason="CPU-only check")
+def test_product_fails_loudly_without_cuda():
+    import gm_diffusion_b200 as G
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        G.apply_gm_to_sdr(torch.rand(4), torch.rand(4))
+    with pytest.raises(RuntimeError, match="CUDA"):
+        G.StableDiffusionGMPipeline(None, None, None, None, G.PNDMScheduler())
+
+
+def test_no_oracle_import_in_product():
+    for f in (ROOT / "gm_diffusion_b200").rglob("*.py"):
+        txt = f.read_text()
+        assert "import oracle" not in txt and "from oracle" not in txt, f"{f} imports the oracle"
+    assert "gm_diffusion_b200" not in sys.modules or "oracle" not in getattr(sys.modules["gm_diffusion_b200"], "__dict__", {})
+
+
+@pytest.mark.parametrize("steps", [4, 10, 50])
+def test_pndm_plan_matches_oracle_coefficients(steps):
+    from gm_diffusion_b200.schedulers import PNDMScheduler
+    from oracle.schedulers_oracle import PNDMOracle
+    p, o = PNDMScheduler(), PNDMOracle()
+    p.set_timesteps(steps); o.set_timesteps(steps)
+    assert torch.equal(p.timesteps, o.timesteps) and torch.equal(p.alphas_cumprod, o.alphas_cumprod)
+    kinds = []
+    x = torch.ones(1)
+    for t in p.timesteps.tolist():
+        plan = p.plan_step(t)
+        kinds.append(plan.plms_kind)
+        # feeding eps = 1, sample = 1 exposes the (sample, eps) coefficients of the oracle's linear update
+        e = torch.ones(1)
+        o_out = o.step(e, t, x)[0]
+        src = 1.0
+        mine = plan.c_sample * src - plan.c_num * 1.0 / plan.c_denom
+        assert abs(float(o_out) - mine) < 1e-6, (t, float(o_out), mine)
+    assert kinds[:5] == [0, 1, 2, 3, 4][: len(kinds[:5])] and all(k == 4 for k in kinds[4:])
+
+
+def test_ddim_plan_matches_oracle():
+    from gm_diffusion_b200.schedulers import DDIMScheduler
+    from oracle.schedulers_oracle import DDIMOracle
+    p, o = DDIMScheduler(), DDIMOracle()
+    p.set_timesteps(10); o.set_timesteps(10)
+    assert torch.equal(p.timesteps, o.timesteps)
+    g = torch.Generator().manual_seed(0)
+    x, e, z = (torch.randn(8, generator=g) for _ in range(3))
+    for eta in (0.0, 0.5):
+        for t in p.timesteps.tolist():
+            sa, sb, sp, dc, sg = p.plan_step(t, eta).ddim
+            mine = sp * ((x - sb * e) / sa) + dc * e + sg * z
+            want = o.step(e, t, x, eta=eta, variance_noise=z)[0]
+            torch.testing.assert_close(mine, want, rtol=1e-5, atol=1e-6)
+
+
+def test_check_inputs_mirrors_reference_errors():
+    from gm_diffusion_b200.pipelines._common import PipelineBase, retrieve_timesteps
+    from gm_diffusion_b200.schedulers import PNDMScheduler
+    pb = object.__new__(PipelineBase)
+    e = torch.zeros(1, 77, 768)
+    with pytest.raises(ValueError, match="divisible by 8"):
+        pb.check_inputs(None, 250, 256, None, prompt_embeds=e)
+    with pytest.raises(ValueError, match="Cannot forward both"):
+        pb.check_inputs("a", 256, 256, None, prompt_embeds=e)
+    with pytest.raises(ValueError, match="Provide either"):
+        pb.check_inputs(None, 256, 256, None)
+    with pytest.raises(ValueError, match="has to be of type"):
+        pb.check_inputs(3, 256, 256, None)
+    with pytest.raises(ValueError, match="same shape"):
+        pb.check_inputs(None, 256, 256, None, prompt_embeds=e, negative_prompt_embeds=e[:, :5])
+    with pytest.raises(ValueError, match="callback_steps"):
+        pb.check_inputs(None, 256, 256, 0, prompt_embeds=e)
+    with pytest.raises(ValueError, match="callback_on_step_end_tensor_inputs"):
+        pb.check_inputs(None, 256, 256, None, prompt_embeds=e, callback_on_step_end_tensor_inputs=["nope"])
+    with pytest.raises(ValueError, match="Only one of"):
+        retrieve_timesteps(PNDMScheduler(), 4, None, timesteps=[1], sigmas=[1.0])
+    with pytest.raises(ValueError, match="does not support custom"):
+        retrieve_timesteps(PNDMScheduler(), None, None, timesteps=[1])
+    ts, n = retrieve_timesteps(PNDMScheduler(), 4)
+    assert n == 4 and ts.tolist() == [751, 501, 501, 251, 1]
+
+
+def test_shard_range_partitions():
+    from gm_diffusion_b200.dist import shard_range
+    for total in (0, 1, 7, 8, 64, 65):
+        for world in (1, 2, 4, 8):
+            spans = [shard_range(total, r, world) for r in range(world)]
+            assert spans[0][0] == 0 and spans[-1][1] == total
+            assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
+            assert max(b - a for a, b in spans) - min(b - a for a, b in spans) <= 1
+    with pytest.raises(ValueError):
+        shard_range(8, 2, 2)
+
+
+def test_gather_outputs_gloo_world2(tmp_path):
+    """N>1 path on CPU: two gloo ranks shard 5 'images', run a stand-in per-image function, all-gather in order."""
+    script = tmp_path / "w.py"
+    script.write_text(f'''
+import sys, torch
+sys.path.insert(0, {str(ROOT)!r})
+from gm_diffusion_b200 import dist as D
+rank, local, world = D.init_from_env("gloo")
+total = 5
+a, b = D.shard_range(total, rank, world)
+x = torch.arange(total, dtype=torch.float32)[a:b, None].repeat(1, 3) * 2 + 1
+full = D.gather_outputs(x, total)
+assert full.shape == (total, 3), full.shape
+assert torch.equal(full[:, 0], torch.arange(total, dtype=torch.float32) * 2 + 1), full
+assert D.max_over_ranks(float(rank), "cpu") == world - 1
+print("ok", rank)
+''')
+    env = dict(os.environ, MASTER_ADDR="127.0.0.1")
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+                        "--master-port", "29533", str(script)], capture_output=True, text=True, env=env, timeout=240)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    assert r.stdout.count("ok") == 2

@@ -1,0 +1,146 @@
+"""CPU suite, part 1: the oracle against the reference's own outputs (golden fixtures generated from the real
+tone_mapping.py) and the analytic pins of SURVEY.md §8c."""
+import math
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import schedulers_oracle as SO
+from oracle import tone_mapping_oracle as O
+
+
+@pytest.fixture(scope="module")
+def gold(golden_dir):
+    return np.load(golden_dir / "tm_reference.npz")
+
+
+@pytest.mark.parametrize("qmax", [9, 49, 99])
+def test_tm_oracle_matches_reference_fixtures(gold, qmax):
+    sdr, gm = torch.from_numpy(gold["sdr"]), torch.from_numpy(gold["gm"])
+    hdr = O.apply_gm_to_sdr(gm, sdr, float(qmax), 1 / 64)
+    assert torch.equal(hdr, torch.from_numpy(gold[f"hdr_q{qmax}"]))
+    assert torch.equal(O.linear_scale_tmo(hdr, qmax), torch.from_numpy(gold[f"linear_q{qmax}"]))
+    assert torch.equal(O.hard_clip_tmo(hdr, qmax), torch.from_numpy(gold[f"hardclip_q{qmax}"]))
+    assert torch.equal(O.fix_mulog_tmo(hdr, qmax), torch.from_numpy(gold[f"mulog_q{qmax}"]))
+    assert torch.equal(O.tmo_cuda(hdr), torch.from_numpy(gold[f"tmo_cuda_q{qmax}"]))
+    torch.testing.assert_close(O.gamut_compress(O.fix_mulog_tmo(hdr, qmax)), torch.from_numpy(gold[f"mulog_gamut_q{qmax}"]), rtol=1e-6, atol=1e-7)
+
+
+def test_tm_oracle_spot_values(golden_dir):
+    g = np.load(golden_dir / "tm_spot.npz")
+    hdr = O.apply_gm_to_sdr(torch.from_numpy(g["gm"]), torch.from_numpy(g["sdr"]), 99.0)
+    assert torch.equal(hdr, torch.from_numpy(g["hdr"]))
+    assert abs(float(hdr.max()) - 85.567) < 1e-3
+    assert abs(float(O.fix_mulog_tmo(hdr, 99).mean()) - 0.55577) < 1e-4
+    assert abs(float(O.gamut_compress(O.fix_mulog_tmo(hdr, 99)).mean()) - 0.53887) < 1e-4
+
+
+@pytest.mark.skipif(not os.path.exists(O.REFERENCE_TM), reason="reference checkout not present (GPU box)")
+def test_tm_oracle_against_live_reference():
+    ref = O.load_reference_tm()
+    g = torch.Generator().manual_seed(42)
+    sdr, gm = torch.rand(2, 3, 17, 13, generator=g) * 1.4 - 0.2, torch.rand(2, 3, 17, 13, generator=g)
+    for q in (9.0, 49.0, 99.0):
+        h = ref.apply_gm_to_sdr(gm, sdr, q)
+        assert torch.equal(O.apply_gm_to_sdr(gm, sdr, q), h)
+        assert torch.equal(O.fix_mulog_tmo(h, q), ref.fix_mulog_tmo(h, q))
+        assert torch.equal(O.linear_scale_tmo(h, q), ref.linear_scale_tmo(h, q))
+        assert torch.equal(O.hard_clip_tmo(h, q), ref.hard_clip_tmo(h, q))
+        assert torch.equal(O.gamut_compress(O.fix_mulog_tmo(h, q)), ref.gamut_compress(ref.fix_mulog_tmo(h, q)))
+    assert torch.equal(O.tmo_cuda(sdr * 20), ref.tmo_cuda(sdr * 20))
+    with pytest.raises(ValueError):
+        O.tmo_cuda(torch.tensor([float("nan")]))
+
+
+def test_tm_identities_and_numpy_twin():
+    s = torch.linspace(0, 1, 101)
+    torch.testing.assert_close(O.apply_gm_to_sdr(torch.zeros_like(s), s, 99.0), s ** 2.2, rtol=1e-6, atol=1e-7)
+    assert float(O.apply_gm_to_sdr(torch.ones(1), torch.ones(1), 99.0)) == 100.0
+    assert float(O.fix_mulog_tmo(torch.tensor([100.0]), 99)) == 1.0 and float(O.fix_mulog_tmo(torch.tensor([0.0]), 99)) == 0.0
+    M = torch.tensor(O.BT2020_TO_709)
+    torch.testing.assert_close(M.sum(1), torch.ones(3), rtol=0, atol=2e-6)       # neutral grey is preserved
+    rng = np.random.default_rng(1)
+    a, b = rng.random((5, 7, 3), dtype=np.float32), rng.random((5, 7, 3), dtype=np.float32)
+    np.testing.assert_allclose(O.apply_gm_to_sdr_numpy(b, a, 99.0), O.apply_gm_to_sdr(torch.from_numpy(b), torch.from_numpy(a), 99.0).numpy(), rtol=2e-6, atol=1e-6)
+
+
+# ---- scheduler pins -------------------------------------------------------------------------
+def test_pndm_timestep_literals():
+    s = SO.PNDMOracle()
+    s.set_timesteps(50)
+    ts = s.timesteps.tolist()
+    assert len(ts) == 51 and ts[:4] == [981, 961, 961, 941] and ts[-2:] == [21, 1]
+    s.set_timesteps(4)
+    assert s.timesteps.tolist() == [751, 501, 501, 251, 1]
+    d = SO.DDIMOracle(); d.set_timesteps(4)
+    assert d.timesteps.tolist() == [751, 501, 251, 1]
+    assert abs(float(s.alphas_cumprod[0]) - 0.999150) < 1e-6 and abs(float(s.alphas_cumprod[981]) - 0.005775) < 1e-5
+
+
+def test_plms_step_equals_ddim_step_for_same_eps():
+    p, d = SO.PNDMOracle(), SO.DDIMOracle()
+    p.set_timesteps(10); d.set_timesteps(10)
+    g = torch.Generator().manual_seed(0)
+    x, e = torch.randn(2, 4, 8, 8, generator=g, dtype=torch.float64), torch.randn(2, 4, 8, 8, generator=g, dtype=torch.float64)
+    p.alphas_cumprod = p.alphas_cumprod.double(); d.alphas_cumprod = d.alphas_cumprod.double()
+    a = p._get_prev_sample(x, 501, 401, e)
+    b = d.step(e, 501, x)[0]
+    torch.testing.assert_close(a, b, rtol=1e-10, atol=1e-10)
+
+
+def test_constant_eps_trajectory_closed_form():
+    """With eps constant every PLMS combination returns eps, so x_t = sqrt(a_t) x0 + sqrt(1-a_t) eps is preserved."""
+    for cls in (SO.PNDMOracle, SO.DDIMOracle):
+        s = cls()
+        s.alphas_cumprod = s.alphas_cumprod.double()
+        s.final_alpha_cumprod = s.alphas_cumprod[0]
+        s.set_timesteps(50)
+        g = torch.Generator().manual_seed(3)
+        x0, e = torch.randn(1, 4, 4, 4, generator=g, dtype=torch.float64), torch.randn(1, 4, 4, 4, generator=g, dtype=torch.float64)
+        a = s.alphas_cumprod[int(s.timesteps[0])]
+        x = a.sqrt() * x0 + (1 - a).sqrt() * e
+        for t in s.timesteps:
+            x = s.step(e, t, x)[0]
+        af = s.alphas_cumprod[0]
+        torch.testing.assert_close(x, af.sqrt() * x0 + (1 - af).sqrt() * e, rtol=1e-8, atol=1e-8)
+
+
+def test_unet_oracle_parameter_counts_and_shapes():
+    from oracle.unet_oracle import UNet2DConditionOracle, count_params, widen_conv_in
+    from oracle.vae_oracle import VaeDecoderOracle
+    with torch.device("meta"):
+        assert count_params(UNet2DConditionOracle(4)) == 859_520_964      # the public SD1.5 figure
+        assert count_params(UNet2DConditionOracle(8)) == 859_532_484      # + 4*320*9 (train_gm_unet.py:658-677)
+    torch.manual_seed(0)
+    small = UNet2DConditionOracle(4, block_out_channels=(32, 64, 64, 64), cross_attention_dim=48).eval()
+    x, ctx = torch.randn(2, 4, 16, 16), torch.randn(2, 77, 48)
+    with torch.no_grad():
+        y = small(x, 501, encoder_hidden_states=ctx)
+        y64 = small.double()(x.double(), 501, encoder_hidden_states=ctx.double())
+    assert y.shape == x.shape
+    assert float((y.double() - y64).norm() / y64.norm()) < 1e-5           # fp32 vs fp64 self-consistency
+    wide = widen_conv_in(small.float())
+    with torch.no_grad():
+        y8 = wide(torch.cat([x, x], 1), 501, encoder_hidden_states=ctx)
+    torch.testing.assert_close(y8, y, rtol=1e-4, atol=1e-5)               # tiled/halved conv_in: f([x,x]) == f(x)
+    v = VaeDecoderOracle(ch=(32, 64, 64, 64)).eval()
+    with torch.no_grad():
+        assert v.decode(torch.randn(1, 4, 4, 4)).shape == (1, 3, 32, 32)
+
+
+def test_oracle_loops_run_and_keep_quirks():
+    from oracle import pipeline_oracle as PO
+    from oracle.unet_oracle import UNet2DConditionOracle, widen_conv_in
+    torch.manual_seed(0)
+    u4 = UNet2DConditionOracle(4, block_out_channels=(32, 64, 64, 64), cross_attention_dim=48).eval()
+    u8 = widen_conv_in(u4)
+    pe, ne = torch.randn(1, 77, 48), torch.randn(1, 77, 48)
+    lat = torch.randn(1, 4, 8, 8)
+    trace = []
+    a, b = PO.dual_unet_loop(u4, u8, SO.PNDMOracle(), pe, ne, lat, num_inference_steps=4, trace=trace)
+    assert [s["t"] for s in trace] == [751, 501, 501, 251, 1] and a.shape == b.shape == lat.shape
+    assert not torch.equal(a, b)
+    c = PO.single_gm_loop(u8, SO.PNDMOracle(), 0.18215 * torch.randn(1, 4, 8, 8), pe, ne, lat, num_inference_steps=4)
+    assert c.shape == lat.shape and torch.isfinite(c).all()

@@ -49,6 +49,8 @@ def test_gemm_epilogues():
     ref = a.float() @ w.float().t()
     check(ops.gemm(a, w, bias=bias), ref + bias, what="bias")
     check(ops.gemm(a, w, bias=bias, residual=res), ref + bias + res.float(), what="bias+residual")
+    res32 = torch.randn(M, N, generator=g).cuda()
+    check(ops.gemm(a, w, bias=bias, residual=res32, out_f32=True), ref + bias + res32, tol=1e-3, what="fp32 residual stream")
     check(ops.gemm(a, w, bias=bias, row_bias=rb, rows_per_sample=S), ref + bias + rb.repeat_interleave(S, 0), what="row_bias")
     out = ops.gemm(a, w, bias=bias, out_f32=True)
     assert out.dtype == torch.float32
@@ -166,6 +168,13 @@ def test_groupnorm(N, HW, C0, C1):
     check(got, ref, what=f"groupnorm+silu {N}x{HW}x{C0}+{C1}")
     got = ops.groupnorm_silu(x.cuda(), ga[:C0].cuda(), be[:C0].cuda(), eps=1e-6, silu=False)
     check(got, F.group_norm(x.float().permute(0, 2, 1), 32, ga[:C0], be[:C0], 1e-6).permute(0, 2, 1), what="groupnorm no silu")
+    again = ops.groupnorm_silu(x.cuda(), ga[:C0].cuda(), be[:C0].cuda(), eps=1e-6, silu=False)
+    assert torch.equal(got, again), "groupnorm must be bit-reproducible"
+    one = ops.groupnorm_silu(x[:1].cuda(), ga[:C0].cuda(), be[:C0].cuda(), eps=1e-6, silu=False)
+    assert torch.equal(got[:1], one), "groupnorm of a sample must not depend on the batch size"
+    x32 = torch.randn(N, HW, C0, generator=g) * 2 + 0.5
+    got = ops.groupnorm_silu(x32.cuda(), ga[:C0].cuda(), be[:C0].cuda(), eps=1e-5)
+    check(got, F.silu(F.group_norm(x32.permute(0, 2, 1), 32, ga[:C0], be[:C0], 1e-5)).permute(0, 2, 1), what="groupnorm fp32-in")
 
 
 @pytest.mark.parametrize("M,Cc", [(8192, 320), (2048, 640), (513, 1280), (7, 512)])
@@ -175,6 +184,8 @@ def test_layernorm(M, Cc):
     x = (torch.randn(M, Cc, generator=g) * 3 + 1).to(bf)
     ga, be = torch.randn(Cc, generator=g), torch.randn(Cc, generator=g)
     check(ops.layernorm(x.cuda(), ga.cuda(), be.cuda()), F.layer_norm(x.float(), (Cc,), ga, be, 1e-5), what=f"layernorm {M}x{Cc}")
+    x32 = torch.randn(M, Cc, generator=g) * 3 + 1
+    check(ops.layernorm(x32.cuda(), ga.cuda(), be.cuda()), F.layer_norm(x32, (Cc,), ga, be, 1e-5), what=f"layernorm fp32-in {M}x{Cc}")
 
 
 def test_softmax_silu_temb():
