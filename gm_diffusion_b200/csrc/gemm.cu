@@ -3,7 +3,7 @@
 //   out[M, N] = A[M, K] * W[N, K]^T (+ fused epilogue)
 //
 // One CTA computes a 128 x BN output tile.  Warp 0 is the TMA producer, warp 1 issues tcgen05.mma
-// (one elected thread) into a TMEM accumulator, warps 2-5 are the epilogue (TMEM -> registers ->
+// (one elected thread) into a TMEM accumulator, warps 2-9 are the epilogue (TMEM -> registers ->
 // bias / time-embedding / residual / GEGLU -> global).  Operands are staged by TMA into a STAGES-deep
 // shared-memory ring in the canonical K-major SWIZZLE_128B layout (64 bf16 = 128 B per row).
 //
@@ -21,7 +21,6 @@ namespace {
 
 constexpr int BM = 128;
 constexpr int BK = 64;  // 64 bf16 = 128 bytes = one swizzle row
-constexpr int A_TILE_BYTES = BM * BK * 2;
 
 struct KernelArgs {
     int mode;       // 0 = GEMM (3-D maps: k, row, batch), 1 = conv (4-D A maps: c, w, h, n)
@@ -32,7 +31,7 @@ struct KernelArgs {
     int ks, stride, upsample;
     int chunks0, chunks1;  // 64-channel blocks per tap from source 0 / 1
     int ctot;              // C0 + C1 (weight K pitch per tap)
-    int bw, bh, bn;        // pixel box of one M tile (bw*bh*bn == 128)
+    int bw, bh, bn;        // pixel box of one 128-row tile (bw*bh*bn == 128)
     int tiles_w, tiles_h;  // tile grid over the (Wg x Hg) iteration grid
     int Wg, Hg, Ng;        // iteration grid (output grid; low-res grid when upsample)
     int Wo, Ho;            // output spatial dims
@@ -42,46 +41,67 @@ struct KernelArgs {
     void* out; int64_t ldo;
     const float* bias;
     const float* row_bias; int64_t ld_row_bias; int64_t rows_per_sample;
-    const __nv_bfloat16* residual; int64_t ldr;
+    const void* residual; int64_t ldr;
     int64_t batch_stride_o, batch_stride_r;
     int flags;
     float alpha;
 };
 
-__device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752f)); }
+// exact-erf GELU with erf from Abramowitz-Stegun 7.1.26 (|abs err| <= 1.5e-7, two MUFU ops): erff() costs ~60
+// instructions and made the GEGLU epilogue compute-bound (ncu: 112 M warp instructions for one 65536 x 2560 GEMM)
+__device__ __forceinline__ float gelu_fast(float x) {
+    const float z = fabsf(x) * 0.70710678118654752f;
+    const float t = __fdividef(1.0f, 1.0f + 0.3275911f * z);
+    const float poly = t * (0.254829592f + t * (-0.284496736f + t * (1.421413741f + t * (-1.453152027f + t * 1.061405429f))));
+    const float e = 1.0f - poly * __expf(-z * z);
+    return 0.5f * x * (1.0f + copysignf(e, x));
+}
 
-template <int BN, int STAGES>
-__global__ void __launch_bounds__(192, 1)
+// Shared-memory plan of one CTA.  RB = bytes per element of the residual prefetch buffer (4 holds fp32 or bf16 rows).
+template <int MT, int BN, int STAGES, int RB>
+struct Plan {
+    static constexpr int A_SUB = BM * BK * 2;               // one 128-row A sub-tile
+    static constexpr int A_BYTES = MT * A_SUB;
+    static constexpr int B_BYTES = BN * BK * 2;
+    static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+    static constexpr int RES_ROW = BN * RB;                  // bytes of one thread-private residual row
+    static constexpr int OFF_RES = STAGES * STAGE_BYTES;
+    static constexpr int OFF_BIAS = OFF_RES + BM * RES_ROW;  // BN floats
+    static constexpr int OFF_BARS = OFF_BIAS + BN * 4;
+    static constexpr int TOTAL = OFF_BARS + (2 * STAGES + 1) * 8 + 16 + 1024;
+    static constexpr uint32_t TMEM_COLS = MT * BN <= 32 ? 32 : MT * BN <= 64 ? 64 : MT * BN <= 128 ? 128 : MT * BN <= 256 ? 256 : 512;
+    static_assert(MT * BN <= 512, "accumulators exceed TMEM");
+    static_assert(TOTAL <= 232448, "shared memory plan exceeds 227 KB");
+};
+
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(smem_dst)), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+
+// CTA tile = (MT * 128) x BN.  MT = 2 keeps TWO accumulators in TMEM and issues two MMAs per B tile: the B operand
+// bytes fetched from L2 are amortised over 256 rows (L2 -> SM bandwidth, ~40 B/clk/SM, is what bounds this kernel).
+template <int MT, int BN, int STAGES, int RB>
+__global__ void __launch_bounds__(320, 1)
 gemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__ CUtensorMap map_a1,
             const __grid_constant__ CUtensorMap map_a2, const __grid_constant__ CUtensorMap map_a3,
             const __grid_constant__ CUtensorMap map_w, const KernelArgs args) {
-    constexpr int B_TILE_BYTES = BN * BK * 2;
-    constexpr int STAGE_BYTES = A_TILE_BYTES + B_TILE_BYTES;
-    constexpr uint32_t TMEM_COLS = BN <= 32 ? 32 : BN <= 64 ? 64 : BN <= 128 ? 128 : BN <= 256 ? 256 : 512;
+    using P = Plan<MT, BN, STAGES, RB>;
     constexpr uint32_t IDESC = umma_idesc_bf16(BM, BN, false, false);
 
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
+    uint8_t* res_s = smem + P::OFF_RES;
+    float* bias_s = reinterpret_cast<float*>(smem + P::OFF_BIAS);
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + P::OFF_BARS);
     uint64_t* empty_bar = full_bar + STAGES;
     uint64_t* acc_bar = empty_bar + STAGES;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_bar + 1);
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
-
-    // ---- tile coordinates ----
     const int n0 = blockIdx.y * BN;  // first weight row of this tile
-    int m0 = 0, tw0 = 0, th0 = 0, tn0 = 0;
-    if (args.mode == 0) {
-        m0 = blockIdx.x * BM;
-    } else {
-        int t = blockIdx.x;
-        int tw = t % args.tiles_w; t /= args.tiles_w;
-        int th = t % args.tiles_h; t /= args.tiles_h;
-        tw0 = tw * args.bw; th0 = th * args.bh; tn0 = t * args.bn;
-    }
-    const int zb = blockIdx.z;  // GEMM: batch index; conv+upsample: output parity class
+    const int zb = blockIdx.z;       // GEMM: batch index; conv+upsample: output parity class
 
     if (threadIdx.x == 0) {
         tma_prefetch_desc(&map_a0);
@@ -90,7 +110,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__ 
         mbar_init(acc_bar, 1);
         fence_barrier_init();
     }
-    if (warp == 1) tmem_alloc<TMEM_COLS>(tmem_slot);
+    if (warp == 1) tmem_alloc<P::TMEM_COLS>(tmem_slot);
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -100,29 +120,40 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__ 
         // =============================== TMA producer ===============================
         if (elect_one()) {
             const int chunks_per_tap = args.chunks0 + args.chunks1;
+            int m0[MT], tw0[MT], th0[MT], tn0[MT];
+#pragma unroll
+            for (int s = 0; s < MT; ++s) {
+                int t = blockIdx.x * MT + s;
+                m0[s] = t * BM;
+                int tw = t % args.tiles_w; t /= args.tiles_w;
+                int th = t % args.tiles_h; t /= args.tiles_h;
+                tw0[s] = tw * args.bw; th0[s] = th * args.bh; tn0[s] = t * args.bn;
+            }
             for (int kb = 0; kb < args.num_kb; ++kb) {
                 const int stage = kb % STAGES;
                 const uint32_t phase = (kb / STAGES) & 1;
                 mbar_wait(&empty_bar[stage], phase ^ 1);
-                uint8_t* sa = smem + stage * STAGE_BYTES;
-                uint8_t* sb = sa + A_TILE_BYTES;
-                mbar_expect_tx(&full_bar[stage], STAGE_BYTES);
+                uint8_t* sa = smem + stage * P::STAGE_BYTES;
+                uint8_t* sb = sa + P::A_BYTES;
+                mbar_expect_tx(&full_bar[stage], P::STAGE_BYTES);
                 if (args.mode == 0) {
-                    if (kb < args.kb_src0) tma_load_3d(sa, &map_a0, &full_bar[stage], kb * BK, m0, zb);
-                    else tma_load_3d(sa, &map_a1, &full_bar[stage], (kb - args.kb_src0) * BK, m0, zb);
+#pragma unroll
+                    for (int s = 0; s < MT; ++s) {
+                        if (kb < args.kb_src0) tma_load_3d(sa + s * P::A_SUB, &map_a0, &full_bar[stage], kb * BK, m0[s], zb);
+                        else tma_load_3d(sa + s * P::A_SUB, &map_a1, &full_bar[stage], (kb - args.kb_src0) * BK, m0[s], zb);
+                    }
                     tma_load_3d(sb, &map_w, &full_bar[stage], kb * BK, n0, zb);
                 } else {
                     const int tap = kb / chunks_per_tap;
                     const int cc = kb - tap * chunks_per_tap;
-                    const int r = tap / args.ks, s = tap - r * args.ks;
+                    const int r = tap / args.ks, sx = tap - r * args.ks;
                     const int pad = args.ks >> 1;
-                    int dh, dw;
+                    int dh, dw, c;
                     const CUtensorMap* map;
-                    int c;
                     if (args.stride == 2) {
                         // input row 2*oh - 1 + r: r=0 -> odd plane, oh-1; r=1 -> even plane, oh; r=2 -> odd plane, oh
-                        const int ph = (r == 1) ? 0 : 1, pw = (s == 1) ? 0 : 1;
-                        dh = (r == 0) ? -1 : 0; dw = (s == 0) ? -1 : 0;
+                        const int ph = (r == 1) ? 0 : 1, pw = (sx == 1) ? 0 : 1;
+                        dh = (r == 0) ? -1 : 0; dw = (sx == 0) ? -1 : 0;
                         const int sel = ph * 2 + pw;
                         map = sel == 0 ? &map_a0 : sel == 1 ? &map_a1 : sel == 2 ? &map_a2 : &map_a3;
                         c = cc * BK;
@@ -130,14 +161,16 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__ 
                         if (args.upsample) {
                             const int py = zb >> 1, px = zb & 1;
                             dh = py == 0 ? (r == 0 ? -1 : 0) : (r == 2 ? 1 : 0);
-                            dw = px == 0 ? (s == 0 ? -1 : 0) : (s == 2 ? 1 : 0);
+                            dw = px == 0 ? (sx == 0 ? -1 : 0) : (sx == 2 ? 1 : 0);
                         } else {
-                            dh = r - pad; dw = s - pad;
+                            dh = r - pad; dw = sx - pad;
                         }
                         if (cc < args.chunks0) { map = &map_a0; c = cc * BK; }
                         else { map = &map_a1; c = (cc - args.chunks0) * BK; }
                     }
-                    tma_load_4d(sa, map, &full_bar[stage], c, tw0 + dw, th0 + dh, tn0);
+#pragma unroll
+                    for (int s = 0; s < MT; ++s)
+                        tma_load_4d(sa + s * P::A_SUB, map, &full_bar[stage], c, tw0[s] + dw, th0[s] + dh, tn0[s]);
                     tma_load_3d(sb, &map_w, &full_bar[stage], tap * args.ctot + cc * BK, n0, 0);
                 }
             }
@@ -150,123 +183,236 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__ 
                 const uint32_t phase = (kb / STAGES) & 1;
                 mbar_wait(&full_bar[stage], phase);
                 tc_fence_after();
-                const uint32_t sa = smem_u32(smem + stage * STAGE_BYTES);
-                const uint64_t da = umma_desc_k_sw128(sa);
-                const uint64_t db = umma_desc_k_sw128(sa + A_TILE_BYTES);
+                const uint32_t sa = smem_u32(smem + stage * P::STAGE_BYTES);
+                const uint64_t db = umma_desc_k_sw128(sa + P::A_BYTES);
 #pragma unroll
                 for (int k = 0; k < BK / 16; ++k) {
-                    // +32 bytes per K=16 step inside the 128-byte swizzle row (address field is >> 4)
-                    umma_bf16_ss(tmem_acc, da + 2 * k, db + 2 * k, IDESC, (kb | k) != 0 ? 1u : 0u);
+#pragma unroll
+                    for (int s = 0; s < MT; ++s) {
+                        // +32 bytes per K=16 step inside the 128-byte swizzle row (address field is >> 4)
+                        const uint64_t da = umma_desc_k_sw128(sa + s * P::A_SUB);
+                        umma_bf16_ss(tmem_acc + s * BN, da + 2 * k, db + 2 * k, IDESC, (kb | k) != 0 ? 1u : 0u);
+                    }
                 }
                 umma_commit(&empty_bar[stage]);  // frees the smem slot once these MMAs have read it
             }
-            umma_commit(acc_bar);  // accumulator complete
+            umma_commit(acc_bar);  // accumulators complete
         }
     } else {
-        // =============================== epilogue ===============================
-        const int lg = warp & 3;             // TMEM lane group this warp may access
-        const int row = lg * 32 + lane;      // row of the 128-row tile
-        mbar_wait(acc_bar, 0);
-        tc_fence_after();
-
-        bool row_ok;
-        int64_t out_row;       // row index into out / residual (pixel index for conv)
-        int64_t sample;        // sample index for row_bias
-        if (args.mode == 0) {
-            int64_t m = (int64_t)m0 + row;
-            row_ok = m < args.M;
-            out_row = m;
-            sample = args.rows_per_sample > 0 ? m / args.rows_per_sample : 0;
-        } else {
-            int w = row % args.bw; int t = row / args.bw;
-            int h = t % args.bh; int n = t / args.bh;
-            w += tw0; h += th0; n += tn0;
-            row_ok = (w < args.Wg) && (h < args.Hg) && (n < args.Ng);
-            int ow = w, oh = h;
-            if (args.upsample) { oh = 2 * h + (zb >> 1); ow = 2 * w + (zb & 1); }
-            out_row = ((int64_t)n * args.Ho + oh) * args.Wo + ow;
-            sample = n;
+        // =============================== epilogue (8 warps) ===============================
+        // Two warps per TMEM lane group (a warp may only read lanes 32*(warp%4)..+31); the pair splits the tile's
+        // column chunks, so every SM sub-partition has two epilogue warps to hide TMEM / smem / ALU latency.
+        // One output row per thread.  Everything besides the accumulator is fetched while the main loop runs: the bias
+        // slice goes to smem and each thread streams ITS OWN residual chunks into a private smem row with cp.async
+        // (fire-and-forget 16-byte copies: full memory-level parallelism, no dependent global loads in the epilogue).
+        const int lg = warp & 3;                  // TMEM lane group
+        const int half = (warp - 2) >> 2;         // which of the two warps of this lane group
+        const int row = lg * 32 + lane;           // row of the 128-row sub-tile
+        const int et = threadIdx.x - 64;          // 0..255
+        const bool geglu = args.flags & GMD_EPI_GEGLU;
+        const bool out_f32 = args.flags & GMD_EPI_OUT_F32;
+        const bool res_f32 = args.flags & GMD_EPI_RESIDUAL_F32;
+        const int out_cols_tile = geglu ? BN / 2 : BN;
+        const int out_col_tile = geglu ? blockIdx.y * (BN / 2) : n0;
+        if (args.bias) {
+            for (int i = et; i < BN; i += 256) {
+                int col = geglu ? (i < BN / 2 ? out_col_tile + i : args.N_out + out_col_tile + (i - BN / 2)) : n0 + i;
+                int lim = geglu ? 2 * args.N_out : args.N_out;
+                bias_s[i] = col < lim ? __ldg(args.bias + col) : 0.0f;
+            }
         }
         const int64_t zoff_o = args.mode == 0 ? (int64_t)zb * args.batch_stride_o : 0;
         const int64_t zoff_r = args.mode == 0 ? (int64_t)zb * args.batch_stride_r : 0;
-        const bool geglu = args.flags & GMD_EPI_GEGLU;
-        const bool out_f32 = args.flags & GMD_EPI_OUT_F32;
-        const uint32_t taddr = tmem_acc + (static_cast<uint32_t>(lg * 32) << 16);
-
-        const int out_cols_tile = geglu ? BN / 2 : BN;
-        const int out_col0_tile = geglu ? blockIdx.y * (BN / 2) : n0;
-        for (int ch = 0; ch < out_cols_tile / 16; ++ch) {
-            uint32_t r0[16], r1[16];
-            tmem_ld_32x16(taddr + ch * 16, r0);
-            if (geglu) tmem_ld_32x16(taddr + BN / 2 + ch * 16, r1);
-            tmem_wait_ld();
-            const int col0 = out_col0_tile + ch * 16;  // output column of element 0
-            if (!row_ok || col0 >= args.N_out) continue;
-            float v[16];
+        const uint32_t taddr_lane = tmem_acc + (static_cast<uint32_t>(lg * 32) << 16);
+        const int res_esize = res_f32 ? 4 : 2;
+        const int out_esize = out_f32 ? 4 : 2;
+        constexpr int RES_NCHUNK = P::RES_ROW / 16;                  // physical 16-byte chunks per private row
+        const int cw = geglu ? 16 : 32;                              // output columns per chunk
+        const int nchunks = (out_cols_tile + cw - 1) / cw;
+        const bool tile_full = out_col_tile + out_cols_tile <= args.N_out && (out_cols_tile % cw) == 0;
+        // async residual path: 16-byte aligned rows, whole chunks only, and the row fits the private buffer
+        const bool res_async = args.residual && tile_full && (BN * res_esize <= P::RES_ROW) &&
+                               ((reinterpret_cast<uintptr_t>(args.residual) & 15) == 0) && ((args.ldr * res_esize) % 16 == 0) &&
+                               ((zoff_r * res_esize) % 16 == 0);
+        const bool fast = tile_full && (!args.residual || res_async) &&
+                          ((reinterpret_cast<uintptr_t>(args.out) & 15) == 0) && ((args.ldo * out_esize) % 16 == 0) && ((zoff_o * out_esize) % 16 == 0) &&
+                          (!args.row_bias || (((reinterpret_cast<uintptr_t>(args.row_bias) & 15) == 0) && (args.ld_row_bias % 4 == 0)));
+        uint8_t* my_res = res_s + row * P::RES_ROW;
+        const int rowmod = row % RES_NCHUNK;
+        bool ok[MT];
+        int64_t out_row[MT], sample[MT];
 #pragma unroll
-            for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(r0[j]);
-            if (args.flags & GMD_EPI_SCALE) {
-#pragma unroll
-                for (int j = 0; j < 16; ++j) v[j] *= args.alpha;
+        for (int s = 0; s < MT; ++s) {
+            int t = blockIdx.x * MT + s;
+            if (args.mode == 0) {
+                int64_t m = (int64_t)t * BM + row;
+                ok[s] = m < args.M; out_row[s] = m;
+                sample[s] = args.rows_per_sample > 0 ? m / args.rows_per_sample : 0;
+            } else {
+                int tw = t % args.tiles_w; t /= args.tiles_w;
+                int th = t % args.tiles_h; t /= args.tiles_h;
+                int w = row % args.bw; int q = row / args.bw;
+                int h = q % args.bh; int n = q / args.bh;
+                w += tw * args.bw; h += th * args.bh; n += t * args.bn;
+                ok[s] = (w < args.Wg) && (h < args.Hg) && (n < args.Ng);
+                int ow = w, oh = h;
+                if (args.upsample) { oh = 2 * h + (zb >> 1); ow = 2 * w + (zb & 1); }
+                out_row[s] = ((int64_t)n * args.Ho + oh) * args.Wo + ow;
+                sample[s] = n;
             }
-            const int ncol = args.N_out - col0 < 16 ? args.N_out - col0 : 16;
-            if (geglu) {
-                // value half uses bias[col], gate half bias[N_out + col]  (diffusers GEGLU: proj(x).chunk(2))
+        }
+        const int res_cpc = cw * res_esize / 16;   // 16-byte residual chunks per column chunk
+        auto phys = [&](int k) { int i = rowmod + k; return i >= RES_NCHUNK ? i - RES_NCHUNK : i; };
+        auto prefetch_residual = [&](int s) {
+            if (!res_async || !ok[s]) return;
+            const uint8_t* src = reinterpret_cast<const uint8_t*>(args.residual) + (zoff_r + out_row[s] * args.ldr + out_col_tile) * res_esize;
+            for (int c = half; c < nchunks; c += 2)
+                for (int j = 0; j < res_cpc; ++j) cp_async16(my_res + phys(c * res_cpc + j) * 16, src + (c * res_cpc + j) * 16);
+        };
+        prefetch_residual(0);
+        asm volatile("bar.sync 1, 256;" ::: "memory");  // bias_s visible to the 8 epilogue warps
+        mbar_wait(acc_bar, 0);
+        tc_fence_after();
+#pragma unroll 1
+        for (int s = 0; s < MT; ++s) {
+            if (s > 0) prefetch_residual(s);
+            cp_async_wait_all();
+            const bool row_ok = ok[s];
+            const int64_t orow = out_row[s];
+            const float* rb_row = args.row_bias ? args.row_bias + sample[s] * args.ld_row_bias : nullptr;
+            const uint32_t tsub = taddr_lane + s * BN;
+            if (fast) {
+                if (geglu) {
+#pragma unroll 1
+                    for (int c = half; c < nchunks; c += 2) {
+                        uint32_t r0[16], r1[16];
+                        tmem_ld_32x16(tsub + c * 16, r0);
+                        tmem_ld_32x16(tsub + BN / 2 + c * 16, r1);
+                        tmem_wait_ld();
+                        if (!row_ok) continue;
+                        float v[16];
+                        const float4* bv = reinterpret_cast<const float4*>(bias_s + c * 16);
+                        const float4* bg = reinterpret_cast<const float4*>(bias_s + BN / 2 + c * 16);
 #pragma unroll
-                for (int j = 0; j < 16; ++j) {
-                    float g = __uint_as_float(r1[j]);
-                    if (args.bias && j < ncol) { v[j] += __ldg(args.bias + col0 + j); g += __ldg(args.bias + args.N_out + col0 + j); }
-                    v[j] = v[j] * gelu_erf(g);
-                }
-            } else if (args.bias) {
+                        for (int j = 0; j < 4; ++j) {
+                            float4 a = args.bias ? bv[j] : make_float4(0, 0, 0, 0), g = args.bias ? bg[j] : make_float4(0, 0, 0, 0);
+                            v[4 * j + 0] = (__uint_as_float(r0[4 * j + 0]) + a.x) * gelu_fast(__uint_as_float(r1[4 * j + 0]) + g.x);
+                            v[4 * j + 1] = (__uint_as_float(r0[4 * j + 1]) + a.y) * gelu_fast(__uint_as_float(r1[4 * j + 1]) + g.y);
+                            v[4 * j + 2] = (__uint_as_float(r0[4 * j + 2]) + a.z) * gelu_fast(__uint_as_float(r1[4 * j + 2]) + g.z);
+                            v[4 * j + 3] = (__uint_as_float(r0[4 * j + 3]) + a.w) * gelu_fast(__uint_as_float(r1[4 * j + 3]) + g.w);
+                        }
+                        const int col0 = out_col_tile + c * 16;
+                        if (out_f32) {
+                            float4* op = reinterpret_cast<float4*>(reinterpret_cast<float*>(args.out) + zoff_o + orow * args.ldo + col0);
 #pragma unroll
-                for (int j = 0; j < 16; ++j) if (j < ncol) v[j] += __ldg(args.bias + col0 + j);
-            }
-            if (args.row_bias) {
-                const float* rb = args.row_bias + sample * args.ld_row_bias + col0;
+                            for (int j = 0; j < 4; ++j) op[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+                        } else {
+                            uint4* op = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(args.out) + zoff_o + orow * args.ldo + col0);
 #pragma unroll
-                for (int j = 0; j < 16; ++j) if (j < ncol) v[j] += __ldg(rb + j);
-            }
-            if (args.residual && (args.flags & GMD_EPI_RESIDUAL_F32)) {
-                const float* rp = reinterpret_cast<const float*>(args.residual) + zoff_r + out_row * args.ldr + col0;
-                if (ncol == 16 && ((reinterpret_cast<uintptr_t>(rp) & 15) == 0)) {
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                        float4 a = __ldg(reinterpret_cast<const float4*>(rp) + j);
-                        v[4 * j] += a.x; v[4 * j + 1] += a.y; v[4 * j + 2] += a.z; v[4 * j + 3] += a.w;
+                            for (int j = 0; j < 2; ++j)
+                                op[j] = make_uint4(pack_bf16x2(v[8 * j], v[8 * j + 1]), pack_bf16x2(v[8 * j + 2], v[8 * j + 3]),
+                                                   pack_bf16x2(v[8 * j + 4], v[8 * j + 5]), pack_bf16x2(v[8 * j + 6], v[8 * j + 7]));
+                        }
                     }
                 } else {
-                    for (int j = 0; j < ncol; ++j) v[j] += rp[j];
-                }
-            } else if (args.residual) {
-                const __nv_bfloat16* rp = args.residual + zoff_r + out_row * args.ldr + col0;
-                if (ncol == 16 && ((reinterpret_cast<uintptr_t>(rp) & 15) == 0)) {
-                    uint4 a = __ldg(reinterpret_cast<const uint4*>(rp));
-                    uint4 b = __ldg(reinterpret_cast<const uint4*>(rp) + 1);
-                    uint32_t rr[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+#pragma unroll 1
+                    for (int c = half; c < nchunks; c += 2) {
+                        uint32_t r[32];
+                        tmem_ld_32x32(tsub + c * 32, r);
+                        tmem_wait_ld();
+                        if (!row_ok) continue;
+                        float v[32];
 #pragma unroll
-                    for (int j = 0; j < 8; ++j) { v[2 * j] += bf16_lo(rr[j]); v[2 * j + 1] += bf16_hi(rr[j]); }
-                } else {
-                    for (int j = 0; j < ncol; ++j) v[j] += __bfloat162float(rp[j]);
+                        for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+                        if (args.flags & GMD_EPI_SCALE) {
+#pragma unroll
+                            for (int j = 0; j < 32; ++j) v[j] *= args.alpha;
+                        }
+                        const int col0 = out_col_tile + c * 32;
+                        if (args.bias) {
+                            const float4* b4 = reinterpret_cast<const float4*>(bias_s + c * 32);
+#pragma unroll
+                            for (int j = 0; j < 8; ++j) { float4 a = b4[j]; v[4 * j] += a.x; v[4 * j + 1] += a.y; v[4 * j + 2] += a.z; v[4 * j + 3] += a.w; }
+                        }
+                        if (rb_row) {
+                            const float4* b4 = reinterpret_cast<const float4*>(rb_row + col0);
+#pragma unroll
+                            for (int j = 0; j < 8; ++j) { float4 a = __ldg(b4 + j); v[4 * j] += a.x; v[4 * j + 1] += a.y; v[4 * j + 2] += a.z; v[4 * j + 3] += a.w; }
+                        }
+                        if (args.residual) {
+                            if (res_f32) {
+#pragma unroll
+                                for (int j = 0; j < 8; ++j) {
+                                    float4 a = *reinterpret_cast<const float4*>(my_res + phys(c * 8 + j) * 16);
+                                    v[4 * j] += a.x; v[4 * j + 1] += a.y; v[4 * j + 2] += a.z; v[4 * j + 3] += a.w;
+                                }
+                            } else {
+#pragma unroll
+                                for (int j = 0; j < 4; ++j) {
+                                    uint4 a = *reinterpret_cast<const uint4*>(my_res + phys(c * 4 + j) * 16);
+                                    v[8 * j + 0] += bf16_lo(a.x); v[8 * j + 1] += bf16_hi(a.x); v[8 * j + 2] += bf16_lo(a.y); v[8 * j + 3] += bf16_hi(a.y);
+                                    v[8 * j + 4] += bf16_lo(a.z); v[8 * j + 5] += bf16_hi(a.z); v[8 * j + 6] += bf16_lo(a.w); v[8 * j + 7] += bf16_hi(a.w);
+                                }
+                            }
+                        }
+                        if (out_f32) {
+                            float4* op = reinterpret_cast<float4*>(reinterpret_cast<float*>(args.out) + zoff_o + orow * args.ldo + col0);
+#pragma unroll
+                            for (int j = 0; j < 8; ++j) op[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+                        } else {
+                            uint4* op = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(args.out) + zoff_o + orow * args.ldo + col0);
+#pragma unroll
+                            for (int j = 0; j < 4; ++j)
+                                op[j] = make_uint4(pack_bf16x2(v[8 * j], v[8 * j + 1]), pack_bf16x2(v[8 * j + 2], v[8 * j + 3]),
+                                                   pack_bf16x2(v[8 * j + 4], v[8 * j + 5]), pack_bf16x2(v[8 * j + 6], v[8 * j + 7]));
+                        }
+                    }
                 }
+                continue;
             }
-            if (out_f32) {
-                float* op = reinterpret_cast<float*>(args.out) + zoff_o + out_row * args.ldo + col0;
-                if (ncol == 16 && ((reinterpret_cast<uintptr_t>(op) & 15) == 0)) {
+            // ---- generic path (edge tiles, unaligned or ragged outputs): 16 columns at a time, element-wise guards ----
+#pragma unroll 1
+            for (int ch = half; ch < (out_cols_tile + 15) / 16; ch += 2) {
+                uint32_t r0[16], r1[16];
+                tmem_ld_32x16(tsub + ch * 16, r0);
+                if (geglu) tmem_ld_32x16(tsub + BN / 2 + ch * 16, r1);
+                tmem_wait_ld();
+                const int col0 = out_col_tile + ch * 16;  // output column of element 0
+                if (!row_ok || col0 >= args.N_out) continue;
+                float v[16];
 #pragma unroll
-                    for (int j = 0; j < 4; ++j)
-                        reinterpret_cast<float4*>(op)[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
-                } else {
-                    for (int j = 0; j < ncol; ++j) op[j] = v[j];
+                for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(r0[j]);
+                if (args.flags & GMD_EPI_SCALE) {
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) v[j] *= args.alpha;
                 }
-            } else {
-                __nv_bfloat16* op = reinterpret_cast<__nv_bfloat16*>(args.out) + zoff_o + out_row * args.ldo + col0;
-                if (ncol == 16 && ((reinterpret_cast<uintptr_t>(op) & 15) == 0)) {
-                    uint4 a = make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7]));
-                    uint4 b = make_uint4(pack_bf16x2(v[8], v[9]), pack_bf16x2(v[10], v[11]), pack_bf16x2(v[12], v[13]), pack_bf16x2(v[14], v[15]));
-                    reinterpret_cast<uint4*>(op)[0] = a;
-                    reinterpret_cast<uint4*>(op)[1] = b;
+                const int ncol = args.N_out - col0 < 16 ? args.N_out - col0 : 16;
+                if (geglu) {
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) {
+                        float g = __uint_as_float(r1[j]);
+                        if (args.bias) { v[j] += bias_s[ch * 16 + j]; g += bias_s[BN / 2 + ch * 16 + j]; }
+                        v[j] *= gelu_fast(g);
+                    }
+                } else if (args.bias) {
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) v[j] += bias_s[ch * 16 + j];
+                }
+                if (rb_row) for (int j = 0; j < ncol; ++j) v[j] += __ldg(rb_row + col0 + j);
+                if (args.residual) {
+                    if (res_f32) {
+                        const float* rp = reinterpret_cast<const float*>(args.residual) + zoff_r + orow * args.ldr + col0;
+                        for (int j = 0; j < ncol; ++j) v[j] += __ldg(rp + j);
+                    } else {
+                        const __nv_bfloat16* rp = reinterpret_cast<const __nv_bfloat16*>(args.residual) + zoff_r + orow * args.ldr + col0;
+                        for (int j = 0; j < ncol; ++j) v[j] += __bfloat162float(rp[j]);
+                    }
+                }
+                if (out_f32) {
+                    float* op = reinterpret_cast<float*>(args.out) + zoff_o + orow * args.ldo + col0;
+                    for (int j = 0; j < ncol; ++j) op[j] = v[j];
                 } else {
+                    __nv_bfloat16* op = reinterpret_cast<__nv_bfloat16*>(args.out) + zoff_o + orow * args.ldo + col0;
                     for (int j = 0; j < ncol; ++j) op[j] = __float2bfloat16(v[j]);
                 }
             }
@@ -276,33 +422,37 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__ 
     __syncthreads();
     if (warp == 1) {
         tc_fence_after();
-        tmem_dealloc<TMEM_COLS>(tmem_acc);
+        tmem_dealloc<P::TMEM_COLS>(tmem_acc);
     }
 }
 
-template <int BN, int STAGES>
-constexpr size_t smem_bytes() { return (size_t)STAGES * (A_TILE_BYTES + BN * BK * 2) + (2 * STAGES + 1) * 8 + 16 + 1024; }
-
-template <int BN, int STAGES>
+template <int MT, int BN, int STAGES, int RB>
 int launch(const CUtensorMap* maps_a, const CUtensorMap& map_w, const KernelArgs& args, dim3 grid, cudaStream_t st) {
     static bool configured = false;
-    constexpr size_t smem = smem_bytes<BN, STAGES>();
+    constexpr size_t smem = Plan<MT, BN, STAGES, RB>::TOTAL;
     if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(gemm_kernel<BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaError_t e = cudaFuncSetAttribute(gemm_kernel<MT, BN, STAGES, RB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) { set_last_error("gemm: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return kErrCuda; }
         configured = true;
     }
-    gemm_kernel<BN, STAGES><<<grid, 192, smem, st>>>(maps_a[0], maps_a[1], maps_a[2], maps_a[3], map_w, args);
+    gemm_kernel<MT, BN, STAGES, RB><<<grid, 320, smem, st>>>(maps_a[0], maps_a[1], maps_a[2], maps_a[3], map_w, args);
     count_launch(1);
     return check_launch("gemm_kernel");
 }
 
-int launch_bn(int bn, const CUtensorMap* maps_a, const CUtensorMap& map_w, const KernelArgs& args, dim3 grid, cudaStream_t st) {
+// tiles_m = number of 128-row tiles; picks the CTA tile and launches
+int launch_cfg(int bn, int64_t tiles_m, int64_t tiles_n, unsigned gz, const CUtensorMap* maps_a, const CUtensorMap& map_w,
+               const KernelArgs& args, cudaStream_t st) {
+    // 256-row CTA tiles (two TMEM accumulators, B tile reused) when that still fills the 148 SMs; the fp32 residual
+    // stream needs the larger private-row buffer, which only fits next to the 128-row pipeline
+    const bool res_f32 = args.residual && (args.flags & GMD_EPI_RESIDUAL_F32);
+    const bool mt2 = (bn == 160 || bn == 128) && !res_f32 && tiles_m >= 2 && ((tiles_m + 1) / 2) * tiles_n * gz >= 120;
+    dim3 grid((unsigned)(mt2 ? (tiles_m + 1) / 2 : tiles_m), (unsigned)tiles_n, gz);
     switch (bn) {
-        case 160: return launch<160, 5>(maps_a, map_w, args, grid, st);
-        case 128: return launch<128, 6>(maps_a, map_w, args, grid, st);
-        case 64: return launch<64, 8>(maps_a, map_w, args, grid, st);
-        case 32: return launch<32, 8>(maps_a, map_w, args, grid, st);
+        case 160: return mt2 ? launch<2, 160, 3, 2>(maps_a, map_w, args, grid, st) : launch<1, 160, 3, 4>(maps_a, map_w, args, grid, st);
+        case 128: return mt2 ? launch<2, 128, 3, 2>(maps_a, map_w, args, grid, st) : launch<1, 128, 4, 4>(maps_a, map_w, args, grid, st);
+        case 64: return launch<1, 64, 6, 4>(maps_a, map_w, args, grid, st);
+        case 32: return launch<1, 32, 6, 4>(maps_a, map_w, args, grid, st);
         default: set_last_error("gemm: unsupported N tile %d", bn); return kErrUnsupported;
     }
 }
@@ -359,15 +509,15 @@ extern "C" int gmd_gemm_fwd(const gmd_gemm_params* p, void* stream) {
     a.bias = (p->flags & GMD_EPI_BIAS) ? p->bias : nullptr;
     a.row_bias = (p->flags & GMD_EPI_ROW_BIAS) ? p->row_bias : nullptr;
     a.ld_row_bias = p->ld_row_bias; a.rows_per_sample = p->rows_per_sample;
-    a.residual = (p->flags & GMD_EPI_RESIDUAL) ? static_cast<const __nv_bfloat16*>(p->residual) : nullptr;
+    a.residual = (p->flags & GMD_EPI_RESIDUAL) ? p->residual : nullptr;
     a.ldr = p->ldr;
     a.batch_stride_o = p->stride_o; a.batch_stride_r = p->stride_o;
+    a.tiles_w = a.tiles_h = 1; a.bw = BM; a.bh = a.bn = 1;  // (unused in GEMM mode; keep the index math well defined)
     a.flags = p->flags; a.alpha = p->alpha;
     if ((p->flags & GMD_EPI_BIAS) && !p->bias) { set_last_error("gmd_gemm_fwd: BIAS flag without bias"); return kErrInvalid; }
     if ((p->flags & GMD_EPI_RESIDUAL) && !p->residual) { set_last_error("gmd_gemm_fwd: RESIDUAL flag without residual"); return kErrInvalid; }
     if ((p->flags & GMD_EPI_ROW_BIAS) && (!p->row_bias || p->rows_per_sample <= 0)) { set_last_error("gmd_gemm_fwd: ROW_BIAS needs row_bias and rows_per_sample"); return kErrInvalid; }
-    dim3 grid((unsigned)((p->M + BM - 1) / BM), (unsigned)((p->N + bn - 1) / bn), (unsigned)batch);
-    return launch_bn(bn, maps_a, map_w, a, grid, static_cast<cudaStream_t>(stream));
+    return launch_cfg(bn, (p->M + BM - 1) / BM, (p->N + bn - 1) / bn, (unsigned)batch, maps_a, map_w, a, static_cast<cudaStream_t>(stream));
 }
 
 extern "C" int gmd_conv_fwd(const gmd_conv_params* p, void* stream) {
@@ -410,7 +560,7 @@ extern "C" int gmd_conv_fwd(const gmd_conv_params* p, void* stream) {
     a.bias = (p->flags & GMD_EPI_BIAS) ? p->bias : nullptr;
     a.row_bias = (p->flags & GMD_EPI_ROW_BIAS) ? p->row_bias : nullptr;
     a.ld_row_bias = p->ld_row_bias;
-    a.residual = (p->flags & GMD_EPI_RESIDUAL) ? static_cast<const __nv_bfloat16*>(p->residual) : nullptr;
+    a.residual = (p->flags & GMD_EPI_RESIDUAL) ? p->residual : nullptr;
     a.ldr = p->Cout;
     a.flags = p->flags & ~GMD_EPI_GEGLU;
     a.alpha = 1.0f;
@@ -453,7 +603,7 @@ extern "C" int gmd_conv_fwd(const gmd_conv_params* p, void* stream) {
         int rc = encode_tensor_map_bf16(&map_w, p->w, 3, dims, strides, boxw, true);
         if (rc) return rc;
     }
-    int tiles_n = (p->N + bn - 1) / bn;
-    dim3 grid((unsigned)(a.tiles_w * a.tiles_h * tiles_n), (unsigned)((p->Cout + bnt - 1) / bnt), p->upsample ? 4u : 1u);
-    return launch_bn(bnt, maps_a, map_w, a, grid, static_cast<cudaStream_t>(stream));
+    int tiles_img = (p->N + bn - 1) / bn;
+    return launch_cfg(bnt, (int64_t)a.tiles_w * a.tiles_h * tiles_img, (p->Cout + bnt - 1) / bnt, p->upsample ? 4u : 1u, maps_a, map_w, a,
+                      static_cast<cudaStream_t>(stream));
 }

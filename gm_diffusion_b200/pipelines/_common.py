@@ -112,6 +112,7 @@ class PipelineBase:
         self._num_timesteps = 0
         self.use_cuda_graph = True
         self._graphs: Dict[Any, Any] = {}
+        self.graph_launches = 0  # kernels executed through CUDA-graph replays (the C-ABI counter only sees eager launches)
 
     # properties, dual_unet.py:751-780
     @property
@@ -265,19 +266,27 @@ class PipelineBase:
         on first use (the forward is ~900 launches; replaying it removes the Python/ctypes launch overhead)."""
         if not self.use_cuda_graph:
             return lambda: unet.forward(sample, temb_row, ctx_kv, out=eps_out)
+        def make_replay(g, n_kernels):
+            def replay():
+                g.replay()
+                self.graph_launches += n_kernels
+            return replay
+
         ent = self._graphs.get(key)
         if ent is not None:
-            g, bufs = ent
+            g, bufs, n_kernels = ent
             same = all(a.data_ptr() == b for a, b in zip([sample, temb_row, eps_out] + list(ctx_kv), bufs))
             if same:
-                return g.replay
+                return make_replay(g, n_kernels)
+        n0 = L.launch_count()
         unet.forward(sample, temb_row, ctx_kv, out=eps_out)  # warm-up: attribute setup, allocator pools
+        n_kernels = L.launch_count() - n0
         torch.cuda.synchronize()
         g = torch.cuda.CUDAGraph()
         with torch.cuda.graph(g):
             unet.forward(sample, temb_row, ctx_kv, out=eps_out)
-        self._graphs[key] = (g, [t.data_ptr() for t in [sample, temb_row, eps_out] + list(ctx_kv)])
-        return g.replay
+        self._graphs[key] = (g, [t.data_ptr() for t in [sample, temb_row, eps_out] + list(ctx_kv)], n_kernels)
+        return make_replay(g, n_kernels)
 
 
 def randn_tensor(shape, generator=None, device=None, dtype=None):
