@@ -1,14 +1,21 @@
 // Kernel (a): flash attention on tcgen05 + TMEM, fed by TMA.   O = softmax(Q K^T * scale) V
 //
-// One CTA owns 128 query rows of one (batch, head).  Warp 0 = TMA producer (Q once, then a ring of K/V
-// tiles of 64 keys), warp 1 = MMA issuer, warps 2-5 = softmax (one thread per query row).
-//   S = Q K^T     : tcgen05.mma  A = Q smem (K-major), B = K smem (K-major)      -> TMEM cols [0, 64)
-//   P = exp2(..)  : softmax warps read S with tcgen05.ld, write bf16 P to smem (K-major, 128B swizzle)
-//   O += P V      : tcgen05.mma  A = P smem (K-major), B = V smem (MN-major)     -> TMEM cols [64, 64+DPV)
-// O is rescaled in place in TMEM (tcgen05.ld / st) only when a row maximum of the warp moved.
-// Head dims 40/80/160 (SD1.5: 8 heads at every level) are zero-padded to a multiple of 16 for free by
-// TMA out-of-bounds fill: the tensor map's innermost dim is the true head dim, the box is 64 wide.
-// Two CTAs are co-resident per SM for d = 40/80 so one CTA's MMAs overlap the other's exponentials.
+// One CTA owns 128 query rows of one (batch, head).  Warp 0 = TMA producer (lane 0: Q then the K ring, lane 1: the V
+// ring), warp 1 = MMA issuer, warps 2-5 = softmax (one thread per query row = one TMEM lane).
+//   S_j = Q K_j^T : tcgen05.mma  A = Q smem (K-major), B = K smem (K-major)     -> TMEM S[j&1]   (double buffered)
+//   P_j = 2^(..)  : softmax warps read S with tcgen05.ld, write bf16 P to smem (K-major, 128B swizzle, double buffered)
+//   O  += P_j V_j : tcgen05.mma  A = P smem (K-major), B = V smem (MN-major)    -> TMEM O
+// Design points
+//   * S is double buffered and S_{j+2} is issued as soon as softmax_j has drained S[j&1], so the QK^T round trip is
+//     never on the softmax warps' critical path; two CTAs are co-resident per SM for d = 40/80.
+//   * the softmax denominator comes out of the SAME MMA as O: column D of the V tile (zero padding written by TMA's
+//     out-of-bounds fill) is overwritten with ones, so O[:, D] = sum_k P[:, k] in fp32, rescaled together with O.
+//   * O is rescaled in TMEM lazily: only when a row maximum grew by more than 2^8 (the stale maximum keeps every
+//     exponent <= 8, well inside bf16/fp32 range), so after the first tiles the correction path is almost never taken.
+//   * per key the softmax warps execute FMNMX + FFMA + MUFU.EX2 + half a pack: the exp2 argument is one fused
+//     s * (scale*log2e) - m, and the kernel is bound by the 16 ex2/clk/SM special-function rate at d = 40.
+// Head dims 40/80/160 (SD1.5: 8 heads at every level) are zero-padded to a multiple of 16 for free by TMA: the tensor
+// map's innermost dim is the true head dim, the box is 64 wide.
 #include "common.cuh"
 #include "../../include/gmd_b200.h"
 
@@ -34,16 +41,22 @@ __device__ __forceinline__ float ex2(float x) {
 
 template <int D>
 struct Cfg {
-    static constexpr int NDB = (D + 63) / 64;            // 64-wide d blocks
-    static constexpr int DP = (D + 15) / 16 * 16;        // K extent of QK^T and N extent of PV
-    static constexpr int STAGES = D <= 40 ? 3 : 2;
+    static constexpr int NDB = (D + 63) / 64;               // 64-wide d blocks
+    static constexpr int DP = (D + 15) / 16 * 16;           // K extent of Q K^T
+    static constexpr int DPV = (D + 1 + 15) / 16 * 16;      // N extent of P V: head dim + the ones column
+    static_assert(DPV <= NDB * 64, "ones column must fall inside the loaded V blocks");
+    static constexpr int KS = 2, VS = 2;                    // K / V ring depths
+    static constexpr int PB = D == 80 ? 1 : 2;              // P buffers (one at d = 80 keeps two CTAs per SM)
     static constexpr int Q_BYTES = NDB * BQ * 128;
-    static constexpr int KV_BLOCK_BYTES = BKV * 128;     // one d block of a K or V tile
+    static constexpr int KV_BLOCK_BYTES = BKV * 128;        // one d block of a K or V tile
     static constexpr int K_BYTES = NDB * KV_BLOCK_BYTES;
-    static constexpr int STAGE_BYTES = 2 * K_BYTES;      // K then V
     static constexpr int P_BYTES = BQ * 128;
-    static constexpr int SMEM = Q_BYTES + STAGES * STAGE_BYTES + P_BYTES + 256 + 1024;
-    static constexpr uint32_t TMEM_COLS = (BKV + DP) <= 128 ? 128 : 256;
+    static constexpr int OFF_K = Q_BYTES;
+    static constexpr int OFF_V = OFF_K + KS * K_BYTES;
+    static constexpr int OFF_P = OFF_V + VS * K_BYTES;
+    static constexpr int OFF_BAR = OFF_P + PB * P_BYTES;
+    static constexpr int SMEM = OFF_BAR + 256 + 1024;
+    static constexpr uint32_t TMEM_COLS = (2 * BKV + DPV) <= 256 ? 256 : 512;
     static constexpr int MIN_CTAS = D <= 80 ? 2 : 1;
 };
 
@@ -55,145 +68,171 @@ attn_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ C
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint8_t* q_smem = smem;
-    uint8_t* kv_smem = smem + C::Q_BYTES;
-    uint8_t* p_smem = kv_smem + C::STAGES * C::STAGE_BYTES;
-    uint64_t* bars = reinterpret_cast<uint64_t*>(p_smem + C::P_BYTES);
-    uint64_t* q_full = bars;
-    uint64_t* kv_full = bars + 1;
-    uint64_t* kv_empty = kv_full + C::STAGES;
-    uint64_t* s_full = kv_empty + C::STAGES;
-    uint64_t* p_full = s_full + 1;
-    uint64_t* pv_done = p_full + 1;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(pv_done + 1);
+    uint8_t* k_smem = smem + C::OFF_K;
+    uint8_t* v_smem = smem + C::OFF_V;
+    uint8_t* p_smem = smem + C::OFF_P;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::OFF_BAR);
+    uint64_t* q_full = bars;            // 1
+    uint64_t* k_full = bars + 1;        // KS
+    uint64_t* k_empty = k_full + 2;     // KS
+    uint64_t* v_full = k_empty + 2;     // VS
+    uint64_t* v_empty = v_full + 2;     // VS
+    uint64_t* s_full = v_empty + 2;     // 2
+    uint64_t* p_full = s_full + 2;      // 2
+    uint64_t* pv_done = p_full + 2;     // 2
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(pv_done + 2);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int q0 = blockIdx.x * BQ, head = blockIdx.y, batch = blockIdx.z;
-    const int num_tiles = (args.Nk + BKV - 1) / BKV;
+    const int T = (args.Nk + BKV - 1) / BKV;
 
     if (threadIdx.x == 0) {
         tma_prefetch_desc(&map_q); tma_prefetch_desc(&map_k); tma_prefetch_desc(&map_v);
         mbar_init(q_full, 1);
-        for (int s = 0; s < C::STAGES; ++s) { mbar_init(&kv_full[s], 1); mbar_init(&kv_empty[s], 1); }
-        mbar_init(s_full, 1);
-        mbar_init(p_full, 128);
-        mbar_init(pv_done, 1);
+        for (int s = 0; s < 2; ++s) {
+            mbar_init(&k_full[s], 1); mbar_init(&k_empty[s], 1); mbar_init(&v_full[s], 1); mbar_init(&v_empty[s], 1);
+            mbar_init(&s_full[s], 1); mbar_init(&p_full[s], 128); mbar_init(&pv_done[s], 1);
+        }
         fence_barrier_init();
     }
     if (warp == 1) tmem_alloc<C::TMEM_COLS>(tmem_slot);
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
-    const uint32_t tmem_s = *tmem_slot;
-    const uint32_t tmem_o = tmem_s + BKV;
+    const uint32_t tmem_base = *tmem_slot;
+    const uint32_t tmem_o = tmem_base + 2 * BKV;
 
     if (warp == 0) {
-        if (elect_one()) {
+        if (lane == 0) {
             mbar_expect_tx(q_full, C::Q_BYTES);
             for (int b = 0; b < C::NDB; ++b) tma_load_4d(q_smem + b * BQ * 128, &map_q, q_full, b * 64, head, q0, batch);
-            for (int j = 0; j < num_tiles; ++j) {
-                const int st = j % C::STAGES;
-                const uint32_t ph = (j / C::STAGES) & 1;
-                mbar_wait(&kv_empty[st], ph ^ 1);
-                uint8_t* ks = kv_smem + st * C::STAGE_BYTES;
-                uint8_t* vs = ks + C::K_BYTES;
-                mbar_expect_tx(&kv_full[st], C::STAGE_BYTES);
-                for (int b = 0; b < C::NDB; ++b) {
-                    tma_load_4d(ks + b * C::KV_BLOCK_BYTES, &map_k, &kv_full[st], b * 64, head, j * BKV, batch);
-                    tma_load_4d(vs + b * C::KV_BLOCK_BYTES, &map_v, &kv_full[st], b * 64, head, j * BKV, batch);
-                }
+            for (int j = 0; j < T; ++j) {
+                const int st = j % C::KS;
+                mbar_wait(&k_empty[st], ((j / C::KS) & 1) ^ 1);
+                mbar_expect_tx(&k_full[st], C::K_BYTES);
+                for (int b = 0; b < C::NDB; ++b)
+                    tma_load_4d(k_smem + st * C::K_BYTES + b * C::KV_BLOCK_BYTES, &map_k, &k_full[st], b * 64, head, j * BKV, batch);
+            }
+        } else if (lane == 1) {
+            for (int j = 0; j < T; ++j) {
+                const int st = j % C::VS;
+                mbar_wait(&v_empty[st], ((j / C::VS) & 1) ^ 1);
+                mbar_expect_tx(&v_full[st], C::K_BYTES);
+                for (int b = 0; b < C::NDB; ++b)
+                    tma_load_4d(v_smem + st * C::K_BYTES + b * C::KV_BLOCK_BYTES, &map_v, &v_full[st], b * 64, head, j * BKV, batch);
             }
         }
     } else if (warp == 1) {
         if (elect_one()) {
             constexpr uint32_t IDESC_S = umma_idesc_bf16(BQ, BKV, false, false);
-            constexpr uint32_t IDESC_O = umma_idesc_bf16(BQ, C::DP, false, true);  // B = V is MN-major
-            const uint32_t q_addr = smem_u32(q_smem), p_addr = smem_u32(p_smem);
+            constexpr uint32_t IDESC_O = umma_idesc_bf16(BQ, C::DPV, false, true);  // B = V is MN-major
+            const uint32_t q_addr = smem_u32(q_smem);
             auto issue_s = [&](int j) {
-                const int st = j % C::STAGES;
-                mbar_wait(&kv_full[st], (j / C::STAGES) & 1);
+                const int st = j % C::KS;
+                mbar_wait(&k_full[st], (j / C::KS) & 1);
                 tc_fence_after();
-                const uint32_t k_addr = smem_u32(kv_smem + st * C::STAGE_BYTES);
+                const uint32_t k_addr = smem_u32(k_smem + st * C::K_BYTES);
 #pragma unroll
                 for (int ks = 0; ks < C::DP / 16; ++ks) {
                     const int blk = ks >> 2, within = ks & 3;
                     uint64_t da = umma_desc_k_sw128(q_addr + blk * (BQ * 128) + within * 32);
                     uint64_t db = umma_desc_k_sw128(k_addr + blk * C::KV_BLOCK_BYTES + within * 32);
-                    umma_bf16_ss(tmem_s, da, db, IDESC_S, ks != 0 ? 1u : 0u);
+                    umma_bf16_ss(tmem_base + (j & 1) * BKV, da, db, IDESC_S, ks != 0 ? 1u : 0u);
                 }
-                umma_commit(s_full);
+                umma_commit(&k_empty[st]);
+                umma_commit(&s_full[j & 1]);
             };
             mbar_wait(q_full, 0);
             issue_s(0);
-            for (int j = 0; j < num_tiles; ++j) {
-                const int st = j % C::STAGES;
-                mbar_wait(p_full, j & 1);
+            if (T > 1) issue_s(1);
+            for (int j = 0; j < T; ++j) {
+                const int st = j % C::VS;
+                mbar_wait(&p_full[j & 1], (j >> 1) & 1);   // softmax_j: P_j in smem, ones column set, S[j&1] drained
+                mbar_wait(&v_full[st], (j / C::VS) & 1);
                 tc_fence_after();
-                const uint32_t v_addr = smem_u32(kv_smem + st * C::STAGE_BYTES + C::K_BYTES);
+                const uint32_t v_addr = smem_u32(v_smem + st * C::K_BYTES);
+                const uint32_t p_addr = smem_u32(p_smem + (C::PB == 2 ? (j & 1) : 0) * C::P_BYTES);
 #pragma unroll
                 for (int ks = 0; ks < BKV / 16; ++ks) {
                     uint64_t da = umma_desc_k_sw128(p_addr + ks * 32);
                     uint64_t db = umma_desc_mn_sw128(v_addr + ks * 16 * 128, C::KV_BLOCK_BYTES);
                     umma_bf16_ss(tmem_o, da, db, IDESC_O, (j | ks) != 0 ? 1u : 0u);
                 }
-                umma_commit(&kv_empty[st]);
-                umma_commit(pv_done);
-                if (j + 1 < num_tiles) issue_s(j + 1);
+                umma_commit(&v_empty[st]);
+                umma_commit(&pv_done[j & 1]);
+                if (j + 2 < T) issue_s(j + 2);
             }
         }
     } else {
         const int lg = warp & 3;
         const int row = lg * 32 + lane;
         const uint32_t lane_off = static_cast<uint32_t>(lg * 32) << 16;
-        float m = -INFINITY, l = 0.0f;
-        for (int j = 0; j < num_tiles; ++j) {
-            mbar_wait(s_full, j & 1);
+        const float c = args.scale_log2;
+        float m = -INFINITY;   // running (possibly stale) row maximum in scaled log2 units
+        for (int j = 0; j < T; ++j) {
+            mbar_wait(&s_full[j & 1], (j >> 1) & 1);
             tc_fence_after();
             uint32_t sr[64];
             {
                 uint32_t t0[32], t1[32];
-                tmem_ld_32x32(tmem_s + lane_off, t0);
-                tmem_ld_32x32(tmem_s + lane_off + 32, t1);
+                tmem_ld_32x32(tmem_base + (j & 1) * BKV + lane_off, t0);
+                tmem_ld_32x32(tmem_base + (j & 1) * BKV + lane_off + 32, t1);
                 tmem_wait_ld();
 #pragma unroll
                 for (int k = 0; k < 32; ++k) { sr[k] = t0[k]; sr[32 + k] = t1[k]; }
             }
-            const int valid = args.Nk - j * BKV;  // columns >= valid are padding keys
-            float mj = -INFINITY;
+            const int valid = args.Nk - j * BKV;  // columns >= valid are padding keys (last tile only)
+            if (valid < BKV) {
 #pragma unroll
-            for (int k = 0; k < 64; ++k) {
-                float s = __uint_as_float(sr[k]) * args.scale_log2;
-                if (k >= valid) s = -INFINITY;
-                sr[k] = __float_as_uint(s);
-                mj = fmaxf(mj, s);
+                for (int k = 0; k < 64; ++k) if (k >= valid) sr[k] = 0xff800000u;  // -inf
             }
-            const float m_new = fmaxf(m, mj);
-            const float alpha = ex2(m - m_new);  // m = -inf on the first tile -> 0
-            float rowsum = 0.0f;
+            // four independent running maxima: a 16-deep dependent chain instead of 64
+            float mx0 = __uint_as_float(sr[0]), mx1 = __uint_as_float(sr[1]), mx2 = __uint_as_float(sr[2]), mx3 = __uint_as_float(sr[3]);
+#pragma unroll
+            for (int k = 4; k < 64; k += 4) {
+                mx0 = fmaxf(mx0, __uint_as_float(sr[k])); mx1 = fmaxf(mx1, __uint_as_float(sr[k + 1]));
+                mx2 = fmaxf(mx2, __uint_as_float(sr[k + 2])); mx3 = fmaxf(mx3, __uint_as_float(sr[k + 3]));
+            }
+            const float mx = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3));
+            const float mt = mx * c;
+            const bool grow = mt > m + 8.0f;           // lazy: keep the stale maximum while exponents stay <= 8
+            const float m_new = grow ? mt : m;
+            const float alpha = grow ? ex2(m - m_new) : 1.0f;   // first tile: m = -inf -> 0
             uint32_t pk[32];
 #pragma unroll
             for (int k = 0; k < 32; ++k) {
-                float p0 = ex2(__uint_as_float(sr[2 * k]) - m_new);
-                float p1 = ex2(__uint_as_float(sr[2 * k + 1]) - m_new);
-                rowsum += p0 + p1;
+                float p0 = ex2(fmaf(__uint_as_float(sr[2 * k]), c, -m_new));
+                float p1 = ex2(fmaf(__uint_as_float(sr[2 * k + 1]), c, -m_new));
                 pk[k] = pack_bf16x2(p0, p1);
             }
-            l = l * alpha + rowsum;
-            if (j > 0) {
-                mbar_wait(pv_done, (j - 1) & 1);  // PV_{j-1} finished: P smem reusable, O stable
-                tc_fence_after();
+            m = m_new;
+            // the P buffer we are about to overwrite was last read by PV_{j-PB}
+            if (j >= C::PB) {
+                const int jj = j - C::PB;
+                mbar_wait(&pv_done[jj & 1], (jj >> 1) & 1);
             }
-            // P row -> smem, K-major SWIZZLE_128B: 16-byte chunk c of row r lands at chunk (c ^ (r & 7))
             {
-                uint8_t* prow = p_smem + row * 128;
+                // P row -> smem, K-major SWIZZLE_128B: 16-byte chunk c of row r lands at chunk (c ^ (r & 7))
+                uint8_t* prow = p_smem + (C::PB == 2 ? (j & 1) : 0) * C::P_BYTES + row * 128;
 #pragma unroll
-                for (int c = 0; c < 8; ++c) {
-                    uint4 v = make_uint4(pk[4 * c], pk[4 * c + 1], pk[4 * c + 2], pk[4 * c + 3]);
-                    *reinterpret_cast<uint4*>(prow + ((c ^ (row & 7)) << 4)) = v;
+                for (int ch = 0; ch < 8; ++ch)
+                    *reinterpret_cast<uint4*>(prow + ((ch ^ (row & 7)) << 4)) = make_uint4(pk[4 * ch], pk[4 * ch + 1], pk[4 * ch + 2], pk[4 * ch + 3]);
+            }
+            // ones column of V_j (column D of the zero padding) -> the P V MMA also accumulates the softmax denominator
+            {
+                const int st = j % C::VS;
+                mbar_wait(&v_full[st], (j / C::VS) & 1);
+                if (row < BKV) {
+                    constexpr int blk = D / 64, cc = (D % 64) / 8, within = (D % 8) * 2;
+                    uint8_t* vrow = v_smem + st * C::K_BYTES + blk * C::KV_BLOCK_BYTES + row * 128;
+                    *reinterpret_cast<uint16_t*>(vrow + ((cc ^ (row & 7)) << 4) + within) = 0x3F80;  // bf16 1.0
                 }
             }
-            if (j > 0 && __any_sync(0xffffffffu, m_new > m)) {
+            if (j > 0 && __any_sync(0xffffffffu, grow)) {
+                mbar_wait(&pv_done[(j - 1) & 1], ((j - 1) >> 1) & 1);   // O must be complete up to tile j-1
+                tc_fence_after();
 #pragma unroll
-                for (int ch = 0; ch < C::DP / 16; ++ch) {
+                for (int ch = 0; ch < C::DPV / 16; ++ch) {
                     uint32_t o[16];
                     tmem_ld_32x16(tmem_o + lane_off + ch * 16, o);
                     tmem_wait_ld();
@@ -203,18 +242,24 @@ attn_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ C
                 }
                 tmem_wait_st();
             }
-            m = m_new;
             fence_proxy_async_smem();
             tc_fence_before();
-            mbar_arrive(p_full);
+            mbar_arrive(&p_full[j & 1]);
         }
-        mbar_wait(pv_done, (num_tiles - 1) & 1);
+        mbar_wait(&pv_done[(T - 1) & 1], ((T - 1) >> 1) & 1);
         tc_fence_after();
-        const float inv_l = 1.0f / l;
         const int q = q0 + row;
         __nv_bfloat16* op = args.o + batch * args.o_stride_b + (int64_t)q * args.o_stride_n + head * args.o_stride_h;
+        float inv_l;
+        {
+            // denominator accumulated by the MMA through the ones column (column D of O)
+            uint32_t o[16];
+            tmem_ld_32x16(tmem_o + lane_off + (D / 16) * 16, o);
+            tmem_wait_ld();
+            inv_l = 1.0f / __uint_as_float(o[D % 16]);
+        }
 #pragma unroll
-        for (int ch = 0; ch < C::DP / 16; ++ch) {
+        for (int ch = 0; ch < (D + 15) / 16; ++ch) {
             uint32_t o[16];
             tmem_ld_32x16(tmem_o + lane_off + ch * 16, o);
             tmem_wait_ld();
@@ -237,7 +282,7 @@ attn_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ C
     __syncthreads();
     if (warp == 1) {
         tc_fence_after();
-        tmem_dealloc<C::TMEM_COLS>(tmem_s);
+        tmem_dealloc<C::TMEM_COLS>(tmem_base);
     }
 }
 
@@ -279,6 +324,7 @@ extern "C" int gmd_attn_fwd(const gmd_attn_params* p, void* stream) {
     using namespace gmd;
     if (!p || !p->q || !p->k || !p->v || !p->o) { set_last_error("gmd_attn_fwd: null pointer"); return kErrInvalid; }
     if (p->B <= 0 || p->H <= 0 || p->Nq <= 0 || p->Nk <= 0) { set_last_error("gmd_attn_fwd: empty problem"); return kErrInvalid; }
+    if (!(p->scale > 0.0f)) { set_last_error("gmd_attn_fwd: scale must be positive"); return kErrInvalid; }
     const int64_t strides[] = {p->q_stride_b, p->q_stride_n, p->q_stride_h, p->k_stride_b, p->k_stride_n, p->k_stride_h,
                                p->v_stride_b, p->v_stride_n, p->v_stride_h, p->o_stride_b, p->o_stride_n, p->o_stride_h};
     for (int64_t s : strides)
