@@ -45,6 +45,8 @@ struct KernelArgs {
     int64_t batch_stride_o, batch_stride_r;
     int flags;
     float alpha;
+    // persistent tile loop: tile -> (super-tile along M, N tile, z)
+    int tiles_mt, tiles_n, gz;
 };
 
 // exact-erf GELU with erf from Abramowitz-Stegun 7.1.26 (|abs err| <= 1.5e-7, two MUFU ops): erff() costs ~60
@@ -68,9 +70,11 @@ struct Plan {
     static constexpr int OFF_RES = STAGES * STAGE_BYTES;
     static constexpr int OFF_BIAS = OFF_RES + BM * RES_ROW;  // BN floats
     static constexpr int OFF_BARS = OFF_BIAS + BN * 4;
-    static constexpr int TOTAL = OFF_BARS + (2 * STAGES + 1) * 8 + 16 + 1024;
-    static constexpr uint32_t TMEM_COLS = MT * BN <= 32 ? 32 : MT * BN <= 64 ? 64 : MT * BN <= 128 ? 128 : MT * BN <= 256 ? 256 : 512;
-    static_assert(MT * BN <= 512, "accumulators exceed TMEM");
+    static constexpr int ACC = 2 * MT * BN <= 512 ? 2 : 1;   // TMEM accumulator sets (2 = epilogue overlaps the next tile's main loop)
+    static constexpr int ACC_COLS = MT * BN;
+    static constexpr int TOTAL = OFF_BARS + (2 * STAGES + 4) * 8 + 16 + 1024;
+    static constexpr uint32_t TMEM_COLS = ACC * ACC_COLS <= 32 ? 32 : ACC * ACC_COLS <= 64 ? 64 : ACC * ACC_COLS <= 128 ? 128 : ACC * ACC_COLS <= 256 ? 256 : 512;
+    static_assert(ACC * ACC_COLS <= 512, "accumulators exceed TMEM");
     static_assert(TOTAL <= 232448, "shared memory plan exceeds 227 KB");
 };
 
@@ -79,8 +83,11 @@ __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
 }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 
-// CTA tile = (MT * 128) x BN.  MT = 2 keeps TWO accumulators in TMEM and issues two MMAs per B tile: the B operand
-// bytes fetched from L2 are amortised over 256 rows (L2 -> SM bandwidth, ~40 B/clk/SM, is what bounds this kernel).
+// PERSISTENT kernel: one CTA per SM loops over output tiles (tile = blockIdx.x, += gridDim.x).  CTA tile = (MT*128) x BN.
+//   * MT = 2 keeps TWO accumulators per tile and issues two MMAs per B tile: the B operand bytes fetched from L2 are
+//     amortised over 256 rows (L2 -> SM bandwidth, ~40 B/clk/SM, is what bounds the main loop).
+//   * when two accumulator sets fit in TMEM (ACC = 2) the epilogue of tile i runs while the main loop of tile i+1
+//     already fills the other set; the smem ring and its mbarrier phases run continuously across tiles.
 template <int MT, int BN, int STAGES, int RB>
 __global__ void __launch_bounds__(320, 1)
 gemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__ CUtensorMap map_a1,
@@ -88,6 +95,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__ 
             const __grid_constant__ CUtensorMap map_w, const KernelArgs args) {
     using P = Plan<MT, BN, STAGES, RB>;
     constexpr uint32_t IDESC = umma_idesc_bf16(BM, BN, false, false);
+    constexpr int ACC = P::ACC;
 
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -95,19 +103,19 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__ 
     float* bias_s = reinterpret_cast<float*>(smem + P::OFF_BIAS);
     uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + P::OFF_BARS);
     uint64_t* empty_bar = full_bar + STAGES;
-    uint64_t* acc_bar = empty_bar + STAGES;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_bar + 1);
+    uint64_t* acc_full = empty_bar + STAGES;   // [2]
+    uint64_t* acc_empty = acc_full + 2;        // [2]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
-    const int n0 = blockIdx.y * BN;  // first weight row of this tile
-    const int zb = blockIdx.z;       // GEMM: batch index; conv+upsample: output parity class
+    const int num_tiles = args.tiles_mt * args.tiles_n * args.gz;
 
     if (threadIdx.x == 0) {
         tma_prefetch_desc(&map_a0);
         tma_prefetch_desc(&map_w);
         for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
-        mbar_init(acc_bar, 1);
+        for (int s = 0; s < 2; ++s) { mbar_init(&acc_full[s], 1); mbar_init(&acc_empty[s], 256); }
         fence_barrier_init();
     }
     if (warp == 1) tmem_alloc<P::TMEM_COLS>(tmem_slot);
@@ -120,91 +128,105 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__ 
         // =============================== TMA producer ===============================
         if (elect_one()) {
             const int chunks_per_tap = args.chunks0 + args.chunks1;
-            int m0[MT], tw0[MT], th0[MT], tn0[MT];
+            uint32_t kbg = 0;  // k-blocks issued so far (ring position carries across tiles)
+            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+                const int mt = tile % args.tiles_mt;
+                const int rest = tile / args.tiles_mt;
+                const int n0 = (rest % args.tiles_n) * BN;
+                const int zb = rest / args.tiles_n;
+                int m0[MT], tw0[MT], th0[MT], tn0[MT];
 #pragma unroll
-            for (int s = 0; s < MT; ++s) {
-                int t = blockIdx.x * MT + s;
-                m0[s] = t * BM;
-                int tw = t % args.tiles_w; t /= args.tiles_w;
-                int th = t % args.tiles_h; t /= args.tiles_h;
-                tw0[s] = tw * args.bw; th0[s] = th * args.bh; tn0[s] = t * args.bn;
-            }
-            for (int kb = 0; kb < args.num_kb; ++kb) {
-                const int stage = kb % STAGES;
-                const uint32_t phase = (kb / STAGES) & 1;
-                mbar_wait(&empty_bar[stage], phase ^ 1);
-                uint8_t* sa = smem + stage * P::STAGE_BYTES;
-                uint8_t* sb = sa + P::A_BYTES;
-                mbar_expect_tx(&full_bar[stage], P::STAGE_BYTES);
-                if (args.mode == 0) {
+                for (int s = 0; s < MT; ++s) {
+                    int t = mt * MT + s;
+                    m0[s] = t * BM;
+                    int tw = t % args.tiles_w; t /= args.tiles_w;
+                    int th = t % args.tiles_h; t /= args.tiles_h;
+                    tw0[s] = tw * args.bw; th0[s] = th * args.bh; tn0[s] = t * args.bn;
+                }
+                for (int kb = 0; kb < args.num_kb; ++kb, ++kbg) {
+                    const int stage = kbg % STAGES;
+                    const uint32_t phase = (kbg / STAGES) & 1;
+                    mbar_wait(&empty_bar[stage], phase ^ 1);
+                    uint8_t* sa = smem + stage * P::STAGE_BYTES;
+                    uint8_t* sb = sa + P::A_BYTES;
+                    mbar_expect_tx(&full_bar[stage], P::STAGE_BYTES);
+                    if (args.mode == 0) {
 #pragma unroll
-                    for (int s = 0; s < MT; ++s) {
-                        if (kb < args.kb_src0) tma_load_3d(sa + s * P::A_SUB, &map_a0, &full_bar[stage], kb * BK, m0[s], zb);
-                        else tma_load_3d(sa + s * P::A_SUB, &map_a1, &full_bar[stage], (kb - args.kb_src0) * BK, m0[s], zb);
-                    }
-                    tma_load_3d(sb, &map_w, &full_bar[stage], kb * BK, n0, zb);
-                } else {
-                    const int tap = kb / chunks_per_tap;
-                    const int cc = kb - tap * chunks_per_tap;
-                    const int r = tap / args.ks, sx = tap - r * args.ks;
-                    const int pad = args.ks >> 1;
-                    int dh, dw, c;
-                    const CUtensorMap* map;
-                    if (args.stride == 2) {
-                        // input row 2*oh - 1 + r: r=0 -> odd plane, oh-1; r=1 -> even plane, oh; r=2 -> odd plane, oh
-                        const int ph = (r == 1) ? 0 : 1, pw = (sx == 1) ? 0 : 1;
-                        dh = (r == 0) ? -1 : 0; dw = (sx == 0) ? -1 : 0;
-                        const int sel = ph * 2 + pw;
-                        map = sel == 0 ? &map_a0 : sel == 1 ? &map_a1 : sel == 2 ? &map_a2 : &map_a3;
-                        c = cc * BK;
-                    } else {
-                        if (args.upsample) {
-                            const int py = zb >> 1, px = zb & 1;
-                            dh = py == 0 ? (r == 0 ? -1 : 0) : (r == 2 ? 1 : 0);
-                            dw = px == 0 ? (sx == 0 ? -1 : 0) : (sx == 2 ? 1 : 0);
-                        } else {
-                            dh = r - pad; dw = sx - pad;
+                        for (int s = 0; s < MT; ++s) {
+                            if (kb < args.kb_src0) tma_load_3d(sa + s * P::A_SUB, &map_a0, &full_bar[stage], kb * BK, m0[s], zb);
+                            else tma_load_3d(sa + s * P::A_SUB, &map_a1, &full_bar[stage], (kb - args.kb_src0) * BK, m0[s], zb);
                         }
-                        if (cc < args.chunks0) { map = &map_a0; c = cc * BK; }
-                        else { map = &map_a1; c = (cc - args.chunks0) * BK; }
-                    }
+                        tma_load_3d(sb, &map_w, &full_bar[stage], kb * BK, n0, zb);
+                    } else {
+                        const int tap = kb / chunks_per_tap;
+                        const int cc = kb - tap * chunks_per_tap;
+                        const int r = tap / args.ks, sx = tap - r * args.ks;
+                        const int pad = args.ks >> 1;
+                        int dh, dw, c;
+                        const CUtensorMap* map;
+                        if (args.stride == 2) {
+                            // input row 2*oh - 1 + r: r=0 -> odd plane, oh-1; r=1 -> even plane, oh; r=2 -> odd plane, oh
+                            const int ph = (r == 1) ? 0 : 1, pw = (sx == 1) ? 0 : 1;
+                            dh = (r == 0) ? -1 : 0; dw = (sx == 0) ? -1 : 0;
+                            const int sel = ph * 2 + pw;
+                            map = sel == 0 ? &map_a0 : sel == 1 ? &map_a1 : sel == 2 ? &map_a2 : &map_a3;
+                            c = cc * BK;
+                        } else {
+                            if (args.upsample) {
+                                const int py = zb >> 1, px = zb & 1;
+                                dh = py == 0 ? (r == 0 ? -1 : 0) : (r == 2 ? 1 : 0);
+                                dw = px == 0 ? (sx == 0 ? -1 : 0) : (sx == 2 ? 1 : 0);
+                            } else {
+                                dh = r - pad; dw = sx - pad;
+                            }
+                            if (cc < args.chunks0) { map = &map_a0; c = cc * BK; }
+                            else { map = &map_a1; c = (cc - args.chunks0) * BK; }
+                        }
 #pragma unroll
-                    for (int s = 0; s < MT; ++s)
-                        tma_load_4d(sa + s * P::A_SUB, map, &full_bar[stage], c, tw0[s] + dw, th0[s] + dh, tn0[s]);
-                    tma_load_3d(sb, &map_w, &full_bar[stage], tap * args.ctot + cc * BK, n0, 0);
+                        for (int s = 0; s < MT; ++s)
+                            tma_load_4d(sa + s * P::A_SUB, map, &full_bar[stage], c, tw0[s] + dw, th0[s] + dh, tn0[s]);
+                        tma_load_3d(sb, &map_w, &full_bar[stage], tap * args.ctot + cc * BK, n0, 0);
+                    }
                 }
             }
         }
     } else if (warp == 1) {
         // =============================== MMA issuer ===============================
         if (elect_one()) {
-            for (int kb = 0; kb < args.num_kb; ++kb) {
-                const int stage = kb % STAGES;
-                const uint32_t phase = (kb / STAGES) & 1;
-                mbar_wait(&full_bar[stage], phase);
+            uint32_t kbg = 0, it = 0;
+            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+                const int ab = it % ACC;
+                mbar_wait(&acc_empty[ab], ((it / ACC) & 1) ^ 1);   // epilogue has drained this accumulator set
                 tc_fence_after();
-                const uint32_t sa = smem_u32(smem + stage * P::STAGE_BYTES);
-                const uint64_t db = umma_desc_k_sw128(sa + P::A_BYTES);
+                const uint32_t tacc = tmem_acc + ab * P::ACC_COLS;
+                for (int kb = 0; kb < args.num_kb; ++kb, ++kbg) {
+                    const int stage = kbg % STAGES;
+                    const uint32_t phase = (kbg / STAGES) & 1;
+                    mbar_wait(&full_bar[stage], phase);
+                    tc_fence_after();
+                    const uint32_t sa = smem_u32(smem + stage * P::STAGE_BYTES);
+                    const uint64_t db = umma_desc_k_sw128(sa + P::A_BYTES);
 #pragma unroll
-                for (int k = 0; k < BK / 16; ++k) {
+                    for (int k = 0; k < BK / 16; ++k) {
 #pragma unroll
-                    for (int s = 0; s < MT; ++s) {
-                        // +32 bytes per K=16 step inside the 128-byte swizzle row (address field is >> 4)
-                        const uint64_t da = umma_desc_k_sw128(sa + s * P::A_SUB);
-                        umma_bf16_ss(tmem_acc + s * BN, da + 2 * k, db + 2 * k, IDESC, (kb | k) != 0 ? 1u : 0u);
+                        for (int s = 0; s < MT; ++s) {
+                            // +32 bytes per K=16 step inside the 128-byte swizzle row (address field is >> 4)
+                            const uint64_t da = umma_desc_k_sw128(sa + s * P::A_SUB);
+                            umma_bf16_ss(tacc + s * BN, da + 2 * k, db + 2 * k, IDESC, (kb | k) != 0 ? 1u : 0u);
+                        }
                     }
+                    umma_commit(&empty_bar[stage]);  // frees the smem slot once these MMAs have read it
                 }
-                umma_commit(&empty_bar[stage]);  // frees the smem slot once these MMAs have read it
+                umma_commit(&acc_full[ab]);  // accumulators of this tile complete
             }
-            umma_commit(acc_bar);  // accumulators complete
         }
     } else {
         // =============================== epilogue (8 warps) ===============================
         // Two warps per TMEM lane group (a warp may only read lanes 32*(warp%4)..+31); the pair splits the tile's
         // column chunks, so every SM sub-partition has two epilogue warps to hide TMEM / smem / ALU latency.
-        // One output row per thread.  Everything besides the accumulator is fetched while the main loop runs: the bias
-        // slice goes to smem and each thread streams ITS OWN residual chunks into a private smem row with cp.async
-        // (fire-and-forget 16-byte copies: full memory-level parallelism, no dependent global loads in the epilogue).
+        // One output row per thread.  Everything besides the accumulator is fetched ahead of time: the bias slice goes to
+        // smem and each thread streams ITS OWN residual chunks into a private smem row with cp.async (fire-and-forget
+        // 16-byte copies: full memory-level parallelism, no dependent global loads in the epilogue).
         const int lg = warp & 3;                  // TMEM lane group
         const int half = (warp - 2) >> 2;         // which of the two warps of this lane group
         const int row = lg * 32 + lane;           // row of the 128-row sub-tile
@@ -213,209 +235,243 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__ 
         const bool out_f32 = args.flags & GMD_EPI_OUT_F32;
         const bool res_f32 = args.flags & GMD_EPI_RESIDUAL_F32;
         const int out_cols_tile = geglu ? BN / 2 : BN;
-        const int out_col_tile = geglu ? blockIdx.y * (BN / 2) : n0;
-        if (args.bias) {
-            for (int i = et; i < BN; i += 256) {
-                int col = geglu ? (i < BN / 2 ? out_col_tile + i : args.N_out + out_col_tile + (i - BN / 2)) : n0 + i;
-                int lim = geglu ? 2 * args.N_out : args.N_out;
-                bias_s[i] = col < lim ? __ldg(args.bias + col) : 0.0f;
-            }
-        }
-        const int64_t zoff_o = args.mode == 0 ? (int64_t)zb * args.batch_stride_o : 0;
-        const int64_t zoff_r = args.mode == 0 ? (int64_t)zb * args.batch_stride_r : 0;
-        const uint32_t taddr_lane = tmem_acc + (static_cast<uint32_t>(lg * 32) << 16);
         const int res_esize = res_f32 ? 4 : 2;
         const int out_esize = out_f32 ? 4 : 2;
         constexpr int RES_NCHUNK = P::RES_ROW / 16;                  // physical 16-byte chunks per private row
         const int cw = geglu ? 16 : 32;                              // output columns per chunk
         const int nchunks = (out_cols_tile + cw - 1) / cw;
-        const bool tile_full = out_col_tile + out_cols_tile <= args.N_out && (out_cols_tile % cw) == 0;
-        // async residual path: 16-byte aligned rows, whole chunks only, and the row fits the private buffer
-        const bool res_async = args.residual && tile_full && (BN * res_esize <= P::RES_ROW) &&
-                               ((reinterpret_cast<uintptr_t>(args.residual) & 15) == 0) && ((args.ldr * res_esize) % 16 == 0) &&
-                               ((zoff_r * res_esize) % 16 == 0);
-        const bool fast = tile_full && (!args.residual || res_async) &&
-                          ((reinterpret_cast<uintptr_t>(args.out) & 15) == 0) && ((args.ldo * out_esize) % 16 == 0) && ((zoff_o * out_esize) % 16 == 0) &&
-                          (!args.row_bias || (((reinterpret_cast<uintptr_t>(args.row_bias) & 15) == 0) && (args.ld_row_bias % 4 == 0)));
+        const int res_cpc = cw * res_esize / 16;                     // 16-byte residual chunks per column chunk
+        const uint32_t taddr_lane = tmem_acc + (static_cast<uint32_t>(lg * 32) << 16);
         uint8_t* my_res = res_s + row * P::RES_ROW;
         const int rowmod = row % RES_NCHUNK;
-        bool ok[MT];
-        int64_t out_row[MT], sample[MT];
-#pragma unroll
-        for (int s = 0; s < MT; ++s) {
-            int t = blockIdx.x * MT + s;
+        auto phys = [&](int k) { int i = rowmod + k; return i >= RES_NCHUNK ? i - RES_NCHUNK : i; };
+        const bool ptrs_ok = ((reinterpret_cast<uintptr_t>(args.out) & 15) == 0) && ((args.ldo * out_esize) % 16 == 0) &&
+                             (!args.row_bias || (((reinterpret_cast<uintptr_t>(args.row_bias) & 15) == 0) && (args.ld_row_bias % 4 == 0)));
+        const bool res_ptr_ok = args.residual && (BN * res_esize <= P::RES_ROW) && ((reinterpret_cast<uintptr_t>(args.residual) & 15) == 0) &&
+                                ((args.ldr * res_esize) % 16 == 0);
+
+        struct TileInfo { int mt, n0, zb, out_col_tile; bool tile_full, res_async, fast; int64_t zoff_o, zoff_r; };
+        auto tile_info = [&](int tile) {
+            TileInfo ti;
+            ti.mt = tile % args.tiles_mt;
+            const int rest = tile / args.tiles_mt;
+            const int nt = rest % args.tiles_n;
+            ti.n0 = nt * BN; ti.zb = rest / args.tiles_n;
+            ti.out_col_tile = geglu ? nt * (BN / 2) : ti.n0;
+            ti.tile_full = ti.out_col_tile + out_cols_tile <= args.N_out && (out_cols_tile % cw) == 0;
+            ti.zoff_o = args.mode == 0 ? (int64_t)ti.zb * args.batch_stride_o : 0;
+            ti.zoff_r = args.mode == 0 ? (int64_t)ti.zb * args.batch_stride_r : 0;
+            ti.res_async = res_ptr_ok && ti.tile_full && ((ti.zoff_r * res_esize) % 16 == 0);
+            ti.fast = ti.tile_full && ptrs_ok && (!args.residual || ti.res_async) && ((ti.zoff_o * out_esize) % 16 == 0);
+            return ti;
+        };
+        struct RowInfo { bool ok; int64_t out_row, sample; };
+        auto row_info = [&](const TileInfo& ti, int s) {
+            RowInfo ri;
+            int t = ti.mt * MT + s;
             if (args.mode == 0) {
                 int64_t m = (int64_t)t * BM + row;
-                ok[s] = m < args.M; out_row[s] = m;
-                sample[s] = args.rows_per_sample > 0 ? m / args.rows_per_sample : 0;
+                ri.ok = m < args.M; ri.out_row = m;
+                ri.sample = args.rows_per_sample > 0 ? m / args.rows_per_sample : 0;
             } else {
                 int tw = t % args.tiles_w; t /= args.tiles_w;
                 int th = t % args.tiles_h; t /= args.tiles_h;
                 int w = row % args.bw; int q = row / args.bw;
                 int h = q % args.bh; int n = q / args.bh;
                 w += tw * args.bw; h += th * args.bh; n += t * args.bn;
-                ok[s] = (w < args.Wg) && (h < args.Hg) && (n < args.Ng);
+                ri.ok = (w < args.Wg) && (h < args.Hg) && (n < args.Ng);
                 int ow = w, oh = h;
-                if (args.upsample) { oh = 2 * h + (zb >> 1); ow = 2 * w + (zb & 1); }
-                out_row[s] = ((int64_t)n * args.Ho + oh) * args.Wo + ow;
-                sample[s] = n;
+                if (args.upsample) { oh = 2 * h + (ti.zb >> 1); ow = 2 * w + (ti.zb & 1); }
+                ri.out_row = ((int64_t)n * args.Ho + oh) * args.Wo + ow;
+                ri.sample = n;
             }
-        }
-        const int res_cpc = cw * res_esize / 16;   // 16-byte residual chunks per column chunk
-        auto phys = [&](int k) { int i = rowmod + k; return i >= RES_NCHUNK ? i - RES_NCHUNK : i; };
-        auto prefetch_residual = [&](int s) {
-            if (!res_async || !ok[s]) return;
-            const uint8_t* src = reinterpret_cast<const uint8_t*>(args.residual) + (zoff_r + out_row[s] * args.ldr + out_col_tile) * res_esize;
+            return ri;
+        };
+        auto prefetch_residual = [&](const TileInfo& ti, const RowInfo& ri) {
+            if (!ti.res_async || !ri.ok) return;
+            const uint8_t* src = reinterpret_cast<const uint8_t*>(args.residual) + (ti.zoff_r + ri.out_row * args.ldr + ti.out_col_tile) * res_esize;
             for (int c = half; c < nchunks; c += 2)
                 for (int j = 0; j < res_cpc; ++j) cp_async16(my_res + phys(c * res_cpc + j) * 16, src + (c * res_cpc + j) * 16);
         };
-        prefetch_residual(0);
-        asm volatile("bar.sync 1, 256;" ::: "memory");  // bias_s visible to the 8 epilogue warps
-        mbar_wait(acc_bar, 0);
-        tc_fence_after();
+
+        uint32_t it = 0;
+        if ((int)blockIdx.x < num_tiles) {
+            TileInfo t0 = tile_info(blockIdx.x);
+            prefetch_residual(t0, row_info(t0, 0));
+        }
+        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+            const TileInfo ti = tile_info(tile);
+            const int ab = it % ACC;
+            // bias slice of this N tile -> smem (the first barrier keeps slow warps of the previous tile from losing theirs)
+            asm volatile("bar.sync 1, 256;" ::: "memory");
+            if (args.bias) {
+                for (int i = et; i < BN; i += 256) {
+                    int col = geglu ? (i < BN / 2 ? ti.out_col_tile + i : args.N_out + ti.out_col_tile + (i - BN / 2)) : ti.n0 + i;
+                    int lim = geglu ? 2 * args.N_out : args.N_out;
+                    bias_s[i] = col < lim ? __ldg(args.bias + col) : 0.0f;
+                }
+            }
+            asm volatile("bar.sync 1, 256;" ::: "memory");
+            mbar_wait(&acc_full[ab], (it / ACC) & 1);
+            tc_fence_after();
+            const int out_col_tile = ti.out_col_tile;
+            const int64_t zoff_o = ti.zoff_o, zoff_r = ti.zoff_r;
+            const bool fast = ti.fast, res_async = ti.res_async;
+            (void)res_async;
 #pragma unroll 1
-        for (int s = 0; s < MT; ++s) {
-            if (s > 0) prefetch_residual(s);
-            cp_async_wait_all();
-            const bool row_ok = ok[s];
-            const int64_t orow = out_row[s];
-            const float* rb_row = args.row_bias ? args.row_bias + sample[s] * args.ld_row_bias : nullptr;
-            const uint32_t tsub = taddr_lane + s * BN;
-            if (fast) {
-                if (geglu) {
+            for (int s = 0; s < MT; ++s) {
+                const RowInfo ri = row_info(ti, s);
+                cp_async_wait_all();
+                const bool row_ok = ri.ok;
+                const int64_t orow = ri.out_row;
+                const float* rb_row = args.row_bias ? args.row_bias + ri.sample * args.ld_row_bias : nullptr;
+                const uint32_t tsub = taddr_lane + ab * P::ACC_COLS + s * BN;
+                if (fast) {
+                    if (geglu) {
 #pragma unroll 1
-                    for (int c = half; c < nchunks; c += 2) {
-                        uint32_t r0[16], r1[16];
-                        tmem_ld_32x16(tsub + c * 16, r0);
-                        tmem_ld_32x16(tsub + BN / 2 + c * 16, r1);
-                        tmem_wait_ld();
-                        if (!row_ok) continue;
-                        float v[16];
-                        const float4* bv = reinterpret_cast<const float4*>(bias_s + c * 16);
-                        const float4* bg = reinterpret_cast<const float4*>(bias_s + BN / 2 + c * 16);
+                        for (int c = half; c < nchunks; c += 2) {
+                            uint32_t r0[16], r1[16];
+                            tmem_ld_32x16(tsub + c * 16, r0);
+                            tmem_ld_32x16(tsub + BN / 2 + c * 16, r1);
+                            tmem_wait_ld();
+                            if (!row_ok) continue;
+                            float v[16];
+                            const float4* bv = reinterpret_cast<const float4*>(bias_s + c * 16);
+                            const float4* bg = reinterpret_cast<const float4*>(bias_s + BN / 2 + c * 16);
 #pragma unroll
-                        for (int j = 0; j < 4; ++j) {
-                            float4 a = args.bias ? bv[j] : make_float4(0, 0, 0, 0), g = args.bias ? bg[j] : make_float4(0, 0, 0, 0);
-                            v[4 * j + 0] = (__uint_as_float(r0[4 * j + 0]) + a.x) * gelu_fast(__uint_as_float(r1[4 * j + 0]) + g.x);
-                            v[4 * j + 1] = (__uint_as_float(r0[4 * j + 1]) + a.y) * gelu_fast(__uint_as_float(r1[4 * j + 1]) + g.y);
-                            v[4 * j + 2] = (__uint_as_float(r0[4 * j + 2]) + a.z) * gelu_fast(__uint_as_float(r1[4 * j + 2]) + g.z);
-                            v[4 * j + 3] = (__uint_as_float(r0[4 * j + 3]) + a.w) * gelu_fast(__uint_as_float(r1[4 * j + 3]) + g.w);
+                            for (int j = 0; j < 4; ++j) {
+                                float4 a = args.bias ? bv[j] : make_float4(0, 0, 0, 0), g = args.bias ? bg[j] : make_float4(0, 0, 0, 0);
+                                v[4 * j + 0] = (__uint_as_float(r0[4 * j + 0]) + a.x) * gelu_fast(__uint_as_float(r1[4 * j + 0]) + g.x);
+                                v[4 * j + 1] = (__uint_as_float(r0[4 * j + 1]) + a.y) * gelu_fast(__uint_as_float(r1[4 * j + 1]) + g.y);
+                                v[4 * j + 2] = (__uint_as_float(r0[4 * j + 2]) + a.z) * gelu_fast(__uint_as_float(r1[4 * j + 2]) + g.z);
+                                v[4 * j + 3] = (__uint_as_float(r0[4 * j + 3]) + a.w) * gelu_fast(__uint_as_float(r1[4 * j + 3]) + g.w);
+                            }
+                            const int col0 = out_col_tile + c * 16;
+                            if (out_f32) {
+                                float4* op = reinterpret_cast<float4*>(reinterpret_cast<float*>(args.out) + zoff_o + orow * args.ldo + col0);
+#pragma unroll
+                                for (int j = 0; j < 4; ++j) op[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+                            } else {
+                                uint4* op = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(args.out) + zoff_o + orow * args.ldo + col0);
+#pragma unroll
+                                for (int j = 0; j < 2; ++j)
+                                    op[j] = make_uint4(pack_bf16x2(v[8 * j], v[8 * j + 1]), pack_bf16x2(v[8 * j + 2], v[8 * j + 3]),
+                                                       pack_bf16x2(v[8 * j + 4], v[8 * j + 5]), pack_bf16x2(v[8 * j + 6], v[8 * j + 7]));
+                            }
                         }
-                        const int col0 = out_col_tile + c * 16;
-                        if (out_f32) {
-                            float4* op = reinterpret_cast<float4*>(reinterpret_cast<float*>(args.out) + zoff_o + orow * args.ldo + col0);
+                    } else {
+#pragma unroll 1
+                        for (int c = half; c < nchunks; c += 2) {
+                            uint32_t r[32];
+                            tmem_ld_32x32(tsub + c * 32, r);
+                            tmem_wait_ld();
+                            if (!row_ok) continue;
+                            float v[32];
 #pragma unroll
-                            for (int j = 0; j < 4; ++j) op[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
-                        } else {
-                            uint4* op = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(args.out) + zoff_o + orow * args.ldo + col0);
+                            for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+                            if (args.flags & GMD_EPI_SCALE) {
 #pragma unroll
-                            for (int j = 0; j < 2; ++j)
-                                op[j] = make_uint4(pack_bf16x2(v[8 * j], v[8 * j + 1]), pack_bf16x2(v[8 * j + 2], v[8 * j + 3]),
-                                                   pack_bf16x2(v[8 * j + 4], v[8 * j + 5]), pack_bf16x2(v[8 * j + 6], v[8 * j + 7]));
+                                for (int j = 0; j < 32; ++j) v[j] *= args.alpha;
+                            }
+                            const int col0 = out_col_tile + c * 32;
+                            if (args.bias) {
+                                const float4* b4 = reinterpret_cast<const float4*>(bias_s + c * 32);
+#pragma unroll
+                                for (int j = 0; j < 8; ++j) { float4 a = b4[j]; v[4 * j] += a.x; v[4 * j + 1] += a.y; v[4 * j + 2] += a.z; v[4 * j + 3] += a.w; }
+                            }
+                            if (rb_row) {
+                                const float4* b4 = reinterpret_cast<const float4*>(rb_row + col0);
+#pragma unroll
+                                for (int j = 0; j < 8; ++j) { float4 a = __ldg(b4 + j); v[4 * j] += a.x; v[4 * j + 1] += a.y; v[4 * j + 2] += a.z; v[4 * j + 3] += a.w; }
+                            }
+                            if (args.residual) {
+                                if (res_f32) {
+#pragma unroll
+                                    for (int j = 0; j < 8; ++j) {
+                                        float4 a = *reinterpret_cast<const float4*>(my_res + phys(c * 8 + j) * 16);
+                                        v[4 * j] += a.x; v[4 * j + 1] += a.y; v[4 * j + 2] += a.z; v[4 * j + 3] += a.w;
+                                    }
+                                } else {
+#pragma unroll
+                                    for (int j = 0; j < 4; ++j) {
+                                        uint4 a = *reinterpret_cast<const uint4*>(my_res + phys(c * 4 + j) * 16);
+                                        v[8 * j + 0] += bf16_lo(a.x); v[8 * j + 1] += bf16_hi(a.x); v[8 * j + 2] += bf16_lo(a.y); v[8 * j + 3] += bf16_hi(a.y);
+                                        v[8 * j + 4] += bf16_lo(a.z); v[8 * j + 5] += bf16_hi(a.z); v[8 * j + 6] += bf16_lo(a.w); v[8 * j + 7] += bf16_hi(a.w);
+                                    }
+                                }
+                            }
+                            if (out_f32) {
+                                float4* op = reinterpret_cast<float4*>(reinterpret_cast<float*>(args.out) + zoff_o + orow * args.ldo + col0);
+#pragma unroll
+                                for (int j = 0; j < 8; ++j) op[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+                            } else {
+                                uint4* op = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(args.out) + zoff_o + orow * args.ldo + col0);
+#pragma unroll
+                                for (int j = 0; j < 4; ++j)
+                                    op[j] = make_uint4(pack_bf16x2(v[8 * j], v[8 * j + 1]), pack_bf16x2(v[8 * j + 2], v[8 * j + 3]),
+                                                       pack_bf16x2(v[8 * j + 4], v[8 * j + 5]), pack_bf16x2(v[8 * j + 6], v[8 * j + 7]));
+                            }
                         }
                     }
                 } else {
+                    // ---- generic path (edge tiles, unaligned or ragged outputs): 16 columns at a time, element-wise guards ----
 #pragma unroll 1
-                    for (int c = half; c < nchunks; c += 2) {
-                        uint32_t r[32];
-                        tmem_ld_32x32(tsub + c * 32, r);
+                    for (int ch = half; ch < (out_cols_tile + 15) / 16; ch += 2) {
+                        uint32_t r0[16], r1[16];
+                        tmem_ld_32x16(tsub + ch * 16, r0);
+                        if (geglu) tmem_ld_32x16(tsub + BN / 2 + ch * 16, r1);
                         tmem_wait_ld();
-                        if (!row_ok) continue;
-                        float v[32];
+                        const int col0 = out_col_tile + ch * 16;  // output column of element 0
+                        if (!row_ok || col0 >= args.N_out) continue;
+                        float v[16];
 #pragma unroll
-                        for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+                        for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(r0[j]);
                         if (args.flags & GMD_EPI_SCALE) {
 #pragma unroll
-                            for (int j = 0; j < 32; ++j) v[j] *= args.alpha;
+                            for (int j = 0; j < 16; ++j) v[j] *= args.alpha;
                         }
-                        const int col0 = out_col_tile + c * 32;
-                        if (args.bias) {
-                            const float4* b4 = reinterpret_cast<const float4*>(bias_s + c * 32);
+                        const int ncol = args.N_out - col0 < 16 ? args.N_out - col0 : 16;
+                        if (geglu) {
 #pragma unroll
-                            for (int j = 0; j < 8; ++j) { float4 a = b4[j]; v[4 * j] += a.x; v[4 * j + 1] += a.y; v[4 * j + 2] += a.z; v[4 * j + 3] += a.w; }
-                        }
-                        if (rb_row) {
-                            const float4* b4 = reinterpret_cast<const float4*>(rb_row + col0);
+                            for (int j = 0; j < 16; ++j) {
+                                float g = __uint_as_float(r1[j]);
+                                if (args.bias) { v[j] += bias_s[ch * 16 + j]; g += bias_s[BN / 2 + ch * 16 + j]; }
+                                v[j] *= gelu_fast(g);
+                            }
+                        } else if (args.bias) {
 #pragma unroll
-                            for (int j = 0; j < 8; ++j) { float4 a = __ldg(b4 + j); v[4 * j] += a.x; v[4 * j + 1] += a.y; v[4 * j + 2] += a.z; v[4 * j + 3] += a.w; }
+                            for (int j = 0; j < 16; ++j) v[j] += bias_s[ch * 16 + j];
                         }
+                        if (rb_row) for (int j = 0; j < ncol; ++j) v[j] += __ldg(rb_row + col0 + j);
                         if (args.residual) {
                             if (res_f32) {
-#pragma unroll
-                                for (int j = 0; j < 8; ++j) {
-                                    float4 a = *reinterpret_cast<const float4*>(my_res + phys(c * 8 + j) * 16);
-                                    v[4 * j] += a.x; v[4 * j + 1] += a.y; v[4 * j + 2] += a.z; v[4 * j + 3] += a.w;
-                                }
+                                const float* rp = reinterpret_cast<const float*>(args.residual) + zoff_r + orow * args.ldr + col0;
+                                for (int j = 0; j < ncol; ++j) v[j] += __ldg(rp + j);
                             } else {
-#pragma unroll
-                                for (int j = 0; j < 4; ++j) {
-                                    uint4 a = *reinterpret_cast<const uint4*>(my_res + phys(c * 4 + j) * 16);
-                                    v[8 * j + 0] += bf16_lo(a.x); v[8 * j + 1] += bf16_hi(a.x); v[8 * j + 2] += bf16_lo(a.y); v[8 * j + 3] += bf16_hi(a.y);
-                                    v[8 * j + 4] += bf16_lo(a.z); v[8 * j + 5] += bf16_hi(a.z); v[8 * j + 6] += bf16_lo(a.w); v[8 * j + 7] += bf16_hi(a.w);
-                                }
+                                const __nv_bfloat16* rp = reinterpret_cast<const __nv_bfloat16*>(args.residual) + zoff_r + orow * args.ldr + col0;
+                                for (int j = 0; j < ncol; ++j) v[j] += __bfloat162float(rp[j]);
                             }
                         }
                         if (out_f32) {
-                            float4* op = reinterpret_cast<float4*>(reinterpret_cast<float*>(args.out) + zoff_o + orow * args.ldo + col0);
-#pragma unroll
-                            for (int j = 0; j < 8; ++j) op[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+                            float* op = reinterpret_cast<float*>(args.out) + zoff_o + orow * args.ldo + col0;
+                            for (int j = 0; j < ncol; ++j) op[j] = v[j];
                         } else {
-                            uint4* op = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(args.out) + zoff_o + orow * args.ldo + col0);
-#pragma unroll
-                            for (int j = 0; j < 4; ++j)
-                                op[j] = make_uint4(pack_bf16x2(v[8 * j], v[8 * j + 1]), pack_bf16x2(v[8 * j + 2], v[8 * j + 3]),
-                                                   pack_bf16x2(v[8 * j + 4], v[8 * j + 5]), pack_bf16x2(v[8 * j + 6], v[8 * j + 7]));
+                            __nv_bfloat16* op = reinterpret_cast<__nv_bfloat16*>(args.out) + zoff_o + orow * args.ldo + col0;
+                            for (int j = 0; j < ncol; ++j) op[j] = __float2bfloat16(v[j]);
                         }
                     }
                 }
-                continue;
-            }
-            // ---- generic path (edge tiles, unaligned or ragged outputs): 16 columns at a time, element-wise guards ----
-#pragma unroll 1
-            for (int ch = half; ch < (out_cols_tile + 15) / 16; ch += 2) {
-                uint32_t r0[16], r1[16];
-                tmem_ld_32x16(tsub + ch * 16, r0);
-                if (geglu) tmem_ld_32x16(tsub + BN / 2 + ch * 16, r1);
-                tmem_wait_ld();
-                const int col0 = out_col_tile + ch * 16;  // output column of element 0
-                if (!row_ok || col0 >= args.N_out) continue;
-                float v[16];
-#pragma unroll
-                for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(r0[j]);
-                if (args.flags & GMD_EPI_SCALE) {
-#pragma unroll
-                    for (int j = 0; j < 16; ++j) v[j] *= args.alpha;
-                }
-                const int ncol = args.N_out - col0 < 16 ? args.N_out - col0 : 16;
-                if (geglu) {
-#pragma unroll
-                    for (int j = 0; j < 16; ++j) {
-                        float g = __uint_as_float(r1[j]);
-                        if (args.bias) { v[j] += bias_s[ch * 16 + j]; g += bias_s[BN / 2 + ch * 16 + j]; }
-                        v[j] *= gelu_fast(g);
-                    }
-                } else if (args.bias) {
-#pragma unroll
-                    for (int j = 0; j < 16; ++j) v[j] += bias_s[ch * 16 + j];
-                }
-                if (rb_row) for (int j = 0; j < ncol; ++j) v[j] += __ldg(rb_row + col0 + j);
-                if (args.residual) {
-                    if (res_f32) {
-                        const float* rp = reinterpret_cast<const float*>(args.residual) + zoff_r + orow * args.ldr + col0;
-                        for (int j = 0; j < ncol; ++j) v[j] += __ldg(rp + j);
-                    } else {
-                        const __nv_bfloat16* rp = reinterpret_cast<const __nv_bfloat16*>(args.residual) + zoff_r + orow * args.ldr + col0;
-                        for (int j = 0; j < ncol; ++j) v[j] += __bfloat162float(rp[j]);
-                    }
-                }
-                if (out_f32) {
-                    float* op = reinterpret_cast<float*>(args.out) + zoff_o + orow * args.ldo + col0;
-                    for (int j = 0; j < ncol; ++j) op[j] = v[j];
-                } else {
-                    __nv_bfloat16* op = reinterpret_cast<__nv_bfloat16*>(args.out) + zoff_o + orow * args.ldo + col0;
-                    for (int j = 0; j < ncol; ++j) op[j] = __float2bfloat16(v[j]);
+                // this thread is done with its private residual row: stream in the next sub-tile's / next tile's chunks
+                if (s + 1 < MT) {
+                    prefetch_residual(ti, row_info(ti, s + 1));
+                } else if (tile + (int)gridDim.x < num_tiles) {
+                    const TileInfo tn = tile_info(tile + gridDim.x);
+                    prefetch_residual(tn, row_info(tn, 0));
                 }
             }
+            // accumulator set drained -> the MMA warp may start the tile after next into it
+            tc_fence_before();
+            mbar_arrive(&acc_empty[ab]);
         }
         tc_fence_before();
     }
@@ -426,8 +482,19 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__ 
     }
 }
 
+int sm_count() {
+    static int sms = 0;
+    if (!sms) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        if (sms <= 0) sms = 148;
+    }
+    return sms;
+}
+
 template <int MT, int BN, int STAGES, int RB>
-int launch(const CUtensorMap* maps_a, const CUtensorMap& map_w, const KernelArgs& args, dim3 grid, cudaStream_t st) {
+int launch(const CUtensorMap* maps_a, const CUtensorMap& map_w, const KernelArgs& args, cudaStream_t st) {
     static bool configured = false;
     constexpr size_t smem = Plan<MT, BN, STAGES, RB>::TOTAL;
     if (!configured) {
@@ -435,6 +502,8 @@ int launch(const CUtensorMap* maps_a, const CUtensorMap& map_w, const KernelArgs
         if (e != cudaSuccess) { set_last_error("gemm: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return kErrCuda; }
         configured = true;
     }
+    const int64_t tiles = (int64_t)args.tiles_mt * args.tiles_n * args.gz;
+    const int grid = (int)(tiles < sm_count() ? tiles : sm_count());  // persistent: one CTA per SM
     gemm_kernel<MT, BN, STAGES, RB><<<grid, 320, smem, st>>>(maps_a[0], maps_a[1], maps_a[2], maps_a[3], map_w, args);
     count_launch(1);
     return check_launch("gemm_kernel");
@@ -442,17 +511,20 @@ int launch(const CUtensorMap* maps_a, const CUtensorMap& map_w, const KernelArgs
 
 // tiles_m = number of 128-row tiles; picks the CTA tile and launches
 int launch_cfg(int bn, int64_t tiles_m, int64_t tiles_n, unsigned gz, const CUtensorMap* maps_a, const CUtensorMap& map_w,
-               const KernelArgs& args, cudaStream_t st) {
-    // 256-row CTA tiles (two TMEM accumulators, B tile reused) when that still fills the 148 SMs; the fp32 residual
-    // stream needs the larger private-row buffer, which only fits next to the 128-row pipeline
+               KernelArgs args, cudaStream_t st) {
+    // 256-row CTA tiles (two accumulators per tile, B tile reused) for long K loops that still fill the 148 SMs; short K loops
+    // keep 128-row tiles with two accumulator SETS so the epilogue overlaps the next tile's main loop.  The fp32 residual
+    // stream needs the larger private-row buffer, which only fits next to the 128-row pipeline.
     const bool res_f32 = args.residual && (args.flags & GMD_EPI_RESIDUAL_F32);
-    const bool mt2 = (bn == 160 || bn == 128) && !res_f32 && tiles_m >= 2 && ((tiles_m + 1) / 2) * tiles_n * gz >= 120;
-    dim3 grid((unsigned)(mt2 ? (tiles_m + 1) / 2 : tiles_m), (unsigned)tiles_n, gz);
+    const bool mt2 = (bn == 160 || bn == 128) && !res_f32 && tiles_m >= 2 && args.num_kb >= 24 && ((tiles_m + 1) / 2) * tiles_n * gz >= 120;
+    args.tiles_mt = (int)(mt2 ? (tiles_m + 1) / 2 : tiles_m);
+    args.tiles_n = (int)tiles_n;
+    args.gz = (int)gz;
     switch (bn) {
-        case 160: return mt2 ? launch<2, 160, 3, 2>(maps_a, map_w, args, grid, st) : launch<1, 160, 3, 4>(maps_a, map_w, args, grid, st);
-        case 128: return mt2 ? launch<2, 128, 3, 2>(maps_a, map_w, args, grid, st) : launch<1, 128, 4, 4>(maps_a, map_w, args, grid, st);
-        case 64: return launch<1, 64, 6, 4>(maps_a, map_w, args, grid, st);
-        case 32: return launch<1, 32, 6, 4>(maps_a, map_w, args, grid, st);
+        case 160: return mt2 ? launch<2, 160, 3, 2>(maps_a, map_w, args, st) : launch<1, 160, 3, 4>(maps_a, map_w, args, st);
+        case 128: return mt2 ? launch<2, 128, 3, 2>(maps_a, map_w, args, st) : launch<1, 128, 4, 4>(maps_a, map_w, args, st);
+        case 64: return launch<1, 64, 6, 4>(maps_a, map_w, args, st);
+        case 32: return launch<1, 32, 6, 4>(maps_a, map_w, args, st);
         default: set_last_error("gemm: unsupported N tile %d", bn); return kErrUnsupported;
     }
 }
