@@ -60,6 +60,15 @@ def load_peaks():
     return 1400.0, 6650.0, "fallback (B200_PROFILING.md)"
 
 
+def ncu_traffic():
+    """DRAM bytes per launch of the dominant kernel from the committed `ncu --set full` capture (profiles/), or None."""
+    p = ROOT / "profiles" / "roofline_traffic.json"
+    try:
+        return json.loads(p.read_text())
+    except Exception:
+        return None
+
+
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
 
@@ -323,7 +332,7 @@ def run_b200(args):
     ach_tf = gm_["flop"] / (gm_["ms"] * 1e-3) / 1e12
     roofline = {"bound": "tensor", "kernel": "gmd::gemm_kernel<BN,STAGES> (tcgen05 GEMM + implicit-GEMM conv; all instantiations)",
                 "achieved": ach_tf, "peak": peak_tf, "unit": "TFLOP/s", "frac": ach_tf / peak_tf, "peak_source": peak_src,
-                "traffic": None, "launches_per_denoise_step": gm_["launches"], "avg_launch_ms": gm_["ms"] / gm_["launches"],
+                "traffic": ncu_traffic(), "launches_per_denoise_step": gm_["launches"], "avg_launch_ms": gm_["ms"] / gm_["launches"],
                 "algorithmic_gflop_per_denoise_step": gm_["flop"] / 1e9, "share_of_step": gm_["ms"] / tot_ms}
     at = fam.get("attn", {"ms": 1e-9, "flop": 0.0, "launches": 1})
     kernels = {k: {"ms_per_denoise_step": round(v["ms"], 3), "share": round(v["ms"] / tot_ms, 4), "launches": v["launches"],
