@@ -260,6 +260,7 @@ def instrumented_step(pipe, B):
 
 
 def run_b200(args):
+    os.environ["NCCL_DEBUG"] = "WARN"  # keep NCCL's version banner off stdout: rank 0 prints exactly one JSON line
     from gm_diffusion_b200 import _lib as L
     from gm_diffusion_b200 import dist as D
     rank, local, world = D.init_from_env()

@@ -66,22 +66,38 @@ struct Plan {
     static constexpr int A_BYTES = MT * A_SUB;
     static constexpr int B_BYTES = BN * BK * 2;
     static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-    static constexpr int RES_ROW = BN * RB;                  // bytes of one thread-private residual row
+    static constexpr int RES_ROW = BN * RB + 16;             // bytes of one private residual row (+16: rows 8 apart share banks, not all)
     static constexpr int OFF_RES = STAGES * STAGE_BYTES;
     static constexpr int OFF_BIAS = OFF_RES + BM * RES_ROW;  // BN floats
     static constexpr int OFF_BARS = OFF_BIAS + BN * 4;
     static constexpr int ACC = 2 * MT * BN <= 512 ? 2 : 1;   // TMEM accumulator sets (2 = epilogue overlaps the next tile's main loop)
     static constexpr int ACC_COLS = MT * BN;
-    static constexpr int TOTAL = OFF_BARS + (2 * STAGES + 4) * 8 + 16 + 1024;
+    static constexpr int TOTAL = OFF_BARS + (2 * STAGES + 5) * 8 + 16 + 1024;
     static constexpr uint32_t TMEM_COLS = ACC * ACC_COLS <= 32 ? 32 : ACC * ACC_COLS <= 64 ? 64 : ACC * ACC_COLS <= 128 ? 128 : ACC * ACC_COLS <= 256 ? 256 : 512;
     static_assert(ACC * ACC_COLS <= 512, "accumulators exceed TMEM");
     static_assert(TOTAL <= 232448, "shared memory plan exceeds 227 KB");
 };
 
-__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(smem_dst)), "l"(gsrc) : "memory");
+// 1-D bulk copy global -> shared (TMA engine, UBLKCP), completion counted in bytes on an mbarrier
+__device__ __forceinline__ void bulk_copy_g2s(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(smem_dst)), "l"(gsrc),
+                 "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
 }
-__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+// 256-bit global store (STG.256, sm_100): one full 32-byte sector per thread per instruction
+__device__ __forceinline__ void st_global_256(void* p, uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t a4, uint32_t a5, uint32_t a6,
+                                              uint32_t a7) {
+    asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(a4), "r"(a5), "r"(a6), "r"(a7)
+                 : "memory");
+}
+__device__ __forceinline__ void st_f32x8(float* p, const float* v) {
+    st_global_256(p, __float_as_uint(v[0]), __float_as_uint(v[1]), __float_as_uint(v[2]), __float_as_uint(v[3]), __float_as_uint(v[4]),
+                  __float_as_uint(v[5]), __float_as_uint(v[6]), __float_as_uint(v[7]));
+}
+__device__ __forceinline__ void st_bf16x16(__nv_bfloat16* p, const float* v) {
+    st_global_256(p, pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7]), pack_bf16x2(v[8], v[9]),
+                  pack_bf16x2(v[10], v[11]), pack_bf16x2(v[12], v[13]), pack_bf16x2(v[14], v[15]));
+}
 
 // PERSISTENT kernel: one CTA per SM loops over output tiles (tile = blockIdx.x, += gridDim.x).  CTA tile = (MT*128) x BN.
 //   * MT = 2 keeps TWO accumulators per tile and issues two MMAs per B tile: the B operand bytes fetched from L2 are
@@ -105,7 +121,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__ 
     uint64_t* empty_bar = full_bar + STAGES;
     uint64_t* acc_full = empty_bar + STAGES;   // [2]
     uint64_t* acc_empty = acc_full + 2;        // [2]
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
+    uint64_t* res_bar = acc_empty + 2;         // residual prefetch rounds
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(res_bar + 1);
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -116,6 +133,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__ 
         tma_prefetch_desc(&map_w);
         for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
         for (int s = 0; s < 2; ++s) { mbar_init(&acc_full[s], 1); mbar_init(&acc_empty[s], 256); }
+        mbar_init(res_bar, 256);
         fence_barrier_init();
     }
     if (warp == 1) tmem_alloc<P::TMEM_COLS>(tmem_slot);
@@ -237,17 +255,16 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__ 
         const int out_cols_tile = geglu ? BN / 2 : BN;
         const int res_esize = res_f32 ? 4 : 2;
         const int out_esize = out_f32 ? 4 : 2;
-        constexpr int RES_NCHUNK = P::RES_ROW / 16;                  // physical 16-byte chunks per private row
         const int cw = geglu ? 16 : 32;                              // output columns per chunk
         const int nchunks = (out_cols_tile + cw - 1) / cw;
-        const int res_cpc = cw * res_esize / 16;                     // 16-byte residual chunks per column chunk
+        // the two warps of a lane group own contiguous halves of the tile's column chunks
+        const int c_begin = half ? (nchunks + 1) / 2 : 0;
+        const int c_end = half ? nchunks : (nchunks + 1) / 2;
         const uint32_t taddr_lane = tmem_acc + (static_cast<uint32_t>(lg * 32) << 16);
         uint8_t* my_res = res_s + row * P::RES_ROW;
-        const int rowmod = row % RES_NCHUNK;
-        auto phys = [&](int k) { int i = rowmod + k; return i >= RES_NCHUNK ? i - RES_NCHUNK : i; };
-        const bool ptrs_ok = ((reinterpret_cast<uintptr_t>(args.out) & 15) == 0) && ((args.ldo * out_esize) % 16 == 0) &&
+        const bool ptrs_ok = ((reinterpret_cast<uintptr_t>(args.out) & 31) == 0) && ((args.ldo * out_esize) % 32 == 0) &&
                              (!args.row_bias || (((reinterpret_cast<uintptr_t>(args.row_bias) & 15) == 0) && (args.ld_row_bias % 4 == 0)));
-        const bool res_ptr_ok = args.residual && (BN * res_esize <= P::RES_ROW) && ((reinterpret_cast<uintptr_t>(args.residual) & 15) == 0) &&
+        const bool res_ptr_ok = args.residual && (BN * res_esize + 16 <= P::RES_ROW) && ((reinterpret_cast<uintptr_t>(args.residual) & 15) == 0) &&
                                 ((args.ldr * res_esize) % 16 == 0);
 
         struct TileInfo { int mt, n0, zb, out_col_tile; bool tile_full, res_async, fast; int64_t zoff_o, zoff_r; };
@@ -262,7 +279,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__ 
             ti.zoff_o = args.mode == 0 ? (int64_t)ti.zb * args.batch_stride_o : 0;
             ti.zoff_r = args.mode == 0 ? (int64_t)ti.zb * args.batch_stride_r : 0;
             ti.res_async = res_ptr_ok && ti.tile_full && ((ti.zoff_r * res_esize) % 16 == 0);
-            ti.fast = ti.tile_full && ptrs_ok && (!args.residual || ti.res_async) && ((ti.zoff_o * out_esize) % 16 == 0);
+            ti.fast = ti.tile_full && ptrs_ok && (!args.residual || ti.res_async) && ((ti.zoff_o * out_esize) % 32 == 0);
             return ti;
         };
         struct RowInfo { bool ok; int64_t out_row, sample; };
@@ -287,12 +304,24 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__ 
             }
             return ri;
         };
+        // One prefetch ROUND: every epilogue thread arrives on res_bar (256 arrivals), threads with a valid row add the byte
+        // count of ONE bulk copy (their contiguous column range of their own row).  Issued by a thread only after it has
+        // finished reading its private row for the previous round, so rounds never overlap in a row.
+        uint32_t res_round = 0;   // rounds issued by this thread (uniform across the epilogue threads)
         auto prefetch_residual = [&](const TileInfo& ti, const RowInfo& ri) {
-            if (!ti.res_async || !ri.ok) return;
-            const uint8_t* src = reinterpret_cast<const uint8_t*>(args.residual) + (ti.zoff_r + ri.out_row * args.ldr + ti.out_col_tile) * res_esize;
-            for (int c = half; c < nchunks; c += 2)
-                for (int j = 0; j < res_cpc; ++j) cp_async16(my_res + phys(c * res_cpc + j) * 16, src + (c * res_cpc + j) * 16);
+            if (!ti.res_async) return;
+            const uint32_t bytes = (uint32_t)((c_end - c_begin) * cw * res_esize);
+            if (ri.ok && bytes > 0) {
+                const uint8_t* src = reinterpret_cast<const uint8_t*>(args.residual) +
+                                     (ti.zoff_r + ri.out_row * args.ldr + ti.out_col_tile + c_begin * cw) * res_esize;
+                mbar_expect_tx(res_bar, bytes);
+                bulk_copy_g2s(my_res + c_begin * cw * res_esize, src, bytes, res_bar);
+            } else {
+                mbar_arrive(res_bar);
+            }
+            ++res_round;
         };
+        uint32_t res_waited = 0;
 
         uint32_t it = 0;
         if ((int)blockIdx.x < num_tiles) {
@@ -321,7 +350,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__ 
 #pragma unroll 1
             for (int s = 0; s < MT; ++s) {
                 const RowInfo ri = row_info(ti, s);
-                cp_async_wait_all();
+                if (ti.res_async) { mbar_wait(res_bar, res_waited & 1); ++res_waited; }
                 const bool row_ok = ri.ok;
                 const int64_t orow = ri.out_row;
                 const float* rb_row = args.row_bias ? args.row_bias + ri.sample * args.ld_row_bias : nullptr;
@@ -329,7 +358,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__ 
                 if (fast) {
                     if (geglu) {
 #pragma unroll 1
-                        for (int c = half; c < nchunks; c += 2) {
+                        for (int c = c_begin; c < c_end; ++c) {
                             uint32_t r0[16], r1[16];
                             tmem_ld_32x16(tsub + c * 16, r0);
                             tmem_ld_32x16(tsub + BN / 2 + c * 16, r1);
@@ -348,20 +377,15 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__ 
                             }
                             const int col0 = out_col_tile + c * 16;
                             if (out_f32) {
-                                float4* op = reinterpret_cast<float4*>(reinterpret_cast<float*>(args.out) + zoff_o + orow * args.ldo + col0);
-#pragma unroll
-                                for (int j = 0; j < 4; ++j) op[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+                                float* op = reinterpret_cast<float*>(args.out) + zoff_o + orow * args.ldo + col0;
+                                st_f32x8(op, v); st_f32x8(op + 8, v + 8);
                             } else {
-                                uint4* op = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(args.out) + zoff_o + orow * args.ldo + col0);
-#pragma unroll
-                                for (int j = 0; j < 2; ++j)
-                                    op[j] = make_uint4(pack_bf16x2(v[8 * j], v[8 * j + 1]), pack_bf16x2(v[8 * j + 2], v[8 * j + 3]),
-                                                       pack_bf16x2(v[8 * j + 4], v[8 * j + 5]), pack_bf16x2(v[8 * j + 6], v[8 * j + 7]));
+                                st_bf16x16(reinterpret_cast<__nv_bfloat16*>(args.out) + zoff_o + orow * args.ldo + col0, v);
                             }
                         }
                     } else {
 #pragma unroll 1
-                        for (int c = half; c < nchunks; c += 2) {
+                        for (int c = c_begin; c < c_end; ++c) {
                             uint32_t r[32];
                             tmem_ld_32x32(tsub + c * 32, r);
                             tmem_wait_ld();
@@ -388,28 +412,25 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__ 
                                 if (res_f32) {
 #pragma unroll
                                     for (int j = 0; j < 8; ++j) {
-                                        float4 a = *reinterpret_cast<const float4*>(my_res + phys(c * 8 + j) * 16);
+                                        float4 a = *reinterpret_cast<const float4*>(my_res + (c * 8 + j) * 16);
                                         v[4 * j] += a.x; v[4 * j + 1] += a.y; v[4 * j + 2] += a.z; v[4 * j + 3] += a.w;
                                     }
                                 } else {
 #pragma unroll
                                     for (int j = 0; j < 4; ++j) {
-                                        uint4 a = *reinterpret_cast<const uint4*>(my_res + phys(c * 4 + j) * 16);
+                                        uint4 a = *reinterpret_cast<const uint4*>(my_res + (c * 4 + j) * 16);
                                         v[8 * j + 0] += bf16_lo(a.x); v[8 * j + 1] += bf16_hi(a.x); v[8 * j + 2] += bf16_lo(a.y); v[8 * j + 3] += bf16_hi(a.y);
                                         v[8 * j + 4] += bf16_lo(a.z); v[8 * j + 5] += bf16_hi(a.z); v[8 * j + 6] += bf16_lo(a.w); v[8 * j + 7] += bf16_hi(a.w);
                                     }
                                 }
                             }
                             if (out_f32) {
-                                float4* op = reinterpret_cast<float4*>(reinterpret_cast<float*>(args.out) + zoff_o + orow * args.ldo + col0);
+                                float* op = reinterpret_cast<float*>(args.out) + zoff_o + orow * args.ldo + col0;
 #pragma unroll
-                                for (int j = 0; j < 8; ++j) op[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+                                for (int j = 0; j < 4; ++j) st_f32x8(op + 8 * j, v + 8 * j);
                             } else {
-                                uint4* op = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(args.out) + zoff_o + orow * args.ldo + col0);
-#pragma unroll
-                                for (int j = 0; j < 4; ++j)
-                                    op[j] = make_uint4(pack_bf16x2(v[8 * j], v[8 * j + 1]), pack_bf16x2(v[8 * j + 2], v[8 * j + 3]),
-                                                       pack_bf16x2(v[8 * j + 4], v[8 * j + 5]), pack_bf16x2(v[8 * j + 6], v[8 * j + 7]));
+                                __nv_bfloat16* op = reinterpret_cast<__nv_bfloat16*>(args.out) + zoff_o + orow * args.ldo + col0;
+                                st_bf16x16(op, v); st_bf16x16(op + 16, v + 16);
                             }
                         }
                     }
