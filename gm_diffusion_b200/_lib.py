@@ -46,14 +46,15 @@ class GemmParams(C.Structure):
     _fields_ = [("a", _vp), ("lda", _i64), ("w", _vp), ("ldw", _i64), ("out", _vp), ("ldo", _i64),
                 ("bias", _vp), ("row_bias", _vp), ("ld_row_bias", _i64), ("rows_per_sample", _i64),
                 ("residual", _vp), ("ldr", _i64), ("M", _i64), ("N", _i64), ("K", _i64), ("batch", _i64),
-                ("stride_a", _i64), ("stride_w", _i64), ("stride_o", _i64), ("flags", _i32), ("alpha", _f32)]
+                ("stride_a", _i64), ("stride_w", _i64), ("stride_o", _i64), ("flags", _i32), ("alpha", _f32),
+                ("workspace", _vp), ("workspace_bytes", _i64), ("w_tiled", _i32)]
 
 
 class ConvParams(C.Structure):
     _fields_ = [("x0", _vp), ("C0", _i32), ("x1", _vp), ("C1", _i32), ("w", _vp), ("out", _vp), ("bias", _vp),
                 ("row_bias", _vp), ("ld_row_bias", _i64), ("residual", _vp), ("N", _i32), ("H", _i32), ("W", _i32),
                 ("Cout", _i32), ("Cout_pad", _i32), ("ksize", _i32), ("stride", _i32), ("upsample", _i32),
-                ("flags", _i32)]
+                ("flags", _i32), ("workspace", _vp), ("workspace_bytes", _i64), ("w_tiled", _i32)]
 
 
 class AttnParams(C.Structure):

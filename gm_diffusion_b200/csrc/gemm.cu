@@ -47,6 +47,10 @@ struct KernelArgs {
     float alpha;
     // persistent tile loop: tile -> (super-tile along M, N tile, z)
     int tiles_mt, tiles_n, gz;
+    // split-K: tile also carries a K slice; partial sums go to an fp32 workspace and are reduced by splitk_finalize_kernel
+    int ksplit, kb_per_split;
+    int64_t split_stride_o;   // elements between the partial-sum planes
+    int w_tiled;              // weights pre-tiled as [N tile][k block][BN][64]: every B tile is one contiguous 128*BN-byte read
 };
 
 // exact-erf GELU with erf from Abramowitz-Stegun 7.1.26 (|abs err| <= 1.5e-7, two MUFU ops): erff() costs ~60
@@ -126,7 +130,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__ 
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
-    const int num_tiles = args.tiles_mt * args.tiles_n * args.gz;
+    const int num_tiles = args.tiles_mt * args.tiles_n * args.gz * args.ksplit;
 
     if (threadIdx.x == 0) {
         tma_prefetch_desc(&map_a0);
@@ -151,7 +155,10 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__ 
                 const int mt = tile % args.tiles_mt;
                 const int rest = tile / args.tiles_mt;
                 const int n0 = (rest % args.tiles_n) * BN;
-                const int zb = rest / args.tiles_n;
+                const int zk = rest / args.tiles_n;
+                const int zb = zk % args.gz, ksl = zk / args.gz;
+                const int kb_begin = ksl * args.kb_per_split;
+                const int kb_end = min(args.num_kb, kb_begin + args.kb_per_split);
                 int m0[MT], tw0[MT], th0[MT], tn0[MT];
 #pragma unroll
                 for (int s = 0; s < MT; ++s) {
@@ -161,7 +168,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__ 
                     int th = t % args.tiles_h; t /= args.tiles_h;
                     tw0[s] = tw * args.bw; th0[s] = th * args.bh; tn0[s] = t * args.bn;
                 }
-                for (int kb = 0; kb < args.num_kb; ++kb, ++kbg) {
+                for (int kb = kb_begin; kb < kb_end; ++kb, ++kbg) {
                     const int stage = kbg % STAGES;
                     const uint32_t phase = (kbg / STAGES) & 1;
                     mbar_wait(&empty_bar[stage], phase ^ 1);
@@ -174,7 +181,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__ 
                             if (kb < args.kb_src0) tma_load_3d(sa + s * P::A_SUB, &map_a0, &full_bar[stage], kb * BK, m0[s], zb);
                             else tma_load_3d(sa + s * P::A_SUB, &map_a1, &full_bar[stage], (kb - args.kb_src0) * BK, m0[s], zb);
                         }
-                        tma_load_3d(sb, &map_w, &full_bar[stage], kb * BK, n0, zb);
+                        if (args.w_tiled) tma_load_3d(sb, &map_w, &full_bar[stage], 0, ((n0 / BN) * args.num_kb + kb) * BN, 0);
+                        else tma_load_3d(sb, &map_w, &full_bar[stage], kb * BK, n0, zb);
                     } else {
                         const int tap = kb / chunks_per_tap;
                         const int cc = kb - tap * chunks_per_tap;
@@ -203,7 +211,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__ 
 #pragma unroll
                         for (int s = 0; s < MT; ++s)
                             tma_load_4d(sa + s * P::A_SUB, map, &full_bar[stage], c, tw0[s] + dw, th0[s] + dh, tn0[s]);
-                        tma_load_3d(sb, &map_w, &full_bar[stage], tap * args.ctot + cc * BK, n0, 0);
+                        if (args.w_tiled) tma_load_3d(sb, &map_w, &full_bar[stage], 0, ((n0 / BN) * args.num_kb + kb) * BN, 0);
+                        else tma_load_3d(sb, &map_w, &full_bar[stage], tap * args.ctot + cc * BK, n0, 0);
                     }
                 }
             }
@@ -217,7 +226,10 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__ 
                 mbar_wait(&acc_empty[ab], ((it / ACC) & 1) ^ 1);   // epilogue has drained this accumulator set
                 tc_fence_after();
                 const uint32_t tacc = tmem_acc + ab * P::ACC_COLS;
-                for (int kb = 0; kb < args.num_kb; ++kb, ++kbg) {
+                const int ksl = tile / (args.tiles_mt * args.tiles_n * args.gz);
+                const int kb_begin = ksl * args.kb_per_split;
+                const int kb_end = min(args.num_kb, kb_begin + args.kb_per_split);
+                for (int kb = kb_begin; kb < kb_end; ++kb, ++kbg) {
                     const int stage = kbg % STAGES;
                     const uint32_t phase = (kbg / STAGES) & 1;
                     mbar_wait(&full_bar[stage], phase);
@@ -230,7 +242,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__ 
                         for (int s = 0; s < MT; ++s) {
                             // +32 bytes per K=16 step inside the 128-byte swizzle row (address field is >> 4)
                             const uint64_t da = umma_desc_k_sw128(sa + s * P::A_SUB);
-                            umma_bf16_ss(tacc + s * BN, da + 2 * k, db + 2 * k, IDESC, (kb | k) != 0 ? 1u : 0u);
+                            umma_bf16_ss(tacc + s * BN, da + 2 * k, db + 2 * k, IDESC, (kb > kb_begin || k != 0) ? 1u : 0u);
                         }
                     }
                     umma_commit(&empty_bar[stage]);  // frees the smem slot once these MMAs have read it
@@ -273,10 +285,11 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__ 
             ti.mt = tile % args.tiles_mt;
             const int rest = tile / args.tiles_mt;
             const int nt = rest % args.tiles_n;
-            ti.n0 = nt * BN; ti.zb = rest / args.tiles_n;
+            const int zk = rest / args.tiles_n;
+            ti.n0 = nt * BN; ti.zb = zk % args.gz;
             ti.out_col_tile = geglu ? nt * (BN / 2) : ti.n0;
             ti.tile_full = ti.out_col_tile + out_cols_tile <= args.N_out && (out_cols_tile % cw) == 0;
-            ti.zoff_o = args.mode == 0 ? (int64_t)ti.zb * args.batch_stride_o : 0;
+            ti.zoff_o = (args.mode == 0 ? (int64_t)ti.zb * args.batch_stride_o : 0) + (int64_t)(zk / args.gz) * args.split_stride_o;
             ti.zoff_r = args.mode == 0 ? (int64_t)ti.zb * args.batch_stride_r : 0;
             ti.res_async = res_ptr_ok && ti.tile_full && ((ti.zoff_r * res_esize) % 16 == 0);
             ti.fast = ti.tile_full && ptrs_ok && (!args.residual || ti.res_async) && ((ti.zoff_o * out_esize) % 32 == 0);
@@ -503,6 +516,39 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__ 
     }
 }
 
+// Deterministic split-K reduction + the fused epilogue (bias, time-embedding row bias, residual) in one elementwise pass.
+__global__ void __launch_bounds__(256) splitk_finalize_kernel(const float* __restrict__ ws, int ksplit, int64_t split_stride, int64_t rows, int N,
+                                                              const float* __restrict__ bias, const float* __restrict__ row_bias, int64_t ld_row_bias,
+                                                              int64_t rows_per_sample, const void* __restrict__ residual, int res_f32, void* __restrict__ out,
+                                                              int out_f32) {
+    const int n4 = N / 4;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < rows * n4; i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t r = i / n4;
+        const int c = (int)(i - r * n4) * 4;
+        float4 acc = __ldg(reinterpret_cast<const float4*>(ws + r * N + c));
+        for (int k = 1; k < ksplit; ++k) {
+            float4 t = __ldg(reinterpret_cast<const float4*>(ws + k * split_stride + r * N + c));
+            acc.x += t.x; acc.y += t.y; acc.z += t.z; acc.w += t.w;
+        }
+        if (bias) { float4 b = __ldg(reinterpret_cast<const float4*>(bias + c)); acc.x += b.x; acc.y += b.y; acc.z += b.z; acc.w += b.w; }
+        if (row_bias) {
+            float4 b = __ldg(reinterpret_cast<const float4*>(row_bias + (r / rows_per_sample) * ld_row_bias + c));
+            acc.x += b.x; acc.y += b.y; acc.z += b.z; acc.w += b.w;
+        }
+        if (residual) {
+            if (res_f32) {
+                float4 b = __ldg(reinterpret_cast<const float4*>(reinterpret_cast<const float*>(residual) + r * N + c));
+                acc.x += b.x; acc.y += b.y; acc.z += b.z; acc.w += b.w;
+            } else {
+                uint2 b = __ldg(reinterpret_cast<const uint2*>(reinterpret_cast<const __nv_bfloat16*>(residual) + r * N + c));
+                acc.x += bf16_lo(b.x); acc.y += bf16_hi(b.x); acc.z += bf16_lo(b.y); acc.w += bf16_hi(b.y);
+            }
+        }
+        if (out_f32) *reinterpret_cast<float4*>(reinterpret_cast<float*>(out) + r * N + c) = acc;
+        else *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(out) + r * N + c) = make_uint2(pack_bf16x2(acc.x, acc.y), pack_bf16x2(acc.z, acc.w));
+    }
+}
+
 int sm_count() {
     static int sms = 0;
     if (!sms) {
@@ -541,6 +587,7 @@ int launch_cfg(int bn, int64_t tiles_m, int64_t tiles_n, unsigned gz, const CUte
     args.tiles_mt = (int)(mt2 ? (tiles_m + 1) / 2 : tiles_m);
     args.tiles_n = (int)tiles_n;
     args.gz = (int)gz;
+    if (args.ksplit < 1) { args.ksplit = 1; args.kb_per_split = args.num_kb; args.split_stride_o = 0; }
     switch (bn) {
         case 160: return mt2 ? launch<2, 160, 3, 2>(maps_a, map_w, args, st) : launch<1, 160, 3, 4>(maps_a, map_w, args, st);
         case 128: return mt2 ? launch<2, 128, 3, 2>(maps_a, map_w, args, st) : launch<1, 128, 4, 4>(maps_a, map_w, args, st);
@@ -560,6 +607,28 @@ int pick_bn(int64_t n_rows, bool geglu) {
 
 inline bool al16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
 
+// Split the K loop over several CTAs when the output has too few tiles to fill the machine (8x8-resolution layers: 32-64
+// tiles, 90-360 k-blocks each).  Returns the number of splits (1 = none) for a problem whose epilogue the finalize kernel can do.
+int plan_splitk(int64_t tiles, int num_kb, int64_t rows, int N, const void* workspace, int64_t workspace_bytes, bool plain_layout) {
+    if (!workspace || !plain_layout || tiles >= 100 || num_kb < 32 || (N % 4)) return 1;
+    int ks = (int)(sm_count() / tiles);
+    if (ks > num_kb / 16) ks = num_kb / 16;
+    if (ks > 8) ks = 8;
+    while (ks > 1 && (int64_t)ks * rows * N * 4 > workspace_bytes) --ks;
+    return ks < 2 ? 1 : ks;
+}
+
+int launch_finalize(const KernelArgs& a, const float* ws, int ksplit, int64_t rows, int N, const float* bias, const float* row_bias,
+                    int64_t ld_row_bias, int64_t rows_per_sample, const void* residual, bool res_f32, void* out, bool out_f32, cudaStream_t st) {
+    int64_t items = rows * (N / 4);
+    int grid = (int)((items + 255) / 256);
+    if (grid > sm_count() * 8) grid = sm_count() * 8;
+    splitk_finalize_kernel<<<grid, 256, 0, st>>>(ws, ksplit, rows * N, rows, N, bias, row_bias, ld_row_bias, rows_per_sample, residual, res_f32 ? 1 : 0,
+                                                 out, out_f32 ? 1 : 0);
+    count_launch(1);
+    return check_launch("splitk_finalize");
+}
+
 }  // namespace
 }  // namespace gmd
 
@@ -567,7 +636,7 @@ extern "C" int gmd_gemm_fwd(const gmd_gemm_params* p, void* stream) {
     using namespace gmd;
     if (!p || !p->a || !p->w || !p->out) { set_last_error("gmd_gemm_fwd: null pointer"); return kErrInvalid; }
     if (p->M <= 0 || p->N <= 0 || p->K <= 0) { set_last_error("gmd_gemm_fwd: empty problem M=%lld N=%lld K=%lld", (long long)p->M, (long long)p->N, (long long)p->K); return kErrInvalid; }
-    if (p->K % 8 || p->lda % 8 || p->ldw % 8 || !al16(p->a) || !al16(p->w)) {
+    if (p->K % 8 || p->lda % 8 || (!p->w_tiled && (p->ldw % 8)) || !al16(p->a) || !al16(p->w)) {
         set_last_error("gmd_gemm_fwd: K, lda, ldw must be multiples of 8 and A, W 16-byte aligned (TMA)"); return kErrInvalid;
     }
     const bool geglu = p->flags & GMD_EPI_GEGLU;
@@ -585,7 +654,15 @@ extern "C" int gmd_gemm_fwd(const gmd_gemm_params* p, void* stream) {
         if (rc) return rc;
         maps_a[1] = maps_a[2] = maps_a[3] = maps_a[0];
     }
-    {
+    if (p->w_tiled) {
+        if (p->w_tiled != bn || batch != 1) { set_last_error("gmd_gemm_fwd: tiled weights were packed for N tile %d, kernel picks %d (batch %lld)", p->w_tiled, bn, (long long)batch); return kErrInvalid; }
+        const uint64_t total_rows = (uint64_t)((p->N + bn - 1) / bn) * ((p->K + BK - 1) / BK) * bn;
+        uint64_t dims[3] = {BK, total_rows, 1};
+        uint64_t strides[3] = {2, BK * 2, total_rows * BK * 2};
+        uint32_t box[3] = {BK, (uint32_t)bn, 1};
+        int rc = encode_tensor_map_bf16(&map_w, p->w, 3, dims, strides, box, true);
+        if (rc) return rc;
+    } else {
         uint64_t dims[3] = {(uint64_t)p->K, (uint64_t)p->N, (uint64_t)batch};
         uint64_t strides[3] = {2, (uint64_t)p->ldw * 2, (uint64_t)(batch > 1 ? p->stride_w : p->ldw * p->N) * 2};
         uint32_t box[3] = {BK, (uint32_t)bn, 1};
@@ -594,6 +671,7 @@ extern "C" int gmd_gemm_fwd(const gmd_gemm_params* p, void* stream) {
     }
     KernelArgs a{};
     a.mode = 0;
+    a.w_tiled = p->w_tiled ? 1 : 0;
     a.num_kb = (int)((p->K + BK - 1) / BK);
     a.kb_src0 = a.num_kb;
     a.M = p->M;
@@ -610,7 +688,21 @@ extern "C" int gmd_gemm_fwd(const gmd_gemm_params* p, void* stream) {
     if ((p->flags & GMD_EPI_BIAS) && !p->bias) { set_last_error("gmd_gemm_fwd: BIAS flag without bias"); return kErrInvalid; }
     if ((p->flags & GMD_EPI_RESIDUAL) && !p->residual) { set_last_error("gmd_gemm_fwd: RESIDUAL flag without residual"); return kErrInvalid; }
     if ((p->flags & GMD_EPI_ROW_BIAS) && (!p->row_bias || p->rows_per_sample <= 0)) { set_last_error("gmd_gemm_fwd: ROW_BIAS needs row_bias and rows_per_sample"); return kErrInvalid; }
-    return launch_cfg(bn, (p->M + BM - 1) / BM, (p->N + bn - 1) / bn, (unsigned)batch, maps_a, map_w, a, static_cast<cudaStream_t>(stream));
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const int64_t tiles_m = (p->M + BM - 1) / BM, tiles_n = (p->N + bn - 1) / bn;
+    const bool plain = batch == 1 && !geglu && !(p->flags & GMD_EPI_SCALE) && p->ldo == p->N && (!a.residual || p->ldr == p->N);
+    const int ks = plan_splitk(tiles_m * tiles_n, a.num_kb, p->M, (int)p->N, p->workspace, p->workspace_bytes, plain);
+    if (ks > 1) {
+        KernelArgs b = a;
+        b.ksplit = ks; b.kb_per_split = (a.num_kb + ks - 1) / ks; b.split_stride_o = p->M * p->N;
+        b.out = p->workspace; b.ldo = p->N; b.bias = nullptr; b.row_bias = nullptr; b.residual = nullptr; b.flags = GMD_EPI_OUT_F32;
+        int rc = launch_cfg(bn, tiles_m, tiles_n, 1u, maps_a, map_w, b, st);
+        if (rc) return rc;
+        return launch_finalize(a, static_cast<const float*>(p->workspace), ks, p->M, (int)p->N, a.bias, a.row_bias, a.ld_row_bias,
+                               a.rows_per_sample > 0 ? a.rows_per_sample : p->M, a.residual, p->flags & GMD_EPI_RESIDUAL_F32, p->out,
+                               p->flags & GMD_EPI_OUT_F32, st);
+    }
+    return launch_cfg(bn, tiles_m, tiles_n, (unsigned)batch, maps_a, map_w, a, st);
 }
 
 extern "C" int gmd_conv_fwd(const gmd_conv_params* p, void* stream) {
@@ -661,7 +753,7 @@ extern "C" int gmd_conv_fwd(const gmd_conv_params* p, void* stream) {
     if ((p->flags & GMD_EPI_RESIDUAL) && !p->residual) { set_last_error("gmd_conv_fwd: RESIDUAL flag without residual"); return kErrInvalid; }
     if ((p->flags & GMD_EPI_ROW_BIAS) && !p->row_bias) { set_last_error("gmd_conv_fwd: ROW_BIAS flag without row_bias"); return kErrInvalid; }
 
-    int rows_w = p->Cout_pad > 0 ? p->Cout_pad : p->Cout;
+    int rows_w = p->w_tiled ? p->Cout : (p->Cout_pad > 0 ? p->Cout_pad : p->Cout);
     int bnt = pick_bn(rows_w, false);
     CUtensorMap maps_a[4], map_w;
     const uint32_t box[4] = {BK, (uint32_t)bw, (uint32_t)bh, (uint32_t)bn};
@@ -689,7 +781,17 @@ extern "C" int gmd_conv_fwd(const gmd_conv_params* p, void* stream) {
         }
         maps_a[2] = maps_a[3] = maps_a[0];
     }
-    {
+    if (p->w_tiled) {
+        // [N tile][k block = tap * chunks + chunk][bnt rows][64]: channels of every tap zero-padded to whole 64-blocks at pack time
+        if (p->w_tiled != bnt) { set_last_error("gmd_conv_fwd: tiled weights were packed for N tile %d, kernel picks %d", p->w_tiled, bnt); return kErrInvalid; }
+        const uint64_t total_rows = (uint64_t)((p->Cout + bnt - 1) / bnt) * a.num_kb * bnt;
+        uint64_t dims[3] = {BK, total_rows, 1};
+        uint64_t strides[3] = {2, BK * 2, total_rows * BK * 2};
+        uint32_t boxw[3] = {BK, (uint32_t)bnt, 1};
+        int rc = encode_tensor_map_bf16(&map_w, p->w, 3, dims, strides, boxw, true);
+        if (rc) return rc;
+        a.w_tiled = 1;
+    } else {
         uint64_t dims[3] = {(uint64_t)taps * ctot, (uint64_t)rows_w, 1};
         uint64_t strides[3] = {2, (uint64_t)taps * ctot * 2, (uint64_t)taps * ctot * rows_w * 2};
         uint32_t boxw[3] = {BK, (uint32_t)bnt, 1};
@@ -697,6 +799,18 @@ extern "C" int gmd_conv_fwd(const gmd_conv_params* p, void* stream) {
         if (rc) return rc;
     }
     int tiles_img = (p->N + bn - 1) / bn;
-    return launch_cfg(bnt, (int64_t)a.tiles_w * a.tiles_h * tiles_img, (p->Cout + bnt - 1) / bnt, p->upsample ? 4u : 1u, maps_a, map_w, a,
-                      static_cast<cudaStream_t>(stream));
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const int64_t tiles_m = (int64_t)a.tiles_w * a.tiles_h * tiles_img, tiles_nn = (p->Cout + bnt - 1) / bnt;
+    const int64_t rows = (int64_t)p->N * Ho * Wo;
+    const int ks = plan_splitk(tiles_m * tiles_nn, a.num_kb, rows, p->Cout, p->workspace, p->workspace_bytes, !p->upsample);
+    if (ks > 1) {
+        KernelArgs b = a;
+        b.ksplit = ks; b.kb_per_split = (a.num_kb + ks - 1) / ks; b.split_stride_o = rows * p->Cout;
+        b.out = p->workspace; b.ldo = p->Cout; b.bias = nullptr; b.row_bias = nullptr; b.residual = nullptr; b.flags = GMD_EPI_OUT_F32;
+        int rc = launch_cfg(bnt, tiles_m, tiles_nn, 1u, maps_a, map_w, b, st);
+        if (rc) return rc;
+        return launch_finalize(a, static_cast<const float*>(p->workspace), ks, rows, p->Cout, a.bias, a.row_bias, a.ld_row_bias, (int64_t)Ho * Wo,
+                               a.residual, p->flags & GMD_EPI_RESIDUAL_F32, p->out, p->flags & GMD_EPI_OUT_F32, st);
+    }
+    return launch_cfg(bnt, tiles_m, tiles_nn, p->upsample ? 4u : 1u, maps_a, map_w, a, st);
 }

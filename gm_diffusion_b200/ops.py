@@ -14,14 +14,68 @@ from . import _lib as L
 
 bf16 = torch.bfloat16
 
+_WS = {}
+
+
+def pick_bn(n_rows: int, geglu: bool = False) -> int:
+    """N tile the GEMM kernel uses for `n_rows` weight rows (mirror of pick_bn in csrc/gemm.cu)."""
+    if n_rows % 160 == 0:
+        return 160
+    if n_rows % 128 == 0 or n_rows > 128:
+        return 128
+    if n_rows > 32 or geglu:
+        return 64
+    return 32
+
+
+class TiledWeight:
+    """Weights pre-tiled for the tcgen05 kernels: `[ceil(N/T)][ceil(K/64)][T][64]` bf16 (zero padded), so every operand tile the
+    TMA fetches is ONE contiguous 128*T-byte read.  With the plain `[N, K]` layout a tile is T separate 128-byte rows, each in
+    a different DRAM page: weight-streaming-bound layers (8x8 / 16x16 resolution) ran at ~0.4 TB/s."""
+
+    def __init__(self, data: torch.Tensor, n: int, k: int, bn: int):
+        self.data, self.n, self.k, self.bn = data, n, k, bn
+
+    @property
+    def shape(self):
+        return (self.n, self.k)
+
+    def to(self, device):
+        return TiledWeight(self.data.to(device), self.n, self.k, self.bn)
+
+
+def tile_weight(w: torch.Tensor, geglu: bool = False) -> TiledWeight:
+    """[N, K] (any float dtype) -> TiledWeight."""
+    n, k = w.shape
+    bn = pick_bn(n, geglu)
+    tn, tk = (n + bn - 1) // bn, (k + 63) // 64
+    wp = torch.zeros((tn * bn, tk * 64), dtype=bf16, device=w.device)
+    wp[:n, :k] = w.to(bf16)
+    data = wp.view(tn, bn, tk, 64).permute(0, 2, 1, 3).contiguous().view(tn * tk * bn, 64)
+    return TiledWeight(data, n, k, bn)
+
+
+
+def splitk_workspace(device) -> torch.Tensor:
+    """fp32 scratch for the split-K partial sums of the few-tile / long-K layers (allocated once per device, static address)."""
+    key = torch.device(device).index or 0
+    ws = _WS.get(key)
+    if ws is None:
+        ws = torch.empty(64 << 20, dtype=torch.uint8, device=device)
+        _WS[key] = ws
+    return ws
+
 
 def gemm(a: torch.Tensor, w: torch.Tensor, *, bias: Optional[torch.Tensor] = None, residual: Optional[torch.Tensor] = None,
          row_bias: Optional[torch.Tensor] = None, rows_per_sample: int = 0, geglu: bool = False, out: Optional[torch.Tensor] = None,
-         out_f32: bool = False, alpha: Optional[float] = None) -> torch.Tensor:
+         out_f32: bool = False, alpha: Optional[float] = None, splitk: bool = False) -> torch.Tensor:
     """out[M,N] = a[M,K] @ w[N,K]^T (+bias +row_bias[sample] +residual | GEGLU).  3-D inputs are batched."""
-    L.require_cuda(a, w)
-    assert a.dtype == bf16 and w.dtype == bf16, "gemm operands must be bf16"
+    tiled = isinstance(w, TiledWeight)
+    wt = w.data if tiled else w
+    L.require_cuda(a, wt)
+    assert a.dtype == bf16 and wt.dtype == bf16, "gemm operands must be bf16"
     batched = a.dim() == 3
+    assert not (tiled and batched)
     if batched:
         Bt, M, K = a.shape
         N = w.shape[1]
@@ -31,18 +85,19 @@ def gemm(a: torch.Tensor, w: torch.Tensor, *, bias: Optional[torch.Tensor] = Non
         N = w.shape[0]
         assert w.shape[1] == K
         Bt = 1
-    assert a.stride(-1) == 1 and w.stride(-1) == 1
+    assert a.stride(-1) == 1 and wt.stride(-1) == 1
     n_out = N // 2 if geglu else N
     if out is None:
         shape = (Bt, M, n_out) if batched else (M, n_out)
         out = torch.empty(shape, dtype=torch.float32 if out_f32 else bf16, device=a.device)
     p = L.GemmParams()
     p.a, p.lda = a.data_ptr(), a.stride(-2)
-    p.w, p.ldw = w.data_ptr(), w.stride(-2)
+    p.w, p.ldw = wt.data_ptr(), (K if tiled else w.stride(-2))
+    p.w_tiled = w.bn if tiled else 0
     p.out, p.ldo = out.data_ptr(), out.stride(-2)
     p.M, p.N, p.K, p.batch = M, N, K, Bt
     if batched:
-        p.stride_a, p.stride_w, p.stride_o = a.stride(0), w.stride(0), out.stride(0)
+        p.stride_a, p.stride_w, p.stride_o = a.stride(0), wt.stride(0), out.stride(0)
     flags = 0
     if bias is not None:
         assert bias.dtype == torch.float32 and bias.numel() == N
@@ -64,29 +119,41 @@ def gemm(a: torch.Tensor, w: torch.Tensor, *, bias: Optional[torch.Tensor] = Non
         flags |= L.EPI_SCALE
         p.alpha = float(alpha)
     p.flags = flags
+    if splitk and not batched:
+        # opt-in: the number of K splits depends on the tile count, i.e. on M — it would make a sample's result depend on the
+        # batch it is computed in (summation order), which the sharded pipelines must not do.  Measured gain on B200: none
+        # (profiles/prof_splitk.py: the few-tile long-K layers are bound by the aggregate L2 line-fetch rate, not by the K loop).
+        ws = splitk_workspace(a.device)
+        p.workspace, p.workspace_bytes = ws.data_ptr(), ws.numel()
     L.check(L.lib().gmd_gemm_fwd(C.byref(p), L.current_stream()), "gmd_gemm_fwd")
     return out
 
 
 def conv2d(x: torch.Tensor, w: torch.Tensor, cout: int, *, ksize: int = 3, stride: int = 1, upsample: bool = False,
            x1: Optional[torch.Tensor] = None, bias: Optional[torch.Tensor] = None, row_bias: Optional[torch.Tensor] = None,
-           residual: Optional[torch.Tensor] = None, out: Optional[torch.Tensor] = None, out_f32: bool = False) -> torch.Tensor:
+           residual: Optional[torch.Tensor] = None, out: Optional[torch.Tensor] = None, out_f32: bool = False, splitk: bool = False) -> torch.Tensor:
     """NHWC bf16 convolution as implicit GEMM (3x3 pad 1 stride 1/2, optional folded nearest-2x upsample)."""
-    L.require_cuda(x, w)
-    assert x.dtype == bf16 and w.dtype == bf16 and x.is_contiguous() and w.is_contiguous()
+    tiled = isinstance(w, TiledWeight)
+    wt = w.data if tiled else w
+    L.require_cuda(x, wt)
+    assert x.dtype == bf16 and wt.dtype == bf16 and x.is_contiguous() and wt.is_contiguous()
     N, H, W, C0 = x.shape
     C1 = 0
     if x1 is not None:
         assert x1.dtype == bf16 and x1.is_contiguous() and x1.shape[:3] == x.shape[:3]
         C1 = x1.shape[3]
-    assert w.shape[1] == ksize * ksize * (C0 + C1), (w.shape, ksize, C0, C1)
+    if tiled:
+        assert w.n == cout and w.k == ksize * ksize * ((C0 + C1 + 63) // 64 * 64), (w.shape, ksize, C0, C1)
+    else:
+        assert w.shape[1] == ksize * ksize * (C0 + C1), (w.shape, ksize, C0, C1)
     Ho, Wo = (H // 2, W // 2) if stride == 2 else ((2 * H, 2 * W) if upsample else (H, W))
     if out is None:
         out = torch.empty((N, Ho, Wo, cout), dtype=torch.float32 if out_f32 else bf16, device=x.device)
     p = L.ConvParams()
     p.x0, p.C0 = x.data_ptr(), C0
     p.x1, p.C1 = (x1.data_ptr(), C1) if x1 is not None else (None, 0)
-    p.w, p.out = w.data_ptr(), out.data_ptr()
+    p.w, p.out = wt.data_ptr(), out.data_ptr()
+    p.w_tiled = w.bn if tiled else 0
     p.N, p.H, p.W, p.Cout, p.Cout_pad = N, H, W, cout, w.shape[0]
     p.ksize, p.stride, p.upsample = ksize, stride, int(upsample)
     flags = 0
@@ -105,6 +172,9 @@ def conv2d(x: torch.Tensor, w: torch.Tensor, cout: int, *, ksize: int = 3, strid
     if out.dtype == torch.float32:
         flags |= L.EPI_OUT_F32
     p.flags = flags
+    if splitk:  # opt-in, see gemm()
+        ws = splitk_workspace(x.device)
+        p.workspace, p.workspace_bytes = ws.data_ptr(), ws.numel()
     L.check(L.lib().gmd_conv_fwd(C.byref(p), L.current_stream()), "gmd_conv_fwd")
     return out
 
@@ -185,6 +255,18 @@ def attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, heads: int, sca
 
 
 # ---- weight repacking helpers (run once at load) ------------------------------------------------------------
+def pack_conv_weight_tiled(w_oihw: torch.Tensor, cin_pad: Optional[int] = None) -> TiledWeight:
+    """OIHW -> TiledWeight with k = (r*kw + s)*Cpad + c, Cpad = channels zero-padded to a multiple of 64 (one k block never
+    straddles two taps).  `cin_pad` first pads the logical input channels (conv_in: 4 -> 8)."""
+    co, ci, kh, kw = w_oihw.shape
+    w = w_oihw.permute(0, 2, 3, 1)
+    ci2 = max(ci, cin_pad or 0)
+    cpad = (ci2 + 63) // 64 * 64
+    if cpad > ci:
+        w = torch.nn.functional.pad(w, (0, cpad - ci))
+    return tile_weight(w.reshape(co, kh * kw * cpad))
+
+
 def pack_conv_weight(w_oihw: torch.Tensor, cin_pad: Optional[int] = None) -> torch.Tensor:
     """OIHW -> [Cout, kh*kw*Cin(_pad)] bf16, k = (r*kw + s)*Cin + c."""
     co, ci, kh, kw = w_oihw.shape
@@ -202,3 +284,8 @@ def pack_geglu_weight(w: torch.Tensor, b: torch.Tensor, tile: int = 160):
     wv, wg = w[:inner].reshape(inner // half, half, -1), w[inner:].reshape(inner // half, half, -1)
     wi = torch.cat([wv, wg], dim=1).reshape(2 * inner, -1)
     return wi.to(bf16).contiguous(), b.float().contiguous()  # bias stays [value | gate]; the kernel indexes both halves
+
+
+def pack_geglu_weight_tiled(w: torch.Tensor, b: torch.Tensor):
+    wi, bi = pack_geglu_weight(w, b, tile=160)
+    return tile_weight(wi, geglu=True), bi

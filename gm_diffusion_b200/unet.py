@@ -24,7 +24,8 @@ def _f32(t, dev):
 
 
 def _w(t, dev):
-    return t.detach().to(device=dev, dtype=bf16).contiguous()
+    """Linear / 1x1-conv weight [N, K] -> device, pre-tiled for the GEMM kernel."""
+    return ops.tile_weight(t.detach().to(device=dev, dtype=bf16))
 
 
 class _Resnet:
@@ -33,11 +34,11 @@ class _Resnet:
         self.eps = eps
         self.n1 = (_f32(g("norm1.weight"), dev), _f32(g("norm1.bias"), dev))
         self.n2 = (_f32(g("norm2.weight"), dev), _f32(g("norm2.bias"), dev))
-        self.w1 = ops.pack_conv_weight(g("conv1.weight")).to(dev)
+        self.w1 = ops.pack_conv_weight_tiled(g("conv1.weight").to(dev))
         self.b1 = _f32(g("conv1.bias"), dev)
-        self.w2 = ops.pack_conv_weight(g("conv2.weight")).to(dev)
+        self.w2 = ops.pack_conv_weight_tiled(g("conv2.weight").to(dev))
         self.b2 = _f32(g("conv2.bias"), dev)
-        self.cout = self.w1.shape[0]
+        self.cout = g("conv1.weight").shape[0]
         self.cin = g("conv1.weight").shape[1]
         self.temb_off = None
         if temb_slices is not None and (prefix + "time_emb_proj.weight") in sd:
@@ -46,7 +47,7 @@ class _Resnet:
             self.temb_off = off
         self.wsc = self.bsc = None
         if (prefix + "conv_shortcut.weight") in sd:
-            self.wsc = _w(g("conv_shortcut.weight").reshape(self.cout, self.cin), dev)
+            self.wsc = ops.pack_conv_weight_tiled(g("conv_shortcut.weight").to(dev))
             self.bsc = _f32(g("conv_shortcut.bias"), dev)
 
     def __call__(self, x, skip, temb_all, ws):
@@ -79,8 +80,8 @@ class _Transformer:
         self.w_q2 = _w(g(t + "attn2.to_q.weight"), dev)
         self.w_kv2 = _w(torch.cat([g(t + "attn2.to_k.weight"), g(t + "attn2.to_v.weight")], 0), dev)
         self.w_o2, self.b_o2 = _w(g(t + "attn2.to_out.0.weight"), dev), _f32(g(t + "attn2.to_out.0.bias"), dev)
-        wff, bff = ops.pack_geglu_weight(g(t + "ff.net.0.proj.weight"), g(t + "ff.net.0.proj.bias"))
-        self.w_ff1, self.b_ff1 = wff.to(dev), bff.to(dev)
+        wff, bff = ops.pack_geglu_weight_tiled(g(t + "ff.net.0.proj.weight").to(dev), g(t + "ff.net.0.proj.bias").to(dev))
+        self.w_ff1, self.b_ff1 = wff, bff
         self.w_ff2, self.b_ff2 = _w(g(t + "ff.net.2.weight"), dev), _f32(g(t + "ff.net.2.bias"), dev)
 
     def project_context(self, ctx2d):
@@ -127,7 +128,7 @@ class B200UNet:
         self.cross_dim = sd["down_blocks.0.attentions.0.transformer_blocks.0.attn2.to_k.weight"].shape[1]
         if self.in_channels > self.IN_PAD:
             raise NotImplementedError("in_channels > 8")
-        self.w_in = ops.pack_conv_weight(sd["conv_in.weight"], cin_pad=self.IN_PAD).to(dev)
+        self.w_in = ops.pack_conv_weight_tiled(sd["conv_in.weight"].to(dev), cin_pad=self.IN_PAD)
         self.b_in = _f32(sd["conv_in.bias"], dev)
         self.t1 = (_w(sd["time_embedding.linear_1.weight"], dev), _f32(sd["time_embedding.linear_1.bias"], dev))
         self.t2 = (_w(sd["time_embedding.linear_2.weight"], dev), _f32(sd["time_embedding.linear_2.bias"], dev))
@@ -144,7 +145,7 @@ class B200UNet:
                 j += 1
             ds = None
             if f"down_blocks.{i}.downsamplers.0.conv.weight" in sd:
-                ds = (ops.pack_conv_weight(sd[f"down_blocks.{i}.downsamplers.0.conv.weight"]).to(dev),
+                ds = (ops.pack_conv_weight_tiled(sd[f"down_blocks.{i}.downsamplers.0.conv.weight"].to(dev)),
                       _f32(sd[f"down_blocks.{i}.downsamplers.0.conv.bias"], dev))
             self.down.append((res, att, ds))
             i += 1
@@ -162,12 +163,12 @@ class B200UNet:
                 j += 1
             us = None
             if f"up_blocks.{i}.upsamplers.0.conv.weight" in sd:
-                us = (ops.pack_conv_weight(sd[f"up_blocks.{i}.upsamplers.0.conv.weight"]).to(dev),
+                us = (ops.pack_conv_weight_tiled(sd[f"up_blocks.{i}.upsamplers.0.conv.weight"].to(dev)),
                       _f32(sd[f"up_blocks.{i}.upsamplers.0.conv.bias"], dev))
             self.up.append((res, att, us))
             i += 1
         self.n_out = (_f32(sd["conv_norm_out.weight"], dev), _f32(sd["conv_norm_out.bias"], dev))
-        self.w_out = ops.pack_conv_weight(sd["conv_out.weight"]).to(dev)
+        self.w_out = ops.pack_conv_weight_tiled(sd["conv_out.weight"].to(dev))
         self.b_out = _f32(sd["conv_out.bias"], dev)
         # all 22 time_emb_proj linears as ONE GEMM: [sum(Cout), 1280]
         self.w_temb = _w(torch.cat([w for w, _ in temb_slices], 0), dev)

@@ -31,15 +31,16 @@ class B200VaeDecoder:
         bpq[:4] = sd["post_quant_conv.bias"].float()
         self.w_pq, self.b_pq = _w(wpq, dev), _f32(bpq, dev)
         d = "decoder."
-        self.w_in = ops.pack_conv_weight(sd[d + "conv_in.weight"], cin_pad=8).to(dev)
+        self.w_in = ops.pack_conv_weight_tiled(sd[d + "conv_in.weight"].to(dev), cin_pad=8)
         self.b_in = _f32(sd[d + "conv_in.bias"], dev)
-        self.c_mid = self.w_in.shape[0]
+        self.c_mid = sd[d + "conv_in.weight"].shape[0]
         self.mid_res = [_Resnet(sd, d + f"mid_block.resnets.{j}.", dev, None, eps=1e-6) for j in range(2)]
         a = d + "mid_block.attentions.0."
         self.a_norm = (_f32(sd[a + "group_norm.weight"], dev), _f32(sd[a + "group_norm.bias"], dev))
         self.w_qk = _w(torch.cat([sd[a + "to_q.weight"], sd[a + "to_k.weight"]], 0), dev)
         self.b_qk = _f32(torch.cat([sd[a + "to_q.bias"], sd[a + "to_k.bias"]], 0), dev)
-        self.w_v, self.b_v = _w(sd[a + "to_v.weight"], dev), _f32(sd[a + "to_v.bias"], dev)
+        # to_v is used as the A operand (V^T = Wv . y^T), so it stays in the plain [N, K] layout
+        self.w_v, self.b_v = sd[a + "to_v.weight"].detach().to(device=dev, dtype=bf16).contiguous(), _f32(sd[a + "to_v.bias"], dev)
         self.w_o, self.b_o = _w(sd[a + "to_out.0.weight"], dev), _f32(sd[a + "to_out.0.bias"], dev)
         self.ups = []
         i = 0
@@ -51,12 +52,12 @@ class B200VaeDecoder:
                 j += 1
             us = None
             if d + f"up_blocks.{i}.upsamplers.0.conv.weight" in sd:
-                us = (ops.pack_conv_weight(sd[d + f"up_blocks.{i}.upsamplers.0.conv.weight"]).to(dev),
+                us = (ops.pack_conv_weight_tiled(sd[d + f"up_blocks.{i}.upsamplers.0.conv.weight"].to(dev)),
                       _f32(sd[d + f"up_blocks.{i}.upsamplers.0.conv.bias"], dev))
             self.ups.append((res, us))
             i += 1
         self.n_out = (_f32(sd[d + "conv_norm_out.weight"], dev), _f32(sd[d + "conv_norm_out.bias"], dev))
-        self.w_out = ops.pack_conv_weight(sd[d + "conv_out.weight"]).to(dev)
+        self.w_out = ops.pack_conv_weight_tiled(sd[d + "conv_out.weight"].to(dev))
         self.b_out = _f32(sd[d + "conv_out.bias"], dev)
         self._gn_ws = torch.empty(64 * 32 * 32 * 2, dtype=torch.float32, device=dev)  # up to 64 samples per forward
 

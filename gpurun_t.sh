@@ -1,8 +1,4 @@
 mkdir -p gpurun_out
-for sel in "tests/test_gpu_tensorcore.py -k 'gemm or conv'" "tests/test_gpu_unet.py" "tests/test_gpu_pipeline.py"; do
-  name=$(echo "$sel" | tr ' /' '__' | tr -d "'")
-  eval timeout 600 python -m pytest $sel -m gpu -q --tb=short -p no:cacheprovider --timeout 300 > gpurun_out/t_$name.log 2>&1
-  echo "== $sel -> rc $?"; tail -n 15 gpurun_out/t_$name.log | cut -c1-300 | grep -v "^$"
-done
-timeout 300 python profiles/prof_gemm_small.py
-timeout 600 python profiles/layer_times.py > gpurun_out/layer_times_r01g.txt 2>&1; echo "layer rc $?"; head -24 gpurun_out/layer_times_r01g.txt
+timeout 1200 python -m pytest tests -m gpu -q --tb=short -p no:cacheprovider --timeout 600 -x > gpurun_out/t_all.log 2>&1; echo "all gpu tests rc $?"; tail -n 6 gpurun_out/t_all.log | cut -c1-300
+python bench.py --steps 2 --warmup 3 --no-cpu-baseline > gpurun_out/bench_r01_c.json 2> gpurun_out/bench_err.log; echo "bench rc $?"; tail -3 gpurun_out/bench_err.log; python -c "
+import json; d=json.load(open('gpurun_out/bench_r01_c.json')); print({k:d[k] for k in ['value','ms_per_step','ms_per_denoise_step','ms_tail_vae_x2_plus_eq1','gpu_launches','clocks']}); print(d['e2e']['value'], d['roofline']['achieved'], d['kernels'])"

@@ -164,6 +164,11 @@ typedef struct gmd_gemm_params {
     int64_t stride_a, stride_w, stride_o;
     int32_t flags;
     float alpha;
+    void* workspace;                     /* optional fp32 scratch for split-K (few output tiles, long K); NULL disables it */
+    int64_t workspace_bytes;
+    int32_t w_tiled;                     /* 0: w is [N, K] row-major.  T > 0: w is pre-tiled [ceil(N/T)][ceil(K/64)][T][64] (zero padded), T = the
+                                          * N tile the kernel uses for this N (160 if N%160==0, else 128 if N%128==0 or N>128, else 64 / 32):
+                                          * every operand tile is then one contiguous DRAM read instead of T strided 128-byte rows */
 } gmd_gemm_params;
 
 int gmd_gemm_fwd(const gmd_gemm_params* p, void* stream);
@@ -185,6 +190,9 @@ typedef struct gmd_conv_params {
     int32_t stride;                      /* 1 or 2 */
     int32_t upsample;                    /* 1: nearest-2x upsample of the input folded into the gather */
     int32_t flags;
+    void* workspace;                     /* optional fp32 scratch for split-K (8x8-resolution layers); NULL disables it */
+    int64_t workspace_bytes;
+    int32_t w_tiled;                     /* as gmd_gemm_params.w_tiled; k blocks ordered (tap, 64-channel chunk of x0 then x1), channels zero padded */
 } gmd_conv_params;
 
 int gmd_conv_fwd(const gmd_conv_params* p, void* stream);

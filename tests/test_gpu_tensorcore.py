@@ -35,6 +35,7 @@ def test_gemm_plain(M, N, K):
     a = torch.randn(M, K, generator=g).to(bf).cuda()
     w = (torch.randn(N, K, generator=g) / math.sqrt(K)).to(bf).cuda()
     check(ops.gemm(a, w), a.float() @ w.float().t(), what=f"gemm {M}x{N}x{K}")
+    check(ops.gemm(a, ops.tile_weight(w)), a.float() @ w.float().t(), what=f"gemm tiled-W {M}x{N}x{K}")
 
 
 def test_gemm_epilogues():
@@ -61,6 +62,28 @@ def test_gemm_epilogues():
     check(ops.gemm(big[:, K:2 * K], w), big[:, K:2 * K].float() @ w.float().t(), what="strided A")
 
 
+def test_gemm_splitk_paths():
+    """Few output tiles + long K -> split-K with the deterministic finalize kernel (bias / row bias / residual / dtypes)."""
+    from gm_diffusion_b200 import ops
+    g = torch.Generator().manual_seed(11)
+    M, N, K = 512, 1280, 5120
+    a = torch.randn(M, K, generator=g).to(bf).cuda()
+    w = (torch.randn(N, K, generator=g) / math.sqrt(K)).to(bf).cuda()
+    bias = torch.randn(N, generator=g).cuda()
+    res32 = torch.randn(M, N, generator=g).cuda()
+    res16 = torch.randn(M, N, generator=g).to(bf).cuda()
+    rb = torch.randn(4, N, generator=g).cuda()
+    ref = a.float() @ w.float().t() + bias
+    from gm_diffusion_b200 import _lib as L
+    L.reset_launch_count()
+    check(ops.gemm(a, w, bias=bias, splitk=True), ref, what="split-K bias")
+    assert L.launch_count() == 2, "split-K = main kernel + finalize kernel"
+    check(ops.gemm(a, w, bias=bias, residual=res32, out_f32=True, splitk=True), ref + res32, tol=1e-3, what="split-K fp32 residual")
+    check(ops.gemm(a, w, bias=bias, residual=res16, row_bias=rb, rows_per_sample=128, splitk=True), ref + res16.float() + rb.repeat_interleave(128, 0), what="split-K bf16 residual + row bias")
+    o1, o2 = ops.gemm(a, w, bias=bias, splitk=True), ops.gemm(a, w, bias=bias, splitk=True)
+    assert torch.equal(o1, o2), "split-K reduction must be deterministic"
+
+
 def test_gemm_geglu():
     from gm_diffusion_b200 import ops
     g = torch.Generator().manual_seed(3)
@@ -70,6 +93,8 @@ def test_gemm_geglu():
     b = torch.randn(8 * Cc, generator=g) * 0.1
     wi, bi = ops.pack_geglu_weight(w, b)
     got = ops.gemm(x, wi.cuda(), bias=bi.cuda(), geglu=True)
+    wt, bt = ops.pack_geglu_weight_tiled(w.cuda(), b.cuda())
+    assert torch.equal(got, ops.gemm(x, wt, bias=bt, geglu=True)), "tiled and plain GEGLU weights must give identical results"
     proj = x.float().cpu() @ w.float().t() + b
     h, gate = proj.chunk(2, -1)
     check(got, h * F.gelu(gate), what="geglu")
@@ -101,6 +126,10 @@ def test_conv3x3(N, H, W, Cin, Cout):
     b = torch.randn(Cout, generator=g)
     got = ops.conv2d(x.cuda(), ops.pack_conv_weight(w).cuda(), Cout, bias=b.cuda(), out_f32=(Cout == 4))
     check(got, _conv_ref(x, w, b), what=f"conv3x3 {N}x{H}x{W} {Cin}->{Cout}")
+    got = ops.conv2d(x.cuda(), ops.pack_conv_weight_tiled(w.cuda()), Cout, bias=b.cuda(), out_f32=(Cout == 4))
+    check(got, _conv_ref(x, w, b), what=f"conv3x3 tiled-W {N}x{H}x{W} {Cin}->{Cout}")
+    got = ops.conv2d(x.cuda(), ops.pack_conv_weight_tiled(w.cuda()), Cout, bias=b.cuda(), out_f32=(Cout == 4), splitk=True)
+    check(got, _conv_ref(x, w, b), what=f"conv3x3 split-K {N}x{H}x{W} {Cin}->{Cout}")
 
 
 def test_conv_stride2_upsample_concat_epilogue():
@@ -120,6 +149,10 @@ def test_conv_stride2_upsample_concat_epilogue():
     ref = _conv_ref(torch.cat([x, x1], -1), w2, b) + rb[:, None, None, :] + res.float()
     got = ops.conv2d(x.cuda(), ops.pack_conv_weight(w2).cuda(), 320, x1=x1.cuda(), bias=b.cuda(), row_bias=rb.cuda(), residual=res.cuda())
     check(got, ref, what="concat+temb+residual")
+    got = ops.conv2d(x.cuda(), ops.pack_conv_weight_tiled(w2.cuda()), 320, x1=x1.cuda(), bias=b.cuda(), row_bias=rb.cuda(), residual=res.cuda())
+    check(got, ref, what="concat+temb+residual tiled-W")
+    check(ops.conv2d(x.cuda(), ops.pack_conv_weight_tiled(w.cuda()), 320, stride=2, bias=b.cuda()), _conv_ref(x, w, b, stride=2), what="stride 2 tiled-W")
+    check(ops.conv2d(x.cuda(), ops.pack_conv_weight_tiled(w.cuda()), 320, upsample=True, bias=b.cuda()), _conv_ref(x, w, b, upsample=True), what="upsample tiled-W")
 
 
 @pytest.mark.parametrize("B,H,Nq,Nk,d", [(2, 8, 4096, 4096, 40), (2, 8, 1024, 1024, 80), (2, 8, 256, 256, 160), (3, 8, 64, 64, 160),
