@@ -241,12 +241,12 @@ def instrumented_step(pipe, B):
         ctx2 = torch.randn(2 * B, 77, 768, device=dev, generator=g)
         kv_s, kv_g = pipe.unet.project_context(ctx2), pipe.gm_unet.project_context(ctx2[:B])
         tb_s, tb_g = pipe.unet.timestep_table([501]), pipe.gm_unet.timestep_table([501])
-        xs = torch.randn(2 * B, h, w, 8, device=dev, generator=g).to(torch.bfloat16)
+        xs = torch.randn(B, h, w, 8, device=dev, generator=g).to(torch.bfloat16)  # one copy: the CFG halves share the prefix
         xs[..., 4:] = 0
         xg = torch.randn(B, h, w, 8, device=dev, generator=g).to(torch.bfloat16)
         records.clear()
         torch.cuda.synchronize()
-        pipe.unet.forward(xs, tb_s, kv_s)
+        pipe.unet.forward(xs, tb_s, kv_s, cfg_shared=True)
         pipe.gm_unet.forward(xg, tb_g, kv_g)
         torch.cuda.synchronize()
     finally:

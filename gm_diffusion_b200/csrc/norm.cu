@@ -40,7 +40,8 @@ __device__ __forceinline__ void gn_load(const T* x0, int C0, const __nv_bfloat16
 
 template <typename T>
 __global__ void gn_stats_kernel(const T* __restrict__ x0, int C0, const __nv_bfloat16* __restrict__ x1, int C1,
-                                float* __restrict__ stats, int HW, int groups, int px_per_cta) {
+                                float* __restrict__ stats, float* __restrict__ finals, int* __restrict__ counters, int HW, int groups,
+                                int px_per_cta, float eps) {
     extern __shared__ float s_part[];  // [blockDim][16]: per-thread per-channel sum / sum of squares
     const int C = C0 + C1, nvec = C / 8, cg = C / groups;
     const int n = blockIdx.y;
@@ -84,32 +85,45 @@ __global__ void gn_stats_kernel(const T* __restrict__ x0, int C0, const __nv_bfl
         float* dst = stats + (((int64_t)n * gridDim.x + blockIdx.x) * groups + g) * 2;
         dst[0] = ss; dst[1] = qq;
     }
+    // The LAST CTA of sample n to finish folds the per-chunk partials, always in chunk order (deterministic), into
+    // (mean, rstd) per group, so the apply kernel starts streaming after two loads instead of a 32-step reduction per thread.
+    __shared__ int s_last;
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int ticket = atomicAdd(counters + n, 1);
+        s_last = (ticket == (int)gridDim.x - 1);
+        if (s_last) counters[n] = 0;   // self-resetting for the next launch
+    }
+    __syncthreads();
+    if (s_last && (int)threadIdx.x < groups) {
+        __threadfence();
+        const int g = threadIdx.x;
+        float s1 = 0.0f, s2 = 0.0f;
+        const volatile float* src = stats + (int64_t)n * gridDim.x * groups * 2 + g * 2;
+        for (int ch = 0; ch < (int)gridDim.x; ++ch) { s1 += src[(int64_t)ch * groups * 2]; s2 += src[(int64_t)ch * groups * 2 + 1]; }
+        const float inv_cnt = 1.0f / ((float)cg * (float)HW);
+        const float mean = s1 * inv_cnt;
+        const float var = fmaxf(s2 * inv_cnt - mean * mean, 0.0f);
+        finals[((int64_t)n * groups + g) * 2] = mean;
+        finals[((int64_t)n * groups + g) * 2 + 1] = rsqrtf(var + eps);
+    }
 }
 
 template <typename T>
 __global__ void gn_apply_kernel(const T* __restrict__ x0, int C0, const __nv_bfloat16* __restrict__ x1, int C1,
-                                const float* __restrict__ stats, const float* __restrict__ gamma, const float* __restrict__ beta,
-                                __nv_bfloat16* __restrict__ out, int HW, int groups, float eps, int apply_silu, int px_per_cta) {
+                                const float* __restrict__ finals, const float* __restrict__ gamma, const float* __restrict__ beta,
+                                __nv_bfloat16* __restrict__ out, int HW, int groups, int apply_silu, int px_per_cta) {
     const int C = C0 + C1, nvec = C / 8, cg = C / groups;
     const int n = blockIdx.y;
     const int cv = threadIdx.x % nvec, pl = threadIdx.x / nvec, P = blockDim.x / nvec;
     if (pl >= P) return;
     float sc[8], sh[8];
-    const float inv_cnt = 1.0f / ((float)cg * (float)HW);
-    int g_cached = -1;
-    float mean = 0.0f, var = 0.0f;
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
         int c = cv * 8 + k, g = c / cg;
-        if (g != g_cached) {
-            float s1 = 0.0f, s2 = 0.0f;
-            const float* src = stats + (int64_t)n * gridDim.x * groups * 2 + g * 2;
-            for (int ch = 0; ch < (int)gridDim.x; ++ch) { s1 += src[(int64_t)ch * groups * 2]; s2 += src[(int64_t)ch * groups * 2 + 1]; }
-            mean = s1 * inv_cnt;
-            var = fmaxf(s2 * inv_cnt - mean * mean, 0.0f);
-            g_cached = g;
-        }
-        float rstd = rsqrtf(var + eps);
+        const float mean = finals[((int64_t)n * groups + g) * 2];
+        const float rstd = finals[((int64_t)n * groups + g) * 2 + 1];
         float ga = gamma[c], be = beta[c];
         sc[k] = rstd * ga; sh[k] = be - mean * rstd * ga;
     }
@@ -267,10 +281,15 @@ int gn_launch(const void* x0, int C0, const void* x1, int C1, const float* gamma
     if (px_per_cta < P * 4) px_per_cta = P * 4;
     int chunks = (HW + px_per_cta - 1) / px_per_cta;  // <= 32
     dim3 grid(chunks, N);
+    // workspace: [1024] arrival counters at a FIXED offset (zero before first use, self-resetting; calls with different N share
+    // the workspace) | [N][32 chunks][groups][2] partials | [N][groups][2] finals
+    int* counters = reinterpret_cast<int*>(stats_ws);
+    float* partials = stats_ws + 1024;
+    float* finals = partials + (int64_t)N * 32 * groups * 2;
     gn_stats_kernel<T><<<grid, threads, threads * 16 * sizeof(float), st>>>(static_cast<const T*>(x0), C0, static_cast<const __nv_bfloat16*>(x1), C1,
-                                                                            stats_ws, HW, groups, px_per_cta);
-    gn_apply_kernel<T><<<grid, threads, 0, st>>>(static_cast<const T*>(x0), C0, static_cast<const __nv_bfloat16*>(x1), C1, stats_ws, gamma, beta,
-                                                 static_cast<__nv_bfloat16*>(out), HW, groups, eps, apply_silu, px_per_cta);
+                                                                            partials, finals, counters, HW, groups, px_per_cta, eps);
+    gn_apply_kernel<T><<<grid, threads, 0, st>>>(static_cast<const T*>(x0), C0, static_cast<const __nv_bfloat16*>(x1), C1, finals, gamma, beta,
+                                                 static_cast<__nv_bfloat16*>(out), HW, groups, apply_silu, px_per_cta);
     count_launch(2);
     return check_launch("groupnorm");
 }
@@ -287,7 +306,7 @@ extern "C" int gmd_groupnorm_silu(const void* x0, int32_t C0, const void* x1, in
     const int C = C0 + C1;
     if (C0 % 8 || C1 % 8 || groups <= 0 || C % groups || N <= 0 || HW <= 0) { set_last_error("gmd_groupnorm_silu: bad shape C0=%d C1=%d groups=%d", C0, C1, groups); return kErrInvalid; }
     if (!al16(x0) || !al16(x1) || !al16(out)) { set_last_error("gmd_groupnorm_silu: pointers must be 16-byte aligned"); return kErrInvalid; }
-    if (C / 8 > 1024 || groups > 256) { set_last_error("gmd_groupnorm_silu: C=%d groups=%d too large", C, groups); return kErrUnsupported; }
+    if (C / 8 > 1024 || groups > 256 || N > 1024) { set_last_error("gmd_groupnorm_silu: C=%d groups=%d too large", C, groups); return kErrUnsupported; }
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     if (in_dtype == GMD_BF16) return gn_launch<__nv_bfloat16>(x0, C0, x1, C1, gamma, beta, out, N, HW, groups, eps, apply_silu, stats_ws, st);
     if (in_dtype == GMD_F32) return gn_launch<float>(x0, C0, x1, C1, gamma, beta, out, N, HW, groups, eps, apply_silu, stats_ws, st);

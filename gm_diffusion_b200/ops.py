@@ -179,6 +179,11 @@ def conv2d(x: torch.Tensor, w: torch.Tensor, cout: int, *, ksize: int = 3, strid
     return out
 
 
+def gn_workspace(n_max: int, groups: int, device) -> torch.Tensor:
+    """Zero-initialised GroupNorm scratch (partials, finals, arrival counters) for up to `n_max` samples."""
+    return torch.zeros(1024 + n_max * 34 * groups * 2, dtype=torch.float32, device=device)
+
+
 def groupnorm_silu(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, *, x1: Optional[torch.Tensor] = None, groups: int = 32,
                    eps: float = 1e-5, silu: bool = True, out: Optional[torch.Tensor] = None, stats_ws: Optional[torch.Tensor] = None) -> torch.Tensor:
     """GroupNorm(+SiLU) over NHWC bf16; with `x1` the channels are [x | x1] and the output is the concatenation."""
@@ -189,8 +194,8 @@ def groupnorm_silu(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, *, 
     if out is None:
         out = torch.empty(x.shape[:-1] + (C0 + C1,), dtype=bf16, device=x.device)
     if stats_ws is None:
-        stats_ws = torch.empty(N * 32 * groups * 2, dtype=torch.float32, device=x.device)
-    assert stats_ws.numel() >= N * 32 * groups * 2, "groupnorm workspace too small"
+        stats_ws = gn_workspace(N, groups, x.device)
+    assert stats_ws.numel() >= 1024 + N * 34 * groups * 2, "groupnorm workspace too small"
     L.check(L.lib().gmd_groupnorm_silu(x.data_ptr(), C0, L.ptr(x1), C1, gamma.data_ptr(), beta.data_ptr(), out.data_ptr(), N, HW,
                                        groups, float(eps), int(silu), L.F32 if x.dtype == torch.float32 else L.BF16, stats_ws.data_ptr(),
                                        L.current_stream()), "gmd_groupnorm_silu")

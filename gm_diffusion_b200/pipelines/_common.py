@@ -261,11 +261,11 @@ class PipelineBase:
         return {"eta": eta if isinstance(self.scheduler, S.DDIMScheduler) else 0.0, "generator": generator}
 
     # ---- CUDA-graph cache for one UNet at one shape ------------------------------------------------------------
-    def _unet_runner(self, key, unet: B200UNet, sample, temb_row, ctx_kv, eps_out):
+    def _unet_runner(self, key, unet: B200UNet, sample, temb_row, ctx_kv, eps_out, cfg_shared: bool = False):
         """Returns a zero-arg callable running unet.forward on the given STATIC buffers; captured into a CUDA graph
         on first use (the forward is ~900 launches; replaying it removes the Python/ctypes launch overhead)."""
         if not self.use_cuda_graph:
-            return lambda: unet.forward(sample, temb_row, ctx_kv, out=eps_out)
+            return lambda: unet.forward(sample, temb_row, ctx_kv, out=eps_out, cfg_shared=cfg_shared)
         def make_replay(g, n_kernels):
             def replay():
                 g.replay()
@@ -279,12 +279,12 @@ class PipelineBase:
             if same:
                 return make_replay(g, n_kernels)
         n0 = L.launch_count()
-        unet.forward(sample, temb_row, ctx_kv, out=eps_out)  # warm-up: attribute setup, allocator pools
+        unet.forward(sample, temb_row, ctx_kv, out=eps_out, cfg_shared=cfg_shared)  # warm-up: attribute setup, allocator pools
         n_kernels = L.launch_count() - n0
         torch.cuda.synchronize()
         g = torch.cuda.CUDAGraph()
         with torch.cuda.graph(g):
-            unet.forward(sample, temb_row, ctx_kv, out=eps_out)
+            unet.forward(sample, temb_row, ctx_kv, out=eps_out, cfg_shared=cfg_shared)
         self._graphs[key] = (g, [t.data_ptr() for t in [sample, temb_row, eps_out] + list(ctx_kv)], n_kernels)
         return make_replay(g, n_kernels)
 

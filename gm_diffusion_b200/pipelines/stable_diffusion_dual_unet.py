@@ -35,7 +35,7 @@ class _Workspace:
         self.B, self.h, self.w, self.n_px = B, h, w, n_px
         self.sdr = S.BranchState(n_px, device)
         self.gm = S.BranchState(n_px, device)
-        self.unet_in = torch.zeros((cfg_mult * B, h, w, 8), dtype=bf16, device=device)
+        self.unet_in = torch.zeros((B, h, w, 8), dtype=bf16, device=device)  # ONE copy: the CFG halves share it (B200UNet cfg_shared)
         self.gm_in = torch.zeros((B, h, w, 8), dtype=bf16, device=device)
         self.eps_sdr = torch.empty((cfg_mult * B, h, w, 4), dtype=torch.float32, device=device)
         self.eps_gm = torch.empty((B, h, w, 4), dtype=torch.float32, device=device)
@@ -149,8 +149,7 @@ class StableDiffusionDualUNetPipeline(PipelineBase):
         ws.gm.x.copy_(ws.sdr.x)
         ws.sdr.reset(); ws.gm.reset()
         L.check(L.lib().gmd_pack_unet_input(ws.sdr.x.data_ptr(), None, ws.unet_in.data_ptr(), ws.n_px, 8, stream), "gmd_pack_unet_input")
-        if do_cfg:
-            ws.unet_in[B:].copy_(ws.unet_in[:B])  # :1045 torch.cat([latents] * 2); later steps: the fused kernel writes both halves
+        # :1045 torch.cat([latents] * 2) is never materialised: both CFG halves read the same buffer (B200UNet cfg_shared)
         # step-invariant work hoisted out of the loop: text K/V per layer, timestep-embedding tables
         sdr_ctx = torch.cat([negative_prompt_embeds, prompt_embeds]) if do_cfg else prompt_embeds  # :983-984
         gm_ctx = prompt_embeds  # conditional half only, no CFG on the GM branch (:1086; batch-correct form VIS:274)
@@ -159,7 +158,7 @@ class StableDiffusionDualUNetPipeline(PipelineBase):
         ts = [int(t) for t in timesteps]
         table_sdr = self.unet.timestep_table(ts)
         table_gm = self.gm_unet.timestep_table(ts)
-        run_sdr = self._unet_runner(("sdr", B, h, w, do_cfg), self.unet, ws.unet_in, ws.temb_sdr, ws.kv_sdr, ws.eps_sdr)
+        run_sdr = self._unet_runner(("sdr", B, h, w, do_cfg), self.unet, ws.unet_in, ws.temb_sdr, ws.kv_sdr, ws.eps_sdr, cfg_shared=do_cfg)
         run_gm = self._unet_runner(("gm", B, h, w), self.gm_unet, ws.gm_in, ws.temb_gm, ws.kv_gm, ws.eps_gm)
         extra = self.prepare_extra_step_kwargs(generator, eta)
         eps_u = ws.eps_sdr[:B].reshape(-1, 4) if do_cfg else None
@@ -179,7 +178,7 @@ class StableDiffusionDualUNetPipeline(PipelineBase):
                     ws.sdr.noise = self._draw_noise(B, h, w, generator)
                 S.fused_step(plan, ws.sdr, eps_c, eps_u, guidance_scale=guidance_scale,        # :1063-1080
                              guidance_rescale=guidance_rescale if do_cfg else 0.0, px_per_sample=h * w,
-                             x0_coeffs=self.scheduler.x0_coeffs(t), unet_in_next=ws.unet_in, unet_in_dup=2 if do_cfg else 1,
+                             x0_coeffs=self.scheduler.x0_coeffs(t), unet_in_next=ws.unet_in, unet_in_dup=1,
                              concat_out=ws.gm_in, concat_tail=ws.gm.x, rescale_ws=ws.rescale_ws)
                 run_gm()                                                        # :1083-1092  GM eps, no CFG
                 gplan = self.gm_scheduler.plan_step(t, extra["eta"])

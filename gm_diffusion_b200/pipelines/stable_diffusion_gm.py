@@ -91,7 +91,7 @@ class StableDiffusionGMPipeline(PipelineBase):
         if ws is None:
             f32 = dict(dtype=torch.float32, device=device)
             ws = dict(state=S.BranchState(n_px, device), sdr_px=torch.empty(n_px, 4, **f32),
-                      unet_in=torch.zeros((mult * B, h, w, 8), dtype=bf16, device=device),
+                      unet_in=torch.zeros((B, h, w, 8), dtype=bf16, device=device),  # one copy; CFG halves share it
                       eps=torch.empty((mult * B, h, w, 4), **f32), temb=torch.empty((1, self.unet.w_temb.shape[0]), **f32),
                       rescale=torch.zeros(B * 4, **f32), kv=None)
             self._ws[key] = ws
@@ -103,8 +103,7 @@ class StableDiffusionGMPipeline(PipelineBase):
         L.check(L.lib().gmd_latents_nchw_to_px(sdr32.data_ptr(), ws["sdr_px"].data_ptr(), B, h * w, stream))
         st.reset()
         L.check(L.lib().gmd_pack_unet_input(ws["sdr_px"].data_ptr(), st.x.data_ptr(), ws["unet_in"].data_ptr(), n_px, 8, stream))
-        if do_cfg:
-            ws["unet_in"][B:].copy_(ws["unet_in"][:B])  # gm.py:1047
+        # gm.py:1047 torch.cat([x] * 2) is never materialised (B200UNet cfg_shared)
         ctx = torch.cat([negative_prompt_embeds, prompt_embeds]) if do_cfg else prompt_embeds
         kv = self.unet.project_context(ctx)
         if ws["kv"] is None or any(a.shape != b.shape for a, b in zip(ws["kv"], kv)):
@@ -114,7 +113,7 @@ class StableDiffusionGMPipeline(PipelineBase):
                 a.copy_(b)
         ts = [int(t) for t in timesteps]
         table = self.unet.timestep_table(ts)
-        run = self._unet_runner(("gm1", B, h, w, do_cfg), self.unet, ws["unet_in"], ws["temb"], ws["kv"], ws["eps"])
+        run = self._unet_runner(("gm1", B, h, w, do_cfg), self.unet, ws["unet_in"], ws["temb"], ws["kv"], ws["eps"], cfg_shared=do_cfg)
         extra = self.prepare_extra_step_kwargs(generator, eta)
         eps_u = ws["eps"][:B].reshape(-1, 4) if do_cfg else None
         eps_c = (ws["eps"][B:] if do_cfg else ws["eps"]).reshape(-1, 4)
@@ -130,7 +129,7 @@ class StableDiffusionGMPipeline(PipelineBase):
                 L.check(L.lib().gmd_latents_nchw_to_px(z.contiguous().data_ptr(), st.noise.data_ptr(), B, h * w, stream))
             S.fused_step(plan, st, eps_c, eps_u, guidance_scale=guidance_scale, guidance_rescale=guidance_rescale if do_cfg else 0.0,
                          px_per_sample=h * w, x0_coeffs=self.scheduler.x0_coeffs(t), concat_out=ws["unet_in"], concat_lead=ws["sdr_px"],
-                         concat_self=True, concat_dup=mult, rescale_ws=ws["rescale"])
+                         concat_self=True, concat_dup=1, rescale_ws=ws["rescale"])
             if callback_on_step_end is not None:  # gm.py:1073-1081
                 cb_kwargs = {}
                 for k in callback_on_step_end_tensor_inputs:
@@ -141,8 +140,6 @@ class StableDiffusionGMPipeline(PipelineBase):
                     new = cb_out["latents"].to(device=device, dtype=torch.float32).contiguous()
                     L.check(L.lib().gmd_latents_nchw_to_px(new.data_ptr(), st.x.data_ptr(), B, h * w, stream))
                     L.check(L.lib().gmd_pack_unet_input(ws["sdr_px"].data_ptr(), st.x.data_ptr(), ws["unet_in"].data_ptr(), n_px, 8, stream))
-                    if do_cfg:
-                        ws["unet_in"][B:].copy_(ws["unet_in"][:B])
         image = self._latents_nchw(st.x, B, h, w).to(out_dtype)
         if output_type != "latent":
             if self.vae is None:

@@ -88,7 +88,10 @@ class _Transformer:
         """Step-invariant text K/V: Linear(768 -> C) of the CLIP states, fused [K | V]."""
         return ops.gemm(ctx2d, self.w_kv2)
 
-    def __call__(self, x, kv, ws):
+    def __call__(self, x, kv, ws, dup: bool = False):
+        """`dup`: x holds ONE copy of a batch whose two CFG halves are still identical (nothing before the first text
+        cross-attention depends on the prompt); everything up to and including self-attention runs once, then the token
+        stream and the residual are duplicated (uncond | cond) and the rest runs on 2B samples."""
         B, H, W, c = x.shape
         n, m = H * W, B * H * W
         y = ops.groupnorm_silu(x, *self.norm, eps=1e-6, silu=False, stats_ws=ws)
@@ -100,6 +103,10 @@ class _Transformer:
         qkv = ops.gemm(h, self.w_qkv).view(B, n, 3 * c)
         a = ops.attention(qkv[..., :c], qkv[..., c:2 * c], qkv[..., 2 * c:], self.heads)
         y = ops.gemm(a.view(m, c), self.w_o1, bias=self.b_o1, residual=y, out_f32=True)
+        if dup:
+            y = torch.cat([y, y], 0)
+            x = torch.cat([x, x], 0)
+            B, m = 2 * B, 2 * m
         # text cross-attention (K/V hoisted)
         h = ops.layernorm(y, *self.ln[1])
         q = ops.gemm(h, self.w_q2).view(B, n, c)
@@ -173,7 +180,7 @@ class B200UNet:
         # all 22 time_emb_proj linears as ONE GEMM: [sum(Cout), 1280]
         self.w_temb = _w(torch.cat([w for w, _ in temb_slices], 0), dev)
         self.b_temb = _f32(torch.cat([b for _, b in temb_slices], 0), dev)
-        self._gn_ws = torch.empty(64 * 32 * 32 * 2, dtype=torch.float32, device=dev)  # up to 64 samples per forward
+        self._gn_ws = ops.gn_workspace(64, 32, dev)  # up to 64 samples per forward
         self.transformers: List[_Transformer] = [a for _, att, _ in self.down for a in att if a is not None] + [self.mid_att] + \
             [a for _, att, _ in self.up for a in att if a is not None]
 
@@ -205,20 +212,31 @@ class B200UNet:
 
     # ---- the forward pass ------------------------------------------------------------------------------------
     def forward(self, sample: torch.Tensor, temb_row: torch.Tensor, context_kv: List[torch.Tensor],
-                out: Optional[torch.Tensor] = None) -> torch.Tensor:
+                out: Optional[torch.Tensor] = None, cfg_shared: bool = False) -> torch.Tensor:
         """sample: bf16 [B,h,w,8] (channel-padded NHWC, written by kernel (c)); temb_row: fp32 [1 or B, sum(Cout)]
-        row(s) of `timestep_table`; context_kv: `project_context` output.  Returns eps fp32 [B,h,w,out_channels]."""
+        row(s) of `timestep_table`; context_kv: `project_context` output.  Returns eps fp32 [B,h,w,out_channels].
+
+        `cfg_shared`: classifier-free guidance feeds the SAME latents to the uncond and cond halves
+        (`torch.cat([latents] * 2)`, stable_diffusion_dual_unet.py:1045), and nothing before the first text cross-attention
+        looks at the prompt.  `sample` then holds ONE copy [B,...], context_kv covers 2B (uncond | cond); conv_in, the first
+        resnet and the first transformer's GroupNorm / proj_in / LayerNorm / QKV / self-attention run once on B samples and the
+        result is duplicated.  Output eps is [2B,...].  Bit-identical to running the duplicated batch (per-sample ops)."""
         B = sample.shape[0]
-        temb_all = temb_row if temb_row.shape[0] == B else temb_row.expand(B, -1)
+        full = 2 * B if cfg_shared else B
+        temb_all = temb_row if temb_row.shape[0] == full else temb_row.expand(full, -1)
         ws = self._gn_ws
         kv = iter(context_kv)
         x = ops.conv2d(sample, self.w_in, self.ch0, bias=self.b_in)
-        skips = [x]
+        skips = [torch.cat([x, x], 0) if cfg_shared else x]
+        pending_dup = cfg_shared
         for res, att, ds in self.down:
             for r, a in zip(res, att):
-                x = r(x, None, temb_all, ws)
+                x = r(x, None, temb_all[: x.shape[0]], ws)
                 if a is not None:
-                    x = a(x, next(kv), ws)
+                    x = a(x, next(kv), ws, dup=pending_dup)
+                    pending_dup = False
+                elif pending_dup:
+                    raise NotImplementedError("cfg_shared needs an attention block after the first resnet")
                 skips.append(x)
             if ds is not None:
                 x = ops.conv2d(x, ds[0], ds[0].shape[0], stride=2, bias=ds[1])

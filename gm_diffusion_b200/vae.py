@@ -59,7 +59,7 @@ class B200VaeDecoder:
         self.n_out = (_f32(sd[d + "conv_norm_out.weight"], dev), _f32(sd[d + "conv_norm_out.bias"], dev))
         self.w_out = ops.pack_conv_weight_tiled(sd[d + "conv_out.weight"].to(dev))
         self.b_out = _f32(sd[d + "conv_out.bias"], dev)
-        self._gn_ws = torch.empty(64 * 32 * 32 * 2, dtype=torch.float32, device=dev)  # up to 64 samples per forward
+        self._gn_ws = ops.gn_workspace(64, 32, dev)  # up to 64 samples per forward
 
     @classmethod
     def from_module(cls, module, device="cuda", **kw) -> "B200VaeDecoder":

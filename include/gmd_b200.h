@@ -201,7 +201,7 @@ int gmd_conv_fwd(const gmd_conv_params* p, void* stream);
  * enum gmd_dtype), output bf16.  Deterministic fixed-order reductions. */
 int gmd_groupnorm_silu(const void* x0, int32_t C0, const void* x1, int32_t C1, const float* gamma, const float* beta,
                        void* out, int32_t N, int32_t HW, int32_t groups, float eps, int32_t apply_silu, int32_t in_dtype,
-                       float* stats_ws /* fp32 workspace, N * 32 * groups * 2 floats */, void* stream);
+                       float* stats_ws /* workspace of 1024 + N*34*groups*2 4-byte words (N <= 1024); the first 1024 (arrival counters) ZEROED before first use */, void* stream);
 /* LayerNorm over the last dim of token-major [M, C] (bf16 or fp32 in, bf16 out). */
 int gmd_layernorm(const void* x, const float* gamma, const float* beta, void* out, int64_t M, int32_t C, float eps,
                   int32_t in_dtype, void* stream);

@@ -44,12 +44,12 @@ g = torch.Generator(device=dev).manual_seed(5)
 ctx2 = torch.randn(2 * B, 77, 768, device=dev, generator=g)
 kv_s, kv_g = pipe.unet.project_context(ctx2), pipe.gm_unet.project_context(ctx2[:B])
 tb_s, tb_g = pipe.unet.timestep_table([501]), pipe.gm_unet.timestep_table([501])
-xs = torch.randn(2 * B, 64, 64, 8, device=dev, generator=g).to(torch.bfloat16)
+xs = torch.randn(B, 64, 64, 8, device=dev, generator=g).to(torch.bfloat16)
 xg = torch.randn(B, 64, 64, 8, device=dev, generator=g).to(torch.bfloat16)
 for it in range(2):
     for n in names: setattr(ops, n, wrap(n))
     rec.clear(); torch.cuda.synchronize()
-    pipe.unet.forward(xs, tb_s, kv_s); pipe.gm_unet.forward(xg, tb_g, kv_g)
+    pipe.unet.forward(xs, tb_s, kv_s, cfg_shared=True); pipe.gm_unet.forward(xg, tb_g, kv_g)
     torch.cuda.synchronize()
     for n in names: setattr(ops, n, orig[n])
 agg = defaultdict(lambda: [0.0, 0.0, 0])

@@ -20,14 +20,14 @@ tb_s, tb_g = pipe.unet.timestep_table([981]), pipe.gm_unet.timestep_table([981])
 n_px = B * h * w
 sdr, gm = S.BranchState(n_px, dev), S.BranchState(n_px, dev)
 sdr.x.normal_(generator=g); gm.x.copy_(sdr.x)
-unet_in = torch.zeros(2 * B, h, w, 8, dtype=torch.bfloat16, device=dev)
+unet_in = torch.zeros(B, h, w, 8, dtype=torch.bfloat16, device=dev)
 gm_in = torch.zeros(B, h, w, 8, dtype=torch.bfloat16, device=dev)
 eps_s = torch.empty(2 * B, h, w, 4, device=dev); eps_g = torch.empty(B, h, w, 4, device=dev)
 
 def step(t):
-    pipe.unet.forward(unet_in, tb_s, kv_s, out=eps_s)
+    pipe.unet.forward(unet_in, tb_s, kv_s, out=eps_s, cfg_shared=True)
     S.fused_step(sched.plan_step(t), sdr, eps_s[B:].reshape(-1, 4), eps_s[:B].reshape(-1, 4), guidance_scale=7.5, px_per_sample=h * w,
-                 x0_coeffs=sched.x0_coeffs(t), unet_in_next=unet_in, unet_in_dup=2, concat_out=gm_in, concat_tail=gm.x)
+                 x0_coeffs=sched.x0_coeffs(t), unet_in_next=unet_in, unet_in_dup=1, concat_out=gm_in, concat_tail=gm.x)
     pipe.gm_unet.forward(gm_in, tb_g, kv_g, out=eps_g)
     S.fused_step(gs.plan_step(t), gm, eps_g.reshape(-1, 4), x0_coeffs=gs.x0_coeffs(t))
 

@@ -58,6 +58,20 @@ def test_unet_batch_independence(b200_unets):
     assert torch.equal(full[1:2], one), f"a sample's eps must not depend on the batch it is in (rel {rel_l2(full[1:2], one):.2e})"
 
 
+def test_cfg_shared_prefix_is_exact(b200_unets):
+    """cfg_shared (one copy of the latents for both CFG halves, prefix computed once) == the duplicated batch, bit for bit."""
+    mine = b200_unets[0]
+    g = torch.Generator().manual_seed(9)
+    x = torch.randn(2, 32, 32, 8, generator=g).to(torch.bfloat16).cuda()
+    x[..., 4:] = 0
+    ctx = torch.randn(4, 77, 768, generator=g).cuda()
+    kv = mine.project_context(ctx)
+    tb = mine.timestep_table([321])
+    full = mine.forward(torch.cat([x, x]), tb, kv)
+    shared = mine.forward(x, tb, kv, cfg_shared=True)
+    assert shared.shape == full.shape and torch.equal(shared, full)
+
+
 def test_vae_decoder_parity():
     from gm_diffusion_b200 import B200VaeDecoder
     from oracle.vae_oracle import VaeDecoderOracle
