@@ -46,7 +46,17 @@ struct Cfg {
     static constexpr int DPV = (D + 1 + 15) / 16 * 16;      // N extent of P V: head dim + the ones column
     static_assert(DPV <= NDB * 64, "ones column must fall inside the loaded V blocks");
     static constexpr int KS = 2, VS = 2;                    // K / V ring depths
-    static constexpr int PB = D == 80 ? 1 : 2;              // P buffers (one at d = 80 keeps two CTAs per SM)
+    // (measured: three co-resident CTAs per SM with single-buffered S / P at d = 40 reach 354 TFLOP/s vs 378 for two CTAs
+    // with double buffering, so the double-buffered configuration stays)
+    static constexpr int SB = 2;                            // S buffers in TMEM
+    // NSET = 2 (d = 40): the 64 keys of a tile are split between TWO independent softmax warp sets (8 warps), each with its
+    // own running maximum, its own O accumulator and its own denominator (flash-decoding style split over keys, merged once
+    // at the end).  ncu on the 4-warp version: XU (MUFU) pipe 52 % busy, issue slots 39 % — latency-bound with one softmax
+    // warp per sub-partition per CTA; the split doubles the warps in flight without any cross-warp exchange per tile.
+    static constexpr int NSET = D == 40 ? 2 : 1;
+    static constexpr int KW = BKV / NSET;                   // keys per softmax thread per tile
+    static constexpr int THREADS = 64 + 128 * NSET;
+    static constexpr int PB = D == 80 ? 1 : 2;              // P buffers in smem (one at d = 80 keeps two CTAs per SM)
     static constexpr int Q_BYTES = NDB * BQ * 128;
     static constexpr int KV_BLOCK_BYTES = BKV * 128;        // one d block of a K or V tile
     static constexpr int K_BYTES = NDB * KV_BLOCK_BYTES;
@@ -56,12 +66,13 @@ struct Cfg {
     static constexpr int OFF_P = OFF_V + VS * K_BYTES;
     static constexpr int OFF_BAR = OFF_P + PB * P_BYTES;
     static constexpr int SMEM = OFF_BAR + 256 + 1024;
-    static constexpr uint32_t TMEM_COLS = (2 * BKV + DPV) <= 256 ? 256 : 512;
+    static constexpr uint32_t TMEM_COLS = (SB * BKV + NSET * DPV) <= 128 ? 128 : (SB * BKV + NSET * DPV) <= 256 ? 256 : 512;
+    static_assert(NSET == 1 || P_BYTES * PB >= BQ * (DPV + 1) * 4, "merge scratch must fit in the P buffers");
     static constexpr int MIN_CTAS = D <= 80 ? 2 : 1;
 };
 
 template <int D>
-__global__ void __launch_bounds__(192, Cfg<D>::MIN_CTAS)
+__global__ void __launch_bounds__(Cfg<D>::THREADS, Cfg<D>::MIN_CTAS)
 attn_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_k,
             const __grid_constant__ CUtensorMap map_v, const AttnArgs args) {
     using C = Cfg<D>;
@@ -91,7 +102,7 @@ attn_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ C
         mbar_init(q_full, 1);
         for (int s = 0; s < 2; ++s) {
             mbar_init(&k_full[s], 1); mbar_init(&k_empty[s], 1); mbar_init(&v_full[s], 1); mbar_init(&v_empty[s], 1);
-            mbar_init(&s_full[s], 1); mbar_init(&p_full[s], 128); mbar_init(&pv_done[s], 1);
+            mbar_init(&s_full[s], 1); mbar_init(&p_full[s], 128 * C::NSET); mbar_init(&pv_done[s], 1);
         }
         fence_barrier_init();
     }
@@ -100,7 +111,7 @@ attn_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ C
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
-    const uint32_t tmem_o = tmem_base + 2 * BKV;
+    const uint32_t tmem_o = tmem_base + C::SB * BKV;
 
     if (warp == 0) {
         if (lane == 0) {
@@ -137,14 +148,14 @@ attn_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ C
                     const int blk = ks >> 2, within = ks & 3;
                     uint64_t da = umma_desc_k_sw128(q_addr + blk * (BQ * 128) + within * 32);
                     uint64_t db = umma_desc_k_sw128(k_addr + blk * C::KV_BLOCK_BYTES + within * 32);
-                    umma_bf16_ss(tmem_base + (j & 1) * BKV, da, db, IDESC_S, ks != 0 ? 1u : 0u);
+                    umma_bf16_ss(tmem_base + (j % C::SB) * BKV, da, db, IDESC_S, ks != 0 ? 1u : 0u);
                 }
                 umma_commit(&k_empty[st]);
-                umma_commit(&s_full[j & 1]);
+                umma_commit(&s_full[j % C::SB]);
             };
             mbar_wait(q_full, 0);
             issue_s(0);
-            if (T > 1) issue_s(1);
+            if (C::SB > 1 && T > 1) issue_s(1);
             for (int j = 0; j < T; ++j) {
                 const int st = j % C::VS;
                 mbar_wait(&p_full[j & 1], (j >> 1) & 1);   // softmax_j: P_j in smem, ones column set, S[j&1] drained
@@ -154,42 +165,50 @@ attn_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ C
                 const uint32_t p_addr = smem_u32(p_smem + (C::PB == 2 ? (j & 1) : 0) * C::P_BYTES);
 #pragma unroll
                 for (int ks = 0; ks < BKV / 16; ++ks) {
+                    // key half ks / (KW/16) accumulates into its own O (NSET = 2), else everything into one
+                    constexpr int KSTEPS = C::KW / 16;
                     uint64_t da = umma_desc_k_sw128(p_addr + ks * 32);
                     uint64_t db = umma_desc_mn_sw128(v_addr + ks * 16 * 128, C::KV_BLOCK_BYTES);
-                    umma_bf16_ss(tmem_o, da, db, IDESC_O, (j | ks) != 0 ? 1u : 0u);
+                    umma_bf16_ss(tmem_o + (ks / KSTEPS) * C::DPV, da, db, IDESC_O, (j != 0 || (ks % KSTEPS) != 0) ? 1u : 0u);
                 }
                 umma_commit(&v_empty[st]);
                 umma_commit(&pv_done[j & 1]);
-                if (j + 2 < T) issue_s(j + 2);
+                if (j + C::SB < T) issue_s(j + C::SB);   // S[j % SB] was drained by softmax_j (p_full_j)
             }
         }
     } else {
+        constexpr int KW = C::KW;
         const int lg = warp & 3;
+        const int set = (warp - 2) >> 2;                      // which key half this warp set owns (NSET = 2), else 0
         const int row = lg * 32 + lane;
         const uint32_t lane_off = static_cast<uint32_t>(lg * 32) << 16;
+        const uint32_t my_o = tmem_o + set * C::DPV + lane_off;
         const float c = args.scale_log2;
-        float m = -INFINITY;   // running (possibly stale) row maximum in scaled log2 units
+        float m = -INFINITY;   // running (possibly stale) row maximum of THIS key half in scaled log2 units
         for (int j = 0; j < T; ++j) {
-            mbar_wait(&s_full[j & 1], (j >> 1) & 1);
+            mbar_wait(&s_full[j % C::SB], (j / C::SB) & 1);
             tc_fence_after();
-            uint32_t sr[64];
-            {
+            uint32_t sr[KW];
+            if constexpr (KW == 64) {
                 uint32_t t0[32], t1[32];
-                tmem_ld_32x32(tmem_base + (j & 1) * BKV + lane_off, t0);
-                tmem_ld_32x32(tmem_base + (j & 1) * BKV + lane_off + 32, t1);
+                tmem_ld_32x32(tmem_base + (j % C::SB) * BKV + lane_off, t0);
+                tmem_ld_32x32(tmem_base + (j % C::SB) * BKV + lane_off + 32, t1);
                 tmem_wait_ld();
 #pragma unroll
                 for (int k = 0; k < 32; ++k) { sr[k] = t0[k]; sr[32 + k] = t1[k]; }
+            } else {
+                tmem_ld_32x32(tmem_base + (j % C::SB) * BKV + lane_off + set * KW, sr);
+                tmem_wait_ld();
             }
-            const int valid = args.Nk - j * BKV;  // columns >= valid are padding keys (last tile only)
-            if (valid < BKV) {
+            const int valid = args.Nk - j * BKV - set * KW;  // columns >= valid are padding keys (last tile only)
+            if (valid < KW) {
 #pragma unroll
-                for (int k = 0; k < 64; ++k) if (k >= valid) sr[k] = 0xff800000u;  // -inf
+                for (int k = 0; k < KW; ++k) if (k >= valid) sr[k] = 0xff800000u;  // -inf
             }
-            // four independent running maxima: a 16-deep dependent chain instead of 64
+            // four independent running maxima: a short dependent chain
             float mx0 = __uint_as_float(sr[0]), mx1 = __uint_as_float(sr[1]), mx2 = __uint_as_float(sr[2]), mx3 = __uint_as_float(sr[3]);
 #pragma unroll
-            for (int k = 4; k < 64; k += 4) {
+            for (int k = 4; k < KW; k += 4) {
                 mx0 = fmaxf(mx0, __uint_as_float(sr[k])); mx1 = fmaxf(mx1, __uint_as_float(sr[k + 1]));
                 mx2 = fmaxf(mx2, __uint_as_float(sr[k + 2])); mx3 = fmaxf(mx3, __uint_as_float(sr[k + 3]));
             }
@@ -198,11 +217,12 @@ attn_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ C
             const bool grow = mt > m + 8.0f;           // lazy: keep the stale maximum while exponents stay <= 8
             const float m_new = grow ? mt : m;
             const float alpha = grow ? ex2(m - m_new) : 1.0f;   // first tile: m = -inf -> 0
-            uint32_t pk[32];
+            const float m_sub = m_new == -INFINITY ? 0.0f : m_new;   // a key half that has seen no valid key yet: p = 2^-inf = 0
+            uint32_t pk[KW / 2];
 #pragma unroll
-            for (int k = 0; k < 32; ++k) {
-                float p0 = ex2(fmaf(__uint_as_float(sr[2 * k]), c, -m_new));
-                float p1 = ex2(fmaf(__uint_as_float(sr[2 * k + 1]), c, -m_new));
+            for (int k = 0; k < KW / 2; ++k) {
+                float p0 = ex2(fmaf(__uint_as_float(sr[2 * k]), c, -m_sub));
+                float p1 = ex2(fmaf(__uint_as_float(sr[2 * k + 1]), c, -m_sub));
                 pk[k] = pack_bf16x2(p0, p1);
             }
             m = m_new;
@@ -215,11 +235,13 @@ attn_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ C
                 // P row -> smem, K-major SWIZZLE_128B: 16-byte chunk c of row r lands at chunk (c ^ (r & 7))
                 uint8_t* prow = p_smem + (C::PB == 2 ? (j & 1) : 0) * C::P_BYTES + row * 128;
 #pragma unroll
-                for (int ch = 0; ch < 8; ++ch)
-                    *reinterpret_cast<uint4*>(prow + ((ch ^ (row & 7)) << 4)) = make_uint4(pk[4 * ch], pk[4 * ch + 1], pk[4 * ch + 2], pk[4 * ch + 3]);
+                for (int ch = 0; ch < KW / 8; ++ch) {
+                    const int cc = set * (KW / 8) + ch;
+                    *reinterpret_cast<uint4*>(prow + ((cc ^ (row & 7)) << 4)) = make_uint4(pk[4 * ch], pk[4 * ch + 1], pk[4 * ch + 2], pk[4 * ch + 3]);
+                }
             }
             // ones column of V_j (column D of the zero padding) -> the P V MMA also accumulates the softmax denominator
-            {
+            if (set == 0) {
                 const int st = j % C::VS;
                 mbar_wait(&v_full[st], (j / C::VS) & 1);
                 if (row < BKV) {
@@ -234,11 +256,11 @@ attn_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ C
 #pragma unroll
                 for (int ch = 0; ch < C::DPV / 16; ++ch) {
                     uint32_t o[16];
-                    tmem_ld_32x16(tmem_o + lane_off + ch * 16, o);
+                    tmem_ld_32x16(my_o + ch * 16, o);
                     tmem_wait_ld();
 #pragma unroll
                     for (int k = 0; k < 16; ++k) o[k] = __float_as_uint(__uint_as_float(o[k]) * alpha);
-                    tmem_st_32x16(tmem_o + lane_off + ch * 16, o);
+                    tmem_st_32x16(my_o + ch * 16, o);
                 }
                 tmem_wait_st();
             }
@@ -250,29 +272,65 @@ attn_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ C
         tc_fence_after();
         const int q = q0 + row;
         __nv_bfloat16* op = args.o + batch * args.o_stride_b + (int64_t)q * args.o_stride_n + head * args.o_stride_h;
-        float inv_l;
-        {
-            // denominator accumulated by the MMA through the ones column (column D of O)
-            uint32_t o[16];
-            tmem_ld_32x16(tmem_o + lane_off + (D / 16) * 16, o);
-            tmem_wait_ld();
-            inv_l = 1.0f / __uint_as_float(o[D % 16]);
-        }
+        if constexpr (C::NSET == 1) {
+            float inv_l;
+            {
+                // denominator accumulated by the MMA through the ones column (column D of O)
+                uint32_t o[16];
+                tmem_ld_32x16(my_o + (D / 16) * 16, o);
+                tmem_wait_ld();
+                inv_l = 1.0f / __uint_as_float(o[D % 16]);
+            }
 #pragma unroll
-        for (int ch = 0; ch < (D + 15) / 16; ++ch) {
-            uint32_t o[16];
-            tmem_ld_32x16(tmem_o + lane_off + ch * 16, o);
-            tmem_wait_ld();
-            if (q < args.Nq) {
+            for (int ch = 0; ch < (D + 15) / 16; ++ch) {
+                uint32_t o[16];
+                tmem_ld_32x16(my_o + ch * 16, o);
+                tmem_wait_ld();
+                if (q < args.Nq) {
 #pragma unroll
-                for (int h8 = 0; h8 < 2; ++h8) {
-                    const int d0 = ch * 16 + h8 * 8;
-                    if (d0 < D) {  // D is a multiple of 8
-                        uint4 v = make_uint4(pack_bf16x2(__uint_as_float(o[h8 * 8 + 0]) * inv_l, __uint_as_float(o[h8 * 8 + 1]) * inv_l),
-                                             pack_bf16x2(__uint_as_float(o[h8 * 8 + 2]) * inv_l, __uint_as_float(o[h8 * 8 + 3]) * inv_l),
-                                             pack_bf16x2(__uint_as_float(o[h8 * 8 + 4]) * inv_l, __uint_as_float(o[h8 * 8 + 5]) * inv_l),
-                                             pack_bf16x2(__uint_as_float(o[h8 * 8 + 6]) * inv_l, __uint_as_float(o[h8 * 8 + 7]) * inv_l));
-                        *reinterpret_cast<uint4*>(op + d0) = v;
+                    for (int h8 = 0; h8 < 2; ++h8) {
+                        const int d0 = ch * 16 + h8 * 8;
+                        if (d0 < D) {  // D is a multiple of 8
+                            uint4 v = make_uint4(pack_bf16x2(__uint_as_float(o[h8 * 8 + 0]) * inv_l, __uint_as_float(o[h8 * 8 + 1]) * inv_l),
+                                                 pack_bf16x2(__uint_as_float(o[h8 * 8 + 2]) * inv_l, __uint_as_float(o[h8 * 8 + 3]) * inv_l),
+                                                 pack_bf16x2(__uint_as_float(o[h8 * 8 + 4]) * inv_l, __uint_as_float(o[h8 * 8 + 5]) * inv_l),
+                                                 pack_bf16x2(__uint_as_float(o[h8 * 8 + 6]) * inv_l, __uint_as_float(o[h8 * 8 + 7]) * inv_l));
+                            *reinterpret_cast<uint4*>(op + d0) = v;
+                        }
+                    }
+                }
+            }
+        } else {
+            // merge the two key halves: O = (O_a 2^(m_a - m) + O_b 2^(m_b - m)) / (l_a 2^(m_a - m) + l_b 2^(m_b - m)).
+            // Set 1 parks (m_b, O_b[0..DPV)) in the (now idle) P buffers, set 0 combines and writes the output row.
+            float ov[C::DPV];
+#pragma unroll
+            for (int ch = 0; ch < C::DPV / 16; ++ch) {
+                uint32_t o[16];
+                tmem_ld_32x16(my_o + ch * 16, o);
+                tmem_wait_ld();
+#pragma unroll
+                for (int k = 0; k < 16; ++k) ov[ch * 16 + k] = __uint_as_float(o[k]);
+            }
+            float* scratch = reinterpret_cast<float*>(p_smem) + row * (C::DPV + 1);   // odd pitch: conflict-free rows
+            if (set == 1) {
+                scratch[C::DPV] = m;
+#pragma unroll
+                for (int k = 0; k <= D; ++k) scratch[k] = ov[k];
+            }
+            asm volatile("bar.sync 2, 256;" ::: "memory");
+            if (set == 0) {
+                const float mb = scratch[C::DPV];
+                const float mm = fmaxf(m, mb);
+                const float wa = ex2(m - mm), wb = mb == -INFINITY ? 0.0f : ex2(mb - mm);
+                const float inv_l = 1.0f / (ov[D] * wa + scratch[D] * wb);
+                if (q < args.Nq) {
+#pragma unroll
+                    for (int d0 = 0; d0 < D; d0 += 8) {
+                        float r[8];
+#pragma unroll
+                        for (int k = 0; k < 8; ++k) r[k] = (ov[d0 + k] * wa + scratch[d0 + k] * wb) * inv_l;
+                        *reinterpret_cast<uint4*>(op + d0) = make_uint4(pack_bf16x2(r[0], r[1]), pack_bf16x2(r[2], r[3]), pack_bf16x2(r[4], r[5]), pack_bf16x2(r[6], r[7]));
                     }
                 }
             }
@@ -312,7 +370,7 @@ int launch(const gmd_attn_params* p, cudaStream_t st) {
     a.Nq = p->Nq; a.Nk = p->Nk;
     a.scale_log2 = p->scale * 1.4426950408889634f;
     dim3 grid((p->Nq + BQ - 1) / BQ, p->H, p->B);
-    attn_kernel<D><<<grid, 192, C::SMEM, st>>>(mq, mk, mv, a);
+    attn_kernel<D><<<grid, C::THREADS, C::SMEM, st>>>(mq, mk, mv, a);
     count_launch(1);
     return check_launch("attn_kernel");
 }

@@ -1,3 +1,2 @@
 mkdir -p gpurun_out
-python profiles/prof_step.py > gpurun_out/plain_step.log 2>&1 && ncu --metrics gpu__time_duration.sum --clock-control none --profile-from-start off --csv --log-file gpurun_out/launches_step_r01.csv python profiles/prof_step.py > gpurun_out/ncu_step.log 2>&1; echo "launch-list rc $?"; cat gpurun_out/plain_step.log | tail -1; wc -l gpurun_out/launches_step_r01.csv
-python profiles/prof_gemm.py > gpurun_out/plain.log 2>&1 && ncu --set full --clock-control none --import-source on -k regex:gemm_kernel -s 2 -c 2 -o gpurun_out/prof_gemm_r01 python profiles/prof_gemm.py > gpurun_out/ncu.log 2>&1; echo "ncu gemm rc $?"
+python profiles/prof_attn.py > gpurun_out/plain.log 2>&1 && ncu --set full --clock-control none --import-source on -k regex:attn_kernel -s 2 -c 1 -o gpurun_out/prof_attn_r01 python profiles/prof_attn.py > gpurun_out/ncu.log 2>&1; echo "ncu rc $?"; tail -2 gpurun_out/ncu.log
