@@ -88,6 +88,30 @@ __device__ __forceinline__ void bulk_copy_g2s(void* smem_dst, const void* gsrc, 
                  "r"(bytes), "r"(smem_u32(bar))
                  : "memory");
 }
+// TMA loads multicast to every CTA of the cluster named in `mask` (same CTA-relative smem offset and mbarrier in each)
+__device__ __forceinline__ void tma_load_3d_mc(void* smem_dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1, int c2, uint16_t mask) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%3, %4, %5}], [%2], %6;"
+        ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "h"(mask)
+        : "memory");
+}
+__device__ __forceinline__ void tma_load_4d_mc(void* smem_dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1, int c2, int c3, uint16_t mask) {
+    asm volatile(
+        "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%3, %4, %5, %6}], [%2], %7;"
+        ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "h"(mask)
+        : "memory");
+}
+// tcgen05.commit arriving on the same mbarrier offset in every CTA of `mask`
+__device__ __forceinline__ void umma_commit_mc(uint64_t* bar, uint16_t mask) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(smem_u32(bar)), "h"(mask)
+                 : "memory");
+}
+__device__ __forceinline__ uint32_t cluster_ctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+
 // 256-bit global store (STG.256, sm_100): one full 32-byte sector per thread per instruction
 __device__ __forceinline__ void st_global_256(void* p, uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t a4, uint32_t a5, uint32_t a6,
                                               uint32_t a7) {
@@ -108,7 +132,11 @@ __device__ __forceinline__ void st_bf16x16(__nv_bfloat16* p, const float* v) {
 //     amortised over 256 rows (L2 -> SM bandwidth, ~40 B/clk/SM, is what bounds the main loop).
 //   * when two accumulator sets fit in TMEM (ACC = 2) the epilogue of tile i runs while the main loop of tile i+1
 //     already fills the other set; the smem ring and its mbarrier phases run continuously across tiles.
-template <int MT, int BN, int STAGES, int RB>
+//   * CL = 2: a CLUSTER of two CTAs works on two neighbouring N tiles of the same M super-tile; each CTA fetches ONE of the two
+//     128-row A sub-tiles and TMA-multicasts it into both CTAs' smem, so the A bytes crossing the L2 -> SM fabric are halved
+//     (36 KB instead of 52 KB per k block at 256x160).  A smem slot is recycled only after BOTH CTAs' MMAs have read it
+//     (tcgen05.commit multicast onto both empty barriers).
+template <int MT, int BN, int STAGES, int RB, int CL>
 __global__ void __launch_bounds__(320, 1)
 gemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__ CUtensorMap map_a1,
             const __grid_constant__ CUtensorMap map_a2, const __grid_constant__ CUtensorMap map_a3,
@@ -128,21 +156,26 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__ 
     uint64_t* res_bar = acc_empty + 2;         // residual prefetch rounds
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(res_bar + 1);
 
+    static_assert(CL == 1 || MT == 2, "the A multicast splits the two 128-row sub-tiles between the two CTAs");
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
-    const int num_tiles = args.tiles_mt * args.tiles_n * args.gz * args.ksplit;
+    const int crank = CL > 1 ? (int)cluster_ctarank() : 0;
+    const int tn_c = args.tiles_n / CL;                 // N tile groups (a cluster covers CL neighbouring N tiles)
+    const int num_tiles = args.tiles_mt * tn_c * args.gz * args.ksplit;
+    const int tile0 = blockIdx.x / CL, tstride = gridDim.x / CL;
 
     if (threadIdx.x == 0) {
         tma_prefetch_desc(&map_a0);
         tma_prefetch_desc(&map_w);
-        for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+        for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], CL); }
         for (int s = 0; s < 2; ++s) { mbar_init(&acc_full[s], 1); mbar_init(&acc_empty[s], 256); }
         mbar_init(res_bar, 256);
         fence_barrier_init();
     }
     if (warp == 1) tmem_alloc<P::TMEM_COLS>(tmem_slot);
     tc_fence_before();
-    __syncthreads();
+    if (CL > 1) cluster_sync_all();   // barrier inits visible cluster-wide before any multicast / remote arrive
+    else __syncthreads();
     tc_fence_after();
     const uint32_t tmem_acc = *tmem_slot;
 
@@ -151,11 +184,11 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__ 
         if (elect_one()) {
             const int chunks_per_tap = args.chunks0 + args.chunks1;
             uint32_t kbg = 0;  // k-blocks issued so far (ring position carries across tiles)
-            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+            for (int tile = tile0; tile < num_tiles; tile += tstride) {
                 const int mt = tile % args.tiles_mt;
                 const int rest = tile / args.tiles_mt;
-                const int n0 = (rest % args.tiles_n) * BN;
-                const int zk = rest / args.tiles_n;
+                const int n0 = ((rest % tn_c) * CL + crank) * BN;
+                const int zk = rest / tn_c;
                 const int zb = zk % args.gz, ksl = zk / args.gz;
                 const int kb_begin = ksl * args.kb_per_split;
                 const int kb_end = min(args.num_kb, kb_begin + args.kb_per_split);
@@ -176,10 +209,15 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__ 
                     uint8_t* sb = sa + P::A_BYTES;
                     mbar_expect_tx(&full_bar[stage], P::STAGE_BYTES);
                     if (args.mode == 0) {
+                        if (CL > 1) {
+                            // this CTA's sub-tile, multicast into both CTAs of the pair
+                            tma_load_3d_mc(sa + crank * P::A_SUB, &map_a0, &full_bar[stage], kb * BK, m0[crank], zb, (uint16_t)0x3);
+                        } else {
 #pragma unroll
-                        for (int s = 0; s < MT; ++s) {
-                            if (kb < args.kb_src0) tma_load_3d(sa + s * P::A_SUB, &map_a0, &full_bar[stage], kb * BK, m0[s], zb);
-                            else tma_load_3d(sa + s * P::A_SUB, &map_a1, &full_bar[stage], (kb - args.kb_src0) * BK, m0[s], zb);
+                            for (int s = 0; s < MT; ++s) {
+                                if (kb < args.kb_src0) tma_load_3d(sa + s * P::A_SUB, &map_a0, &full_bar[stage], kb * BK, m0[s], zb);
+                                else tma_load_3d(sa + s * P::A_SUB, &map_a1, &full_bar[stage], (kb - args.kb_src0) * BK, m0[s], zb);
+                            }
                         }
                         if (args.w_tiled) tma_load_3d(sb, &map_w, &full_bar[stage], 0, ((n0 / BN) * args.num_kb + kb) * BN, 0);
                         else tma_load_3d(sb, &map_w, &full_bar[stage], kb * BK, n0, zb);
@@ -208,9 +246,13 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__ 
                             if (cc < args.chunks0) { map = &map_a0; c = cc * BK; }
                             else { map = &map_a1; c = (cc - args.chunks0) * BK; }
                         }
+                        if (CL > 1) {
+                            tma_load_4d_mc(sa + crank * P::A_SUB, map, &full_bar[stage], c, tw0[crank] + dw, th0[crank] + dh, tn0[crank], (uint16_t)0x3);
+                        } else {
 #pragma unroll
-                        for (int s = 0; s < MT; ++s)
-                            tma_load_4d(sa + s * P::A_SUB, map, &full_bar[stage], c, tw0[s] + dw, th0[s] + dh, tn0[s]);
+                            for (int s = 0; s < MT; ++s)
+                                tma_load_4d(sa + s * P::A_SUB, map, &full_bar[stage], c, tw0[s] + dw, th0[s] + dh, tn0[s]);
+                        }
                         if (args.w_tiled) tma_load_3d(sb, &map_w, &full_bar[stage], 0, ((n0 / BN) * args.num_kb + kb) * BN, 0);
                         else tma_load_3d(sb, &map_w, &full_bar[stage], tap * args.ctot + cc * BK, n0, 0);
                     }
@@ -221,12 +263,12 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__ 
         // =============================== MMA issuer ===============================
         if (elect_one()) {
             uint32_t kbg = 0, it = 0;
-            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+            for (int tile = tile0; tile < num_tiles; tile += tstride, ++it) {
                 const int ab = it % ACC;
                 mbar_wait(&acc_empty[ab], ((it / ACC) & 1) ^ 1);   // epilogue has drained this accumulator set
                 tc_fence_after();
                 const uint32_t tacc = tmem_acc + ab * P::ACC_COLS;
-                const int ksl = tile / (args.tiles_mt * args.tiles_n * args.gz);
+                const int ksl = tile / (args.tiles_mt * tn_c * args.gz);
                 const int kb_begin = ksl * args.kb_per_split;
                 const int kb_end = min(args.num_kb, kb_begin + args.kb_per_split);
                 for (int kb = kb_begin; kb < kb_end; ++kb, ++kbg) {
@@ -245,7 +287,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__ 
                             umma_bf16_ss(tacc + s * BN, da + 2 * k, db + 2 * k, IDESC, (kb > kb_begin || k != 0) ? 1u : 0u);
                         }
                     }
-                    umma_commit(&empty_bar[stage]);  // frees the smem slot once these MMAs have read it
+                    if (CL > 1) umma_commit_mc(&empty_bar[stage], (uint16_t)0x3);  // both CTAs' producers write this slot
+                    else umma_commit(&empty_bar[stage]);  // frees the smem slot once these MMAs have read it
                 }
                 umma_commit(&acc_full[ab]);  // accumulators of this tile complete
             }
@@ -284,8 +327,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__ 
             TileInfo ti;
             ti.mt = tile % args.tiles_mt;
             const int rest = tile / args.tiles_mt;
-            const int nt = rest % args.tiles_n;
-            const int zk = rest / args.tiles_n;
+            const int nt = (rest % tn_c) * CL + crank;
+            const int zk = rest / tn_c;
             ti.n0 = nt * BN; ti.zb = zk % args.gz;
             ti.out_col_tile = geglu ? nt * (BN / 2) : ti.n0;
             ti.tile_full = ti.out_col_tile + out_cols_tile <= args.N_out && (out_cols_tile % cw) == 0;
@@ -337,11 +380,11 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__ 
         uint32_t res_waited = 0;
 
         uint32_t it = 0;
-        if ((int)blockIdx.x < num_tiles) {
-            TileInfo t0 = tile_info(blockIdx.x);
+        if (tile0 < num_tiles) {
+            TileInfo t0 = tile_info(tile0);
             prefetch_residual(t0, row_info(t0, 0));
         }
-        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+        for (int tile = tile0; tile < num_tiles; tile += tstride, ++it) {
             const TileInfo ti = tile_info(tile);
             const int ab = it % ACC;
             // bias slice of this N tile -> smem (the first barrier keeps slow warps of the previous tile from losing theirs)
@@ -498,8 +541,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__ 
                 // this thread is done with its private residual row: stream in the next sub-tile's / next tile's chunks
                 if (s + 1 < MT) {
                     prefetch_residual(ti, row_info(ti, s + 1));
-                } else if (tile + (int)gridDim.x < num_tiles) {
-                    const TileInfo tn = tile_info(tile + gridDim.x);
+                } else if (tile + tstride < num_tiles) {
+                    const TileInfo tn = tile_info(tile + tstride);
                     prefetch_residual(tn, row_info(tn, 0));
                 }
             }
@@ -509,7 +552,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__ 
         }
         tc_fence_before();
     }
-    __syncthreads();
+    if (CL > 1) cluster_sync_all();   // no CTA may exit while its partner can still multicast into it / arrive on its barriers
+    else __syncthreads();
     if (warp == 1) {
         tc_fence_after();
         tmem_dealloc<P::TMEM_COLS>(tmem_acc);
@@ -549,9 +593,13 @@ __global__ void __launch_bounds__(256) splitk_finalize_kernel(const float* __res
     }
 }
 
+bool g_disable_cluster = false;   // GMD_NO_CLUSTER=1 in the environment falls back to single-CTA tiles (A/B measurements)
+
 int sm_count() {
     static int sms = 0;
     if (!sms) {
+        const char* e = getenv("GMD_NO_CLUSTER");
+        g_disable_cluster = e && e[0] == '1';
         int dev = 0;
         cudaGetDevice(&dev);
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
@@ -560,18 +608,27 @@ int sm_count() {
     return sms;
 }
 
-template <int MT, int BN, int STAGES, int RB>
+template <int MT, int BN, int STAGES, int RB, int CL = 1>
 int launch(const CUtensorMap* maps_a, const CUtensorMap& map_w, const KernelArgs& args, cudaStream_t st) {
     static bool configured = false;
     constexpr size_t smem = Plan<MT, BN, STAGES, RB>::TOTAL;
     if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(gemm_kernel<MT, BN, STAGES, RB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaError_t e = cudaFuncSetAttribute(gemm_kernel<MT, BN, STAGES, RB, CL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) { set_last_error("gemm: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return kErrCuda; }
         configured = true;
     }
-    const int64_t tiles = (int64_t)args.tiles_mt * args.tiles_n * args.gz;
-    const int grid = (int)(tiles < sm_count() ? tiles : sm_count());  // persistent: one CTA per SM
-    gemm_kernel<MT, BN, STAGES, RB><<<grid, 320, smem, st>>>(maps_a[0], maps_a[1], maps_a[2], maps_a[3], map_w, args);
+    // persistent: one CTA per SM; with CL = 2 one cluster (two SMs) per pair of N tiles
+    const int64_t items = (int64_t)args.tiles_mt * (args.tiles_n / CL) * args.gz * args.ksplit;
+    const int max_items = sm_count() / CL;
+    const int grid = (int)(items < max_items ? items : max_items) * CL;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(grid); cfg.blockDim = dim3(320); cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = CL; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr; cfg.numAttrs = CL > 1 ? 1 : 0;
+    cudaError_t e = cudaLaunchKernelEx(&cfg, gemm_kernel<MT, BN, STAGES, RB, CL>, maps_a[0], maps_a[1], maps_a[2], maps_a[3], map_w, args);
+    if (e != cudaSuccess) { set_last_error("gemm: launch: %s", cudaGetErrorString(e)); return kErrCuda; }
     count_launch(1);
     return check_launch("gemm_kernel");
 }
@@ -583,14 +640,19 @@ int launch_cfg(int bn, int64_t tiles_m, int64_t tiles_n, unsigned gz, const CUte
     // keep 128-row tiles with two accumulator SETS so the epilogue overlaps the next tile's main loop.  The fp32 residual
     // stream needs the larger private-row buffer, which only fits next to the 128-row pipeline.
     const bool res_f32 = args.residual && (args.flags & GMD_EPI_RESIDUAL_F32);
-    const bool mt2 = (bn == 160 || bn == 128) && !res_f32 && tiles_m >= 2 && args.num_kb >= 24 && ((tiles_m + 1) / 2) * tiles_n * gz >= 120;
+    const bool mt2 = (bn == 160 || bn == 128) && !res_f32 && tiles_m >= 2 && args.num_kb >= 16 && ((tiles_m + 1) / 2) * tiles_n * gz >= 120;
     args.tiles_mt = (int)(mt2 ? (tiles_m + 1) / 2 : tiles_m);
     args.tiles_n = (int)tiles_n;
     args.gz = (int)gz;
     if (args.ksplit < 1) { args.ksplit = 1; args.kb_per_split = args.num_kb; args.split_stride_o = 0; }
+    // pair neighbouring N tiles into 2-CTA clusters that share (multicast) the A operand
+    (void)sm_count();  // also reads GMD_NO_CLUSTER once
+    const bool cl2 = mt2 && (tiles_n % 2 == 0) && args.ksplit == 1 && (args.mode == 1 || args.kb_src0 == args.num_kb) && !g_disable_cluster;
     switch (bn) {
-        case 160: return mt2 ? launch<2, 160, 3, 2>(maps_a, map_w, args, st) : launch<1, 160, 3, 4>(maps_a, map_w, args, st);
-        case 128: return mt2 ? launch<2, 128, 3, 2>(maps_a, map_w, args, st) : launch<1, 128, 4, 4>(maps_a, map_w, args, st);
+        case 160: return mt2 ? (cl2 ? launch<2, 160, 3, 2, 2>(maps_a, map_w, args, st) : launch<2, 160, 3, 2>(maps_a, map_w, args, st))
+                             : launch<1, 160, 3, 4>(maps_a, map_w, args, st);
+        case 128: return mt2 ? (cl2 ? launch<2, 128, 3, 2, 2>(maps_a, map_w, args, st) : launch<2, 128, 3, 2>(maps_a, map_w, args, st))
+                             : launch<1, 128, 4, 4>(maps_a, map_w, args, st);
         case 64: return launch<1, 64, 6, 4>(maps_a, map_w, args, st);
         case 32: return launch<1, 32, 6, 4>(maps_a, map_w, args, st);
         default: set_last_error("gemm: unsupported N tile %d", bn); return kErrUnsupported;

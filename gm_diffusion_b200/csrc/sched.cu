@@ -122,6 +122,18 @@ __global__ void __launch_bounds__(256) sched_kernel(gmd_sched_params p) {
         // sample_coeff * sample - (a_prev - a_t) * model_output / denom
 #pragma unroll
         for (int k = 0; k < 4; ++k) xn.v[k] = SUB(MUL(p.c_sample, xs.v[k]), DIV(MUL(p.c_num, ep.v[k]), p.c_denom));
+    } else if (p.mode == GMD_SCHED_DDPM) {
+        // diffusers DDPMScheduler.step (epsilon, fixed_small): pred_x0; prev = c_x0 * pred_x0 + c_xt * x (+ sqrt(var) * noise if t > 0)
+        F4 z;
+        const bool noisy = p.noise && p.ddim_sigma != 0.0f;
+        if (noisy) z = ld(p.noise, i);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            float p0 = DIV(SUB(x.v[k], MUL(p.ddim_sqrt_1m_alpha_t, e.v[k])), p.ddim_sqrt_alpha_t);
+            float v = ADD(MUL(p.ddim_sqrt_alpha_prev, p0), MUL(p.ddim_dir_coeff, x.v[k]));
+            if (noisy) v = ADD(v, MUL(p.ddim_sigma, z.v[k]));
+            xn.v[k] = v;
+        }
     } else {
         // diffusers DDIMScheduler.step: pred_x0, direction, prev (+ sigma * noise)
         F4 z;
@@ -188,7 +200,7 @@ extern "C" int gmd_cfg_sched_step(const gmd_sched_params* p, void* stream) {
     if ((p->unet_in_next || p->concat_out) && (p->unet_in_ch < 8 || p->unet_in_ch % 8)) {
         set_last_error("gmd_cfg_sched_step: unet_in_ch must be a multiple of 8 (got %d)", p->unet_in_ch); return kErrInvalid;
     }
-    if (p->mode != GMD_SCHED_LINEAR && p->mode != GMD_SCHED_DDIM) { set_last_error("gmd_cfg_sched_step: bad mode %d", p->mode); return kErrInvalid; }
+    if (p->mode != GMD_SCHED_LINEAR && p->mode != GMD_SCHED_DDIM && p->mode != GMD_SCHED_DDPM) { set_last_error("gmd_cfg_sched_step: bad mode %d", p->mode); return kErrInvalid; }
     const void* ptrs[] = {p->eps_uncond, p->eps_cond, p->x, p->x_stash, p->hist[0], p->hist[1], p->hist[2], p->noise, p->x_next,
                           p->stash_out, p->eps_out, p->unet_in_next, p->concat_out, p->concat_tail, p->concat_lead, p->x0_out};
     for (const void* q : ptrs)

@@ -71,7 +71,7 @@ def as_b200_vae(vae, device) -> Optional[B200VaeDecoder]:
 
 def as_b200_scheduler(scheduler):
     """Accept our schedulers, or any object with a diffusers scheduler `config` whose class name we support."""
-    if isinstance(scheduler, (S.PNDMScheduler, S.DDIMScheduler)):
+    if isinstance(scheduler, (S.PNDMScheduler, S.DDIMScheduler, S.DDPMScheduler)):
         return scheduler
     name = type(scheduler).__name__
     cfg = getattr(scheduler, "config", None)
@@ -79,9 +79,11 @@ def as_b200_scheduler(scheduler):
         return S.PNDMScheduler.from_config(cfg)
     if cfg is not None and "DDIM" in name:
         return S.DDIMScheduler.from_config(cfg)
+    if cfg is not None and "DDPM" in name:
+        return S.DDPMScheduler.from_config(cfg)
     raise NotImplementedError(
-        f"scheduler {name} is not accelerated yet: the fused step kernel implements PNDM (PLMS) and DDIM "
-        "(north_star scope); DDPM / DPMSolver++ are the next rows of SURVEY.md §8f")
+        f"scheduler {name} is not accelerated yet: the fused step kernel implements PNDM (PLMS), DDIM "
+        "and DDPM; DPMSolver++ is the next row of SURVEY.md §8f")
 
 
 class PipelineBase:

@@ -163,6 +163,37 @@ class DDIMScheduler(_SchedulerBase):
         return plan
 
 
+class DDPMScheduler(_SchedulerBase):
+    """diffusers DDPMScheduler (epsilon prediction, fixed_small variance, leading spacing) — the scheduler every reference CLI
+    actually passes (scripts/inference/generate_hdr.py:162-176; formal_baseline.py:175-191).  Ancestral noise is drawn by the
+    pipeline from the caller's generator in the reference's order (SDR branch first, then GM branch, each step)."""
+
+    def set_timesteps(self, num_inference_steps: int, device=None):
+        self.num_inference_steps = int(num_inference_steps)
+        ratio = self.config.num_train_timesteps // self.num_inference_steps
+        ts = (np.arange(0, self.num_inference_steps) * ratio).round()[::-1].copy().astype(np.int64) + self.config.steps_offset
+        self.timesteps = torch.from_numpy(ts)
+
+    def plan_step(self, timestep: int, eta: float = 0.0) -> StepPlan:
+        t = int(timestep)
+        prev = t - self.config.num_train_timesteps // self.num_inference_steps
+        a_t = self.alphas_cumprod[t]
+        a_p = self.alphas_cumprod[prev] if prev >= 0 else torch.tensor(1.0)
+        b_t, b_p = 1 - a_t, 1 - a_p
+        cur_alpha = a_t / a_p
+        cur_beta = 1 - cur_alpha
+        c_x0 = (a_p ** 0.5 * cur_beta) / b_t
+        c_xt = cur_alpha ** 0.5 * b_p / b_t
+        sigma = 0.0
+        if t > 0:
+            variance = torch.clamp((1 - a_p) / (1 - a_t) * cur_beta, min=1e-20)
+            sigma = float(variance ** 0.5)
+        plan = StepPlan(mode=L.SCHED_DDPM, push_eps=False)
+        plan.ddim = (float(a_t ** 0.5), float(b_t ** 0.5), float(c_x0), float(c_xt), sigma)
+        plan.needs_noise = sigma != 0.0
+        return plan
+
+
 class BranchState:
     """Device state of one denoising branch (SDR or GM): fp32 pixel-major latents [B*h*w, 4], a 4-slot eps ring
     and the PLMS stash.  Allocated once; every step is in-place (CUDA-graph friendly)."""

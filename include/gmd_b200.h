@@ -86,7 +86,11 @@ float gmd_decode_ordered(int32_t v);
 /*     and stable_diffusion_gm.py:1045-1048,1062-1071 plus diffusers PNDMScheduler.step_plms / */
 /*     DDIMScheduler.step (called at :1077/:1093).                                             */
 /* ------------------------------------------------------------------------------------------ */
-enum gmd_sched_mode { GMD_SCHED_LINEAR = 0 /* PLMS: x' = c_sample*x_src - c_num*eps'/c_denom */, GMD_SCHED_DDIM = 1 };
+enum gmd_sched_mode {
+    GMD_SCHED_LINEAR = 0, /* PLMS: x' = c_sample*x_src - c_num*eps'/c_denom */
+    GMD_SCHED_DDIM = 1,   /* x' = sqrt(a_prev)*x0 + dir_coeff*eps (+ sigma*noise) */
+    GMD_SCHED_DDPM = 2    /* ancestral: x' = c_x0*x0 + c_xt*x (+ sigma*noise); the scheduler every reference CLI passes (generate_hdr.py:162-176) */
+};
 /* PLMS multistep combination eps' (diffusers PNDMScheduler.step_plms):
  *   0: eps   1: (eps + h0)/2   2: (3 eps - h0)/2   3: (23 eps - 16 h0 + 5 h1)/12   4: (55 eps - 59 h0 + 37 h1 - 9 h2)/24 */
 
@@ -125,7 +129,8 @@ typedef struct gmd_sched_params {
     float c_sample;          /* LINEAR mode: (a_prev/a_t)^0.5 */
     float c_num;             /*              a_prev - a_t */
     float c_denom;           /*              a_t*(1-a_prev)^0.5 + (a_t*(1-a_t)*a_prev)^0.5 */
-    float ddim_sqrt_alpha_t, ddim_sqrt_1m_alpha_t, ddim_sqrt_alpha_prev, ddim_dir_coeff, ddim_sigma; /* DDIM mode */
+    float ddim_sqrt_alpha_t, ddim_sqrt_1m_alpha_t, ddim_sqrt_alpha_prev, ddim_dir_coeff, ddim_sigma; /* DDIM mode; DDPM mode reuses
+        them as sqrt(a_t), sqrt(1-a_t), c_x0, c_xt, sigma */
 } gmd_sched_params;
 
 int gmd_cfg_sched_step(const gmd_sched_params* p, void* stream);

@@ -127,7 +127,7 @@ class DDIMOracle(_Base):
         prev = a_p ** 0.5 * pred_x0 + direction
         if eta > 0:
             if variance_noise is None:
-                variance_noise = torch.randn(model_output.shape, generator=generator, dtype=model_output.dtype)
+                variance_noise = _randn_like(model_output, generator)
             prev = prev + std * variance_noise
         return (prev,)
 
@@ -156,10 +156,16 @@ class DDPMOracle(_Base):
         prev = c_x0 * pred_x0 + c_xt * sample
         if t > 0:
             if variance_noise is None:
-                variance_noise = torch.randn(model_output.shape, generator=generator, dtype=model_output.dtype)
+                variance_noise = _randn_like(model_output, generator)
             variance = torch.clamp((1 - a_p) / (1 - a_t) * cur_beta, min=1e-20)
             prev = prev + variance ** 0.5 * variance_noise
         return (prev,)
+
+
+def _randn_like(ref: torch.Tensor, generator):
+    """diffusers.utils.torch_utils.randn_tensor: a CPU generator draws on the CPU, then the sample moves to the tensor's device."""
+    dev = generator.device if generator is not None else ref.device
+    return torch.randn(ref.shape, generator=generator, device=dev, dtype=ref.dtype).to(ref.device)
 
 
 def rescale_noise_cfg(noise_cfg, noise_pred_text, guidance_rescale=0.0):

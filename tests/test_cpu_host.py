@@ -114,6 +114,23 @@ def test_ddim_plan_matches_oracle():
             torch.testing.assert_close(mine, want, rtol=1e-5, atol=1e-6)
 
 
+def test_ddpm_plan_matches_oracle():
+    from gm_diffusion_b200.schedulers import DDPMScheduler
+    from oracle.schedulers_oracle import DDPMOracle
+    p, o = DDPMScheduler(), DDPMOracle()
+    p.set_timesteps(10); o.set_timesteps(10)
+    assert torch.equal(p.timesteps, o.timesteps)
+    g = torch.Generator().manual_seed(0)
+    x, e, z = (torch.randn(8, generator=g) for _ in range(3))
+    for t in p.timesteps.tolist():
+        plan = p.plan_step(t)
+        sa, sb, c0, c1, sg = plan.ddim
+        mine = c0 * ((x - sb * e) / sa) + c1 * x + sg * z
+        want = o.step(e, t, x, variance_noise=z)[0]
+        torch.testing.assert_close(mine, want, rtol=1e-5, atol=1e-6)
+        assert plan.needs_noise == (t > 0)
+
+
 def test_check_inputs_mirrors_reference_errors():
     from gm_diffusion_b200.pipelines._common import PipelineBase, retrieve_timesteps
     from gm_diffusion_b200.schedulers import PNDMScheduler

@@ -131,6 +131,23 @@ def test_dual_batch_sharding_independence(dual_pipe):
         assert torch.equal(s2[b:b + 1], s1) and torch.equal(g2[b:b + 1], g1), (rel_l2(s2[b:b + 1], s1), rel_l2(g2[b:b + 1], g1))
 
 
+def test_ddpm_dual_pipeline_reference_cli_scheduler(models, dual_pipe):
+    """DDPM is what scripts/inference/generate_hdr.py:162-176 passes: ancestral noise from the shared generator, SDR draw then GM."""
+    from gm_diffusion_b200 import DDPMScheduler, StableDiffusionDualUNetPipeline
+    from oracle import pipeline_oracle as PO
+    from oracle.schedulers_oracle import DDPMOracle
+    u4, u8, _ = models
+    pe, ne, lat, _ = _inputs()
+    want_sdr, want_gm = PO.dual_unet_loop(u4, u8, DDPMOracle(), pe, ne, lat.clone(), num_inference_steps=4, guidance_scale=7.5,
+                                          generator=torch.Generator().manual_seed(123))
+    pipe = StableDiffusionDualUNetPipeline(vae=None, text_encoder=None, tokenizer=None, unet=dual_pipe.unet, gm_unet=dual_pipe.gm_unet,
+                                           scheduler=DDPMScheduler())
+    got_sdr, got_gm = pipe(prompt_embeds=pe, negative_prompt_embeds=ne, latents=lat.clone(), height=256, width=256, num_inference_steps=4,
+                           guidance_scale=7.5, output_type="latent", generator=torch.Generator().manual_seed(123))
+    r1, r2 = rel_l2(got_sdr, want_sdr), rel_l2(got_gm, want_gm)
+    assert r1 < 3e-2 and r2 < 3e-2, f"DDPM final latents rel-L2 sdr {r1:.3e} gm {r2:.3e}"
+
+
 def test_ddim_and_errors(models, dual_pipe):
     from gm_diffusion_b200 import DDIMScheduler, StableDiffusionDualUNetImprovedPipeline
     from oracle import pipeline_oracle as PO

@@ -44,15 +44,16 @@ def _run_dual(sched_cls, oracle_cls, steps, B=2, h=8, w=8, g=7.5, phi=0.0, eta=0
             e = O.rescale_noise_cfg(e, ec, phi)
         a = so.alphas_cumprod[t]
         x0 = (x_o - (1 - a).sqrt() * e) / a.sqrt()
-        kw = dict(eta=eta, variance_noise=nz[0]) if eta > 0 else {}
+        ancestral = oracle_cls.__name__ == "DDPMOracle"
+        kw = dict(eta=eta, variance_noise=nz[0]) if eta > 0 else (dict(variance_noise=nz[0]) if ancestral else {})
         x_o_next = so.step(e, t, x_o, **kw)[0]
         gm_in_o = torch.cat([x0, gm_o], 1)
-        kw = dict(eta=eta, variance_noise=nz[1]) if eta > 0 else {}
+        kw = dict(eta=eta, variance_noise=nz[1]) if eta > 0 else (dict(variance_noise=nz[1]) if ancestral else {})
         gm_o = go.step(eg, t, gm_o, **kw)[0]
         x_o = x_o_next
         # product
         plan = sp.plan_step(t, eta)
-        if plan.needs_noise:
+        if plan.needs_noise or ancestral:
             sdr.noise = px(nz[0]).cuda(); gm.noise = px(nz[1]).cuda()
         S.fused_step(plan, sdr, px(ec).cuda(), px(eu).cuda(), guidance_scale=g, guidance_rescale=phi, px_per_sample=h * w,
                      x0_coeffs=sp.x0_coeffs(t), unet_in_next=unet_in, concat_out=gm_in, concat_tail=gm.x, rescale_ws=ws)
@@ -85,6 +86,14 @@ def test_ddim_dual(eta):
     from gm_diffusion_b200.schedulers import DDIMScheduler
     from oracle.schedulers_oracle import DDIMOracle
     _run_dual(DDIMScheduler, DDIMOracle, 10, eta=eta)
+
+
+@pytest.mark.parametrize("steps", [5, 50])
+def test_ddpm_dual(steps):
+    """The scheduler the reference CLIs really pass (generate_hdr.py:162-176): ancestral noise, SDR draw then GM draw."""
+    from gm_diffusion_b200.schedulers import DDPMScheduler
+    from oracle.schedulers_oracle import DDPMOracle
+    _run_dual(DDPMScheduler, DDPMOracle, steps)
 
 
 def test_latent_layout_roundtrip_and_pack():
