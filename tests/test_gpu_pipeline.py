@@ -148,6 +148,23 @@ def test_ddpm_dual_pipeline_reference_cli_scheduler(models, dual_pipe):
     assert r1 < 3e-2 and r2 < 3e-2, f"DDPM final latents rel-L2 sdr {r1:.3e} gm {r2:.3e}"
 
 
+def test_full_config_512_50_steps_hdr_psnr(models, dual_pipe):
+    """BASELINE.json configs[1] geometry at batch 1: 512x512, 50 PNDM steps (51 evals), CFG 7.5 -> VAE -> Eq.(1) qmax 99; final HDR
+    vs the fp32 oracle pipeline, gate >= 40 dB in the log domain (north_star)."""
+    from oracle import pipeline_oracle as PO
+    from oracle.schedulers_oracle import PNDMOracle
+    u4, u8, vae = models
+    pe, ne, lat, _ = _inputs(B=1, hw=64)
+    want_sdr, want_gm = PO.dual_unet_loop(u4, u8, PNDMOracle(), pe, ne, lat.clone(), num_inference_steps=50, guidance_scale=7.5)
+    _, _, hdr_want = PO.decode_and_reconstruct(vae, want_sdr, want_gm, qmax=99.0)
+    dual_pipe.use_cuda_graph = True
+    hdr_got, _, _ = dual_pipe(prompt_embeds=pe, negative_prompt_embeds=ne, latents=lat.clone(), height=512, width=512,
+                              num_inference_steps=50, guidance_scale=7.5, output_type="hdr")
+    p = psnr_log(hdr_got.permute(0, 3, 1, 2), hdr_want)
+    print(f"512x512 / 50-step HDR log-domain PSNR vs fp32 oracle: {p:.1f} dB")
+    assert p >= 40.0, f"HDR log-domain PSNR {p:.1f} dB < 40 dB"
+
+
 def test_ddim_and_errors(models, dual_pipe):
     from gm_diffusion_b200 import DDIMScheduler, StableDiffusionDualUNetImprovedPipeline
     from oracle import pipeline_oracle as PO
