@@ -51,6 +51,7 @@ struct KernelArgs {
     int ksplit, kb_per_split;
     int64_t split_stride_o;   // elements between the partial-sum planes
     int w_tiled;              // weights pre-tiled as [N tile][k block][BN][64]: every B tile is one contiguous 128*BN-byte read
+    const uint8_t* w_bulk;    // non-null: tiles are also PRE-SWIZZLED (smem image) -> one 1-D bulk copy per B tile instead of BN tensor rows
 };
 
 // exact-erf GELU with erf from Abramowitz-Stegun 7.1.26 (|abs err| <= 1.5e-7, two MUFU ops): erff() costs ~60
@@ -219,7 +220,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__ 
                                 else tma_load_3d(sa + s * P::A_SUB, &map_a1, &full_bar[stage], (kb - args.kb_src0) * BK, m0[s], zb);
                             }
                         }
-                        if (args.w_tiled) tma_load_3d(sb, &map_w, &full_bar[stage], 0, ((n0 / BN) * args.num_kb + kb) * BN, 0);
+                        if (args.w_bulk) bulk_copy_g2s(sb, args.w_bulk + (size_t)((n0 / BN) * args.num_kb + kb) * P::B_BYTES, P::B_BYTES, &full_bar[stage]);
+                        else if (args.w_tiled) tma_load_3d(sb, &map_w, &full_bar[stage], 0, ((n0 / BN) * args.num_kb + kb) * BN, 0);
                         else tma_load_3d(sb, &map_w, &full_bar[stage], kb * BK, n0, zb);
                     } else {
                         const int tap = kb / chunks_per_tap;
@@ -253,7 +255,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__ 
                             for (int s = 0; s < MT; ++s)
                                 tma_load_4d(sa + s * P::A_SUB, map, &full_bar[stage], c, tw0[s] + dw, th0[s] + dh, tn0[s]);
                         }
-                        if (args.w_tiled) tma_load_3d(sb, &map_w, &full_bar[stage], 0, ((n0 / BN) * args.num_kb + kb) * BN, 0);
+                        if (args.w_bulk) bulk_copy_g2s(sb, args.w_bulk + (size_t)((n0 / BN) * args.num_kb + kb) * P::B_BYTES, P::B_BYTES, &full_bar[stage]);
+                        else if (args.w_tiled) tma_load_3d(sb, &map_w, &full_bar[stage], 0, ((n0 / BN) * args.num_kb + kb) * BN, 0);
                         else tma_load_3d(sb, &map_w, &full_bar[stage], tap * args.ctot + cc * BK, n0, 0);
                     }
                 }
@@ -716,8 +719,9 @@ extern "C" int gmd_gemm_fwd(const gmd_gemm_params* p, void* stream) {
         if (rc) return rc;
         maps_a[1] = maps_a[2] = maps_a[3] = maps_a[0];
     }
+    const int w_tile = p->w_tiled >= 1000 ? p->w_tiled - 1000 : p->w_tiled;
     if (p->w_tiled) {
-        if (p->w_tiled != bn || batch != 1) { set_last_error("gmd_gemm_fwd: tiled weights were packed for N tile %d, kernel picks %d (batch %lld)", p->w_tiled, bn, (long long)batch); return kErrInvalid; }
+        if (w_tile != bn || batch != 1) { set_last_error("gmd_gemm_fwd: tiled weights were packed for N tile %d, kernel picks %d (batch %lld)", p->w_tiled, bn, (long long)batch); return kErrInvalid; }
         const uint64_t total_rows = (uint64_t)((p->N + bn - 1) / bn) * ((p->K + BK - 1) / BK) * bn;
         uint64_t dims[3] = {BK, total_rows, 1};
         uint64_t strides[3] = {2, BK * 2, total_rows * BK * 2};
@@ -734,6 +738,7 @@ extern "C" int gmd_gemm_fwd(const gmd_gemm_params* p, void* stream) {
     KernelArgs a{};
     a.mode = 0;
     a.w_tiled = p->w_tiled ? 1 : 0;
+    a.w_bulk = p->w_tiled >= 1000 ? static_cast<const uint8_t*>(p->w) : nullptr;
     a.num_kb = (int)((p->K + BK - 1) / BK);
     a.kb_src0 = a.num_kb;
     a.M = p->M;
@@ -845,7 +850,7 @@ extern "C" int gmd_conv_fwd(const gmd_conv_params* p, void* stream) {
     }
     if (p->w_tiled) {
         // [N tile][k block = tap * chunks + chunk][bnt rows][64]: channels of every tap zero-padded to whole 64-blocks at pack time
-        if (p->w_tiled != bnt) { set_last_error("gmd_conv_fwd: tiled weights were packed for N tile %d, kernel picks %d", p->w_tiled, bnt); return kErrInvalid; }
+        if ((p->w_tiled >= 1000 ? p->w_tiled - 1000 : p->w_tiled) != bnt) { set_last_error("gmd_conv_fwd: tiled weights were packed for N tile %d, kernel picks %d", p->w_tiled, bnt); return kErrInvalid; }
         const uint64_t total_rows = (uint64_t)((p->Cout + bnt - 1) / bnt) * a.num_kb * bnt;
         uint64_t dims[3] = {BK, total_rows, 1};
         uint64_t strides[3] = {2, BK * 2, total_rows * BK * 2};
@@ -853,6 +858,7 @@ extern "C" int gmd_conv_fwd(const gmd_conv_params* p, void* stream) {
         int rc = encode_tensor_map_bf16(&map_w, p->w, 3, dims, strides, boxw, true);
         if (rc) return rc;
         a.w_tiled = 1;
+        a.w_bulk = p->w_tiled >= 1000 ? static_cast<const uint8_t*>(p->w) : nullptr;
     } else {
         uint64_t dims[3] = {(uint64_t)taps * ctot, (uint64_t)rows_w, 1};
         uint64_t strides[3] = {2, (uint64_t)taps * ctot * 2, (uint64_t)taps * ctot * rows_w * 2};

@@ -33,26 +33,37 @@ class TiledWeight:
     TMA fetches is ONE contiguous 128*T-byte read.  With the plain `[N, K]` layout a tile is T separate 128-byte rows, each in
     a different DRAM page: weight-streaming-bound layers (8x8 / 16x16 resolution) ran at ~0.4 TB/s."""
 
-    def __init__(self, data: torch.Tensor, n: int, k: int, bn: int):
-        self.data, self.n, self.k, self.bn = data, n, k, bn
+    def __init__(self, data: torch.Tensor, n: int, k: int, bn: int, swizzled: bool = False):
+        self.data, self.n, self.k, self.bn, self.swizzled = data, n, k, bn, swizzled
+
+    @property
+    def code(self) -> int:
+        """value of the C-ABI `w_tiled` field"""
+        return self.bn + (1000 if self.swizzled else 0)
 
     @property
     def shape(self):
         return (self.n, self.k)
 
     def to(self, device):
-        return TiledWeight(self.data.to(device), self.n, self.k, self.bn)
+        return TiledWeight(self.data.to(device), self.n, self.k, self.bn, self.swizzled)
 
 
-def tile_weight(w: torch.Tensor, geglu: bool = False) -> TiledWeight:
-    """[N, K] (any float dtype) -> TiledWeight."""
+def tile_weight(w: torch.Tensor, geglu: bool = False, swizzle: bool = True) -> TiledWeight:
+    """[N, K] (any float dtype) -> TiledWeight.  `swizzle`: store each [T][64] tile as its SWIZZLE_128B shared-memory image so
+    the kernel fetches it with one bulk copy."""
     n, k = w.shape
     bn = pick_bn(n, geglu)
     tn, tk = (n + bn - 1) // bn, (k + 63) // 64
     wp = torch.zeros((tn * bn, tk * 64), dtype=bf16, device=w.device)
     wp[:n, :k] = w.to(bf16)
     data = wp.view(tn, bn, tk, 64).permute(0, 2, 1, 3).contiguous().view(tn * tk * bn, 64)
-    return TiledWeight(data, n, k, bn)
+    if swizzle:
+        # 16-byte chunk c (8 bf16) of tile row r moves to chunk c ^ (r & 7); bn is a multiple of 8, so r & 7 == global row & 7
+        rows = torch.arange(data.shape[0], device=data.device) & 7
+        src_chunk = torch.arange(8, device=data.device)[None, :] ^ rows[:, None]          # dst chunk j holds src chunk j ^ (r & 7)
+        data = data.view(-1, 8, 8).gather(1, src_chunk[:, :, None].expand(-1, -1, 8)).reshape(-1, 64).contiguous()
+    return TiledWeight(data, n, k, bn, swizzle)
 
 
 
@@ -93,7 +104,7 @@ def gemm(a: torch.Tensor, w: torch.Tensor, *, bias: Optional[torch.Tensor] = Non
     p = L.GemmParams()
     p.a, p.lda = a.data_ptr(), a.stride(-2)
     p.w, p.ldw = wt.data_ptr(), (K if tiled else w.stride(-2))
-    p.w_tiled = w.bn if tiled else 0
+    p.w_tiled = w.code if tiled else 0
     p.out, p.ldo = out.data_ptr(), out.stride(-2)
     p.M, p.N, p.K, p.batch = M, N, K, Bt
     if batched:
@@ -153,7 +164,7 @@ def conv2d(x: torch.Tensor, w: torch.Tensor, cout: int, *, ksize: int = 3, strid
     p.x0, p.C0 = x.data_ptr(), C0
     p.x1, p.C1 = (x1.data_ptr(), C1) if x1 is not None else (None, 0)
     p.w, p.out = wt.data_ptr(), out.data_ptr()
-    p.w_tiled = w.bn if tiled else 0
+    p.w_tiled = w.code if tiled else 0
     p.N, p.H, p.W, p.Cout, p.Cout_pad = N, H, W, cout, w.shape[0]
     p.ksize, p.stride, p.upsample = ksize, stride, int(upsample)
     flags = 0

@@ -173,7 +173,9 @@ typedef struct gmd_gemm_params {
     int64_t workspace_bytes;
     int32_t w_tiled;                     /* 0: w is [N, K] row-major.  T > 0: w is pre-tiled [ceil(N/T)][ceil(K/64)][T][64] (zero padded), T = the
                                           * N tile the kernel uses for this N (160 if N%160==0, else 128 if N%128==0 or N>128, else 64 / 32):
-                                          * every operand tile is then one contiguous DRAM read instead of T strided 128-byte rows */
+                                          * every operand tile is then one contiguous DRAM read instead of T strided 128-byte rows.
+                                          * 1000 + T: the tiles are additionally stored as the SWIZZLE_128B shared-memory image (16-byte chunk c of
+                                          * row r at chunk c ^ (r & 7)) and fetched with ONE 1-D bulk copy per tile instead of T tensor rows */
 } gmd_gemm_params;
 
 int gmd_gemm_fwd(const gmd_gemm_params* p, void* stream);

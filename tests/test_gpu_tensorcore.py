@@ -35,7 +35,8 @@ def test_gemm_plain(M, N, K):
     a = torch.randn(M, K, generator=g).to(bf).cuda()
     w = (torch.randn(N, K, generator=g) / math.sqrt(K)).to(bf).cuda()
     check(ops.gemm(a, w), a.float() @ w.float().t(), what=f"gemm {M}x{N}x{K}")
-    check(ops.gemm(a, ops.tile_weight(w)), a.float() @ w.float().t(), what=f"gemm tiled-W {M}x{N}x{K}")
+    check(ops.gemm(a, ops.tile_weight(w)), a.float() @ w.float().t(), what=f"gemm tiled+swizzled-W {M}x{N}x{K}")
+    assert torch.equal(ops.gemm(a, ops.tile_weight(w, swizzle=False)), ops.gemm(a, ops.tile_weight(w))), "tiled vs tiled+pre-swizzled weights"
 
 
 def test_gemm_epilogues():
