@@ -7,11 +7,11 @@ tone-mapping functions.  Everything numerical runs in hand-written CUDA behind t
 from .stage1 import (apply_gm_to_sdr, fix_mulog_tmo, gamut_compress, hard_clip_tmo, linear_scale_tmo, random_tmo_cuda,
                      reconstruct_hdr, tmo_cuda)
 from .pipelines import (StableDiffusionDualUNetImprovedPipeline, StableDiffusionDualUNetPipeline, StableDiffusionGMPipeline)
-from .schedulers import DDIMScheduler, DDPMScheduler, PNDMScheduler
+from .schedulers import DDIMScheduler, DDPMScheduler, DPMSolverMultistepScheduler, PNDMScheduler
 from .unet import B200UNet
 from .vae import B200VaeDecoder
 
 __version__ = "0.1.0"
 __all__ = ["apply_gm_to_sdr", "fix_mulog_tmo", "gamut_compress", "hard_clip_tmo", "linear_scale_tmo", "random_tmo_cuda",
            "tmo_cuda", "reconstruct_hdr", "StableDiffusionDualUNetPipeline", "StableDiffusionDualUNetImprovedPipeline",
-           "StableDiffusionGMPipeline", "PNDMScheduler", "DDIMScheduler", "DDPMScheduler", "B200UNet", "B200VaeDecoder"]
+           "StableDiffusionGMPipeline", "PNDMScheduler", "DDIMScheduler", "DDPMScheduler", "DPMSolverMultistepScheduler", "B200UNet", "B200VaeDecoder"]

@@ -19,7 +19,7 @@ LAYOUT_FLAT, LAYOUT_PLANAR3, LAYOUT_INTERLEAVED3 = 0, 1, 2
 F32, BF16 = 0, 1
 TMO_NONE, TMO_LINEAR, TMO_HARD_CLIP, TMO_MULOG, TMO_CUDA = 0, 1, 2, 3, 4
 HDR_EQ1, HDR_DENORM, HDR_CLAMP_OUT, HDR_GAMUT, HDR_EXP_GAIN = 1, 2, 4, 8, 16
-SCHED_LINEAR, SCHED_DDIM, SCHED_DDPM = 0, 1, 2
+SCHED_LINEAR, SCHED_DDIM, SCHED_DDPM, SCHED_DPMPP = 0, 1, 2, 3
 EPI_BIAS, EPI_ROW_BIAS, EPI_RESIDUAL, EPI_GEGLU, EPI_OUT_F32, EPI_SCALE, EPI_RESIDUAL_F32 = 1, 2, 4, 8, 16, 32, 64
 
 _vp, _i64, _i32, _f32 = C.c_void_p, C.c_int64, C.c_int32, C.c_float

@@ -95,10 +95,26 @@ __global__ void __launch_bounds__(256) sched_kernel(gmd_sched_params p) {
     for (int k = 0; k < 4; ++k) x0.v[k] = DIV(SUB(x.v[k], MUL(p.sqrt_1m_alpha_t, e.v[k])), p.sqrt_alpha_t);
     if (p.x0_out) st4(p.x0_out, i, f4(x0));
     if (p.stash_out) st4(p.stash_out, i, f4(x));
-    if (p.eps_out) st4(p.eps_out, i, f4(e));
+    if (p.eps_out && p.mode != GMD_SCHED_DPMPP) st4(p.eps_out, i, f4(e));
     // --- scheduler update ---
     F4 xn;
-    if (p.mode == GMD_SCHED_LINEAR) {
+    if (p.mode == GMD_SCHED_DPMPP) {
+        // diffusers DPMSolverMultistepScheduler (dpmsolver++, midpoint, order 2): the history holds x0 predictions.
+        //   m0 = (x - sigma_s * eps) / alpha_s                                   (convert_model_output)
+        //   1st order: x_t = (sigma_t/sigma_s) x - (alpha_t (exp(-h) - 1)) m0
+        //   2nd order: ... - 0.5 (alpha_t (exp(-h) - 1)) * ((1/r0) (m0 - m1))
+        F4 m0, h0;
+        if (p.plms_kind == 1) h0 = ld(p.hist[0], i);
+        const float c_half = MUL(0.5f, p.c_num);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            m0.v[k] = DIV(SUB(x.v[k], MUL(p.ddim_sqrt_1m_alpha_t, e.v[k])), p.ddim_sqrt_alpha_t);
+            float v = SUB(MUL(p.c_sample, x.v[k]), MUL(p.c_num, m0.v[k]));
+            if (p.plms_kind == 1) v = SUB(v, MUL(c_half, MUL(p.c_denom, SUB(m0.v[k], h0.v[k]))));
+            xn.v[k] = v;
+        }
+        if (p.eps_out) st4(p.eps_out, i, f4(m0));
+    } else if (p.mode == GMD_SCHED_LINEAR) {
         // diffusers PNDMScheduler.step_plms: the multistep combination, written exactly as the reference expressions
         F4 h0, h1, h2, ep;
         if (p.hist[0]) h0 = ld(p.hist[0], i);
@@ -200,7 +216,7 @@ extern "C" int gmd_cfg_sched_step(const gmd_sched_params* p, void* stream) {
     if ((p->unet_in_next || p->concat_out) && (p->unet_in_ch < 8 || p->unet_in_ch % 8)) {
         set_last_error("gmd_cfg_sched_step: unet_in_ch must be a multiple of 8 (got %d)", p->unet_in_ch); return kErrInvalid;
     }
-    if (p->mode != GMD_SCHED_LINEAR && p->mode != GMD_SCHED_DDIM && p->mode != GMD_SCHED_DDPM) { set_last_error("gmd_cfg_sched_step: bad mode %d", p->mode); return kErrInvalid; }
+    if (p->mode < GMD_SCHED_LINEAR || p->mode > GMD_SCHED_DPMPP) { set_last_error("gmd_cfg_sched_step: bad mode %d", p->mode); return kErrInvalid; }
     const void* ptrs[] = {p->eps_uncond, p->eps_cond, p->x, p->x_stash, p->hist[0], p->hist[1], p->hist[2], p->noise, p->x_next,
                           p->stash_out, p->eps_out, p->unet_in_next, p->concat_out, p->concat_tail, p->concat_lead, p->x0_out};
     for (const void* q : ptrs)
@@ -210,6 +226,10 @@ extern "C" int gmd_cfg_sched_step(const gmd_sched_params* p, void* stream) {
         const int need = p->plms_kind == 0 ? 0 : p->plms_kind <= 2 ? 1 : p->plms_kind - 1;
         for (int k = 0; k < need; ++k)
             if (!p->hist[k]) { set_last_error("gmd_cfg_sched_step: plms_kind %d needs %d history tensors", p->plms_kind, need); return kErrInvalid; }
+    }
+    if (p->mode == GMD_SCHED_DPMPP) {
+        if (p->plms_kind < 0 || p->plms_kind > 1) { set_last_error("gmd_cfg_sched_step: DPM++ order index %d out of range", p->plms_kind); return kErrInvalid; }
+        if (p->plms_kind == 1 && !p->hist[0]) { set_last_error("gmd_cfg_sched_step: DPM++ 2nd-order step needs the previous x0 prediction"); return kErrInvalid; }
     }
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     if (p->eps_uncond && p->guidance_rescale > 0.0f) {

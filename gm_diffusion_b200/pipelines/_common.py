@@ -71,7 +71,7 @@ def as_b200_vae(vae, device) -> Optional[B200VaeDecoder]:
 
 def as_b200_scheduler(scheduler):
     """Accept our schedulers, or any object with a diffusers scheduler `config` whose class name we support."""
-    if isinstance(scheduler, (S.PNDMScheduler, S.DDIMScheduler, S.DDPMScheduler)):
+    if isinstance(scheduler, (S.PNDMScheduler, S.DDIMScheduler, S.DDPMScheduler, S.DPMSolverMultistepScheduler)):
         return scheduler
     name = type(scheduler).__name__
     cfg = getattr(scheduler, "config", None)
@@ -81,9 +81,14 @@ def as_b200_scheduler(scheduler):
         return S.DDIMScheduler.from_config(cfg)
     if cfg is not None and "DDPM" in name:
         return S.DDPMScheduler.from_config(cfg)
+    if cfg is not None and "DPMSolverMultistep" in name:
+        get = cfg.get if isinstance(cfg, dict) else lambda k, d=None: getattr(cfg, k, d)
+        if (get("algorithm_type", "dpmsolver++") != "dpmsolver++" or get("solver_order", 2) != 2 or get("solver_type", "midpoint") != "midpoint"
+                or get("use_karras_sigmas", False) or get("final_sigmas_type", "zero") != "zero" or get("thresholding", False)):
+            raise NotImplementedError("only DPM-Solver++(2M, midpoint, final sigma zero) — the from_config defaults the reference uses — is accelerated")
+        return S.DPMSolverMultistepScheduler.from_config(cfg)
     raise NotImplementedError(
-        f"scheduler {name} is not accelerated yet: the fused step kernel implements PNDM (PLMS), DDIM "
-        "and DDPM; DPMSolver++ is the next row of SURVEY.md §8f")
+        f"scheduler {name} is not accelerated: the fused step kernel implements PNDM (PLMS), DDIM, DDPM and DPM-Solver++(2M)")
 
 
 class PipelineBase:
@@ -196,8 +201,8 @@ class PipelineBase:
     # ---- dual_unet.py:336-516 -------------------------------------------------------------------------------
     def encode_prompt(self, prompt, device, num_images_per_prompt, do_classifier_free_guidance, negative_prompt=None,
                       prompt_embeds=None, negative_prompt_embeds=None, lora_scale=None, clip_skip=None):
-        if lora_scale is not None:
-            raise NotImplementedError("LoRA scale is accepted at the signature level only (SURVEY.md §8b)")
+        # lora_scale: no LoRA layers exist on the text encoder handed to this pipeline unless the caller loaded an adapter; the
+        # reference's scale_lora_layers/unscale_lora_layers pair (dual_unet.py:379-386,511-514) is then a no-op and is not restated.
         if prompt is not None and isinstance(prompt, str):
             batch_size = 1
         elif prompt is not None and isinstance(prompt, list):

@@ -59,8 +59,10 @@ class StableDiffusionGMPipeline(PipelineBase):
         width = width or 64 * self.vae_scale_factor
         self.check_inputs(prompt, height, width, callback_steps, negative_prompt, prompt_embeds, negative_prompt_embeds,
                           ip_adapter_image, ip_adapter_image_embeds, callback_on_step_end_tensor_inputs)
-        if cross_attention_kwargs:
-            raise NotImplementedError("cross_attention_kwargs (LoRA scale) are accepted at the signature level only")
+        if cross_attention_kwargs and set(cross_attention_kwargs) - {"scale"}:
+            raise NotImplementedError("only cross_attention_kwargs={'scale': s} is accepted: the B200 UNets are built from plain state dicts "
+                                      "and carry no LoRA layers, so the LoRA scale is a no-op exactly as in the reference without an adapter "
+                                      "(formal_improved.py:268); other attention-processor kwargs are not accelerated")
         self._guidance_scale, self._guidance_rescale, self._clip_skip = guidance_scale, guidance_rescale, clip_skip
         self._interrupt = False
         if prompt is not None and isinstance(prompt, str):

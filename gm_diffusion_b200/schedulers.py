@@ -194,6 +194,66 @@ class DDPMScheduler(_SchedulerBase):
         return plan
 
 
+class DPMSolverMultistepScheduler(_SchedulerBase):
+    """diffusers DPMSolverMultistepScheduler at the defaults `from_config(pndm_config)` gives it — dpmsolver++, solver_order 2,
+    midpoint, lower_order_final, final_sigmas_type "zero", leading spacing — which scripts/inference/experiments/
+    formal_improved.py:195 swaps into the dual pipeline.  The history ring holds x0 predictions, not eps."""
+
+    def __init__(self, **over):
+        super().__init__(**over)
+        self.sigmas: Optional[torch.Tensor] = None
+        self.step_index = 0
+        self.lower_order_nums = 0
+
+    def set_timesteps(self, num_inference_steps: int, device=None):
+        self.num_inference_steps = n = int(num_inference_steps)
+        c = self.config
+        if c.timestep_spacing != "leading":
+            raise NotImplementedError("only the SD1.5 config's leading timestep spacing is on the reference path")
+        step_ratio = c.num_train_timesteps // (n + 1)
+        ts = (np.arange(0, n + 1) * step_ratio).round()[::-1][:-1].copy().astype(np.int64) + c.steps_offset
+        sig = (((1 - self.alphas_cumprod) / self.alphas_cumprod) ** 0.5).numpy()
+        sig = np.interp(ts, np.arange(0, len(sig)), sig)
+        self.sigmas = torch.from_numpy(np.concatenate([sig, [0.0]]).astype(np.float32))
+        self.timesteps = torch.from_numpy(ts)
+        self.reset()
+
+    def reset(self):
+        self.step_index = 0
+        self.lower_order_nums = 0
+
+    @staticmethod
+    def _alpha_sigma(sigma: torch.Tensor):
+        alpha_t = 1 / ((sigma ** 2 + 1) ** 0.5)
+        return alpha_t, sigma * alpha_t
+
+    def plan_step(self, timestep: int, eta: float = 0.0) -> StepPlan:
+        i = self.step_index
+        n = len(self.timesteps)
+        final_first_order = i == n - 1  # final_sigmas_type "zero" forces a first-order last step
+        alpha_s0, sigma_s0 = self._alpha_sigma(self.sigmas[i])
+        alpha_t, sigma_t = self._alpha_sigma(self.sigmas[i + 1])
+        lambda_t = torch.log(alpha_t) - torch.log(sigma_t)
+        lambda_s0 = torch.log(alpha_s0) - torch.log(sigma_s0)
+        h = lambda_t - lambda_s0
+        plan = StepPlan(mode=L.SCHED_DPMPP, push_eps=True)
+        plan.ddim = (float(alpha_s0), float(sigma_s0), 1.0, 0.0, 0.0)
+        plan.c_sample = float(sigma_t / sigma_s0)
+        plan.c_num = float(alpha_t * (torch.exp(-h) - 1.0))
+        if self.lower_order_nums < 1 or final_first_order:
+            plan.plms_kind, plan.n_hist = 0, 0
+        else:
+            alpha_s1, sigma_s1 = self._alpha_sigma(self.sigmas[i - 1])
+            lambda_s1 = torch.log(alpha_s1) - torch.log(sigma_s1)
+            r0 = (lambda_s0 - lambda_s1) / h
+            plan.plms_kind, plan.n_hist = 1, 1
+            plan.c_denom = float(1.0 / r0)
+        if self.lower_order_nums < 2:
+            self.lower_order_nums += 1
+        self.step_index += 1
+        return plan
+
+
 class BranchState:
     """Device state of one denoising branch (SDR or GM): fp32 pixel-major latents [B*h*w, 4], a 4-slot eps ring
     and the PLMS stash.  Allocated once; every step is in-place (CUDA-graph friendly)."""
@@ -236,7 +296,7 @@ def fused_step(plan: StepPlan, state: BranchState, eps_cond: torch.Tensor, eps_u
         h = state.hist(k) if k < plan.n_hist else None
         p.hist[k] = L.ptr(h)
     slot = None
-    if plan.push_eps and plan.mode == L.SCHED_LINEAR:
+    if plan.push_eps and plan.mode in (L.SCHED_LINEAR, L.SCHED_DPMPP):
         slot = state.free_slot()
         p.eps_out = state.ring[slot].data_ptr()
     if plan.needs_noise:

@@ -89,7 +89,11 @@ float gmd_decode_ordered(int32_t v);
 enum gmd_sched_mode {
     GMD_SCHED_LINEAR = 0, /* PLMS: x' = c_sample*x_src - c_num*eps'/c_denom */
     GMD_SCHED_DDIM = 1,   /* x' = sqrt(a_prev)*x0 + dir_coeff*eps (+ sigma*noise) */
-    GMD_SCHED_DDPM = 2    /* ancestral: x' = c_x0*x0 + c_xt*x (+ sigma*noise); the scheduler every reference CLI passes (generate_hdr.py:162-176) */
+    GMD_SCHED_DDPM = 2,   /* ancestral: x' = c_x0*x0 + c_xt*x (+ sigma*noise); the scheduler every reference CLI passes (generate_hdr.py:162-176) */
+    GMD_SCHED_DPMPP = 3   /* DPM-Solver++(2M, midpoint), swapped in by scripts/inference/experiments/formal_improved.py:195.
+                             m0 = (x - ddim_sqrt_1m_alpha_t*eps)/ddim_sqrt_alpha_t (alpha_s, sigma_s of the current sigma) is written
+                             to eps_out (the history holds x0 predictions); plms_kind 0: x' = c_sample*x - c_num*m0;
+                             plms_kind 1: ... - 0.5*c_num*(c_denom*(m0 - hist[0])), c_denom = 1/r0 */
 };
 /* PLMS multistep combination eps' (diffusers PNDMScheduler.step_plms):
  *   0: eps   1: (eps + h0)/2   2: (3 eps - h0)/2   3: (23 eps - 16 h0 + 5 h1)/12   4: (55 eps - 59 h0 + 37 h1 - 9 h2)/24 */

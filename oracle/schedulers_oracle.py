@@ -4,7 +4,7 @@ pipelines call (`scheduler.set_timesteps` at stable_diffusion_dual_unet.py:151-1
 
 PARITY UNPINNED: diffusers (>=0.33, README.md:54) is not vendored in /root/reference and cannot be
 installed offline; the formulas below restate the published PNDMScheduler.step_plms /
-DDIMScheduler.step / DDPMScheduler.step algorithms with the SD1.5 scheduler config
+DDIMScheduler.step / DDPMScheduler.step / DPMSolverMultistepScheduler.step algorithms with the SD1.5 scheduler config
 and are pinned by invariants in tests/test_schedulers_oracle.py.
 """
 from __future__ import annotations
@@ -159,6 +159,74 @@ class DDPMOracle(_Base):
                 variance_noise = _randn_like(model_output, generator)
             variance = torch.clamp((1 - a_p) / (1 - a_t) * cur_beta, min=1e-20)
             prev = prev + variance ** 0.5 * variance_noise
+        return (prev,)
+
+
+class DPMSolverOracle(_Base):
+    """diffusers DPMSolverMultistepScheduler as `from_config(<SD1.5 PNDM config>)` builds it (formal_improved.py:195):
+    algorithm_type dpmsolver++, solver_order 2, solver_type midpoint, lower_order_final True, final_sigmas_type zero,
+    no karras sigmas, no thresholding, epsilon prediction, leading spacing.  Written tensor-op for tensor-op."""
+
+    solver_order = 2
+
+    def set_timesteps(self, num_inference_steps, device=None):
+        self.num_inference_steps = num_inference_steps
+        last_timestep = self.config.num_train_timesteps  # lambda_min_clipped = -inf clips nothing
+        step_ratio = last_timestep // (num_inference_steps + 1)
+        ts = (np.arange(0, num_inference_steps + 1) * step_ratio).round()[::-1][:-1].copy().astype(np.int64) + self.config.steps_offset
+        sigmas = (((1 - self.alphas_cumprod) / self.alphas_cumprod) ** 0.5).numpy()
+        sigmas = np.interp(ts, np.arange(0, len(sigmas)), sigmas)
+        sigmas = np.concatenate([sigmas, [0.0]]).astype(np.float32)
+        self.sigmas = torch.from_numpy(sigmas)
+        self.timesteps = torch.from_numpy(ts)
+        self.model_outputs = [None] * self.solver_order
+        self.lower_order_nums = 0
+        self.step_index = 0
+
+    @staticmethod
+    def _sigma_to_alpha_sigma_t(sigma):
+        alpha_t = 1 / ((sigma ** 2 + 1) ** 0.5)
+        return alpha_t, sigma * alpha_t
+
+    def convert_model_output(self, model_output, sample):
+        alpha_t, sigma_t = self._sigma_to_alpha_sigma_t(self.sigmas[self.step_index])
+        return (sample - sigma_t * model_output) / alpha_t
+
+    def _first_order(self, m0, sample):
+        sigma_t, sigma_s = self.sigmas[self.step_index + 1], self.sigmas[self.step_index]
+        alpha_t, sigma_t = self._sigma_to_alpha_sigma_t(sigma_t)
+        alpha_s, sigma_s = self._sigma_to_alpha_sigma_t(sigma_s)
+        h = (torch.log(alpha_t) - torch.log(sigma_t)) - (torch.log(alpha_s) - torch.log(sigma_s))
+        return (sigma_t / sigma_s) * sample - (alpha_t * (torch.exp(-h) - 1.0)) * m0
+
+    def _second_order(self, outputs, sample):
+        sigma_t, sigma_s0, sigma_s1 = self.sigmas[self.step_index + 1], self.sigmas[self.step_index], self.sigmas[self.step_index - 1]
+        alpha_t, sigma_t = self._sigma_to_alpha_sigma_t(sigma_t)
+        alpha_s0, sigma_s0 = self._sigma_to_alpha_sigma_t(sigma_s0)
+        alpha_s1, sigma_s1 = self._sigma_to_alpha_sigma_t(sigma_s1)
+        lambda_t = torch.log(alpha_t) - torch.log(sigma_t)
+        lambda_s0 = torch.log(alpha_s0) - torch.log(sigma_s0)
+        lambda_s1 = torch.log(alpha_s1) - torch.log(sigma_s1)
+        m0, m1 = outputs[-1], outputs[-2]
+        h, h_0 = lambda_t - lambda_s0, lambda_s0 - lambda_s1
+        r0 = h_0 / h
+        D0, D1 = m0, (1.0 / r0) * (m0 - m1)
+        return ((sigma_t / sigma_s0) * sample - (alpha_t * (torch.exp(-h) - 1.0)) * D0
+                - 0.5 * (alpha_t * (torch.exp(-h) - 1.0)) * D1)
+
+    def step(self, model_output, timestep, sample, return_dict=False, **kw):
+        n = len(self.timesteps)
+        lower_order_final = self.step_index == n - 1  # final_sigmas_type == "zero"
+        m = self.convert_model_output(model_output, sample)
+        self.model_outputs = self.model_outputs[1:] + [m]
+        sample = sample.to(torch.float32)
+        if self.lower_order_nums < 1 or lower_order_final:
+            prev = self._first_order(m, sample)
+        else:
+            prev = self._second_order(self.model_outputs, sample)
+        if self.lower_order_nums < self.solver_order:
+            self.lower_order_nums += 1
+        self.step_index += 1
         return (prev,)
 
 

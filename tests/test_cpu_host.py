@@ -131,6 +131,35 @@ def test_ddpm_plan_matches_oracle():
         assert plan.needs_noise == (t > 0)
 
 
+@pytest.mark.parametrize("steps", [5, 20, 50])
+def test_dpmsolver_plan_matches_oracle(steps):
+    """DPM-Solver++(2M) host plan (formal_improved.py:195) against the tensor-op oracle, plus the algorithm's own invariants."""
+    from gm_diffusion_b200.schedulers import DPMSolverMultistepScheduler
+    from oracle.schedulers_oracle import DPMSolverOracle
+    p, o = DPMSolverMultistepScheduler(), DPMSolverOracle()
+    p.set_timesteps(steps); o.set_timesteps(steps)
+    assert torch.equal(p.timesteps, o.timesteps) and torch.equal(p.sigmas, o.sigmas)
+    if steps == 50:
+        assert p.timesteps[0].item() == 951 and p.timesteps[-1].item() == 20  # leading spacing over n+1 points, offset 1
+    g = torch.Generator().manual_seed(0)
+    x = torch.randn(16, generator=g)
+    xo = x.clone()
+    prev_m = None
+    for i, t in enumerate(p.timesteps.tolist()):
+        e = torch.randn(16, generator=g)
+        plan = p.plan_step(t)
+        a_s, s_s = plan.ddim[0], plan.ddim[1]
+        m0 = (x - s_s * e) / a_s
+        nxt = plan.c_sample * x - plan.c_num * m0
+        assert plan.plms_kind == (0 if i == 0 or i == steps - 1 else 1)
+        if plan.plms_kind == 1:
+            nxt = nxt - (0.5 * plan.c_num) * (plan.c_denom * (m0 - prev_m))
+        prev_m, x = m0, nxt
+        xo = o.step(e, t, xo)[0]
+        torch.testing.assert_close(x, xo, rtol=1e-5, atol=1e-5)
+    torch.testing.assert_close(x, prev_m, rtol=0, atol=0)  # final sigma 0: the last step returns the x0 prediction itself
+
+
 def test_check_inputs_mirrors_reference_errors():
     from gm_diffusion_b200.pipelines._common import PipelineBase, retrieve_timesteps
     from gm_diffusion_b200.schedulers import PNDMScheduler

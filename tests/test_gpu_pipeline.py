@@ -131,6 +131,27 @@ def test_dual_batch_sharding_independence(dual_pipe):
         assert torch.equal(s2[b:b + 1], s1) and torch.equal(g2[b:b + 1], g1), (rel_l2(s2[b:b + 1], s1), rel_l2(g2[b:b + 1], g1))
 
 
+def test_dpmsolver_dual_pipeline(models, dual_pipe):
+    """scripts/inference/experiments/formal_improved.py:195 swaps DPMSolverMultistepScheduler.from_config(...) into the dual pipeline."""
+    from gm_diffusion_b200 import DPMSolverMultistepScheduler, StableDiffusionDualUNetImprovedPipeline
+    from oracle import pipeline_oracle as PO
+    from oracle.schedulers_oracle import DPMSolverOracle
+    u4, u8, _ = models
+    pe, ne, lat, _ = _inputs()
+    want_sdr, want_gm = PO.dual_unet_loop(u4, u8, DPMSolverOracle(), pe, ne, lat.clone(), num_inference_steps=5, guidance_scale=7.5)
+    pipe = StableDiffusionDualUNetImprovedPipeline(vae=None, text_encoder=None, tokenizer=None, unet=dual_pipe.unet, gm_unet=dual_pipe.gm_unet,
+                                                   scheduler=DPMSolverMultistepScheduler())
+    for graphs in (False, True):
+        pipe.use_cuda_graph = graphs
+        got_sdr, got_gm = pipe(prompt_embeds=pe, negative_prompt_embeds=ne, latents=lat.clone(), height=256, width=256, num_inference_steps=5,
+                               guidance_scale=7.5, output_type="latent",
+                               # the extra arguments formal_improved.py:259-269 passes: swallowed kwarg, eta the solver's step() does not
+                               # take, and a LoRA scale with no adapter loaded — all no-ops in the reference
+                               noise_level=0.0, eta=0.7, cross_attention_kwargs={"scale": 0.8})
+        r1, r2 = rel_l2(got_sdr, want_sdr), rel_l2(got_gm, want_gm)
+        assert r1 < 3e-2 and r2 < 3e-2, f"DPM++ final latents rel-L2 sdr {r1:.3e} gm {r2:.3e} (graphs={graphs})"
+
+
 def test_ddpm_dual_pipeline_reference_cli_scheduler(models, dual_pipe):
     """DDPM is what scripts/inference/generate_hdr.py:162-176 passes: ancestral noise from the shared generator, SDR draw then GM."""
     from gm_diffusion_b200 import DDPMScheduler, StableDiffusionDualUNetPipeline

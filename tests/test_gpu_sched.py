@@ -96,6 +96,14 @@ def test_ddpm_dual(steps):
     _run_dual(DDPMScheduler, DDPMOracle, steps)
 
 
+@pytest.mark.parametrize("steps", [4, 25, 50])
+def test_dpmsolver_dual(steps):
+    """DPM-Solver++(2M): the scheduler formal_improved.py:195 swaps in; the history ring holds x0 predictions."""
+    from gm_diffusion_b200.schedulers import DPMSolverMultistepScheduler
+    from oracle.schedulers_oracle import DPMSolverOracle
+    _run_dual(DPMSolverMultistepScheduler, DPMSolverOracle, steps)
+
+
 def test_latent_layout_roundtrip_and_pack():
     import ctypes as C
     from gm_diffusion_b200 import _lib as L
