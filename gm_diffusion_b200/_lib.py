@@ -28,7 +28,8 @@ _vp, _i64, _i32, _f32 = C.c_void_p, C.c_int64, C.c_int32, C.c_float
 class HdrParams(C.Structure):
     _fields_ = [("sdr", _vp), ("gm", _vp), ("hdr_out", _vp), ("tmo_out", _vp), ("minmax", _vp),
                 ("n_px", _i64), ("batch", _i64), ("layout", _i32), ("in_dtype", _i32), ("flags", _i32),
-                ("tmo", _i32), ("qmax", _f32), ("eps", _f32), ("mu", _f32)]
+                ("tmo", _i32), ("qmax", _f32), ("eps", _f32), ("mu", _f32), ("rgbe_div", _f32),
+                ("rgbe_out", _vp), ("sdr_u8_out", _vp), ("gm_u8_out", _vp)]
 
 
 class SchedParams(C.Structure):

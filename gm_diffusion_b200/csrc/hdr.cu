@@ -14,8 +14,31 @@ struct HdrConsts {
     float inv_hi;                 // 1 / (qmax + 1)
     float mu, inv_log1p_mu;
     float log2_hi;                // for the optional exponential gain
+    float rgbe_div;               // RGBE encodes hdr / rgbe_div (save_hdr_image's division by qmax + 1)
+    float rgbe_min;               // smallest float >= 1e-32 (the C comparison `v < 1e-32` is done in double)
     int flags, tmo;
 };
+
+struct ByteOuts {
+    uint8_t* rgbe;     // [pixels, 4] R,G,B,E (3-channel layouts only)
+    uint8_t* sdr_u8;   // same element order as the input
+    uint8_t* gm_u8;
+};
+
+// Radiance shared-exponent pixel, as OpenCV's HdrEncoder quantises it (Ward's float2rgbe): v = max(r,g,b); v < 1e-32 -> 0;
+// else (m, e) = frexp(v); scale = m * 256 / v; bytes = trunc(c * scale), e + 128.  m * 256 / v is exactly 2^(8-e), so the scale
+// is built from the exponent bits and the products are exact: the result is bit-identical to the C code.
+__device__ __forceinline__ uint32_t rgbe_pack(float r, float g, float b, float vmin) {
+    float v = fmaxf(r, fmaxf(g, b));
+    if (!(v >= vmin)) return 0u;
+    int e = (int)((__float_as_uint(v) >> 23) & 0xffu) - 126;
+    float scale = __uint_as_float((uint32_t)(127 + 8 - e) << 23);
+    int R = min(max((int)(r * scale), 0), 255), G = min(max((int)(g * scale), 0), 255), B = min(max((int)(b * scale), 0), 255);
+    return (uint32_t)R | ((uint32_t)G << 8) | ((uint32_t)B << 16) | ((uint32_t)((e + 128) & 0xff) << 24);
+}
+
+// (x * 255).astype(uint8) of generate_hdr.py:243-244 (x in [0,1]; truncation)
+__device__ __forceinline__ uint32_t to_u8(float x) { return (uint32_t)min(max((int)__fmul_rn(x, 255.0f), 0), 255); }
 
 // x^2.2 on [0,1] as x*x * 2^(0.2*log2 x): the MUFU approximations only see the 0.2 exponent, so their
 // absolute error (2^-22 on lg2) is damped 11x compared with a direct 2^(2.2*log2 x): <= ~4e-7 relative.
@@ -136,10 +159,10 @@ __device__ __forceinline__ void store4(float* p, int64_t i, const float* v) {
 // matrix sees r,g,b of the same pixel.  CH = 1 is the flat elementwise case.
 //   plane_stride: elements between channel planes (H*W) ; img_stride = CH * plane_stride
 //   INTERLEAVED (CH == 3 only): pixel-major [n_px, 3]; VEC pixels = 3*VEC consecutive floats.
-template <typename T, int CH, int VEC, bool INTERLEAVED>
+template <typename T, int CH, int VEC, bool INTERLEAVED, bool BYTES>
 __global__ void __launch_bounds__(256) hdr_kernel(const T* __restrict__ sdr, const T* __restrict__ gm,
                                                   float* __restrict__ hdr_out, float* __restrict__ tmo_out,
-                                                  int32_t* __restrict__ minmax, int64_t items_per_img, int64_t n_items,
+                                                  int32_t* __restrict__ minmax, ByteOuts bo, int64_t items_per_img, int64_t n_items,
                                                   int64_t plane_stride, HdrConsts c) {
     MinMax mm;
     const bool do_eq1 = c.flags & GMD_HDR_EQ1;
@@ -148,6 +171,7 @@ __global__ void __launch_bounds__(256) hdr_kernel(const T* __restrict__ sdr, con
          it += (int64_t)gridDim.x * blockDim.x) {
         float s[CH][VEC], g[CH][VEC], h[CH][VEC];
         int64_t off[CH];
+        int64_t px0;  // index of this item's first pixel over the whole batch
         if (INTERLEAVED) {
             // 3*VEC contiguous floats, VEC == 4 -> three 16-byte vectors
             int64_t base = it * (3 * VEC);
@@ -177,9 +201,11 @@ __global__ void __launch_bounds__(256) hdr_kernel(const T* __restrict__ sdr, con
 #pragma unroll
                 for (int ch = 0; ch < CH; ++ch) { s[ch][v] = sv[3 * v + ch]; g[ch][v] = gv[3 * v + ch]; }
             off[0] = base;
+            px0 = it * VEC;
         } else {
             int64_t img = it / items_per_img;
             int64_t px = (it - img * items_per_img) * VEC;
+            px0 = img * plane_stride + px;
 #pragma unroll
             for (int ch = 0; ch < CH; ++ch) off[ch] = (img * CH + ch) * plane_stride + px;
 #pragma unroll
@@ -203,6 +229,49 @@ __global__ void __launch_bounds__(256) hdr_kernel(const T* __restrict__ sdr, con
                 h[ch][v] = x;
                 if (minmax) mm.add(x);
             }
+        // byte outputs for the host tail (generate_hdr.py:27-30,243-244): PNG-ready uint8 SDR / GM and Radiance RGBE
+        if (BYTES && (bo.sdr_u8 || bo.gm_u8)) {
+#pragma unroll
+            for (int which = 0; which < 2; ++which) {
+                uint8_t* dst = which ? bo.gm_u8 : bo.sdr_u8;
+                if (!dst) continue;
+                if (INTERLEAVED) {
+                    uint32_t w[(3 * VEC + 3) / 4] = {};
+#pragma unroll
+                    for (int v = 0; v < VEC; ++v)
+#pragma unroll
+                        for (int ch = 0; ch < CH; ++ch) {
+                            int k = 3 * v + ch;
+                            w[k / 4] |= to_u8(denorm(which ? g[ch][v] : s[ch][v], c.flags)) << (8 * (k % 4));
+                        }
+                    if (VEC == 4) {
+#pragma unroll
+                        for (int q = 0; q < 3; ++q) reinterpret_cast<uint32_t*>(dst + off[0])[q] = w[q];
+                    } else {
+#pragma unroll
+                        for (int k = 0; k < 3 * VEC; ++k) dst[off[0] + k] = (uint8_t)(w[k / 4] >> (8 * (k % 4)));
+                    }
+                } else {
+#pragma unroll
+                    for (int ch = 0; ch < CH; ++ch) {
+                        uint32_t w = 0;
+#pragma unroll
+                        for (int v = 0; v < VEC; ++v) w |= to_u8(denorm(which ? g[ch][v] : s[ch][v], c.flags)) << (8 * v);
+                        if (VEC == 4) *reinterpret_cast<uint32_t*>(dst + off[ch]) = w;
+                        else dst[off[ch]] = (uint8_t)w;
+                    }
+                }
+            }
+        }
+        if (BYTES && CH == 3 && bo.rgbe) {
+            uint32_t w[VEC];
+#pragma unroll
+            for (int v = 0; v < VEC; ++v)
+                w[v] = rgbe_pack(__fdiv_rn(h[0][v], c.rgbe_div), __fdiv_rn(h[CH > 1 ? 1 : 0][v], c.rgbe_div),
+                                 __fdiv_rn(h[CH > 2 ? 2 : 0][v], c.rgbe_div), c.rgbe_min);
+            if (VEC == 4) __stcs(reinterpret_cast<uint4*>(bo.rgbe + 4 * px0), make_uint4(w[0], w[1], w[2], w[3]));
+            else reinterpret_cast<uint32_t*>(bo.rgbe)[px0] = w[0];
+        }
         if (hdr_out) {
             if (INTERLEAVED) {
                 float ov[3 * VEC];
@@ -277,9 +346,14 @@ int launch(const gmd_hdr_params* p, const HdrConsts& c, int64_t items_per_img, i
     int64_t want = (n_items + 255) / 256;
     int64_t cap = (int64_t)sms * 8;   // 8 resident CTAs of 256 threads per SM; grid-stride over the rest
     int grid = (int)(want < cap ? (want > 0 ? want : 1) : cap);
-    hdr_kernel<T, CH, VEC, INTER><<<grid, 256, 0, st>>>(static_cast<const T*>(p->sdr), static_cast<const T*>(p->gm),
-                                                         p->hdr_out, p->tmo_out, p->minmax, items_per_img, n_items,
-                                                         plane_stride, c);
+    // the byte outputs cost ~16-35 registers: only the launches that ask for them pay (BYTES instantiation)
+    ByteOuts bo{p->rgbe_out, p->sdr_u8_out, p->gm_u8_out};
+    auto* sdr = static_cast<const T*>(p->sdr);
+    auto* gm = static_cast<const T*>(p->gm);
+    if (bo.rgbe || bo.sdr_u8 || bo.gm_u8)
+        hdr_kernel<T, CH, VEC, INTER, true><<<grid, 256, 0, st>>>(sdr, gm, p->hdr_out, p->tmo_out, p->minmax, bo, items_per_img, n_items, plane_stride, c);
+    else
+        hdr_kernel<T, CH, VEC, INTER, false><<<grid, 256, 0, st>>>(sdr, gm, p->hdr_out, p->tmo_out, p->minmax, bo, items_per_img, n_items, plane_stride, c);
     count_launch(1);
     return check_launch("hdr_kernel");
 }
@@ -290,7 +364,7 @@ int dispatch(const gmd_hdr_params* p, const HdrConsts& c, cudaStream_t st) {
     const size_t in_align = sizeof(T) == 4 ? 15 : 7;
     bool ptr_ok = (reinterpret_cast<uintptr_t>(p->sdr) & in_align) == 0 &&
                   (p->gm == nullptr || (reinterpret_cast<uintptr_t>(p->gm) & in_align) == 0) && aligned16(p->hdr_out) &&
-                  aligned16(p->tmo_out);
+                  aligned16(p->tmo_out) && aligned16(p->rgbe_out) && aligned16(p->sdr_u8_out) && aligned16(p->gm_u8_out);
     if (p->layout == GMD_LAYOUT_PLANAR3) {
         if (ptr_ok && p->n_px % 4 == 0)
             return launch<T, 3, 4, false>(p, c, p->n_px / 4, p->batch * (p->n_px / 4), p->n_px, st);
@@ -313,7 +387,11 @@ extern "C" int gmd_hdr_reconstruct(const gmd_hdr_params* p, void* stream) {
     using namespace gmd;
     if (!p || !p->sdr) { set_last_error("gmd_hdr_reconstruct: null input"); return kErrInvalid; }
     if ((p->flags & GMD_HDR_EQ1) && !p->gm) { set_last_error("gmd_hdr_reconstruct: Eq.(1) needs a gain map"); return kErrInvalid; }
-    if (!p->hdr_out && !p->tmo_out && !p->minmax) { set_last_error("gmd_hdr_reconstruct: no output requested"); return kErrInvalid; }
+    if (!p->hdr_out && !p->tmo_out && !p->minmax && !p->rgbe_out && !p->sdr_u8_out && !p->gm_u8_out) {
+        set_last_error("gmd_hdr_reconstruct: no output requested"); return kErrInvalid;
+    }
+    if (p->rgbe_out && p->layout == GMD_LAYOUT_FLAT) { set_last_error("gmd_hdr_reconstruct: RGBE output needs a 3-channel layout"); return kErrInvalid; }
+    if (p->gm_u8_out && !p->gm) { set_last_error("gmd_hdr_reconstruct: gm_u8_out without a gain map"); return kErrInvalid; }
     if (p->n_px < 0 || p->batch < 0) { set_last_error("gmd_hdr_reconstruct: negative size"); return kErrInvalid; }
     if ((p->flags & GMD_HDR_GAMUT) && p->layout == GMD_LAYOUT_FLAT) {
         set_last_error("gmd_hdr_reconstruct: gamut compression needs a 3-channel layout"); return kErrInvalid;
@@ -334,6 +412,9 @@ extern "C" int gmd_hdr_reconstruct(const gmd_hdr_params* p, void* stream) {
     c.mu = (float)mu;
     c.inv_log1p_mu = (float)(1.0 / log1p(mu));
     c.log2_hi = (float)log2((double)p->qmax + 1.0);
+    c.rgbe_div = p->rgbe_div != 0.0f ? p->rgbe_div : 1.0f;
+    c.rgbe_min = (float)1e-32;
+    if ((double)c.rgbe_min < 1e-32) c.rgbe_min = nextafterf(c.rgbe_min, INFINITY);
     if (p->in_dtype == GMD_F32) return dispatch<float>(p, c, st);
     if (p->in_dtype == GMD_BF16) return dispatch<__nv_bfloat16>(p, c, st);
     set_last_error("gmd_hdr_reconstruct: unknown in_dtype %d", p->in_dtype);

@@ -11,7 +11,8 @@ Differences from the reference, all deliberate:
   * `output_type="latent"` returns `(latents, gm_latents)` exactly like the reference.  Other output types are broken in
     the reference (:1118-1131 index the batch of a single SDR decode); here they decode BOTH latents:
     "pt"/"np"/"pil" -> `(sdr_images, gm_images)`, and "hdr" additionally applies Eq.(1) on the GPU and returns
-    `(hdr [B,H,W,3] fp32, sdr, gm)`.
+    `(hdr [B,H,W,3] fp32, sdr, gm)`; "disk" returns what the scripts write to files, produced by the same single launch:
+    `(rgbe uint8 [B,H,W,4], sdr_u8 [B,H,W,3], gm_u8 [B,H,W,3])` (generate_hdr.py:243-244 and save_hdr_image :27-30).
   * cross-attention K/V and the timestep-embedding MLP are hoisted out of the loop; latents / PLMS history / CFG math
     stay in fp32 regardless of the UNet compute dtype (bf16).
 """
@@ -226,6 +227,10 @@ class StableDiffusionDualUNetPipeline(PipelineBase):
             # de-normalise + Eq.(1) in ONE kernel (generate_hdr.py:227,232,256-265 run this on the host in numpy; no clamp there)
             hdr, _ = TM.reconstruct_hdr(sdr_img, gm_img, qmax=qmax, eps=hdr_eps, denormalize=True, clamp=False, channels_last=True)
             return hdr, sdr_img, gm_img
+        if output_type == "disk":
+            # same launch, but emitting what the scripts write to disk (generate_hdr.py:243-244 PNG uint8, :27-30 Radiance RGBE of
+            # hdr/(qmax+1)): 10 B/px leave the GPU instead of 24 B/px of fp32, and `hdr_io.pack_radiance` only adds the container
+            return TM.reconstruct_for_disk(sdr_img, gm_img, qmax=qmax, eps=hdr_eps, denormalize=True, clamp=False, channels_last=True)
         outs = []
         for img in (sdr_img, gm_img):
             x = (img.float() / 2 + 0.5).clamp(0, 1)       # VaeImageProcessor.postprocess de-normalise

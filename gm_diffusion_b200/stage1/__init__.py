@@ -6,9 +6,11 @@ from .tone_mapping import (
     hard_clip_tmo,
     linear_scale_tmo,
     random_tmo_cuda,
+    reconstruct_for_disk,
     reconstruct_hdr,
+    rgbe_encode,
     tmo_cuda,
 )
 
 __all__ = ["apply_gm_to_sdr", "fix_mulog_tmo", "gamut_compress", "hard_clip_tmo", "linear_scale_tmo",
-           "random_tmo_cuda", "tmo_cuda", "reconstruct_hdr"]
+           "random_tmo_cuda", "tmo_cuda", "reconstruct_hdr", "reconstruct_for_disk", "rgbe_encode"]

@@ -23,7 +23,9 @@ def _prep(t: torch.Tensor) -> Tuple[torch.Tensor, int]:
     return t.to(torch.float32).contiguous(), L.F32
 
 
-def _run(sdr, gm, *, flags, tmo, qmax, eps, mu, want_hdr, want_tmo, want_minmax, layout=None):
+def _run(sdr, gm, *, flags, tmo, qmax, eps, mu, want_hdr, want_tmo, want_minmax, layout=None, want_rgbe=False, want_u8=False,
+         rgbe_div=1.0):
+    """Returns (hdr, tmo, minmax) and, when byte outputs are requested, (hdr, tmo, minmax, rgbe, sdr_u8, gm_u8)."""
     L.require_cuda(sdr, gm)
     sdr, dt = _prep(sdr)
     if gm is not None:
@@ -44,6 +46,10 @@ def _run(sdr, gm, *, flags, tmo, qmax, eps, mu, want_hdr, want_tmo, want_minmax,
     if sdr.numel() == 0:  # empty input: nothing to launch
         e = torch.empty(sdr.shape, dtype=torch.float32, device=sdr.device)
         mm0 = torch.tensor([0x7F800000, -2139095041], dtype=torch.int32, device=sdr.device) if want_minmax else None  # (+inf, -inf)
+        if want_rgbe or want_u8:
+            u = torch.empty(sdr.shape, dtype=torch.uint8, device=sdr.device)
+            r = torch.empty((*_px_shape(sdr, layout), 4), dtype=torch.uint8, device=sdr.device) if want_rgbe else None
+            return (e if want_hdr else None), (e.clone() if want_tmo else None), mm0, r, (u if want_u8 else None), (u.clone() if want_u8 and gm is not None else None)
         return (e if want_hdr else None), (e.clone() if want_tmo else None), mm0
     hdr = torch.empty(sdr.shape, dtype=torch.float32, device=sdr.device) if want_hdr else None
     out = torch.empty(sdr.shape, dtype=torch.float32, device=sdr.device) if want_tmo else None
@@ -51,8 +57,27 @@ def _run(sdr, gm, *, flags, tmo, qmax, eps, mu, want_hdr, want_tmo, want_minmax,
     p.sdr, p.gm, p.hdr_out, p.tmo_out, p.minmax = L.ptr(sdr), L.ptr(gm), L.ptr(hdr), L.ptr(out), L.ptr(mm)
     p.layout, p.in_dtype, p.flags, p.tmo = layout, dt, flags, tmo
     p.qmax, p.eps, p.mu = float(qmax), float(eps), float(mu)
+    rgbe = s8 = g8 = None
+    if want_rgbe:
+        if layout == L.LAYOUT_FLAT:
+            raise ValueError("RGBE output needs [B,3,H,W] or channels_last [...,3]")
+        rgbe = torch.empty((*_px_shape(sdr, layout), 4), dtype=torch.uint8, device=sdr.device)
+        p.rgbe_out, p.rgbe_div = rgbe.data_ptr(), float(rgbe_div)
+    if want_u8:
+        s8 = torch.empty(sdr.shape, dtype=torch.uint8, device=sdr.device)
+        p.sdr_u8_out = s8.data_ptr()
+        if gm is not None:
+            g8 = torch.empty(sdr.shape, dtype=torch.uint8, device=sdr.device)
+            p.gm_u8_out = g8.data_ptr()
     L.check(L.lib().gmd_hdr_reconstruct(C.byref(p), L.current_stream()), "gmd_hdr_reconstruct")
+    if want_rgbe or want_u8:
+        return hdr, out, mm, rgbe, s8, g8
     return hdr, out, mm
+
+
+def _px_shape(t: torch.Tensor, layout: int):
+    """Shape of the pixel grid: [B,3,H,W] -> (B,H,W); [...,3] -> (...)."""
+    return (t.shape[0], *t.shape[2:]) if layout == L.LAYOUT_PLANAR3 else tuple(t.shape[:-1])
 
 
 def _decode_minmax(mm: torch.Tensor) -> Tuple[float, float]:
@@ -141,5 +166,41 @@ def reconstruct_hdr(sdr: torch.Tensor, gm: torch.Tensor, qmax: float = 99.0, eps
     return hdr, out
 
 
+def reconstruct_for_disk(sdr: torch.Tensor, gm: torch.Tensor, qmax: float = 99.0, eps: float = 1 / 64, *, denormalize: bool = True,
+                         clamp: bool = False, channels_last: bool = False, return_hdr: bool = False):
+    """The inference scripts' whole host tail in ONE launch (generate_hdr.py:225-268 + save_hdr_image :27-30): de-normalise the two
+    VAE images, Eq.(1) (numpy-twin behaviour: no output clamp by default), and emit what goes to disk — PNG-ready uint8 SDR and
+    GM (`(x * 255).astype(np.uint8)`, :243-244) and the Radiance RGBE pixels of `hdr / (qmax + 1)` exactly as
+    `cv2.imwrite("x.hdr", ...)` quantises them — so the device->host copy is 4 + 3 + 3 B/px instead of 2 x 12 B/px of fp32.
+
+    Returns (rgbe uint8 [B,H,W,4] in R,G,B,E order, sdr_u8, gm_u8[, hdr fp32]); sdr_u8/gm_u8 keep the input's layout."""
+    flags = L.HDR_EQ1 | (L.HDR_DENORM if denormalize else 0) | (L.HDR_CLAMP_OUT if clamp else 0)
+    if channels_last:
+        if sdr.shape[-1] != 3:
+            raise ValueError("channels_last expects [...,3]")
+        layout = L.LAYOUT_INTERLEAVED3
+    elif sdr.dim() == 4 and sdr.shape[1] == 3:
+        layout = L.LAYOUT_PLANAR3
+    else:
+        raise ValueError("reconstruct_for_disk needs [B,3,H,W] or channels_last [...,3]")
+    hdr, _, _, rgbe, s8, g8 = _run(sdr, gm, flags=flags, tmo=L.TMO_NONE, qmax=qmax, eps=eps, mu=0, want_hdr=return_hdr, want_tmo=False,
+                                   want_minmax=False, layout=layout, want_rgbe=True, want_u8=True, rgbe_div=float(qmax) + 1.0)
+    return (rgbe, s8, g8, hdr) if return_hdr else (rgbe, s8, g8)
+
+
+def rgbe_encode(hdr: torch.Tensor, divisor: float = 1.0, *, channels_last: bool = True) -> torch.Tensor:
+    """Radiance RGBE pixels of `hdr / divisor` (uint8 [...,4], R,G,B,E) — the quantisation `cv2.imwrite("x.hdr", bgr)` applies."""
+    if channels_last:
+        if hdr.shape[-1] != 3:
+            raise ValueError("channels_last expects [...,3]")
+        layout = L.LAYOUT_INTERLEAVED3
+    elif hdr.dim() == 4 and hdr.shape[1] == 3:
+        layout = L.LAYOUT_PLANAR3
+    else:
+        raise ValueError("rgbe_encode needs [B,3,H,W] or channels_last [...,3]")
+    return _run(hdr, None, flags=0, tmo=L.TMO_NONE, qmax=0, eps=0, mu=0, want_hdr=False, want_tmo=False, want_minmax=False,
+                layout=layout, want_rgbe=True, rgbe_div=float(divisor))[3]
+
+
 __all__ = ["linear_scale_tmo", "hard_clip_tmo", "fix_mulog_tmo", "tmo_cuda", "random_tmo_cuda", "apply_gm_to_sdr",
-           "gamut_compress", "reconstruct_hdr"]
+           "gamut_compress", "reconstruct_hdr", "reconstruct_for_disk", "rgbe_encode"]

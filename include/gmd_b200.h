@@ -75,6 +75,12 @@ typedef struct gmd_hdr_params {
     float qmax;
     float eps;
     float mu;          /* GMD_TMO_MULOG only */
+    /* Host-tail byte outputs (all optional; scripts/inference/generate_hdr.py:27-30,243-244):                                 */
+    float rgbe_div;      /* RGBE encodes hdr / rgbe_div — save_hdr_image's `apply_HDR / (qmax+1)`; 0 means 1                 */
+    uint8_t* rgbe_out;   /* [pixels,4] Radiance R,G,B,E of the (pre-TMO) HDR value, quantised as cv2.imwrite("x.hdr") does    */
+                         /* (Ward float2rgbe); needs PLANAR3 or INTERLEAVED3; pixel order = batch-major scan order            */
+    uint8_t* sdr_u8_out; /* trunc(clamp01(sdr) * 255), same element order as `sdr` (after DENORM when that flag is set)       */
+    uint8_t* gm_u8_out;  /* same for the gain map                                                                              */
 } gmd_hdr_params;
 
 int gmd_hdr_reconstruct(const gmd_hdr_params* p, void* stream);

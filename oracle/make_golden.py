@@ -49,5 +49,36 @@ def main():
           "mulog mean", float(ref.fix_mulog_tmo(h, 99).mean()))
 
 
+def rgbe_golden():
+    """tests/golden/rgbe_cv2.npz: RGBE bytes parsed out of files the REAL cv2.imwrite wrote through the reference's own
+    save_hdr_image recipe (scripts/inference/generate_hdr.py:27-30: /(qmax+1), float32, RGB->BGR flip)."""
+    import os
+    import tempfile
+
+    import cv2
+
+    from . import rgbe_oracle as ro
+    rng = np.random.default_rng(0)
+    H, W = 24, 40
+    hdr = (rng.random((H, W, 3), dtype=np.float32) * np.exp(rng.uniform(-14, 5, (H, W, 1))).astype(np.float32)) * 100.0
+    hdr[0, :8] = [[0, 0, 0], [1e-31, 0, 0], [100, 100, 100], [50, 25, 12.5], [100, 0, 0], [0, 100, 0], [0, 0, 100], [3e-31, 2e-31, 1e-31]]
+    hdr[1, :4] = [[1.0, 2.0, 4.0], [127.99, 128.0, 128.01], [1e-30, 1e-30, 1e-30], [99.999, 1e-3, 1e-6]]
+    narrow = hdr[:5, :6].copy()  # W < 8: OpenCV writes flat pixels
+    out = {}
+    with tempfile.TemporaryDirectory() as d:
+        for name, img in (("wide", hdr), ("narrow", narrow)):
+            q = 99
+            x = (img / (q + 1)).astype(np.float32)
+            cv2.imwrite(os.path.join(d, f"{name}.hdr"), x[:, :, [2, 1, 0]])
+            raw = open(os.path.join(d, f"{name}.hdr"), "rb").read()
+            out[f"{name}_hdr"] = img
+            out[f"{name}_rgbe"] = ro.parse_radiance(raw)
+            out[f"{name}_decoded"] = cv2.imread(os.path.join(d, f"{name}.hdr"), cv2.IMREAD_UNCHANGED)[:, :, ::-1].copy()
+    out["cv2_version"] = np.array(cv2.__version__)
+    np.savez_compressed(OUT / "rgbe_cv2.npz", **out)
+    print("wrote rgbe_cv2.npz (cv2", cv2.__version__, ")")
+
+
 if __name__ == "__main__":
+    rgbe_golden()
     main()

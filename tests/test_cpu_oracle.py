@@ -144,3 +144,39 @@ def test_oracle_loops_run_and_keep_quirks():
     assert not torch.equal(a, b)
     c = PO.single_gm_loop(u8, SO.PNDMOracle(), 0.18215 * torch.randn(1, 4, 8, 8), pe, ne, lat, num_inference_steps=4)
     assert c.shape == lat.shape and torch.isfinite(c).all()
+
+
+# ---- host tail: Radiance RGBE as cv2.imwrite quantises it (generate_hdr.py:27-30) ----------------------------------------
+def test_rgbe_oracle_matches_real_cv2_files(golden_dir):
+    """oracle/rgbe_oracle.py is pinned to bytes parsed out of files the real cv2.imwrite wrote (oracle/make_golden.py)."""
+    from oracle import rgbe_oracle as RO
+    g = np.load(golden_dir / "rgbe_cv2.npz")
+    for name in ("wide", "narrow"):
+        want = g[f"{name}_rgbe"]
+        got = RO.save_hdr_pixels(g[f"{name}_hdr"], 99)
+        assert np.array_equal(got, want), f"{name}: {int((got != want).any(-1).sum())} pixels differ"
+        assert np.array_equal(RO.rgbe2float(want), g[f"{name}_decoded"])
+    # edge pixels: below the 1e-32 cut-off -> all-zero RGBE; exact powers of two sit at mantissa 128
+    px = RO.float2rgbe(np.array([[0, 0, 0], [9e-33, 0, 0], [1, 1, 1], [0.5, 0.25, 0.125]], np.float32))
+    assert px.tolist() == [[0, 0, 0, 0], [0, 0, 0, 0], [128, 128, 128, 129], [128, 64, 32, 128]]
+
+
+def test_radiance_container_roundtrip_and_cv2_read(golden_dir, tmp_path):
+    """gm_diffusion_b200.hdr_io.pack_radiance (host code, no GPU): parse(pack(x)) == x for RLE-able and flat widths, and the real
+    cv2.imread decodes our file to exactly what it decodes the reference-written file to."""
+    from gm_diffusion_b200.hdr_io import pack_radiance
+    from oracle import rgbe_oracle as RO
+    rng = np.random.default_rng(3)
+    for H, W in ((3, 8), (2, 127), (2, 128), (3, 129), (1, 300), (4, 5), (2, 1)):
+        x = rng.integers(0, 256, (H, W, 4), dtype=np.uint8)
+        x[0, 0] = (2, 2, 0, W & 255)  # a first pixel that looks like an RLE marker must survive
+        assert np.array_equal(RO.parse_radiance(pack_radiance(x)), x), (H, W)
+    with pytest.raises(ValueError):
+        pack_radiance(np.zeros((4, 4, 3), np.uint8))
+    cv2 = pytest.importorskip("cv2")
+    g = np.load(golden_dir / "rgbe_cv2.npz")
+    for name in ("wide", "narrow"):
+        path = tmp_path / f"{name}.hdr"
+        path.write_bytes(pack_radiance(g[f"{name}_rgbe"]))
+        back = cv2.imread(str(path), cv2.IMREAD_UNCHANGED)[:, :, ::-1]
+        assert np.array_equal(back, g[f"{name}_decoded"]), name

@@ -3,6 +3,7 @@
 Gates (north_star): teacher-forced per-step UNet eps <= 1e-2 rel-L2; final HDR >= 40 dB PSNR in the log domain."""
 import math
 
+import numpy as np
 import pytest
 import torch
 
@@ -76,6 +77,12 @@ def test_dual_pipeline_config0(models, dual_pipe, graph):
                               num_inference_steps=4, guidance_scale=7.5, output_type="hdr")
     p = psnr_log(hdr_got.permute(0, 3, 1, 2), hdr_want)
     assert p >= 40.0, f"HDR log-domain PSNR {p:.1f} dB < 40 dB"
+    # output_type="disk": the same trajectory, emitted as the bytes the scripts write (generate_hdr.py:27-30,243-244)
+    from oracle import rgbe_oracle as RO
+    rgbe, s8, g8 = dual_pipe(prompt_embeds=pe, negative_prompt_embeds=ne, latents=lat.clone(), height=256, width=256,
+                             num_inference_steps=4, guidance_scale=7.5, output_type="disk")
+    assert rgbe.shape == (1, 256, 256, 4) and s8.shape == g8.shape == (1, 256, 256, 3) and rgbe.dtype == s8.dtype == torch.uint8
+    assert np.array_equal(rgbe.cpu().numpy(), RO.save_hdr_pixels(hdr_got.cpu().numpy(), 99))
 
 
 def test_teacher_forced_step_eps(models):
