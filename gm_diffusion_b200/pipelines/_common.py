@@ -118,6 +118,7 @@ class PipelineBase:
         self._interrupt = False
         self._num_timesteps = 0
         self.use_cuda_graph = True
+        self.skip_identical_cfg = True  # drop the uncond forward when negative_prompt_embeds == prompt_embeds (bit-exact)
         self._graphs: Dict[Any, Any] = {}
         self.graph_launches = 0  # kernels executed through CUDA-graph replays (the C-ABI counter only sees eager launches)
 

@@ -77,6 +77,12 @@ class StableDiffusionGMPipeline(PipelineBase):
             prompt_embeds=prompt_embeds, negative_prompt_embeds=negative_prompt_embeds, clip_skip=self.clip_skip)
         out_dtype = prompt_embeds.dtype
         do_cfg = self.do_classifier_free_guidance
+        if (do_cfg and self.skip_identical_cfg and guidance_rescale == 0.0 and negative_prompt_embeds is not None
+                and negative_prompt_embeds.shape == prompt_embeds.shape and torch.equal(negative_prompt_embeds, prompt_embeds)):
+            # the negative prompt IS the prompt — e.g. the SDR->HDR CLI's prompt=[""] with the default negative
+            # (generate_hdr.py:212-218).  Both CFG halves are then the same forward and eps_u + g*(eps_c - eps_u) == eps_c bit for
+            # bit (the kernels are deterministic and batch-independent), so the unconditional half is not run.
+            do_cfg = False
         B = batch_size * num_images_per_prompt
         timesteps, num_inference_steps = retrieve_timesteps(self.scheduler, num_inference_steps, device, timesteps, sigmas)
         # gm.py:1005-1015: 4 latent channels, spatial size from sdr_latent (height/width ignored)

@@ -127,6 +127,33 @@ def test_single_pipeline_config0(models):
     assert none is None and img.shape == (1, 3, 256, 256) and float(img.min()) >= 0 and float(img.max()) <= 1
 
 
+def test_identical_cfg_halves_skip_is_bit_exact(models, dual_pipe):
+    """with negative_prompt_embeds == prompt_embeds (the SDR->HDR CLI's prompt=[""], generate_hdr.py:212-218)
+    the uncond forward is skipped; the result must equal the full CFG path bit for bit, and the SDR UNet must run at half batch."""
+    from gm_diffusion_b200 import PNDMScheduler, StableDiffusionGMPipeline
+    _, u8, _ = models
+    pe, _, lat, sdr = _inputs()
+    pipe = StableDiffusionGMPipeline(vae=None, text_encoder=None, tokenizer=None, unet=dual_pipe.gm_unet, scheduler=PNDMScheduler())
+    kw = dict(prompt_embeds=pe, negative_prompt_embeds=pe.clone(), num_inference_steps=4, guidance_scale=7.5, output_type="latent")
+    outs, launches = {}, {}
+    for skip in (False, True):
+        pipe.skip_identical_cfg = skip
+        pipe.use_cuda_graph = False
+        from gm_diffusion_b200 import _lib as L
+        L.lib().gmd_reset_launch_count()
+        outs[skip] = pipe(sdr, latents=lat.clone(), **kw).images
+        launches[skip] = L.lib().gmd_launch_count()
+    assert torch.equal(outs[True], outs[False]), rel_l2(outs[True], outs[False])
+    dual_pipe.use_cuda_graph = False
+    d = {}
+    for skip in (False, True):
+        dual_pipe.skip_identical_cfg = skip
+        d[skip] = dual_pipe(prompt_embeds=pe, negative_prompt_embeds=pe.clone(), latents=lat.clone(), height=256, width=256,
+                            num_inference_steps=3, guidance_scale=7.5, output_type="latent")
+    dual_pipe.skip_identical_cfg = True
+    assert torch.equal(d[True][0], d[False][0]) and torch.equal(d[True][1], d[False][1])
+
+
 def test_dual_batch_sharding_independence(dual_pipe):
     """Images are independent trajectories: batch-of-2 == two batch-of-1 runs (what rank sharding relies on)."""
     pe, ne, lat, _ = _inputs(B=2)
