@@ -21,6 +21,7 @@ TMO_NONE, TMO_LINEAR, TMO_HARD_CLIP, TMO_MULOG, TMO_CUDA = 0, 1, 2, 3, 4
 HDR_EQ1, HDR_DENORM, HDR_CLAMP_OUT, HDR_GAMUT, HDR_EXP_GAIN = 1, 2, 4, 8, 16
 SCHED_LINEAR, SCHED_DDIM, SCHED_DDPM, SCHED_DPMPP = 0, 1, 2, 3
 EPI_BIAS, EPI_ROW_BIAS, EPI_RESIDUAL, EPI_GEGLU, EPI_OUT_F32, EPI_SCALE, EPI_RESIDUAL_F32 = 1, 2, 4, 8, 16, 32, 64
+CONV_PAD_END = 256
 
 _vp, _i64, _i32, _f32 = C.c_void_p, C.c_int64, C.c_int32, C.c_float
 
@@ -97,6 +98,8 @@ def lib() -> C.CDLL:
     L.gmd_latents_nchw_to_px.argtypes = [_vp, _vp, _i64, _i64, _vp]
     L.gmd_latents_px_to_nchw.argtypes = [_vp, _vp, _i64, _i64, _vp]
     L.gmd_pack_unet_input.argtypes = [_vp, _vp, _vp, _i64, _i32, _vp]
+    L.gmd_pack_image_nchw.argtypes = [_vp, _vp, _i64, _i64, _i32, _vp]
+    L.gmd_vae_sample.argtypes = [_vp, _vp, _vp, _i64, _f32, _vp]
     L.gmd_gemm_fwd.argtypes = [C.POINTER(GemmParams), _vp]
     L.gmd_conv_fwd.argtypes = [C.POINTER(ConvParams), _vp]
     L.gmd_groupnorm_silu.argtypes = [_vp, _i32, _vp, _i32, _vp, _vp, _vp, _i32, _i32, _i32, _f32, _i32, _i32, _vp, _vp]

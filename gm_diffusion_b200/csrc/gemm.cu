@@ -29,6 +29,7 @@ struct KernelArgs {
     int kb_src0;    // K blocks taken from A source 0 (the rest from source 1)
     // conv
     int ks, stride, upsample;
+    int pad_end;              // stride 2: taps start at input row/col 2*o (zero row/col appended at the end) instead of 2*o - 1
     int chunks0, chunks1;  // 64-channel blocks per tap from source 0 / 1
     int ctot;              // C0 + C1 (weight K pitch per tap)
     int bw, bh, bn;        // pixel box of one 128-row tile (bw*bh*bn == 128)
@@ -232,8 +233,13 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__ 
                         const CUtensorMap* map;
                         if (args.stride == 2) {
                             // input row 2*oh - 1 + r: r=0 -> odd plane, oh-1; r=1 -> even plane, oh; r=2 -> odd plane, oh
-                            const int ph = (r == 1) ? 0 : 1, pw = (sx == 1) ? 0 : 1;
+                            int ph = (r == 1) ? 0 : 1, pw = (sx == 1) ? 0 : 1;
                             dh = (r == 0) ? -1 : 0; dw = (sx == 0) ? -1 : 0;
+                            if (args.pad_end) {
+                                // input row 2*oh + r: r=0 -> even plane, oh; r=1 -> odd plane, oh; r=2 -> even plane, oh+1 (TMA zero-fills past the end)
+                                ph = (r == 1) ? 1 : 0; pw = (sx == 1) ? 1 : 0;
+                                dh = (r == 2) ? 1 : 0; dw = (sx == 2) ? 1 : 0;
+                            }
                             const int sel = ph * 2 + pw;
                             map = sel == 0 ? &map_a0 : sel == 1 ? &map_a1 : sel == 2 ? &map_a2 : &map_a3;
                             c = cc * BK;
@@ -801,6 +807,8 @@ extern "C" int gmd_conv_fwd(const gmd_conv_params* p, void* stream) {
     KernelArgs a{};
     a.mode = 1;
     a.ks = p->ksize; a.stride = p->stride; a.upsample = p->upsample;
+    a.pad_end = (p->flags & GMD_CONV_PAD_END) ? 1 : 0;
+    if (a.pad_end && p->stride != 2) { set_last_error("gmd_conv_fwd: GMD_CONV_PAD_END needs stride 2"); return kErrInvalid; }
     a.chunks0 = (p->C0 + BK - 1) / BK; a.chunks1 = (C1 + BK - 1) / BK;
     a.ctot = ctot;
     a.num_kb = taps * (a.chunks0 + a.chunks1);
@@ -814,7 +822,7 @@ extern "C" int gmd_conv_fwd(const gmd_conv_params* p, void* stream) {
     a.ld_row_bias = p->ld_row_bias;
     a.residual = (p->flags & GMD_EPI_RESIDUAL) ? p->residual : nullptr;
     a.ldr = p->Cout;
-    a.flags = p->flags & ~GMD_EPI_GEGLU;
+    a.flags = p->flags & ~(GMD_EPI_GEGLU | GMD_CONV_PAD_END);
     a.alpha = 1.0f;
     if ((p->flags & GMD_EPI_BIAS) && !p->bias) { set_last_error("gmd_conv_fwd: BIAS flag without bias"); return kErrInvalid; }
     if ((p->flags & GMD_EPI_RESIDUAL) && !p->residual) { set_last_error("gmd_conv_fwd: RESIDUAL flag without residual"); return kErrInvalid; }

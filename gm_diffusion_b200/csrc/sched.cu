@@ -201,6 +201,39 @@ __global__ void __launch_bounds__(256) pack_unet_input_kernel(const float* __res
     store_row(dst, i, ch, ld4(lead, i), tail ? ld4(tail, i) : zero);
 }
 
+// image NCHW fp32 [B,C,H,W], C <= 8  ->  NHWC bf16 [B,H,W,8] (zero-padded channels): the VAE encoder's conv_in operand
+__global__ void __launch_bounds__(256) pack_image_kernel(const float* __restrict__ src, void* dst, int64_t batch, int64_t hw, int c) {
+    int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i >= batch * hw) return;
+    int64_t b = i / hw, p = i - b * hw;
+    const float* s = src + b * c * hw + p;
+    float v[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) v[k] = k < c ? __ldg(s + k * hw) : 0.0f;
+    store_row(dst, i, 8, make_float4(v[0], v[1], v[2], v[3]), make_float4(v[4], v[5], v[6], v[7]));
+}
+
+// diffusers DiagonalGaussianDistribution (what `vae.encode(x).latent_dist` is, generate_hdr.py:208): moments [n_px, 8] =
+// (mean[4], logvar[4]); logvar = clamp(logvar, -30, 20); std = exp(0.5 * logvar); sample = mean + std * noise; mode = mean.
+__global__ void __launch_bounds__(256) vae_sample_kernel(const float* __restrict__ moments, const float* __restrict__ noise,
+                                                         float* __restrict__ out, int64_t n_px, float scale) {
+    int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i >= n_px) return;
+    F4 mean = ld(moments, 2 * i), lv = ld(moments, 2 * i + 1), z;
+    if (noise) z = ld(noise, i);
+    F4 o;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        float v = mean.v[k];
+        if (noise) {
+            float l = fminf(fmaxf(lv.v[k], -30.0f), 20.0f);
+            v = ADD(v, MUL(expf(MUL(0.5f, l)), z.v[k]));
+        }
+        o.v[k] = scale == 1.0f ? v : MUL(v, scale);
+    }
+    st4(out, i, f4(o));
+}
+
 inline bool al16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
 
 }  // namespace
@@ -271,4 +304,21 @@ extern "C" int gmd_pack_unet_input(const float* lead, const float* tail, void* d
     pack_unet_input_kernel<<<(unsigned)((n_px + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(lead, tail, dst, n_px, ch);
     count_launch(1);
     return check_launch("pack_unet_input");
+}
+
+extern "C" int gmd_pack_image_nchw(const float* src, void* dst, int64_t batch, int64_t hw, int32_t channels, void* stream) {
+    using namespace gmd;
+    if (batch * hw == 0) return kOk;
+    if (!src || !dst || channels < 1 || channels > 8 || !al16(dst)) { set_last_error("gmd_pack_image_nchw: bad arguments"); return kErrInvalid; }
+    pack_image_kernel<<<(unsigned)((batch * hw + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(src, dst, batch, hw, channels);
+    count_launch(1);
+    return check_launch("pack_image_nchw");
+}
+extern "C" int gmd_vae_sample(const float* moments, const float* noise, float* out, int64_t n_px, float scale, void* stream) {
+    using namespace gmd;
+    if (n_px == 0) return kOk;
+    if (!moments || !out || !al16(moments) || !al16(noise) || !al16(out)) { set_last_error("gmd_vae_sample: bad arguments"); return kErrInvalid; }
+    vae_sample_kernel<<<(unsigned)((n_px + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(moments, noise, out, n_px, scale);
+    count_launch(1);
+    return check_launch("vae_sample");
 }

@@ -142,8 +142,10 @@ def gemm(a: torch.Tensor, w: torch.Tensor, *, bias: Optional[torch.Tensor] = Non
 
 def conv2d(x: torch.Tensor, w: torch.Tensor, cout: int, *, ksize: int = 3, stride: int = 1, upsample: bool = False,
            x1: Optional[torch.Tensor] = None, bias: Optional[torch.Tensor] = None, row_bias: Optional[torch.Tensor] = None,
-           residual: Optional[torch.Tensor] = None, out: Optional[torch.Tensor] = None, out_f32: bool = False, splitk: bool = False) -> torch.Tensor:
-    """NHWC bf16 convolution as implicit GEMM (3x3 pad 1 stride 1/2, optional folded nearest-2x upsample)."""
+           residual: Optional[torch.Tensor] = None, out: Optional[torch.Tensor] = None, out_f32: bool = False, splitk: bool = False,
+           pad_end: bool = False) -> torch.Tensor:
+    """NHWC bf16 convolution as implicit GEMM (3x3 pad 1 stride 1/2, optional folded nearest-2x upsample).  `pad_end` (stride 2):
+    the AutoencoderKL encoder's asymmetric padding — no leading pad, one zero row/column at the bottom/right."""
     tiled = isinstance(w, TiledWeight)
     wt = w.data if tiled else w
     L.require_cuda(x, wt)
@@ -182,6 +184,9 @@ def conv2d(x: torch.Tensor, w: torch.Tensor, cout: int, *, ksize: int = 3, strid
         p.residual = residual.data_ptr()
     if out.dtype == torch.float32:
         flags |= L.EPI_OUT_F32
+    if pad_end:
+        assert stride == 2
+        flags |= L.CONV_PAD_END
     p.flags = flags
     if splitk:  # opt-in, see gemm()
         ws = splitk_workspace(x.device)

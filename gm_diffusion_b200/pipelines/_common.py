@@ -12,7 +12,7 @@ import torch
 from .. import _lib as L
 from .. import schedulers as S
 from ..unet import B200UNet
-from ..vae import B200VaeDecoder
+from ..vae import B200Vae, B200VaeDecoder
 
 bf16 = torch.bfloat16
 
@@ -65,7 +65,8 @@ def as_b200_vae(vae, device) -> Optional[B200VaeDecoder]:
     if vae is None or isinstance(vae, B200VaeDecoder):
         return vae
     if hasattr(vae, "state_dict"):
-        return B200VaeDecoder.from_module(vae, device=device)
+        has_encoder = any(k.startswith("encoder.") for k in vae.state_dict())
+        return (B200Vae if has_encoder else B200VaeDecoder).from_module(vae, device=device)
     raise TypeError(f"vae must be a B200VaeDecoder or expose a diffusers-style state_dict(), got {type(vae)}")
 
 

@@ -122,6 +122,33 @@ def sd_vae_decoder_state_dict(seed: int = 0, device="cuda", block_out_channels: 
     return g.sd
 
 
+def sd_vae_state_dict(seed: int = 0, device="cuda", block_out_channels: Tuple[int, ...] = (128, 256, 512, 512)) -> Dict[str, torch.Tensor]:
+    """Full AutoencoderKL (encoder + quant_conv + decoder) with diffusers key names."""
+    sd = sd_vae_decoder_state_dict(seed, device, block_out_channels)
+    g = _Gen(seed + 1, device)
+    ch = block_out_channels
+    e = "encoder."
+    g.conv(e + "conv_in", 3, ch[0], 3)
+    c = ch[0]
+    for i, co in enumerate(ch):
+        for j in range(2):
+            g.resnet(e + f"down_blocks.{i}.resnets.{j}.", c if j == 0 else co, co, 0)
+        if i < len(ch) - 1:
+            g.conv(e + f"down_blocks.{i}.downsamplers.0.conv", co, co, 3)
+        c = co
+    g.resnet(e + "mid_block.resnets.0.", c, c, 0)
+    a = e + "mid_block.attentions.0."
+    g.norm(a + "group_norm", c)
+    for n in ("to_q", "to_k", "to_v", "to_out.0"):
+        g.linear(a + n, c, c)
+    g.resnet(e + "mid_block.resnets.1.", c, c, 0)
+    g.norm(e + "conv_norm_out", c)
+    g.conv(e + "conv_out", c, 8, 3)
+    g.conv("quant_conv", 8, 8, 1)
+    sd.update(g.sd)
+    return sd
+
+
 def widen_conv_in_state_dict(sd4: Dict[str, torch.Tensor]) -> Dict[str, torch.Tensor]:
     """scripts/stage2/train_gm_unet.py:658-677 `_replace_unet_conv_in`: 4 -> 8 input channels (tiled x0.5)."""
     sd = dict(sd4)

@@ -150,6 +150,12 @@ int gmd_latents_nchw_to_px(const float* src, float* dst, int64_t batch, int64_t 
 int gmd_latents_px_to_nchw(const float* src, float* dst, int64_t batch, int64_t hw, void* stream);
 /* fp32 [n_px,4] -> bf16 [n_px, ch] zero-padded rows, optional second source in ch4-7 */
 int gmd_pack_unet_input(const float* lead, const float* tail, void* dst, int64_t n_px, int32_t ch, void* stream);
+/* SDR->HDR entry (`pipeline.vae.encode(sdr_image).latent_dist.sample()`, scripts/inference/generate_hdr.py:208):
+   image NCHW fp32 [batch, channels<=8, hw] -> NHWC bf16 [batch, hw, 8] (zero-padded), the encoder conv_in operand */
+int gmd_pack_image_nchw(const float* src, void* dst, int64_t batch, int64_t hw, int32_t channels, void* stream);
+/* diffusers DiagonalGaussianDistribution on the encoder moments fp32 [n_px, 8] = (mean[4], logvar[4]):
+   out[n_px,4] = scale * (mean + exp(0.5*clamp(logvar,-30,20)) * noise); noise NULL -> mode() (= mean) */
+int gmd_vae_sample(const float* moments, const float* noise, float* out, int64_t n_px, float scale, void* stream);
 
 /* ------------------------------------------------------------------------------------------ */
 /* (b) convolutions / linears as tcgen05 implicit GEMM; GroupNorm+SiLU; LayerNorm               */
@@ -163,7 +169,10 @@ enum gmd_epilogue_flags {
     GMD_EPI_GEGLU = 8,      /* out[m, j] = (acc[m, j] + b[j]) * gelu(acc[m, j + N/2] + b[j + N/2]); weight rows interleaved per tile */
     GMD_EPI_OUT_F32 = 16,   /* write fp32 instead of bf16 */
     GMD_EPI_SCALE = 32,     /* acc *= alpha before everything else */
-    GMD_EPI_RESIDUAL_F32 = 64 /* the residual tensor is fp32 (the transformer token stream is kept in fp32) */
+    GMD_EPI_RESIDUAL_F32 = 64, /* the residual tensor is fp32 (the transformer token stream is kept in fp32) */
+    GMD_CONV_PAD_END = 256     /* gmd_conv_fwd, stride 2 only: no leading pad, one zero row/column appended at the bottom/right —
+                                  diffusers Downsample2D(padding=0) + F.pad(x,(0,1,0,1)) of the AutoencoderKL encoder
+                                  (`pipeline.vae.encode`, scripts/inference/generate_hdr.py:208) */
 };
 
 typedef struct gmd_gemm_params {

@@ -77,6 +77,82 @@ class Decoder(nn.Module):
         return self.conv_out(F.silu(self.conv_norm_out(x)))
 
 
+class VaeDown(nn.Module):
+    """diffusers DownEncoderBlock2D: resnets without temb, then Downsample2D(padding=0): F.pad(x, (0,1,0,1)) + 3x3 stride-2 conv."""
+
+    def __init__(self, cin, cout, add_down):
+        super().__init__()
+        self.resnets = nn.ModuleList([ResnetBlock2D(cin if i == 0 else cout, cout, temb_dim=None, eps=1e-6) for i in range(2)])
+        self.downsamplers = nn.ModuleList([nn.Module()]) if add_down else None
+        if add_down:
+            self.downsamplers[0].conv = nn.Conv2d(cout, cout, 3, stride=2, padding=0)
+
+    def forward(self, x):
+        for r in self.resnets:
+            x = r(x)
+        if self.downsamplers is not None:
+            x = self.downsamplers[0].conv(F.pad(x, (0, 1, 0, 1), mode="constant", value=0))
+        return x
+
+
+class Encoder(nn.Module):
+    def __init__(self, ch=(128, 256, 512, 512), cin=3, latent=4):
+        super().__init__()
+        self.conv_in = nn.Conv2d(cin, ch[0], 3, padding=1)
+        downs, c = [], ch[0]
+        for i, co in enumerate(ch):
+            downs.append(VaeDown(c, co, add_down=i < len(ch) - 1))
+            c = co
+        self.down_blocks = nn.ModuleList(downs)
+        self.mid_block = VaeMid(ch[-1])
+        self.conv_norm_out = nn.GroupNorm(32, ch[-1], eps=1e-6)
+        self.conv_out = nn.Conv2d(ch[-1], 2 * latent, 3, padding=1)
+
+    def forward(self, x):
+        x = self.conv_in(x)
+        for d in self.down_blocks:
+            x = d(x)
+        return self.conv_out(F.silu(self.conv_norm_out(self.mid_block(x))))
+
+
+class DiagonalGaussian:
+    """diffusers DiagonalGaussianDistribution (`vae.encode(x).latent_dist`, generate_hdr.py:208)."""
+
+    def __init__(self, moments):
+        self.mean, logvar = torch.chunk(moments, 2, dim=1)
+        self.logvar = torch.clamp(logvar, -30.0, 20.0)
+        self.std = torch.exp(0.5 * self.logvar)
+
+    def sample(self, generator=None, noise=None):
+        if noise is None:
+            noise = torch.randn(self.mean.shape, generator=generator, device=self.mean.device, dtype=self.mean.dtype)
+        return self.mean + self.std * noise
+
+    def mode(self):
+        return self.mean
+
+
+class VaeOracle(nn.Module):
+    """Full AutoencoderKL (SD1.5 config): `encode(x)` -> DiagonalGaussian, `decode(z)` as VaeDecoderOracle."""
+
+    def __init__(self, ch=(128, 256, 512, 512)):
+        super().__init__()
+        self.encoder = Encoder(ch)
+        self.quant_conv = nn.Conv2d(8, 8, 1)
+        self.post_quant_conv = nn.Conv2d(4, 4, 1)
+        self.decoder = Decoder(ch)
+        self.config = dict(scaling_factor=SCALING_FACTOR, block_out_channels=tuple(ch))
+
+    def moments(self, x):
+        return self.quant_conv(self.encoder(x))
+
+    def encode(self, x):
+        return DiagonalGaussian(self.moments(x))
+
+    def decode(self, z):
+        return self.decoder(self.post_quant_conv(z))
+
+
 class VaeDecoderOracle(nn.Module):
     """`decode(z)` == AutoencoderKL.decode(z, return_dict=False)[0]; the caller divides by scaling_factor."""
 

@@ -128,6 +128,24 @@ def test_unet_oracle_parameter_counts_and_shapes():
     v = VaeDecoderOracle(ch=(32, 64, 64, 64)).eval()
     with torch.no_grad():
         assert v.decode(torch.randn(1, 4, 4, 4)).shape == (1, 3, 32, 32)
+    # full AutoencoderKL: the public SD VAE figures (83 653 863 parameters = encoder 34 163 592 + decoder 49 490 179 + 72 + 20)
+    from oracle.vae_oracle import VaeOracle
+    with torch.device("meta"):
+        full = VaeOracle()
+        assert count_params(full.encoder) == 34_163_592 and count_params(full.decoder) == 49_490_179
+        assert count_params(full) == 83_653_863
+    torch.manual_seed(0)
+    e = VaeOracle(ch=(32, 64, 64, 64)).eval()
+    with torch.no_grad():
+        d = e.encode(torch.randn(1, 3, 32, 48))
+        assert d.mean.shape == (1, 4, 4, 6) and torch.equal(d.mode(), d.mean)
+        z = d.sample(generator=torch.Generator().manual_seed(1))
+        n = torch.randn(1, 4, 4, 6, generator=torch.Generator().manual_seed(1))
+        torch.testing.assert_close(z, d.mean + torch.exp(0.5 * d.logvar) * n)
+    from gm_diffusion_b200.random_init import sd_vae_state_dict
+    sd = sd_vae_state_dict(0, device="cpu", block_out_channels=(32, 64, 64, 64))
+    want = {k: tuple(t.shape) for k, t in e.state_dict().items()}
+    assert {k: tuple(t.shape) for k, t in sd.items()} == want  # the bench's random-init VAE has diffusers' key names and shapes
 
 
 def test_oracle_loops_run_and_keep_quirks():

@@ -156,6 +156,20 @@ def test_conv_stride2_upsample_concat_epilogue():
     check(ops.conv2d(x.cuda(), ops.pack_conv_weight_tiled(w.cuda()), 320, upsample=True, bias=b.cuda()), _conv_ref(x, w, b, upsample=True), what="upsample tiled-W")
 
 
+@pytest.mark.parametrize("N,H,W,C,Cout", [(2, 64, 64, 128, 128), (1, 32, 48, 256, 256), (1, 16, 16, 512, 512)])
+def test_conv_stride2_pad_end(N, H, W, C, Cout):
+    """AutoencoderKL encoder downsample: F.pad(x, (0,1,0,1)) + 3x3 stride-2 conv with padding 0 (diffusers Downsample2D(padding=0))."""
+    from gm_diffusion_b200 import ops
+    g = torch.Generator().manual_seed(H + C)
+    x = torch.randn(N, H, W, C, generator=g).to(bf)
+    w = (torch.randn(Cout, C, 3, 3, generator=g) / math.sqrt(9 * C)).to(bf)
+    b = torch.randn(Cout, generator=g)
+    ref = F.conv2d(F.pad(x.float().permute(0, 3, 1, 2), (0, 1, 0, 1)), w.float(), b, stride=2, padding=0).permute(0, 2, 3, 1)
+    got = ops.conv2d(x.cuda(), ops.pack_conv_weight_tiled(w.cuda()), Cout, stride=2, pad_end=True, bias=b.cuda())
+    assert got.shape == (N, H // 2, W // 2, Cout)
+    check(got, ref, what="stride 2, bottom/right pad")
+
+
 @pytest.mark.parametrize("B,H,Nq,Nk,d", [(2, 8, 4096, 4096, 40), (2, 8, 1024, 1024, 80), (2, 8, 256, 256, 160), (3, 8, 64, 64, 160),
                                          (2, 8, 4096, 77, 40), (2, 8, 1024, 77, 80), (2, 8, 256, 77, 160), (1, 8, 200, 130, 40)])
 def test_attention(B, H, Nq, Nk, d):

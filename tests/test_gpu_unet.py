@@ -86,3 +86,37 @@ def test_vae_decoder_parity():
     assert got.shape == want.shape
     r = rel_l2(got, want)
     assert r < 3e-2, f"VAE decode rel-L2 {r:.3e}"  # ~40 bf16 conv/GN layers at up to 512 channels; the HDR PSNR gate covers the end-to-end effect
+
+
+def test_vae_encoder_parity_and_latent_dist():
+    """`pipeline.vae.encode(sdr_image).latent_dist.sample()` (generate_hdr.py:207-209) on the B200 kernels vs the fp32 oracle."""
+    from gm_diffusion_b200 import B200Vae
+    from gm_diffusion_b200 import _lib as L
+    from oracle.vae_oracle import VaeOracle
+    torch.manual_seed(2)
+    ref = VaeOracle().eval().cuda()
+    mine = B200Vae.from_module(ref)
+    g = torch.Generator().manual_seed(5)
+    img = (torch.rand(2, 3, 128, 192, generator=g) * 2 - 1).cuda()
+    with torch.no_grad():
+        want = ref.moments(img)                                   # [B,8,h,w]
+    L.lib().gmd_reset_launch_count()
+    dist = mine.encode(img).latent_dist
+    assert L.lib().gmd_launch_count() > 50                        # the encoder ran on the library's kernels
+    assert dist.mean.shape == (2, 4, 16, 24) and dist.parameters.dtype == torch.float32
+    r_mean = rel_l2(dist.mean, want[:, :4])
+    r_all = rel_l2(dist.parameters.permute(0, 3, 1, 2), want)
+    assert r_mean < 3e-2 and r_all < 3e-2, f"encoder moments rel-L2 mean {r_mean:.3e} all {r_all:.3e}"
+    # sample / mode: exact DiagonalGaussianDistribution arithmetic on the product's own moments
+    noise = torch.randn(2, 4, 16, 24, generator=g).cuda()
+    got = dist.sample(noise=noise)
+    lv = dist.logvar.clamp(-30.0, 20.0)
+    torch.testing.assert_close(got, dist.mean + torch.exp(0.5 * lv) * noise, rtol=2e-6, atol=2e-6)
+    assert torch.equal(dist.mode(), dist.mean.contiguous())
+    a = dist.sample(generator=torch.Generator().manual_seed(9))   # CPU generator: CPU draw moved to the device, like randn_tensor
+    b = dist.sample(noise=torch.randn(2, 4, 16, 24, generator=torch.Generator().manual_seed(9)).cuda())
+    assert torch.equal(a, b)
+    with pytest.raises(ValueError):
+        mine.encode(torch.zeros(1, 3, 100, 128, device="cuda"))
+    # encode -> decode keeps the image geometry (SDR -> latent -> image)
+    assert mine.decode(dist.mode()).shape == (2, 3, 128, 192)
