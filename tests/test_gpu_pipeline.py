@@ -154,6 +154,45 @@ def test_identical_cfg_halves_skip_is_bit_exact(models, dual_pipe):
     assert torch.equal(d[True][0], d[False][0]) and torch.equal(d[True][1], d[False][1])
 
 
+def test_sdr_to_hdr_cli_flow(models, dual_pipe, tmp_path):
+    """The reference's SDR->HDR CLI, line by line (scripts/inference/generate_hdr.py:205-282) with the drop-in classes:
+    vae.encode(sdr).latent_dist.sample() * scaling_factor -> single pipeline with prompt_embeds == negative (prompt=[""])
+    -> decode both -> de-normalise -> Eq.(1) qmax 99 -> save_hdr_image; against the same flow through the oracles."""
+    from gm_diffusion_b200 import B200Vae, PNDMScheduler, StableDiffusionGMPipeline, reconstruct_for_disk, save_hdr_image
+    from oracle import pipeline_oracle as PO
+    from oracle import rgbe_oracle as RO
+    from oracle.schedulers_oracle import PNDMOracle
+    from oracle.vae_oracle import VaeOracle
+    _, u8, _ = models
+    torch.manual_seed(6)
+    vae_o = VaeOracle().eval().cuda()
+    vae = B200Vae.from_module(vae_o)
+    pipe = StableDiffusionGMPipeline(vae=vae, text_encoder=None, tokenizer=None, unet=dual_pipe.gm_unet, scheduler=PNDMScheduler())
+    g = torch.Generator().manual_seed(21)
+    sdr_image = (torch.rand(1, 3, 256, 256, generator=g) * 2 - 1).cuda()
+    enc_noise = torch.randn(1, 4, 32, 32, generator=g).cuda()
+    pe = torch.randn(1, 77, 768, generator=g).cuda()          # stands in for CLIP("") on both CFG halves
+    lat = torch.randn(1, 4, 32, 32, generator=g).cuda()
+    sf = pipe.vae.config.scaling_factor
+    # oracle flow
+    with torch.no_grad():
+        sdr_lat_o = vae_o.encode(sdr_image).sample(noise=enc_noise) * sf
+        gm_lat_o = PO.single_gm_loop(u8, PNDMOracle(), sdr_lat_o, pe, pe, lat.clone(), num_inference_steps=4, guidance_scale=7.5)
+        _, _, hdr_o = PO.decode_and_reconstruct(vae_o, sdr_lat_o, gm_lat_o, qmax=99.0)
+    # product flow
+    sdr_lat = pipe.vae.encode(sdr_image).latent_dist.sample(noise=enc_noise) * sf
+    assert rel_l2(sdr_lat, sdr_lat_o) < 3e-2
+    gm_lat = pipe(sdr_lat, prompt_embeds=pe, negative_prompt_embeds=pe.clone(), latents=lat.clone(), num_inference_steps=4,
+                  output_type="latent").images[0].unsqueeze(0)
+    sdr_dec = pipe.vae.decode(sdr_lat / sf)
+    gm_dec = pipe.vae.decode(gm_lat / sf)
+    rgbe, s8, g8, hdr = reconstruct_for_disk(sdr_dec, gm_dec, 99, return_hdr=True)
+    p = psnr_log(hdr, hdr_o)
+    assert p >= 40.0, f"SDR->HDR flow: HDR log-domain PSNR {p:.1f} dB < 40 dB"
+    path = save_hdr_image(hdr[0].permute(1, 2, 0).contiguous(), str(tmp_path), "hdr_test.hdr", 99)
+    assert np.array_equal(RO.parse_radiance(open(path, "rb").read()), rgbe[0].cpu().numpy())
+
+
 def test_dual_batch_sharding_independence(dual_pipe):
     """Images are independent trajectories: batch-of-2 == two batch-of-1 runs (what rank sharding relies on)."""
     pe, ne, lat, _ = _inputs(B=2)
