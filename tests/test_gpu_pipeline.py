@@ -193,6 +193,24 @@ def test_sdr_to_hdr_cli_flow(models, dual_pipe, tmp_path):
     assert np.array_equal(RO.parse_radiance(open(path, "rb").read()), rgbe[0].cpu().numpy())
 
 
+def test_single_pipeline_1024_config3(models, dual_pipe):
+    """BASELINE.json config 3: the SDR-conditioned single pipeline at 1024x1024 (latent 128x128, 16384 tokens at level 0)."""
+    from gm_diffusion_b200 import PNDMScheduler, StableDiffusionGMPipeline
+    from oracle import pipeline_oracle as PO
+    from oracle.schedulers_oracle import PNDMOracle
+    _, u8, _ = models
+    pe, ne, lat, sdr = _inputs(hw=128)
+    with torch.no_grad():
+        want = PO.single_gm_loop(u8, PNDMOracle(), sdr, pe, ne, lat.clone(), num_inference_steps=2, guidance_scale=7.5)
+    torch.cuda.empty_cache()
+    pipe = StableDiffusionGMPipeline(vae=None, text_encoder=None, tokenizer=None, unet=dual_pipe.gm_unet, scheduler=PNDMScheduler())
+    out = pipe(sdr, prompt_embeds=pe, negative_prompt_embeds=ne, latents=lat.clone(), num_inference_steps=2, guidance_scale=7.5,
+               output_type="latent").images
+    assert out.shape == (1, 4, 128, 128)
+    r = rel_l2(out, want)
+    assert r < 3e-2, f"1024x1024 single pipeline final latents rel-L2 {r:.3e}"
+
+
 def test_dual_batch_sharding_independence(dual_pipe):
     """Images are independent trajectories: batch-of-2 == two batch-of-1 runs (what rank sharding relies on)."""
     pe, ne, lat, _ = _inputs(B=2)
