@@ -689,6 +689,14 @@ int plan_splitk(int64_t tiles, int num_kb, int64_t rows, int N, const void* work
     return ks < 2 ? 1 : ks;
 }
 
+// Split rule for the low-resolution convolutions (8x8 and below: 32-64 output tiles on 148 SMs, 180-360 k-blocks each, every CTA
+// bound by its own operand ingest).  It depends only on the per-image geometry and K — never on the batch — so an image goes
+// through the same summation order whatever batch it is part of, and image sharding stays bit-exact.
+int conv_splitk_rule(int Ho, int Wo, int num_kb, int Cout, bool plain_layout) {
+    if (!plain_layout || (Cout % 4) || Ho * Wo > 64 || num_kb < 64) return 1;
+    return 4;
+}
+
 int launch_finalize(const KernelArgs& a, const float* ws, int ksplit, int64_t rows, int N, const float* bias, const float* row_bias,
                     int64_t ld_row_bias, int64_t rows_per_sample, const void* residual, bool res_f32, void* out, bool out_f32, cudaStream_t st) {
     int64_t items = rows * (N / 4);
@@ -878,8 +886,31 @@ extern "C" int gmd_conv_fwd(const gmd_conv_params* p, void* stream) {
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     const int64_t tiles_m = (int64_t)a.tiles_w * a.tiles_h * tiles_img, tiles_nn = (p->Cout + bnt - 1) / bnt;
     const int64_t rows = (int64_t)p->N * Ho * Wo;
-    const int ks = plan_splitk(tiles_m * tiles_nn, a.num_kb, rows, p->Cout, p->workspace, p->workspace_bytes, !p->upsample);
+    const int ks = p->workspace ? conv_splitk_rule(Ho, Wo, a.num_kb, p->Cout, !p->upsample && p->stride == 1) : 1;
     if (ks > 1) {
+        // the fp32 partial planes of the whole batch must fit the workspace; otherwise run the batch in image chunks (whole tiles),
+        // which leaves every image's arithmetic unchanged
+        const int64_t per_img = (int64_t)ks * Ho * Wo * p->Cout * 4;
+        int64_t fit = p->workspace_bytes / per_img;
+        if (fit < p->N) {
+            fit = fit / bn * bn;
+            if (fit < 1) { set_last_error("gmd_conv_fwd: split-K workspace (%lld B) cannot hold one tile of %d images", (long long)p->workspace_bytes, bn); return kErrInvalid; }
+            for (int64_t n0 = 0; n0 < p->N; n0 += fit) {
+                gmd_conv_params q = *p;
+                q.N = (int32_t)((p->N - n0) < fit ? (p->N - n0) : fit);
+                q.x0 = static_cast<const __nv_bfloat16*>(p->x0) + n0 * p->H * p->W * p->C0;
+                if (p->x1) q.x1 = static_cast<const __nv_bfloat16*>(p->x1) + n0 * p->H * p->W * C1;
+                const int64_t o = n0 * Ho * Wo * p->Cout;
+                q.out = (p->flags & GMD_EPI_OUT_F32) ? static_cast<void*>(static_cast<float*>(p->out) + o) : static_cast<void*>(static_cast<__nv_bfloat16*>(p->out) + o);
+                if (p->residual)
+                    q.residual = (p->flags & GMD_EPI_RESIDUAL_F32) ? static_cast<const void*>(static_cast<const float*>(p->residual) + o)
+                                                                   : static_cast<const void*>(static_cast<const __nv_bfloat16*>(p->residual) + o);
+                if (p->row_bias) q.row_bias = p->row_bias + n0 * p->ld_row_bias;
+                int rc = gmd_conv_fwd(&q, stream);
+                if (rc) return rc;
+            }
+            return kOk;
+        }
         KernelArgs b = a;
         b.ksplit = ks; b.kb_per_split = (a.num_kb + ks - 1) / ks; b.split_stride_o = rows * p->Cout;
         b.out = p->workspace; b.ldo = p->Cout; b.bias = nullptr; b.row_bias = nullptr; b.residual = nullptr; b.flags = GMD_EPI_OUT_F32;

@@ -72,7 +72,7 @@ def splitk_workspace(device) -> torch.Tensor:
     key = torch.device(device).index or 0
     ws = _WS.get(key)
     if ws is None:
-        ws = torch.empty(64 << 20, dtype=torch.uint8, device=device)
+        ws = torch.empty(128 << 20, dtype=torch.uint8, device=device)
         _WS[key] = ws
     return ws
 
@@ -131,9 +131,9 @@ def gemm(a: torch.Tensor, w: torch.Tensor, *, bias: Optional[torch.Tensor] = Non
         p.alpha = float(alpha)
     p.flags = flags
     if splitk and not batched:
-        # opt-in: the number of K splits depends on the tile count, i.e. on M — it would make a sample's result depend on the
-        # batch it is computed in (summation order), which the sharded pipelines must not do.  Measured gain on B200: none
-        # (profiles/prof_splitk.py: the few-tile long-K layers are bound by the aggregate L2 line-fetch rate, not by the K loop).
+        # opt-in for GEMMs: here the number of K splits depends on the tile count, i.e. on M — it would make a sample's result
+        # depend on the batch it is computed in (summation order), which the sharded pipelines must not do.  (The convolution
+        # entry point uses a batch-independent rule instead and is on by default, see conv2d.)
         ws = splitk_workspace(a.device)
         p.workspace, p.workspace_bytes = ws.data_ptr(), ws.numel()
     L.check(L.lib().gmd_gemm_fwd(C.byref(p), L.current_stream()), "gmd_gemm_fwd")
@@ -142,7 +142,7 @@ def gemm(a: torch.Tensor, w: torch.Tensor, *, bias: Optional[torch.Tensor] = Non
 
 def conv2d(x: torch.Tensor, w: torch.Tensor, cout: int, *, ksize: int = 3, stride: int = 1, upsample: bool = False,
            x1: Optional[torch.Tensor] = None, bias: Optional[torch.Tensor] = None, row_bias: Optional[torch.Tensor] = None,
-           residual: Optional[torch.Tensor] = None, out: Optional[torch.Tensor] = None, out_f32: bool = False, splitk: bool = False,
+           residual: Optional[torch.Tensor] = None, out: Optional[torch.Tensor] = None, out_f32: bool = False, splitk: bool = True,
            pad_end: bool = False) -> torch.Tensor:
     """NHWC bf16 convolution as implicit GEMM (3x3 pad 1 stride 1/2, optional folded nearest-2x upsample).  `pad_end` (stride 2):
     the AutoencoderKL encoder's asymmetric padding — no leading pad, one zero row/column at the bottom/right."""
@@ -188,7 +188,9 @@ def conv2d(x: torch.Tensor, w: torch.Tensor, cout: int, *, ksize: int = 3, strid
         assert stride == 2
         flags |= L.CONV_PAD_END
     p.flags = flags
-    if splitk:  # opt-in, see gemm()
+    if splitk:
+        # the library splits K four ways for the <= 8x8-resolution layers (32-64 tiles on 148 SMs otherwise: 79 -> 32 us per conv,
+        # profiles/prof_splitk.py); the rule looks only at the per-image geometry, so results do not depend on the batch
         ws = splitk_workspace(x.device)
         p.workspace, p.workspace_bytes = ws.data_ptr(), ws.numel()
     L.check(L.lib().gmd_conv_fwd(C.byref(p), L.current_stream()), "gmd_conv_fwd")

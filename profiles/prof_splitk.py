@@ -14,9 +14,13 @@ def bench(fn, n=30):
     for _ in range(n): fn()
     e1.record(); torch.cuda.synchronize()
     return e0.elapsed_time(e1) / n * 1000
-real = ops.splitk_workspace
-def nosplit(): ops.splitk_workspace = lambda dev: torch.empty(16, dtype=torch.uint8, device=dev)
-def split(): ops.splitk_workspace = real
+SPLIT = False
+def nosplit():
+    global SPLIT
+    SPLIT = False
+def split():
+    global SPLIT
+    SPLIT = True
 w = (torch.randn(1280, 11520, device="cuda", generator=g) / 107).to(torch.bfloat16)
 wt = ops.tile_weight(w)
 b = torch.randn(1280, device="cuda", generator=g)
@@ -24,8 +28,8 @@ for B in (8, 16, 32):
     x = torch.randn(B, 8, 8, 1280, device="cuda", generator=g).to(torch.bfloat16)
     a = torch.randn(B * 64, 11520, device="cuda", generator=g).to(torch.bfloat16)
     res = {}
-    for name, fn in [("conv plainW", lambda: ops.conv2d(x, w, 1280, bias=b)), ("conv tiledW", lambda: ops.conv2d(x, wt, 1280, bias=b)),
-                     ("gemm plainW", lambda: ops.gemm(a, w, bias=b)), ("gemm tiledW", lambda: ops.gemm(a, wt, bias=b))]:
+    for name, fn in [("conv plainW", lambda: ops.conv2d(x, w, 1280, bias=b, splitk=SPLIT)), ("conv tiledW", lambda: ops.conv2d(x, wt, 1280, bias=b, splitk=SPLIT)),
+                     ("gemm plainW", lambda: ops.gemm(a, w, bias=b, splitk=SPLIT)), ("gemm tiledW", lambda: ops.gemm(a, wt, bias=b, splitk=SPLIT))]:
         nosplit(); t0 = bench(fn); split(); t1 = bench(fn)
         res[name] = (t0, t1)
     print(f"B={B} M={B*64}: " + " | ".join(f"{k}: {v[0]:.1f} / split {v[1]:.1f} us" for k, v in res.items()))

@@ -156,6 +156,41 @@ def test_conv_stride2_upsample_concat_epilogue():
     check(ops.conv2d(x.cuda(), ops.pack_conv_weight_tiled(w.cuda()), 320, upsample=True, bias=b.cuda()), _conv_ref(x, w, b, upsample=True), what="upsample tiled-W")
 
 
+def test_conv_lowres_splitk_is_batch_independent():
+    """The <= 8x8 layers split K four ways by a rule that only looks at the per-image geometry: a batch of 5 == five batches of 1,
+    bit for bit, also when the partial-sum workspace only holds one tile of images at a time (chunked launches)."""
+    from gm_diffusion_b200 import _lib as L
+    from gm_diffusion_b200 import ops
+    g = torch.Generator().manual_seed(12)
+    for hw, cin in ((8, 1280), (4, 1280), (8, 2560)):
+        x = torch.randn(5, hw, hw, cin, generator=g).to(bf).cuda()
+        w = (torch.randn(1280, cin, 3, 3, generator=g) / math.sqrt(9 * cin)).to(bf)
+        b = torch.randn(1280, generator=g).cuda()
+        rb = torch.randn(5, 1280, generator=g).cuda()
+        res = torch.randn(5, hw, hw, 1280, generator=g).to(bf).cuda()
+        wt = ops.pack_conv_weight_tiled(w.cuda())
+        L.lib().gmd_reset_launch_count()
+        full = ops.conv2d(x, wt, 1280, bias=b, row_bias=rb, residual=res)
+        assert L.lib().gmd_launch_count() == 2, "expected the split main loop + the finalize kernel"
+        ref = _conv_ref(x.cpu(), w, b.cpu()) + rb.cpu()[:, None, None, :] + res.float().cpu()
+        check(full, ref, what=f"low-res split-K conv {hw}x{hw} K={9 * cin}")
+        for i in range(5):
+            one = ops.conv2d(x[i:i + 1].contiguous(), wt, 1280, bias=b, row_bias=rb[i:i + 1].contiguous(), residual=res[i:i + 1].contiguous())
+            assert torch.equal(one, full[i:i + 1]), (hw, cin, i)
+        # chunked: a workspace that only fits one tile of images
+        big = ops._WS.get(0)
+        try:
+            per_img = 4 * hw * hw * 1280 * 4
+            imgs_per_tile = 128 // (hw * hw)
+            ops._WS[0] = torch.empty(per_img * imgs_per_tile + 64, dtype=torch.uint8, device="cuda")
+            L.lib().gmd_reset_launch_count()
+            chunked = ops.conv2d(x, wt, 1280, bias=b, row_bias=rb, residual=res)
+            assert L.lib().gmd_launch_count() == 2 * -(-5 // imgs_per_tile)
+        finally:
+            ops._WS[0] = big
+        assert torch.equal(chunked, full), (hw, cin)
+
+
 @pytest.mark.parametrize("N,H,W,C,Cout", [(2, 64, 64, 128, 128), (1, 32, 48, 256, 256), (1, 16, 16, 512, 512)])
 def test_conv_stride2_pad_end(N, H, W, C, Cout):
     """AutoencoderKL encoder downsample: F.pad(x, (0,1,0,1)) + 3x3 stride-2 conv with padding 0 (diffusers Downsample2D(padding=0))."""
