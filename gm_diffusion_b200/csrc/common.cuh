@@ -226,7 +226,7 @@ int encode_tensor_map_bf16(CUtensorMap* out, const void* base, int rank, const u
 // ----------------------------------------------------------------------------------------------
 // numerics helpers
 // ----------------------------------------------------------------------------------------------
-__device__ __forceinline__ float silu_f(float x) { return x / (1.0f + __expf(-x)); }
+__device__ __forceinline__ float silu_f(float x) { return __fdividef(x, 1.0f + __expf(-x)); }  // 2 MUFU + 2 FP32 ops; <= 2 ulp, the result is rounded to bf16
 __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
     __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
     return *reinterpret_cast<uint32_t*>(&v);

@@ -111,50 +111,232 @@ __global__ void gn_stats_kernel(const T* __restrict__ x0, int C0, const __nv_bfl
 }
 
 template <typename T>
-__global__ void gn_apply_kernel(const T* __restrict__ x0, int C0, const __nv_bfloat16* __restrict__ x1, int C1,
+__global__ void __launch_bounds__(1024, 1) gn_apply_kernel(const T* __restrict__ x0, int C0, const __nv_bfloat16* __restrict__ x1, int C1,
                                 const float* __restrict__ finals, const float* __restrict__ gamma, const float* __restrict__ beta,
-                                __nv_bfloat16* __restrict__ out, int HW, int groups, int apply_silu, int px_per_cta) {
+                                __nv_bfloat16* __restrict__ out, int HW, int groups, int apply_silu, int N, int blocks_per_sample,
+                                int px_per_block) {
+    // persistent: the grid is sized to what is resident (4 CTAs per SM) and strides over (sample, pixel block) items, so there is
+    // no partial last wave (the one-CTA-per-chunk launch ran 512 CTAs on 444 slots: 1.15 waves)
     const int C = C0 + C1, nvec = C / 8, cg = C / groups;
-    const int n = blockIdx.y;
     const int cv = threadIdx.x % nvec, pl = threadIdx.x / nvec, P = blockDim.x / nvec;
     if (pl >= P) return;
     float sc[8], sh[8];
-#pragma unroll
-    for (int k = 0; k < 8; ++k) {
-        int c = cv * 8 + k, g = c / cg;
-        const float mean = finals[((int64_t)n * groups + g) * 2];
-        const float rstd = finals[((int64_t)n * groups + g) * 2 + 1];
-        float ga = gamma[c], be = beta[c];
-        sc[k] = rstd * ga; sh[k] = be - mean * rstd * ga;
-    }
-    const int p0 = blockIdx.x * px_per_cta;
-    const int p1 = min(p0 + px_per_cta, HW);
-    int p = p0 + pl;
-    for (; p + 3 * P < p1; p += 4 * P) {
-        float f[4][8];
-#pragma unroll
-        for (int u = 0; u < 4; ++u) gn_load<T>(x0, C0, x1, C1, (int64_t)n * HW + p + u * P, cv * 8, f[u]);
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {
+    int cur_n = -1;
+    const int items = N * blocks_per_sample;
+    for (int item = blockIdx.x; item < items; item += gridDim.x) {
+        const int n = item / blocks_per_sample, blk = item - n * blocks_per_sample;
+        if (n != cur_n) {
+            cur_n = n;
 #pragma unroll
             for (int k = 0; k < 8; ++k) {
-                float y = f[u][k] * sc[k] + sh[k];
-                f[u][k] = apply_silu ? silu_f(y) : y;
+                int c = cv * 8 + k, g = c / cg;
+                const float mean = finals[((int64_t)n * groups + g) * 2];
+                const float rstd = finals[((int64_t)n * groups + g) * 2 + 1];
+                float ga = gamma[c], be = beta[c];
+                sc[k] = rstd * ga; sh[k] = be - mean * rstd * ga;
             }
-            *reinterpret_cast<uint4*>(out + ((int64_t)n * HW + p + u * P) * C + cv * 8) = pack8(f[u]);
+        }
+        const int p0 = blk * px_per_block;
+        const int p1 = min(p0 + px_per_block, HW);
+        int p = p0 + pl;
+        for (; p + 3 * P < p1; p += 4 * P) {
+            float f[4][8];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) gn_load<T>(x0, C0, x1, C1, (int64_t)n * HW + p + u * P, cv * 8, f[u]);
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+#pragma unroll
+                for (int k = 0; k < 8; ++k) {
+                    float y = f[u][k] * sc[k] + sh[k];
+                    f[u][k] = apply_silu ? silu_f(y) : y;
+                }
+                *reinterpret_cast<uint4*>(out + ((int64_t)n * HW + p + u * P) * C + cv * 8) = pack8(f[u]);
+            }
+        }
+        for (; p < p1; p += P) {
+            float f[8];
+            const int64_t px = (int64_t)n * HW + p;
+            gn_load<T>(x0, C0, x1, C1, px, cv * 8, f);
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                float y = f[k] * sc[k] + sh[k];
+                f[k] = apply_silu ? silu_f(y) : y;
+            }
+            *reinterpret_cast<uint4*>(out + px * C + cv * 8) = pack8(f);
         }
     }
-    for (; p < p1; p += P) {
-        float f[8];
-        const int64_t px = (int64_t)n * HW + p;
-        gn_load<T>(x0, C0, x1, C1, px, cv * 8, f);
+}
+
+// ---------------------------------------------------------------------------------------------
+// One-pass GroupNorm for everything that fits on chip (all UNet shapes up to 1024^2 images): a thread-block CLUSTER owns
+// (sample, slab of whole groups) and splits the pixels between its CTAs; every CTA parks its part of the input in shared
+// memory, the per-group sums are exchanged through distributed shared memory in rank order (fixed order: deterministic
+// and independent of the batch), and the normalised + SiLU'd bf16 output is produced from the parked copy.  The tensor is
+// read once and written once by ONE launch — the two-kernel path below reads it twice and was wave-quantised / latency-bound
+// (41.7 + 18.0 us for a 42 MB tensor, profiles/ncu_gn_r01_summary.txt).
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t cl_rank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
+__device__ __forceinline__ uint32_t cl_size() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_nctarank;" : "=r"(r)); return r; }
+__device__ __forceinline__ void cl_sync() {
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ float ld_dsmem(const float* local, uint32_t rank) {
+    uint32_t a = smem_u32(local), r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(rank));
+    float v;
+    asm volatile("ld.shared::cluster.f32 %0, [%1];" : "=f"(v) : "r"(r) : "memory");
+    return v;
+}
+
+template <typename T> struct ParkVec;            // how 8 channels are parked in shared memory
+template <> struct ParkVec<__nv_bfloat16> { using type = uint4; };
+template <> struct ParkVec<float> { struct alignas(16) type { float4 a, b; }; };
+
+template <typename T>
+__device__ __forceinline__ void park_load(const T* x0, int C0, const __nv_bfloat16* x1, int C1, int64_t px, int c, typename ParkVec<T>::type& raw, float (&f)[8]);
+template <>
+__device__ __forceinline__ void park_load<__nv_bfloat16>(const __nv_bfloat16* x0, int C0, const __nv_bfloat16* x1, int C1, int64_t px, int c, uint4& raw, float (&f)[8]) {
+    raw = (c < C0) ? __ldg(reinterpret_cast<const uint4*>(x0 + px * C0 + c)) : __ldg(reinterpret_cast<const uint4*>(x1 + px * C1 + (c - C0)));
+    unpack8(raw, f);
+}
+template <>
+__device__ __forceinline__ void park_load<float>(const float* x0, int C0, const __nv_bfloat16* x1, int C1, int64_t px, int c, ParkVec<float>::type& raw, float (&f)[8]) {
+    gn_load<float>(x0, C0, x1, C1, px, c, f);
+    raw.a = make_float4(f[0], f[1], f[2], f[3]); raw.b = make_float4(f[4], f[5], f[6], f[7]);
+}
+__device__ __forceinline__ void park_read(const uint4& raw, float (&f)[8]) { unpack8(raw, f); }
+__device__ __forceinline__ void park_read(const ParkVec<float>::type& raw, float (&f)[8]) {
+    f[0] = raw.a.x; f[1] = raw.a.y; f[2] = raw.a.z; f[3] = raw.a.w; f[4] = raw.b.x; f[5] = raw.b.y; f[6] = raw.b.z; f[7] = raw.b.w;
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256, 5) gn_fused_kernel(const T* __restrict__ x0, int C0, const __nv_bfloat16* __restrict__ x1, int C1,
+                                                       const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                       __nv_bfloat16* __restrict__ out, int HW, int groups, int apply_silu, float eps,
+                                                       int V, int px_per_cta) {
+    using PV = typename ParkVec<T>::type;
+    extern __shared__ __align__(16) uint8_t gn_smem[];
+    float* s_warp = reinterpret_cast<float*>(gn_smem);          // [8 warps][V][16] per-warp channel sums
+    float* s_ch = s_warp + 8 * 16 * 16;                         // [V*8][2]  per-channel sums of this CTA
+    float* s_grp = s_ch + 128 * 2;                              // [G][2]    per-group sums of this CTA (read by the cluster)
+    float* s_stat = s_grp + 16 * 2;                             // [G][2]    mean, rstd
+    PV* park = reinterpret_cast<PV*>(s_stat + 16 * 2);
+    const int C = C0 + C1, cg = C / groups, G = V * 8 / cg;
+    const uint32_t CLN = cl_size(), rank = cl_rank();
+    const int slab = blockIdx.x / CLN, n = blockIdx.y;
+    const int cv = threadIdx.x % V, pl = threadIdx.x / V, P = blockDim.x / V;
+    const int c0 = (slab * V + cv) * 8;                         // first channel of this thread's vector
+    const int p0 = rank * px_per_cta;
+    const int npx = max(0, min(px_per_cta, HW - p0));
+    float s[8] = {0, 0, 0, 0, 0, 0, 0, 0}, q[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    float ga[8], be[8];
+    if (pl < P) {
+        // affine parameters: requested now, needed only in the apply phase (their latency hides behind everything else)
+        const float4 g0 = __ldg(reinterpret_cast<const float4*>(gamma + c0)), g1 = __ldg(reinterpret_cast<const float4*>(gamma + c0) + 1);
+        const float4 b0 = __ldg(reinterpret_cast<const float4*>(beta + c0)), b1 = __ldg(reinterpret_cast<const float4*>(beta + c0) + 1);
+        ga[0] = g0.x; ga[1] = g0.y; ga[2] = g0.z; ga[3] = g0.w; ga[4] = g1.x; ga[5] = g1.y; ga[6] = g1.z; ga[7] = g1.w;
+        be[0] = b0.x; be[1] = b0.y; be[2] = b0.z; be[3] = b0.w; be[4] = b1.x; be[5] = b1.y; be[6] = b1.z; be[7] = b1.w;
+        // Park this thread's vectors with cp.async: ALL of them are in flight at once (a register-staged loop paid one memory
+        // round trip per 4 vectors, ~5 in a row per CTA, and that chain — not bandwidth — set the kernel time).
+        const bool src1 = c0 >= C0;
+        const char* base = src1 ? reinterpret_cast<const char*>(x1 + (int64_t)(n * (int64_t)HW + p0) * C1 + (c0 - C0))
+                                : reinterpret_cast<const char*>(x0 + (int64_t)(n * (int64_t)HW + p0) * C0 + c0);
+        const int64_t pitch = src1 ? (int64_t)C1 * 2 : (int64_t)C0 * (int64_t)sizeof(T);
+        const bool wide = !src1 && sizeof(T) == 4;                      // fp32 source: 32 bytes per vector
+        if (sizeof(T) == 4 && src1) {
+            // bf16 skip tensor behind an fp32 first source: widen through registers (not on the UNet path)
+            for (int p = pl; p < npx; p += P) {
+                PV raw; float f[8];
+                park_load<T>(x0, C0, x1, C1, (int64_t)n * HW + p0 + p, c0, raw, f);
+                park[p * V + cv] = raw;
+            }
+        } else {
+            for (int p = pl; p < npx; p += P) {
+                const uint32_t dst = smem_u32(park + p * V + cv);
+                const char* src = base + p * pitch;
+                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+                if (wide) asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + 16), "l"(src + 16) : "memory");
+            }
+            asm volatile("cp.async.commit_group;" ::: "memory");
+            asm volatile("cp.async.wait_group 0;" ::: "memory");
+        }
+        // each thread reads back exactly what it copied: no barrier needed
+        for (int p = pl; p < npx; p += P) {
+            float f[8];
+            park_read(park[p * V + cv], f);
+#pragma unroll
+            for (int k = 0; k < 8; ++k) { s[k] += f[k]; q[k] += f[k] * f[k]; }
+        }
+    }
+    // lanes L, L+V, L+2V, ... of a warp own the same channel vector: fold them with a shuffle tree (fixed order), so only V lanes
+    // per warp go through shared memory
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    int dmax = V;
+    while (dmax * 2 < 32) dmax *= 2;
+    for (int d = dmax; d >= V; d >>= 1) {
 #pragma unroll
         for (int k = 0; k < 8; ++k) {
-            float y = f[k] * sc[k] + sh[k];
-            f[k] = apply_silu ? silu_f(y) : y;
+            const float a = __shfl_down_sync(0xffffffffu, s[k], d), b = __shfl_down_sync(0xffffffffu, q[k], d);
+            if (lane + d < 32) { s[k] += a; q[k] += b; }
         }
-        *reinterpret_cast<uint4*>(out + px * C + cv * 8) = pack8(f);
     }
+    if (lane < V) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) { s_warp[(warp * 16 + cv) * 16 + k] = s[k]; s_warp[(warp * 16 + cv) * 16 + 8 + k] = q[k]; }
+    }
+    __syncthreads();
+    // per channel (and per moment): fold the 8 warps in warp order
+    if ((int)threadIdx.x < V * 16) {
+        const int ch = threadIdx.x >> 1, m = threadIdx.x & 1;        // channel within the slab, 0 = sum / 1 = sum of squares
+        const int v = ch >> 3, k = ch & 7;
+        float acc = 0.0f;
+#pragma unroll
+        for (int w = 0; w < 8; ++w) acc += s_warp[(w * 16 + v) * 16 + m * 8 + k];
+        s_ch[ch * 2 + m] = acc;
+    }
+    __syncthreads();
+    if ((int)threadIdx.x < G * 2) {
+        const int g = threadIdx.x >> 1, m = threadIdx.x & 1;
+        float acc = 0.0f;
+        for (int c = g * cg; c < (g + 1) * cg; ++c) acc += s_ch[c * 2 + m];
+        s_grp[g * 2 + m] = acc;
+    }
+    cl_sync();                                                       // every CTA's s_grp is complete and visible cluster-wide
+    if ((int)threadIdx.x < G) {
+        const int g = threadIdx.x;
+        float s1 = 0.0f, s2 = 0.0f;
+        for (uint32_t r = 0; r < CLN; ++r) { s1 += ld_dsmem(s_grp + g * 2, r); s2 += ld_dsmem(s_grp + g * 2 + 1, r); }
+        const float inv_cnt = 1.0f / ((float)cg * (float)HW);
+        const float mean = s1 * inv_cnt;
+        const float var = fmaxf(s2 * inv_cnt - mean * mean, 0.0f);
+        s_stat[g * 2] = mean;
+        s_stat[g * 2 + 1] = rsqrtf(var + eps);
+    }
+    // second cluster barrier, split: arrive now (this CTA's remote reads are done), wait only before exiting, so that no CTA
+    // retires while a neighbour may still read its s_grp — the apply phase runs in between
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    __syncthreads();                                                 // s_stat visible to the CTA
+    if (pl < P) {
+        float sc[8], sh[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            const int cl = cv * 8 + k, g = cl / cg;
+            const float mean = s_stat[g * 2], rstd = s_stat[g * 2 + 1];
+            sc[k] = rstd * ga[k]; sh[k] = be[k] - mean * rstd * ga[k];
+        }
+        for (int p = pl; p < npx; p += P) {
+            float f[8];
+            park_read(park[p * V + cv], f);
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                float y = f[k] * sc[k] + sh[k];
+                f[k] = apply_silu ? silu_f(y) : y;
+            }
+            *reinterpret_cast<uint4*>(out + ((int64_t)n * HW + p0 + p) * C + c0) = pack8(f);
+        }
+    }
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -270,10 +452,54 @@ __global__ void silu_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* 
 
 inline bool al16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
 
+// GMD_GN_TWO_PASS=1 forces the stats + apply pair (A/B measurements; the VAE's >= 256x256 planes always use it)
+const bool g_gn_two_pass = [] { const char* e = getenv("GMD_GN_TWO_PASS"); return e && e[0] == '1'; }();
+
 template <typename T>
 int gn_launch(const void* x0, int C0, const void* x1, int C1, const float* gamma, const float* beta, void* out, int N, int HW, int groups,
               float eps, int apply_silu, float* stats_ws, cudaStream_t st) {
     const int nvec = (C0 + C1) / 8;
+    {
+        // one-pass cluster kernel whenever a sample's slab fits the shared memory of <= 8 CTAs.  The plan depends on (HW, C, groups,
+        // dtype) only — never on N — so a sample's result does not depend on the batch it is in.
+        const int cgc = (C0 + C1) / groups;
+        int a = 8, b = cgc;
+        while (b) { int t = a % b; a = b; b = t; }
+        int V = cgc / a;                                          // lcm(8, cg) / 8 vectors hold whole groups
+        while (V < 4 && nvec % (V * 2) == 0) V *= 2;              // >= 64 contiguous bytes per pixel where the shape allows
+        const int G = V * 8 / cgc;
+        const size_t vec_bytes = sizeof(typename ParkVec<T>::type), fixed = (8 * 16 * 16 + 128 * 2 + 16 * 2 + 16 * 2) * sizeof(float);
+        if (V <= 16 && G <= 16 && nvec % V == 0 && !g_gn_two_pass) {
+            // parked bytes per CTA <= 36 KB (+ 9.5 KB of reduction scratch): >= 4 CTAs per SM, whose load / reduce / apply phases overlap
+            int cl = 1;
+            while (cl < 8 && (size_t)((HW + cl - 1) / cl) * V * vec_bytes > (36u << 10)) cl *= 2;
+            const int px_per_cta = (HW + cl - 1) / cl;
+            const size_t smem = fixed + (size_t)px_per_cta * V * vec_bytes;
+            // beyond 42 KB per CTA at the largest cluster the tensor cannot be parked in about two waves: the stats + apply pair
+            // (second read from L2) streams better
+            if ((size_t)px_per_cta * V * vec_bytes <= (42u << 10)) {
+                static bool attr_done[2] = {false, false};
+                if (!attr_done[sizeof(T) == 4]) {
+                    cudaFuncSetAttribute(gn_fused_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, 56 << 10);
+                    attr_done[sizeof(T) == 4] = true;
+                }
+                cudaLaunchConfig_t cfg = {};
+                cfg.gridDim = dim3((unsigned)(cl * (nvec / V)), (unsigned)N, 1);
+                cfg.blockDim = dim3(256, 1, 1);
+                cfg.dynamicSmemBytes = smem;
+                cfg.stream = st;
+                cudaLaunchAttribute attr[1];
+                attr[0].id = cudaLaunchAttributeClusterDimension;
+                attr[0].val.clusterDim.x = cl; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+                cfg.attrs = attr; cfg.numAttrs = 1;
+                cudaError_t e = cudaLaunchKernelEx(&cfg, gn_fused_kernel<T>, static_cast<const T*>(x0), C0, static_cast<const __nv_bfloat16*>(x1), C1, gamma, beta,
+                                                   static_cast<__nv_bfloat16*>(out), HW, groups, apply_silu, eps, V, px_per_cta);
+                if (e != cudaSuccess) { set_last_error("gn_fused launch: %s", cudaGetErrorString(e)); return kErrCuda; }
+                count_launch(1);
+                return check_launch("groupnorm(fused)");
+            }
+        }
+    }
     int P = 256 / nvec; if (P < 1) P = 1;
     int threads = (nvec * P + 31) / 32 * 32;
     // chunking depends on (HW, C) only, never on N: a sample's statistics are bit-identical for any batch size / sharding
@@ -288,8 +514,12 @@ int gn_launch(const void* x0, int C0, const void* x1, int C1, const float* gamma
     float* finals = partials + (int64_t)N * 32 * groups * 2;
     gn_stats_kernel<T><<<grid, threads, threads * 16 * sizeof(float), st>>>(static_cast<const T*>(x0), C0, static_cast<const __nv_bfloat16*>(x1), C1,
                                                                             partials, finals, counters, HW, groups, px_per_cta, eps);
-    gn_apply_kernel<T><<<grid, threads, 0, st>>>(static_cast<const T*>(x0), C0, static_cast<const __nv_bfloat16*>(x1), C1, finals, gamma, beta,
-                                                 static_cast<__nv_bfloat16*>(out), HW, groups, apply_silu, px_per_cta);
+    const int px_per_block = 8 * P;
+    const int blocks_per_sample = (HW + px_per_block - 1) / px_per_block;
+    int64_t agrid = (int64_t)N * blocks_per_sample;
+    if (agrid > 4 * 148) agrid = 4 * 148;
+    gn_apply_kernel<T><<<(unsigned)agrid, threads, 0, st>>>(static_cast<const T*>(x0), C0, static_cast<const __nv_bfloat16*>(x1), C1, finals, gamma, beta,
+                                                            static_cast<__nv_bfloat16*>(out), HW, groups, apply_silu, N, blocks_per_sample, px_per_block);
     count_launch(2);
     return check_launch("groupnorm");
 }
@@ -305,7 +535,7 @@ extern "C" int gmd_groupnorm_silu(const void* x0, int32_t C0, const void* x1, in
     if (!x1) C1 = 0;
     const int C = C0 + C1;
     if (C0 % 8 || C1 % 8 || groups <= 0 || C % groups || N <= 0 || HW <= 0) { set_last_error("gmd_groupnorm_silu: bad shape C0=%d C1=%d groups=%d", C0, C1, groups); return kErrInvalid; }
-    if (!al16(x0) || !al16(x1) || !al16(out)) { set_last_error("gmd_groupnorm_silu: pointers must be 16-byte aligned"); return kErrInvalid; }
+    if (!al16(x0) || !al16(x1) || !al16(out) || !al16(gamma) || !al16(beta)) { set_last_error("gmd_groupnorm_silu: pointers must be 16-byte aligned"); return kErrInvalid; }
     if (C / 8 > 1024 || groups > 256 || N > 1024) { set_last_error("gmd_groupnorm_silu: C=%d groups=%d too large", C, groups); return kErrUnsupported; }
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     if (in_dtype == GMD_BF16) return gn_launch<__nv_bfloat16>(x0, C0, x1, C1, gamma, beta, out, N, HW, groups, eps, apply_silu, stats_ws, st);

@@ -237,7 +237,8 @@ def test_attention_large_logits():
     check(got, ref.transpose(1, 2).reshape(B, N, H * d), tol=2e-2, what="peaky softmax (running-max rescale path)")
 
 
-@pytest.mark.parametrize("N,HW,C0,C1", [(2, 4096, 320, 0), (2, 1024, 1280, 640), (3, 64, 1280, 1280), (1, 256, 640, 320), (2, 4096, 128, 0), (1, 100, 512, 0)])
+@pytest.mark.parametrize("N,HW,C0,C1", [(2, 4096, 320, 0), (2, 1024, 1280, 640), (3, 64, 1280, 1280), (1, 256, 640, 320), (2, 4096, 128, 0), (1, 100, 512, 0),
+                                        (1, 16384, 512, 0), (1, 65536, 128, 0), (2, 4096, 640, 320)])  # 65536: too big for the one-pass cluster kernel -> two-pass
 def test_groupnorm(N, HW, C0, C1):
     from gm_diffusion_b200 import ops
     g = torch.Generator().manual_seed(HW + C0 + C1)
