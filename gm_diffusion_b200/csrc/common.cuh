@@ -226,7 +226,12 @@ int encode_tensor_map_bf16(CUtensorMap* out, const void* base, int rank, const u
 // ----------------------------------------------------------------------------------------------
 // numerics helpers
 // ----------------------------------------------------------------------------------------------
-__device__ __forceinline__ float silu_f(float x) { return __fdividef(x, 1.0f + __expf(-x)); }  // 2 MUFU + 2 FP32 ops; <= 2 ulp, the result is rounded to bf16
+// Bare MUFU approximations (flush-to-zero forms): without -ftz the __expf / __fdividef intrinsics wrap every MUFU in range
+// fix-ups (FSETP + 2-4 FMUL + predicated code per call — the GEGLU epilogue spent 41 instructions per output on them).
+__device__ __forceinline__ float ex2_ftz(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float rcp_ftz(float x) { float y; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+// x * sigmoid(x): FMUL, MUFU.EX2, FADD, MUFU.RCP, FMUL; ~2 ulp, the result is rounded to bf16.  x -> -inf: ex2 -> inf, rcp -> 0.
+__device__ __forceinline__ float silu_f(float x) { return x * rcp_ftz(1.0f + ex2_ftz(-1.4426950408889634f * x)); }
 __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
     __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
     return *reinterpret_cast<uint32_t*>(&v);

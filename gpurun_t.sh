@@ -1,5 +1,4 @@
 mkdir -p gpurun_out
-timeout 1500 python -m pytest tests -m gpu -q --tb=short -p no:cacheprovider --timeout 900 -x > gpurun_out/t_all.log 2>&1; echo "all gpu tests rc $?"; tail -n 6 gpurun_out/t_all.log | cut -c1-400
-timeout 300 python -c "import __graft_entry__ as g; g.smoke(); print('smoke ok')" > gpurun_out/smoke.log 2>&1; tail -2 gpurun_out/smoke.log
-timeout 900 python bench.py --steps 3 --warmup 3 > gpurun_out/bench_r01_g.json 2> gpurun_out/bench_err.log; echo "bench rc $?"; cut -c1-900 gpurun_out/bench_r01_g.json
-timeout 600 python bench.py --impl reference --steps 1 --warmup 0 > gpurun_out/bench_r01_ref_g.json 2> gpurun_out/bench_ref_err.log; echo "ref bench rc $?"; cut -c1-600 gpurun_out/bench_r01_ref_g.json
+timeout 600 python -m pytest tests/test_gpu_tensorcore.py -k "conv or gemm or groupnorm" -m gpu -q --tb=short -p no:cacheprovider --timeout 300 > gpurun_out/t_tc.log 2>&1; echo "tc tests rc $?"; tail -n 5 gpurun_out/t_tc.log | cut -c1-400
+timeout 600 python profiles/layer_times.py > gpurun_out/layer_times_r01q.txt 2>&1; echo "layer rc $?"; head -1 gpurun_out/layer_times_r01q.txt; grep -E "geglu" gpurun_out/layer_times_r01q.txt | head -8
+python profiles/bench_gn.py 2>&1 | head -6
