@@ -71,19 +71,24 @@ __device__ __forceinline__ float gelu_fast(float x) {
 }
 
 // Shared-memory plan of one CTA.  RB = bytes per element of the residual prefetch buffer (4 holds fp32 or bf16 rows).
-template <int MT, int BN, int STAGES, int RB>
+template <int MT, int BN, int STAGES, int RB, int HALO = 0>
 struct Plan {
     static constexpr int A_SUB = BM * BK * 2;               // one 128-row A sub-tile
-    static constexpr int A_BYTES = MT * A_SUB;
+    // HALO: one A slot holds the pixel rows of all MT sub-tiles PLUS one image row above and below (up to 64 pixels wide), so
+    // the three vertical filter taps read the same copy at row offsets 0 / bw / 2*bw (see the HALO main loop)
+    static constexpr int A_BYTES = HALO ? (MT * BM + 2 * 64) * BK * 2 : MT * A_SUB;
     static constexpr int B_BYTES = BN * BK * 2;
-    static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+    static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;    // non-HALO ring slot
+    static constexpr int A_SLOTS = 2;                         // HALO: A ring depth (B ring depth is STAGES)
+    static constexpr int OFF_B = A_SLOTS * A_BYTES;           // HALO: start of the B ring
+    static constexpr int RING_BYTES = HALO ? A_SLOTS * A_BYTES + STAGES * B_BYTES : STAGES * STAGE_BYTES;
     static constexpr int RES_ROW = BN * RB + 16;             // bytes of one private residual row (+16: rows 8 apart share banks, not all)
-    static constexpr int OFF_RES = STAGES * STAGE_BYTES;
+    static constexpr int OFF_RES = RING_BYTES;
     static constexpr int OFF_BIAS = OFF_RES + BM * RES_ROW;  // BN floats
     static constexpr int OFF_BARS = OFF_BIAS + BN * 4;
     static constexpr int ACC = 2 * MT * BN <= 512 ? 2 : 1;   // TMEM accumulator sets (2 = epilogue overlaps the next tile's main loop)
     static constexpr int ACC_COLS = MT * BN;
-    static constexpr int TOTAL = OFF_BARS + (2 * STAGES + 5) * 8 + 16 + 1024;
+    static constexpr int TOTAL = OFF_BARS + (2 * STAGES + 5 + 2 * A_SLOTS) * 8 + 16 + 1024;
     static constexpr uint32_t TMEM_COLS = ACC * ACC_COLS <= 32 ? 32 : ACC * ACC_COLS <= 64 ? 64 : ACC * ACC_COLS <= 128 ? 128 : ACC * ACC_COLS <= 256 ? 256 : 512;
     static_assert(ACC * ACC_COLS <= 512, "accumulators exceed TMEM");
     static_assert(TOTAL <= 232448, "shared memory plan exceeds 227 KB");
@@ -143,14 +148,15 @@ __device__ __forceinline__ void st_bf16x16(__nv_bfloat16* p, const float* v) {
 //     128-row A sub-tiles and TMA-multicasts it into both CTAs' smem, so the A bytes crossing the L2 -> SM fabric are halved
 //     (36 KB instead of 52 KB per k block at 256x160).  A smem slot is recycled only after BOTH CTAs' MMAs have read it
 //     (tcgen05.commit multicast onto both empty barriers).
-template <int MT, int BN, int STAGES, int RB, int CL>
+template <int MT, int BN, int STAGES, int RB, int CL, int HALO>
 __global__ void __launch_bounds__(320, 1)
 gemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__ CUtensorMap map_a1,
             const __grid_constant__ CUtensorMap map_a2, const __grid_constant__ CUtensorMap map_a3,
             const __grid_constant__ CUtensorMap map_w, const KernelArgs args) {
-    using P = Plan<MT, BN, STAGES, RB>;
+    using P = Plan<MT, BN, STAGES, RB, HALO>;
     constexpr uint32_t IDESC = umma_idesc_bf16(BM, BN, false, false);
     constexpr int ACC = P::ACC;
+    static_assert(!HALO || CL == 1, "the halo main loop is single-CTA");
 
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -161,7 +167,9 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__ 
     uint64_t* acc_full = empty_bar + STAGES;   // [2]
     uint64_t* acc_empty = acc_full + 2;        // [2]
     uint64_t* res_bar = acc_empty + 2;         // residual prefetch rounds
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(res_bar + 1);
+    uint64_t* a_full = res_bar + 1;            // HALO: A ring (P::A_SLOTS each)
+    uint64_t* a_empty = a_full + P::A_SLOTS;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(a_empty + P::A_SLOTS);
 
     static_assert(CL == 1 || MT == 2, "the A multicast splits the two 128-row sub-tiles between the two CTAs");
     const int warp = threadIdx.x >> 5;
@@ -177,6 +185,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__ 
         for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], CL); }
         for (int s = 0; s < 2; ++s) { mbar_init(&acc_full[s], 1); mbar_init(&acc_empty[s], 256); }
         mbar_init(res_bar, 256);
+        for (int s = 0; s < P::A_SLOTS; ++s) { mbar_init(&a_full[s], 1); mbar_init(&a_empty[s], 1); }
         fence_barrier_init();
     }
     if (warp == 1) tmem_alloc<P::TMEM_COLS>(tmem_slot);
@@ -188,7 +197,39 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__ 
 
     if (warp == 0) {
         // =============================== TMA producer ===============================
-        if (elect_one()) {
+        if (HALO && elect_one()) {
+            // HALO main loop (3x3, stride 1, tile = MT*bh consecutive image rows of one image, full width): for every
+            // (horizontal tap sx, 64-channel chunk) ONE TMA box of MT*bh + 2 image rows is loaded and the three vertical taps
+            // read it at row offsets 0, bw, 2*bw — the A bytes entering the SM drop from 3 x MT x 16 KB to (MT*128 + 2*bw) x 128 B
+            // per three k blocks (-50 % at MT = 2, bw = 64); the weights keep their own ring, one tile per k block.
+            const int chunks = args.chunks0 + args.chunks1;
+            const uint32_t a_bytes = (uint32_t)(MT * BM + 2 * args.bw) * (BK * 2);
+            uint32_t ag = 0, kbg = 0;
+            for (int tile = tile0; tile < num_tiles; tile += tstride) {
+                const int mt = tile % args.tiles_mt;
+                const int n0 = ((tile / args.tiles_mt) % tn_c) * BN;
+                int t = mt * MT;
+                t /= args.tiles_w;                                  // tiles_w == 1
+                const int th0 = (t % args.tiles_h) * args.bh, tn0 = t / args.tiles_h;
+                for (int sx = 0; sx < 3; ++sx) {
+                    for (int cc = 0; cc < chunks; ++cc, ++ag) {
+                        const int slot = ag % P::A_SLOTS;
+                        mbar_wait(&a_empty[slot], ((ag / P::A_SLOTS) & 1) ^ 1);
+                        mbar_expect_tx(&a_full[slot], a_bytes);
+                        if (cc < args.chunks0) tma_load_4d(smem + slot * P::A_BYTES, &map_a2, &a_full[slot], cc * BK, sx - 1, th0 - 1, tn0);
+                        else tma_load_4d(smem + slot * P::A_BYTES, &map_a3, &a_full[slot], (cc - args.chunks0) * BK, sx - 1, th0 - 1, tn0);
+                        for (int r = 0; r < 3; ++r, ++kbg) {
+                            const int kb = (r * 3 + sx) * chunks + cc;
+                            const int stage = kbg % STAGES;
+                            mbar_wait(&empty_bar[stage], ((kbg / STAGES) & 1) ^ 1);
+                            mbar_expect_tx(&full_bar[stage], P::B_BYTES);
+                            bulk_copy_g2s(smem + P::OFF_B + stage * P::B_BYTES, args.w_bulk + (size_t)((n0 / BN) * args.num_kb + kb) * P::B_BYTES,
+                                          P::B_BYTES, &full_bar[stage]);
+                        }
+                    }
+                }
+            }
+        } else if (!HALO && elect_one()) {
             const int chunks_per_tap = args.chunks0 + args.chunks1;
             uint32_t kbg = 0;  // k-blocks issued so far (ring position carries across tiles)
             for (int tile = tile0; tile < num_tiles; tile += tstride) {
@@ -275,7 +316,39 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__ 
         }
     } else if (warp == 1) {
         // =============================== MMA issuer ===============================
-        if (elect_one()) {
+        if (HALO && elect_one()) {
+            const int groups = 3 * (args.chunks0 + args.chunks1);
+            uint32_t ag = 0, kbg = 0, it = 0;
+            for (int tile = tile0; tile < num_tiles; tile += tstride, ++it) {
+                const int ab = it % ACC;
+                mbar_wait(&acc_empty[ab], ((it / ACC) & 1) ^ 1);
+                tc_fence_after();
+                const uint32_t tacc = tmem_acc + ab * P::ACC_COLS;
+                for (int g = 0; g < groups; ++g, ++ag) {
+                    const int slot = ag % P::A_SLOTS;
+                    mbar_wait(&a_full[slot], (ag / P::A_SLOTS) & 1);
+                    const uint32_t sa = smem_u32(smem + slot * P::A_BYTES);
+                    for (int r = 0; r < 3; ++r, ++kbg) {
+                        const int stage = kbg % STAGES;
+                        mbar_wait(&full_bar[stage], (kbg / STAGES) & 1);
+                        tc_fence_after();
+                        const uint64_t db = umma_desc_k_sw128(smem_u32(smem + P::OFF_B + stage * P::B_BYTES));
+                        const uint32_t sar = sa + (uint32_t)(r * args.bw) * (BK * 2);   // vertical tap r: r image rows further down
+#pragma unroll
+                        for (int k = 0; k < BK / 16; ++k) {
+#pragma unroll
+                            for (int s = 0; s < MT; ++s) {
+                                const uint64_t da = umma_desc_k_sw128(sar + s * P::A_SUB);
+                                umma_bf16_ss(tacc + s * BN, da + 2 * k, db + 2 * k, IDESC, (g | r | k) != 0 ? 1u : 0u);
+                            }
+                        }
+                        umma_commit(&empty_bar[stage]);
+                    }
+                    umma_commit(&a_empty[slot]);
+                }
+                umma_commit(&acc_full[ab]);
+            }
+        } else if (!HALO && elect_one()) {
             uint32_t kbg = 0, it = 0;
             for (int tile = tile0; tile < num_tiles; tile += tstride, ++it) {
                 const int ab = it % ACC;
@@ -607,6 +680,7 @@ __global__ void __launch_bounds__(256) splitk_finalize_kernel(const float* __res
     }
 }
 
+bool g_disable_halo = false;      // GMD_NO_HALO=1: 3x3 convolutions take the one-box-per-tap main loop (A/B measurements)
 bool g_disable_cluster = false;   // GMD_NO_CLUSTER=1 in the environment falls back to single-CTA tiles (A/B measurements)
 
 int sm_count() {
@@ -614,6 +688,8 @@ int sm_count() {
     if (!sms) {
         const char* e = getenv("GMD_NO_CLUSTER");
         g_disable_cluster = e && e[0] == '1';
+        e = getenv("GMD_NO_HALO");
+        g_disable_halo = e && e[0] == '1';
         int dev = 0;
         cudaGetDevice(&dev);
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
@@ -622,12 +698,12 @@ int sm_count() {
     return sms;
 }
 
-template <int MT, int BN, int STAGES, int RB, int CL = 1>
+template <int MT, int BN, int STAGES, int RB, int CL = 1, int HALO = 0>
 int launch(const CUtensorMap* maps_a, const CUtensorMap& map_w, const KernelArgs& args, cudaStream_t st) {
     static bool configured = false;
-    constexpr size_t smem = Plan<MT, BN, STAGES, RB>::TOTAL;
+    constexpr size_t smem = Plan<MT, BN, STAGES, RB, HALO>::TOTAL;
     if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(gemm_kernel<MT, BN, STAGES, RB, CL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaError_t e = cudaFuncSetAttribute(gemm_kernel<MT, BN, STAGES, RB, CL, HALO>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) { set_last_error("gemm: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return kErrCuda; }
         configured = true;
     }
@@ -641,20 +717,25 @@ int launch(const CUtensorMap* maps_a, const CUtensorMap& map_w, const KernelArgs
     attr[0].id = cudaLaunchAttributeClusterDimension;
     attr[0].val.clusterDim.x = CL; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr; cfg.numAttrs = CL > 1 ? 1 : 0;
-    cudaError_t e = cudaLaunchKernelEx(&cfg, gemm_kernel<MT, BN, STAGES, RB, CL>, maps_a[0], maps_a[1], maps_a[2], maps_a[3], map_w, args);
+    cudaError_t e = cudaLaunchKernelEx(&cfg, gemm_kernel<MT, BN, STAGES, RB, CL, HALO>, maps_a[0], maps_a[1], maps_a[2], maps_a[3], map_w, args);
     if (e != cudaSuccess) { set_last_error("gemm: launch: %s", cudaGetErrorString(e)); return kErrCuda; }
     count_launch(1);
     return check_launch("gemm_kernel");
 }
 
 // tiles_m = number of 128-row tiles; picks the CTA tile and launches
+// 256-row CTA tiles (two accumulators per tile, B tile reused) for long K loops that still fill the 148 SMs
+inline bool want_mt2(int bn, bool res_f32, int64_t tiles_m, int64_t tiles_n, unsigned gz, int num_kb) {
+    return (bn == 160 || bn == 128) && !res_f32 && tiles_m >= 2 && num_kb >= 16 && ((tiles_m + 1) / 2) * tiles_n * gz >= 120;
+}
+
 int launch_cfg(int bn, int64_t tiles_m, int64_t tiles_n, unsigned gz, const CUtensorMap* maps_a, const CUtensorMap& map_w,
-               KernelArgs args, cudaStream_t st) {
+               KernelArgs args, cudaStream_t st, bool halo_ok = false) {
     // 256-row CTA tiles (two accumulators per tile, B tile reused) for long K loops that still fill the 148 SMs; short K loops
     // keep 128-row tiles with two accumulator SETS so the epilogue overlaps the next tile's main loop.  The fp32 residual
     // stream needs the larger private-row buffer, which only fits next to the 128-row pipeline.
     const bool res_f32 = args.residual && (args.flags & GMD_EPI_RESIDUAL_F32);
-    const bool mt2 = (bn == 160 || bn == 128) && !res_f32 && tiles_m >= 2 && args.num_kb >= 16 && ((tiles_m + 1) / 2) * tiles_n * gz >= 120;
+    const bool mt2 = want_mt2(bn, res_f32, tiles_m, tiles_n, gz, args.num_kb);
     args.tiles_mt = (int)(mt2 ? (tiles_m + 1) / 2 : tiles_m);
     args.tiles_n = (int)tiles_n;
     args.gz = (int)gz;
@@ -662,6 +743,12 @@ int launch_cfg(int bn, int64_t tiles_m, int64_t tiles_n, unsigned gz, const CUte
     // pair neighbouring N tiles into 2-CTA clusters that share (multicast) the A operand
     (void)sm_count();  // also reads GMD_NO_CLUSTER once
     const bool cl2 = mt2 && (tiles_n % 2 == 0) && args.ksplit == 1 && (args.mode == 1 || args.kb_src0 == args.num_kb) && !g_disable_cluster;
+    if (halo_ok && args.ksplit == 1 && !g_disable_halo) {
+        // vertical-tap halo reuse (maps_a[2], maps_a[3] hold the tall boxes, built for this MT by the caller): -31 % operand bytes
+        // per k block at 256x160, -26 % at 128x160
+        if (bn == 160) return mt2 ? launch<2, 160, 4, 2, 1, 1>(maps_a, map_w, args, st) : launch<1, 160, 4, 2, 1, 1>(maps_a, map_w, args, st);
+        if (bn == 128) return mt2 ? launch<2, 128, 4, 2, 1, 1>(maps_a, map_w, args, st) : launch<1, 128, 4, 2, 1, 1>(maps_a, map_w, args, st);
+    }
     switch (bn) {
         case 160: return mt2 ? (cl2 ? launch<2, 160, 3, 2, 2>(maps_a, map_w, args, st) : launch<2, 160, 3, 2>(maps_a, map_w, args, st))
                              : launch<1, 160, 3, 4>(maps_a, map_w, args, st);
@@ -869,6 +956,35 @@ extern "C" int gmd_conv_fwd(const gmd_conv_params* p, void* stream) {
         }
         maps_a[2] = maps_a[3] = maps_a[0];
     }
+    // HALO main loop eligibility: 3x3 stride 1 without upsample, a tile = whole image rows of one image (tiles_w == 1, bn == 1),
+    // pairs of 128-row sub-tiles vertically adjacent inside an image, pre-swizzled weight tiles (bulk-copied)
+    bool halo_ok = p->ksize == 3 && p->stride == 1 && !p->upsample && bw <= 64 && bw >= 8 && bw == p->W && bn == 1 && bw * bh == BM &&
+                   p->w_tiled >= 1000 && !(p->flags & GMD_EPI_RESIDUAL_F32) && (bnt == 160 || bnt == 128) && a.num_kb >= 16;
+    if (halo_ok) {
+        const int64_t tm = (int64_t)a.tiles_w * a.tiles_h * ((p->N + bn - 1) / bn), tnn = (p->Cout + bnt - 1) / bnt;
+        const bool pair = want_mt2(bnt, false, tm, tnn, 1u, a.num_kb);
+        if (pair && (a.tiles_h % 2)) halo_ok = false;     // 256-row tiles must pair two row blocks of the SAME image
+        else {
+            const bool split = conv_splitk_rule(Ho, Wo, a.num_kb, p->Cout, true) > 1 && p->workspace;
+            if (split) halo_ok = false;
+        }
+    }
+    if (halo_ok) {
+        const int64_t tm = (int64_t)a.tiles_w * a.tiles_h * ((p->N + bn - 1) / bn), tnn = (p->Cout + bnt - 1) / bnt;
+        const int mtv = want_mt2(bnt, false, tm, tnn, 1u, a.num_kb) ? 2 : 1;
+        const uint32_t hbox[4] = {BK, (uint32_t)bw, (uint32_t)(mtv * bh + 2), 1};
+        uint64_t dims[4] = {(uint64_t)p->C0, (uint64_t)p->W, (uint64_t)p->H, (uint64_t)p->N};
+        uint64_t strides[4] = {2, (uint64_t)p->C0 * 2, (uint64_t)p->W * p->C0 * 2, (uint64_t)p->H * p->W * p->C0 * 2};
+        int rc = encode_tensor_map_bf16(&maps_a[2], p->x0, 4, dims, strides, hbox, true);
+        if (rc) return rc;
+        maps_a[3] = maps_a[2];
+        if (p->x1) {
+            uint64_t d1[4] = {(uint64_t)C1, (uint64_t)p->W, (uint64_t)p->H, (uint64_t)p->N};
+            uint64_t s1[4] = {2, (uint64_t)C1 * 2, (uint64_t)p->W * C1 * 2, (uint64_t)p->H * p->W * C1 * 2};
+            rc = encode_tensor_map_bf16(&maps_a[3], p->x1, 4, d1, s1, hbox, true);
+            if (rc) return rc;
+        }
+    }
     if (p->w_tiled) {
         // [N tile][k block = tap * chunks + chunk][bnt rows][64]: channels of every tap zero-padded to whole 64-blocks at pack time
         if ((p->w_tiled >= 1000 ? p->w_tiled - 1000 : p->w_tiled) != bnt) { set_last_error("gmd_conv_fwd: tiled weights were packed for N tile %d, kernel picks %d", p->w_tiled, bnt); return kErrInvalid; }
@@ -924,5 +1040,5 @@ extern "C" int gmd_conv_fwd(const gmd_conv_params* p, void* stream) {
         return launch_finalize(a, static_cast<const float*>(p->workspace), ks, rows, p->Cout, a.bias, a.row_bias, a.ld_row_bias, (int64_t)Ho * Wo,
                                a.residual, p->flags & GMD_EPI_RESIDUAL_F32, p->out, p->flags & GMD_EPI_OUT_F32, st);
     }
-    return launch_cfg(bnt, tiles_m, tiles_nn, p->upsample ? 4u : 1u, maps_a, map_w, a, st);
+    return launch_cfg(bnt, tiles_m, tiles_nn, p->upsample ? 4u : 1u, maps_a, map_w, a, st, halo_ok);
 }

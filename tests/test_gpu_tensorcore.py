@@ -156,6 +156,32 @@ def test_conv_stride2_upsample_concat_epilogue():
     check(ops.conv2d(x.cuda(), ops.pack_conv_weight_tiled(w.cuda()), 320, upsample=True, bias=b.cuda()), _conv_ref(x, w, b, upsample=True), what="upsample tiled-W")
 
 
+@pytest.mark.parametrize("N,H,W,C0,C1,Cout", [(8, 64, 64, 320, 0, 320), (16, 32, 32, 640, 0, 640), (16, 16, 16, 1280, 0, 1280), (8, 64, 64, 640, 320, 320),
+                                                (6, 32, 32, 1280, 640, 640), (9, 64, 64, 128, 0, 128)])
+def test_conv3x3_halo_main_loop(N, H, W, C0, C1, Cout):
+    """Problems big enough for the 256-row tiles: the 3x3 main loop loads one tall box per (horizontal tap, channel chunk) and the
+    three vertical taps read it at shifted rows.  Checked against torch, against a batch of one (bit-exact) and with the epilogue extras."""
+    from gm_diffusion_b200 import ops
+    g = torch.Generator().manual_seed(N + H + C0 + C1)
+    x = torch.randn(N, H, W, C0, generator=g).to(bf)
+    x1 = torch.randn(N, H, W, C1, generator=g).to(bf) if C1 else None
+    w = (torch.randn(Cout, C0 + C1, 3, 3, generator=g) / math.sqrt(9 * (C0 + C1))).to(bf)
+    b = torch.randn(Cout, generator=g)
+    rb = torch.randn(N, Cout, generator=g)
+    res = torch.randn(N, H, W, Cout, generator=g).to(bf)
+    wt = ops.pack_conv_weight_tiled(w.cuda())
+    full = torch.cat([x, x1], -1) if C1 else x
+    ref = _conv_ref(full, w, b)
+    got = ops.conv2d(x.cuda(), wt, Cout, x1=x1.cuda() if C1 else None, bias=b.cuda())
+    check(got, ref, what=f"halo conv {N}x{H}x{W} {C0}+{C1}->{Cout}")
+    got2 = ops.conv2d(x.cuda(), wt, Cout, x1=x1.cuda() if C1 else None, bias=b.cuda(), row_bias=rb.cuda(), residual=res.cuda())
+    check(got2, ref + rb[:, None, None, :] + res.float(), what="halo conv + temb + residual")
+    f32 = ops.conv2d(x.cuda(), wt, Cout, x1=x1.cuda() if C1 else None, bias=b.cuda(), out_f32=True)
+    check(f32, ref, what="halo conv fp32 out")
+    one = ops.conv2d(x[:1].cuda(), wt, Cout, x1=x1[:1].cuda() if C1 else None, bias=b.cuda())   # small batch: one-box-per-tap loop
+    check(one, ref[:1], what="batch of one")
+
+
 def test_conv_lowres_splitk_is_batch_independent():
     """The <= 8x8 layers split K four ways by a rule that only looks at the per-image geometry: a batch of 5 == five batches of 1,
     bit for bit, also when the partial-sum workspace only holds one tile of images at a time (chunked launches)."""
