@@ -29,6 +29,7 @@ struct KernelArgs {
     int kb_src0;    // K blocks taken from A source 0 (the rest from source 1)
     // conv
     int ks, stride, upsample;
+    int bw_log2, bh_log2;     // the pixel box of a tile has power-of-two extents: row -> (w, h, n) by shifts
     int pad_end;              // stride 2: taps start at input row/col 2*o (zero row/col appended at the end) instead of 2*o - 1
     int chunks0, chunks1;  // 64-channel blocks per tap from source 0 / 1
     int ctot;              // C0 + C1 (weight K pitch per tap)
@@ -130,6 +131,13 @@ __device__ __forceinline__ void st_global_256(void* p, uint32_t a0, uint32_t a1,
     asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(a4), "r"(a5), "r"(a6), "r"(a7)
                  : "memory");
 }
+// 16-byte load from shared memory by 32-bit shared address (a pointer derived from the dynamic smem base is generic to the compiler:
+// it emitted LD.E, which goes through the global/generic path)
+__device__ __forceinline__ float4 lds128(uint32_t addr) {
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+    return v;
+}
 __device__ __forceinline__ void st_f32x8(float* p, const float* v) {
     st_global_256(p, __float_as_uint(v[0]), __float_as_uint(v[1]), __float_as_uint(v[2]), __float_as_uint(v[3]), __float_as_uint(v[4]),
                   __float_as_uint(v[5]), __float_as_uint(v[6]), __float_as_uint(v[7]));
@@ -162,6 +170,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__ 
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint8_t* res_s = smem + P::OFF_RES;
     float* bias_s = reinterpret_cast<float*>(smem + P::OFF_BIAS);
+    const uint32_t bias_sa = smem_u32(bias_s);
     uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + P::OFF_BARS);
     uint64_t* empty_bar = full_bar + STAGES;
     uint64_t* acc_full = empty_bar + STAGES;   // [2]
@@ -432,12 +441,12 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__ 
             if (args.mode == 0) {
                 int64_t m = (int64_t)t * BM + row;
                 ri.ok = m < args.M; ri.out_row = m;
-                ri.sample = args.rows_per_sample > 0 ? m / args.rows_per_sample : 0;
+                ri.sample = (args.row_bias && args.rows_per_sample > 0) ? (int64_t)((uint32_t)m / (uint32_t)args.rows_per_sample) : 0;
             } else {
                 int tw = t % args.tiles_w; t /= args.tiles_w;
                 int th = t % args.tiles_h; t /= args.tiles_h;
-                int w = row % args.bw; int q = row / args.bw;
-                int h = q % args.bh; int n = q / args.bh;
+                int w = row & (args.bw - 1); int q = row >> args.bw_log2;
+                int h = q & (args.bh - 1); int n = q >> args.bh_log2;
                 w += tw * args.bw; h += th * args.bh; n += t * args.bn;
                 ri.ok = (w < args.Wg) && (h < args.Hg) && (n < args.Ng);
                 int ow = w, oh = h;
@@ -467,6 +476,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__ 
         uint32_t res_waited = 0;
 
         uint32_t it = 0;
+        int bias_n0 = -1;
         if (tile0 < num_tiles) {
             TileInfo t0 = tile_info(tile0);
             prefetch_residual(t0, row_info(t0, 0));
@@ -474,16 +484,20 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__ 
         for (int tile = tile0; tile < num_tiles; tile += tstride, ++it) {
             const TileInfo ti = tile_info(tile);
             const int ab = it % ACC;
-            // bias slice of this N tile -> smem (the first barrier keeps slow warps of the previous tile from losing theirs)
-            asm volatile("bar.sync 1, 256;" ::: "memory");
-            if (args.bias) {
+            // bias slice of this N tile -> smem, only when the N tile changes (a CTA's consecutive tiles mostly share it): the
+            // reload is a dependent global load plus two 256-thread barriers on the epilogue's critical path, ~1 us per tile,
+            // which is what bounded the short-K GEMMs (55 tiles per CTA).  The first barrier keeps slow warps of the previous
+            // tile from losing their copy.
+            if (args.bias && ti.n0 != bias_n0) {
+                bias_n0 = ti.n0;
+                asm volatile("bar.sync 1, 256;" ::: "memory");
                 for (int i = et; i < BN; i += 256) {
                     int col = geglu ? (i < BN / 2 ? ti.out_col_tile + i : args.N_out + ti.out_col_tile + (i - BN / 2)) : ti.n0 + i;
                     int lim = geglu ? 2 * args.N_out : args.N_out;
                     bias_s[i] = col < lim ? __ldg(args.bias + col) : 0.0f;
                 }
+                asm volatile("bar.sync 1, 256;" ::: "memory");
             }
-            asm volatile("bar.sync 1, 256;" ::: "memory");
             mbar_wait(&acc_full[ab], (it / ACC) & 1);
             tc_fence_after();
             const int out_col_tile = ti.out_col_tile;
@@ -508,11 +522,10 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__ 
                             tmem_wait_ld();
                             if (!row_ok) continue;
                             float v[16];
-                            const float4* bv = reinterpret_cast<const float4*>(bias_s + c * 16);
-                            const float4* bg = reinterpret_cast<const float4*>(bias_s + BN / 2 + c * 16);
+                            const uint32_t bv = bias_sa + (c * 16) * 4, bg = bias_sa + (BN / 2 + c * 16) * 4;
 #pragma unroll
                             for (int j = 0; j < 4; ++j) {
-                                float4 a = args.bias ? bv[j] : make_float4(0, 0, 0, 0), g = args.bias ? bg[j] : make_float4(0, 0, 0, 0);
+                                float4 a = args.bias ? lds128(bv + 16 * j) : make_float4(0, 0, 0, 0), g = args.bias ? lds128(bg + 16 * j) : make_float4(0, 0, 0, 0);
                                 v[4 * j + 0] = (__uint_as_float(r0[4 * j + 0]) + a.x) * gelu_fast(__uint_as_float(r1[4 * j + 0]) + g.x);
                                 v[4 * j + 1] = (__uint_as_float(r0[4 * j + 1]) + a.y) * gelu_fast(__uint_as_float(r1[4 * j + 1]) + g.y);
                                 v[4 * j + 2] = (__uint_as_float(r0[4 * j + 2]) + a.z) * gelu_fast(__uint_as_float(r1[4 * j + 2]) + g.z);
@@ -542,9 +555,9 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__ 
                             }
                             const int col0 = out_col_tile + c * 32;
                             if (args.bias) {
-                                const float4* b4 = reinterpret_cast<const float4*>(bias_s + c * 32);
+                                const uint32_t b4 = bias_sa + (c * 32) * 4;
 #pragma unroll
-                                for (int j = 0; j < 8; ++j) { float4 a = b4[j]; v[4 * j] += a.x; v[4 * j + 1] += a.y; v[4 * j + 2] += a.z; v[4 * j + 3] += a.w; }
+                                for (int j = 0; j < 8; ++j) { float4 a = lds128(b4 + 16 * j); v[4 * j] += a.x; v[4 * j + 1] += a.y; v[4 * j + 2] += a.z; v[4 * j + 3] += a.w; }
                             }
                             if (rb_row) {
                                 const float4* b4 = reinterpret_cast<const float4*>(rb_row + col0);
@@ -750,10 +763,12 @@ int launch_cfg(int bn, int64_t tiles_m, int64_t tiles_n, unsigned gz, const CUte
         if (bn == 128) return mt2 ? launch<2, 128, 4, 2, 1, 1>(maps_a, map_w, args, st) : launch<1, 128, 4, 2, 1, 1>(maps_a, map_w, args, st);
     }
     switch (bn) {
+        // 128-row tiles: the main loop is bound by the operand bytes in flight (ring capacity / TMA latency — the "40 B/clk/SM" of the
+        // 3-stage ring is 108 KB per ~2700 cycles), so everything the fp32 residual row buffer does not need goes to more stages
         case 160: return mt2 ? (cl2 ? launch<2, 160, 3, 2, 2>(maps_a, map_w, args, st) : launch<2, 160, 3, 2>(maps_a, map_w, args, st))
-                             : launch<1, 160, 3, 4>(maps_a, map_w, args, st);
+                             : (res_f32 ? launch<1, 160, 3, 4>(maps_a, map_w, args, st) : launch<1, 160, 5, 2>(maps_a, map_w, args, st));
         case 128: return mt2 ? (cl2 ? launch<2, 128, 3, 2, 2>(maps_a, map_w, args, st) : launch<2, 128, 3, 2>(maps_a, map_w, args, st))
-                             : launch<1, 128, 4, 4>(maps_a, map_w, args, st);
+                             : (res_f32 ? launch<1, 128, 4, 4>(maps_a, map_w, args, st) : launch<1, 128, 5, 2>(maps_a, map_w, args, st));
         case 64: return launch<1, 64, 6, 4>(maps_a, map_w, args, st);
         case 32: return launch<1, 32, 6, 4>(maps_a, map_w, args, st);
         default: set_last_error("gemm: unsupported N tile %d", bn); return kErrUnsupported;
@@ -913,6 +928,8 @@ extern "C" int gmd_conv_fwd(const gmd_conv_params* p, void* stream) {
     a.ctot = ctot;
     a.num_kb = taps * (a.chunks0 + a.chunks1);
     a.bw = bw; a.bh = bh; a.bn = bn;
+    a.bw_log2 = 0; while ((1 << a.bw_log2) < bw) ++a.bw_log2;
+    a.bh_log2 = 0; while ((1 << a.bh_log2) < bh) ++a.bh_log2;
     a.tiles_w = (Wg + bw - 1) / bw; a.tiles_h = (Hg + bh - 1) / bh;
     a.Wg = Wg; a.Hg = Hg; a.Ng = p->N; a.Wo = Wo; a.Ho = Ho;
     a.N_out = p->Cout;
