@@ -748,6 +748,7 @@ int launch_cfg(int bn, int64_t tiles_m, int64_t tiles_n, unsigned gz, const CUte
     // keep 128-row tiles with two accumulator SETS so the epilogue overlaps the next tile's main loop.  The fp32 residual
     // stream needs the larger private-row buffer, which only fits next to the 128-row pipeline.
     const bool res_f32 = args.residual && (args.flags & GMD_EPI_RESIDUAL_F32);
+    const bool no_res = !args.residual;
     const bool mt2 = want_mt2(bn, res_f32, tiles_m, tiles_n, gz, args.num_kb);
     args.tiles_mt = (int)(mt2 ? (tiles_m + 1) / 2 : tiles_m);
     args.tiles_n = (int)tiles_n;
@@ -759,14 +760,19 @@ int launch_cfg(int bn, int64_t tiles_m, int64_t tiles_n, unsigned gz, const CUte
     if (halo_ok && args.ksplit == 1 && !g_disable_halo) {
         // vertical-tap halo reuse (maps_a[2], maps_a[3] hold the tall boxes, built for this MT by the caller): -31 % operand bytes
         // per k block at 256x160, -26 % at 128x160
+        // (no residual: the private residual rows are not needed and their 43 KB go to deeper operand rings, RB = 0)
+        if (bn == 160 && no_res) return mt2 ? launch<2, 160, 6, 0, 1, 1>(maps_a, map_w, args, st) : launch<1, 160, 7, 0, 1, 1>(maps_a, map_w, args, st);
         if (bn == 160) return mt2 ? launch<2, 160, 4, 2, 1, 1>(maps_a, map_w, args, st) : launch<1, 160, 4, 2, 1, 1>(maps_a, map_w, args, st);
         if (bn == 128) return mt2 ? launch<2, 128, 4, 2, 1, 1>(maps_a, map_w, args, st) : launch<1, 128, 4, 2, 1, 1>(maps_a, map_w, args, st);
     }
     switch (bn) {
         // 128-row tiles: the main loop is bound by the operand bytes in flight (ring capacity / TMA latency — the "40 B/clk/SM" of the
-        // 3-stage ring is 108 KB per ~2700 cycles), so everything the fp32 residual row buffer does not need goes to more stages
-        case 160: return mt2 ? (cl2 ? launch<2, 160, 3, 2, 2>(maps_a, map_w, args, st) : launch<2, 160, 3, 2>(maps_a, map_w, args, st))
-                             : (res_f32 ? launch<1, 160, 3, 4>(maps_a, map_w, args, st) : launch<1, 160, 5, 2>(maps_a, map_w, args, st));
+        // 3-stage ring is 108 KB per ~2700 cycles), so everything the residual row buffer does not need goes to more stages
+        case 160:
+            if (no_res) return mt2 ? (cl2 ? launch<2, 160, 4, 0, 2>(maps_a, map_w, args, st) : launch<2, 160, 4, 0>(maps_a, map_w, args, st))
+                                   : launch<1, 160, 6, 0>(maps_a, map_w, args, st);
+            return mt2 ? (cl2 ? launch<2, 160, 3, 2, 2>(maps_a, map_w, args, st) : launch<2, 160, 3, 2>(maps_a, map_w, args, st))
+                       : (res_f32 ? launch<1, 160, 3, 4>(maps_a, map_w, args, st) : launch<1, 160, 5, 2>(maps_a, map_w, args, st));
         case 128: return mt2 ? (cl2 ? launch<2, 128, 3, 2, 2>(maps_a, map_w, args, st) : launch<2, 128, 3, 2>(maps_a, map_w, args, st))
                              : (res_f32 ? launch<1, 128, 4, 4>(maps_a, map_w, args, st) : launch<1, 128, 5, 2>(maps_a, map_w, args, st));
         case 64: return launch<1, 64, 6, 4>(maps_a, map_w, args, st);
