@@ -1,3 +1,3 @@
 mkdir -p gpurun_out
-timeout 600 python -m pytest tests/test_gpu_tensorcore.py -k "gemm or conv" -m gpu -q --tb=short -p no:cacheprovider --timeout 300 > gpurun_out/t_tc.log 2>&1; echo "tc tests rc $?"; tail -n 6 gpurun_out/t_tc.log | cut -c1-600
-timeout 600 python profiles/layer_times.py > gpurun_out/layer_times_r01w.txt 2>&1; echo "layer rc $?"; head -1 gpurun_out/layer_times_r01w.txt; grep -E "geglu|conv3 \(16, (64|32), " gpurun_out/layer_times_r01w.txt | head -14
+timeout 600 python -m pytest tests/test_gpu_tensorcore.py -k "attention" -m gpu -q --tb=short -p no:cacheprovider --timeout 300 > gpurun_out/t_attn.log 2>&1; echo "attn tests rc $?"; tail -n 5 gpurun_out/t_attn.log | cut -c1-400
+timeout 600 python profiles/layer_times.py > gpurun_out/layer_times_r01x.txt 2>&1; echo "layer rc $?"; head -1 gpurun_out/layer_times_r01x.txt; grep -E "attn" gpurun_out/layer_times_r01x.txt | head -6
