@@ -6,11 +6,10 @@ import torch
 from gm_diffusion_b200 import ops
 g = torch.Generator(device="cuda").manual_seed(0)
 x = torch.randn(16, 64, 64, 320, device="cuda", generator=g).to(torch.bfloat16)
-w = (torch.randn(320, 2880, device="cuda", generator=g) / 54).to(torch.bfloat16)
+w = ops.pack_conv_weight_tiled((torch.randn(320, 320, 3, 3, device="cuda", generator=g) / 54).to(torch.bfloat16))   # production layout -> halo main loop
 b = torch.randn(320, device="cuda", generator=g)
 a = torch.randn(65536, 320, device="cuda", generator=g).to(torch.bfloat16)
-w2 = (torch.randn(2560, 320, device="cuda", generator=g) / 18).to(torch.bfloat16)
-b2 = torch.randn(2560, device="cuda", generator=g)
+w2, b2 = ops.pack_geglu_weight_tiled((torch.randn(2560, 320, device="cuda", generator=g) / 18).to(torch.bfloat16), torch.randn(2560, device="cuda", generator=g))
 for _ in range(3):
     ops.conv2d(x, w, 320, bias=b)
     ops.gemm(a, w2, bias=b2, geglu=True)
