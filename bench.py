@@ -182,7 +182,7 @@ def run_reference(args):
             "config": workload_config(args.gpus), "cpu_baseline": base,
             "e2e": {"value": base["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "note": "reference pipelines need diffusers (not installable offline); this arm times the oracle port of the same loop on the host cores"}
-    print(json.dumps(line))
+    emit(line)
     return 0
 
 
@@ -260,7 +260,7 @@ def instrumented_step(pipe, B):
 
 
 def run_b200(args):
-    os.environ["NCCL_DEBUG"] = "WARN"  # keep NCCL's version banner off stdout: rank 0 prints exactly one JSON line
+    os.environ.setdefault("NCCL_DEBUG", "WARN")
     from gm_diffusion_b200 import _lib as L
     from gm_diffusion_b200 import dist as D
     rank, local, world = D.init_from_env()
@@ -361,13 +361,29 @@ def run_b200(args):
             "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "kernels": kernels,
             "attention": {"achieved_tflops": at["flop"] / (at["ms"] * 1e-3) / 1e12, "note": "true head dims 40/80/160, true Nk; padding not credited"},
             "cpu_baseline": cpu_base}
-    print(json.dumps(line))
+    emit(line)
     if world > 1:
         torch.distributed.barrier()
+        torch.distributed.destroy_process_group()
     return 0
 
 
+_JSON_OUT = None
+
+
+def emit(line: dict) -> None:
+    """The ONE stdout line of the contract.  File descriptor 1 is pointed at stderr for the whole run (see main), so nothing a
+    library prints on stdout — NCCL's version banner at process-group creation — can land next to it."""
+    out = _JSON_OUT or sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
+
+
 def main():
+    global _JSON_OUT
+    _JSON_OUT = os.fdopen(os.dup(1), "w")
+    sys.stdout.flush()
+    os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=2)

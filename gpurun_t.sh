@@ -1,4 +1,2 @@
 mkdir -p gpurun_out
-timeout 1500 python -m pytest tests -m gpu -q --tb=short -p no:cacheprovider --timeout 900 -x > gpurun_out/t_all.log 2>&1; echo "all gpu tests rc $?"; tail -n 4 gpurun_out/t_all.log | cut -c1-400
-timeout 900 python bench.py --steps 3 --warmup 3 > gpurun_out/bench_r01_j.json 2> gpurun_out/bench_err.log; echo "bench rc $?"; python -c "
-import json; d=json.load(open('gpurun_out/bench_r01_j.json')); print(d['value'], 'img/s', d['ms_per_denoise_step'], 'ms/step; e2e', d['e2e']['value'], 'tail', d['ms_tail_vae_x2_plus_eq1'], 'roofline', d['roofline']['achieved'], d['roofline']['frac'])"
+timeout 1200 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus 2 --steps 2 --warmup 3 > gpurun_out/bench_r01_2gpu.json 2> gpurun_out/bench2_err.log; echo "bench2 rc $?"; tail -c 1500 gpurun_out/bench_r01_2gpu.json; tail -3 gpurun_out/bench2_err.log | cut -c1-300
