@@ -53,6 +53,17 @@ __device__ __forceinline__ float ex2_poly(float x) {
     return __int_as_float(__float_as_int(p) + (__float_as_int(t) << 23));
 }
 
+// Packed exponentials: two bf16 logits in, two bf16 probabilities out, ONE special-function instruction (the probabilities are
+// rounded to bf16 for the P V MMA anyway).  The logit difference x = s*c - m is rounded to bf16 first: relative error of 2^x is
+// <= ln2 * 2^-9 * |x| (0.14 % at |x| < 1, the same size as the bf16 rounding of p itself), which is why the lazy-rescale window
+// is narrowed to LAZY_T when this path is on.
+__device__ __forceinline__ uint32_t ex2_bf16x2(float x_lo, float x_hi) {
+    uint32_t xb, y;
+    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(xb) : "f"(x_hi), "f"(x_lo));
+    asm("ex2.approx.ftz.bf16x2 %0, %1;" : "=r"(y) : "r"(xb));
+    return y;
+}
+
 template <int D>
 struct Cfg {
     static constexpr int NDB = (D + 63) / 64;               // 64-wide d blocks
@@ -89,6 +100,12 @@ struct Cfg {
     // softmax warps are issue/latency-bound, not special-function-bound, so the extra ~8 instructions per element cost more than
     // the freed MUFU slots give back.  Kept for the record, off.
     static constexpr bool POLY_EXP = false;
+    // packed bf16x2 exponentials (see ex2_bf16x2): halve the special-function work and remove the pack, accuracy unchanged
+    // (UNet eps 8.47e-3 either way) — and no faster (388.7 vs 392 TFLOP/s at d = 40): with deeper K/V rings, the polynomial exp2
+    // and this all neutral, what paces the kernel is the per-tile latency chain of a softmax warp (S ready -> tcgen05.ld -> max ->
+    // exp -> P to shared memory -> fence -> arrive), ~1900 cycles per tile per CTA with two CTAs per SM.  Off: fp32 exponentials.
+    static constexpr bool BF16_EXP = false;
+    static constexpr float LAZY_T = BF16_EXP ? 2.0f : 8.0f;  // lazy-rescale window of the running maximum, in log2 units
 };
 
 template <int D>
@@ -232,7 +249,7 @@ attn_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ C
             }
             const float mx = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3));
             const float mt = mx * c;
-            const bool grow = mt > m + 8.0f;           // lazy: keep the stale maximum while exponents stay <= 8
+            const bool grow = mt > m + C::LAZY_T;      // lazy: keep the stale maximum while exponents stay <= LAZY_T
             const float m_new = grow ? mt : m;
             const float alpha = grow ? ex2(m - m_new) : 1.0f;   // first tile: m = -inf -> 0
             const float m_sub = m_new == -INFINITY ? 0.0f : m_new;   // a key half that has seen no valid key yet: p = 2^-inf = 0
@@ -240,10 +257,14 @@ attn_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ C
 #pragma unroll
             for (int k = 0; k < KW / 2; ++k) {
                 const float x0 = fmaf(__uint_as_float(sr[2 * k]), c, -m_sub), x1 = fmaf(__uint_as_float(sr[2 * k + 1]), c, -m_sub);
-                const bool poly = C::POLY_EXP && (k & 1);
-                const float p0 = poly ? ex2_poly(x0) : ex2(x0);
-                const float p1 = poly ? ex2_poly(x1) : ex2(x1);
-                pk[k] = pack_bf16x2(p0, p1);
+                if (C::BF16_EXP) {
+                    pk[k] = ex2_bf16x2(x0, x1);
+                } else {
+                    const bool poly = C::POLY_EXP && (k & 1);
+                    const float p0 = poly ? ex2_poly(x0) : ex2(x0);
+                    const float p1 = poly ? ex2_poly(x1) : ex2(x1);
+                    pk[k] = pack_bf16x2(p0, p1);
+                }
             }
             m = m_new;
             // the P buffer we are about to overwrite was last read by PV_{j-PB}
