@@ -89,7 +89,7 @@ struct Plan {
     static constexpr int OFF_BARS = OFF_BIAS + BN * 4;
     static constexpr int ACC = 2 * MT * BN <= 512 ? 2 : 1;   // TMEM accumulator sets (2 = epilogue overlaps the next tile's main loop)
     static constexpr int ACC_COLS = MT * BN;
-    static constexpr int TOTAL = OFF_BARS + (2 * STAGES + 5 + 2 * A_SLOTS) * 8 + 16 + 1024;
+    static constexpr int TOTAL = OFF_BARS + (2 * STAGES + 5 + 2 * A_SLOTS) * 8 + 16;   // the dynamic smem base is declared 1024-byte aligned
     static constexpr uint32_t TMEM_COLS = ACC * ACC_COLS <= 32 ? 32 : ACC * ACC_COLS <= 64 ? 64 : ACC * ACC_COLS <= 128 ? 128 : ACC * ACC_COLS <= 256 ? 256 : 512;
     static_assert(ACC * ACC_COLS <= 512, "accumulators exceed TMEM");
     static_assert(TOTAL <= 232448, "shared memory plan exceeds 227 KB");
@@ -166,8 +166,11 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__ 
     constexpr int ACC = P::ACC;
     static_assert(!HALO || CL == 1, "the halo main loop is single-CTA");
 
-    extern __shared__ uint8_t smem_raw[];
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    // SWIZZLE_128B tiles need a 1024-byte aligned base; declaring the alignment (instead of rounding the pointer up) gives the
+    // 1 KB of slack back to the plan — it is what lets the fp32-residual instantiation hold a 4th operand stage
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    uint8_t* smem = smem_raw;
+    if (threadIdx.x == 0 && (smem_u32(smem) & 1023u) != 0) { printf("gemm_kernel: dynamic shared memory base is not 1024-byte aligned\n"); __trap(); }
     uint8_t* res_s = smem + P::OFF_RES;
     float* bias_s = reinterpret_cast<float*>(smem + P::OFF_BIAS);
     const uint32_t bias_sa = smem_u32(bias_s);
@@ -772,7 +775,7 @@ int launch_cfg(int bn, int64_t tiles_m, int64_t tiles_n, unsigned gz, const CUte
             if (no_res) return mt2 ? (cl2 ? launch<2, 160, 4, 0, 2>(maps_a, map_w, args, st) : launch<2, 160, 4, 0>(maps_a, map_w, args, st))
                                    : launch<1, 160, 6, 0>(maps_a, map_w, args, st);
             return mt2 ? (cl2 ? launch<2, 160, 3, 2, 2>(maps_a, map_w, args, st) : launch<2, 160, 3, 2>(maps_a, map_w, args, st))
-                       : (res_f32 ? launch<1, 160, 3, 4>(maps_a, map_w, args, st) : launch<1, 160, 5, 2>(maps_a, map_w, args, st));
+                       : (res_f32 ? launch<1, 160, 4, 4>(maps_a, map_w, args, st) : launch<1, 160, 5, 2>(maps_a, map_w, args, st));
         case 128: return mt2 ? (cl2 ? launch<2, 128, 3, 2, 2>(maps_a, map_w, args, st) : launch<2, 128, 3, 2>(maps_a, map_w, args, st))
                              : (res_f32 ? launch<1, 128, 4, 4>(maps_a, map_w, args, st) : launch<1, 128, 5, 2>(maps_a, map_w, args, st));
         case 64: return launch<1, 64, 6, 4>(maps_a, map_w, args, st);
