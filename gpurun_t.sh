@@ -1,4 +1,5 @@
 mkdir -p gpurun_out
-timeout 1200 python -m torch.distributed.run --nnodes=1 --nproc-per-node 4 --master-addr 127.0.0.1 --master-port 29513 bench.py --gpus 4 --steps 2 --warmup 3 > gpurun_out/bench_r01_4gpu.json 2> gpurun_out/bench4_err.log; echo "bench4 rc $?"; wc -l gpurun_out/bench_r01_4gpu.json; python -c "
-import json; d=json.loads(open('gpurun_out/bench_r01_4gpu.json').read().strip().splitlines()[-1]); print(d['value'], d['unit'], 'n_gpus', d['n_gpus'], 'ms/step', d['ms_per_step'], 'e2e', d['e2e']['value'], d['clocks'])"
-timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node 4 --master-addr 127.0.0.1 --master-port 29514 bench.py --impl reference --gpus 4 --steps 1 --warmup 0 > gpurun_out/bench_r01_ref4.json 2> gpurun_out/bench_ref4_err.log; echo "ref4 rc $?"; wc -l gpurun_out/bench_r01_ref4.json; head -c 300 gpurun_out/bench_r01_ref4.json
+timeout 1500 python -m pytest tests -m gpu -q --tb=short -p no:cacheprovider --timeout 900 -x > gpurun_out/t_all.log 2>&1; echo "all gpu tests rc $?"; tail -n 4 gpurun_out/t_all.log | cut -c1-400
+timeout 300 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/smoke.log 2>&1; tail -1 gpurun_out/smoke.log
+timeout 900 python bench.py > gpurun_out/bench_r01_k.json 2> gpurun_out/bench_err.log; echo "bench rc $?"; python -c "
+import json; d=json.load(open('gpurun_out/bench_r01_k.json')); print(d['value'], 'img/s', d['ms_per_denoise_step'], 'ms/step; e2e', d['e2e']['value'], 'tail', d['ms_tail_vae_x2_plus_eq1'], 'roofline', d['roofline']['achieved'], d['roofline']['frac'], 'cpu', d['cpu_baseline'])"
