@@ -1,5 +1,2 @@
 mkdir -p gpurun_out
-timeout 1500 python -m pytest tests -m gpu -q --tb=short -p no:cacheprovider --timeout 900 -x > gpurun_out/t_all.log 2>&1; echo "all gpu tests rc $?"; tail -n 4 gpurun_out/t_all.log | cut -c1-400
-timeout 300 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/smoke.log 2>&1; tail -1 gpurun_out/smoke.log
-timeout 900 python bench.py > gpurun_out/bench_r01_k.json 2> gpurun_out/bench_err.log; echo "bench rc $?"; python -c "
-import json; d=json.load(open('gpurun_out/bench_r01_k.json')); print(d['value'], 'img/s', d['ms_per_denoise_step'], 'ms/step; e2e', d['e2e']['value'], 'tail', d['ms_tail_vae_x2_plus_eq1'], 'roofline', d['roofline']['achieved'], d['roofline']['frac'], 'cpu', d['cpu_baseline'])"
+timeout 600 python -m pytest tests/test_gpu_tensorcore.py -k "halo" -m gpu -q --tb=short -p no:cacheprovider --timeout 300 > gpurun_out/t_tc.log 2>&1; echo "halo tests rc $?"; tail -n 12 gpurun_out/t_tc.log | cut -c1-700
