@@ -196,12 +196,20 @@ class B200UNet:
         fp32 [len(timesteps), sum(Cout)].  (diffusers: get_timestep_embedding -> TimestepEmbedding ->
         per-resnet Linear(SiLU(temb)); depends on t only.)"""
         ts = [float(t) for t in timesteps]
+        key = tuple(ts)
+        cache = self.__dict__.setdefault("_temb_tables", {})
+        if key in cache:                      # depends on the weights and the schedule only: one table per (pipeline, num_inference_steps)
+            return cache[key]
         emb = torch.empty((len(ts), self.ch0), dtype=bf16, device=self.device)
         for i, t in enumerate(ts):
             ops.timestep_embedding(t, 1, self.ch0, self.device, out=emb[i:i + 1])
         h = ops.silu(ops.gemm(emb, self.t1[0], bias=self.t1[1]))
         temb = ops.silu(ops.gemm(h, self.t2[0], bias=self.t2[1]))
-        return ops.gemm(temb, self.w_temb, bias=self.b_temb, out_f32=True)
+        table = ops.gemm(temb, self.w_temb, bias=self.b_temb, out_f32=True)
+        if len(cache) >= 8:
+            cache.clear()
+        cache[key] = table
+        return table
 
     def project_context(self, encoder_hidden_states: torch.Tensor) -> List[torch.Tensor]:
         """Cross-attention K/V of every transformer layer for `encoder_hidden_states` [B,77,768]; identical at
