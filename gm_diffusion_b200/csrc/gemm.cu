@@ -89,9 +89,14 @@ struct Plan {
     static constexpr int OFF_BARS = OFF_BIAS + BN * 4;
     static constexpr int ACC = 2 * MT * BN <= 512 ? 2 : 1;   // TMEM accumulator sets (2 = epilogue overlaps the next tile's main loop)
     static constexpr int ACC_COLS = MT * BN;
-    static constexpr int TOTAL = OFF_BARS + (2 * STAGES + 5 + 2 * A_SLOTS) * 8 + 16;   // the dynamic smem base is declared 1024-byte aligned
-    static constexpr uint32_t TMEM_COLS = ACC * ACC_COLS <= 32 ? 32 : ACC * ACC_COLS <= 64 ? 64 : ACC * ACC_COLS <= 128 ? 128 : ACC * ACC_COLS <= 256 ? 256 : 512;
-    static_assert(ACC * ACC_COLS <= 512, "accumulators exceed TMEM");
+    // ROT: 256-row tiles whose two sets do not fit (2 x 2 x 160 > 512) rotate their two accumulators through THREE BN-column
+    // slots: tile i uses slots (2i) % 3 and (2i+1) % 3, so the next tile's main loop starts as soon as the epilogue has drained
+    // the FIRST sub-tile of this one (the other slot it needs was free all along) — half of the epilogue leaves the critical path
+    static constexpr bool ROT = ACC == 1 && MT == 2 && 3 * BN <= 512;
+    static constexpr int TOTAL = OFF_BARS + (2 * STAGES + 7 + 2 * A_SLOTS) * 8 + 16;   // the dynamic smem base is declared 1024-byte aligned
+    static constexpr int TMEM_USED = ROT ? 3 * BN : ACC * ACC_COLS;
+    static constexpr uint32_t TMEM_COLS = TMEM_USED <= 32 ? 32 : TMEM_USED <= 64 ? 64 : TMEM_USED <= 128 ? 128 : TMEM_USED <= 256 ? 256 : 512;
+    static_assert(TMEM_USED <= 512, "accumulators exceed TMEM");
     static_assert(TOTAL <= 232448, "shared memory plan exceeds 227 KB");
 };
 
@@ -176,9 +181,9 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__ 
     const uint32_t bias_sa = smem_u32(bias_s);
     uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + P::OFF_BARS);
     uint64_t* empty_bar = full_bar + STAGES;
-    uint64_t* acc_full = empty_bar + STAGES;   // [2]
-    uint64_t* acc_empty = acc_full + 2;        // [2]
-    uint64_t* res_bar = acc_empty + 2;         // residual prefetch rounds
+    uint64_t* acc_full = empty_bar + STAGES;   // [3] per accumulator set (or per rotating slot)
+    uint64_t* acc_empty = acc_full + 3;        // [3]
+    uint64_t* res_bar = acc_empty + 3;         // residual prefetch rounds
     uint64_t* a_full = res_bar + 1;            // HALO: A ring (P::A_SLOTS each)
     uint64_t* a_empty = a_full + P::A_SLOTS;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(a_empty + P::A_SLOTS);
@@ -195,7 +200,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__ 
         tma_prefetch_desc(&map_a0);
         tma_prefetch_desc(&map_w);
         for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], CL); }
-        for (int s = 0; s < 2; ++s) { mbar_init(&acc_full[s], 1); mbar_init(&acc_empty[s], 256); }
+        for (int s = 0; s < 3; ++s) { mbar_init(&acc_full[s], 1); mbar_init(&acc_empty[s], 256); }
         mbar_init(res_bar, 256);
         for (int s = 0; s < P::A_SLOTS; ++s) { mbar_init(&a_full[s], 1); mbar_init(&a_empty[s], 1); }
         fence_barrier_init();
@@ -333,9 +338,20 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__ 
             uint32_t ag = 0, kbg = 0, it = 0;
             for (int tile = tile0; tile < num_tiles; tile += tstride, ++it) {
                 const int ab = it % ACC;
-                mbar_wait(&acc_empty[ab], ((it / ACC) & 1) ^ 1);
+                uint32_t tsl[MT];                                     // TMEM column base of each sub-tile's accumulator
+                if (P::ROT) {
+#pragma unroll
+                    for (int s = 0; s < MT; ++s) {
+                        const uint32_t u = 2 * it + s;
+                        mbar_wait(&acc_empty[u % 3], ((u / 3) & 1) ^ 1);
+                        tsl[s] = tmem_acc + (u % 3) * BN;
+                    }
+                } else {
+                    mbar_wait(&acc_empty[ab], ((it / ACC) & 1) ^ 1);
+#pragma unroll
+                    for (int s = 0; s < MT; ++s) tsl[s] = tmem_acc + ab * P::ACC_COLS + s * BN;
+                }
                 tc_fence_after();
-                const uint32_t tacc = tmem_acc + ab * P::ACC_COLS;
                 for (int g = 0; g < groups; ++g, ++ag) {
                     const int slot = ag % P::A_SLOTS;
                     mbar_wait(&a_full[slot], (ag / P::A_SLOTS) & 1);
@@ -351,22 +367,34 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__ 
 #pragma unroll
                             for (int s = 0; s < MT; ++s) {
                                 const uint64_t da = umma_desc_k_sw128(sar + s * P::A_SUB);
-                                umma_bf16_ss(tacc + s * BN, da + 2 * k, db + 2 * k, IDESC, (g | r | k) != 0 ? 1u : 0u);
+                                umma_bf16_ss(tsl[s], da + 2 * k, db + 2 * k, IDESC, (g | r | k) != 0 ? 1u : 0u);
                             }
                         }
                         umma_commit(&empty_bar[stage]);
                     }
                     umma_commit(&a_empty[slot]);
                 }
-                umma_commit(&acc_full[ab]);
+                if (P::ROT) { umma_commit(&acc_full[(2 * it) % 3]); umma_commit(&acc_full[(2 * it + 1) % 3]); }
+                else umma_commit(&acc_full[ab]);
             }
         } else if (!HALO && elect_one()) {
             uint32_t kbg = 0, it = 0;
             for (int tile = tile0; tile < num_tiles; tile += tstride, ++it) {
                 const int ab = it % ACC;
-                mbar_wait(&acc_empty[ab], ((it / ACC) & 1) ^ 1);   // epilogue has drained this accumulator set
+                uint32_t tsl[MT];
+                if (P::ROT) {
+#pragma unroll
+                    for (int s = 0; s < MT; ++s) {
+                        const uint32_t u = 2 * it + s;
+                        mbar_wait(&acc_empty[u % 3], ((u / 3) & 1) ^ 1);
+                        tsl[s] = tmem_acc + (u % 3) * BN;
+                    }
+                } else {
+                    mbar_wait(&acc_empty[ab], ((it / ACC) & 1) ^ 1);   // epilogue has drained this accumulator set
+#pragma unroll
+                    for (int s = 0; s < MT; ++s) tsl[s] = tmem_acc + ab * P::ACC_COLS + s * BN;
+                }
                 tc_fence_after();
-                const uint32_t tacc = tmem_acc + ab * P::ACC_COLS;
                 const int ksl = tile / (args.tiles_mt * tn_c * args.gz);
                 const int kb_begin = ksl * args.kb_per_split;
                 const int kb_end = min(args.num_kb, kb_begin + args.kb_per_split);
@@ -383,13 +411,14 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__ 
                         for (int s = 0; s < MT; ++s) {
                             // +32 bytes per K=16 step inside the 128-byte swizzle row (address field is >> 4)
                             const uint64_t da = umma_desc_k_sw128(sa + s * P::A_SUB);
-                            umma_bf16_ss(tacc + s * BN, da + 2 * k, db + 2 * k, IDESC, (kb > kb_begin || k != 0) ? 1u : 0u);
+                            umma_bf16_ss(tsl[s], da + 2 * k, db + 2 * k, IDESC, (kb > kb_begin || k != 0) ? 1u : 0u);
                         }
                     }
                     if (CL > 1) umma_commit_mc(&empty_bar[stage], (uint16_t)0x3);  // both CTAs' producers write this slot
                     else umma_commit(&empty_bar[stage]);  // frees the smem slot once these MMAs have read it
                 }
-                umma_commit(&acc_full[ab]);  // accumulators of this tile complete
+                if (P::ROT) { umma_commit(&acc_full[(2 * it) % 3]); umma_commit(&acc_full[(2 * it + 1) % 3]); }
+                else umma_commit(&acc_full[ab]);  // accumulators of this tile complete
             }
         }
     } else {
@@ -501,8 +530,10 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__ 
                 }
                 asm volatile("bar.sync 1, 256;" ::: "memory");
             }
-            mbar_wait(&acc_full[ab], (it / ACC) & 1);
-            tc_fence_after();
+            if (!P::ROT) {
+                mbar_wait(&acc_full[ab], (it / ACC) & 1);
+                tc_fence_after();
+            }
             const int out_col_tile = ti.out_col_tile;
             const int64_t zoff_o = ti.zoff_o, zoff_r = ti.zoff_r;
             const bool fast = ti.fast, res_async = ti.res_async;
@@ -514,7 +545,12 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__ 
                 const bool row_ok = ri.ok;
                 const int64_t orow = ri.out_row;
                 const float* rb_row = args.row_bias ? args.row_bias + ri.sample * args.ld_row_bias : nullptr;
-                const uint32_t tsub = taddr_lane + ab * P::ACC_COLS + s * BN;
+                const uint32_t rot_u = 2 * it + s;
+                if (P::ROT) {
+                    mbar_wait(&acc_full[rot_u % 3], (rot_u / 3) & 1);
+                    tc_fence_after();
+                }
+                const uint32_t tsub = P::ROT ? taddr_lane + (rot_u % 3) * BN : taddr_lane + ab * P::ACC_COLS + s * BN;
                 if (fast) {
                     if (geglu) {
 #pragma unroll 1
@@ -648,10 +684,16 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__ 
                     const TileInfo tn = tile_info(tile + tstride);
                     prefetch_residual(tn, row_info(tn, 0));
                 }
+                if (P::ROT) {   // this sub-tile's slot is drained: the next tile's main loop may already need it
+                    tc_fence_before();
+                    mbar_arrive(&acc_empty[rot_u % 3]);
+                }
             }
             // accumulator set drained -> the MMA warp may start the tile after next into it
-            tc_fence_before();
-            mbar_arrive(&acc_empty[ab]);
+            if (!P::ROT) {
+                tc_fence_before();
+                mbar_arrive(&acc_empty[ab]);
+            }
         }
         tc_fence_before();
     }
