@@ -96,7 +96,7 @@ struct Cfg {
     static constexpr uint32_t TMEM_COLS = (SB * BKV + NSET * DPV) <= 128 ? 128 : (SB * BKV + NSET * DPV) <= 256 ? 256 : 512;
     static_assert(NSET == 1 || P_BYTES * PB >= BQ * (DPV + 1) * 4, "merge scratch must fit in the P buffers");
     static constexpr int MIN_CTAS = D <= 80 ? 2 : 1;
-    // half of the exponentials on the FMA pipe (ex2_poly): measured 394 -> 377 TFLOP/s at d = 40 and 353 -> 361 at d = 80 — the
+    // half of the exponentials on the FMA pipe (ex2_poly): measured 394 -> 377 TFLOP/s at d = 40 and 353 -> 361 at d = 80 with every second pair, 393 / 360 with one pair in four — the
     // softmax warps are issue/latency-bound, not special-function-bound, so the extra ~8 instructions per element cost more than
     // the freed MUFU slots give back.  Kept for the record, off.
     static constexpr bool POLY_EXP = false;
@@ -260,7 +260,7 @@ attn_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ C
                 if (C::BF16_EXP) {
                     pk[k] = ex2_bf16x2(x0, x1);
                 } else {
-                    const bool poly = C::POLY_EXP && (k & 1);
+                    const bool poly = C::POLY_EXP && (k & 3) == 3;   // one pair in four
                     const float p0 = poly ? ex2_poly(x0) : ex2(x0);
                     const float p1 = poly ? ex2_poly(x1) : ex2(x1);
                     pk[k] = pack_bf16x2(p0, p1);

@@ -1,4 +1,3 @@
 mkdir -p gpurun_out
-timeout 900 python -m pytest tests/test_gpu_unet.py tests/test_gpu_pipeline.py -m gpu -q --tb=short -p no:cacheprovider --timeout 600 -x > gpurun_out/t_up.log 2>&1; echo "unet/pipe tests rc $?"; tail -n 5 gpurun_out/t_up.log | cut -c1-400
-timeout 900 python bench.py --steps 3 --warmup 3 --no-cpu-baseline > gpurun_out/bench_r01_l.json 2> gpurun_out/bench_err.log; echo "bench rc $?"; python -c "
-import json; d=json.load(open('gpurun_out/bench_r01_l.json')); print(d['value'], 'img/s', d['ms_per_denoise_step'], 'ms/step; tail', d['ms_tail_vae_x2_plus_eq1'], 'roofline', d['roofline']['achieved'])"
+timeout 600 python -m pytest tests/test_gpu_tensorcore.py -k "attention" -m gpu -q --tb=short -p no:cacheprovider --timeout 300 > gpurun_out/t_attn.log 2>&1; echo "attn tests rc $?"; tail -n 3 gpurun_out/t_attn.log | cut -c1-300
+timeout 600 python profiles/layer_times.py > gpurun_out/layer_times_r01ab.txt 2>&1; echo "layer rc $?"; head -1 gpurun_out/layer_times_r01ab.txt; grep -E "attn" gpurun_out/layer_times_r01ab.txt | head -5
