@@ -380,6 +380,96 @@ int dispatch(const gmd_hdr_params* p, const HdrConsts& c, cudaStream_t st) {
     return launch<T, 1, 1, false>(p, c, n, n, n, st);
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// Backward of the same chain (stage-1 training: scripts/stage1/train_vqgan_lora.py:1134-1141 differentiates
+// apply_gm_to_sdr -> TMO -> gamut_compress through torch autograd).  One pass, everything recomputed from the inputs;
+// clamp gradients follow torch.clamp (passed where min <= x <= max), pow follows torch.pow (2.2 * s^1.2).
+// ---------------------------------------------------------------------------------------------
+struct BwdArgs {
+    const float* sdr; const float* gm; const float* grad_out; float* grad_sdr; float* grad_gm;
+    int64_t n_px, batch, ch_stride, px_stride, img_stride;   // element (img, ch, px) at img*img_stride + ch*ch_stride + px*px_stride
+    int ch;             // 1 (flat) or 3
+    int wrt_tmo;        // grad_out is w.r.t. the TMO(+gamut) output (1) or w.r.t. the Eq.(1) output (0)
+};
+
+__device__ __forceinline__ float clamp_mask(float x, float lo, float hi) { return (x >= lo && x <= hi) ? 1.0f : 0.0f; }
+
+__global__ void __launch_bounds__(256) hdr_bwd_kernel(BwdArgs a, HdrConsts c) {
+    const bool do_eq1 = c.flags & GMD_HDR_EQ1;
+    const bool do_gamut = (c.flags & GMD_HDR_GAMUT) && a.ch == 3 && a.wrt_tmo;
+    const int64_t total = a.batch * a.n_px;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t img = i / a.n_px, px = i - img * a.n_px;
+        const int64_t base = img * a.img_stride + px * a.px_stride;
+        float g[3] = {0, 0, 0}, x[3], dlin_ds[3], gain[3], lin[3], m_hdr[3], m_s[3];
+        for (int k = 0; k < a.ch; ++k) g[k] = a.grad_out[base + k * a.ch_stride];
+        // ---- forward recompute up to the TMO input ----
+        for (int k = 0; k < a.ch; ++k) {
+            const float s_raw = a.sdr[base + k * a.ch_stride];
+            if (do_eq1) {
+                const float gmv = a.gm[base + k * a.ch_stride];
+                const float s = fminf(fmaxf(s_raw, 0.0f), 1.0f);
+                m_s[k] = clamp_mask(s_raw, 0.0f, 1.0f);
+                lin[k] = s > 0.0f ? powf(s, 2.2f) : 0.0f;
+                dlin_ds[k] = s > 0.0f ? 2.2f * powf(s, 1.2f) : 0.0f;
+                gain[k] = 1.0f + gmv * c.qmax;
+                float h = (lin[k] + c.eps) * gain[k] - c.eps;
+                m_hdr[k] = 1.0f;
+                if (c.flags & GMD_HDR_CLAMP_OUT) { m_hdr[k] = clamp_mask(h, 0.0f, c.hi); h = fminf(fmaxf(h, 0.0f), c.hi); }
+                x[k] = h;
+            } else {
+                x[k] = s_raw; m_hdr[k] = 1.0f;
+            }
+        }
+        // ---- backward through gamut and TMO ----
+        if (a.wrt_tmo) {
+            float t[3], dt[3];
+            for (int k = 0; k < a.ch; ++k) {
+                switch (c.tmo) {
+                    case GMD_TMO_LINEAR: t[k] = x[k] * c.inv_hi; dt[k] = c.inv_hi; break;
+                    case GMD_TMO_HARD_CLIP: t[k] = fminf(fmaxf(x[k], 0.0f), 1.0f); dt[k] = clamp_mask(x[k], 0.0f, 1.0f); break;
+                    case GMD_TMO_MULOG: {
+                        const float y = x[k] * c.inv_hi;
+                        const float tt = log1pf(c.mu * y) * c.inv_log1p_mu;
+                        t[k] = fminf(fmaxf(tt, 0.0f), 1.0f);
+                        dt[k] = clamp_mask(tt, 0.0f, 1.0f) * c.mu * c.inv_hi * c.inv_log1p_mu / (1.0f + c.mu * y);
+                        break;
+                    }
+                    case GMD_TMO_CUDA: {
+                        const float y0 = x[k] * 0.1f, y = fminf(fmaxf(y0, 0.0f), 1.0f);
+                        t[k] = log1pf(c.mu * y) * c.inv_log1p_mu;
+                        dt[k] = clamp_mask(y0, 0.0f, 1.0f) * 0.1f * c.mu * c.inv_log1p_mu / (1.0f + c.mu * y);
+                        break;
+                    }
+                    default: t[k] = x[k]; dt[k] = 1.0f; break;
+                }
+            }
+            if (do_gamut) {
+                const float M[3][3] = {{1.660491f, -0.587641f, -0.072850f}, {-0.124550f, 1.132900f, -0.008349f}, {-0.018151f, -0.100579f, 1.118730f}};
+                float go[3];
+                for (int r = 0; r < 3; ++r) {
+                    const float o = M[r][0] * t[0] + M[r][1] * t[1] + M[r][2] * t[2];
+                    go[r] = g[r] * clamp_mask(o, 0.0f, 1.0f);
+                }
+                for (int k = 0; k < 3; ++k) g[k] = M[0][k] * go[0] + M[1][k] * go[1] + M[2][k] * go[2];
+            }
+            for (int k = 0; k < a.ch; ++k) g[k] *= dt[k];
+        }
+        // ---- backward through Eq.(1) ----
+        for (int k = 0; k < a.ch; ++k) {
+            const int64_t off = base + k * a.ch_stride;
+            if (do_eq1) {
+                const float gh = g[k] * m_hdr[k];
+                if (a.grad_gm) a.grad_gm[off] = gh * (lin[k] + c.eps) * c.qmax;
+                if (a.grad_sdr) a.grad_sdr[off] = gh * gain[k] * dlin_ds[k] * m_s[k];
+            } else if (a.grad_sdr) {
+                a.grad_sdr[off] = g[k];
+            }
+        }
+    }
+}
+
 }  // namespace
 }  // namespace gmd
 
@@ -426,4 +516,38 @@ extern "C" float gmd_decode_ordered(int32_t v) {
     float f;
     memcpy(&f, &i, sizeof(f));
     return f;
+}
+
+extern "C" int gmd_hdr_reconstruct_bwd(const gmd_hdr_params* p, const float* grad_out, float* grad_sdr, float* grad_gm, int32_t wrt_tmo, void* stream) {
+    using namespace gmd;
+    if (!p || !p->sdr || !grad_out) { set_last_error("gmd_hdr_reconstruct_bwd: null input"); return kErrInvalid; }
+    if (!grad_sdr && !grad_gm) { set_last_error("gmd_hdr_reconstruct_bwd: no gradient requested"); return kErrInvalid; }
+    if ((p->flags & GMD_HDR_EQ1) && !p->gm) { set_last_error("gmd_hdr_reconstruct_bwd: Eq.(1) needs the gain map"); return kErrInvalid; }
+    if (!(p->flags & GMD_HDR_EQ1) && grad_gm) { set_last_error("gmd_hdr_reconstruct_bwd: grad_gm without Eq.(1)"); return kErrInvalid; }
+    if (p->in_dtype != GMD_F32 || (p->flags & (GMD_HDR_DENORM | GMD_HDR_EXP_GAIN))) {
+        set_last_error("gmd_hdr_reconstruct_bwd: fp32 inputs in [0,1] with the linear gain only (the training path)"); return kErrUnsupported;
+    }
+    if ((p->flags & GMD_HDR_GAMUT) && p->layout == GMD_LAYOUT_FLAT) { set_last_error("gmd_hdr_reconstruct_bwd: gamut needs a 3-channel layout"); return kErrInvalid; }
+    if (p->tmo < GMD_TMO_NONE || p->tmo > GMD_TMO_CUDA) { set_last_error("gmd_hdr_reconstruct_bwd: unknown tmo %d", p->tmo); return kErrInvalid; }
+    BwdArgs a{};
+    a.sdr = static_cast<const float*>(p->sdr); a.gm = static_cast<const float*>(p->gm); a.grad_out = grad_out; a.grad_sdr = grad_sdr; a.grad_gm = grad_gm;
+    a.wrt_tmo = wrt_tmo;
+    if (p->layout == GMD_LAYOUT_PLANAR3) { a.ch = 3; a.n_px = p->n_px; a.batch = p->batch; a.ch_stride = p->n_px; a.px_stride = 1; a.img_stride = 3 * p->n_px; }
+    else if (p->layout == GMD_LAYOUT_INTERLEAVED3) { a.ch = 3; a.n_px = p->n_px; a.batch = 1; a.ch_stride = 1; a.px_stride = 3; a.img_stride = 0; }
+    else { a.ch = 1; a.n_px = p->n_px; a.batch = 1; a.ch_stride = 0; a.px_stride = 1; a.img_stride = 0; }
+    const int64_t total = a.batch * a.n_px;
+    if (total == 0) return kOk;
+    HdrConsts c;
+    c.qmax = p->qmax; c.eps = p->eps; c.hi = p->qmax + 1.0f;
+    c.inv_hi = (float)(1.0 / ((double)p->qmax + 1.0));
+    c.flags = p->flags; c.tmo = p->tmo;
+    double mu = p->tmo == GMD_TMO_CUDA ? 5000.0 : (double)p->mu;
+    c.mu = (float)mu;
+    c.inv_log1p_mu = (float)(1.0 / log1p(mu));
+    c.log2_hi = 0.0f; c.rgbe_div = 1.0f; c.rgbe_min = 0.0f;
+    int64_t want = (total + 255) / 256;
+    int grid = (int)(want < 148 * 8 ? want : 148 * 8);
+    hdr_bwd_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(a, c);
+    count_launch(1);
+    return check_launch("hdr_bwd_kernel");
 }

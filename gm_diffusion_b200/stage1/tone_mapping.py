@@ -80,6 +80,61 @@ def _px_shape(t: torch.Tensor, layout: int):
     return (t.shape[0], *t.shape[2:]) if layout == L.LAYOUT_PLANAR3 else tuple(t.shape[:-1])
 
 
+def _needs_grad(*ts) -> bool:
+    return torch.is_grad_enabled() and any(t is not None and t.requires_grad for t in ts)
+
+
+class _HdrChainFn(torch.autograd.Function):
+    """Autograd support for stage-1 training (scripts/stage1/train_vqgan_lora.py:1134-1141 back-propagates through
+    apply_gm_to_sdr -> TMO -> gamut_compress): forward = the fused kernel, backward = `gmd_hdr_reconstruct_bwd`, one launch each."""
+
+    @staticmethod
+    def forward(ctx, sdr, gm, cfg):
+        if sdr.dtype != torch.float32 or (gm is not None and (gm.dtype != torch.float32 or gm.shape != sdr.shape)):
+            raise NotImplementedError("differentiable Eq.(1)/TMO needs fp32 inputs of identical shape (the training path)")
+        sdr_c = sdr.detach().contiguous()
+        gm_c = gm.detach().contiguous() if gm is not None else None
+        hdr, out, _ = _run(sdr_c, gm_c, flags=cfg["flags"], tmo=cfg["tmo"], qmax=cfg["qmax"], eps=cfg["eps"], mu=cfg["mu"],
+                           want_hdr=cfg["which"] == "hdr", want_tmo=cfg["which"] == "tmo", want_minmax=False, layout=cfg["layout"])
+        ctx.save_for_backward(sdr_c, gm_c if gm_c is not None else sdr_c.new_empty(0))
+        ctx.cfg = cfg
+        ctx.has_gm = gm is not None
+        return hdr if cfg["which"] == "hdr" else out
+
+    @staticmethod
+    def backward(ctx, grad):
+        sdr, gm = ctx.saved_tensors
+        cfg = ctx.cfg
+        grad = grad.to(torch.float32).contiguous()
+        p = L.HdrParams()
+        layout = cfg["layout"]
+        if layout is None:
+            layout = L.LAYOUT_PLANAR3 if (sdr.dim() == 4 and sdr.shape[1] == 3 and (cfg["flags"] & L.HDR_GAMUT)) else L.LAYOUT_FLAT
+        if layout == L.LAYOUT_PLANAR3:
+            p.n_px, p.batch = sdr.shape[2] * sdr.shape[3], sdr.shape[0]
+        elif layout == L.LAYOUT_INTERLEAVED3:
+            p.n_px, p.batch = sdr.numel() // 3, 1
+        else:
+            p.n_px, p.batch = sdr.numel(), 1
+        p.sdr, p.gm = sdr.data_ptr(), (gm.data_ptr() if ctx.has_gm else None)
+        p.layout, p.in_dtype, p.flags, p.tmo = layout, L.F32, cfg["flags"], cfg["tmo"]
+        p.qmax, p.eps, p.mu = float(cfg["qmax"]), float(cfg["eps"]), float(cfg["mu"])
+        g_sdr = torch.empty_like(sdr) if ctx.needs_input_grad[0] else None
+        g_gm = torch.empty_like(sdr) if (ctx.has_gm and ctx.needs_input_grad[1]) else None
+        if g_sdr is None and g_gm is None:
+            return None, None, None
+        if sdr.numel():
+            L.check(L.lib().gmd_hdr_reconstruct_bwd(C.byref(p), grad.data_ptr(), L.ptr(g_sdr), L.ptr(g_gm), int(cfg["which"] == "tmo"),
+                                                    L.current_stream()), "gmd_hdr_reconstruct_bwd")
+        return g_sdr, g_gm, None
+
+
+def _chain(sdr, gm, *, flags, tmo, qmax, eps, mu, which, layout=None):
+    """One differentiable output of the fused chain (`which` = "hdr" | "tmo")."""
+    L.require_cuda(sdr, gm)
+    return _HdrChainFn.apply(sdr, gm, dict(flags=flags, tmo=tmo, qmax=qmax, eps=eps, mu=mu, which=which, layout=layout))
+
+
 def _decode_minmax(mm: torch.Tensor) -> Tuple[float, float]:
     lo, hi = mm.tolist()  # device -> host sync, like hdr.max()/hdr.min() at generate_hdr.py:268
     return float(L.lib().gmd_decode_ordered(lo)), float(L.lib().gmd_decode_ordered(hi))
@@ -87,6 +142,8 @@ def _decode_minmax(mm: torch.Tensor) -> Tuple[float, float]:
 
 def linear_scale_tmo(img: torch.Tensor, qmax: float) -> torch.Tensor:
     """tone_mapping.py:14-18."""
+    if _needs_grad(img):
+        return _chain(img, None, flags=0, tmo=L.TMO_LINEAR, qmax=qmax, eps=0, mu=0, which="tmo")
     return _run(img, None, flags=0, tmo=L.TMO_LINEAR, qmax=qmax, eps=0, mu=0, want_hdr=False, want_tmo=True,
                 want_minmax=False)[1]
 
@@ -94,12 +151,16 @@ def linear_scale_tmo(img: torch.Tensor, qmax: float) -> torch.Tensor:
 def hard_clip_tmo(hdr_img: torch.Tensor, qmax: float) -> torch.Tensor:
     """tone_mapping.py:21-26 (qmax ignored, kept for API compatibility)."""
     del qmax
+    if _needs_grad(hdr_img):
+        return _chain(hdr_img, None, flags=0, tmo=L.TMO_HARD_CLIP, qmax=0, eps=0, mu=0, which="tmo")
     return _run(hdr_img, None, flags=0, tmo=L.TMO_HARD_CLIP, qmax=0, eps=0, mu=0, want_hdr=False, want_tmo=True,
                 want_minmax=False)[1]
 
 
 def fix_mulog_tmo(hdr_img: torch.Tensor, qmax: float) -> torch.Tensor:
     """tone_mapping.py:29-36 (mu = 500)."""
+    if _needs_grad(hdr_img):
+        return _chain(hdr_img, None, flags=0, tmo=L.TMO_MULOG, qmax=qmax, eps=0, mu=500.0, which="tmo")
     return _run(hdr_img, None, flags=0, tmo=L.TMO_MULOG, qmax=qmax, eps=0, mu=500.0, want_hdr=False, want_tmo=True,
                 want_minmax=False)[1]
 
@@ -111,18 +172,24 @@ def tmo_cuda(hdr_img: torch.Tensor) -> torch.Tensor:
     lo, hi = _decode_minmax(mm)
     if hdr_img.numel() and not (hi < float("inf")):  # the kernel flags NaN inputs as max = +inf
         raise ValueError("HDR image values should be in the range [0, 1]")
+    if _needs_grad(hdr_img):
+        return _chain(hdr_img, None, flags=0, tmo=L.TMO_CUDA, qmax=0, eps=0, mu=5000.0, which="tmo")
     return out
 
 
 def random_tmo_cuda(hdr_img: torch.Tensor, qmax: float) -> torch.Tensor:
     """tone_mapping.py:50-57: mu ~ U(500, 5000) from Python's `random`, as in the reference."""
     mu = random.uniform(500, 5_000)
+    if _needs_grad(hdr_img):
+        return _chain(hdr_img, None, flags=0, tmo=L.TMO_MULOG, qmax=qmax, eps=0, mu=mu, which="tmo")
     return _run(hdr_img, None, flags=0, tmo=L.TMO_MULOG, qmax=qmax, eps=0, mu=mu, want_hdr=False, want_tmo=True,
                 want_minmax=False)[1]
 
 
 def apply_gm_to_sdr(gm: torch.Tensor, sdr: torch.Tensor, qmax: float = 9, eps: float = 1 / 64) -> torch.Tensor:
     """tone_mapping.py:60-71: hdr = clamp((clamp(sdr,0,1)^2.2 + eps) * (1 + gm*qmax) - eps, 0, qmax+1)."""
+    if _needs_grad(sdr, gm):
+        return _chain(sdr, gm, flags=L.HDR_EQ1 | L.HDR_CLAMP_OUT, tmo=L.TMO_NONE, qmax=qmax, eps=eps, mu=0, which="hdr")
     return _run(sdr, gm, flags=L.HDR_EQ1 | L.HDR_CLAMP_OUT, tmo=L.TMO_NONE, qmax=qmax, eps=eps, mu=0, want_hdr=True,
                 want_tmo=False, want_minmax=False)[0]
 
@@ -132,6 +199,8 @@ def gamut_compress(tmo_hdr_img: torch.Tensor) -> torch.Tensor:
     if tmo_hdr_img.dim() != 4 or tmo_hdr_img.shape[1] != 3:
         # the reference's permute(0,2,3,1) @ [3,3] fails on anything else
         raise RuntimeError(f"gamut_compress expects [B,3,H,W], got {tuple(tmo_hdr_img.shape)}")
+    if _needs_grad(tmo_hdr_img):
+        return _chain(tmo_hdr_img, None, flags=L.HDR_GAMUT, tmo=L.TMO_NONE, qmax=0, eps=0, mu=0, which="tmo", layout=L.LAYOUT_PLANAR3)
     return _run(tmo_hdr_img, None, flags=L.HDR_GAMUT, tmo=L.TMO_NONE, qmax=0, eps=0, mu=0, want_hdr=False, want_tmo=True,
                 want_minmax=False, layout=L.LAYOUT_PLANAR3)[1]
 
@@ -159,6 +228,12 @@ def reconstruct_hdr(sdr: torch.Tensor, gm: torch.Tensor, qmax: float = 99.0, eps
         if gamut:
             raise ValueError("gamut compression needs [B,3,H,W] or channels_last [...,3]")
         layout = L.LAYOUT_FLAT
+    if _needs_grad(sdr, gm):
+        # training: the whole chain as ONE differentiable op (forward one launch, backward one launch)
+        if denormalize or exp_gain or return_minmax or not want_tmo:
+            raise NotImplementedError("differentiable reconstruct_hdr: [0,1] inputs, linear gain, a TMO and/or gamut output, no min/max")
+        out = _chain(sdr, gm, flags=flags, tmo=_TMO[tmo], qmax=qmax, eps=eps, mu=mu, which="tmo", layout=layout)
+        return None, out
     hdr, out, mm = _run(sdr, gm, flags=flags, tmo=_TMO[tmo], qmax=qmax, eps=eps, mu=mu, want_hdr=return_hdr,
                         want_tmo=want_tmo, want_minmax=return_minmax, layout=layout)
     if return_minmax:

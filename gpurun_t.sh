@@ -1,3 +1,2 @@
 mkdir -p gpurun_out
-timeout 600 python -m pytest tests/test_gpu_tensorcore.py -k "attention" -m gpu -q --tb=short -p no:cacheprovider --timeout 300 > gpurun_out/t_attn.log 2>&1; echo "attn tests rc $?"; tail -n 3 gpurun_out/t_attn.log | cut -c1-300
-timeout 600 python profiles/layer_times.py > gpurun_out/layer_times_r01ab.txt 2>&1; echo "layer rc $?"; head -1 gpurun_out/layer_times_r01ab.txt; grep -E "attn" gpurun_out/layer_times_r01ab.txt | head -5
+timeout 600 python -m pytest tests/test_gpu_hdr.py -m gpu -q --tb=short -p no:cacheprovider --timeout 300 > gpurun_out/t_hdr.log 2>&1; echo "hdr tests rc $?"; tail -n 25 gpurun_out/t_hdr.log | cut -c1-600

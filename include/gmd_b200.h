@@ -84,6 +84,11 @@ typedef struct gmd_hdr_params {
 } gmd_hdr_params;
 
 int gmd_hdr_reconstruct(const gmd_hdr_params* p, void* stream);
+/* Backward of the same chain for stage-1 training (scripts/stage1/train_vqgan_lora.py:1134-1141 back-propagates through
+   apply_gm_to_sdr -> TMO -> gamut_compress, tone_mapping.py:14-90, with torch autograd).  `p` describes the forward call (inputs,
+   layout, flags, tmo, qmax, eps, mu; fp32 inputs, no DENORM / EXP_GAIN); grad_out has the forward output's layout and is the
+   gradient w.r.t. the TMO(+gamut) output (wrt_tmo = 1) or w.r.t. the Eq.(1) output (wrt_tmo = 0); grad_sdr / grad_gm are optional. */
+int gmd_hdr_reconstruct_bwd(const gmd_hdr_params* p, const float* grad_out, float* grad_sdr, float* grad_gm, int32_t wrt_tmo, void* stream);
 float gmd_decode_ordered(int32_t v);
 
 /* ------------------------------------------------------------------------------------------ */

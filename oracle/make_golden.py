@@ -79,6 +79,41 @@ def rgbe_golden():
     print("wrote rgbe_cv2.npz (cv2", cv2.__version__, ")")
 
 
+def grad_golden():
+    """tests/golden/tm_grads.npz: gradients of the stage-1 training chain (scripts/stage1/train_vqgan_lora.py:1134-1141:
+    apply_gm_to_sdr(qmax=49) -> fix_mulog_tmo -> gamut_compress) and of each function alone, from torch autograd through the
+    REAL reference tone_mapping.py."""
+    ref = tmo.load_reference_tm()
+    if ref is None:
+        raise SystemExit("reference not present")
+    g = torch.Generator().manual_seed(7)
+    shape = (2, 3, 16, 12)
+    sdr = (torch.rand(shape, generator=g) * 0.96 + 0.02)
+    gm = (torch.rand(shape, generator=g) * 0.96 + 0.02)
+    w = torch.randn(shape, generator=g)
+    out = dict(sdr=sdr.numpy(), gm=gm.numpy(), w=w.numpy())
+
+    def grads(fn, *xs):
+        xs = [x.clone().requires_grad_(True) for x in xs]
+        y = fn(*xs)
+        (y * w).sum().backward()
+        return y.detach().numpy(), [x.grad.numpy() for x in xs]
+
+    y, (g_gm, g_sdr) = grads(lambda a, b: ref.gamut_compress(ref.fix_mulog_tmo(ref.apply_gm_to_sdr(a, b, qmax=49), 49)), gm, sdr)
+    out.update(chain_out=y, chain_g_gm=g_gm, chain_g_sdr=g_sdr)
+    y, (g_gm, g_sdr) = grads(lambda a, b: ref.apply_gm_to_sdr(a, b, qmax=49), gm, sdr)
+    out.update(eq1_out=y, eq1_g_gm=g_gm, eq1_g_sdr=g_sdr)
+    hdr = torch.from_numpy(y)
+    for name, fn in (("mulog", lambda x: ref.fix_mulog_tmo(x, 49)), ("linear", lambda x: ref.linear_scale_tmo(x, 49)),
+                     ("hardclip", lambda x: ref.hard_clip_tmo(x * 0.03, 49)), ("gamut", lambda x: ref.gamut_compress(x * 0.02)),
+                     ("tmo_cuda", lambda x: ref.tmo_cuda(x * 0.3))):
+        y2, (gx,) = grads(fn, hdr)
+        out[f"{name}_out"], out[f"{name}_g"] = y2, gx
+    np.savez_compressed(OUT / "tm_grads.npz", **out)
+    print("wrote tm_grads.npz")
+
+
 if __name__ == "__main__":
     rgbe_golden()
+    grad_golden()
     main()

@@ -198,3 +198,17 @@ def test_radiance_container_roundtrip_and_cv2_read(golden_dir, tmp_path):
         path.write_bytes(pack_radiance(g[f"{name}_rgbe"]))
         back = cv2.imread(str(path), cv2.IMREAD_UNCHANGED)[:, :, ::-1]
         assert np.array_equal(back, g[f"{name}_decoded"]), name
+
+
+def test_tm_oracle_gradients_match_reference_autograd(golden_dir):
+    """The stage-1 training chain is differentiated with autograd in the reference (train_vqgan_lora.py:1134-1141); the oracle's
+    autograd gradients must equal the fixtures taken from the REAL tone_mapping.py (oracle/make_golden.py:grad_golden)."""
+    g = np.load(golden_dir / "tm_grads.npz")
+    w = torch.from_numpy(g["w"])
+    gm = torch.from_numpy(g["gm"]).requires_grad_(True)
+    sdr = torch.from_numpy(g["sdr"]).requires_grad_(True)
+    y = O.gamut_compress(O.fix_mulog_tmo(O.apply_gm_to_sdr(gm, sdr, qmax=49), 49))
+    (y * w).sum().backward()
+    np.testing.assert_allclose(y.detach().numpy(), g["chain_out"], rtol=1e-6, atol=1e-7)
+    np.testing.assert_allclose(gm.grad.numpy(), g["chain_g_gm"], rtol=1e-5, atol=1e-7)
+    np.testing.assert_allclose(sdr.grad.numpy(), g["chain_g_sdr"], rtol=1e-5, atol=1e-7)
