@@ -7,12 +7,13 @@ tone-mapping functions.  Everything numerical runs in hand-written CUDA behind t
 from .stage1 import (apply_gm_to_sdr, fix_mulog_tmo, gamut_compress, hard_clip_tmo, linear_scale_tmo, random_tmo_cuda,
                      reconstruct_for_disk, reconstruct_hdr, rgbe_encode, tmo_cuda)
 from .hdr_io import pack_radiance, save_hdr_image
+from .stage1 import RandomExposureAdjust
 from .pipelines import (StableDiffusionDualUNetImprovedPipeline, StableDiffusionDualUNetPipeline, StableDiffusionGMPipeline)
 from .schedulers import DDIMScheduler, DDPMScheduler, DPMSolverMultistepScheduler, PNDMScheduler
 from .unet import B200UNet
 from .vae import B200Vae, B200VaeDecoder
 
 __version__ = "0.1.0"
-__all__ = ["apply_gm_to_sdr", "fix_mulog_tmo", "gamut_compress", "hard_clip_tmo", "linear_scale_tmo", "random_tmo_cuda",
+__all__ = ["RandomExposureAdjust", "apply_gm_to_sdr", "fix_mulog_tmo", "gamut_compress", "hard_clip_tmo", "linear_scale_tmo", "random_tmo_cuda",
            "tmo_cuda", "reconstruct_hdr", "reconstruct_for_disk", "rgbe_encode", "save_hdr_image", "pack_radiance", "StableDiffusionDualUNetPipeline", "StableDiffusionDualUNetImprovedPipeline",
            "StableDiffusionGMPipeline", "PNDMScheduler", "DDIMScheduler", "DDPMScheduler", "DPMSolverMultistepScheduler", "B200UNet", "B200VaeDecoder", "B200Vae"]

@@ -94,6 +94,7 @@ def lib() -> C.CDLL:
     L.gmd_decode_ordered.restype = C.c_float
     L.gmd_decode_ordered.argtypes = [C.c_int32]
     L.gmd_hdr_reconstruct.argtypes = [C.POINTER(HdrParams), _vp]
+    L.gmd_exposure_adjust.argtypes = [_vp, _vp, _i64, _i32, C.c_double, _f32, _f32, C.c_double, _vp]
     L.gmd_hdr_reconstruct_bwd.argtypes = [C.POINTER(HdrParams), _vp, _vp, _vp, _i32, _vp]
     L.gmd_cfg_sched_step.argtypes = [C.POINTER(SchedParams), _vp]
     L.gmd_latents_nchw_to_px.argtypes = [_vp, _vp, _i64, _i64, _vp]

@@ -470,6 +470,22 @@ __global__ void __launch_bounds__(256) hdr_bwd_kernel(BwdArgs a, HdrConsts c) {
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// RandomExposureAdjust (gm_diffusion/stage1/augmentations.py:24-73) as one elementwise pass:
+//   inverse camera curve ((sigma*y) / (1 + sigma - y + 1e-8))^(1/n)  ->  uint16 discretisation (clamp(x*65535, 0, 65535).round() / 65535)
+//   ->  exposure + display gamma  clamp(x*exposure, 0, 1)^(1/gamma).   Stage flags select sub-chains (the class's helper methods).
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) exposure_kernel(const float* __restrict__ src, float* __restrict__ dst, int64_t n, int stages, float inv_n, float sigma,
+                                                       float exposure, float inv_gamma) {
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        float x = __ldcs(src + i);
+        if (stages & 1) x = powf(__fdiv_rn(__fmul_rn(sigma, x), __fadd_rn(__fsub_rn(__fadd_rn(1.0f, sigma), x), 1e-8f)), inv_n);
+        if (stages & 2) x = __fdiv_rn(rintf(fminf(fmaxf(__fmul_rn(x, 65535.0f), 0.0f), 65535.0f)), 65535.0f);
+        if (stages & 4) x = powf(fminf(fmaxf(__fmul_rn(x, exposure), 0.0f), 1.0f), inv_gamma);
+        __stcs(dst + i, x);
+    }
+}
+
 }  // namespace
 }  // namespace gmd
 
@@ -550,4 +566,19 @@ extern "C" int gmd_hdr_reconstruct_bwd(const gmd_hdr_params* p, const float* gra
     hdr_bwd_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(a, c);
     count_launch(1);
     return check_launch("hdr_bwd_kernel");
+}
+
+extern "C" int gmd_exposure_adjust(const float* src, float* dst, int64_t n, int32_t stages, double n_curve, float sigma, float exposure, double gamma, void* stream) {
+    using namespace gmd;
+    if (n == 0) return kOk;
+    if (!src || !dst || n < 0) { set_last_error("gmd_exposure_adjust: bad arguments"); return kErrInvalid; }
+    if ((stages & 1) && !(n_curve > 0.0)) { set_last_error("gmd_exposure_adjust: camera-curve exponent n must be positive"); return kErrInvalid; }
+    if ((stages & 4) && !(gamma > 0.0)) { set_last_error("gmd_exposure_adjust: gamma must be positive"); return kErrInvalid; }
+    int64_t want = (n + 255) / 256;
+    int grid = (int)(want < 148 * 8 ? want : 148 * 8);
+    // 1/n and 1/gamma as Python computes them: a double division rounded to fp32 when torch.pow receives the scalar
+    exposure_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(src, dst, n, stages, (float)(1.0 / n_curve), sigma, exposure,
+                                                                          (float)(1.0 / gamma));
+    count_launch(1);
+    return check_launch("exposure_kernel");
 }

@@ -1,4 +1,5 @@
 """Stage-1 numerics (Eq.(1), tone-mapping operators, gamut) — same names as gm_diffusion/stage1/__init__.py:8-16."""
+from .augmentations import RandomExposureAdjust
 from .tone_mapping import (
     apply_gm_to_sdr,
     fix_mulog_tmo,
@@ -12,5 +13,5 @@ from .tone_mapping import (
     tmo_cuda,
 )
 
-__all__ = ["apply_gm_to_sdr", "fix_mulog_tmo", "gamut_compress", "hard_clip_tmo", "linear_scale_tmo",
+__all__ = ["RandomExposureAdjust", "apply_gm_to_sdr", "fix_mulog_tmo", "gamut_compress", "hard_clip_tmo", "linear_scale_tmo",
            "random_tmo_cuda", "tmo_cuda", "reconstruct_hdr", "reconstruct_for_disk", "rgbe_encode"]

@@ -88,6 +88,10 @@ int gmd_hdr_reconstruct(const gmd_hdr_params* p, void* stream);
    apply_gm_to_sdr -> TMO -> gamut_compress, tone_mapping.py:14-90, with torch autograd).  `p` describes the forward call (inputs,
    layout, flags, tmo, qmax, eps, mu; fp32 inputs, no DENORM / EXP_GAIN); grad_out has the forward output's layout and is the
    gradient w.r.t. the TMO(+gamut) output (wrt_tmo = 1) or w.r.t. the Eq.(1) output (wrt_tmo = 0); grad_sdr / grad_gm are optional. */
+/* RandomExposureAdjust (gm_diffusion/stage1/augmentations.py:24-73), fp32 elementwise: stages bit 0 = inverse camera curve
+   ((sigma*y)/(1+sigma-y+1e-8))^(1/n), bit 1 = uint16 discretisation, bit 2 = clamp(x*exposure,0,1)^(1/gamma).
+   n_curve and gamma are doubles: the exponents 1/n and 1/gamma are formed in double like the Python expressions and rounded once. */
+int gmd_exposure_adjust(const float* src, float* dst, int64_t n, int32_t stages, double n_curve, float sigma, float exposure, double gamma, void* stream);
 int gmd_hdr_reconstruct_bwd(const gmd_hdr_params* p, const float* grad_out, float* grad_sdr, float* grad_gm, int32_t wrt_tmo, void* stream);
 float gmd_decode_ordered(int32_t v);
 

@@ -113,7 +113,34 @@ def grad_golden():
     print("wrote tm_grads.npz")
 
 
+def exposure_golden():
+    """tests/golden/exposure_reference.npz: the REAL gm_diffusion/stage1/augmentations.py (pure torch) executed by file path."""
+    import importlib.util
+    import random
+    path = "/root/reference/gm_diffusion/stage1/augmentations.py"
+    spec = importlib.util.spec_from_file_location("ref_aug", path)
+    m = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(m)
+    out = {}
+    random.seed(3); torch.manual_seed(3)
+    aug = m.RandomExposureAdjust()
+    g = torch.Generator().manual_seed(9)
+    x = torch.rand(2, 3, 20, 28, generator=g)
+    x.view(-1)[:6] = torch.tensor([0.0, 1.0, 0.5, 1e-6, 0.999999, 0.25])
+    out["x"] = x.numpy()
+    for i in range(4):
+        y, meta = aug(x, return_metadata=True)
+        out[f"y{i}"] = y.numpy()
+        out[f"meta{i}"] = np.array([meta["exposure"], meta["n"], meta["sigma"]], np.float64)
+    out["curve"] = m.RandomExposureAdjust.apply_inv_sigmoid_curve(x, 0.7, 0.55).numpy()
+    out["quant"] = m.RandomExposureAdjust.discretize_to_uint16(x * 1.2 - 0.1).numpy()
+    out["ldr"] = aug.hdr_to_ldr(x * 3, 0.5).numpy()
+    np.savez_compressed(OUT / "exposure_reference.npz", **out)
+    print("wrote exposure_reference.npz")
+
+
 if __name__ == "__main__":
     rgbe_golden()
     grad_golden()
+    exposure_golden()
     main()

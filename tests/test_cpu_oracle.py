@@ -212,3 +212,19 @@ def test_tm_oracle_gradients_match_reference_autograd(golden_dir):
     np.testing.assert_allclose(y.detach().numpy(), g["chain_out"], rtol=1e-6, atol=1e-7)
     np.testing.assert_allclose(gm.grad.numpy(), g["chain_g_gm"], rtol=1e-5, atol=1e-7)
     np.testing.assert_allclose(sdr.grad.numpy(), g["chain_g_sdr"], rtol=1e-5, atol=1e-7)
+
+
+def test_exposure_oracle_matches_reference_fixture(golden_dir):
+    """oracle/augment_oracle.py vs outputs of the REAL augmentations.py for the same seeds (same RNG consumption, same arithmetic)."""
+    import random
+    from oracle import augment_oracle as AO
+    g = np.load(golden_dir / "exposure_reference.npz")
+    x = torch.from_numpy(g["x"])
+    random.seed(3); torch.manual_seed(3)
+    for i in range(4):
+        y, meta = AO.random_exposure_adjust(x)
+        assert [meta["exposure"], meta["n"], meta["sigma"]] == g[f"meta{i}"].tolist()
+        assert np.array_equal(y.numpy(), g[f"y{i}"])
+    assert np.array_equal(AO.apply_inv_sigmoid_curve(x, 0.7, 0.55).numpy(), g["curve"])
+    assert np.array_equal(AO.discretize_to_uint16(x * 1.2 - 0.1).numpy(), g["quant"])
+    assert np.array_equal(AO.hdr_to_ldr(x * 3, 0.5).numpy(), g["ldr"])
