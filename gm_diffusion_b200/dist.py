@@ -56,3 +56,23 @@ def max_over_ranks(value: float, device) -> float:
     t = torch.tensor([value], dtype=torch.float64, device=device)
     dist.all_reduce(t, op=dist.ReduceOp.MAX)
     return float(t.item())
+
+
+class CfgPair:
+    """Optional latency mode of SURVEY.md §8e: two ranks work on the SAME images.  Rank 0 of the pair runs the unconditional half
+    of the SDR UNet's classifier-free-guidance batch, rank 1 the conditional half; the two eps tensors (64 KB per image) are
+    exchanged with one all-gather per step and both ranks run the fused scheduler step redundantly (deterministic, so their
+    latents stay bit-identical).  The GM UNet (no CFG) is split by images across the pair and its eps all-gathered the same way.
+    Because every kernel is batch-independent, the result equals the single-GPU result bit for bit."""
+
+    def __init__(self, group=None):
+        if not dist.is_initialized():
+            raise RuntimeError("CfgPair needs an initialised torch.distributed process group")
+        if dist.get_world_size(group) != 2:
+            raise ValueError(f"CfgPair works on a group of exactly two ranks, got {dist.get_world_size(group)}")
+        self.group = group
+        self.rank = dist.get_rank(group)
+
+    def gather(self, local: torch.Tensor, out: torch.Tensor) -> None:
+        """out[r] = rank r's `local` (stream-ordered on the current CUDA stream)."""
+        dist.all_gather_into_tensor(out, local, group=self.group)

@@ -71,6 +71,15 @@ class StableDiffusionDualUNetPipeline(PipelineBase):
                              f"{self.unet.in_channels} / {self.gm_unet.in_channels}")
         self.gm_scheduler = None
         self._ws: Dict[Any, _Workspace] = {}
+        self._pair_ws: Dict[Any, Dict[str, Any]] = {}
+        self.cfg_pair = None   # gm_diffusion_b200.dist.CfgPair: split the CFG halves / the GM images over two ranks (latency mode)
+
+    def enable_cfg_pair(self, group=None):
+        """SURVEY.md §8e optional mode: see `gm_diffusion_b200.dist.CfgPair`.  Both ranks must call the pipeline with identical
+        arguments; both return the full result."""
+        from ..dist import CfgPair
+        self.cfg_pair = CfgPair(group)
+        return self
 
     # ------------------------------------------------------------------------------------------------------------
     @torch.no_grad()
@@ -151,6 +160,7 @@ class StableDiffusionDualUNetPipeline(PipelineBase):
         self._num_timesteps = len(timesteps)
         self.gm_scheduler = S.clone_scheduler(self.scheduler)  # :1036-1037
 
+        pair = self.cfg_pair if do_cfg else None          # without CFG there is nothing to split between the two ranks
         ws = self._workspace(B, h, w, 2 if do_cfg else 1)
         stream = L.current_stream()
         lat32 = latents.to(device=device, dtype=torch.float32).contiguous()
@@ -162,13 +172,32 @@ class StableDiffusionDualUNetPipeline(PipelineBase):
         # step-invariant work hoisted out of the loop: text K/V per layer, timestep-embedding tables
         sdr_ctx = torch.cat([negative_prompt_embeds, prompt_embeds]) if do_cfg else prompt_embeds  # :983-984
         gm_ctx = prompt_embeds  # conditional half only, no CFG on the GM branch (:1086; batch-correct form VIS:274)
-        ws.set_context("kv_sdr", self.unet.project_context(sdr_ctx))
-        ws.set_context("kv_gm", self.gm_unet.project_context(gm_ctx))
         ts = [int(t) for t in timesteps]
         table_sdr = self.unet.timestep_table(ts)
         table_gm = self.gm_unet.timestep_table(ts)
-        run_sdr = self._unet_runner(("sdr", B, h, w, do_cfg), self.unet, ws.unet_in, ws.temb_sdr, ws.kv_sdr, ws.eps_sdr, cfg_shared=do_cfg)
-        run_gm = self._unet_runner(("gm", B, h, w), self.gm_unet, ws.gm_in, ws.temb_gm, ws.kv_gm, ws.eps_gm)
+        if pair is None:
+            ws.set_context("kv_sdr", self.unet.project_context(sdr_ctx))
+            ws.set_context("kv_gm", self.gm_unet.project_context(gm_ctx))
+            run_sdr = self._unet_runner(("sdr", B, h, w, do_cfg), self.unet, ws.unet_in, ws.temb_sdr, ws.kv_sdr, ws.eps_sdr, cfg_shared=do_cfg)
+            run_gm = self._unet_runner(("gm", B, h, w), self.gm_unet, ws.gm_in, ws.temb_gm, ws.kv_gm, ws.eps_gm)
+            gm_lo, gm_hi = 0, B
+        else:
+            # CFG-pair mode: this rank's CFG half of the SDR UNet on all B images, and its half of the images for the GM UNet;
+            # ws.eps_sdr [2B] is then filled by an all-gather (rank 0 = uncond rows, rank 1 = cond rows), ws.eps_gm likewise
+            half_ctx = negative_prompt_embeds if pair.rank == 0 else prompt_embeds
+            gm_lo, gm_hi = (0, B) if B % 2 else (pair.rank * (B // 2), (pair.rank + 1) * (B // 2))
+            pw = self._pair_ws.setdefault((B, h, w), {})
+            if not pw:
+                f32 = dict(dtype=torch.float32, device=device)
+                pw.update(eps_half=torch.empty((B, h, w, 4), **f32), eps_gm_part=torch.empty((gm_hi - gm_lo, h, w, 4), **f32), kv_sdr=None, kv_gm=None)
+            for name, kv in (("kv_sdr", self.unet.project_context(half_ctx)), ("kv_gm", self.gm_unet.project_context(gm_ctx[gm_lo:gm_hi]))):
+                if pw[name] is None:
+                    pw[name] = kv
+                else:
+                    for a_, b_ in zip(pw[name], kv):
+                        a_.copy_(b_)
+            run_sdr = self._unet_runner(("sdr-pair", B, h, w, pair.rank), self.unet, ws.unet_in, ws.temb_sdr, pw["kv_sdr"], pw["eps_half"])
+            run_gm = self._unet_runner(("gm-pair", B, h, w, pair.rank), self.gm_unet, ws.gm_in[gm_lo:gm_hi], ws.temb_gm, pw["kv_gm"], pw["eps_gm_part"])
         extra = self.prepare_extra_step_kwargs(generator, eta)
         eps_u = ws.eps_sdr[:B].reshape(-1, 4) if do_cfg else None
         eps_c = (ws.eps_sdr[B:] if do_cfg else ws.eps_sdr).reshape(-1, 4)
@@ -182,6 +211,8 @@ class StableDiffusionDualUNetPipeline(PipelineBase):
                 ws.temb_sdr.copy_(table_sdr[i:i + 1])
                 ws.temb_gm.copy_(table_gm[i:i + 1])
                 run_sdr()                                                       # :1052-1060  SDR eps (uncond | cond)
+                if pair is not None:
+                    pair.gather(pw["eps_half"], ws.eps_sdr)                     # [uncond rows of rank 0 | cond rows of rank 1]
                 plan = self.scheduler.plan_step(t, extra["eta"])
                 if plan.needs_noise:                                            # DDIM eta > 0: SDR draw first, then GM (§8a-Q7)
                     ws.sdr.noise = self._draw_noise(B, h, w, generator)
@@ -190,6 +221,11 @@ class StableDiffusionDualUNetPipeline(PipelineBase):
                              x0_coeffs=self.scheduler.x0_coeffs(t), unet_in_next=ws.unet_in, unet_in_dup=1,
                              concat_out=ws.gm_in, concat_tail=ws.gm.x, rescale_ws=ws.rescale_ws)
                 run_gm()                                                        # :1083-1092  GM eps, no CFG
+                if pair is not None:
+                    if gm_hi - gm_lo == B:
+                        ws.eps_gm.copy_(pw["eps_gm_part"])                      # odd batch: both ranks ran all images
+                    else:
+                        pair.gather(pw["eps_gm_part"], ws.eps_gm)
                 gplan = self.gm_scheduler.plan_step(t, extra["eta"])
                 if gplan.needs_noise:
                     ws.gm.noise = self._draw_noise(B, h, w, generator)

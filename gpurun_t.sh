@@ -1,2 +1,2 @@
 mkdir -p gpurun_out
-timeout 600 python -m pytest tests/test_gpu_hdr.py -k "exposure or gradient" -m gpu -q --tb=short -p no:cacheprovider --timeout 300 > gpurun_out/t_hdr.log 2>&1; echo "hdr tests rc $?"; tail -n 25 gpurun_out/t_hdr.log | cut -c1-600
+timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29521 profiles/bench_cfg_pair.py > gpurun_out/pair_bench.log 2>&1; echo "rc $?"; grep "B=" gpurun_out/pair_bench.log
