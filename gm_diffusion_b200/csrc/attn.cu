@@ -64,7 +64,7 @@ __device__ __forceinline__ uint32_t ex2_bf16x2(float x_lo, float x_hi) {
     return y;
 }
 
-template <int D>
+template <int D, bool SHORT = false>
 struct Cfg {
     static constexpr int NDB = (D + 63) / 64;               // 64-wide d blocks
     static constexpr int DP = (D + 15) / 16 * 16;           // K extent of Q K^T
@@ -75,15 +75,18 @@ struct Cfg {
     static constexpr int KS = 2, VS = KS;
     // (measured: three co-resident CTAs per SM with single-buffered S / P at d = 40 reach 354 TFLOP/s vs 378 for two CTAs
     // with double buffering, so the double-buffered configuration stays)
-    static constexpr int SB = 2;                            // S buffers in TMEM
+    // SHORT (text cross-attention, Nk <= 2 key tiles): the whole CTA lives for ~2 tiles, so what matters is how many CTAs are
+    // resident to overlap their prologues (TMEM allocation, Q / K / V round trip) — single S and P buffers, one softmax set:
+    // 112 TMEM columns and ~64 KB of shared memory per CTA at d = 40 instead of 224 columns and 80 KB
+    static constexpr int SB = SHORT ? 1 : 2;                // S buffers in TMEM
     // NSET = 2 (d = 40): the 64 keys of a tile are split between TWO independent softmax warp sets (8 warps), each with its
     // own running maximum, its own O accumulator and its own denominator (flash-decoding style split over keys, merged once
     // at the end).  ncu on the 4-warp version: XU (MUFU) pipe 52 % busy, issue slots 39 % — latency-bound with one softmax
     // warp per sub-partition per CTA; the split doubles the warps in flight without any cross-warp exchange per tile.
-    static constexpr int NSET = D == 40 ? 2 : 1;
+    static constexpr int NSET = (D == 40 && !SHORT) ? 2 : 1;
     static constexpr int KW = BKV / NSET;                   // keys per softmax thread per tile
     static constexpr int THREADS = 64 + 128 * NSET;
-    static constexpr int PB = D == 80 ? 1 : 2;              // P buffers in smem (one at d = 80 keeps two CTAs per SM)
+    static constexpr int PB = (D == 80 || SHORT) ? 1 : 2;   // P buffers in smem (one at d = 80 keeps two CTAs per SM)
     static constexpr int Q_BYTES = NDB * BQ * 128;
     static constexpr int KV_BLOCK_BYTES = BKV * 128;        // one d block of a K or V tile
     static constexpr int K_BYTES = NDB * KV_BLOCK_BYTES;
@@ -95,7 +98,7 @@ struct Cfg {
     static constexpr int SMEM = OFF_BAR + 256 + 1024;
     static constexpr uint32_t TMEM_COLS = (SB * BKV + NSET * DPV) <= 128 ? 128 : (SB * BKV + NSET * DPV) <= 256 ? 256 : 512;
     static_assert(NSET == 1 || P_BYTES * PB >= BQ * (DPV + 1) * 4, "merge scratch must fit in the P buffers");
-    static constexpr int MIN_CTAS = D <= 80 ? 2 : 1;
+    static constexpr int MIN_CTAS = SHORT ? (D == 40 ? 3 : D == 80 ? 2 : 1) : (D <= 80 ? 2 : 1);
     // half of the exponentials on the FMA pipe (ex2_poly): measured 394 -> 377 TFLOP/s at d = 40 and 353 -> 361 at d = 80 with every second pair, 393 / 360 with one pair in four — the
     // softmax warps are issue/latency-bound, not special-function-bound, so the extra ~8 instructions per element cost more than
     // the freed MUFU slots give back.  Kept for the record, off.
@@ -108,11 +111,11 @@ struct Cfg {
     static constexpr float LAZY_T = BF16_EXP ? 2.0f : 8.0f;  // lazy-rescale window of the running maximum, in log2 units
 };
 
-template <int D>
-__global__ void __launch_bounds__(Cfg<D>::THREADS, Cfg<D>::MIN_CTAS)
+template <int D, bool SHORT>
+__global__ void __launch_bounds__(Cfg<D, SHORT>::THREADS, Cfg<D, SHORT>::MIN_CTAS)
 attn_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_k,
             const __grid_constant__ CUtensorMap map_v, const AttnArgs args) {
-    using C = Cfg<D>;
+    using C = Cfg<D, SHORT>;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint8_t* q_smem = smem;
@@ -385,12 +388,12 @@ attn_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ C
     }
 }
 
-template <int D>
+template <int D, bool SHORT>
 int launch(const gmd_attn_params* p, cudaStream_t st) {
-    using C = Cfg<D>;
+    using C = Cfg<D, SHORT>;
     static bool configured = false;
     if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(attn_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM);
+        cudaError_t e = cudaFuncSetAttribute(attn_kernel<D, SHORT>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM);
         if (e != cudaSuccess) { set_last_error("attn: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return kErrCuda; }
         configured = true;
     }
@@ -411,7 +414,7 @@ int launch(const gmd_attn_params* p, cudaStream_t st) {
     a.Nq = p->Nq; a.Nk = p->Nk;
     a.scale_log2 = p->scale * 1.4426950408889634f;
     dim3 grid((p->Nq + BQ - 1) / BQ, p->H, p->B);
-    attn_kernel<D><<<grid, C::THREADS, C::SMEM, st>>>(mq, mk, mv, a);
+    attn_kernel<D, SHORT><<<grid, C::THREADS, C::SMEM, st>>>(mq, mk, mv, a);
     count_launch(1);
     return check_launch("attn_kernel");
 }
@@ -433,9 +436,9 @@ extern "C" int gmd_attn_fwd(const gmd_attn_params* p, void* stream) {
         if (reinterpret_cast<uintptr_t>(q) & 15) { set_last_error("gmd_attn_fwd: pointers must be 16-byte aligned"); return kErrInvalid; }
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     switch (p->d) {
-        case 40: return launch<40>(p, st);
-        case 80: return launch<80>(p, st);
-        case 160: return launch<160>(p, st);
+        case 40: return p->Nk <= 2 * BKV ? launch<40, true>(p, st) : launch<40, false>(p, st);
+        case 80: return launch<80, false>(p, st);   // (the short configuration does not add a third resident CTA at d = 80: measured slightly slower)
+        case 160: return launch<160, false>(p, st);
         default: set_last_error("gmd_attn_fwd: head dim %d not instantiated (40, 80, 160)", p->d); return kErrUnsupported;
     }
 }

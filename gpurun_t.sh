@@ -1,2 +1,3 @@
 mkdir -p gpurun_out
-timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29521 profiles/bench_cfg_pair.py > gpurun_out/pair_bench.log 2>&1; echo "rc $?"; grep "B=" gpurun_out/pair_bench.log
+timeout 600 python -m pytest tests/test_gpu_tensorcore.py -k "attention" -m gpu -q --tb=short -p no:cacheprovider --timeout 300 > gpurun_out/t_attn.log 2>&1; echo "attn tests rc $?"; tail -n 5 gpurun_out/t_attn.log | cut -c1-400
+timeout 600 python profiles/layer_times.py > gpurun_out/layer_times_r01ac.txt 2>&1; echo "layer rc $?"; head -1 gpurun_out/layer_times_r01ac.txt; grep -E "attn.*Nk=77" gpurun_out/layer_times_r01ac.txt | head -8
