@@ -72,13 +72,14 @@ __device__ __forceinline__ float gelu_fast(float x) {
 }
 
 // Shared-memory plan of one CTA.  RB = bytes per element of the residual prefetch buffer (4 holds fp32 or bf16 rows).
-template <int MT, int BN, int STAGES, int RB, int HALO = 0>
+template <int MT, int BN, int STAGES, int RB, int HALO = 0, int PAIR = 0>
 struct Plan {
     static constexpr int A_SUB = BM * BK * 2;               // one 128-row A sub-tile
     // HALO: one A slot holds the pixel rows of all MT sub-tiles PLUS one image row above and below (up to 64 pixels wide), so
     // the three vertical filter taps read the same copy at row offsets 0 / bw / 2*bw (see the HALO main loop)
     static constexpr int A_BYTES = HALO ? (MT * BM + 2 * 64) * BK * 2 : MT * A_SUB;
-    static constexpr int B_BYTES = BN * BK * 2;
+    // PAIR (cta_group::2): each CTA of the pair stages HALF of the weight tile; the MMA reads both halves
+    static constexpr int B_BYTES = (PAIR ? BN / 2 : BN) * BK * 2;
     static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;    // non-HALO ring slot
     static constexpr int A_SLOTS = 2;                         // HALO: A ring depth (B ring depth is STAGES)
     static constexpr int OFF_B = A_SLOTS * A_BYTES;           // HALO: start of the B ring
@@ -124,6 +125,41 @@ __device__ __forceinline__ void umma_commit_mc(uint64_t* bar, uint16_t mask) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(smem_u32(bar)), "h"(mask)
                  : "memory");
 }
+// ---- CTA-pair (cta_group::2) forms; instruction strings as in CUTLASS cute/arch/{copy_sm100_tma,mma_sm100_umma,tmem_allocator_sm100}.hpp ----
+constexpr uint32_t kPeerBitMask = 0xFEFFFFFFu;   // clears the peer bit of a shared-window address: the even (leader) CTA of the pair
+// TMA load issued by EITHER CTA of the pair into its own shared memory, completing on the LEADER's mbarrier
+__device__ __forceinline__ void tma_load_3d_2sm(void* smem_dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1, int c2) {
+    asm volatile("cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+                 ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar) & kPeerBitMask), "r"(c0), "r"(c1), "r"(c2)
+                 : "memory");
+}
+// D[tmem of both CTAs] (+)= A[256 rows: 128 from each CTA's smem] * B[N rows: N/2 from each CTA's smem]; issued by the leader only
+__device__ __forceinline__ void umma_bf16_ss_2sm(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t"
+        "}\n" ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void umma_commit_2sm_mc(uint64_t* bar, uint16_t mask) {
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(smem_u32(bar)), "h"(mask)
+                 : "memory");
+}
+// arrive on the LEADER's copy of a barrier (from either CTA of the pair)
+__device__ __forceinline__ void mbar_arrive_leader(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(smem_u32(bar) & kPeerBitMask) : "memory");
+}
+template <uint32_t kCols>
+__device__ __forceinline__ void tmem_alloc_2sm(uint32_t* smem_slot) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_slot)), "n"(kCols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+template <uint32_t kCols>
+__device__ __forceinline__ void tmem_dealloc_2sm(uint32_t taddr) {
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "n"(kCols) : "memory");
+}
 __device__ __forceinline__ uint32_t cluster_ctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
 __device__ __forceinline__ void cluster_sync_all() {
     asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
@@ -161,13 +197,14 @@ __device__ __forceinline__ void st_bf16x16(__nv_bfloat16* p, const float* v) {
 //     128-row A sub-tiles and TMA-multicasts it into both CTAs' smem, so the A bytes crossing the L2 -> SM fabric are halved
 //     (36 KB instead of 52 KB per k block at 256x160).  A smem slot is recycled only after BOTH CTAs' MMAs have read it
 //     (tcgen05.commit multicast onto both empty barriers).
-template <int MT, int BN, int STAGES, int RB, int CL, int HALO>
+template <int MT, int BN, int STAGES, int RB, int CL, int HALO, int PAIR>
 __global__ void __launch_bounds__(320, 1)
 gemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__ CUtensorMap map_a1,
             const __grid_constant__ CUtensorMap map_a2, const __grid_constant__ CUtensorMap map_a3,
             const __grid_constant__ CUtensorMap map_w, const KernelArgs args) {
-    using P = Plan<MT, BN, STAGES, RB, HALO>;
-    constexpr uint32_t IDESC = umma_idesc_bf16(BM, BN, false, false);
+    using P = Plan<MT, BN, STAGES, RB, HALO, PAIR>;
+    constexpr uint32_t IDESC = umma_idesc_bf16(PAIR ? 2 * BM : BM, BN, false, false);
+    static_assert(!PAIR || (CL == 2 && HALO == 0), "the CTA-pair MMA runs in 2-CTA clusters, plain GEMM main loop");
     constexpr int ACC = P::ACC;
     static_assert(!HALO || CL == 1, "the halo main loop is single-CTA");
 
@@ -188,24 +225,25 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__ 
     uint64_t* a_empty = a_full + P::A_SLOTS;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(a_empty + P::A_SLOTS);
 
-    static_assert(CL == 1 || MT == 2, "the A multicast splits the two 128-row sub-tiles between the two CTAs");
+    static_assert(CL == 1 || MT == 2 || PAIR, "the A multicast splits the two 128-row sub-tiles between the two CTAs");
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
     const int crank = CL > 1 ? (int)cluster_ctarank() : 0;
-    const int tn_c = args.tiles_n / CL;                 // N tile groups (a cluster covers CL neighbouring N tiles)
+    const int tn_c = PAIR ? args.tiles_n : args.tiles_n / CL;   // N tile groups (a multicast cluster covers CL neighbouring N tiles; a PAIR shares one)
     const int num_tiles = args.tiles_mt * tn_c * args.gz * args.ksplit;
     const int tile0 = blockIdx.x / CL, tstride = gridDim.x / CL;
 
     if (threadIdx.x == 0) {
         tma_prefetch_desc(&map_a0);
         tma_prefetch_desc(&map_w);
-        for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], CL); }
-        for (int s = 0; s < 3; ++s) { mbar_init(&acc_full[s], 1); mbar_init(&acc_empty[s], 256); }
+        for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], PAIR ? 1 : CL); }
+        for (int s = 0; s < 3; ++s) { mbar_init(&acc_full[s], 1); mbar_init(&acc_empty[s], PAIR ? 512 : 256); }   // PAIR: both CTAs' epilogues release the leader's
         mbar_init(res_bar, 256);
         for (int s = 0; s < P::A_SLOTS; ++s) { mbar_init(&a_full[s], 1); mbar_init(&a_empty[s], 1); }
         fence_barrier_init();
     }
-    if (warp == 1) tmem_alloc<P::TMEM_COLS>(tmem_slot);
+    if (PAIR) cluster_sync_all();     // both CTAs of the pair are running before the paired TMEM allocation
+    if (warp == 1) { if (PAIR) tmem_alloc_2sm<P::TMEM_COLS>(tmem_slot); else tmem_alloc<P::TMEM_COLS>(tmem_slot); }
     tc_fence_before();
     if (CL > 1) cluster_sync_all();   // barrier inits visible cluster-wide before any multicast / remote arrive
     else __syncthreads();
@@ -252,7 +290,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__ 
             for (int tile = tile0; tile < num_tiles; tile += tstride) {
                 const int mt = tile % args.tiles_mt;
                 const int rest = tile / args.tiles_mt;
-                const int n0 = ((rest % tn_c) * CL + crank) * BN;
+                const int n0 = PAIR ? (rest % tn_c) * BN : ((rest % tn_c) * CL + crank) * BN;
                 const int zk = rest / tn_c;
                 const int zb = zk % args.gz, ksl = zk / args.gz;
                 const int kb_begin = ksl * args.kb_per_split;
@@ -260,7 +298,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__ 
                 int m0[MT], tw0[MT], th0[MT], tn0[MT];
 #pragma unroll
                 for (int s = 0; s < MT; ++s) {
-                    int t = mt * MT + s;
+                    int t = PAIR ? mt * (2 * MT) + 2 * s + crank : mt * MT + s;   // PAIR: sub-tile s = 256 rows, this CTA's half
                     m0[s] = t * BM;
                     int tw = t % args.tiles_w; t /= args.tiles_w;
                     int th = t % args.tiles_h; t /= args.tiles_h;
@@ -272,6 +310,14 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__ 
                     mbar_wait(&empty_bar[stage], phase ^ 1);
                     uint8_t* sa = smem + stage * P::STAGE_BYTES;
                     uint8_t* sb = sa + P::A_BYTES;
+                    if (PAIR) {
+                        // both CTAs load their own rows of A and their half of the weight tile; every byte completes on the leader's barrier
+                        if (crank == 0) mbar_expect_tx(&full_bar[stage], 2 * P::STAGE_BYTES);
+#pragma unroll
+                        for (int s = 0; s < MT; ++s) tma_load_3d_2sm(sa + s * P::A_SUB, &map_a0, &full_bar[stage], kb * BK, m0[s], zb);
+                        tma_load_3d_2sm(sb, &map_w, &full_bar[stage], 0, ((n0 / BN) * args.num_kb + kb) * BN + crank * (BN / 2), 0);
+                        continue;
+                    }
                     mbar_expect_tx(&full_bar[stage], P::STAGE_BYTES);
                     if (args.mode == 0) {
                         if (CL > 1) {
@@ -377,7 +423,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__ 
                 if (P::ROT) { umma_commit(&acc_full[(2 * it) % 3]); umma_commit(&acc_full[(2 * it + 1) % 3]); }
                 else umma_commit(&acc_full[ab]);
             }
-        } else if (!HALO && elect_one()) {
+        } else if (!HALO && (!PAIR || crank == 0) && elect_one()) {   // PAIR: only the leader CTA issues the MMAs
             uint32_t kbg = 0, it = 0;
             for (int tile = tile0; tile < num_tiles; tile += tstride, ++it) {
                 const int ab = it % ACC;
@@ -411,13 +457,18 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__ 
                         for (int s = 0; s < MT; ++s) {
                             // +32 bytes per K=16 step inside the 128-byte swizzle row (address field is >> 4)
                             const uint64_t da = umma_desc_k_sw128(sa + s * P::A_SUB);
-                            umma_bf16_ss(tsl[s], da + 2 * k, db + 2 * k, IDESC, (kb > kb_begin || k != 0) ? 1u : 0u);
+                            if (PAIR) umma_bf16_ss_2sm(tsl[s], da + 2 * k, db + 2 * k, IDESC, (kb > kb_begin || k != 0) ? 1u : 0u);
+                            else umma_bf16_ss(tsl[s], da + 2 * k, db + 2 * k, IDESC, (kb > kb_begin || k != 0) ? 1u : 0u);
                         }
                     }
-                    if (CL > 1) umma_commit_mc(&empty_bar[stage], (uint16_t)0x3);  // both CTAs' producers write this slot
+                    if (PAIR) umma_commit_2sm_mc(&empty_bar[stage], (uint16_t)0x3);
+                    else if (CL > 1) umma_commit_mc(&empty_bar[stage], (uint16_t)0x3);  // both CTAs' producers write this slot
                     else umma_commit(&empty_bar[stage]);  // frees the smem slot once these MMAs have read it
                 }
-                if (P::ROT) { umma_commit(&acc_full[(2 * it) % 3]); umma_commit(&acc_full[(2 * it + 1) % 3]); }
+                if (PAIR) {
+                    if (P::ROT) { umma_commit_2sm_mc(&acc_full[(2 * it) % 3], (uint16_t)0x3); umma_commit_2sm_mc(&acc_full[(2 * it + 1) % 3], (uint16_t)0x3); }
+                    else umma_commit_2sm_mc(&acc_full[ab], (uint16_t)0x3);
+                } else if (P::ROT) { umma_commit(&acc_full[(2 * it) % 3]); umma_commit(&acc_full[(2 * it + 1) % 3]); }
                 else umma_commit(&acc_full[ab]);  // accumulators of this tile complete
             }
         }
@@ -455,7 +506,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__ 
             TileInfo ti;
             ti.mt = tile % args.tiles_mt;
             const int rest = tile / args.tiles_mt;
-            const int nt = (rest % tn_c) * CL + crank;
+            const int nt = PAIR ? rest % tn_c : (rest % tn_c) * CL + crank;
             const int zk = rest / tn_c;
             ti.n0 = nt * BN; ti.zb = zk % args.gz;
             ti.out_col_tile = geglu ? nt * (BN / 2) : ti.n0;
@@ -469,7 +520,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__ 
         struct RowInfo { bool ok; int64_t out_row, sample; };
         auto row_info = [&](const TileInfo& ti, int s) {
             RowInfo ri;
-            int t = ti.mt * MT + s;
+            int t = PAIR ? ti.mt * (2 * MT) + 2 * s + crank : ti.mt * MT + s;
             if (args.mode == 0) {
                 int64_t m = (int64_t)t * BM + row;
                 ri.ok = m < args.M; ri.out_row = m;
@@ -686,13 +737,13 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__ 
                 }
                 if (P::ROT) {   // this sub-tile's slot is drained: the next tile's main loop may already need it
                     tc_fence_before();
-                    mbar_arrive(&acc_empty[rot_u % 3]);
+                    if (PAIR) mbar_arrive_leader(&acc_empty[rot_u % 3]); else mbar_arrive(&acc_empty[rot_u % 3]);
                 }
             }
             // accumulator set drained -> the MMA warp may start the tile after next into it
             if (!P::ROT) {
                 tc_fence_before();
-                mbar_arrive(&acc_empty[ab]);
+                if (PAIR) mbar_arrive_leader(&acc_empty[ab]); else mbar_arrive(&acc_empty[ab]);
             }
         }
         tc_fence_before();
@@ -701,7 +752,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__ 
     else __syncthreads();
     if (warp == 1) {
         tc_fence_after();
-        tmem_dealloc<P::TMEM_COLS>(tmem_acc);
+        if (PAIR) tmem_dealloc_2sm<P::TMEM_COLS>(tmem_acc); else tmem_dealloc<P::TMEM_COLS>(tmem_acc);
     }
 }
 
@@ -738,6 +789,8 @@ __global__ void __launch_bounds__(256) splitk_finalize_kernel(const float* __res
     }
 }
 
+int g_pair_min_kb = 8;            // GMD_PAIR_MIN_KB: shortest K loop (in 64-wide blocks) that takes the CTA-pair path
+bool g_disable_pair = false;      // GMD_NO_PAIR=1: GEMMs stay on single-CTA MMAs (A/B measurements)
 bool g_disable_halo = false;      // GMD_NO_HALO=1: 3x3 convolutions take the one-box-per-tap main loop (A/B measurements)
 bool g_disable_cluster = false;   // GMD_NO_CLUSTER=1 in the environment falls back to single-CTA tiles (A/B measurements)
 
@@ -748,6 +801,10 @@ int sm_count() {
         g_disable_cluster = e && e[0] == '1';
         e = getenv("GMD_NO_HALO");
         g_disable_halo = e && e[0] == '1';
+        e = getenv("GMD_NO_PAIR");
+        g_disable_pair = e && e[0] == '1';
+        e = getenv("GMD_PAIR_MIN_KB");
+        if (e && atoi(e) > 0) g_pair_min_kb = atoi(e);
         int dev = 0;
         cudaGetDevice(&dev);
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
@@ -756,17 +813,17 @@ int sm_count() {
     return sms;
 }
 
-template <int MT, int BN, int STAGES, int RB, int CL = 1, int HALO = 0>
+template <int MT, int BN, int STAGES, int RB, int CL = 1, int HALO = 0, int PAIR = 0>
 int launch(const CUtensorMap* maps_a, const CUtensorMap& map_w, const KernelArgs& args, cudaStream_t st) {
     static bool configured = false;
-    constexpr size_t smem = Plan<MT, BN, STAGES, RB, HALO>::TOTAL;
+    constexpr size_t smem = Plan<MT, BN, STAGES, RB, HALO, PAIR>::TOTAL;
     if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(gemm_kernel<MT, BN, STAGES, RB, CL, HALO>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaError_t e = cudaFuncSetAttribute(gemm_kernel<MT, BN, STAGES, RB, CL, HALO, PAIR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) { set_last_error("gemm: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return kErrCuda; }
         configured = true;
     }
     // persistent: one CTA per SM; with CL = 2 one cluster (two SMs) per pair of N tiles
-    const int64_t items = (int64_t)args.tiles_mt * (args.tiles_n / CL) * args.gz * args.ksplit;
+    const int64_t items = (int64_t)args.tiles_mt * (PAIR ? args.tiles_n : args.tiles_n / CL) * args.gz * args.ksplit;
     const int max_items = sm_count() / CL;
     const int grid = (int)(items < max_items ? items : max_items) * CL;
     cudaLaunchConfig_t cfg = {};
@@ -775,7 +832,7 @@ int launch(const CUtensorMap* maps_a, const CUtensorMap& map_w, const KernelArgs
     attr[0].id = cudaLaunchAttributeClusterDimension;
     attr[0].val.clusterDim.x = CL; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr; cfg.numAttrs = CL > 1 ? 1 : 0;
-    cudaError_t e = cudaLaunchKernelEx(&cfg, gemm_kernel<MT, BN, STAGES, RB, CL, HALO>, maps_a[0], maps_a[1], maps_a[2], maps_a[3], map_w, args);
+    cudaError_t e = cudaLaunchKernelEx(&cfg, gemm_kernel<MT, BN, STAGES, RB, CL, HALO, PAIR>, maps_a[0], maps_a[1], maps_a[2], maps_a[3], map_w, args);
     if (e != cudaSuccess) { set_last_error("gemm: launch: %s", cudaGetErrorString(e)); return kErrCuda; }
     count_launch(1);
     return check_launch("gemm_kernel");
@@ -788,7 +845,7 @@ inline bool want_mt2(int bn, bool res_f32, int64_t tiles_m, int64_t tiles_n, uns
 }
 
 int launch_cfg(int bn, int64_t tiles_m, int64_t tiles_n, unsigned gz, const CUtensorMap* maps_a, const CUtensorMap& map_w,
-               KernelArgs args, cudaStream_t st, bool halo_ok = false) {
+               KernelArgs args, cudaStream_t st, bool halo_ok = false, bool pair_ok = false) {
     // 256-row CTA tiles (two accumulators per tile, B tile reused) for long K loops that still fill the 148 SMs; short K loops
     // keep 128-row tiles with two accumulator SETS so the epilogue overlaps the next tile's main loop.  The fp32 residual
     // stream needs the larger private-row buffer, which only fits next to the 128-row pipeline.
@@ -802,6 +859,15 @@ int launch_cfg(int bn, int64_t tiles_m, int64_t tiles_n, unsigned gz, const CUte
     // pair neighbouring N tiles into 2-CTA clusters that share (multicast) the A operand
     (void)sm_count();  // also reads GMD_NO_CLUSTER once
     const bool cl2 = mt2 && (tiles_n % 2 == 0) && args.ksplit == 1 && (args.mode == 1 || args.kb_src0 == args.num_kb) && !g_disable_cluster;
+    if (pair_ok && args.ksplit == 1) {
+        // CTA pairs (cta_group::2): map_w was built with the half-tile box by the caller.  512-row pair tiles (two 256-row MMAs)
+        // when that still leaves ~one item per pair of SMs and K is long, else 256-row pair tiles with two accumulator sets.
+        const bool pmt2 = args.num_kb >= 16 && ((tiles_m + 3) / 4) * tiles_n >= 60 && !res_f32;
+        args.tiles_mt = (int)(pmt2 ? (tiles_m + 3) / 4 : (tiles_m + 1) / 2);
+        if (no_res) return pmt2 ? launch<2, 160, 5, 0, 2, 0, 1>(maps_a, map_w, args, st) : launch<1, 160, 8, 0, 2, 0, 1>(maps_a, map_w, args, st);
+        if (res_f32) return launch<1, 160, 5, 4, 2, 0, 1>(maps_a, map_w, args, st);        // fp32 residual rows (84 KB) + 5 stages of 26 KB
+        return pmt2 ? launch<2, 160, 4, 2, 2, 0, 1>(maps_a, map_w, args, st) : launch<1, 160, 7, 2, 2, 0, 1>(maps_a, map_w, args, st);
+    }
     if (halo_ok && args.ksplit == 1 && !g_disable_halo) {
         // vertical-tap halo reuse (maps_a[2], maps_a[3] hold the tall boxes, built for this MT by the caller): -31 % operand bytes
         // per k block at 256x160, -26 % at 128x160
@@ -892,7 +958,21 @@ extern "C" int gmd_gemm_fwd(const gmd_gemm_params* p, void* stream) {
         maps_a[1] = maps_a[2] = maps_a[3] = maps_a[0];
     }
     const int w_tile = p->w_tiled >= 1000 ? p->w_tiled - 1000 : p->w_tiled;
-    if (p->w_tiled) {
+    (void)sm_count();   // reads the GMD_NO_* switches once
+    const int64_t num_kb0 = (p->K + BK - 1) / BK, tm0 = (p->M + BM - 1) / BM, tn0 = (p->N + bn - 1) / bn;
+    // CTA-pair main loop: tiled weights (one half-tile TMA box per CTA), no residual stream, enough rows for every pair of SMs,
+    // K long enough for the weight bytes to matter, and not a candidate for the GEMM split-K
+    const bool pair_ok = !g_disable_pair && bn == 160 && p->w_tiled && w_tile == bn && batch == 1 && num_kb0 >= g_pair_min_kb &&
+                         ((tm0 + 1) / 2) * tn0 >= 60 && !p->workspace;
+    if (pair_ok) {
+        const uint64_t total_rows = (uint64_t)tn0 * num_kb0 * bn;
+        uint64_t dims[3] = {BK, total_rows, 1};
+        uint64_t strides[3] = {2, BK * 2, total_rows * BK * 2};
+        uint32_t box[3] = {BK, (uint32_t)bn / 2, 1};
+        // pre-swizzled tiles are already the shared-memory image: copy them verbatim; plain tiles get swizzled by the TMA
+        int rc = encode_tensor_map_bf16(&map_w, p->w, 3, dims, strides, box, p->w_tiled < 1000);
+        if (rc) return rc;
+    } else if (p->w_tiled) {
         if (w_tile != bn || batch != 1) { set_last_error("gmd_gemm_fwd: tiled weights were packed for N tile %d, kernel picks %d (batch %lld)", p->w_tiled, bn, (long long)batch); return kErrInvalid; }
         const uint64_t total_rows = (uint64_t)((p->N + bn - 1) / bn) * ((p->K + BK - 1) / BK) * bn;
         uint64_t dims[3] = {BK, total_rows, 1};
@@ -941,7 +1021,7 @@ extern "C" int gmd_gemm_fwd(const gmd_gemm_params* p, void* stream) {
                                a.rows_per_sample > 0 ? a.rows_per_sample : p->M, a.residual, p->flags & GMD_EPI_RESIDUAL_F32, p->out,
                                p->flags & GMD_EPI_OUT_F32, st);
     }
-    return launch_cfg(bn, tiles_m, tiles_n, (unsigned)batch, maps_a, map_w, a, st);
+    return launch_cfg(bn, tiles_m, tiles_n, (unsigned)batch, maps_a, map_w, a, st, false, pair_ok);
 }
 
 extern "C" int gmd_conv_fwd(const gmd_conv_params* p, void* stream) {

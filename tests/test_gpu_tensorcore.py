@@ -101,6 +101,37 @@ def test_gemm_geglu():
     check(got, h * F.gelu(gate), what="geglu")
 
 
+@pytest.mark.parametrize("M,N,K", [(4096, 1280, 1280), (16384, 640, 640), (4000, 1920, 640), (8192, 320, 2560), (2048, 3840, 1280)])
+def test_gemm_cta_pair(M, N, K):
+    """Tiled weights, no residual, enough rows: the GEMM runs as CTA pairs (tcgen05 cta_group::2, each CTA stages half of the weight tile)."""
+    from gm_diffusion_b200 import ops
+    g = torch.Generator().manual_seed(M % 997 + N + K)
+    a = torch.randn(M, K, generator=g).to(bf).cuda()
+    w = (torch.randn(N, K, generator=g) / math.sqrt(K)).to(bf).cuda()
+    b = torch.randn(N, generator=g).cuda()
+    ref = a.float() @ w.float().t() + b
+    for swz in (True, False):
+        wt = ops.tile_weight(w, swizzle=swz)
+        got = ops.gemm(a, wt, bias=b)
+        check(got, ref, what=f"pair gemm swizzled={swz}")
+        assert torch.equal(got, ops.gemm(a, w, bias=b)), "pair (tiled weights) and single-CTA (plain weights) paths must agree bit for bit"
+    check(ops.gemm(a, ops.tile_weight(w), bias=b, out_f32=True), ref, tol=2e-3, what="pair gemm fp32 out")
+
+
+def test_gemm_cta_pair_geglu():
+    from gm_diffusion_b200 import ops
+    g = torch.Generator().manual_seed(77)
+    M, Cc = 4096, 1280
+    x = torch.randn(M, Cc, generator=g).to(bf).cuda()
+    w = (torch.randn(8 * Cc, Cc, generator=g) / math.sqrt(Cc)).to(bf).cuda()
+    b = (torch.randn(8 * Cc, generator=g) * 0.1).cuda()
+    wt, bt = ops.pack_geglu_weight_tiled(w, b)
+    got = ops.gemm(x, wt, bias=bt, geglu=True)
+    proj = x.float() @ w.float().t() + b
+    h, gate = proj.chunk(2, -1)
+    check(got, h * F.gelu(gate), what="geglu pair")
+
+
 def test_gemm_batched():
     from gm_diffusion_b200 import ops
     g = torch.Generator().manual_seed(4)
