@@ -133,6 +133,11 @@ __device__ __forceinline__ void tma_load_3d_2sm(void* smem_dst, const CUtensorMa
                  ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar) & kPeerBitMask), "r"(c0), "r"(c1), "r"(c2)
                  : "memory");
 }
+__device__ __forceinline__ void tma_load_4d_2sm(void* smem_dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1, int c2, int c3) {
+    asm volatile("cp.async.bulk.tensor.4d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+                 ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar) & kPeerBitMask), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+                 : "memory");
+}
 // D[tmem of both CTAs] (+)= A[256 rows: 128 from each CTA's smem] * B[N rows: N/2 from each CTA's smem]; issued by the leader only
 __device__ __forceinline__ void umma_bf16_ss_2sm(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
     asm volatile(
@@ -204,9 +209,9 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__ 
             const __grid_constant__ CUtensorMap map_w, const KernelArgs args) {
     using P = Plan<MT, BN, STAGES, RB, HALO, PAIR>;
     constexpr uint32_t IDESC = umma_idesc_bf16(PAIR ? 2 * BM : BM, BN, false, false);
-    static_assert(!PAIR || (CL == 2 && HALO == 0), "the CTA-pair MMA runs in 2-CTA clusters, plain GEMM main loop");
+    static_assert(!PAIR || CL == 2, "the CTA-pair MMA runs in 2-CTA clusters");
     constexpr int ACC = P::ACC;
-    static_assert(!HALO || CL == 1, "the halo main loop is single-CTA");
+    static_assert(!HALO || CL == 1 || PAIR, "the halo main loop is single-CTA unless it runs as a CTA pair");
 
     // SWIZZLE_128B tiles need a 1024-byte aligned base; declaring the alignment (instead of rounding the pointer up) gives the
     // 1 KB of slack back to the plan — it is what lets the fp32-residual instantiation hold a 4th operand stage
@@ -263,23 +268,36 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__ 
             for (int tile = tile0; tile < num_tiles; tile += tstride) {
                 const int mt = tile % args.tiles_mt;
                 const int n0 = ((tile / args.tiles_mt) % tn_c) * BN;
-                int t = mt * MT;
+                int t = PAIR ? mt * (2 * MT) + crank * MT : mt * MT;   // PAIR: each CTA of the pair owns MT consecutive row blocks
                 t /= args.tiles_w;                                  // tiles_w == 1
                 const int th0 = (t % args.tiles_h) * args.bh, tn0 = t / args.tiles_h;
                 for (int sx = 0; sx < 3; ++sx) {
                     for (int cc = 0; cc < chunks; ++cc, ++ag) {
                         const int slot = ag % P::A_SLOTS;
                         mbar_wait(&a_empty[slot], ((ag / P::A_SLOTS) & 1) ^ 1);
-                        mbar_expect_tx(&a_full[slot], a_bytes);
-                        if (cc < args.chunks0) tma_load_4d(smem + slot * P::A_BYTES, &map_a2, &a_full[slot], cc * BK, sx - 1, th0 - 1, tn0);
-                        else tma_load_4d(smem + slot * P::A_BYTES, &map_a3, &a_full[slot], (cc - args.chunks0) * BK, sx - 1, th0 - 1, tn0);
+                        const CUtensorMap* am = cc < args.chunks0 ? &map_a2 : &map_a3;
+                        const int ac = cc < args.chunks0 ? cc * BK : (cc - args.chunks0) * BK;
+                        if (PAIR) {
+                            // each CTA loads ITS tall box and ITS half of the weight tile; all bytes complete on the leader's barriers
+                            if (crank == 0) mbar_expect_tx(&a_full[slot], 2 * a_bytes);
+                            tma_load_4d_2sm(smem + slot * P::A_BYTES, am, &a_full[slot], ac, sx - 1, th0 - 1, tn0);
+                        } else {
+                            mbar_expect_tx(&a_full[slot], a_bytes);
+                            tma_load_4d(smem + slot * P::A_BYTES, am, &a_full[slot], ac, sx - 1, th0 - 1, tn0);
+                        }
                         for (int r = 0; r < 3; ++r, ++kbg) {
                             const int kb = (r * 3 + sx) * chunks + cc;
                             const int stage = kbg % STAGES;
                             mbar_wait(&empty_bar[stage], ((kbg / STAGES) & 1) ^ 1);
-                            mbar_expect_tx(&full_bar[stage], P::B_BYTES);
-                            bulk_copy_g2s(smem + P::OFF_B + stage * P::B_BYTES, args.w_bulk + (size_t)((n0 / BN) * args.num_kb + kb) * P::B_BYTES,
-                                          P::B_BYTES, &full_bar[stage]);
+                            if (PAIR) {
+                                if (crank == 0) mbar_expect_tx(&full_bar[stage], 2 * P::B_BYTES);
+                                tma_load_3d_2sm(smem + P::OFF_B + stage * P::B_BYTES, &map_w, &full_bar[stage], 0,
+                                                ((n0 / BN) * args.num_kb + kb) * BN + crank * (BN / 2), 0);
+                            } else {
+                                mbar_expect_tx(&full_bar[stage], P::B_BYTES);
+                                bulk_copy_g2s(smem + P::OFF_B + stage * P::B_BYTES, args.w_bulk + (size_t)((n0 / BN) * args.num_kb + kb) * P::B_BYTES,
+                                              P::B_BYTES, &full_bar[stage]);
+                            }
                         }
                     }
                 }
@@ -298,7 +316,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__ 
                 int m0[MT], tw0[MT], th0[MT], tn0[MT];
 #pragma unroll
                 for (int s = 0; s < MT; ++s) {
-                    int t = PAIR ? mt * (2 * MT) + 2 * s + crank : mt * MT + s;   // PAIR: sub-tile s = 256 rows, this CTA's half
+                    int t = PAIR ? mt * (2 * MT) + crank * MT + s : mt * MT + s;   // PAIR: this CTA owns MT consecutive 128-row blocks of the pair tile
                     m0[s] = t * BM;
                     int tw = t % args.tiles_w; t /= args.tiles_w;
                     int th = t % args.tiles_h; t /= args.tiles_h;
@@ -379,7 +397,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__ 
         }
     } else if (warp == 1) {
         // =============================== MMA issuer ===============================
-        if (HALO && elect_one()) {
+        if (HALO && (!PAIR || crank == 0) && elect_one()) {   // PAIR: only the leader issues MMAs
             const int groups = 3 * (args.chunks0 + args.chunks1);
             uint32_t ag = 0, kbg = 0, it = 0;
             for (int tile = tile0; tile < num_tiles; tile += tstride, ++it) {
@@ -413,14 +431,18 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__ 
 #pragma unroll
                             for (int s = 0; s < MT; ++s) {
                                 const uint64_t da = umma_desc_k_sw128(sar + s * P::A_SUB);
-                                umma_bf16_ss(tsl[s], da + 2 * k, db + 2 * k, IDESC, (g | r | k) != 0 ? 1u : 0u);
+                                if (PAIR) umma_bf16_ss_2sm(tsl[s], da + 2 * k, db + 2 * k, IDESC, (g | r | k) != 0 ? 1u : 0u);
+                                else umma_bf16_ss(tsl[s], da + 2 * k, db + 2 * k, IDESC, (g | r | k) != 0 ? 1u : 0u);
                             }
                         }
-                        umma_commit(&empty_bar[stage]);
+                        if (PAIR) umma_commit_2sm_mc(&empty_bar[stage], (uint16_t)0x3); else umma_commit(&empty_bar[stage]);
                     }
-                    umma_commit(&a_empty[slot]);
+                    if (PAIR) umma_commit_2sm_mc(&a_empty[slot], (uint16_t)0x3); else umma_commit(&a_empty[slot]);
                 }
-                if (P::ROT) { umma_commit(&acc_full[(2 * it) % 3]); umma_commit(&acc_full[(2 * it + 1) % 3]); }
+                if (PAIR) {
+                    if (P::ROT) { umma_commit_2sm_mc(&acc_full[(2 * it) % 3], (uint16_t)0x3); umma_commit_2sm_mc(&acc_full[(2 * it + 1) % 3], (uint16_t)0x3); }
+                    else umma_commit_2sm_mc(&acc_full[ab], (uint16_t)0x3);
+                } else if (P::ROT) { umma_commit(&acc_full[(2 * it) % 3]); umma_commit(&acc_full[(2 * it + 1) % 3]); }
                 else umma_commit(&acc_full[ab]);
             }
         } else if (!HALO && (!PAIR || crank == 0) && elect_one()) {   // PAIR: only the leader CTA issues the MMAs
@@ -520,7 +542,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__ 
         struct RowInfo { bool ok; int64_t out_row, sample; };
         auto row_info = [&](const TileInfo& ti, int s) {
             RowInfo ri;
-            int t = PAIR ? ti.mt * (2 * MT) + 2 * s + crank : ti.mt * MT + s;
+            int t = PAIR ? ti.mt * (2 * MT) + crank * MT + s : ti.mt * MT + s;
             if (args.mode == 0) {
                 int64_t m = (int64_t)t * BM + row;
                 ri.ok = m < args.M; ri.out_row = m;
@@ -845,7 +867,7 @@ inline bool want_mt2(int bn, bool res_f32, int64_t tiles_m, int64_t tiles_n, uns
 }
 
 int launch_cfg(int bn, int64_t tiles_m, int64_t tiles_n, unsigned gz, const CUtensorMap* maps_a, const CUtensorMap& map_w,
-               KernelArgs args, cudaStream_t st, bool halo_ok = false, bool pair_ok = false) {
+               KernelArgs args, cudaStream_t st, bool halo_ok = false, bool pair_ok = false, int halo_mt = 0) {
     // 256-row CTA tiles (two accumulators per tile, B tile reused) for long K loops that still fill the 148 SMs; short K loops
     // keep 128-row tiles with two accumulator SETS so the epilogue overlaps the next tile's main loop.  The fp32 residual
     // stream needs the larger private-row buffer, which only fits next to the 128-row pipeline.
@@ -859,6 +881,13 @@ int launch_cfg(int bn, int64_t tiles_m, int64_t tiles_n, unsigned gz, const CUte
     // pair neighbouring N tiles into 2-CTA clusters that share (multicast) the A operand
     (void)sm_count();  // also reads GMD_NO_CLUSTER once
     const bool cl2 = mt2 && (tiles_n % 2 == 0) && args.ksplit == 1 && (args.mode == 1 || args.kb_src0 == args.num_kb) && !g_disable_cluster;
+    if (pair_ok && halo_ok && args.ksplit == 1) {
+        // halo convolution loop as CTA pairs: each CTA owns one 128-row block (its own tall box) and half of the weight tile, so the
+        // weight ring is 10 KB per slot; maps_a[2..3] and map_w were built for this by the caller
+        (void)halo_mt;   // pairs are used for the 128-row-tile cases only (see gmd_conv_fwd)
+        args.tiles_mt = (int)((tiles_m + 1) / 2);
+        return no_res ? launch<1, 160, 10, 0, 2, 1, 1>(maps_a, map_w, args, st) : launch<1, 160, 8, 2, 2, 1, 1>(maps_a, map_w, args, st);
+    }
     if (pair_ok && args.ksplit == 1) {
         // CTA pairs (cta_group::2): map_w was built with the half-tile box by the caller.  512-row pair tiles (two 256-row MMAs)
         // when that still leaves ~one item per pair of SMs and K is long, else 256-row pair tiles with two accumulator sets.
@@ -1108,18 +1137,24 @@ extern "C" int gmd_conv_fwd(const gmd_conv_params* p, void* stream) {
     // pairs of 128-row sub-tiles vertically adjacent inside an image, pre-swizzled weight tiles (bulk-copied)
     bool halo_ok = p->ksize == 3 && p->stride == 1 && !p->upsample && bw <= 64 && bw >= 8 && bw == p->W && bn == 1 && bw * bh == BM &&
                    p->w_tiled >= 1000 && !(p->flags & GMD_EPI_RESIDUAL_F32) && (bnt == 160 || bnt == 128) && a.num_kb >= 16;
+    bool conv_pair = false;   // run the halo loop as CTA pairs (cta_group::2)
+    int mtv = 1;              // 128-row blocks per CTA tile
+    if (halo_ok && conv_splitk_rule(Ho, Wo, a.num_kb, p->Cout, true) > 1 && p->workspace) halo_ok = false;
     if (halo_ok) {
+        (void)sm_count();
         const int64_t tm = (int64_t)a.tiles_w * a.tiles_h * ((p->N + bn - 1) / bn), tnn = (p->Cout + bnt - 1) / bnt;
-        const bool pair = want_mt2(bnt, false, tm, tnn, 1u, a.num_kb);
-        if (pair && (a.tiles_h % 2)) halo_ok = false;     // 256-row tiles must pair two row blocks of the SAME image
-        else {
-            const bool split = conv_splitk_rule(Ho, Wo, a.num_kb, p->Cout, true) > 1 && p->workspace;
-            if (split) halo_ok = false;
+        // CTA pairs only where the single-CTA choice would be 128-row tiles (batch-8 layers at 16x16: 128 CTAs on 148 SMs, +6 %);
+        // the 256-row halo tiles are MMA-bound already and measured neutral as pairs (9.26 vs 9.22-9.28 ms of convolutions per step)
+        const bool single_mt2 = want_mt2(bnt, false, tm, tnn, 1u, a.num_kb);
+        conv_pair = !g_disable_pair && bnt == 160 && !single_mt2 && ((tm + 1) / 2) * tnn >= 60;
+        if (conv_pair) {
+            mtv = 1;
+        } else {
+            mtv = single_mt2 ? 2 : 1;
+            if (mtv == 2 && (a.tiles_h % 2)) halo_ok = false;     // 256-row tiles must pair two row blocks of the SAME image
         }
     }
     if (halo_ok) {
-        const int64_t tm = (int64_t)a.tiles_w * a.tiles_h * ((p->N + bn - 1) / bn), tnn = (p->Cout + bnt - 1) / bnt;
-        const int mtv = want_mt2(bnt, false, tm, tnn, 1u, a.num_kb) ? 2 : 1;
         const uint32_t hbox[4] = {BK, (uint32_t)bw, (uint32_t)(mtv * bh + 2), 1};
         uint64_t dims[4] = {(uint64_t)p->C0, (uint64_t)p->W, (uint64_t)p->H, (uint64_t)p->N};
         uint64_t strides[4] = {2, (uint64_t)p->C0 * 2, (uint64_t)p->W * p->C0 * 2, (uint64_t)p->H * p->W * p->C0 * 2};
@@ -1133,7 +1168,18 @@ extern "C" int gmd_conv_fwd(const gmd_conv_params* p, void* stream) {
             if (rc) return rc;
         }
     }
-    if (p->w_tiled) {
+    if (halo_ok && conv_pair) {
+        // half-tile boxes of the pre-swizzled weight image, copied verbatim (SWIZZLE_NONE): one per CTA of the pair
+        if (p->w_tiled - 1000 != bnt) { set_last_error("gmd_conv_fwd: tiled weights were packed for N tile %d, kernel picks %d", p->w_tiled, bnt); return kErrInvalid; }
+        const uint64_t total_rows = (uint64_t)((p->Cout + bnt - 1) / bnt) * a.num_kb * bnt;
+        uint64_t dims[3] = {BK, total_rows, 1};
+        uint64_t strides[3] = {2, BK * 2, total_rows * BK * 2};
+        uint32_t boxw[3] = {BK, (uint32_t)bnt / 2, 1};
+        int rc = encode_tensor_map_bf16(&map_w, p->w, 3, dims, strides, boxw, false);
+        if (rc) return rc;
+        a.w_tiled = 1;
+        a.w_bulk = static_cast<const uint8_t*>(p->w);
+    } else if (p->w_tiled) {
         // [N tile][k block = tap * chunks + chunk][bnt rows][64]: channels of every tap zero-padded to whole 64-blocks at pack time
         if ((p->w_tiled >= 1000 ? p->w_tiled - 1000 : p->w_tiled) != bnt) { set_last_error("gmd_conv_fwd: tiled weights were packed for N tile %d, kernel picks %d", p->w_tiled, bnt); return kErrInvalid; }
         const uint64_t total_rows = (uint64_t)((p->Cout + bnt - 1) / bnt) * a.num_kb * bnt;
@@ -1188,5 +1234,5 @@ extern "C" int gmd_conv_fwd(const gmd_conv_params* p, void* stream) {
         return launch_finalize(a, static_cast<const float*>(p->workspace), ks, rows, p->Cout, a.bias, a.row_bias, a.ld_row_bias, (int64_t)Ho * Wo,
                                a.residual, p->flags & GMD_EPI_RESIDUAL_F32, p->out, p->flags & GMD_EPI_OUT_F32, st);
     }
-    return launch_cfg(bnt, tiles_m, tiles_nn, p->upsample ? 4u : 1u, maps_a, map_w, a, st, halo_ok);
+    return launch_cfg(bnt, tiles_m, tiles_nn, p->upsample ? 4u : 1u, maps_a, map_w, a, st, halo_ok, halo_ok && conv_pair, mtv);
 }

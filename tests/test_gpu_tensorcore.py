@@ -189,7 +189,8 @@ def test_conv_stride2_upsample_concat_epilogue():
 
 @pytest.mark.parametrize("N,H,W,C0,C1,Cout", [(8, 64, 64, 320, 0, 320), (16, 32, 32, 640, 0, 640), (16, 16, 16, 1280, 0, 1280), (8, 64, 64, 640, 320, 320),
                                                 (6, 32, 32, 1280, 640, 640), (9, 64, 64, 128, 0, 128),
-                                                (5, 34, 32, 192, 0, 160), (3, 33, 64, 128, 0, 320)])   # ragged last row block (128-row halo tiles)
+                                                (5, 34, 32, 192, 0, 160), (3, 33, 64, 128, 0, 320),    # ragged last row block (128-row halo tiles)
+                                                (8, 16, 16, 1280, 0, 1280), (7, 16, 16, 1280, 1280, 1280)])   # 128-row tiles run as CTA pairs (cta_group::2)
 def test_conv3x3_halo_main_loop(N, H, W, C0, C1, Cout):
     """Problems big enough for the 256-row tiles: the 3x3 main loop loads one tall box per (horizontal tap, channel chunk) and the
     three vertical taps read it at shifted rows.  Checked against torch, against a batch of one (bit-exact) and with the epilogue extras."""
