@@ -23,6 +23,9 @@ namespace gmd {
 void count_launch(int n);
 namespace {
 
+#ifndef GMD_ATTN_PIPE
+#define GMD_ATTN_PIPE 0
+#endif
 constexpr int BQ = 128;   // query rows per CTA
 constexpr int BKV = 64;   // keys per tile (one 128-byte swizzle row of P)
 
@@ -109,6 +112,12 @@ struct Cfg {
     // exp -> P to shared memory -> fence -> arrive), ~1900 cycles per tile per CTA with two CTAs per SM.  Off: fp32 exponentials.
     static constexpr bool BF16_EXP = false;
     static constexpr float LAZY_T = BF16_EXP ? 2.0f : 8.0f;  // lazy-rescale window of the running maximum, in log2 units
+    // software-pipelined TMEM reads of S in the softmax warps (needs the double-buffered S): see `tile` in the kernel.  Measured
+    // and OFF: with the request for S_{j+1} issued in the middle of tile j's exponentials (no spills) d = 40 drops from 413 to 346
+    // TFLOP/s and d = 160 from 228 to 210 — an in-flight tcgen05.ld does not overlap the MUFU stream of the same warp.  What did
+    // help is storing every 16-byte chunk of P as soon as its eight probabilities exist (376 -> 413 at d = 40, 141 -> 228 at d = 160).
+    static constexpr bool PIPE = SB == 2 && GMD_ATTN_PIPE;
+    static constexpr int PIPE_AT = KW == 32 ? 8 : 16;   // pair index in the exponential loop where S_{j+1} is requested (d = 80: later, register budget of two CTAs/SM)                   // pair index in the exponential loop where S_{j+1} is requested
 };
 
 template <int D, bool SHORT>
@@ -223,21 +232,18 @@ attn_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ C
         const uint32_t my_o = tmem_o + set * C::DPV + lane_off;
         const float c = args.scale_log2;
         float m = -INFINITY;   // running (possibly stale) row maximum of THIS key half in scaled log2 units
-        for (int j = 0; j < T; ++j) {
+        // S_j -> registers (asynchronous: the values are valid after tmem_wait_ld)
+        auto load_s = [&](int j, uint32_t (&dst)[KW]) {
             mbar_wait(&s_full[j % C::SB], (j / C::SB) & 1);
             tc_fence_after();
-            uint32_t sr[KW];
-            if constexpr (KW == 64) {
-                uint32_t t0[32], t1[32];
-                tmem_ld_32x32(tmem_base + (j % C::SB) * BKV + lane_off, t0);
-                tmem_ld_32x32(tmem_base + (j % C::SB) * BKV + lane_off + 32, t1);
-                tmem_wait_ld();
-#pragma unroll
-                for (int k = 0; k < 32; ++k) { sr[k] = t0[k]; sr[32 + k] = t1[k]; }
-            } else {
-                tmem_ld_32x32(tmem_base + (j % C::SB) * BKV + lane_off + set * KW, sr);
-                tmem_wait_ld();
-            }
+            const uint32_t a = tmem_base + (j % C::SB) * BKV + lane_off + set * KW;
+            if constexpr (KW == 64) tmem_ld_32x64(a, dst); else tmem_ld_32x32(a, dst);
+        };
+        // One key tile.  PIPE: the logits of tile j were requested during tile j-1 and the request for tile j+1 goes out in the
+        // middle of this tile's exponentials, so neither the wait for S nor the TMEM read latency is on this warp's per-tile chain.
+        auto tile = [&](int j, uint32_t (&sr)[KW], uint32_t (&sn)[KW]) {
+            if constexpr (!C::PIPE) load_s(j, sr);
+            tmem_wait_ld();
             const int valid = args.Nk - j * BKV - set * KW;  // columns >= valid are padding keys (last tile only)
             if (valid < KW) {
 #pragma unroll
@@ -256,34 +262,35 @@ attn_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ C
             const float m_new = grow ? mt : m;
             const float alpha = grow ? ex2(m - m_new) : 1.0f;   // first tile: m = -inf -> 0
             const float m_sub = m_new == -INFINITY ? 0.0f : m_new;   // a key half that has seen no valid key yet: p = 2^-inf = 0
-            uint32_t pk[KW / 2];
-#pragma unroll
-            for (int k = 0; k < KW / 2; ++k) {
-                const float x0 = fmaf(__uint_as_float(sr[2 * k]), c, -m_sub), x1 = fmaf(__uint_as_float(sr[2 * k + 1]), c, -m_sub);
-                if (C::BF16_EXP) {
-                    pk[k] = ex2_bf16x2(x0, x1);
-                } else {
-                    const bool poly = C::POLY_EXP && (k & 3) == 3;   // one pair in four
-                    const float p0 = poly ? ex2_poly(x0) : ex2(x0);
-                    const float p1 = poly ? ex2_poly(x1) : ex2(x1);
-                    pk[k] = pack_bf16x2(p0, p1);
-                }
-            }
-            m = m_new;
-            // the P buffer we are about to overwrite was last read by PV_{j-PB}
+            // the P buffer we are about to overwrite was last read by PV_{j-PB} (long complete: two tiles ago)
             if (j >= C::PB) {
                 const int jj = j - C::PB;
                 mbar_wait(&pv_done[jj & 1], (jj >> 1) & 1);
             }
-            {
-                // P row -> smem, K-major SWIZZLE_128B: 16-byte chunk c of row r lands at chunk (c ^ (r & 7))
-                uint8_t* prow = p_smem + (C::PB == 2 ? (j & 1) : 0) * C::P_BYTES + row * 128;
+            // P row -> smem, K-major SWIZZLE_128B: 16-byte chunk c of row r lands at chunk (c ^ (r & 7)); every chunk is stored as
+            // soon as its eight probabilities exist, so at most four packed registers are live next to the in-flight S_{j+1}
+            uint8_t* prow = p_smem + (C::PB == 2 ? (j & 1) : 0) * C::P_BYTES + row * 128;
+            uint32_t pk[4];
 #pragma unroll
-                for (int ch = 0; ch < KW / 8; ++ch) {
-                    const int cc = set * (KW / 8) + ch;
-                    *reinterpret_cast<uint4*>(prow + ((cc ^ (row & 7)) << 4)) = make_uint4(pk[4 * ch], pk[4 * ch + 1], pk[4 * ch + 2], pk[4 * ch + 3]);
+            for (int k = 0; k < KW / 2; ++k) {
+                if (C::PIPE && k == C::PIPE_AT) {
+                    if (j + 1 < T) load_s(j + 1, sn);
+                }
+                const float x0 = fmaf(__uint_as_float(sr[2 * k]), c, -m_sub), x1 = fmaf(__uint_as_float(sr[2 * k + 1]), c, -m_sub);
+                if (C::BF16_EXP) {
+                    pk[k & 3] = ex2_bf16x2(x0, x1);
+                } else {
+                    const bool poly = C::POLY_EXP && (k & 3) == 3;   // one pair in four
+                    const float p0 = poly ? ex2_poly(x0) : ex2(x0);
+                    const float p1 = poly ? ex2_poly(x1) : ex2(x1);
+                    pk[k & 3] = pack_bf16x2(p0, p1);
+                }
+                if ((k & 3) == 3) {
+                    const int cc = set * (KW / 8) + (k >> 2);
+                    *reinterpret_cast<uint4*>(prow + ((cc ^ (row & 7)) << 4)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
                 }
             }
+            m = m_new;
             // ones column of V_j (column D of the zero padding) -> the P V MMA also accumulates the softmax denominator
             if (set == 0) {
                 const int st = j % C::VS;
@@ -297,6 +304,7 @@ attn_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ C
             if (j > 0 && __any_sync(0xffffffffu, grow)) {
                 mbar_wait(&pv_done[(j - 1) & 1], ((j - 1) >> 1) & 1);   // O must be complete up to tile j-1
                 tc_fence_after();
+                if constexpr (C::PIPE) tmem_wait_ld();   // the in-flight read of S_{j+1} must land before the scratch registers below are recycled
 #pragma unroll
                 for (int ch = 0; ch < C::DPV / 16; ++ch) {
                     uint32_t o[16];
@@ -311,6 +319,14 @@ attn_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ C
             fence_proxy_async_smem();
             tc_fence_before();
             mbar_arrive(&p_full[j & 1]);
+        };
+        {
+            uint32_t sa[KW], sb[KW];
+            if constexpr (C::PIPE) load_s(0, sa);
+            for (int j = 0; j < T; j += 2) {
+                tile(j, sa, sb);
+                if (j + 1 < T) tile(j + 1, sb, sa);
+            }
         }
         mbar_wait(&pv_done[(T - 1) & 1], ((T - 1) >> 1) & 1);
         tc_fence_after();
