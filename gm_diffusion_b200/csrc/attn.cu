@@ -26,6 +26,22 @@ namespace {
 #ifndef GMD_ATTN_PIPE
 #define GMD_ATTN_PIPE 0
 #endif
+#ifndef GMD_ATTN_ALT
+#define GMD_ATTN_ALT 1
+#endif
+// Three follow-ups suggested by the ncu stall samples of the ALT kernel (23 % of all samples sit on the s_full / pv_done / v_full
+// waits of the softmax warps) were built, measured at B=16, N=4096 and left OFF: a 4-deep V ring (416 vs 419 TFLOP/s), S_{j+3}
+// queued ahead of P V_j to force the sets half a tile apart (354), the first two P chunks held in registers across the pv_done wait
+// (371 with all three on).  The waits are slack, not the critical path.
+#ifndef GMD_ATTN_VS
+#define GMD_ATTN_VS 2
+#endif
+#ifndef GMD_ATTN_SEARLY
+#define GMD_ATTN_SEARLY 0
+#endif
+#ifndef GMD_ATTN_PVHOLD
+#define GMD_ATTN_PVHOLD 0
+#endif
 constexpr int BQ = 128;   // query rows per CTA
 constexpr int BKV = 64;   // keys per tile (one 128-byte swizzle row of P)
 
@@ -75,7 +91,7 @@ struct Cfg {
     static_assert(DPV <= NDB * 64, "ones column must fall inside the loaded V blocks");
     // K / V ring depths (measured at d = 40: 3-deep rings change nothing, 394 vs 392 TFLOP/s — the kernel is not waiting for K/V;
     // 4-deep rings cost the second resident CTA)
-    static constexpr int KS = 2, VS = KS;
+    static constexpr int KS = 2;
     // (measured: three co-resident CTAs per SM with single-buffered S / P at d = 40 reach 354 TFLOP/s vs 378 for two CTAs
     // with double buffering, so the double-buffered configuration stays)
     // SHORT (text cross-attention, Nk <= 2 key tiles): the whole CTA lives for ~2 tiles, so what matters is how many CTAs are
@@ -88,6 +104,15 @@ struct Cfg {
     // warp per sub-partition per CTA; the split doubles the warps in flight without any cross-warp exchange per tile.
     static constexpr int NSET = (D == 40 && !SHORT) ? 2 : 1;
     static constexpr int KW = BKV / NSET;                   // keys per softmax thread per tile
+    // ALT (d = 40): the two warp sets own ALTERNATING WHOLE TILES (set s: tiles j = s mod 2, S buffer s, P buffer s, O accumulator s)
+    // instead of the two key halves of every tile.  Per synchronisation round a thread now handles 64 keys instead of 32 (half the
+    // barrier / fence / arrive overhead per exponential) and the two sets of a CTA run out of phase, so an SM has four independent
+    // softmax phase groups instead of two to keep the special-function pipe fed.  The exponentials of the first 32 keys use the
+    // running (stale) maximum without waiting for this tile's maximum; the tile maximum is known before the second 32, and a growth
+    // beyond the lazy window (rare after the first tile) redoes the first half from TMEM.
+    static constexpr bool ALT = NSET == 2 && GMD_ATTN_ALT;
+    // V ring depth (see GMD_ATTN_VS above: deeper rings measured neutral)
+    static constexpr int VS = ALT ? GMD_ATTN_VS : KS;
     static constexpr int THREADS = 64 + 128 * NSET;
     static constexpr int PB = (D == 80 || SHORT) ? 1 : 2;   // P buffers in smem (one at d = 80 keeps two CTAs per SM)
     static constexpr int Q_BYTES = NDB * BQ * 128;
@@ -140,7 +165,8 @@ attn_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ C
     uint64_t* s_full = v_empty + C::VS; // 2
     uint64_t* p_full = s_full + 2;      // 2
     uint64_t* pv_done = p_full + 2;     // 2
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(pv_done + 2);
+    uint64_t* s_free = pv_done + 2;     // 2 (ALT only: S buffer drained by its softmax set)
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(s_free + 2);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int q0 = blockIdx.x * BQ, head = blockIdx.y, batch = blockIdx.z;
@@ -149,8 +175,9 @@ attn_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ C
     if (threadIdx.x == 0) {
         tma_prefetch_desc(&map_q); tma_prefetch_desc(&map_k); tma_prefetch_desc(&map_v);
         mbar_init(q_full, 1);
-        for (int s = 0; s < C::KS; ++s) { mbar_init(&k_full[s], 1); mbar_init(&k_empty[s], 1); mbar_init(&v_full[s], 1); mbar_init(&v_empty[s], 1); }
-        for (int s = 0; s < 2; ++s) { mbar_init(&s_full[s], 1); mbar_init(&p_full[s], 128 * C::NSET); mbar_init(&pv_done[s], 1); }
+        for (int s = 0; s < C::KS; ++s) { mbar_init(&k_full[s], 1); mbar_init(&k_empty[s], 1); }
+        for (int s = 0; s < C::VS; ++s) { mbar_init(&v_full[s], 1); mbar_init(&v_empty[s], 1); }
+        for (int s = 0; s < 2; ++s) { mbar_init(&s_full[s], 1); mbar_init(&p_full[s], C::ALT ? 128 : 128 * C::NSET); mbar_init(&pv_done[s], 1); mbar_init(&s_free[s], 128); }
         fence_barrier_init();
     }
     if (warp == 1) tmem_alloc<C::TMEM_COLS>(tmem_slot);
@@ -203,8 +230,20 @@ attn_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ C
             mbar_wait(q_full, 0);
             issue_s(0);
             if (C::SB > 1 && T > 1) issue_s(1);
+            // ALT: S_{i+2} reuses buffer i&1 as soon as its set has the logits of tile i in registers (mid-tile).  Issue order
+            // S_2 | S_3 PV_0 | S_4 PV_1 | ...: P V_{j} is queued behind S_{j+3}, i.e. behind the OTHER set's mid-tile point, which
+            // pushes the two sets of a CTA half a tile out of phase.
+            auto issue_s_after_free = [&](int i) {
+                if (i + 2 < T) {
+                    mbar_wait(&s_free[i & 1], (i >> 1) & 1);
+                    tc_fence_after();
+                    issue_s(i + 2);
+                }
+            };
+            if constexpr (C::ALT && GMD_ATTN_SEARLY) issue_s_after_free(0);
             for (int j = 0; j < T; ++j) {
                 const int st = j % C::VS;
+                if constexpr (C::ALT) issue_s_after_free(GMD_ATTN_SEARLY ? j + 1 : j);
                 mbar_wait(&p_full[j & 1], (j >> 1) & 1);   // softmax_j: P_j in smem, ones column set, S[j&1] drained
                 mbar_wait(&v_full[st], (j / C::VS) & 1);
                 tc_fence_after();
@@ -216,11 +255,14 @@ attn_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ C
                     constexpr int KSTEPS = C::KW / 16;
                     uint64_t da = umma_desc_k_sw128(p_addr + ks * 32);
                     uint64_t db = umma_desc_mn_sw128(v_addr + ks * 16 * 128, C::KV_BLOCK_BYTES);
-                    umma_bf16_ss(tmem_o + (ks / KSTEPS) * C::DPV, da, db, IDESC_O, (j != 0 || (ks % KSTEPS) != 0) ? 1u : 0u);
+                    if constexpr (C::ALT)   // whole tile into the accumulator of the set that owns it
+                        umma_bf16_ss(tmem_o + (j & 1) * C::DPV, da, db, IDESC_O, (j >= 2 || ks != 0) ? 1u : 0u);
+                    else
+                        umma_bf16_ss(tmem_o + (ks / KSTEPS) * C::DPV, da, db, IDESC_O, (j != 0 || (ks % KSTEPS) != 0) ? 1u : 0u);
                 }
                 umma_commit(&v_empty[st]);
                 umma_commit(&pv_done[j & 1]);
-                if (j + C::SB < T) issue_s(j + C::SB);   // S[j % SB] was drained by softmax_j (p_full_j)
+                if (!C::ALT && j + C::SB < T) issue_s(j + C::SB);   // S[j % SB] was drained by softmax_j (p_full_j)
             }
         }
     } else {
@@ -320,7 +362,109 @@ attn_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ C
             tc_fence_before();
             mbar_arrive(&p_full[j & 1]);
         };
-        {
+        int n_own = 0;   // ALT: tiles this set has processed
+        if constexpr (C::ALT) {
+            const uint32_t s_addr = tmem_base + set * BKV + lane_off;
+            uint8_t* prow = p_smem + set * C::P_BYTES + row * 128;
+            // exponentials of 32 logits against the maximum m_sub; every 16-byte chunk of the P row (K-major SWIZZLE_128B) is stored as
+            // soon as it exists.  `pv_parity` >= 0: wait for the P V MMA that last read this P buffer just before the first store.
+            auto exp_half = [&](const uint32_t (&v)[32], float m_sub, int chunk0, int pv_parity) {
+                // (the first HOLD chunks stay in registers until that P V has been awaited: it was issued when this set finished its
+                // previous tile, a few hundred cycles ago)
+                constexpr int HOLD = GMD_ATTN_PVHOLD ? 2 : 1;
+                uint32_t pk[4 * HOLD] = {};
+                auto store_chunk = [&](int ch) {
+                    const int cc = chunk0 + ch, b = (ch % HOLD) * 4;
+                    *reinterpret_cast<uint4*>(prow + ((cc ^ (row & 7)) << 4)) = make_uint4(pk[b], pk[b + 1], pk[b + 2], pk[b + 3]);
+                };
+#pragma unroll
+                for (int k = 0; k < 16; ++k) {
+                    const float x0 = fmaf(__uint_as_float(v[2 * k]), c, -m_sub), x1 = fmaf(__uint_as_float(v[2 * k + 1]), c, -m_sub);
+                    pk[k % (4 * HOLD)] = pack_bf16x2(ex2(x0), ex2(x1));
+                    if ((k & 3) == 3) {
+                        const int ch = k >> 2;
+                        if (pv_parity >= 0 && ch < HOLD) {
+                            if (ch == HOLD - 1) {
+                                mbar_wait(&pv_done[set], pv_parity);
+#pragma unroll
+                                for (int h = 0; h < HOLD; ++h) store_chunk(h);
+                            }
+                        } else {
+                            store_chunk(ch);
+                        }
+                    }
+                }
+            };
+            auto max32 = [&](const uint32_t (&v)[32]) {
+                float mx0 = __uint_as_float(v[0]), mx1 = __uint_as_float(v[1]), mx2 = __uint_as_float(v[2]), mx3 = __uint_as_float(v[3]);
+#pragma unroll
+                for (int k = 4; k < 32; k += 4) {
+                    mx0 = fmaxf(mx0, __uint_as_float(v[k])); mx1 = fmaxf(mx1, __uint_as_float(v[k + 1]));
+                    mx2 = fmaxf(mx2, __uint_as_float(v[k + 2])); mx3 = fmaxf(mx3, __uint_as_float(v[k + 3]));
+                }
+                return fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3));
+            };
+            auto load_half = [&](int h, int valid, uint32_t (&v)[32]) {
+                tmem_ld_32x32(s_addr + h * 32, v);
+                tmem_wait_ld();
+                if (valid < 32) {   // padding keys (last tile only)
+#pragma unroll
+                    for (int k = 0; k < 32; ++k) if (k >= valid) v[k] = 0xff800000u;  // -inf
+                }
+            };
+            for (int j = set; j < T; j += 2, ++n_own) {
+                const int valid = args.Nk - j * BKV;
+                mbar_wait(&s_full[set], n_own & 1);
+                tc_fence_after();
+                uint32_t sa[32], sb[32];
+                load_half(0, valid, sa);
+                const float mxa = max32(sa);
+                // first half against the stale maximum: the special-function pipe starts right after the TMEM read
+                // (the set's first tile has no maximum yet and always takes the redo path below)
+                if (n_own > 0) exp_half(sa, m, 0, (n_own - 1) & 1);
+                load_half(1, valid - 32, sb);
+                const float mt = fmaxf(mxa, max32(sb)) * c;
+                const bool grow = mt > m + C::LAZY_T;
+                if (__any_sync(0xffffffffu, grow)) {
+                    // the first tile of the set, or a row maximum that left the lazy window: new maximum, first half again, O rescaled
+                    const float m_new = grow ? mt : m;
+                    const float alpha = grow ? ex2(m - m_new) : 1.0f;
+                    m = m_new;
+                    load_half(0, valid, sa);
+                    exp_half(sa, m, 0, -1);
+                    if (n_own > 0) {   // O of this set is complete up to its previous tile (pv_done was awaited by the first exp_half)
+                        tc_fence_after();
+#pragma unroll
+                        for (int ch = 0; ch < C::DPV / 16; ++ch) {
+                            uint32_t o[16];
+                            tmem_ld_32x16(my_o + ch * 16, o);
+                            tmem_wait_ld();
+#pragma unroll
+                            for (int k = 0; k < 16; ++k) o[k] = __float_as_uint(__uint_as_float(o[k]) * alpha);
+                            tmem_st_32x16(my_o + ch * 16, o);
+                        }
+                        tmem_wait_st();
+                    }
+                    load_half(1, valid - 32, sb);
+                }
+                tc_fence_before();
+                mbar_arrive(&s_free[set]);   // both halves are out of TMEM: S_{j+2} may overwrite the buffer
+                exp_half(sb, m, 4, -1);
+                // ones column of V_j (column D of the zero padding) -> the P V MMA also accumulates the softmax denominator
+                {
+                    const int st = j % C::VS;
+                    mbar_wait(&v_full[st], (j / C::VS) & 1);
+                    if (row < BKV) {
+                        constexpr int blk = D / 64, cc = (D % 64) / 8, within = (D % 8) * 2;
+                        uint8_t* vrow = v_smem + st * C::K_BYTES + blk * C::KV_BLOCK_BYTES + row * 128;
+                        *reinterpret_cast<uint16_t*>(vrow + ((cc ^ (row & 7)) << 4) + within) = 0x3F80;  // bf16 1.0
+                    }
+                }
+                fence_proxy_async_smem();
+                tc_fence_before();
+                mbar_arrive(&p_full[set]);
+            }
+        } else {
             uint32_t sa[KW], sb[KW];
             if constexpr (C::PIPE) load_s(0, sa);
             for (int j = 0; j < T; j += 2) {
@@ -328,7 +472,14 @@ attn_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ C
                 if (j + 1 < T) tile(j + 1, sb, sa);
             }
         }
-        mbar_wait(&pv_done[(T - 1) & 1], ((T - 1) >> 1) & 1);
+        if constexpr (C::ALT) {
+            // every set waits for ITS last P V (the phase it has been tracking); after the named barrier both accumulators are final
+            // and the P buffers (the merge scratch) are no longer read by the tensor core
+            mbar_wait(&pv_done[set], (n_own - 1) & 1);
+            asm volatile("bar.sync 2, 256;" ::: "memory");
+        } else {
+            mbar_wait(&pv_done[(T - 1) & 1], ((T - 1) >> 1) & 1);
+        }
         tc_fence_after();
         const int q = q0 + row;
         __nv_bfloat16* op = args.o + batch * args.o_stride_b + (int64_t)q * args.o_stride_n + head * args.o_stride_h;
