@@ -390,7 +390,17 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--comparators", action="store_true",
+                    help="GPU-side comparators (SURVEY 8d): torch SDPA / flash_attn / cuDNN / un-fused torch chains / torch-eager UNet "
+                         "on the same shapes, next to the hand-written kernels; prints one JSON object")
     args = ap.parse_args()
+    if args.comparators:
+        sys.path.insert(0, str(Path(__file__).resolve().parent / "profiles"))
+        import bench_comparators
+        from oracle import tone_mapping_oracle, unet_oracle   # torch restatements, timed on the GPU as the reference's stack
+        _JSON_OUT.write(json.dumps(bench_comparators.run(tone_mapping_oracle, unet_oracle, build_pipeline), indent=1) + "\n")
+        _JSON_OUT.flush()
+        return 0
     if args.impl == "reference":
         return run_reference(args)
     return run_b200(args)

@@ -33,6 +33,17 @@ namespace {
 // waits of the softmax warps) were built, measured at B=16, N=4096 and left OFF: a 4-deep V ring (416 vs 419 TFLOP/s), S_{j+3}
 // queued ahead of P V_j to force the sets half a tile apart (354), the first two P chunks held in registers across the pv_done wait
 // (371 with all three on).  The waits are slack, not the critical path.
+// timing-only knock-outs (wrong results; never set in the product build): 1 = no MUFU (exponentials replaced by the argument),
+// 2 = no ones column / V wait in the softmax warps, 4 = no P stores, 8 = no row maxima
+#ifndef GMD_ATTN_KO
+#define GMD_ATTN_KO 0
+#endif
+#ifndef GMD_ATTN_KVDENSE
+#define GMD_ATTN_KVDENSE 1
+#endif
+#ifndef GMD_ATTN_KS
+#define GMD_ATTN_KS 2
+#endif
 #ifndef GMD_ATTN_VS
 #define GMD_ATTN_VS 2
 #endif
@@ -50,6 +61,7 @@ struct AttnArgs {
     int64_t o_stride_b, o_stride_n, o_stride_h;
     int Nq, Nk;
     float scale_log2;
+    int kv_dense;   // K / V tensor maps are 3-D (channel, token, batch): see launch()
 };
 
 __device__ __forceinline__ float ex2(float x) {
@@ -91,7 +103,7 @@ struct Cfg {
     static_assert(DPV <= NDB * 64, "ones column must fall inside the loaded V blocks");
     // K / V ring depths (measured at d = 40: 3-deep rings change nothing, 394 vs 392 TFLOP/s — the kernel is not waiting for K/V;
     // 4-deep rings cost the second resident CTA)
-    static constexpr int KS = 2;
+    static constexpr int KS = (D == 40 && !SHORT) ? GMD_ATTN_KS : 2;
     // (measured: three co-resident CTAs per SM with single-buffered S / P at d = 40 reach 354 TFLOP/s vs 378 for two CTAs
     // with double buffering, so the double-buffered configuration stays)
     // SHORT (text cross-attention, Nk <= 2 key tiles): the whole CTA lives for ~2 tiles, so what matters is how many CTAs are
@@ -193,18 +205,24 @@ attn_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ C
             for (int b = 0; b < C::NDB; ++b) tma_load_4d(q_smem + b * BQ * 128, &map_q, q_full, b * 64, head, q0, batch);
             for (int j = 0; j < T; ++j) {
                 const int st = j % C::KS;
-                mbar_wait(&k_empty[st], ((j / C::KS) & 1) ^ 1);
+                if (!(GMD_ATTN_KO & 64)) mbar_wait(&k_empty[st], ((j / C::KS) & 1) ^ 1);
+                if (GMD_ATTN_KO & 256) { mbar_arrive(&k_full[st]); continue; }
                 mbar_expect_tx(&k_full[st], C::K_BYTES);
-                for (int b = 0; b < C::NDB; ++b)
-                    tma_load_4d(k_smem + st * C::K_BYTES + b * C::KV_BLOCK_BYTES, &map_k, &k_full[st], b * 64, head, j * BKV, batch);
+                for (int b = 0; b < C::NDB; ++b) {
+                    if (args.kv_dense) tma_load_3d(k_smem + st * C::K_BYTES + b * C::KV_BLOCK_BYTES, &map_k, &k_full[st], head * D + b * 64, j * BKV, batch);
+                    else tma_load_4d(k_smem + st * C::K_BYTES + b * C::KV_BLOCK_BYTES, &map_k, &k_full[st], b * 64, head, j * BKV, batch);
+                }
             }
         } else if (lane == 1) {
             for (int j = 0; j < T; ++j) {
                 const int st = j % C::VS;
-                mbar_wait(&v_empty[st], ((j / C::VS) & 1) ^ 1);
+                if (!(GMD_ATTN_KO & 64)) mbar_wait(&v_empty[st], ((j / C::VS) & 1) ^ 1);
+                if (GMD_ATTN_KO & 256) { mbar_arrive(&v_full[st]); continue; }
                 mbar_expect_tx(&v_full[st], C::K_BYTES);
-                for (int b = 0; b < C::NDB; ++b)
-                    tma_load_4d(v_smem + st * C::K_BYTES + b * C::KV_BLOCK_BYTES, &map_v, &v_full[st], b * 64, head, j * BKV, batch);
+                for (int b = 0; b < C::NDB; ++b) {
+                    if (args.kv_dense) tma_load_3d(v_smem + st * C::K_BYTES + b * C::KV_BLOCK_BYTES, &map_v, &v_full[st], head * D + b * 64, j * BKV, batch);
+                    else tma_load_4d(v_smem + st * C::K_BYTES + b * C::KV_BLOCK_BYTES, &map_v, &v_full[st], b * 64, head, j * BKV, batch);
+                }
             }
         }
     } else if (warp == 1) {
@@ -235,7 +253,7 @@ attn_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ C
             // pushes the two sets of a CTA half a tile out of phase.
             auto issue_s_after_free = [&](int i) {
                 if (i + 2 < T) {
-                    mbar_wait(&s_free[i & 1], (i >> 1) & 1);
+                    if (!(GMD_ATTN_KO & 128)) mbar_wait(&s_free[i & 1], (i >> 1) & 1);
                     tc_fence_after();
                     issue_s(i + 2);
                 }
@@ -375,17 +393,18 @@ attn_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ C
                 uint32_t pk[4 * HOLD] = {};
                 auto store_chunk = [&](int ch) {
                     const int cc = chunk0 + ch, b = (ch % HOLD) * 4;
+                    if ((GMD_ATTN_KO & 4) && pk[b] != 0x12345678u) return;
                     *reinterpret_cast<uint4*>(prow + ((cc ^ (row & 7)) << 4)) = make_uint4(pk[b], pk[b + 1], pk[b + 2], pk[b + 3]);
                 };
 #pragma unroll
                 for (int k = 0; k < 16; ++k) {
                     const float x0 = fmaf(__uint_as_float(v[2 * k]), c, -m_sub), x1 = fmaf(__uint_as_float(v[2 * k + 1]), c, -m_sub);
-                    pk[k % (4 * HOLD)] = pack_bf16x2(ex2(x0), ex2(x1));
+                    pk[k % (4 * HOLD)] = (GMD_ATTN_KO & 1) ? pack_bf16x2(x0, x1) : pack_bf16x2(ex2(x0), ex2(x1));
                     if ((k & 3) == 3) {
                         const int ch = k >> 2;
                         if (pv_parity >= 0 && ch < HOLD) {
                             if (ch == HOLD - 1) {
-                                mbar_wait(&pv_done[set], pv_parity);
+                                if (!(GMD_ATTN_KO & 16)) mbar_wait(&pv_done[set], pv_parity);
 #pragma unroll
                                 for (int h = 0; h < HOLD; ++h) store_chunk(h);
                             }
@@ -398,7 +417,7 @@ attn_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ C
             auto max32 = [&](const uint32_t (&v)[32]) {
                 float mx0 = __uint_as_float(v[0]), mx1 = __uint_as_float(v[1]), mx2 = __uint_as_float(v[2]), mx3 = __uint_as_float(v[3]);
 #pragma unroll
-                for (int k = 4; k < 32; k += 4) {
+                for (int k = 4; k < ((GMD_ATTN_KO & 8) ? 4 : 32); k += 4) {
                     mx0 = fmaxf(mx0, __uint_as_float(v[k])); mx1 = fmaxf(mx1, __uint_as_float(v[k + 1]));
                     mx2 = fmaxf(mx2, __uint_as_float(v[k + 2])); mx3 = fmaxf(mx3, __uint_as_float(v[k + 3]));
                 }
@@ -414,7 +433,7 @@ attn_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ C
             };
             for (int j = set; j < T; j += 2, ++n_own) {
                 const int valid = args.Nk - j * BKV;
-                mbar_wait(&s_full[set], n_own & 1);
+                if (!(GMD_ATTN_KO & 32)) mbar_wait(&s_full[set], n_own & 1);
                 tc_fence_after();
                 uint32_t sa[32], sb[32];
                 load_half(0, valid, sa);
@@ -451,7 +470,7 @@ attn_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ C
                 mbar_arrive(&s_free[set]);   // both halves are out of TMEM: S_{j+2} may overwrite the buffer
                 exp_half(sb, m, 4, -1);
                 // ones column of V_j (column D of the zero padding) -> the P V MMA also accumulates the softmax denominator
-                {
+                if (!(GMD_ATTN_KO & 2)) {
                     const int st = j % C::VS;
                     mbar_wait(&v_full[st], (j / C::VS) & 1);
                     if (row < BKV) {
@@ -573,13 +592,31 @@ int launch(const gmd_attn_params* p, cudaStream_t st) {
     };
     int rc;
     if ((rc = enc(&mq, p->q, p->q_stride_b, p->q_stride_n, p->q_stride_h, p->Nq, BQ))) return rc;
-    if ((rc = enc(&mk, p->k, p->k_stride_b, p->k_stride_n, p->k_stride_h, p->Nk, BKV))) return rc;
-    if ((rc = enc(&mv, p->v, p->v_stride_b, p->v_stride_n, p->v_stride_h, p->Nk, BKV))) return rc;
+    // K / V: when the heads of a token are contiguous (stride_h == d: the fused QKV / KV GEMM outputs) the map is 3-D over the whole
+    // channel row and the 64-wide box starts at channel head*d: the columns past the head's d are the NEXT head's values (finite,
+    // multiplied by Q's zero padding in Q K^T and landing in never-read columns of O in P V) instead of TMA out-of-bounds fill.
+    // Measured: the zero-filled 80-byte rows of the 4-D (d, head, token, batch) map paced the whole kernel (ncu / knock-out runs:
+    // 808 us with the softmax removed vs 483 us without the K / V loads, B=16 N=4096 d=40).
+    const bool kv_dense = GMD_ATTN_KVDENSE && p->k_stride_h == D && p->v_stride_h == D;
+    auto enc_dense = [&](CUtensorMap* m, const void* base, int64_t sb, int64_t sn, int n) {
+        uint64_t dims[3] = {(uint64_t)D * p->H, (uint64_t)n, (uint64_t)p->B};
+        uint64_t strides[3] = {2, (uint64_t)sn * 2, (uint64_t)sb * 2};
+        uint32_t box[3] = {64, (uint32_t)BKV, 1};
+        return encode_tensor_map_bf16(m, base, 3, dims, strides, box, true);
+    };
+    if (kv_dense) {
+        if ((rc = enc_dense(&mk, p->k, p->k_stride_b, p->k_stride_n, p->Nk))) return rc;
+        if ((rc = enc_dense(&mv, p->v, p->v_stride_b, p->v_stride_n, p->Nk))) return rc;
+    } else {
+        if ((rc = enc(&mk, p->k, p->k_stride_b, p->k_stride_n, p->k_stride_h, p->Nk, BKV))) return rc;
+        if ((rc = enc(&mv, p->v, p->v_stride_b, p->v_stride_n, p->v_stride_h, p->Nk, BKV))) return rc;
+    }
     AttnArgs a;
     a.o = static_cast<__nv_bfloat16*>(p->o);
     a.o_stride_b = p->o_stride_b; a.o_stride_n = p->o_stride_n; a.o_stride_h = p->o_stride_h;
     a.Nq = p->Nq; a.Nk = p->Nk;
     a.scale_log2 = p->scale * 1.4426950408889634f;
+    a.kv_dense = kv_dense ? 1 : 0;
     dim3 grid((p->Nq + BQ - 1) / BQ, p->H, p->B);
     attn_kernel<D, SHORT><<<grid, C::THREADS, C::SMEM, st>>>(mq, mk, mv, a);
     count_launch(1);
