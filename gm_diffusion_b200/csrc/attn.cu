@@ -38,6 +38,12 @@ namespace {
 #ifndef GMD_ATTN_KO
 #define GMD_ATTN_KO 0
 #endif
+#ifndef GMD_ATTN_BF16EXP
+#define GMD_ATTN_BF16EXP 0
+#endif
+#ifndef GMD_ATTN_POLY
+#define GMD_ATTN_POLY 0
+#endif
 #ifndef GMD_ATTN_KVDENSE
 #define GMD_ATTN_KVDENSE 1
 #endif
@@ -148,7 +154,7 @@ struct Cfg {
     // and this all neutral, what paces the kernel is the per-tile latency chain of a softmax warp (S ready -> tcgen05.ld -> max ->
     // exp -> P to shared memory -> fence -> arrive), ~1900 cycles per tile per CTA with two CTAs per SM.  Off: fp32 exponentials.
     static constexpr bool BF16_EXP = false;
-    static constexpr float LAZY_T = BF16_EXP ? 2.0f : 8.0f;  // lazy-rescale window of the running maximum, in log2 units
+    static constexpr float LAZY_T = (BF16_EXP || GMD_ATTN_BF16EXP) ? 2.0f : 8.0f;  // lazy-rescale window of the running maximum, in log2 units
     // software-pipelined TMEM reads of S in the softmax warps (needs the double-buffered S): see `tile` in the kernel.  Measured
     // and OFF: with the request for S_{j+1} issued in the middle of tile j's exponentials (no spills) d = 40 drops from 413 to 346
     // TFLOP/s and d = 160 from 228 to 210 — an in-flight tcgen05.ld does not overlap the MUFU stream of the same warp.  What did
@@ -399,7 +405,14 @@ attn_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ C
 #pragma unroll
                 for (int k = 0; k < 16; ++k) {
                     const float x0 = fmaf(__uint_as_float(v[2 * k]), c, -m_sub), x1 = fmaf(__uint_as_float(v[2 * k + 1]), c, -m_sub);
-                    pk[k % (4 * HOLD)] = (GMD_ATTN_KO & 1) ? pack_bf16x2(x0, x1) : pack_bf16x2(ex2(x0), ex2(x1));
+                    if (GMD_ATTN_KO & 1) {
+                        pk[k % (4 * HOLD)] = pack_bf16x2(x0, x1);
+                    } else if (GMD_ATTN_BF16EXP) {
+                        pk[k % (4 * HOLD)] = ex2_bf16x2(x0, x1);
+                    } else {
+                        const bool poly = GMD_ATTN_POLY > 0 && (k % (GMD_ATTN_POLY > 0 ? GMD_ATTN_POLY : 1)) == 0;
+                        pk[k % (4 * HOLD)] = poly ? pack_bf16x2(ex2_poly(x0), ex2_poly(x1)) : pack_bf16x2(ex2(x0), ex2(x1));
+                    }
                     if ((k & 3) == 3) {
                         const int ch = k >> 2;
                         if (pv_parity >= 0 && ch < HOLD) {
