@@ -44,6 +44,12 @@ namespace {
 #ifndef GMD_ATTN_POLY
 #define GMD_ATTN_POLY 0
 #endif
+#ifndef GMD_XATTN_KO
+#define GMD_XATTN_KO 0   // timing-only knock-outs of the text cross-attention kernel: 1 no MUFU, 2 no epilogue, 4 no P stores, 8 no maxima
+#endif
+#ifndef GMD_ATTN_XATTN
+#define GMD_ATTN_XATTN 1
+#endif
 #ifndef GMD_ATTN_KVDENSE
 #define GMD_ATTN_KVDENSE 1
 #endif
@@ -636,6 +642,313 @@ int launch(const gmd_attn_params* p, cudaStream_t st) {
     return check_launch("attn_kernel");
 }
 
+
+// ---------------------------------------------------------------------------------------------------------------------------------
+// Text cross-attention (64 < Nk <= 80: SD1.5's 77 CLIP tokens), d = 40 / 80.  K and V of one (batch, head) stay resident in shared
+// memory and the CTA walks over QT consecutive 128-row query tiles; all keys are visible at once, so the softmax is exact in one pass
+// (no running maximum, no rescale).  Two softmax warp sets own alternating query tiles together with their Q slot, S / O
+// accumulators and P buffer, so the S MMA, the softmax, the P V MMA and the output write of neighbouring tiles overlap.  The
+// per-tile CTA of the general kernel lived for two key tiles and was bound by its prologue (TMEM allocation, Q/K/V round trip).
+template <int D>
+struct XCfg {
+    static constexpr int NDB = (D + 63) / 64;
+    static constexpr int DP = (D + 15) / 16 * 16;
+    static constexpr int DPV = (D + 1 + 15) / 16 * 16;
+    static constexpr int NKP = 80;                        // keys padded to a multiple of 16 (N of Q K^T, K of P V)
+    static constexpr int Q_BYTES = NDB * BQ * 128;
+    static constexpr int KV_BLOCK = NKP * 128;            // one 64-wide d block of K or V
+    static constexpr int KV_BYTES = NDB * KV_BLOCK;
+    static constexpr int P_BLOCK = BQ * 128;              // P block 0: keys 0-63, block 1: keys 64-79 (first 32 bytes of each row)
+    static constexpr int P_BYTES = 2 * P_BLOCK;
+    // softmax warp sets = query tiles in flight.  The per-tile chain (S ready -> 80-column TMEM read -> exponentials -> P -> P V ->
+    // O read -> global store) is ~5000 cycles of latency, so d = 40 runs four sets (all 512 TMEM columns: 4 x (80 + 48), 212 KB of
+    // shared memory); d = 80 has room for two.
+    static constexpr int NSET = D == 40 ? 4 : 2;
+    static constexpr int SSTRIDE = NSET == 4 ? NKP : 128;  // TMEM columns between the S accumulators of consecutive sets
+    static constexpr int OFF_K = NSET * Q_BYTES;
+    static constexpr int OFF_V = OFF_K + KV_BYTES;
+    static constexpr int OFF_P = OFF_V + KV_BYTES;
+    static constexpr int OFF_BAR = OFF_P + NSET * P_BYTES;
+    static constexpr int SMEM = OFF_BAR + 512 + 1024;
+    static constexpr int THREADS = 64 + 128 * NSET;
+    static_assert(KV_BLOCK % 1024 == 0, "swizzle atoms");
+    static_assert(NSET * (SSTRIDE + DPV) <= 512, "TMEM");
+    static_assert(SMEM <= 227 * 1024, "shared memory");
+};
+
+template <int D>
+__global__ void __launch_bounds__(XCfg<D>::THREADS, 1)
+xattn_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_k,
+             const __grid_constant__ CUtensorMap map_v, const __grid_constant__ CUtensorMap map_o, const AttnArgs args, const int QT) {
+    using C = XCfg<D>;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t* q_smem = smem;
+    uint8_t* k_smem = smem + C::OFF_K;
+    uint8_t* v_smem = smem + C::OFF_V;
+    uint8_t* p_smem = smem + C::OFF_P;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::OFF_BAR);
+    constexpr int NS = C::NSET;
+    uint64_t* kv_full = bars;           // 1
+    uint64_t* q_full = bars + 1;        // NS each from here on
+    uint64_t* q_empty = q_full + NS;
+    uint64_t* s_full = q_empty + NS;
+    uint64_t* s_free = s_full + NS;
+    uint64_t* p_full = s_free + NS;
+    uint64_t* o_full = p_full + NS;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_full + NS);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int head = blockIdx.y, batch = blockIdx.z;
+    const int nq_tiles = (args.Nq + BQ - 1) / BQ;
+    const int i0 = blockIdx.x * QT;
+    const int n = min(QT, nq_tiles - i0);   // query tiles of this CTA
+
+    if (threadIdx.x == 0) {
+        tma_prefetch_desc(&map_q); tma_prefetch_desc(&map_k); tma_prefetch_desc(&map_v); tma_prefetch_desc(&map_o);
+        mbar_init(kv_full, 1);
+        for (int s = 0; s < NS; ++s) {
+            mbar_init(&q_full[s], 1); mbar_init(&q_empty[s], 1); mbar_init(&s_full[s], 1);
+            mbar_init(&s_free[s], 128); mbar_init(&p_full[s], 128); mbar_init(&o_full[s], 1);
+        }
+        fence_barrier_init();
+    }
+    if (warp == 1) tmem_alloc<512>(tmem_slot);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    const uint32_t tmem_o = tmem_base + NS * C::SSTRIDE;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            mbar_expect_tx(kv_full, 2 * C::KV_BYTES);
+            for (int b = 0; b < C::NDB; ++b) {
+                tma_load_4d(k_smem + b * C::KV_BLOCK, &map_k, kv_full, b * 64, head, 0, batch);   // zero-filled past d (once per CTA)
+                tma_load_3d(v_smem + b * C::KV_BLOCK, &map_v, kv_full, head * D + b * 64, 0, batch);
+            }
+            for (int i = 0; i < n; ++i) {
+                const int slot = i % NS;
+                mbar_wait(&q_empty[slot], ((i / NS) & 1) ^ 1);
+                mbar_expect_tx(&q_full[slot], C::Q_BYTES);
+                for (int b = 0; b < C::NDB; ++b)
+                    tma_load_3d(q_smem + slot * C::Q_BYTES + b * BQ * 128, &map_q, &q_full[slot], head * D + b * 64, (i0 + i) * BQ, batch);
+            }
+        }
+    } else if (warp == 1) {
+        if (elect_one()) {
+            constexpr uint32_t IDESC_S = umma_idesc_bf16(BQ, C::NKP, false, false);
+            constexpr uint32_t IDESC_O = umma_idesc_bf16(BQ, C::DPV, false, true);  // B = V is MN-major
+            const uint32_t q_addr = smem_u32(q_smem), k_addr = smem_u32(k_smem), v_addr = smem_u32(v_smem), p_addr = smem_u32(p_smem);
+            auto issue_s = [&](int i) {
+                const int slot = i % NS;
+                mbar_wait(&q_full[slot], (i / NS) & 1);
+                if (i >= NS) mbar_wait(&s_free[slot], ((i / NS) - 1) & 1);   // the set has its previous S in registers
+                tc_fence_after();
+#pragma unroll
+                for (int ks = 0; ks < C::DP / 16; ++ks) {
+                    const int blk = ks >> 2, within = ks & 3;
+                    uint64_t da = umma_desc_k_sw128(q_addr + slot * C::Q_BYTES + blk * (BQ * 128) + within * 32);
+                    uint64_t db = umma_desc_k_sw128(k_addr + blk * C::KV_BLOCK + within * 32);
+                    umma_bf16_ss(tmem_base + slot * C::SSTRIDE, da, db, IDESC_S, ks != 0 ? 1u : 0u);
+                }
+                umma_commit(&q_empty[slot]);
+                umma_commit(&s_full[slot]);
+            };
+            mbar_wait(kv_full, 0);
+            for (int i = 0; i < NS && i < n; ++i) issue_s(i);
+            for (int i = 0; i < n; ++i) {
+                const int slot = i % NS;
+                mbar_wait(&p_full[slot], (i / NS) & 1);   // P_i in smem, ones column set, O[slot] drained by the previous tile's epilogue
+                tc_fence_after();
+#pragma unroll
+                for (int ks = 0; ks < C::NKP / 16; ++ks) {
+                    uint64_t da = umma_desc_k_sw128(p_addr + slot * C::P_BYTES + (ks >> 2) * C::P_BLOCK + (ks & 3) * 32);
+                    uint64_t db = umma_desc_mn_sw128(v_addr + ks * 16 * 128, C::KV_BLOCK);
+                    umma_bf16_ss(tmem_o + slot * C::DPV, da, db, IDESC_O, ks != 0 ? 1u : 0u);
+                }
+                umma_commit(&o_full[slot]);
+                if (i + NS < n) issue_s(i + NS);
+            }
+        }
+    } else {
+        const int lg = warp & 3;
+        const int set = (warp - 2) >> 2;
+        const int row = lg * 32 + lane;
+        const uint32_t lane_off = static_cast<uint32_t>(lg * 32) << 16;
+        const uint32_t my_s = tmem_base + set * C::SSTRIDE + lane_off;
+        const uint32_t my_o = tmem_o + set * C::DPV + lane_off;
+        const float c = args.scale_log2;
+        uint8_t* prow = p_smem + set * C::P_BYTES + row * 128;
+        const bool issuer = ((warp - 2) & 3) == 0 && lane == 0;   // one thread per set owns its TMA-store bulk groups
+        // ones column of V (column D of its padding) -> the P V MMA also accumulates the softmax denominator.  Both sets write it
+        // (idempotent) so that each set's first p_full arrival orders it before that set's first P V.
+        mbar_wait(kv_full, 0);
+        if (row < C::NKP) {
+            constexpr int blk = D / 64, cc = (D % 64) / 8, within = (D % 8) * 2;
+            uint8_t* vrow = v_smem + blk * C::KV_BLOCK + row * 128;
+            *reinterpret_cast<uint16_t*>(vrow + ((cc ^ (row & 7)) << 4) + within) = 0x3F80;  // bf16 1.0
+        }
+        for (int i = set; i < n; i += NS) {
+            const uint32_t ph = (i / NS) & 1;
+            mbar_wait(&s_full[set], ph);
+            tc_fence_after();
+            uint32_t sr[C::NKP];
+            {
+                uint32_t t0[32], t1[32], t2[16];
+                tmem_ld_32x32(my_s, t0);
+                tmem_ld_32x32(my_s + 32, t1);
+                tmem_ld_32x16(my_s + 64, t2);
+                tmem_wait_ld();
+#pragma unroll
+                for (int k = 0; k < 32; ++k) { sr[k] = t0[k]; sr[32 + k] = t1[k]; }
+#pragma unroll
+                for (int k = 0; k < 16; ++k) sr[64 + k] = t2[k];
+            }
+            tc_fence_before();
+            mbar_arrive(&s_free[set]);   // S[set] may be overwritten by S_{i+2}
+#pragma unroll
+            for (int k = 64; k < C::NKP; ++k) if (k >= args.Nk) sr[k] = 0xff800000u;  // padding keys -> -inf
+            float mx0 = __uint_as_float(sr[0]), mx1 = __uint_as_float(sr[1]), mx2 = __uint_as_float(sr[2]), mx3 = __uint_as_float(sr[3]);
+#pragma unroll
+            for (int k = 4; k < ((GMD_XATTN_KO & 8) ? 4 : C::NKP); k += 4) {
+                mx0 = fmaxf(mx0, __uint_as_float(sr[k])); mx1 = fmaxf(mx1, __uint_as_float(sr[k + 1]));
+                mx2 = fmaxf(mx2, __uint_as_float(sr[k + 2])); mx3 = fmaxf(mx3, __uint_as_float(sr[k + 3]));
+            }
+            const float m = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3)) * c;
+            // P[set] was last read by P V of this set's previous tile (awaited before its epilogue) and then by the TMA store of that
+            // tile's output, which used it as staging: the issuing thread waits for the store to have read it
+            if (i >= NS) {
+                if (issuer) tma_store_wait_read();
+                asm volatile("bar.sync %0, 128;" ::"r"(1 + set) : "memory");
+            }
+#pragma unroll
+            for (int ch = 0; ch < C::NKP / 8; ++ch) {
+                uint32_t pk[4];
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    const float x0 = fmaf(__uint_as_float(sr[ch * 8 + 2 * k]), c, -m), x1 = fmaf(__uint_as_float(sr[ch * 8 + 2 * k + 1]), c, -m);
+                    pk[k] = (GMD_XATTN_KO & 1) ? pack_bf16x2(x0, x1) : pack_bf16x2(ex2(x0), ex2(x1));
+                }
+                if ((GMD_XATTN_KO & 4) && pk[0] != 0x12345678u) continue;
+                // K-major SWIZZLE_128B: 16-byte chunk cc of row r lands at chunk (cc ^ (r & 7)) of its 128-byte row
+                uint8_t* dst = prow + (ch >> 3) * C::P_BLOCK + (((ch & 7) ^ (row & 7)) << 4);
+                *reinterpret_cast<uint4*>(dst) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+            }
+            fence_proxy_async_smem();
+            tc_fence_before();
+            mbar_arrive(&p_full[set]);
+            // epilogue of this tile: O / l -> global
+            mbar_wait(&o_full[set], ph);
+            tc_fence_after();
+            // O / l as bf16 into this set's P buffer (its P V is complete) in the SWIZZLE_128B layout, then ONE asynchronous TMA store
+            // per 64-wide d block: rows past Nq and columns past d are clipped by the tensor map.  (Per-thread 16-byte global stores
+            // of 80-byte rows cost 15 of 42 us at B=16, Nq=4096.)
+            float inv_l;
+            {
+                uint32_t o[16];
+                tmem_ld_32x16(my_o + (D / 16) * 16, o);
+                tmem_wait_ld();
+                inv_l = 1.0f / __uint_as_float(o[D % 16]);
+            }
+            uint8_t* orow = p_smem + set * C::P_BYTES + row * 128;
+#pragma unroll
+            for (int ch = 0; ch < (D + 15) / 16; ++ch) {
+                uint32_t o[16];
+                tmem_ld_32x16(my_o + ch * 16, o);
+                tmem_wait_ld();
+#pragma unroll
+                for (int h8 = 0; h8 < 2; ++h8) {
+                    const int d0 = ch * 16 + h8 * 8;
+                    if (d0 < D) {  // D is a multiple of 8
+                        uint4 v = make_uint4(pack_bf16x2(__uint_as_float(o[h8 * 8 + 0]) * inv_l, __uint_as_float(o[h8 * 8 + 1]) * inv_l),
+                                             pack_bf16x2(__uint_as_float(o[h8 * 8 + 2]) * inv_l, __uint_as_float(o[h8 * 8 + 3]) * inv_l),
+                                             pack_bf16x2(__uint_as_float(o[h8 * 8 + 4]) * inv_l, __uint_as_float(o[h8 * 8 + 5]) * inv_l),
+                                             pack_bf16x2(__uint_as_float(o[h8 * 8 + 6]) * inv_l, __uint_as_float(o[h8 * 8 + 7]) * inv_l));
+                        *reinterpret_cast<uint4*>(orow + (d0 / 64) * C::P_BLOCK + ((((d0 % 64) / 8) ^ (row & 7)) << 4)) = v;
+                    }
+                }
+            }
+            fence_proxy_async_smem();
+            tc_fence_before();
+            asm volatile("bar.sync %0, 128;" ::"r"(1 + set) : "memory");
+            if (issuer) {
+                for (int b = 0; b < C::NDB; ++b)
+                    tma_store_4d(&map_o, p_smem + set * C::P_BYTES + b * C::P_BLOCK, b * 64, head, (i0 + i) * BQ, batch);
+                tma_store_commit();
+            }
+        }
+        if (issuer) tma_store_wait_all();
+        tc_fence_before();
+    }
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        tmem_dealloc<512>(tmem_base);
+    }
+}
+
+template <int D>
+int launch_x(const gmd_attn_params* p, cudaStream_t st) {
+    using C = XCfg<D>;
+    static bool configured = false;
+    static int sms = 148;
+    if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(xattn_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM);
+        if (e != cudaSuccess) { set_last_error("xattn: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return kErrCuda; }
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        configured = true;
+    }
+    CUtensorMap mq, mk, mv;
+    int rc;
+    // Q (one tile per step of the loop) and V go through dense 3-D maps over the whole channel row: the columns past the head's d
+    // hold the next head's values.  K — loaded once per CTA — keeps the 4-D (d, head, token, batch) map whose out-of-bounds fill
+    // zeroes its columns d..63, so the padded part of the Q K^T contraction (d = 40: columns 40-47) contributes exactly 0.
+    auto enc_dense = [&](CUtensorMap* m, const void* base, int64_t sb, int64_t sn, int n, int rows) {
+        uint64_t dims[3] = {(uint64_t)D * p->H, (uint64_t)n, (uint64_t)p->B};
+        uint64_t strides[3] = {2, (uint64_t)sn * 2, (uint64_t)sb * 2};
+        uint32_t box[3] = {64, (uint32_t)rows, 1};
+        return encode_tensor_map_bf16(m, base, 3, dims, strides, box, true);
+    };
+    if ((rc = enc_dense(&mq, p->q, p->q_stride_b, p->q_stride_n, p->Nq, BQ))) return rc;
+    {
+        uint64_t dims[4] = {(uint64_t)D, (uint64_t)p->H, (uint64_t)p->Nk, (uint64_t)p->B};
+        uint64_t strides[4] = {2, (uint64_t)p->k_stride_h * 2, (uint64_t)p->k_stride_n * 2, (uint64_t)p->k_stride_b * 2};
+        uint32_t box[4] = {64, 1, (uint32_t)C::NKP, 1};
+        if ((rc = encode_tensor_map_bf16(&mk, p->k, 4, dims, strides, box, true))) return rc;
+    }
+    if ((rc = enc_dense(&mv, p->v, p->v_stride_b, p->v_stride_n, p->Nk, C::NKP))) return rc;
+    CUtensorMap mo;
+    {
+        uint64_t dims[4] = {(uint64_t)D, (uint64_t)p->H, (uint64_t)p->Nq, (uint64_t)p->B};
+        uint64_t strides[4] = {2, (uint64_t)p->o_stride_h * 2, (uint64_t)p->o_stride_n * 2, (uint64_t)p->o_stride_b * 2};
+        uint32_t box[4] = {64, 1, (uint32_t)BQ, 1};
+        if ((rc = encode_tensor_map_bf16(&mo, p->o, 4, dims, strides, box, true))) return rc;
+    }
+    AttnArgs a;
+    a.o = static_cast<__nv_bfloat16*>(p->o);
+    a.o_stride_b = p->o_stride_b; a.o_stride_n = p->o_stride_n; a.o_stride_h = p->o_stride_h;
+    a.Nq = p->Nq; a.Nk = p->Nk;
+    a.scale_log2 = p->scale * 1.4426950408889634f;
+    a.kv_dense = 1;
+    // query tiles per CTA: fewest waves x (prologue + QT tiles), in units of ~950 cycles per tile and ~2500 per prologue
+    const int nq_tiles = (p->Nq + BQ - 1) / BQ;
+    int best_qt = nq_tiles;
+    double best = 1e30;
+    for (int parts = 1; parts <= nq_tiles; parts *= 2) {
+        const int qt = (nq_tiles + parts - 1) / parts;
+        const int64_t ctas = (int64_t)p->B * p->H * ((nq_tiles + qt - 1) / qt);
+        const double cost = (double)((ctas + sms - 1) / sms) * (2500.0 + 950.0 * qt);
+        if (cost < best) { best = cost; best_qt = qt; }
+    }
+    dim3 grid((nq_tiles + best_qt - 1) / best_qt, p->H, p->B);
+    xattn_kernel<D><<<grid, C::THREADS, C::SMEM, st>>>(mq, mk, mv, mo, a, best_qt);
+    count_launch(1);
+    return check_launch("xattn_kernel");
+}
+
 }  // namespace
 }  // namespace gmd
 
@@ -652,9 +965,15 @@ extern "C" int gmd_attn_fwd(const gmd_attn_params* p, void* stream) {
     for (const void* q : ptrs)
         if (reinterpret_cast<uintptr_t>(q) & 15) { set_last_error("gmd_attn_fwd: pointers must be 16-byte aligned"); return kErrInvalid; }
     cudaStream_t st = static_cast<cudaStream_t>(stream);
+    // text cross-attention (SD1.5: 77 keys): K / V resident, persistent over query tiles
+    const bool xattn = GMD_ATTN_XATTN && p->Nk > 64 && p->Nk <= 80 && p->q_stride_h == p->d && p->v_stride_h == p->d;
     switch (p->d) {
-        case 40: return p->Nk <= 2 * BKV ? launch<40, true>(p, st) : launch<40, false>(p, st);
-        case 80: return launch<80, false>(p, st);   // (the short configuration does not add a third resident CTA at d = 80: measured slightly slower)
+        case 40:
+            if (xattn) return launch_x<40>(p, st);
+            return p->Nk <= 2 * BKV ? launch<40, true>(p, st) : launch<40, false>(p, st);
+        case 80:
+            if (xattn) return launch_x<80>(p, st);
+            return launch<80, false>(p, st);   // (the short configuration does not add a third resident CTA at d = 80: measured slightly slower)
         case 160: return launch<160, false>(p, st);
         default: set_last_error("gmd_attn_fwd: head dim %d not instantiated (40, 80, 160)", p->d); return kErrUnsupported;
     }

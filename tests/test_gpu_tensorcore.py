@@ -283,6 +283,23 @@ def test_attention(B, H, Nq, Nk, d):
     check(got, ref.transpose(1, 2).reshape(B, Nq, Cc), tol=1e-2, what=f"attn B{B} H{H} {Nq}x{Nk} d{d}")
 
 
+@pytest.mark.parametrize("B,H,Nq,Nk,d", [(1, 8, 200, 77, 40), (3, 8, 384, 65, 40), (2, 8, 128, 80, 80), (1, 8, 1000, 77, 80), (2, 8, 16384, 77, 40),
+                                         (5, 8, 4096, 77, 40), (1, 8, 77, 77, 40)])
+def test_attention_text_cross(B, H, Nq, Nk, d):
+    """The persistent text cross-attention kernel (64 < Nk <= 80, d = 40 / 80): ragged query counts, odd tile counts per CTA, both
+    ends of the key range, and batch counts that leave partial waves."""
+    from gm_diffusion_b200 import ops
+    g = torch.Generator().manual_seed(7 * Nq + Nk + d)
+    Cc = H * d
+    q = torch.randn(B, Nq, Cc, generator=g).to(bf).cuda()
+    kv = torch.randn(B, Nk, 2 * Cc, generator=g).to(bf).cuda()
+    k, v = kv[..., :Cc], kv[..., Cc:]
+    got = ops.attention(q, k, v, H)
+    qh, kh, vh = (t.float().reshape(B, -1, H, d).transpose(1, 2) for t in (q, k, v))
+    ref = torch.softmax(qh @ kh.transpose(-1, -2) * d ** -0.5, -1) @ vh
+    check(got, ref.transpose(1, 2).reshape(B, Nq, Cc), tol=1e-2, what=f"text cross-attn B{B} H{H} {Nq}x{Nk} d{d}")
+
+
 def test_attention_large_logits():
     from gm_diffusion_b200 import ops
     g = torch.Generator().manual_seed(2)
