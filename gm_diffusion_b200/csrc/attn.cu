@@ -38,6 +38,18 @@ namespace {
 #ifndef GMD_ATTN_KO
 #define GMD_ATTN_KO 0
 #endif
+#ifndef GMD_ATTN_FINE
+#define GMD_ATTN_FINE 1
+#endif
+// B=16, N=4096, d=40: 32 columns per read without prefetch 721 us (default); 16 / 8 columns 747 / 756; with the next read in flight
+// under the exponentials 757-766 for every size (an in-flight tcgen05.ld serialises with the same sub-partition's MUFU stream);
+// half-tile variant below (!GMD_ATTN_FINE) 731
+#ifndef GMD_ATTN_FINE_CH
+#define GMD_ATTN_FINE_CH 32
+#endif
+#ifndef GMD_ATTN_FINE_PREF
+#define GMD_ATTN_FINE_PREF 0
+#endif
 #ifndef GMD_ATTN_BF16EXP
 #define GMD_ATTN_BF16EXP 0
 #endif
@@ -450,7 +462,102 @@ attn_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ C
                     for (int k = 0; k < 32; ++k) if (k >= valid) v[k] = 0xff800000u;  // -inf
                 }
             };
-            for (int j = set; j < T; j += 2, ++n_own) {
+            // FINE: the whole tile is exponentiated against the stale maximum, piece by piece as it comes out of TMEM; the tile maximum is
+            // formed on the side and growth beyond the lazy window redoes the tile (the set's first tile takes a maximum-only pass first).
+            auto ex2v = [](float x) { float y; asm volatile("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; };
+            auto fine_pass = [&](int valid, float m_use, int pv_parity, bool do_exp, float& mx_out) {
+                constexpr int CH = GMD_ATTN_FINE_CH, NCH = BKV / CH;   // columns per TMEM read
+                uint32_t a[CH], b[CH];
+                float mx0 = -INFINITY, mx1 = -INFINITY;
+                auto ld = [&](int cidx, uint32_t (&dst)[CH]) {
+#if GMD_ATTN_FINE_CH == 8
+                    tmem_ld_32x8(s_addr + cidx * CH, dst);
+#elif GMD_ATTN_FINE_CH == 16
+                    tmem_ld_32x16(s_addr + cidx * CH, dst);
+#else
+                    tmem_ld_32x32(s_addr + cidx * CH, dst);
+#endif
+                };
+                if (GMD_ATTN_FINE_PREF) ld(0, a);
+#pragma unroll
+                for (int cidx = 0; cidx < NCH; ++cidx) {
+                    uint32_t (&cur)[CH] = (cidx & 1) ? b : a;
+                    uint32_t (&nxt)[CH] = (cidx & 1) ? a : b;
+                    if (!GMD_ATTN_FINE_PREF) ld(cidx, cur);
+                    tmem_wait_ld();
+                    if (GMD_ATTN_FINE_PREF && cidx < NCH - 1) ld(cidx + 1, nxt);
+                    if (valid < (cidx + 1) * CH) {
+#pragma unroll
+                        for (int k = 0; k < CH; ++k) if (cidx * CH + k >= valid) cur[k] = 0xff800000u;
+                    }
+#pragma unroll
+                    for (int k = 0; k < CH; k += 2) {
+                        mx0 = fmaxf(mx0, __uint_as_float(cur[k])); mx1 = fmaxf(mx1, __uint_as_float(cur[k + 1]));
+                    }
+                    if (do_exp) {
+#pragma unroll
+                        for (int q8 = 0; q8 < CH / 8; ++q8) {
+                            uint32_t pk[4];
+#pragma unroll
+                            for (int k = 0; k < 4; ++k) {
+                                const float x0 = fmaf(__uint_as_float(cur[q8 * 8 + 2 * k]), c, -m_use), x1 = fmaf(__uint_as_float(cur[q8 * 8 + 2 * k + 1]), c, -m_use);
+                                pk[k] = pack_bf16x2(ex2v(x0), ex2v(x1));
+                            }
+                            if (cidx == 0 && q8 == 0 && pv_parity >= 0) mbar_wait(&pv_done[set], pv_parity);
+                            const int cc = cidx * (CH / 8) + q8;
+                            *reinterpret_cast<uint4*>(prow + ((cc ^ (row & 7)) << 4)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+                        }
+                    }
+                }
+                mx_out = fmaxf(mx0, mx1);
+            };
+            for (int j = set; GMD_ATTN_FINE && j < T; j += 2, ++n_own) {
+                const int valid = args.Nk - j * BKV;
+                mbar_wait(&s_full[set], n_own & 1);
+                tc_fence_after();
+                float mx;
+                if (n_own == 0) {   // the set's first tile: maximum first
+                    fine_pass(valid, 0.0f, -1, false, mx);
+                    m = mx * c;
+                    fine_pass(valid, m, -1, true, mx);
+                } else {
+                    fine_pass(valid, m, (n_own - 1) & 1, true, mx);
+                    const float mt = mx * c;
+                    const bool grow = mt > m + C::LAZY_T;
+                    if (__any_sync(0xffffffffu, grow)) {   // rare: a row maximum left the lazy window -> new maximum, tile again, O rescaled
+                        const float m_new = grow ? mt : m;
+                        const float alpha = grow ? ex2(m - m_new) : 1.0f;
+                        m = m_new;
+                        fine_pass(valid, m, -1, true, mx);
+                        tc_fence_after();   // (pv_done of the previous tile was awaited before the first P store)
+#pragma unroll
+                        for (int ch = 0; ch < C::DPV / 16; ++ch) {
+                            uint32_t o[16];
+                            tmem_ld_32x16(my_o + ch * 16, o);
+                            tmem_wait_ld();
+#pragma unroll
+                            for (int k = 0; k < 16; ++k) o[k] = __float_as_uint(__uint_as_float(o[k]) * alpha);
+                            tmem_st_32x16(my_o + ch * 16, o);
+                        }
+                        tmem_wait_st();
+                    }
+                }
+                tc_fence_before();
+                mbar_arrive(&s_free[set]);
+                {
+                    const int st = j % C::VS;
+                    mbar_wait(&v_full[st], (j / C::VS) & 1);
+                    if (row < BKV) {
+                        constexpr int blk = D / 64, cc = (D % 64) / 8, within = (D % 8) * 2;
+                        uint8_t* vrow = v_smem + st * C::K_BYTES + blk * C::KV_BLOCK_BYTES + row * 128;
+                        *reinterpret_cast<uint16_t*>(vrow + ((cc ^ (row & 7)) << 4) + within) = 0x3F80;  // bf16 1.0
+                    }
+                }
+                fence_proxy_async_smem();
+                tc_fence_before();
+                mbar_arrive(&p_full[set]);
+            }
+            for (int j = set; !GMD_ATTN_FINE && j < T; j += 2, ++n_own) {
                 const int valid = args.Nk - j * BKV;
                 if (!(GMD_ATTN_KO & 32)) mbar_wait(&s_full[set], n_own & 1);
                 tc_fence_after();
