@@ -1,21 +1,22 @@
 // Kernel (a): flash attention on tcgen05 + TMEM, fed by TMA.   O = softmax(Q K^T * scale) V
 //
-// One CTA owns 128 query rows of one (batch, head).  Warp 0 = TMA producer (lane 0: Q then the K ring, lane 1: the V
-// ring), warp 1 = MMA issuer, warps 2-5 = softmax (one thread per query row = one TMEM lane).
+// attn_kernel<D, SHORT>: one CTA owns 128 query rows of one (batch, head).  Warp 0 = TMA producer (lane 0: Q then the K ring,
+// lane 1: the V ring), warp 1 = MMA issuer, warps 2.. = softmax (one thread per query row = one TMEM lane).
 //   S_j = Q K_j^T : tcgen05.mma  A = Q smem (K-major), B = K smem (K-major)     -> TMEM S[j&1]   (double buffered)
-//   P_j = 2^(..)  : softmax warps read S with tcgen05.ld, write bf16 P to smem (K-major, 128B swizzle, double buffered)
+//   P_j = 2^(..)  : softmax warps read S with tcgen05.ld, write bf16 P to smem (K-major, 128B swizzle)
 //   O  += P_j V_j : tcgen05.mma  A = P smem (K-major), B = V smem (MN-major)    -> TMEM O
+// xattn_kernel<D>: text cross-attention (77 keys) with K / V resident and a loop over query tiles (second half of this file).
 // Design points
-//   * S is double buffered and S_{j+2} is issued as soon as softmax_j has drained S[j&1], so the QK^T round trip is
-//     never on the softmax warps' critical path; two CTAs are co-resident per SM for d = 40/80.
-//   * the softmax denominator comes out of the SAME MMA as O: column D of the V tile (zero padding written by TMA's
-//     out-of-bounds fill) is overwritten with ones, so O[:, D] = sum_k P[:, k] in fp32, rescaled together with O.
-//   * O is rescaled in TMEM lazily: only when a row maximum grew by more than 2^8 (the stale maximum keeps every
-//     exponent <= 8, well inside bf16/fp32 range), so after the first tiles the correction path is almost never taken.
-//   * per key the softmax warps execute FMNMX + FFMA + MUFU.EX2 + half a pack: the exp2 argument is one fused
-//     s * (scale*log2e) - m, and the kernel is bound by the 16 ex2/clk/SM special-function rate at d = 40.
-// Head dims 40/80/160 (SD1.5: 8 heads at every level) are zero-padded to a multiple of 16 for free by TMA: the tensor
-// map's innermost dim is the true head dim, the box is 64 wide.
+//   * the softmax denominator comes out of the SAME MMA as O: column D of the V tile is overwritten with ones, so
+//     O[:, D] = sum_k P[:, k] in fp32, rescaled together with O.
+//   * O is rescaled in TMEM lazily: only when a row maximum grew by more than 2^8 (the stale maximum keeps every exponent <= 8,
+//     well inside bf16 / fp32 range), so after the first tiles the correction path is almost never taken.
+//   * d = 40 runs two softmax warp sets on alternating whole tiles (Cfg::ALT), exponentiating against the stale maximum.
+//   * K / V tiles are fetched through a dense (channel, token, batch) map: no out-of-bounds fill on the 80-byte head rows (launch()).
+//   * what bounds d = 40: the TMEM read of S (128x64 fp32 per tile at 64 B/clk/SM = 512 cycles) and its 8192 ex2 (16/clk/SM = 512
+//     cycles) — two co-equal floors; the tensor pipe is 25 % busy.
+// Head dims 40/80/160 (SD1.5: 8 heads at every level) are zero-padded to a multiple of 16 for free by TMA on the Q side: that
+// tensor map's innermost dim is the true head dim, the box is 64 wide.
 #include "common.cuh"
 #include "../../include/gmd_b200.h"
 
@@ -23,59 +24,17 @@ namespace gmd {
 void count_launch(int n);
 namespace {
 
-#ifndef GMD_ATTN_PIPE
-#define GMD_ATTN_PIPE 0
-#endif
-#ifndef GMD_ATTN_ALT
-#define GMD_ATTN_ALT 1
-#endif
-// Three follow-ups suggested by the ncu stall samples of the ALT kernel (23 % of all samples sit on the s_full / pv_done / v_full
-// waits of the softmax warps) were built, measured at B=16, N=4096 and left OFF: a 4-deep V ring (416 vs 419 TFLOP/s), S_{j+3}
-// queued ahead of P V_j to force the sets half a tile apart (354), the first two P chunks held in registers across the pv_done wait
-// (371 with all three on).  The waits are slack, not the critical path.
-// timing-only knock-outs (wrong results; never set in the product build): 1 = no MUFU (exponentials replaced by the argument),
-// 2 = no ones column / V wait in the softmax warps, 4 = no P stores, 8 = no row maxima
+// Timing-only knock-outs (wrong results; never set in the product build) — how DESIGN.md §3a located the bounds of these kernels:
+// build a second library with -DGMD_ATTN_KO=<bits> and run profiles/bench_attn.py against it (GMD_AB_LIB).
+//   attn_kernel d = 40:  1 no MUFU (exponentials replaced by their argument), 2 no ones column / V wait in the softmax warps,
+//                        4 no P stores, 8 no row maxima, 16 no pv_done wait, 32 no s_full wait, 64 producer ignores the ring's
+//                        empty barriers, 128 MMA warp ignores s_free, 256 no K / V loads
+//   xattn_kernel:        1 no MUFU, 4 no P stores, 8 no row maxima
 #ifndef GMD_ATTN_KO
 #define GMD_ATTN_KO 0
 #endif
-#ifndef GMD_ATTN_FINE
-#define GMD_ATTN_FINE 1
-#endif
-// B=16, N=4096, d=40: 32 columns per read without prefetch 721 us (default); 16 / 8 columns 747 / 756; with the next read in flight
-// under the exponentials 757-766 for every size (an in-flight tcgen05.ld serialises with the same sub-partition's MUFU stream);
-// half-tile variant below (!GMD_ATTN_FINE) 731
-#ifndef GMD_ATTN_FINE_CH
-#define GMD_ATTN_FINE_CH 32
-#endif
-#ifndef GMD_ATTN_FINE_PREF
-#define GMD_ATTN_FINE_PREF 0
-#endif
-#ifndef GMD_ATTN_BF16EXP
-#define GMD_ATTN_BF16EXP 0
-#endif
-#ifndef GMD_ATTN_POLY
-#define GMD_ATTN_POLY 0
-#endif
 #ifndef GMD_XATTN_KO
-#define GMD_XATTN_KO 0   // timing-only knock-outs of the text cross-attention kernel: 1 no MUFU, 2 no epilogue, 4 no P stores, 8 no maxima
-#endif
-#ifndef GMD_ATTN_XATTN
-#define GMD_ATTN_XATTN 1
-#endif
-#ifndef GMD_ATTN_KVDENSE
-#define GMD_ATTN_KVDENSE 1
-#endif
-#ifndef GMD_ATTN_KS
-#define GMD_ATTN_KS 2
-#endif
-#ifndef GMD_ATTN_VS
-#define GMD_ATTN_VS 2
-#endif
-#ifndef GMD_ATTN_SEARLY
-#define GMD_ATTN_SEARLY 0
-#endif
-#ifndef GMD_ATTN_PVHOLD
-#define GMD_ATTN_PVHOLD 0
+#define GMD_XATTN_KO 0
 #endif
 constexpr int BQ = 128;   // query rows per CTA
 constexpr int BKV = 64;   // keys per tile (one 128-byte swizzle row of P)
@@ -94,61 +53,30 @@ __device__ __forceinline__ float ex2(float x) {
     return y;
 }
 
-// 2^x for x <= 0 on the FMA / integer pipes (Cody-Waite split at the nearest integer through the 1.5*2^23 magic constant, degree-3
-// minimax polynomial for 2^f on [-0.5, 0.5]: max relative error 7.5e-5, 26x below the bf16 rounding of P that follows; the
-// integer part goes straight into the exponent field).  Every second pair of a row's probabilities is computed this way, so the
-// special-function pipe (16 lanes/clk/SM, shared with the fp32->bf16 packs) sees half of the exponentials.
-__device__ __forceinline__ float ex2_poly(float x) {
-    x = fmaxf(x, -126.0f);
-    const float t = x + 12582912.0f;
-    const float f = x - (t - 12582912.0f);
-    float p = fmaf(0.0551716648f, f, 0.2426111251f);
-    p = fmaf(p, f, 0.6932609677f);
-    p = fmaf(p, f, 0.9999280572f);
-    return __int_as_float(__float_as_int(p) + (__float_as_int(t) << 23));
-}
-
-// Packed exponentials: two bf16 logits in, two bf16 probabilities out, ONE special-function instruction (the probabilities are
-// rounded to bf16 for the P V MMA anyway).  The logit difference x = s*c - m is rounded to bf16 first: relative error of 2^x is
-// <= ln2 * 2^-9 * |x| (0.14 % at |x| < 1, the same size as the bf16 rounding of p itself), which is why the lazy-rescale window
-// is narrowed to LAZY_T when this path is on.
-__device__ __forceinline__ uint32_t ex2_bf16x2(float x_lo, float x_hi) {
-    uint32_t xb, y;
-    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(xb) : "f"(x_hi), "f"(x_lo));
-    asm("ex2.approx.ftz.bf16x2 %0, %1;" : "=r"(y) : "r"(xb));
-    return y;
-}
-
 template <int D, bool SHORT = false>
 struct Cfg {
     static constexpr int NDB = (D + 63) / 64;               // 64-wide d blocks
     static constexpr int DP = (D + 15) / 16 * 16;           // K extent of Q K^T
     static constexpr int DPV = (D + 1 + 15) / 16 * 16;      // N extent of P V: head dim + the ones column
     static_assert(DPV <= NDB * 64, "ones column must fall inside the loaded V blocks");
-    // K / V ring depths (measured at d = 40: 3-deep rings change nothing, 394 vs 392 TFLOP/s — the kernel is not waiting for K/V;
-    // 4-deep rings cost the second resident CTA)
-    static constexpr int KS = (D == 40 && !SHORT) ? GMD_ATTN_KS : 2;
+    // K / V ring depth (measured at d = 40: 3- and 4-deep rings change nothing — the kernel is not waiting for K / V)
+    static constexpr int KS = 2, VS = KS;
     // (measured: three co-resident CTAs per SM with single-buffered S / P at d = 40 reach 354 TFLOP/s vs 378 for two CTAs
     // with double buffering, so the double-buffered configuration stays)
     // SHORT (text cross-attention, Nk <= 2 key tiles): the whole CTA lives for ~2 tiles, so what matters is how many CTAs are
     // resident to overlap their prologues (TMEM allocation, Q / K / V round trip) — single S and P buffers, one softmax set:
     // 112 TMEM columns and ~64 KB of shared memory per CTA at d = 40 instead of 224 columns and 80 KB
     static constexpr int SB = SHORT ? 1 : 2;                // S buffers in TMEM
-    // NSET = 2 (d = 40): the 64 keys of a tile are split between TWO independent softmax warp sets (8 warps), each with its
-    // own running maximum, its own O accumulator and its own denominator (flash-decoding style split over keys, merged once
-    // at the end).  ncu on the 4-warp version: XU (MUFU) pipe 52 % busy, issue slots 39 % — latency-bound with one softmax
-    // warp per sub-partition per CTA; the split doubles the warps in flight without any cross-warp exchange per tile.
+    // NSET = 2 (d = 40): TWO independent softmax warp sets (8 warps), each with its own running maximum, its own O accumulator and
+    // its own denominator (a flash-decoding style split over keys, merged once at the end): one softmax warp per sub-partition per
+    // CTA was latency-bound (ncu: XU pipe 52 % busy, issue slots 39 %).
     static constexpr int NSET = (D == 40 && !SHORT) ? 2 : 1;
     static constexpr int KW = BKV / NSET;                   // keys per softmax thread per tile
-    // ALT (d = 40): the two warp sets own ALTERNATING WHOLE TILES (set s: tiles j = s mod 2, S buffer s, P buffer s, O accumulator s)
-    // instead of the two key halves of every tile.  Per synchronisation round a thread now handles 64 keys instead of 32 (half the
-    // barrier / fence / arrive overhead per exponential) and the two sets of a CTA run out of phase, so an SM has four independent
-    // softmax phase groups instead of two to keep the special-function pipe fed.  The exponentials of the first 32 keys use the
-    // running (stale) maximum without waiting for this tile's maximum; the tile maximum is known before the second 32, and a growth
-    // beyond the lazy window (rare after the first tile) redoes the first half from TMEM.
-    static constexpr bool ALT = NSET == 2 && GMD_ATTN_ALT;
-    // V ring depth (see GMD_ATTN_VS above: deeper rings measured neutral)
-    static constexpr int VS = ALT ? GMD_ATTN_VS : KS;
+    // ALT: the two sets own ALTERNATING WHOLE TILES (set s: tiles j = s mod 2, S buffer s, P buffer s, O accumulator s) rather than
+    // the two key halves of every tile: per synchronisation round a thread handles 64 keys instead of 32 and the sets of a CTA run
+    // out of phase.  A tile is exponentiated against the running (stale) maximum while its own maximum is formed on the side;
+    // growth beyond the lazy window (rare after a set's first tile, which takes a maximum-only pass first) redoes the tile from TMEM.
+    static constexpr bool ALT = NSET == 2;
     static constexpr int THREADS = 64 + 128 * NSET;
     static constexpr int PB = (D == 80 || SHORT) ? 1 : 2;   // P buffers in smem (one at d = 80 keeps two CTAs per SM)
     static constexpr int Q_BYTES = NDB * BQ * 128;
@@ -163,22 +91,12 @@ struct Cfg {
     static constexpr uint32_t TMEM_COLS = (SB * BKV + NSET * DPV) <= 128 ? 128 : (SB * BKV + NSET * DPV) <= 256 ? 256 : 512;
     static_assert(NSET == 1 || P_BYTES * PB >= BQ * (DPV + 1) * 4, "merge scratch must fit in the P buffers");
     static constexpr int MIN_CTAS = SHORT ? (D == 40 ? 3 : D == 80 ? 2 : 1) : (D <= 80 ? 2 : 1);
-    // half of the exponentials on the FMA pipe (ex2_poly): measured 394 -> 377 TFLOP/s at d = 40 and 353 -> 361 at d = 80 with every second pair, 393 / 360 with one pair in four — the
-    // softmax warps are issue/latency-bound, not special-function-bound, so the extra ~8 instructions per element cost more than
-    // the freed MUFU slots give back.  Kept for the record, off.
-    static constexpr bool POLY_EXP = false;
-    // packed bf16x2 exponentials (see ex2_bf16x2): halve the special-function work and remove the pack, accuracy unchanged
-    // (UNet eps 8.47e-3 either way) — and no faster (388.7 vs 392 TFLOP/s at d = 40): with deeper K/V rings, the polynomial exp2
-    // and this all neutral, what paces the kernel is the per-tile latency chain of a softmax warp (S ready -> tcgen05.ld -> max ->
-    // exp -> P to shared memory -> fence -> arrive), ~1900 cycles per tile per CTA with two CTAs per SM.  Off: fp32 exponentials.
-    static constexpr bool BF16_EXP = false;
-    static constexpr float LAZY_T = (BF16_EXP || GMD_ATTN_BF16EXP) ? 2.0f : 8.0f;  // lazy-rescale window of the running maximum, in log2 units
-    // software-pipelined TMEM reads of S in the softmax warps (needs the double-buffered S): see `tile` in the kernel.  Measured
-    // and OFF: with the request for S_{j+1} issued in the middle of tile j's exponentials (no spills) d = 40 drops from 413 to 346
-    // TFLOP/s and d = 160 from 228 to 210 — an in-flight tcgen05.ld does not overlap the MUFU stream of the same warp.  What did
-    // help is storing every 16-byte chunk of P as soon as its eight probabilities exist (376 -> 413 at d = 40, 141 -> 228 at d = 160).
-    static constexpr bool PIPE = SB == 2 && GMD_ATTN_PIPE;
-    static constexpr int PIPE_AT = KW == 32 ? 8 : 16;   // pair index in the exponential loop where S_{j+1} is requested (d = 80: later, register budget of two CTAs/SM)                   // pair index in the exponential loop where S_{j+1} is requested
+    static constexpr float LAZY_T = 8.0f;   // lazy-rescale window of the running maximum, in log2 units
+    // Measured and not kept (numbers at B=16, N=4096, d=40 unless noted; DESIGN.md §3a has the full list): the next tile's TMEM read in
+    // flight under the exponentials (serialises with the same sub-partition's MUFU stream: 993 us vs 785 without, both sets variants),
+    // 8- / 16-column TMEM reads (756 / 747 vs 721 us), packed ex2.approx.bf16x2 (915 us: its narrow lazy window fires the redo
+    // path), a degree-3 polynomial exp2 on the FMA pipe for 1/4, 1/3, 1/2 of the pairs (724 / 766 / 800 vs 731 us: issue-bound),
+    // S_{j+3} queued ahead of P V_j, P chunks held across the pv_done wait, three CTAs per SM with single-buffered S.
 };
 
 template <int D, bool SHORT>
@@ -272,20 +190,16 @@ attn_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ C
             mbar_wait(q_full, 0);
             issue_s(0);
             if (C::SB > 1 && T > 1) issue_s(1);
-            // ALT: S_{i+2} reuses buffer i&1 as soon as its set has the logits of tile i in registers (mid-tile).  Issue order
-            // S_2 | S_3 PV_0 | S_4 PV_1 | ...: P V_{j} is queued behind S_{j+3}, i.e. behind the OTHER set's mid-tile point, which
-            // pushes the two sets of a CTA half a tile out of phase.
-            auto issue_s_after_free = [&](int i) {
-                if (i + 2 < T) {
-                    if (!(GMD_ATTN_KO & 128)) mbar_wait(&s_free[i & 1], (i >> 1) & 1);
-                    tc_fence_after();
-                    issue_s(i + 2);
-                }
-            };
-            if constexpr (C::ALT && GMD_ATTN_SEARLY) issue_s_after_free(0);
             for (int j = 0; j < T; ++j) {
                 const int st = j % C::VS;
-                if constexpr (C::ALT) issue_s_after_free(GMD_ATTN_SEARLY ? j + 1 : j);
+                if constexpr (C::ALT) {
+                    // S_{j+2} reuses buffer j&1 as soon as its set has taken the logits of tile j out of TMEM, ahead of P V_j
+                    if (j + 2 < T) {
+                        if (!(GMD_ATTN_KO & 128)) mbar_wait(&s_free[j & 1], (j >> 1) & 1);
+                        tc_fence_after();
+                        issue_s(j + 2);
+                    }
+                }
                 mbar_wait(&p_full[j & 1], (j >> 1) & 1);   // softmax_j: P_j in smem, ones column set, S[j&1] drained
                 mbar_wait(&v_full[st], (j / C::VS) & 1);
                 tc_fence_after();
@@ -316,17 +230,14 @@ attn_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ C
         const uint32_t my_o = tmem_o + set * C::DPV + lane_off;
         const float c = args.scale_log2;
         float m = -INFINITY;   // running (possibly stale) row maximum of THIS key half in scaled log2 units
-        // S_j -> registers (asynchronous: the values are valid after tmem_wait_ld)
-        auto load_s = [&](int j, uint32_t (&dst)[KW]) {
+        // One key tile of the single-set configurations (d = 80 / 160 and the short text cross-attention)
+        auto tile = [&](int j, uint32_t (&sr)[KW]) {
             mbar_wait(&s_full[j % C::SB], (j / C::SB) & 1);
             tc_fence_after();
-            const uint32_t a = tmem_base + (j % C::SB) * BKV + lane_off + set * KW;
-            if constexpr (KW == 64) tmem_ld_32x64(a, dst); else tmem_ld_32x32(a, dst);
-        };
-        // One key tile.  PIPE: the logits of tile j were requested during tile j-1 and the request for tile j+1 goes out in the
-        // middle of this tile's exponentials, so neither the wait for S nor the TMEM read latency is on this warp's per-tile chain.
-        auto tile = [&](int j, uint32_t (&sr)[KW], uint32_t (&sn)[KW]) {
-            if constexpr (!C::PIPE) load_s(j, sr);
+            {
+                const uint32_t a = tmem_base + (j % C::SB) * BKV + lane_off + set * KW;
+                if constexpr (KW == 64) tmem_ld_32x64(a, sr); else tmem_ld_32x32(a, sr);
+            }
             tmem_wait_ld();
             const int valid = args.Nk - j * BKV - set * KW;  // columns >= valid are padding keys (last tile only)
             if (valid < KW) {
@@ -357,18 +268,8 @@ attn_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ C
             uint32_t pk[4];
 #pragma unroll
             for (int k = 0; k < KW / 2; ++k) {
-                if (C::PIPE && k == C::PIPE_AT) {
-                    if (j + 1 < T) load_s(j + 1, sn);
-                }
                 const float x0 = fmaf(__uint_as_float(sr[2 * k]), c, -m_sub), x1 = fmaf(__uint_as_float(sr[2 * k + 1]), c, -m_sub);
-                if (C::BF16_EXP) {
-                    pk[k & 3] = ex2_bf16x2(x0, x1);
-                } else {
-                    const bool poly = C::POLY_EXP && (k & 3) == 3;   // one pair in four
-                    const float p0 = poly ? ex2_poly(x0) : ex2(x0);
-                    const float p1 = poly ? ex2_poly(x1) : ex2(x1);
-                    pk[k & 3] = pack_bf16x2(p0, p1);
-                }
+                pk[k & 3] = pack_bf16x2(ex2(x0), ex2(x1));
                 if ((k & 3) == 3) {
                     const int cc = set * (KW / 8) + (k >> 2);
                     *reinterpret_cast<uint4*>(prow + ((cc ^ (row & 7)) << 4)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
@@ -388,7 +289,6 @@ attn_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ C
             if (j > 0 && __any_sync(0xffffffffu, grow)) {
                 mbar_wait(&pv_done[(j - 1) & 1], ((j - 1) >> 1) & 1);   // O must be complete up to tile j-1
                 tc_fence_after();
-                if constexpr (C::PIPE) tmem_wait_ld();   // the in-flight read of S_{j+1} must land before the scratch registers below are recycled
 #pragma unroll
                 for (int ch = 0; ch < C::DPV / 16; ++ch) {
                     uint32_t o[16];
@@ -408,87 +308,23 @@ attn_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ C
         if constexpr (C::ALT) {
             const uint32_t s_addr = tmem_base + set * BKV + lane_off;
             uint8_t* prow = p_smem + set * C::P_BYTES + row * 128;
-            // exponentials of 32 logits against the maximum m_sub; every 16-byte chunk of the P row (K-major SWIZZLE_128B) is stored as
-            // soon as it exists.  `pv_parity` >= 0: wait for the P V MMA that last read this P buffer just before the first store.
-            auto exp_half = [&](const uint32_t (&v)[32], float m_sub, int chunk0, int pv_parity) {
-                // (the first HOLD chunks stay in registers until that P V has been awaited: it was issued when this set finished its
-                // previous tile, a few hundred cycles ago)
-                constexpr int HOLD = GMD_ATTN_PVHOLD ? 2 : 1;
-                uint32_t pk[4 * HOLD] = {};
-                auto store_chunk = [&](int ch) {
-                    const int cc = chunk0 + ch, b = (ch % HOLD) * 4;
-                    if ((GMD_ATTN_KO & 4) && pk[b] != 0x12345678u) return;
-                    *reinterpret_cast<uint4*>(prow + ((cc ^ (row & 7)) << 4)) = make_uint4(pk[b], pk[b + 1], pk[b + 2], pk[b + 3]);
-                };
-#pragma unroll
-                for (int k = 0; k < 16; ++k) {
-                    const float x0 = fmaf(__uint_as_float(v[2 * k]), c, -m_sub), x1 = fmaf(__uint_as_float(v[2 * k + 1]), c, -m_sub);
-                    if (GMD_ATTN_KO & 1) {
-                        pk[k % (4 * HOLD)] = pack_bf16x2(x0, x1);
-                    } else if (GMD_ATTN_BF16EXP) {
-                        pk[k % (4 * HOLD)] = ex2_bf16x2(x0, x1);
-                    } else {
-                        const bool poly = GMD_ATTN_POLY > 0 && (k % (GMD_ATTN_POLY > 0 ? GMD_ATTN_POLY : 1)) == 0;
-                        pk[k % (4 * HOLD)] = poly ? pack_bf16x2(ex2_poly(x0), ex2_poly(x1)) : pack_bf16x2(ex2(x0), ex2(x1));
-                    }
-                    if ((k & 3) == 3) {
-                        const int ch = k >> 2;
-                        if (pv_parity >= 0 && ch < HOLD) {
-                            if (ch == HOLD - 1) {
-                                if (!(GMD_ATTN_KO & 16)) mbar_wait(&pv_done[set], pv_parity);
-#pragma unroll
-                                for (int h = 0; h < HOLD; ++h) store_chunk(h);
-                            }
-                        } else {
-                            store_chunk(ch);
-                        }
-                    }
-                }
-            };
-            auto max32 = [&](const uint32_t (&v)[32]) {
-                float mx0 = __uint_as_float(v[0]), mx1 = __uint_as_float(v[1]), mx2 = __uint_as_float(v[2]), mx3 = __uint_as_float(v[3]);
-#pragma unroll
-                for (int k = 4; k < ((GMD_ATTN_KO & 8) ? 4 : 32); k += 4) {
-                    mx0 = fmaxf(mx0, __uint_as_float(v[k])); mx1 = fmaxf(mx1, __uint_as_float(v[k + 1]));
-                    mx2 = fmaxf(mx2, __uint_as_float(v[k + 2])); mx3 = fmaxf(mx3, __uint_as_float(v[k + 3]));
-                }
-                return fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3));
-            };
-            auto load_half = [&](int h, int valid, uint32_t (&v)[32]) {
-                tmem_ld_32x32(s_addr + h * 32, v);
-                tmem_wait_ld();
-                if (valid < 32) {   // padding keys (last tile only)
-#pragma unroll
-                    for (int k = 0; k < 32; ++k) if (k >= valid) v[k] = 0xff800000u;  // -inf
-                }
-            };
-            // FINE: the whole tile is exponentiated against the stale maximum, piece by piece as it comes out of TMEM; the tile maximum is
-            // formed on the side and growth beyond the lazy window redoes the tile (the set's first tile takes a maximum-only pass first).
+            // One pass over the tile in two 32-column TMEM reads: row maximum on the side and, with `do_exp`, the probabilities
+            // 2^(s*c - m_use) as bf16 into the P row (K-major SWIZZLE_128B: 16-byte chunk cc of row r lands at chunk cc ^ (r & 7)),
+            // every chunk stored as soon as its eight values exist.  `pv_parity` >= 0: the P V MMA that last read this P buffer is
+            // awaited just before the first store.  (volatile ex2: keeps the exponentials in program order behind their TMEM read.)
             auto ex2v = [](float x) { float y; asm volatile("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; };
-            auto fine_pass = [&](int valid, float m_use, int pv_parity, bool do_exp, float& mx_out) {
-                constexpr int CH = GMD_ATTN_FINE_CH, NCH = BKV / CH;   // columns per TMEM read
+            auto tile_pass = [&](int valid, float m_use, int pv_parity, bool do_exp, float& mx_out) {
+                constexpr int CH = 32, NCH = BKV / CH;
                 uint32_t a[CH], b[CH];
                 float mx0 = -INFINITY, mx1 = -INFINITY;
-                auto ld = [&](int cidx, uint32_t (&dst)[CH]) {
-#if GMD_ATTN_FINE_CH == 8
-                    tmem_ld_32x8(s_addr + cidx * CH, dst);
-#elif GMD_ATTN_FINE_CH == 16
-                    tmem_ld_32x16(s_addr + cidx * CH, dst);
-#else
-                    tmem_ld_32x32(s_addr + cidx * CH, dst);
-#endif
-                };
-                if (GMD_ATTN_FINE_PREF) ld(0, a);
 #pragma unroll
                 for (int cidx = 0; cidx < NCH; ++cidx) {
                     uint32_t (&cur)[CH] = (cidx & 1) ? b : a;
-                    uint32_t (&nxt)[CH] = (cidx & 1) ? a : b;
-                    if (!GMD_ATTN_FINE_PREF) ld(cidx, cur);
+                    tmem_ld_32x32(s_addr + cidx * CH, cur);
                     tmem_wait_ld();
-                    if (GMD_ATTN_FINE_PREF && cidx < NCH - 1) ld(cidx + 1, nxt);
-                    if (valid < (cidx + 1) * CH) {
+                    if (valid < (cidx + 1) * CH) {   // padding keys (last tile only)
 #pragma unroll
-                        for (int k = 0; k < CH; ++k) if (cidx * CH + k >= valid) cur[k] = 0xff800000u;
+                        for (int k = 0; k < CH; ++k) if (cidx * CH + k >= valid) cur[k] = 0xff800000u;  // -inf
                     }
 #pragma unroll
                     for (int k = 0; k < CH; k += 2) {
@@ -501,34 +337,35 @@ attn_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ C
 #pragma unroll
                             for (int k = 0; k < 4; ++k) {
                                 const float x0 = fmaf(__uint_as_float(cur[q8 * 8 + 2 * k]), c, -m_use), x1 = fmaf(__uint_as_float(cur[q8 * 8 + 2 * k + 1]), c, -m_use);
-                                pk[k] = pack_bf16x2(ex2v(x0), ex2v(x1));
+                                pk[k] = (GMD_ATTN_KO & 1) ? pack_bf16x2(x0, x1) : pack_bf16x2(ex2v(x0), ex2v(x1));
                             }
-                            if (cidx == 0 && q8 == 0 && pv_parity >= 0) mbar_wait(&pv_done[set], pv_parity);
+                            if (cidx == 0 && q8 == 0 && pv_parity >= 0 && !(GMD_ATTN_KO & 16)) mbar_wait(&pv_done[set], pv_parity);
                             const int cc = cidx * (CH / 8) + q8;
+                            if ((GMD_ATTN_KO & 4) && pk[0] != 0x12345678u) continue;
                             *reinterpret_cast<uint4*>(prow + ((cc ^ (row & 7)) << 4)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
                         }
                     }
                 }
                 mx_out = fmaxf(mx0, mx1);
             };
-            for (int j = set; GMD_ATTN_FINE && j < T; j += 2, ++n_own) {
+            for (int j = set; j < T; j += 2, ++n_own) {
                 const int valid = args.Nk - j * BKV;
-                mbar_wait(&s_full[set], n_own & 1);
+                if (!(GMD_ATTN_KO & 32)) mbar_wait(&s_full[set], n_own & 1);
                 tc_fence_after();
                 float mx;
                 if (n_own == 0) {   // the set's first tile: maximum first
-                    fine_pass(valid, 0.0f, -1, false, mx);
+                    tile_pass(valid, 0.0f, -1, false, mx);
                     m = mx * c;
-                    fine_pass(valid, m, -1, true, mx);
+                    tile_pass(valid, m, -1, true, mx);
                 } else {
-                    fine_pass(valid, m, (n_own - 1) & 1, true, mx);
+                    tile_pass(valid, m, (n_own - 1) & 1, true, mx);
                     const float mt = mx * c;
                     const bool grow = mt > m + C::LAZY_T;
                     if (__any_sync(0xffffffffu, grow)) {   // rare: a row maximum left the lazy window -> new maximum, tile again, O rescaled
                         const float m_new = grow ? mt : m;
                         const float alpha = grow ? ex2(m - m_new) : 1.0f;
                         m = m_new;
-                        fine_pass(valid, m, -1, true, mx);
+                        tile_pass(valid, m, -1, true, mx);
                         tc_fence_after();   // (pv_done of the previous tile was awaited before the first P store)
 #pragma unroll
                         for (int ch = 0; ch < C::DPV / 16; ++ch) {
@@ -543,59 +380,8 @@ attn_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ C
                     }
                 }
                 tc_fence_before();
-                mbar_arrive(&s_free[set]);
-                {
-                    const int st = j % C::VS;
-                    mbar_wait(&v_full[st], (j / C::VS) & 1);
-                    if (row < BKV) {
-                        constexpr int blk = D / 64, cc = (D % 64) / 8, within = (D % 8) * 2;
-                        uint8_t* vrow = v_smem + st * C::K_BYTES + blk * C::KV_BLOCK_BYTES + row * 128;
-                        *reinterpret_cast<uint16_t*>(vrow + ((cc ^ (row & 7)) << 4) + within) = 0x3F80;  // bf16 1.0
-                    }
-                }
-                fence_proxy_async_smem();
-                tc_fence_before();
-                mbar_arrive(&p_full[set]);
-            }
-            for (int j = set; !GMD_ATTN_FINE && j < T; j += 2, ++n_own) {
-                const int valid = args.Nk - j * BKV;
-                if (!(GMD_ATTN_KO & 32)) mbar_wait(&s_full[set], n_own & 1);
-                tc_fence_after();
-                uint32_t sa[32], sb[32];
-                load_half(0, valid, sa);
-                const float mxa = max32(sa);
-                // first half against the stale maximum: the special-function pipe starts right after the TMEM read
-                // (the set's first tile has no maximum yet and always takes the redo path below)
-                if (n_own > 0) exp_half(sa, m, 0, (n_own - 1) & 1);
-                load_half(1, valid - 32, sb);
-                const float mt = fmaxf(mxa, max32(sb)) * c;
-                const bool grow = mt > m + C::LAZY_T;
-                if (__any_sync(0xffffffffu, grow)) {
-                    // the first tile of the set, or a row maximum that left the lazy window: new maximum, first half again, O rescaled
-                    const float m_new = grow ? mt : m;
-                    const float alpha = grow ? ex2(m - m_new) : 1.0f;
-                    m = m_new;
-                    load_half(0, valid, sa);
-                    exp_half(sa, m, 0, -1);
-                    if (n_own > 0) {   // O of this set is complete up to its previous tile (pv_done was awaited by the first exp_half)
-                        tc_fence_after();
-#pragma unroll
-                        for (int ch = 0; ch < C::DPV / 16; ++ch) {
-                            uint32_t o[16];
-                            tmem_ld_32x16(my_o + ch * 16, o);
-                            tmem_wait_ld();
-#pragma unroll
-                            for (int k = 0; k < 16; ++k) o[k] = __float_as_uint(__uint_as_float(o[k]) * alpha);
-                            tmem_st_32x16(my_o + ch * 16, o);
-                        }
-                        tmem_wait_st();
-                    }
-                    load_half(1, valid - 32, sb);
-                }
-                tc_fence_before();
-                mbar_arrive(&s_free[set]);   // both halves are out of TMEM: S_{j+2} may overwrite the buffer
-                exp_half(sb, m, 4, -1);
-                // ones column of V_j (column D of the zero padding) -> the P V MMA also accumulates the softmax denominator
+                mbar_arrive(&s_free[set]);   // the tile is out of TMEM: S_{j+2} may overwrite the buffer
+                // ones column of V_j (column D of its padding) -> the P V MMA also accumulates the softmax denominator
                 if (!(GMD_ATTN_KO & 2)) {
                     const int st = j % C::VS;
                     mbar_wait(&v_full[st], (j / C::VS) & 1);
@@ -611,10 +397,9 @@ attn_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ C
             }
         } else {
             uint32_t sa[KW], sb[KW];
-            if constexpr (C::PIPE) load_s(0, sa);
             for (int j = 0; j < T; j += 2) {
-                tile(j, sa, sb);
-                if (j + 1 < T) tile(j + 1, sb, sa);
+                tile(j, sa);
+                if (j + 1 < T) tile(j + 1, sb);
             }
         }
         if constexpr (C::ALT) {
@@ -723,7 +508,7 @@ int launch(const gmd_attn_params* p, cudaStream_t st) {
     // multiplied by Q's zero padding in Q K^T and landing in never-read columns of O in P V) instead of TMA out-of-bounds fill.
     // Measured: the zero-filled 80-byte rows of the 4-D (d, head, token, batch) map paced the whole kernel (ncu / knock-out runs:
     // 808 us with the softmax removed vs 483 us without the K / V loads, B=16 N=4096 d=40).
-    const bool kv_dense = GMD_ATTN_KVDENSE && p->k_stride_h == D && p->v_stride_h == D;
+    const bool kv_dense = p->k_stride_h == D && p->v_stride_h == D;
     auto enc_dense = [&](CUtensorMap* m, const void* base, int64_t sb, int64_t sn, int n) {
         uint64_t dims[3] = {(uint64_t)D * p->H, (uint64_t)n, (uint64_t)p->B};
         uint64_t strides[3] = {2, (uint64_t)sn * 2, (uint64_t)sb * 2};
@@ -1073,7 +858,7 @@ extern "C" int gmd_attn_fwd(const gmd_attn_params* p, void* stream) {
         if (reinterpret_cast<uintptr_t>(q) & 15) { set_last_error("gmd_attn_fwd: pointers must be 16-byte aligned"); return kErrInvalid; }
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     // text cross-attention (SD1.5: 77 keys): K / V resident, persistent over query tiles
-    const bool xattn = GMD_ATTN_XATTN && p->Nk > 64 && p->Nk <= 80 && p->q_stride_h == p->d && p->v_stride_h == p->d;
+    const bool xattn = p->Nk > 64 && p->Nk <= 80 && p->q_stride_h == p->d && p->v_stride_h == p->d;
     switch (p->d) {
         case 40:
             if (xattn) return launch_x<40>(p, st);
