@@ -251,6 +251,11 @@ int gmd_softmax_rows(const void* x, void* out, int64_t M, int64_t N, float scale
 /* (a) attention: softmax(Q K^T * scale) V, tcgen05 + TMEM + TMA, streaming softmax            */
 /*     replaces F.scaled_dot_product_attention inside diffusers AttnProcessor2_0 (self- and    */
 /*     text cross-attention of the UNets called at stable_diffusion_dual_unet.py:1052,1083).   */
+/*     d in {40, 80, 160}; strides in elements, multiples of 8; pointers 16-byte aligned.      */
+/*     Dispatch (no change of results, only of kernel): heads contiguous within a token row    */
+/*     (stride_h == d) -> K / V tiles fetched through dense tensor maps; 64 < Nk <= 80 with    */
+/*     d in {40, 80} -> the persistent text cross-attention kernel; Nk <= 128 otherwise -> the */
+/*     short configuration; anything else -> the streaming kernel.                             */
 /* ------------------------------------------------------------------------------------------ */
 typedef struct gmd_attn_params {
     /* q: [B, Nq, H, d] view with element strides; k, v: [B, Nk, H, d]; o: [B, Nq, H*d] bf16 */
