@@ -391,6 +391,48 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const T* __restrict__ x,
     }
 }
 
+// fp32 token stream, C = LPR * 4 * V4 exactly (the UNet's 320 / 640 / 1280): LPR lanes per row, V4 float4 per lane, so every lane of
+// every load is busy (the generic kernel's 8-element vectors leave 24 of 32 lanes idle in the second round at C = 320) and a warp
+// at C = 320 keeps two rows in flight.  Same arithmetic order per row for any M: batch-independent.
+template <int LPR, int V4>
+__global__ void __launch_bounds__(256) layernorm_f32_exact_kernel(const float* __restrict__ x, const float* __restrict__ gamma,
+                                                                  const float* __restrict__ beta, __nv_bfloat16* __restrict__ out,
+                                                                  int64_t M, float eps) {
+    constexpr int C = LPR * 4 * V4, RPW = 32 / LPR;   // rows per warp
+    const int lane = threadIdx.x & 31, sub = lane % LPR;
+    const int64_t row = (blockIdx.x * (int64_t)(blockDim.x >> 5) + (threadIdx.x >> 5)) * RPW + lane / LPR;
+    const bool live = row < M;
+    const float4* xr = reinterpret_cast<const float4*>(x + (live ? row : 0) * C);
+    float4 v[V4];
+    float s = 0.0f;
+#pragma unroll
+    for (int i = 0; i < V4; ++i) {
+        v[i] = live ? __ldg(xr + sub + i * LPR) : make_float4(0.f, 0.f, 0.f, 0.f);
+        s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+    }
+#pragma unroll
+    for (int o = LPR / 2; o > 0; o >>= 1) s += __shfl_xor_sync(~0u, s, o);
+    const float mean = s * (1.0f / (float)C);
+    float q = 0.0f;
+#pragma unroll
+    for (int i = 0; i < V4; ++i) {
+        const float a = v[i].x - mean, b = v[i].y - mean, c = v[i].z - mean, d = v[i].w - mean;
+        q += (a * a + b * b) + (c * c + d * d);
+    }
+#pragma unroll
+    for (int o = LPR / 2; o > 0; o >>= 1) q += __shfl_xor_sync(~0u, q, o);
+    const float rstd = rsqrtf(q * (1.0f / (float)C) + eps);
+    if (!live) return;
+    uint2* orow = reinterpret_cast<uint2*>(out + row * C);
+#pragma unroll
+    for (int i = 0; i < V4; ++i) {
+        const int vi = sub + i * LPR;
+        const float4 g = __ldg(reinterpret_cast<const float4*>(gamma) + vi), b = __ldg(reinterpret_cast<const float4*>(beta) + vi);
+        orow[vi] = make_uint2(pack_bf16x2((v[i].x - mean) * rstd * g.x + b.x, (v[i].y - mean) * rstd * g.y + b.y),
+                              pack_bf16x2((v[i].z - mean) * rstd * g.z + b.z, (v[i].w - mean) * rstd * g.w + b.w));
+    }
+}
+
 // ---------------------------------------------------------------------------------------------
 // Row softmax (bf16 in/out, fp32 math): one CTA per row, three passes (the row stays in L1/L2).
 // ---------------------------------------------------------------------------------------------
@@ -560,7 +602,11 @@ extern "C" int gmd_layernorm(const void* x, const float* gamma, const float* bet
     if (in_dtype == GMD_BF16) {
         if (nvec <= 64) GMD_LN(__nv_bfloat16, 2); else if (nvec <= 160) GMD_LN(__nv_bfloat16, 5); else GMD_LN(__nv_bfloat16, 8);
     } else {
-        if (nvec <= 64) GMD_LN(float, 2); else if (nvec <= 160) GMD_LN(float, 5); else GMD_LN(float, 8);
+        const float* xf = static_cast<const float*>(x);
+        if (C == 320) layernorm_f32_exact_kernel<16, 5><<<(unsigned)((M + 15) / 16), 256, 0, st>>>(xf, gamma, beta, op, M, eps);
+        else if (C == 640) layernorm_f32_exact_kernel<32, 5><<<grid, 256, 0, st>>>(xf, gamma, beta, op, M, eps);
+        else if (C == 1280) layernorm_f32_exact_kernel<32, 10><<<grid, 256, 0, st>>>(xf, gamma, beta, op, M, eps);
+        else if (nvec <= 64) GMD_LN(float, 2); else if (nvec <= 160) GMD_LN(float, 5); else GMD_LN(float, 8);
     }
 #undef GMD_LN
     count_launch(1);

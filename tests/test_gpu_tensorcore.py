@@ -337,7 +337,7 @@ def test_groupnorm(N, HW, C0, C1):
     check(got, F.silu(F.group_norm(x32.permute(0, 2, 1), 32, ga[:C0], be[:C0], 1e-5)).permute(0, 2, 1), what="groupnorm fp32-in")
 
 
-@pytest.mark.parametrize("M,Cc", [(8192, 320), (2048, 640), (513, 1280), (7, 512)])
+@pytest.mark.parametrize("M,Cc", [(8192, 320), (2048, 640), (513, 1280), (7, 512), (1001, 320), (5, 640), (1, 320)])
 def test_layernorm(M, Cc):
     from gm_diffusion_b200 import ops
     g = torch.Generator().manual_seed(M + Cc)
