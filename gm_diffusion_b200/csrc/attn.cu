@@ -36,6 +36,9 @@ namespace {
 #ifndef GMD_XATTN_KO
 #define GMD_XATTN_KO 0
 #endif
+#ifndef GMD_ATTN_NSET80
+#define GMD_ATTN_NSET80 3   // softmax warp sets at d = 80 (1 = the single-set, two-CTAs-per-SM configuration)
+#endif
 constexpr int BQ = 128;   // query rows per CTA
 constexpr int BKV = 64;   // keys per tile (one 128-byte swizzle row of P)
 
@@ -60,25 +63,26 @@ struct Cfg {
     static constexpr int DPV = (D + 1 + 15) / 16 * 16;      // N extent of P V: head dim + the ones column
     static_assert(DPV <= NDB * 64, "ones column must fall inside the loaded V blocks");
     // K / V ring depth (measured at d = 40: 3- and 4-deep rings change nothing — the kernel is not waiting for K / V)
-    static constexpr int KS = 2, VS = KS;
+    static constexpr int KS = (D == 80 && !SHORT) ? 3 : 2, VS = KS;   // (d = 80: three tiles in flight)
     // (measured: three co-resident CTAs per SM with single-buffered S / P at d = 40 reach 354 TFLOP/s vs 378 for two CTAs
     // with double buffering, so the double-buffered configuration stays)
     // SHORT (text cross-attention, Nk <= 2 key tiles): the whole CTA lives for ~2 tiles, so what matters is how many CTAs are
     // resident to overlap their prologues (TMEM allocation, Q / K / V round trip) — single S and P buffers, one softmax set:
     // 112 TMEM columns and ~64 KB of shared memory per CTA at d = 40 instead of 224 columns and 80 KB
-    static constexpr int SB = SHORT ? 1 : 2;                // S buffers in TMEM
+    static constexpr int NSET = SHORT ? 1 : (D == 40 ? 2 : D == 80 ? GMD_ATTN_NSET80 : 1);
+    static constexpr int SB = SHORT ? 1 : (NSET > 2 ? NSET : 2);   // S buffers in TMEM (ALT: one per set)
     // NSET = 2 (d = 40): TWO independent softmax warp sets (8 warps), each with its own running maximum, its own O accumulator and
     // its own denominator (a flash-decoding style split over keys, merged once at the end): one softmax warp per sub-partition per
     // CTA was latency-bound (ncu: XU pipe 52 % busy, issue slots 39 %).
-    static constexpr int NSET = (D == 40 && !SHORT) ? 2 : 1;
-    static constexpr int KW = BKV / NSET;                   // keys per softmax thread per tile
+    static constexpr int KW = BKV;                          // keys per softmax thread per tile
     // ALT: the two sets own ALTERNATING WHOLE TILES (set s: tiles j = s mod 2, S buffer s, P buffer s, O accumulator s) rather than
     // the two key halves of every tile: per synchronisation round a thread handles 64 keys instead of 32 and the sets of a CTA run
     // out of phase.  A tile is exponentiated against the running (stale) maximum while its own maximum is formed on the side;
     // growth beyond the lazy window (rare after a set's first tile, which takes a maximum-only pass first) redoes the tile from TMEM.
-    static constexpr bool ALT = NSET == 2;
+    static constexpr bool ALT = NSET >= 2;
+    static constexpr int NB = ALT ? NSET : 2;               // p_full / pv_done / s_free barriers (tile j uses slot j % NB)
     static constexpr int THREADS = 64 + 128 * NSET;
-    static constexpr int PB = (D == 80 || SHORT) ? 1 : 2;   // P buffers in smem (one at d = 80 keeps two CTAs per SM)
+    static constexpr int PB = ALT ? NSET : ((D == 80 || SHORT) ? 1 : 2);   // P buffers in smem (ALT: one per set)
     static constexpr int Q_BYTES = NDB * BQ * 128;
     static constexpr int KV_BLOCK_BYTES = BKV * 128;        // one d block of a K or V tile
     static constexpr int K_BYTES = NDB * KV_BLOCK_BYTES;
@@ -89,8 +93,8 @@ struct Cfg {
     static constexpr int OFF_BAR = OFF_P + PB * P_BYTES;
     static constexpr int SMEM = OFF_BAR + 256 + 1024;
     static constexpr uint32_t TMEM_COLS = (SB * BKV + NSET * DPV) <= 128 ? 128 : (SB * BKV + NSET * DPV) <= 256 ? 256 : 512;
-    static_assert(NSET == 1 || P_BYTES * PB >= BQ * (DPV + 1) * 4, "merge scratch must fit in the P buffers");
-    static constexpr int MIN_CTAS = SHORT ? (D == 40 ? 3 : D == 80 ? 2 : 1) : (D <= 80 ? 2 : 1);
+    static_assert(NSET == 1 || OFF_P >= (NSET - 1) * BQ * (DPV + 1) * 4, "merge scratch must fit in the (then idle) Q / K / V buffers");
+    static constexpr int MIN_CTAS = SHORT ? (D == 40 ? 3 : D == 80 ? 2 : 1) : ((D <= 80 && TMEM_COLS <= 256) ? 2 : 1);
     static constexpr float LAZY_T = 8.0f;   // lazy-rescale window of the running maximum, in log2 units
     // Measured and not kept (numbers at B=16, N=4096, d=40 unless noted; DESIGN.md §3a has the full list): the next tile's TMEM read in
     // flight under the exponentials (serialises with the same sub-partition's MUFU stream: 993 us vs 785 without, both sets variants),
@@ -116,11 +120,12 @@ attn_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ C
     uint64_t* k_empty = k_full + C::KS; // KS
     uint64_t* v_full = k_empty + C::KS; // VS
     uint64_t* v_empty = v_full + C::VS; // VS
-    uint64_t* s_full = v_empty + C::VS; // 2
-    uint64_t* p_full = s_full + 2;      // 2
-    uint64_t* pv_done = p_full + 2;     // 2
-    uint64_t* s_free = pv_done + 2;     // 2 (ALT only: S buffer drained by its softmax set)
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(s_free + 2);
+    constexpr int NB = C::NB;
+    uint64_t* s_full = v_empty + C::VS; // NB (SB used)
+    uint64_t* p_full = s_full + NB;     // NB
+    uint64_t* pv_done = p_full + NB;    // NB
+    uint64_t* s_free = pv_done + NB;    // NB (ALT only: S buffer drained by its softmax set)
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(s_free + NB);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int q0 = blockIdx.x * BQ, head = blockIdx.y, batch = blockIdx.z;
@@ -131,7 +136,7 @@ attn_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ C
         mbar_init(q_full, 1);
         for (int s = 0; s < C::KS; ++s) { mbar_init(&k_full[s], 1); mbar_init(&k_empty[s], 1); }
         for (int s = 0; s < C::VS; ++s) { mbar_init(&v_full[s], 1); mbar_init(&v_empty[s], 1); }
-        for (int s = 0; s < 2; ++s) { mbar_init(&s_full[s], 1); mbar_init(&p_full[s], C::ALT ? 128 : 128 * C::NSET); mbar_init(&pv_done[s], 1); mbar_init(&s_free[s], 128); }
+        for (int s = 0; s < NB; ++s) { mbar_init(&s_full[s], 1); mbar_init(&p_full[s], 128); mbar_init(&pv_done[s], 1); mbar_init(&s_free[s], 128); }
         fence_barrier_init();
     }
     if (warp == 1) tmem_alloc<C::TMEM_COLS>(tmem_slot);
@@ -188,23 +193,24 @@ attn_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ C
                 umma_commit(&s_full[j % C::SB]);
             };
             mbar_wait(q_full, 0);
-            issue_s(0);
-            if (C::SB > 1 && T > 1) issue_s(1);
+            for (int i = 0; i < C::SB && i < T; ++i) issue_s(i);
             for (int j = 0; j < T; ++j) {
                 const int st = j % C::VS;
+                const int sl = j % NB;                      // barrier slot (ALT: = owning set)
+                const uint32_t sl_ph = (j / NB) & 1;
                 if constexpr (C::ALT) {
-                    // S_{j+2} reuses buffer j&1 as soon as its set has taken the logits of tile j out of TMEM, ahead of P V_j
-                    if (j + 2 < T) {
-                        if (!(GMD_ATTN_KO & 128)) mbar_wait(&s_free[j & 1], (j >> 1) & 1);
+                    // S_{j+NSET} reuses the set's buffer as soon as the set has taken the logits of tile j out of TMEM, ahead of P V_j
+                    if (j + NB < T) {
+                        if (!(GMD_ATTN_KO & 128)) mbar_wait(&s_free[sl], sl_ph);
                         tc_fence_after();
-                        issue_s(j + 2);
+                        issue_s(j + NB);
                     }
                 }
-                mbar_wait(&p_full[j & 1], (j >> 1) & 1);   // softmax_j: P_j in smem, ones column set, S[j&1] drained
+                mbar_wait(&p_full[sl], sl_ph);   // softmax_j: P_j in smem, ones column set (non-ALT: S[j&1] drained)
                 mbar_wait(&v_full[st], (j / C::VS) & 1);
                 tc_fence_after();
                 const uint32_t v_addr = smem_u32(v_smem + st * C::K_BYTES);
-                const uint32_t p_addr = smem_u32(p_smem + (C::PB == 2 ? (j & 1) : 0) * C::P_BYTES);
+                const uint32_t p_addr = smem_u32(p_smem + (j % C::PB) * C::P_BYTES);
 #pragma unroll
                 for (int ks = 0; ks < BKV / 16; ++ks) {
                     // key half ks / (KW/16) accumulates into its own O (NSET = 2), else everything into one
@@ -212,12 +218,12 @@ attn_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ C
                     uint64_t da = umma_desc_k_sw128(p_addr + ks * 32);
                     uint64_t db = umma_desc_mn_sw128(v_addr + ks * 16 * 128, C::KV_BLOCK_BYTES);
                     if constexpr (C::ALT)   // whole tile into the accumulator of the set that owns it
-                        umma_bf16_ss(tmem_o + (j & 1) * C::DPV, da, db, IDESC_O, (j >= 2 || ks != 0) ? 1u : 0u);
+                        umma_bf16_ss(tmem_o + sl * C::DPV, da, db, IDESC_O, (j >= NB || ks != 0) ? 1u : 0u);
                     else
                         umma_bf16_ss(tmem_o + (ks / KSTEPS) * C::DPV, da, db, IDESC_O, (j != 0 || (ks % KSTEPS) != 0) ? 1u : 0u);
                 }
                 umma_commit(&v_empty[st]);
-                umma_commit(&pv_done[j & 1]);
+                umma_commit(&pv_done[sl]);
                 if (!C::ALT && j + C::SB < T) issue_s(j + C::SB);   // S[j % SB] was drained by softmax_j (p_full_j)
             }
         }
@@ -264,7 +270,7 @@ attn_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ C
             }
             // P row -> smem, K-major SWIZZLE_128B: 16-byte chunk c of row r lands at chunk (c ^ (r & 7)); every chunk is stored as
             // soon as its eight probabilities exist, so at most four packed registers are live next to the in-flight S_{j+1}
-            uint8_t* prow = p_smem + (C::PB == 2 ? (j & 1) : 0) * C::P_BYTES + row * 128;
+            uint8_t* prow = p_smem + (j % C::PB) * C::P_BYTES + row * 128;
             uint32_t pk[4];
 #pragma unroll
             for (int k = 0; k < KW / 2; ++k) {
@@ -348,7 +354,7 @@ attn_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ C
                 }
                 mx_out = fmaxf(mx0, mx1);
             };
-            for (int j = set; j < T; j += 2, ++n_own) {
+            for (int j = set; j < T; j += C::NSET, ++n_own) {
                 const int valid = args.Nk - j * BKV;
                 if (!(GMD_ATTN_KO & 32)) mbar_wait(&s_full[set], n_own & 1);
                 tc_fence_after();
@@ -406,7 +412,7 @@ attn_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ C
             // every set waits for ITS last P V (the phase it has been tracking); after the named barrier both accumulators are final
             // and the P buffers (the merge scratch) are no longer read by the tensor core
             mbar_wait(&pv_done[set], (n_own - 1) & 1);
-            asm volatile("bar.sync 2, 256;" ::: "memory");
+            asm volatile("bar.sync 2, %0;" ::"n"(128 * C::NSET) : "memory");
         } else {
             mbar_wait(&pv_done[(T - 1) & 1], ((T - 1) >> 1) & 1);
         }
@@ -442,8 +448,8 @@ attn_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ C
                 }
             }
         } else {
-            // merge the two key halves: O = (O_a 2^(m_a - m) + O_b 2^(m_b - m)) / (l_a 2^(m_a - m) + l_b 2^(m_b - m)).
-            // Set 1 parks (m_b, O_b[0..DPV)) in the (now idle) P buffers, set 0 combines and writes the output row.
+            // merge the sets' partial results: O = sum_s O_s 2^(m_s - m) / sum_s l_s 2^(m_s - m), m = max_s m_s.
+            // Sets 1.. park (m_s, O_s[0..D]) in the (now idle) Q / K / V buffers, set 0 combines and writes the output row.
             float ov[C::DPV];
 #pragma unroll
             for (int ch = 0; ch < C::DPV / 16; ++ch) {
@@ -453,24 +459,41 @@ attn_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ C
 #pragma unroll
                 for (int k = 0; k < 16; ++k) ov[ch * 16 + k] = __uint_as_float(o[k]);
             }
-            float* scratch = reinterpret_cast<float*>(p_smem) + row * (C::DPV + 1);   // odd pitch: conflict-free rows
-            if (set == 1) {
-                scratch[C::DPV] = m;
+            constexpr int PITCH = C::DPV + 1;   // odd pitch: conflict-free rows
+            float* scratch = reinterpret_cast<float*>(smem);
+            if (set > 0) {
+                float* mine = scratch + ((set - 1) * BQ + row) * PITCH;
+                mine[C::DPV] = m;   // -inf for a set that owned no tile (Nk <= 64 * (NSET - 1)): its accumulator was never written
 #pragma unroll
-                for (int k = 0; k <= D; ++k) scratch[k] = ov[k];
+                for (int k = 0; k <= D; ++k) mine[k] = n_own > 0 ? ov[k] : 0.0f;
             }
-            asm volatile("bar.sync 2, 256;" ::: "memory");
+            asm volatile("bar.sync 2, %0;" ::"n"(128 * C::NSET) : "memory");
             if (set == 0) {
-                const float mb = scratch[C::DPV];
-                const float mm = fmaxf(m, mb);
-                const float wa = ex2(m - mm), wb = mb == -INFINITY ? 0.0f : ex2(mb - mm);
-                const float inv_l = 1.0f / (ov[D] * wa + scratch[D] * wb);
+                float mm = m;
+#pragma unroll
+                for (int t = 0; t < C::NSET - 1; ++t) mm = fmaxf(mm, scratch[(t * BQ + row) * PITCH + C::DPV]);
+                float w[C::NSET];
+                w[0] = ex2(m - mm);
+                float l = ov[D] * w[0];
+#pragma unroll
+                for (int t = 0; t < C::NSET - 1; ++t) {
+                    const float* other = scratch + (t * BQ + row) * PITCH;
+                    const float mo = other[C::DPV];
+                    w[t + 1] = mo == -INFINITY ? 0.0f : ex2(mo - mm);
+                    l += other[D] * w[t + 1];
+                }
+                const float inv_l = 1.0f / l;
                 if (q < args.Nq) {
 #pragma unroll
                     for (int d0 = 0; d0 < D; d0 += 8) {
                         float r[8];
 #pragma unroll
-                        for (int k = 0; k < 8; ++k) r[k] = (ov[d0 + k] * wa + scratch[d0 + k] * wb) * inv_l;
+                        for (int k = 0; k < 8; ++k) {
+                            float acc = ov[d0 + k] * w[0];
+#pragma unroll
+                            for (int t = 0; t < C::NSET - 1; ++t) acc += scratch[(t * BQ + row) * PITCH + d0 + k] * w[t + 1];
+                            r[k] = acc * inv_l;
+                        }
                         *reinterpret_cast<uint4*>(op + d0) = make_uint4(pack_bf16x2(r[0], r[1]), pack_bf16x2(r[2], r[3]), pack_bf16x2(r[4], r[5]), pack_bf16x2(r[6], r[7]));
                     }
                 }
