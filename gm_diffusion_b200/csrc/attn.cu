@@ -11,7 +11,8 @@
 //     O[:, D] = sum_k P[:, k] in fp32, rescaled together with O.
 //   * O is rescaled in TMEM lazily: only when a row maximum grew by more than 2^8 (the stale maximum keeps every exponent <= 8,
 //     well inside bf16 / fp32 range), so after the first tiles the correction path is almost never taken.
-//   * d = 40 runs two softmax warp sets on alternating whole tiles (Cfg::ALT), exponentiating against the stale maximum.
+//   * d = 40 runs two and d = 80 three softmax warp sets on alternating whole tiles (Cfg::ALT), exponentiating against the stale
+//     maximum; the sets' partial results are merged once at the end.
 //   * K / V tiles are fetched through a dense (channel, token, batch) map: no out-of-bounds fill on the 80-byte head rows (launch()).
 //   * what bounds d = 40: the TMEM read of S (128x64 fp32 per tile at 64 B/clk/SM = 512 cycles) and its 8192 ex2 (16/clk/SM = 512
 //     cycles) — two co-equal floors; the tensor pipe is 25 % busy.
