@@ -37,6 +37,11 @@ namespace {
 #ifndef GMD_XATTN_KO
 #define GMD_XATTN_KO 0
 #endif
+#ifndef GMD_ATTN_NSET40
+#define GMD_ATTN_NSET40 2   // softmax warp sets at d = 40.  2: two CTAs per SM, 721 us at B=16 N=4096.  3 / 4: one CTA per SM, 871 / 872 us —
+                            // the same for both, i.e. paced by the ONE MMA-issuing thread (~935 cycles per tile: four barrier polls, seven
+                            // MMAs, four commits); with two CTAs per SM there are two of them
+#endif
 #ifndef GMD_ATTN_NSET80
 #define GMD_ATTN_NSET80 3   // softmax warp sets at d = 80 (1 = the single-set, two-CTAs-per-SM configuration)
 #endif
@@ -64,13 +69,13 @@ struct Cfg {
     static constexpr int DPV = (D + 1 + 15) / 16 * 16;      // N extent of P V: head dim + the ones column
     static_assert(DPV <= NDB * 64, "ones column must fall inside the loaded V blocks");
     // K / V ring depth (measured at d = 40: 3- and 4-deep rings change nothing — the kernel is not waiting for K / V)
-    static constexpr int KS = (D == 80 && !SHORT) ? 3 : 2, VS = KS;   // (d = 80: three tiles in flight)
+    static constexpr int KS = SHORT ? 2 : (D == 80 ? 3 : D == 40 ? (GMD_ATTN_NSET40 > 2 ? GMD_ATTN_NSET40 : 2) : 2), VS = KS;   // (one slot per tile in flight)
     // (measured: three co-resident CTAs per SM with single-buffered S / P at d = 40 reach 354 TFLOP/s vs 378 for two CTAs
     // with double buffering, so the double-buffered configuration stays)
     // SHORT (text cross-attention, Nk <= 2 key tiles): the whole CTA lives for ~2 tiles, so what matters is how many CTAs are
     // resident to overlap their prologues (TMEM allocation, Q / K / V round trip) — single S and P buffers, one softmax set:
     // 112 TMEM columns and ~64 KB of shared memory per CTA at d = 40 instead of 224 columns and 80 KB
-    static constexpr int NSET = SHORT ? 1 : (D == 40 ? 2 : D == 80 ? GMD_ATTN_NSET80 : 1);
+    static constexpr int NSET = SHORT ? 1 : (D == 40 ? GMD_ATTN_NSET40 : D == 80 ? GMD_ATTN_NSET80 : 1);
     static constexpr int SB = SHORT ? 1 : (NSET > 2 ? NSET : 2);   // S buffers in TMEM (ALT: one per set)
     // NSET = 2 (d = 40): TWO independent softmax warp sets (8 warps), each with its own running maximum, its own O accumulator and
     // its own denominator (a flash-decoding style split over keys, merged once at the end): one softmax warp per sub-partition per
