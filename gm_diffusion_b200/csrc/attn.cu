@@ -37,6 +37,9 @@ namespace {
 #ifndef GMD_XATTN_KO
 #define GMD_XATTN_KO 0
 #endif
+#ifndef GMD_ATTN_SKIPV
+#define GMD_ATTN_SKIPV 1
+#endif
 #ifndef GMD_ATTN_NSET40
 #define GMD_ATTN_NSET40 2   // softmax warp sets at d = 40.  2: two CTAs per SM, 721 us at B=16 N=4096.  3 / 4: one CTA per SM, 871 / 872 us —
                             // the same for both, i.e. paced by the ONE MMA-issuing thread (~935 cycles per tile: four barrier polls, seven
@@ -213,7 +216,9 @@ attn_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ C
                     }
                 }
                 mbar_wait(&p_full[sl], sl_ph);   // softmax_j: P_j in smem, ones column set (non-ALT: S[j&1] drained)
-                mbar_wait(&v_full[st], (j / C::VS) & 1);
+                // (ALT: the owning set polled v_full before it wrote the ones column and arrived on p_full — no second poll here; every
+                // poll costs this thread ~90 cycles and it paces the kernel, see GMD_ATTN_NSET40)
+                if (!(C::ALT && GMD_ATTN_SKIPV)) mbar_wait(&v_full[st], (j / C::VS) & 1);
                 tc_fence_after();
                 const uint32_t v_addr = smem_u32(v_smem + st * C::K_BYTES);
                 const uint32_t p_addr = smem_u32(p_smem + (j % C::PB) * C::P_BYTES);
