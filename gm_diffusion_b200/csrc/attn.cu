@@ -71,24 +71,22 @@ struct Cfg {
     static constexpr int DP = (D + 15) / 16 * 16;           // K extent of Q K^T
     static constexpr int DPV = (D + 1 + 15) / 16 * 16;      // N extent of P V: head dim + the ones column
     static_assert(DPV <= NDB * 64, "ones column must fall inside the loaded V blocks");
-    // K / V ring depth (measured at d = 40: 3- and 4-deep rings change nothing — the kernel is not waiting for K / V)
-    static constexpr int KS = SHORT ? 2 : (D == 80 ? 3 : D == 40 ? (GMD_ATTN_NSET40 > 2 ? GMD_ATTN_NSET40 : 2) : 2), VS = KS;   // (one slot per tile in flight)
-    // (measured: three co-resident CTAs per SM with single-buffered S / P at d = 40 reach 354 TFLOP/s vs 378 for two CTAs
-    // with double buffering, so the double-buffered configuration stays)
-    // SHORT (text cross-attention, Nk <= 2 key tiles): the whole CTA lives for ~2 tiles, so what matters is how many CTAs are
-    // resident to overlap their prologues (TMEM allocation, Q / K / V round trip) — single S and P buffers, one softmax set:
-    // 112 TMEM columns and ~64 KB of shared memory per CTA at d = 40 instead of 224 columns and 80 KB
+    // SHORT (key counts of at most two tiles that the text cross-attention kernel does not take): the whole CTA lives for ~2 tiles, so
+    // what matters is how many CTAs are resident to overlap their prologues (TMEM allocation, Q / K / V round trip) — single S and P
+    // buffers, one softmax set: 112 TMEM columns and ~64 KB of shared memory per CTA at d = 40.
+    // NSET (d = 40: 2 sets, two CTAs per SM; d = 80: 3 sets, one CTA per SM): independent softmax warp sets of 4 warps, each with its
+    // own running maximum, O accumulator and denominator (a flash-decoding style split over keys, merged once at the end): one
+    // softmax warp per sub-partition per CTA was latency-bound (ncu: XU pipe 52 % busy, issue slots 39 %).
     static constexpr int NSET = SHORT ? 1 : (D == 40 ? GMD_ATTN_NSET40 : D == 80 ? GMD_ATTN_NSET80 : 1);
-    static constexpr int SB = SHORT ? 1 : (NSET > 2 ? NSET : 2);   // S buffers in TMEM (ALT: one per set)
-    // NSET = 2 (d = 40): TWO independent softmax warp sets (8 warps), each with its own running maximum, its own O accumulator and
-    // its own denominator (a flash-decoding style split over keys, merged once at the end): one softmax warp per sub-partition per
-    // CTA was latency-bound (ncu: XU pipe 52 % busy, issue slots 39 %).
-    static constexpr int KW = BKV;                          // keys per softmax thread per tile
-    // ALT: the two sets own ALTERNATING WHOLE TILES (set s: tiles j = s mod 2, S buffer s, P buffer s, O accumulator s) rather than
-    // the two key halves of every tile: per synchronisation round a thread handles 64 keys instead of 32 and the sets of a CTA run
-    // out of phase.  A tile is exponentiated against the running (stale) maximum while its own maximum is formed on the side;
-    // growth beyond the lazy window (rare after a set's first tile, which takes a maximum-only pass first) redoes the tile from TMEM.
+    // ALT: the sets own ALTERNATING WHOLE TILES (set s: tiles j = s mod NSET, S buffer s, P buffer s, O accumulator s) rather than
+    // slices of every tile's keys: per synchronisation round a thread handles 64 keys and the sets of a CTA run out of phase.
+    // A tile is exponentiated against the running (stale) maximum while its own maximum is formed on the side; growth beyond
+    // the lazy window (rare after a set's first tile, which takes a maximum-only pass first) redoes the tile from TMEM.
     static constexpr bool ALT = NSET >= 2;
+    static constexpr int SB = SHORT ? 1 : (NSET > 2 ? NSET : 2);   // S buffers in TMEM (ALT: one per set)
+    // K / V ring depth: one slot per tile in flight (measured at d = 40: deeper rings change nothing — the kernel does not wait for K / V)
+    static constexpr int KS = NSET > 2 ? NSET : 2, VS = KS;
+    static constexpr int KW = BKV;                          // keys per softmax thread per tile
     static constexpr int NB = ALT ? NSET : 2;               // p_full / pv_done / s_free barriers (tile j uses slot j % NB)
     static constexpr int THREADS = 64 + 128 * NSET;
     static constexpr int PB = ALT ? NSET : ((D == 80 || SHORT) ? 1 : 2);   // P buffers in smem (ALT: one per set)
