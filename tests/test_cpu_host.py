@@ -75,6 +75,18 @@ def test_no_oracle_import_in_product():
         txt = f.read_text()
         assert "import oracle" not in txt and "from oracle" not in txt, f"{f} imports the oracle"
     assert "gm_diffusion_b200" not in sys.modules or "oracle" not in getattr(sys.modules["gm_diffusion_b200"], "__dict__", {})
+    # measurement scripts under profiles/ do not import it either: the GPU-side comparators receive the oracle's torch modules from
+    # `bench.py --comparators` (bench.py is the one script besides tests/ and smoke() that may execute oracle/)
+    for f in (ROOT / "profiles").glob("*.py"):
+        txt = f.read_text()
+        assert "import oracle" not in txt and "from oracle" not in txt, f"{f} imports the oracle"
+
+
+def test_bench_cli_declares_the_contract_flags():
+    """bench.py keeps the driver's flags (--gpus/--steps/--warmup/--impl) next to the comparator switch."""
+    txt = (ROOT / "bench.py").read_text()
+    for flag in ("--gpus", "--steps", "--warmup", "--impl", "--comparators", "--no-cpu-baseline"):
+        assert f'"{flag}"' in txt, flag
 
 
 @pytest.mark.parametrize("steps", [4, 10, 50])
