@@ -77,6 +77,25 @@ def declared_symbols() -> list[str]:
     return sorted(set(re.findall(r"\b(gmd_[a-z0-9_]+)\s*\(", text)))
 
 
+def _header_version():
+    m = re.search(r"#define\s+GMD_VERSION\s+(\d+)", HEADER_PATH.read_text()) if HEADER_PATH.exists() else None
+    return int(m.group(1)) if m else None
+
+
+def _check_fresh() -> None:
+    """A library built from other sources than the ones in the tree (and so, possibly, with other struct layouts than the ctypes
+    mirrors below) must not be used silently: compare the build stamp with the digest of csrc/ + the header."""
+    if LIB_PATH.parent != _ROOT / "_C" or os.environ.get("GMD_SKIP_DIGEST_CHECK") == "1":
+        return   # an explicitly chosen A/B library (profiles/*: GMD_AB_LIB)
+    stamp = LIB_PATH.parent / "build.sha256"
+    from . import build as _build
+    if not (_build.CSRC.exists() and HEADER_PATH.exists()):
+        return
+    if not stamp.exists() or stamp.read_text().strip() != _build._digest():
+        raise RuntimeError(f"{LIB_PATH} is stale (csrc/ or include/gmd_b200.h changed since it was built): rebuild with "
+                           "`python -m gm_diffusion_b200.build`")
+
+
 def lib() -> C.CDLL:
     """Load the shared library (once). Raises if it has not been built — there is no CPU path."""
     global _lib
@@ -86,7 +105,12 @@ def lib() -> C.CDLL:
         raise RuntimeError(
             f"{LIB_PATH} is missing: build it with `python -m gm_diffusion_b200.build` "
             "(gm_diffusion_b200 has no CPU or PyTorch fallback)")
+    _check_fresh()
     L = C.CDLL(str(LIB_PATH), mode=os.RTLD_GLOBAL if hasattr(os, "RTLD_GLOBAL") else 0)
+    want = _header_version()
+    if want is not None and int(L.gmd_version()) != want:
+        raise RuntimeError(f"{LIB_PATH} reports gmd_version() = {int(L.gmd_version())} but include/gmd_b200.h declares {want}: "
+                           "rebuild with `python -m gm_diffusion_b200.build --force`")
     L.gmd_version.restype = C.c_int
     L.gmd_last_error.restype = C.c_char_p
     L.gmd_launch_count.restype = C.c_int64
@@ -142,9 +166,51 @@ def require_cuda(*tensors) -> None:
 
     if not torch.cuda.is_available():
         raise RuntimeError("gm_diffusion_b200 needs a CUDA device (sm_100a); there is no CPU fallback")
+    cur = torch.cuda.current_device()
     for t in tensors:
-        if t is not None and not t.is_cuda:
+        if t is None:
+            continue
+        if not t.is_cuda:
             raise RuntimeError("gm_diffusion_b200: expected CUDA tensors (no CPU fallback)")
+        if t.device.index != cur:
+            # kernels launch on the CURRENT device's current stream: a tensor elsewhere would be read through a wrong context
+            raise RuntimeError(f"gm_diffusion_b200: tensor lives on cuda:{t.device.index} but the current CUDA device is cuda:{cur}; "
+                               "run the call under `with torch.cuda.device(tensor.device):` (the pipelines, B200UNet and B200Vae do)")
+
+
+def on_own_device(method):
+    """Decorator for methods of objects with a `.device`: run under `torch.cuda.device(self.device)` so every C-ABI launch inside
+    goes to the stream and kernel attributes of THAT device (one process may hold pipelines on several GPUs)."""
+    import functools
+
+    @functools.wraps(method)
+    def wrapper(self, *a, **kw):
+        import torch
+
+        dev = torch.device(self.device)
+        if dev.type != "cuda" or dev.index is None or dev.index == torch.cuda.current_device():
+            return method(self, *a, **kw)
+        with torch.cuda.device(dev):
+            return method(self, *a, **kw)
+    return wrapper
+
+
+def on_tensor_device(fn):
+    """Decorator for free functions whose first CUDA tensor argument decides the device."""
+    import functools
+
+    @functools.wraps(fn)
+    def wrapper(*a, **kw):
+        import torch
+
+        for t in list(a) + list(kw.values()):
+            if isinstance(t, torch.Tensor) and t.is_cuda:
+                if t.device.index == torch.cuda.current_device():
+                    break
+                with torch.cuda.device(t.device):
+                    return fn(*a, **kw)
+        return fn(*a, **kw)
+    return wrapper
 
 
 def ptr(t) -> int | None:

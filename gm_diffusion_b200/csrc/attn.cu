@@ -19,6 +19,7 @@
 // Head dims 40/80/160 (SD1.5: 8 heads at every level) are zero-padded to a multiple of 16 for free by TMA on the Q side: that
 // tensor map's innermost dim is the true head dim, the box is 64 wide.
 #include "common.cuh"
+#include <type_traits>
 #include "../../include/gmd_b200.h"
 
 namespace gmd {
@@ -64,6 +65,34 @@ __device__ __forceinline__ float ex2(float x) {
     asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
     return y;
 }
+// 2^x on the FMA / ALU pipes (no MUFU): x = n + f with n = round(x), f in [-0.5, 0.5]; degree-3 polynomial for 2^f (relative error
+// 1.1e-4 — the result is rounded to bf16, 3.9e-3); the exponent is added to the bit pattern.  x <= 8 (lazy window) on this path.
+__device__ __forceinline__ float exp2_poly(float x) {
+    x = fmaxf(x, -125.0f);
+    const float xf = x + 12582912.0f;                 // 1.5 * 2^23: the low mantissa bits now hold round(x)
+    const float f = x - (xf - 12582912.0f);
+    float p = fmaf(f, 0.0555041086f, 0.2402265069f);
+    p = fmaf(p, f, 0.6931471806f);
+    p = fmaf(p, f, 1.0f);
+    return __int_as_float(__float_as_int(p) + (__float_as_int(xf) << 23));
+}
+#ifndef GMD_ATTN2_POLY
+#define GMD_ATTN2_POLY 0      // every POLY-th exponential of attn2_kernel on the FMA pipe (0 = all on MUFU)
+#endif
+constexpr int POLY = GMD_ATTN2_POLY;
+#ifdef GMD_ATTN2_TRACE
+// debug build only (profiles/trace_attn.py): clock64 timestamps of CTA (0,0,0), 8 event slots per key tile
+__device__ long long g_attn_trace[8 * 1024];
+#define TRACE(slot, j) do { if (blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && (j) < 1024) g_attn_trace[(j) * 8 + (slot)] = clock64(); } while (0)
+#else
+#define TRACE(slot, j) do { } while (0)
+#endif
+#ifndef GMD_ATTN2_SFIRST
+#define GMD_ATTN2_SFIRST 0    // 1: the MMA thread issues S_{j+SB} ahead of P V_j (A/B measurements)
+#endif
+#ifndef GMD_ATTN2_KO
+#define GMD_ATTN2_KO 0        // timing-only knock-outs of attn2_kernel (wrong results): 1 no MUFU, 2 no P stores, 4 no S loads, 8 no row sums / maxima
+#endif
 
 template <int D, bool SHORT = false>
 struct Cfg {
@@ -520,11 +549,12 @@ attn_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ C
 template <int D, bool SHORT>
 int launch(const gmd_attn_params* p, cudaStream_t st) {
     using C = Cfg<D, SHORT>;
-    static bool configured = false;
-    if (!configured) {
+    static bool configured[kMaxDevices] = {};
+    const int dev = device_ordinal();
+    if (!configured[dev]) {
         cudaError_t e = cudaFuncSetAttribute(attn_kernel<D, SHORT>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM);
         if (e != cudaSuccess) { set_last_error("attn: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return kErrCuda; }
-        configured = true;
+        configured[dev] = true;
     }
     CUtensorMap mq, mk, mv;
     auto enc = [&](CUtensorMap* m, const void* base, int64_t sb, int64_t sn, int64_t sh, int n, uint32_t rows) {
@@ -564,6 +594,369 @@ int launch(const gmd_attn_params* p, cudaStream_t st) {
     attn_kernel<D, SHORT><<<grid, C::THREADS, C::SMEM, st>>>(mq, mk, mv, a);
     count_launch(1);
     return check_launch("attn_kernel");
+}
+
+
+// ---------------------------------------------------------------------------------------------------------------------------------
+// attn2_kernel<D, BKV, SB, PB, KS>: self-attention with P KEPT IN TENSOR MEMORY (round 2).
+//
+// What the round-1 kernel was actually bound by (profiles/ubench_tmem_r02.txt, ubench_mma_issue_r02.txt, measured on B200):
+//   * reading a 128x64 fp32 S tile out of TMEM costs ~35 cycles per SM, not 512 — tcgen05.ld is NOT a floor; the only hard floor of
+//     the softmax is MUFU: 8192 ex2 per tile at 16 / clk / SM = 512 cycles, and a bare ld -> max -> fma -> ex2 -> pack loop reaches
+//     548 cycles per tile with two warps per sub-partition;
+//   * an SS-form tcgen05.mma with N <= 64 costs ~46 cycles whatever N is: it is bound by the 6 KB of A + B operand bytes it pulls
+//     through the 128 B/clk shared-memory port.  Per 64-key tile the v1 kernel moved 42 KB of MMA operands + 16 KB of P stores +
+//     16 KB of TMA writes = 74 KB = 578 cycles of shared-memory bandwidth — MORE than the MUFU floor;
+//   * each poll of an mbarrier costs the MMA-issuing thread ~86 cycles, a tcgen05.commit ~5.
+// Hence this kernel:
+//   * P = 2^(S*c - m) goes registers -> tcgen05.st -> TMEM and is the A operand of the P V MMA in its TS form: no P stores, no
+//     fence.proxy.async and no A-operand reads on the shared-memory port (26-36 KB per 64 keys instead of 74);
+//   * the softmax denominator is accumulated by the softmax threads (one FADD per element; issue slots are not the bound) instead
+//     of a ones column written into the V tile, so the softmax warps never touch shared memory or wait for V;
+//   * ONE softmax warp set per CTA and two CTAs per SM: no end-of-kernel merge of partial results, prologue / epilogue of one CTA
+//     overlap the main loop of the other, two MMA-issuing threads per SM;
+//   * p_full(j) — "P_j is in TMEM" — also means "S_j has been read": one barrier, one poll per tile for the MMA thread
+//     (k_full for the next S, p_full and v_full for P V: three polls, four commits per tile);
+//   * the running maximum is checked per 32-column chunk BEFORE the chunk is exponentiated (growth beyond the lazy window 2^8 takes a
+//     rare slow path that rescales O, the denominator and the tile's earlier P chunks in TMEM), so S can be released as soon as it
+//     has been read and is never read twice.
+//   * NQT = 2 (d = 40): one CTA owns TWO 128-row query tiles ("chains"), each with its own softmax warp set, S / P columns and O
+//     accumulator, sharing every K / V tile — four softmax warps per sub-partition with two CTAs per SM.  A softmax warp spends
+//     ~600 cycles per tile on the MUFU pipe and about as long NOT on it (barrier polls, TMEM round trips, branches: ncu source
+//     view, profiles/ncu_attn2_r02_summary.txt), so two warps per sub-partition leave the pipe ~35 % idle.  TMEM then only has room
+//     for ALIAS: P_j overwrites S_j in place (stored after the whole tile has been read and the growth check has passed) and
+//     S_{j+1} follows P V_j in the tensor pipe's issue order.
+template <int D, int BKV_, int NQT_, bool ALIAS_, int SB_, int PB_, int KS_>
+struct Cfg2 {
+    static constexpr int BKV = BKV_;                        // keys per tile
+    static constexpr int NQT = NQT_;                        // 128-row query tiles (chains) per CTA
+    static constexpr bool ALIAS = ALIAS_;                   // P_j is stored over S_j (single buffer per chain)
+    static constexpr int SB = ALIAS ? 1 : SB_, PB = ALIAS ? 1 : PB_;   // S / P buffers per chain in TMEM
+    static constexpr int KS = KS_;                          // K and V ring depth (separate rings, separate barriers)
+    static constexpr int NDB = (D + 63) / 64;               // 64-wide d blocks
+    static constexpr int DP = (D + 15) / 16 * 16;           // K extent of Q K^T
+    static constexpr int DPV = (D + 15) / 16 * 16;          // N extent of P V
+    static constexpr int PCOLS = BKV / 2;                   // TMEM columns of one bf16 P tile (two keys per 32-bit cell)
+    static constexpr int CH_COLS = ALIAS ? BKV : SB * BKV + PB * PCOLS;   // S (+ P) columns of one chain
+    static constexpr int TM_O = NQT * CH_COLS;
+    static constexpr int TMEM_USED = TM_O + NQT * DPV;
+    static constexpr uint32_t TMEM_COLS = TMEM_USED <= 128 ? 128 : TMEM_USED <= 256 ? 256 : 512;
+    static constexpr int MIN_CTAS = TMEM_COLS <= 256 ? 2 : 1;
+    static constexpr int QT_BYTES = NDB * BQ * 128;         // one query tile
+    static constexpr int Q_BYTES = NQT * QT_BYTES;
+    static constexpr int KV_BLOCK_BYTES = BKV * 128;        // one d block of a K or V tile
+    static constexpr int K_BYTES = NDB * KV_BLOCK_BYTES;
+    static constexpr int OFF_K = Q_BYTES;
+    static constexpr int OFF_V = OFF_K + KS * K_BYTES;
+    static constexpr int OFF_BAR = OFF_V + KS * K_BYTES;
+    static constexpr int SMEM = OFF_BAR + 256 + 1024;
+    static constexpr int THREADS = 64 + 128 * NQT;          // warp 0: TMA, warp 1: MMA, then 4 softmax warps per chain (one thread per query row)
+    static constexpr int NBAR = 1 + 4 * KS + NQT * (SB + 2 * PB);
+    static constexpr float LAZY_T = 8.0f;
+    static_assert(BKV % 32 == 0 && BKV <= 256, "tile");
+    static_assert(KS >= SB, "S_{j+SB} needs its K tile while V_j is still in use");
+    static_assert(SMEM * MIN_CTAS <= 227 * 1024, "shared memory");
+    static_assert(NBAR * 8 + 4 <= 256, "barrier block");
+};
+
+template <int D, int BKV, int NQT, bool ALIAS, int SB_, int PB_, int KS>
+__global__ void __launch_bounds__(Cfg2<D, BKV, NQT, ALIAS, SB_, PB_, KS>::THREADS, Cfg2<D, BKV, NQT, ALIAS, SB_, PB_, KS>::MIN_CTAS)
+attn2_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_k,
+             const __grid_constant__ CUtensorMap map_v, const AttnArgs args) {
+    using C = Cfg2<D, BKV, NQT, ALIAS, SB_, PB_, KS>;
+    constexpr int SB = C::SB, PB = C::PB;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t* q_smem = smem;
+    uint8_t* k_smem = smem + C::OFF_K;
+    uint8_t* v_smem = smem + C::OFF_V;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::OFF_BAR);
+    uint64_t* q_full = bars;             // 1
+    uint64_t* k_full = bars + 1;         // KS
+    uint64_t* k_empty = k_full + KS;     // KS
+    uint64_t* v_full = k_empty + KS;     // KS
+    uint64_t* v_empty = v_full + KS;     // KS
+    uint64_t* s_full = v_empty + KS;     // [NQT][SB]
+    uint64_t* p_full = s_full + NQT * SB;    // [NQT][PB]  (128 arrivals: P_j in TMEM, S_j read)
+    uint64_t* pv_done = p_full + NQT * PB;   // [NQT][PB]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(pv_done + NQT * PB);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int q0 = blockIdx.x * (BQ * NQT), head = blockIdx.y, batch = blockIdx.z;
+    const int T = (args.Nk + BKV - 1) / BKV;
+
+    if (threadIdx.x == 0) {
+        tma_prefetch_desc(&map_q); tma_prefetch_desc(&map_k); tma_prefetch_desc(&map_v);
+        mbar_init(q_full, 1);
+        for (int s = 0; s < KS; ++s) { mbar_init(&k_full[s], 1); mbar_init(&k_empty[s], 1); mbar_init(&v_full[s], 1); mbar_init(&v_empty[s], 1); }
+        for (int s = 0; s < NQT * SB; ++s) mbar_init(&s_full[s], 1);
+        for (int s = 0; s < NQT * PB; ++s) { mbar_init(&p_full[s], 128); mbar_init(&pv_done[s], 1); }
+        fence_barrier_init();
+    }
+    if (warp == 1) tmem_alloc<C::TMEM_COLS>(tmem_slot);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    // TMEM columns of chain t: S buffers, then (unless aliased) P buffers; O accumulators of all chains behind
+    auto tm_s = [&](int t, int sb) { return tmem_base + t * C::CH_COLS + sb * BKV; };
+    auto tm_p = [&](int t, int pb) { return ALIAS ? tmem_base + t * C::CH_COLS : tmem_base + t * C::CH_COLS + SB * BKV + pb * C::PCOLS; };
+    auto tm_o = [&](int t) { return tmem_base + C::TM_O + t * C::DPV; };
+
+    if (warp == 0) {
+        if (lane == 0) {
+            mbar_expect_tx(q_full, C::Q_BYTES);
+            for (int t = 0; t < NQT; ++t)
+                for (int b = 0; b < C::NDB; ++b) tma_load_4d(q_smem + t * C::QT_BYTES + b * BQ * 128, &map_q, q_full, b * 64, head, q0 + t * BQ, batch);
+            // (the K and the V stream have their own lane: a K slot is free again as soon as S_j has read it, long before the V slot of
+            // the same tile — one in-order stream would hold K_{j+KS} back behind V_{j+KS-1}, i.e. behind P V_{j-1})
+            for (int j = 0; j < T; ++j) {
+                const int st = j % KS;
+                mbar_wait(&k_empty[st], ((j / KS) & 1) ^ 1);
+                mbar_expect_tx(&k_full[st], C::K_BYTES);
+                for (int b = 0; b < C::NDB; ++b) tma_load_3d(k_smem + st * C::K_BYTES + b * C::KV_BLOCK_BYTES, &map_k, &k_full[st], head * D + b * 64, j * BKV, batch);
+                TRACE(0, j);
+            }
+        } else if (lane == 1) {
+            for (int j = 0; j < T; ++j) {
+                const int st = j % KS;
+                mbar_wait(&v_empty[st], ((j / KS) & 1) ^ 1);
+                mbar_expect_tx(&v_full[st], C::K_BYTES);
+                for (int b = 0; b < C::NDB; ++b) tma_load_3d(v_smem + st * C::K_BYTES + b * C::KV_BLOCK_BYTES, &map_v, &v_full[st], head * D + b * 64, j * BKV, batch);
+            }
+        }
+    } else if (warp == 1) {
+        if (elect_one()) {
+            constexpr uint32_t IDESC_S = umma_idesc_bf16(BQ, BKV, false, false);
+            constexpr uint32_t IDESC_O = umma_idesc_bf16(BQ, C::DPV, false, true);   // A = P from TMEM (K-major), B = V is MN-major
+            const uint32_t q_addr = smem_u32(q_smem);
+            // S_t(j) = Q_t K_j^T.  The K tile is polled once per j (chain 0) and released after the last chain's MMAs.
+            auto issue_s = [&](int t, int j) {
+                const int st = j % KS;
+                if (t == 0) { mbar_wait(&k_full[st], (j / KS) & 1); tc_fence_after(); TRACE(1, j); }
+                const uint32_t k_addr = smem_u32(k_smem + st * C::K_BYTES);
+#pragma unroll
+                for (int ks = 0; ks < C::DP / 16; ++ks) {
+                    const int blk = ks >> 2, within = ks & 3;
+                    const uint64_t da = umma_desc_k_sw128(q_addr + t * C::QT_BYTES + blk * (BQ * 128) + within * 32);
+                    const uint64_t db = umma_desc_k_sw128(k_addr + blk * C::KV_BLOCK_BYTES + within * 32);
+                    umma_bf16_ss(tm_s(t, j % SB), da, db, IDESC_S, ks != 0 ? 1u : 0u);
+                }
+                umma_commit(&s_full[t * SB + j % SB]);
+                if (t == NQT - 1) umma_commit(&k_empty[st]);
+                if (t == 0) TRACE(2, j);
+            };
+            mbar_wait(q_full, 0);
+            for (int i = 0; i < SB && i < T; ++i)
+                for (int t = 0; t < NQT; ++t) issue_s(t, i);
+            for (int j = 0; j < T; ++j) {
+                const int st = j % KS, pb = j % PB;
+                const uint32_t v_addr = smem_u32(v_smem + st * C::K_BYTES);
+#pragma unroll
+                for (int t = 0; t < NQT; ++t) {
+                    mbar_wait(&p_full[t * PB + pb], (j / PB) & 1);       // P_t(j) in TMEM; S_t(j) read (its buffer may be overwritten)
+                    if (t == 0) TRACE(3, j);
+                    if (GMD_ATTN2_SFIRST && !ALIAS && j + SB < T) issue_s(t, j + SB);   // the next S ahead of P V_j: it is what the softmax warps wait for
+                    if (t == 0) mbar_wait(&v_full[st], (j / KS) & 1);
+                    tc_fence_after();
+                    if (t == 0) TRACE(4, j);
+#pragma unroll
+                    for (int ks = 0; ks < BKV / 16; ++ks) {
+                        const uint64_t db = umma_desc_mn_sw128(v_addr + ks * 16 * 128, C::KV_BLOCK_BYTES);
+                        umma_bf16_ts(tm_o(t), tm_p(t, pb) + ks * 8, db, IDESC_O, (j != 0 || ks != 0) ? 1u : 0u);
+                    }
+                    umma_commit(&pv_done[t * PB + pb]);
+                    if (t == NQT - 1) umma_commit(&v_empty[st]);
+                    if (t == 0) TRACE(5, j);
+                    // the chain's next S right behind its P V (ALIAS: it overwrites P_t(j), after P V_t(j) in the pipe's issue order)
+                    if (!(GMD_ATTN2_SFIRST && !ALIAS) && j + SB < T) issue_s(t, j + SB);
+                }
+            }
+        }
+    } else {
+        const int lg = warp & 3;
+        const int t = (warp - 2) >> 2;           // chain (query tile) of this softmax warp
+        const int row = lg * 32 + lane;
+        const uint32_t lane_off = static_cast<uint32_t>(lg * 32) << 16;
+        const uint32_t my_o = tm_o(t) + lane_off;
+        const float c = args.scale_log2;
+        float m = -INFINITY;     // running (possibly stale) row maximum, scaled log2 units
+        float l = 0.0f;          // running denominator, relative to m
+        constexpr int NCH = BKV / 32;
+        // One pass over the S tile in 32-column TMEM reads.  EXP: probabilities 2^(s*c - m_use) as packed bf16 into pk[] (stored to
+        // TMEM by the caller once the growth check has passed), their fp32 sum into `lsum`; the row maximum of the raw logits is
+        // formed on the side (never on the exponentials' dependency chain).  MASK: columns >= valid are padding keys (last tile of
+        // a ragged key count only).  The exponentials are plain (non-volatile) asm behind tmem_wait_ld_regs, so ptxas interleaves the
+        // 32 independent fma -> ex2 -> add / pack chains of a chunk freely (one MUFU every ~4 issue slots in the SASS).
+        auto tile_pass = [&](auto exp_tag, auto mask_tag, uint32_t s_addr, int valid, float m_use, uint32_t* pk, float& mx_out, float& lsum) {
+            constexpr bool EXP = decltype(exp_tag)::value, MASK = decltype(mask_tag)::value;
+            float mx0 = -INFINITY, mx1 = -INFINITY, l0 = 0.0f, l1 = 0.0f, l2 = 0.0f, l3 = 0.0f;
+#pragma unroll
+            for (int ch = 0; ch < NCH; ++ch) {
+                uint32_t r[32];
+                if (GMD_ATTN2_KO & 4) {
+#pragma unroll
+                    for (int k = 0; k < 32; ++k) r[k] = __float_as_uint(m_use + k);
+                } else {
+                    tmem_ld_32x32(s_addr + ch * 32, r);
+                    tmem_wait_ld_regs(r);
+                }
+                if (MASK) {
+#pragma unroll
+                    for (int k = 0; k < 32; ++k) if (ch * 32 + k >= valid) r[k] = 0xff800000u;   // -inf
+                }
+#pragma unroll
+                for (int k = 0; k < ((GMD_ATTN2_KO & 8) ? 4 : 32); k += 4) {
+                    mx0 = fmaxf(mx0, fmaxf(__uint_as_float(r[k]), __uint_as_float(r[k + 1])));
+                    mx1 = fmaxf(mx1, fmaxf(__uint_as_float(r[k + 2]), __uint_as_float(r[k + 3])));
+                }
+                if (EXP) {
+                    float pr[32];
+#pragma unroll
+                    for (int k = 0; k < 32; ++k) {
+                        const float x = fmaf(__uint_as_float(r[k]), c, -m_use);
+                        pr[k] = (GMD_ATTN2_KO & 1) ? x : (POLY > 0 && (k % (POLY > 0 ? POLY : 1)) == POLY - 1) ? exp2_poly(x) : ex2(x);
+                    }
+#pragma unroll
+                    for (int k = 0; k < ((GMD_ATTN2_KO & 8) ? 4 : 32); k += 4) { l0 += pr[k]; l1 += pr[k + 1]; l2 += pr[k + 2]; l3 += pr[k + 3]; }
+#pragma unroll
+                    for (int k = 0; k < 16; ++k) pk[ch * 16 + k] = pack_bf16x2(pr[2 * k], pr[2 * k + 1]);
+                }
+            }
+            mx_out = fmaxf(mx0, mx1);
+            lsum = (l0 + l1) + (l2 + l3);
+        };
+        auto do_tile = [&](auto mask_tag, int j) {
+            const int sb = j % SB, pb = j % PB;
+            const uint32_t s_addr = tm_s(t, sb) + lane_off, p_addr = tm_p(t, pb) + lane_off;
+            const int valid = args.Nk - j * BKV;
+            mbar_wait(&s_full[t * SB + sb], (j / SB) & 1);
+            tc_fence_after();
+            if (warp == 2 && lane == 0) TRACE(6, j);
+            float mx, ls;
+            uint32_t pk[NCH * 16];
+            if (j == 0) {   // first tile: maximum first
+                tile_pass(std::false_type{}, mask_tag, s_addr, valid, 0.0f, pk, mx, ls);
+                m = mx * c;
+            }
+            const float m_use = m == -INFINITY ? 0.0f : m;   // no valid key yet: 2^(-inf) = 0
+            tile_pass(std::true_type{}, mask_tag, s_addr, valid, m_use, pk, mx, ls);
+            const float mt = mx * c;
+            const bool grow = mt > m + C::LAZY_T;
+            if (__any_sync(0xffffffffu, grow)) {
+                // rare: a row maximum left the lazy window.  S_j is still intact in TMEM (P_j has not been stored yet and the buffer is
+                // only released by the p_full arrival below): take the new maximum, bring O and l to the new scale and exponentiate
+                // the tile again.
+                const float m_new = grow ? mt : m;
+                const float alpha = grow ? ex2(m - m_new) : 1.0f;    // (m is finite here: j > 0 or the maximum-first pass ran)
+                m = m_new;
+                l *= alpha;
+                if (j > 0) {
+                    mbar_wait(&pv_done[t * PB + (j - 1) % PB], ((j - 1) / PB) & 1);   // O complete up to tile j-1 (P V_j waits for our p_full arrival)
+                    tc_fence_after();
+#pragma unroll
+                    for (int oc = 0; oc < C::DPV / 16; ++oc) {
+                        uint32_t o[16];
+                        tmem_ld_32x16(my_o + oc * 16, o);
+                        tmem_wait_ld();
+#pragma unroll
+                        for (int k = 0; k < 16; ++k) o[k] = __float_as_uint(__uint_as_float(o[k]) * alpha);
+                        tmem_st_32x16(my_o + oc * 16, o);
+                    }
+                    tmem_wait_st();
+                }
+                tile_pass(std::true_type{}, mask_tag, s_addr, valid, m, pk, mx, ls);
+            }
+            l += ls;
+            // The P buffer was last read by P V_{j-PB}.  ALIAS: P V_{j-1} was issued before S_j by the same thread, so s_full(j) implies
+            // it is complete; PB == SB likewise (P V_{j-PB} precedes S_j in the issue order).  Otherwise wait for it.
+            if (!ALIAS && (PB != SB || GMD_ATTN2_SFIRST) && j >= PB) { mbar_wait(&pv_done[t * PB + pb], ((j - PB) / PB) & 1); tc_fence_after(); }
+            if (!(GMD_ATTN2_KO & 2)) {
+#pragma unroll
+                for (int ch = 0; ch < NCH; ++ch) tmem_st_32x16p(p_addr + ch * 16, pk + ch * 16);
+                tmem_wait_st();
+            } else if (pk[0] == 0x12345678u && pk[17] == 0x9abcdef0u) {
+                tmem_st_32x16p(p_addr, pk);
+            }
+            tc_fence_before();
+            mbar_arrive(&p_full[t * PB + pb]);
+            if (warp == 2 && lane == 0) TRACE(7, j);
+        };
+        const bool ragged = (args.Nk % BKV) != 0;
+        for (int j = 0; j < T - 1; ++j) do_tile(std::false_type{}, j);
+        if (ragged) do_tile(std::true_type{}, T - 1); else do_tile(std::false_type{}, T - 1);
+        mbar_wait(&pv_done[t * PB + (T - 1) % PB], ((T - 1) / PB) & 1);
+        tc_fence_after();
+        const int q = q0 + t * BQ + row;
+        __nv_bfloat16* op = args.o + batch * args.o_stride_b + (int64_t)q * args.o_stride_n + head * args.o_stride_h;
+        const float inv_l = 1.0f / l;
+#pragma unroll
+        for (int oc = 0; oc < C::DPV / 16; ++oc) {
+            uint32_t o[16];
+            tmem_ld_32x16(my_o + oc * 16, o);
+            tmem_wait_ld();
+            if (q < args.Nq) {
+#pragma unroll
+                for (int h8 = 0; h8 < 2; ++h8) {
+                    const int d0 = oc * 16 + h8 * 8;
+                    if (d0 < D) {  // D is a multiple of 8
+                        uint4 v = make_uint4(pack_bf16x2(__uint_as_float(o[h8 * 8 + 0]) * inv_l, __uint_as_float(o[h8 * 8 + 1]) * inv_l),
+                                             pack_bf16x2(__uint_as_float(o[h8 * 8 + 2]) * inv_l, __uint_as_float(o[h8 * 8 + 3]) * inv_l),
+                                             pack_bf16x2(__uint_as_float(o[h8 * 8 + 4]) * inv_l, __uint_as_float(o[h8 * 8 + 5]) * inv_l),
+                                             pack_bf16x2(__uint_as_float(o[h8 * 8 + 6]) * inv_l, __uint_as_float(o[h8 * 8 + 7]) * inv_l));
+                        *reinterpret_cast<uint4*>(op + d0) = v;
+                    }
+                }
+            }
+        }
+        tc_fence_before();
+    }
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        tmem_dealloc<C::TMEM_COLS>(tmem_base);
+    }
+}
+
+int g_attn_v1 = -1;     // GMD_ATTN_V1=1 in the environment: keep the round-1 kernel for d = 40 / 80 (A/B measurements)
+int g_attn2_cfg40 = 0;  // GMD_ATTN2_CFG40: 0 = one chain per CTA with double-buffered S and P (default), 1 = two aliased chains per CTA (A/B measurements)
+
+template <int D, int BKV, int NQT, bool ALIAS, int SB, int PB, int KS>
+int launch2(const gmd_attn_params* p, cudaStream_t st) {
+    using C = Cfg2<D, BKV, NQT, ALIAS, SB, PB, KS>;
+    static bool configured[kMaxDevices] = {};
+    const int dev = device_ordinal();
+    if (!configured[dev]) {
+        cudaError_t e = cudaFuncSetAttribute(attn2_kernel<D, BKV, NQT, ALIAS, SB, PB, KS>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM);
+        if (e != cudaSuccess) { set_last_error("attn2: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return kErrCuda; }
+        configured[dev] = true;
+    }
+    CUtensorMap mq, mk, mv;
+    int rc;
+    {
+        uint64_t dims[4] = {(uint64_t)D, (uint64_t)p->H, (uint64_t)p->Nq, (uint64_t)p->B};
+        uint64_t strides[4] = {2, (uint64_t)p->q_stride_h * 2, (uint64_t)p->q_stride_n * 2, (uint64_t)p->q_stride_b * 2};
+        uint32_t box[4] = {64, 1, (uint32_t)BQ, 1};
+        if ((rc = encode_tensor_map_bf16(&mq, p->q, 4, dims, strides, box, true))) return rc;
+    }
+    auto enc_dense = [&](CUtensorMap* m, const void* base, int64_t sb, int64_t sn, int n) {
+        uint64_t dims[3] = {(uint64_t)D * p->H, (uint64_t)n, (uint64_t)p->B};
+        uint64_t strides[3] = {2, (uint64_t)sn * 2, (uint64_t)sb * 2};
+        uint32_t box[3] = {64, (uint32_t)BKV, 1};
+        return encode_tensor_map_bf16(m, base, 3, dims, strides, box, true);
+    };
+    if ((rc = enc_dense(&mk, p->k, p->k_stride_b, p->k_stride_n, p->Nk))) return rc;
+    if ((rc = enc_dense(&mv, p->v, p->v_stride_b, p->v_stride_n, p->Nk))) return rc;
+    AttnArgs a;
+    a.o = static_cast<__nv_bfloat16*>(p->o);
+    a.o_stride_b = p->o_stride_b; a.o_stride_n = p->o_stride_n; a.o_stride_h = p->o_stride_h;
+    a.Nq = p->Nq; a.Nk = p->Nk;
+    a.scale_log2 = p->scale * 1.4426950408889634f;
+    a.kv_dense = 1;
+    dim3 grid((p->Nq + BQ * NQT - 1) / (BQ * NQT), p->H, p->B);
+    attn2_kernel<D, BKV, NQT, ALIAS, SB, PB, KS><<<grid, C::THREADS, C::SMEM, st>>>(mq, mk, mv, a);
+    count_launch(1);
+    return check_launch("attn2_kernel");
 }
 
 
@@ -815,16 +1208,17 @@ xattn_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ 
 template <int D>
 int launch_x(const gmd_attn_params* p, cudaStream_t st) {
     using C = XCfg<D>;
-    static bool configured = false;
-    static int sms = 148;
-    if (!configured) {
+    static bool configured[kMaxDevices] = {};
+    static int sms_of[kMaxDevices] = {};
+    const int dev = device_ordinal();
+    if (!configured[dev]) {
         cudaError_t e = cudaFuncSetAttribute(xattn_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM);
         if (e != cudaSuccess) { set_last_error("xattn: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return kErrCuda; }
-        int dev = 0;
-        cudaGetDevice(&dev);
-        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-        configured = true;
+        cudaDeviceGetAttribute(&sms_of[dev], cudaDevAttrMultiProcessorCount, dev);
+        if (sms_of[dev] <= 0) sms_of[dev] = 148;
+        configured[dev] = true;
     }
+    const int sms = sms_of[dev];
     CUtensorMap mq, mk, mv;
     int rc;
     // Q (one tile per step of the loop) and V go through dense 3-D maps over the whole channel row: the columns past the head's d
@@ -876,6 +1270,12 @@ int launch_x(const gmd_attn_params* p, cudaStream_t st) {
 }  // namespace
 }  // namespace gmd
 
+#ifdef GMD_ATTN2_TRACE
+extern "C" int gmd_attn_trace_dump(long long* host, int n) {
+    return (int)cudaMemcpyFromSymbol(host, gmd::g_attn_trace, sizeof(long long) * n);
+}
+#endif
+
 extern "C" int gmd_attn_fwd(const gmd_attn_params* p, void* stream) {
     using namespace gmd;
     if (!p || !p->q || !p->k || !p->v || !p->o) { set_last_error("gmd_attn_fwd: null pointer"); return kErrInvalid; }
@@ -891,12 +1291,22 @@ extern "C" int gmd_attn_fwd(const gmd_attn_params* p, void* stream) {
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     // text cross-attention (SD1.5: 77 keys): K / V resident, persistent over query tiles
     const bool xattn = p->Nk > 64 && p->Nk <= 80 && p->q_stride_h == p->d && p->v_stride_h == p->d;
+    if (g_attn_v1 < 0) {
+        const char* e = getenv("GMD_ATTN_V1");
+        g_attn_v1 = (e && e[0] == '1') ? 1 : 0;
+        e = getenv("GMD_ATTN2_CFG40");
+        if (e) g_attn2_cfg40 = atoi(e);
+    }
+    // self-attention (key tiles beyond the short configurations, K / V rows dense over the heads): P-in-TMEM kernel
+    const bool v2 = !g_attn_v1 && !xattn && p->Nk > 2 * BKV && p->k_stride_h == p->d && p->v_stride_h == p->d;
     switch (p->d) {
         case 40:
             if (xattn) return launch_x<40>(p, st);
+            if (v2) return g_attn2_cfg40 == 1 ? launch2<40, 64, 2, true, 1, 1, 3>(p, st) : launch2<40, 64, 1, false, 2, 2, 3>(p, st);
             return p->Nk <= 2 * BKV ? launch<40, true>(p, st) : launch<40, false>(p, st);
         case 80:
             if (xattn) return launch_x<80>(p, st);
+            if (v2) return launch2<80, 64, 1, false, 2, 1, 2>(p, st);
             return launch<80, false>(p, st);   // (the short configuration does not add a third resident CTA at d = 80: measured slightly slower)
         case 160: return launch<160, false>(p, st);
         default: set_last_error("gmd_attn_fwd: head dim %d not instantiated (40, 80, 160)", p->d); return kErrUnsupported;

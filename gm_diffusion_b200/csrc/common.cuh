@@ -23,6 +23,15 @@ constexpr int kErrInvalid = -1;   // bad argument (shim raises ValueError)
 constexpr int kErrCuda = -2;      // CUDA runtime error (shim raises RuntimeError)
 constexpr int kErrUnsupported = -3;
 
+// Kernel attributes (cudaFuncSetAttribute) and the SM count are PER DEVICE: every cached "configured" flag is indexed by the
+// ordinal of the device that is current at the call (one process may drive several GPUs).
+constexpr int kMaxDevices = 64;
+inline int device_ordinal() {
+    int d = 0;
+    cudaGetDevice(&d);
+    return (d < 0 || d >= kMaxDevices) ? 0 : d;
+}
+
 // ----------------------------------------------------------------------------------------------
 // small utilities
 // ----------------------------------------------------------------------------------------------
@@ -79,6 +88,21 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
         if (clock64() - t0 > 4000000000LL) {  // ~2 s at 2 GHz
             printf("gmd: mbarrier watchdog block=(%d,%d,%d) thread=%d parity=%u\n", blockIdx.x, blockIdx.y,
                    blockIdx.z, threadIdx.x, parity);
+            __trap();
+        }
+    }
+}
+
+// Same with a sleep between polls: for waits that are EXPECTED to take long (a TMA producer waiting for a free ring slot, the MMA thread
+// waiting for the softmax warps).  Every failed try_wait is an instruction through the sub-partition's MIO queue — the queue MUFU,
+// tcgen05.ld/st and the softmax warps' own barrier operations use.
+__device__ __forceinline__ void mbar_wait_sleep(uint64_t* bar, uint32_t parity, uint32_t ns) {
+    if (mbar_try_wait(bar, parity)) return;
+    long long t0 = clock64();
+    while (!mbar_try_wait(bar, parity)) {
+        __nanosleep(ns);
+        if (clock64() - t0 > 4000000000LL) {
+            printf("gmd: mbarrier watchdog block=(%d,%d,%d) thread=%d parity=%u\n", blockIdx.x, blockIdx.y, blockIdx.z, threadIdx.x, parity);
             __trap();
         }
     }
@@ -159,6 +183,19 @@ __device__ __forceinline__ void umma_bf16_ss(uint32_t tmem_d, uint64_t desc_a, u
         "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
         : "memory");
 }
+// D[tmem] (+)= A[tmem] * B[smem]: the A operand (M lanes x 8 columns per K = 16 step, two bf16 per 32-bit cell, K-major) is read
+// from tensor memory — the softmax warps' tcgen05.st output feeds the second attention MMA without touching shared memory.
+__device__ __forceinline__ void umma_bf16_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t desc_b, uint32_t idesc,
+                                             uint32_t accumulate) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t"
+        "}\n" ::"r"(tmem_d),
+        "r"(tmem_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
 // Arrive on an mbarrier once all previously issued tcgen05.mma of this thread have completed.
 // (implies tcgen05.fence::before_thread_sync)
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
@@ -207,6 +244,25 @@ __device__ __forceinline__ void tmem_st_32x16(uint32_t taddr, const uint32_t (&r
         "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]),
         "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
         : "memory");
+}
+__device__ __forceinline__ void tmem_st_32x16p(uint32_t taddr, const uint32_t* r) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
+        "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};" ::"r"(taddr),
+        "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]),
+        "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
+        : "memory");
+}
+// tcgen05.wait::ld that also "produces" the loaded registers: consumers of r[] then depend on the wait itself, so they need not be
+// volatile to stay behind it and ptxas is free to software-pipeline them
+__device__ __forceinline__ void tmem_wait_ld_regs(uint32_t (&r)[32]) {
+    asm volatile("tcgen05.wait::ld.sync.aligned;"
+                 : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]), "+r"(r[8]), "+r"(r[9]),
+                   "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15]), "+r"(r[16]), "+r"(r[17]), "+r"(r[18]),
+                   "+r"(r[19]), "+r"(r[20]), "+r"(r[21]), "+r"(r[22]), "+r"(r[23]), "+r"(r[24]), "+r"(r[25]), "+r"(r[26]), "+r"(r[27]),
+                   "+r"(r[28]), "+r"(r[29]), "+r"(r[30]), "+r"(r[31])
+                 :
+                 : "memory");
 }
 __device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }

@@ -817,8 +817,12 @@ bool g_disable_halo = false;      // GMD_NO_HALO=1: 3x3 convolutions take the on
 bool g_disable_cluster = false;   // GMD_NO_CLUSTER=1 in the environment falls back to single-CTA tiles (A/B measurements)
 
 int sm_count() {
-    static int sms = 0;
-    if (!sms) {
+    static int sms_of[kMaxDevices] = {};
+    static bool env_read = false;
+    const int dev = device_ordinal();
+    int& sms = sms_of[dev];
+    if (!env_read) {
+        env_read = true;
         const char* e = getenv("GMD_NO_CLUSTER");
         g_disable_cluster = e && e[0] == '1';
         e = getenv("GMD_NO_HALO");
@@ -827,8 +831,8 @@ int sm_count() {
         g_disable_pair = e && e[0] == '1';
         e = getenv("GMD_PAIR_MIN_KB");
         if (e && atoi(e) > 0) g_pair_min_kb = atoi(e);
-        int dev = 0;
-        cudaGetDevice(&dev);
+    }
+    if (!sms) {
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
         if (sms <= 0) sms = 148;
     }
@@ -837,12 +841,13 @@ int sm_count() {
 
 template <int MT, int BN, int STAGES, int RB, int CL = 1, int HALO = 0, int PAIR = 0>
 int launch(const CUtensorMap* maps_a, const CUtensorMap& map_w, const KernelArgs& args, cudaStream_t st) {
-    static bool configured = false;
+    static bool configured[kMaxDevices] = {};
+    const int dev = device_ordinal();
     constexpr size_t smem = Plan<MT, BN, STAGES, RB, HALO, PAIR>::TOTAL;
-    if (!configured) {
+    if (!configured[dev]) {
         cudaError_t e = cudaFuncSetAttribute(gemm_kernel<MT, BN, STAGES, RB, CL, HALO, PAIR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) { set_last_error("gemm: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return kErrCuda; }
-        configured = true;
+        configured[dev] = true;
     }
     // persistent: one CTA per SM; with CL = 2 one cluster (two SMs) per pair of N tiles
     const int64_t items = (int64_t)args.tiles_mt * (PAIR ? args.tiles_n : args.tiles_n / CL) * args.gz * args.ksplit;

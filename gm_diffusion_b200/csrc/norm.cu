@@ -520,10 +520,11 @@ int gn_launch(const void* x0, int C0, const void* x1, int C1, const float* gamma
             // beyond 42 KB per CTA at the largest cluster the tensor cannot be parked in about two waves: the stats + apply pair
             // (second read from L2) streams better
             if ((size_t)px_per_cta * V * vec_bytes <= (42u << 10)) {
-                static bool attr_done[2] = {false, false};
-                if (!attr_done[sizeof(T) == 4]) {
+                static bool attr_done[kMaxDevices] = {};   // (one array per instantiation of this template)
+                const int dev = device_ordinal();
+                if (!attr_done[dev]) {
                     cudaFuncSetAttribute(gn_fused_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, 56 << 10);
-                    attr_done[sizeof(T) == 4] = true;
+                    attr_done[dev] = true;
                 }
                 cudaLaunchConfig_t cfg = {};
                 cfg.gridDim = dim3((unsigned)(cl * (nvec / V)), (unsigned)N, 1);

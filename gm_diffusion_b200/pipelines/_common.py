@@ -83,7 +83,7 @@ def as_b200_scheduler(scheduler):
     if cfg is not None and "DDPM" in name:
         return S.DDPMScheduler.from_config(cfg)
     if cfg is not None and "DPMSolverMultistep" in name:
-        get = cfg.get if isinstance(cfg, dict) else lambda k, d=None: getattr(cfg, k, d)
+        get = cfg.get if hasattr(cfg, "get") else lambda k, d=None: getattr(cfg, k, d)
         if (get("algorithm_type", "dpmsolver++") != "dpmsolver++" or get("solver_order", 2) != 2 or get("solver_type", "midpoint") != "midpoint"
                 or get("use_karras_sigmas", False) or get("final_sigmas_type", "zero") != "zero" or get("thresholding", False)):
             raise NotImplementedError("only DPM-Solver++(2M, midpoint, final sigma zero) — the from_config defaults the reference uses — is accelerated")
@@ -107,7 +107,7 @@ class PipelineBase:
         self.vae = as_b200_vae(vae, self.device)
         self.text_encoder = text_encoder
         self.tokenizer = tokenizer
-        self.scheduler = as_b200_scheduler(scheduler)
+        self.scheduler = scheduler   # (property: converts diffusers-style schedulers, also when assigned after construction)
         self.safety_checker = None  # accepted at the signature level, never run
         self.feature_extractor = feature_extractor
         self.image_encoder = image_encoder
@@ -122,6 +122,17 @@ class PipelineBase:
         self.skip_identical_cfg = True  # drop the uncond forward when negative_prompt_embeds == prompt_embeds (bit-exact)
         self._graphs: Dict[Any, Any] = {}
         self.graph_launches = 0  # kernels executed through CUDA-graph replays (the C-ABI counter only sees eager launches)
+
+    # The reference scripts swap the scheduler AFTER construction (`pipeline.scheduler = DPMSolverMultistepScheduler.from_config(
+    # pipeline.scheduler.config)`: formal_improved.py:195, rebuttal_r2q2.py:195, formal_improved_ablation.py:195, rebuttal_visual.py:270):
+    # every assignment goes through the same conversion as the constructor argument.
+    @property
+    def scheduler(self):
+        return self._scheduler
+
+    @scheduler.setter
+    def scheduler(self, value):
+        self._scheduler = as_b200_scheduler(value)
 
     # properties, dual_unet.py:751-780
     @property

@@ -83,6 +83,7 @@ class StableDiffusionDualUNetPipeline(PipelineBase):
 
     # ------------------------------------------------------------------------------------------------------------
     @torch.no_grad()
+    @L.on_own_device
     def __call__(
         self,
         prompt: Union[str, List[str]] = None,

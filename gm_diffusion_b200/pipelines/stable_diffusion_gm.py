@@ -25,6 +25,7 @@ class StableDiffusionGMPipeline(PipelineBase):
         self._ws: Dict[Any, dict] = {}
 
     @torch.no_grad()
+    @L.on_own_device
     def __call__(
         self,
         sdr_latent: torch.Tensor,

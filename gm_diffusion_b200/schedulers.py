@@ -12,7 +12,6 @@ from __future__ import annotations
 import copy
 import ctypes as C
 from dataclasses import dataclass, field
-from types import SimpleNamespace
 from typing import List, Optional
 
 import numpy as np
@@ -21,12 +20,42 @@ import torch
 from . import _lib as L
 
 
+class SchedulerConfig(dict):
+    """Scheduler configuration that reads like diffusers' FrozenDict: attribute access (`config.steps_offset`), mapping access
+    (`config["steps_offset"]`, `.get`, `dict(config)`) and `vars()`-free copying — so the reference scripts' post-construction swap
+    `DPMSolverMultistepScheduler.from_config(pipeline.scheduler.config)` (formal_improved.py:195, rebuttal_r2q2.py:195) works with
+    our classes and with the real diffusers ones."""
+
+    def __getattr__(self, k):
+        try:
+            return self[k]
+        except KeyError:
+            raise AttributeError(k) from None
+
+    def __setattr__(self, k, v):
+        self[k] = v
+
+
+_SD15_DEFAULTS = dict(num_train_timesteps=1000, beta_start=0.00085, beta_end=0.012, beta_schedule="scaled_linear",
+                      skip_prk_steps=True, set_alpha_to_one=False, steps_offset=1, prediction_type="epsilon",
+                      clip_sample=False, timestep_spacing="leading",
+                      # keys the fused step kernel does not implement: accepted only at the value the SD1.5 scheduler_config.json has
+                      trained_betas=None, variance_type="fixed_small", thresholding=False, rescale_betas_zero_snr=False)
+
+
 def _sd15_config(**over):
-    cfg = dict(num_train_timesteps=1000, beta_start=0.00085, beta_end=0.012, beta_schedule="scaled_linear",
-               skip_prk_steps=True, set_alpha_to_one=False, steps_offset=1, prediction_type="epsilon",
-               clip_sample=False, timestep_spacing="leading")
+    cfg = dict(_SD15_DEFAULTS)
     cfg.update(over)
-    return SimpleNamespace(**cfg)
+    return SchedulerConfig(cfg)
+
+
+def _config_items(config) -> dict:
+    """dict view of a diffusers FrozenDict / dict / namespace-like scheduler config."""
+    if isinstance(config, dict):
+        return dict(config)
+    if hasattr(config, "items"):
+        return dict(config.items())
+    return dict(vars(config))
 
 
 @dataclass
@@ -48,6 +77,8 @@ class StepPlan:
 class _SchedulerBase:
     order = 1
     init_noise_sigma = 1.0
+    _uses_clip_sample = False      # DDIM / DDPM clamp the x0 prediction when clip_sample is set; PNDM / DPM-Solver have no such key
+    _uses_variance_type = False    # DDPM only
 
     def __init__(self, **over):
         self.config = _sd15_config(**over)
@@ -60,6 +91,22 @@ class _SchedulerBase:
             raise NotImplementedError(f"beta_schedule {c.beta_schedule}")
         if c.prediction_type != "epsilon":
             raise NotImplementedError("only epsilon prediction is on the reference path (SD1.5 scheduler config)")
+        # Options the fused step kernel does not implement must not be dropped silently: a diffusers DDIMScheduler() / DDPMScheduler()
+        # built with LIBRARY defaults has clip_sample=True and would produce different latents from the reference after conversion.
+        # (The SD1.5 scheduler_config.json the reference loads — generate_hdr.py:162-176 — sets every one of these as accepted here.)
+        if c.clip_sample and self._uses_clip_sample:
+            raise NotImplementedError("clip_sample=True is not implemented by the fused scheduler kernel (the SD1.5 scheduler config sets "
+                                      "clip_sample=false); pass clip_sample=False")
+        if c.timestep_spacing != "leading":
+            raise NotImplementedError(f"timestep_spacing={c.timestep_spacing!r}: only the SD1.5 config's 'leading' spacing is on the reference path")
+        if c.trained_betas is not None:
+            raise NotImplementedError("trained_betas is not supported (the reference uses the scaled_linear schedule)")
+        if c.thresholding:
+            raise NotImplementedError("dynamic thresholding is not implemented by the fused scheduler kernel")
+        if c.rescale_betas_zero_snr:
+            raise NotImplementedError("rescale_betas_zero_snr is not implemented")
+        if self._uses_variance_type and c.variance_type != "fixed_small":
+            raise NotImplementedError(f"variance_type={c.variance_type!r}: the fused DDPM step implements 'fixed_small' (the SD1.5 config)")
         self.betas = betas
         self.alphas_cumprod = torch.cumprod(1.0 - betas, dim=0)
         self.final_alpha_cumprod = torch.tensor(1.0) if c.set_alpha_to_one else self.alphas_cumprod[0]
@@ -68,10 +115,9 @@ class _SchedulerBase:
 
     @classmethod
     def from_config(cls, config, **over):
-        d = dict(vars(config)) if not isinstance(config, dict) else dict(config)
+        d = _config_items(config)
         d.update(over)
-        known = vars(_sd15_config())
-        return cls(**{k: v for k, v in d.items() if k in known})
+        return cls(**{k: v for k, v in d.items() if k in _SD15_DEFAULTS})
 
     def scale_model_input(self, sample, timestep=None):
         return sample  # identity for PNDM / DDIM / DDPM (dual_unet.py:1047-1048)
@@ -143,6 +189,8 @@ class PNDMScheduler(_SchedulerBase):
 
 
 class DDIMScheduler(_SchedulerBase):
+    _uses_clip_sample = True
+
     def set_timesteps(self, num_inference_steps: int, device=None):
         self.num_inference_steps = int(num_inference_steps)
         ratio = self.config.num_train_timesteps // self.num_inference_steps
@@ -167,6 +215,8 @@ class DDPMScheduler(_SchedulerBase):
     """diffusers DDPMScheduler (epsilon prediction, fixed_small variance, leading spacing) — the scheduler every reference CLI
     actually passes (scripts/inference/generate_hdr.py:162-176; formal_baseline.py:175-191).  Ancestral noise is drawn by the
     pipeline from the caller's generator in the reference's order (SDR branch first, then GM branch, each step)."""
+    _uses_clip_sample = True
+    _uses_variance_type = True
 
     def set_timesteps(self, num_inference_steps: int, device=None):
         self.num_inference_steps = int(num_inference_steps)

@@ -23,6 +23,7 @@ def _prep(t: torch.Tensor) -> Tuple[torch.Tensor, int]:
     return t.to(torch.float32).contiguous(), L.F32
 
 
+@L.on_tensor_device
 def _run(sdr, gm, *, flags, tmo, qmax, eps, mu, want_hdr, want_tmo, want_minmax, layout=None, want_rgbe=False, want_u8=False,
          rgbe_div=1.0):
     """Returns (hdr, tmo, minmax) and, when byte outputs are requested, (hdr, tmo, minmax, rgbe, sdr_u8, gm_u8)."""

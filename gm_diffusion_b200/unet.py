@@ -14,6 +14,7 @@ from typing import Dict, List, Optional, Tuple
 
 import torch
 
+from . import _lib as L
 from . import ops
 
 bf16 = torch.bfloat16
@@ -191,6 +192,7 @@ class B200UNet:
         return cls({k: v for k, v in module.state_dict().items()}, device=device, **kw)
 
     # ---- step-invariant work, hoisted out of the loop --------------------------------------------------------
+    @L.on_own_device
     def timestep_table(self, timesteps) -> torch.Tensor:
         """Rows of SiLU(temb) projected through every resnet's time_emb_proj, for ALL timesteps at once:
         fp32 [len(timesteps), sum(Cout)].  (diffusers: get_timestep_embedding -> TimestepEmbedding ->
@@ -211,6 +213,7 @@ class B200UNet:
         cache[key] = table
         return table
 
+    @L.on_own_device
     def project_context(self, encoder_hidden_states: torch.Tensor) -> List[torch.Tensor]:
         """Cross-attention K/V of every transformer layer for `encoder_hidden_states` [B,77,768]; identical at
         every denoising step, so computed once per call instead of 51x."""
@@ -219,6 +222,7 @@ class B200UNet:
         return [t.project_context(ctx) for t in self.transformers]
 
     # ---- the forward pass ------------------------------------------------------------------------------------
+    @L.on_own_device
     def forward(self, sample: torch.Tensor, temb_row: torch.Tensor, context_kv: List[torch.Tensor],
                 out: Optional[torch.Tensor] = None, cfg_shared: bool = False) -> torch.Tensor:
         """sample: bf16 [B,h,w,8] (channel-padded NHWC, written by kernel (c)); temb_row: fp32 [1 or B, sum(Cout)]
@@ -266,6 +270,7 @@ class B200UNet:
 
     # ---- convenience: the diffusers call convention (used by tests and by eager callers) -----------------------
     @torch.no_grad()
+    @L.on_own_device
     def forward_nchw(self, sample_nchw: torch.Tensor, timestep, encoder_hidden_states: torch.Tensor) -> torch.Tensor:
         """`unet(sample, t, encoder_hidden_states=...)[0]` convention: NCHW in, NCHW fp32 eps out."""
         B, c, h, w = sample_nchw.shape

@@ -105,6 +105,7 @@ class B200VaeDecoder:
         return self.mid_attn(x, self._gn_ws)
 
 
+    @L.on_own_device
     def decode_px(self, latents_px: torch.Tensor, B: int, h: int, w: int) -> torch.Tensor:
         """latents_px: fp32 pixel-major [B*h*w, 4] SCALED latents (the division by scaling_factor is folded into
         post_quant_conv).  Returns the decoder image, bf16 NHWC [B, 8h, 8w, 3], range ~[-1,1]."""
@@ -126,6 +127,7 @@ class B200VaeDecoder:
         return ops.conv2d(x, self.w_out, self.w_out.shape[0], bias=self.b_out)
 
     @torch.no_grad()
+    @L.on_own_device
     def decode(self, z_nchw: torch.Tensor) -> torch.Tensor:
         """diffusers convention: `vae.decode(latents / scaling_factor)` -> image NCHW (model dtype bf16 here).
         `z_nchw` is the UNSCALED latent, exactly what the reference passes at generate_hdr.py:226,231."""
@@ -219,6 +221,7 @@ class B200Vae(B200VaeDecoder):
         b = wq @ sd[e + "conv_out.bias"].to(dev, torch.float32) + sd["quant_conv.bias"].to(dev, torch.float32)
         self.e_w_out, self.e_b_out = ops.pack_conv_weight_tiled(w), _f32(b, dev)
 
+    @L.on_own_device
     def moments(self, image: torch.Tensor) -> torch.Tensor:
         """image: [B,3,H,W] in [-1,1] (any float dtype) -> fp32 moments NHWC [B, H/8, W/8, 8]."""
         B, c, H, W = image.shape
@@ -241,6 +244,7 @@ class B200Vae(B200VaeDecoder):
         return ops.conv2d(x, self.e_w_out, 8, bias=self.e_b_out, out_f32=True)
 
     @torch.no_grad()
+    @L.on_own_device
     def encode(self, image: torch.Tensor, return_dict: bool = True):
         out = EncoderOutput(LatentDistribution(self.moments(image)))
         return out if return_dict else (out.latent_dist,)

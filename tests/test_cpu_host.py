@@ -37,7 +37,8 @@ def test_struct_layouts_match_header(lib):
     #include "gmd_b200.h"
     int main(void){ printf("%zu %zu %zu %zu %zu\n", sizeof(gmd_hdr_params), sizeof(gmd_sched_params), sizeof(gmd_gemm_params),
                             sizeof(gmd_conv_params), sizeof(gmd_attn_params)); return 0; }'''
-    tmp = ROOT / "gm_diffusion_b200" / "_C"
+    import tempfile
+    tmp = Path(tempfile.mkdtemp(prefix="gmd_sizes_"))
     (tmp / "sizes.c").write_text(src)
     subprocess.run(["gcc", "-I", str(ROOT / "include"), str(tmp / "sizes.c"), "-o", str(tmp / "sizes")], check=True)
     out = subprocess.run([str(tmp / "sizes")], check=True, capture_output=True, text=True).stdout.split()
@@ -233,3 +234,80 @@ print("ok", rank)
                         "--master-port", "29533", str(script)], capture_output=True, text=True, env=env, timeout=240)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
     assert r.stdout.count("ok") == 2
+
+
+# ---- scheduler configuration: nothing the fused step kernel does not implement may be dropped silently --------------------
+def test_scheduler_config_is_enforced_not_dropped():
+    from types import SimpleNamespace
+    from gm_diffusion_b200 import schedulers as S
+    from gm_diffusion_b200.pipelines._common import as_b200_scheduler
+    sd15 = dict(num_train_timesteps=1000, beta_start=0.00085, beta_end=0.012, beta_schedule="scaled_linear", steps_offset=1,
+                set_alpha_to_one=False, skip_prk_steps=True, clip_sample=False, prediction_type="epsilon", timestep_spacing="leading")
+
+    class DDIMScheduler:      # stands for a diffusers scheduler object: class name + .config
+        def __init__(self, **kw):
+            self.config = dict(sd15, **kw)
+
+    class DDPMScheduler(DDIMScheduler):
+        pass
+
+    assert isinstance(as_b200_scheduler(DDIMScheduler()), S.DDIMScheduler)          # the SD1.5 scheduler_config.json: accepted
+    assert isinstance(as_b200_scheduler(DDPMScheduler(variance_type="fixed_small")), S.DDPMScheduler)
+    # diffusers LIBRARY defaults of DDIMScheduler() / DDPMScheduler(): clip_sample=True -> must refuse, not silently differ
+    for cls in (DDIMScheduler, DDPMScheduler):
+        with pytest.raises(NotImplementedError, match="clip_sample"):
+            as_b200_scheduler(cls(clip_sample=True))
+    with pytest.raises(NotImplementedError, match="timestep_spacing"):
+        S.PNDMScheduler(timestep_spacing="trailing")
+    with pytest.raises(NotImplementedError, match="variance_type"):
+        S.DDPMScheduler(variance_type="learned_range")
+    with pytest.raises(NotImplementedError, match="thresholding"):
+        S.DDIMScheduler(thresholding=True)
+    with pytest.raises(NotImplementedError, match="trained_betas"):
+        S.DDPMScheduler(trained_betas=[0.1, 0.2])
+    with pytest.raises(NotImplementedError, match="rescale_betas_zero_snr"):
+        S.DDIMScheduler(rescale_betas_zero_snr=True)
+    S.PNDMScheduler(clip_sample=True)     # PNDM has no clip_sample behaviour: the key is inert there, as in diffusers
+    # namespace-style configs still convert
+    assert isinstance(S.DDIMScheduler.from_config(SimpleNamespace(**sd15)), S.DDIMScheduler)
+
+
+def test_scheduler_swap_after_construction_like_the_reference_scripts():
+    """`pipeline.scheduler = DPMSolverMultistepScheduler.from_config(pipeline.scheduler.config)` (formal_improved.py:195,
+    rebuttal_r2q2.py:195, rebuttal_visual.py:270) must keep working: config is a mapping AND has attributes, and every assignment
+    to `.scheduler` is converted."""
+    import copy
+    from gm_diffusion_b200 import schedulers as S
+    from gm_diffusion_b200.pipelines._common import PipelineBase
+    pipe = PipelineBase.__new__(PipelineBase)      # (the constructor needs a CUDA device; the property does not)
+    pipe.scheduler = S.PNDMScheduler()
+    cfg = pipe.scheduler.config
+    assert cfg["steps_offset"] == cfg.steps_offset == cfg.get("steps_offset") == 1 and dict(cfg)["beta_schedule"] == "scaled_linear"
+    assert copy.deepcopy(cfg) == cfg
+    pipe.scheduler = S.DPMSolverMultistepScheduler.from_config(pipe.scheduler.config)      # our class
+    assert isinstance(pipe.scheduler, S.DPMSolverMultistepScheduler)
+
+    class DPMSolverMultistepScheduler:               # a diffusers-style object assigned after construction
+        def __init__(self, config):
+            self.config = dict(config, algorithm_type="dpmsolver++", solver_order=2, solver_type="midpoint", final_sigmas_type="zero")
+
+        @classmethod
+        def from_config(cls, config):
+            assert hasattr(config, "items")           # what diffusers' ConfigMixin.from_config needs from a FrozenDict
+            return cls(dict(config.items()))
+
+    pipe.scheduler = DPMSolverMultistepScheduler.from_config(pipe.scheduler.config)
+    assert isinstance(pipe.scheduler, S.DPMSolverMultistepScheduler) and hasattr(pipe.scheduler, "plan_step")
+    pipe.scheduler.set_timesteps(10)
+    assert len(pipe.scheduler.timesteps) == 10
+
+
+def test_stale_library_is_refused(lib, monkeypatch):
+    """A libgmd_b200.so built from other sources than the tree's (other struct layouts, possibly) must not load silently."""
+    from gm_diffusion_b200 import build
+    lib._check_fresh()                                   # the fixture just built it
+    monkeypatch.setattr(build, "_digest", lambda: "0" * 64)
+    with pytest.raises(RuntimeError, match="stale"):
+        lib._check_fresh()
+    monkeypatch.setenv("GMD_SKIP_DIGEST_CHECK", "1")
+    lib._check_fresh()
