@@ -115,6 +115,8 @@ def lib() -> C.CDLL:
     L.gmd_last_error.restype = C.c_char_p
     L.gmd_launch_count.restype = C.c_int64
     L.gmd_reset_launch_count.restype = None
+    L.gmd_add_launch_count.restype = None
+    L.gmd_add_launch_count.argtypes = [C.c_int64]
     L.gmd_decode_ordered.restype = C.c_float
     L.gmd_decode_ordered.argtypes = [C.c_int32]
     L.gmd_hdr_reconstruct.argtypes = [C.POINTER(HdrParams), _vp]

@@ -81,3 +81,4 @@ extern "C" int gmd_version(void) { return GMD_VERSION; }
 extern "C" const char* gmd_last_error(void) { return gmd::g_err; }
 extern "C" int64_t gmd_launch_count(void) { return gmd::g_launches.load(); }
 extern "C" void gmd_reset_launch_count(void) { gmd::g_launches.store(0); }
+extern "C" void gmd_add_launch_count(int64_t n) { gmd::g_launches.fetch_add(n); }

@@ -72,6 +72,8 @@ class StableDiffusionDualUNetPipeline(PipelineBase):
         self.gm_scheduler = None
         self._ws: Dict[Any, _Workspace] = {}
         self._pair_ws: Dict[Any, Dict[str, Any]] = {}
+        self._loop_graphs: Dict[Any, Any] = {}
+        self.use_loop_graph = True   # capture the whole denoising loop as one CUDA graph when nothing needs the host between steps
         self.cfg_pair = None   # gm_diffusion_b200.dist.CfgPair: split the CFG halves / the GM images over two ranks (latency mode)
 
     def enable_cfg_pair(self, group=None):
@@ -176,11 +178,28 @@ class StableDiffusionDualUNetPipeline(PipelineBase):
         ts = [int(t) for t in timesteps]
         table_sdr = self.unet.timestep_table(ts)
         table_gm = self.gm_unet.timestep_table(ts)
+        extra = self.prepare_extra_step_kwargs(generator, eta)
+        # The WHOLE loop as one CUDA graph: every scheduler coefficient, time-embedding row and history-ring
+        # slot of every step is a function of (scheduler, timesteps, guidance) only, so the 51 x (row select, UNet forward, fused
+        # step) x 2 sequence is captured once per such key and a call is ONE graph launch.  Eager stepping (with one graph per UNet
+        # forward) remains for everything that needs the host between steps: callbacks (the reference's cooperative cancel can only
+        # be requested from one), per-step ancestral noise drawn from the caller's generator (DDPM, DDIM eta > 0), the CFG-pair
+        # exchange, and use_cuda_graph / use_loop_graph = False.
+        stochastic = isinstance(self.scheduler, S.DDPMScheduler) or (isinstance(self.scheduler, S.DDIMScheduler) and extra["eta"] > 0)
+        loop_graph_ok = (self.use_cuda_graph and self.use_loop_graph and pair is None and callback is None and callback_on_step_end is None
+                         and not stochastic)
+        loop_key = (B, h, w, do_cfg, type(self.scheduler).__name__, tuple(ts), float(guidance_scale), float(guidance_rescale if do_cfg else 0.0),
+                    table_sdr.data_ptr(), table_gm.data_ptr())
         if pair is None:
             ws.set_context("kv_sdr", self.unet.project_context(sdr_ctx))
             ws.set_context("kv_gm", self.gm_unet.project_context(gm_ctx))
-            run_sdr = self._unet_runner(("sdr", B, h, w, do_cfg), self.unet, ws.unet_in, ws.temb_sdr, ws.kv_sdr, ws.eps_sdr, cfg_shared=do_cfg)
-            run_gm = self._unet_runner(("gm", B, h, w), self.gm_unet, ws.gm_in, ws.temb_gm, ws.kv_gm, ws.eps_gm)
+            if loop_graph_ok:
+                # (torch refuses to replay a graph inside a capture, so the loop graph holds the UNet kernels themselves)
+                run_sdr = lambda: self.unet.forward(ws.unet_in, ws.temb_sdr, ws.kv_sdr, out=ws.eps_sdr, cfg_shared=do_cfg)
+                run_gm = lambda: self.gm_unet.forward(ws.gm_in, ws.temb_gm, ws.kv_gm, out=ws.eps_gm)
+            else:
+                run_sdr = self._unet_runner(("sdr", B, h, w, do_cfg), self.unet, ws.unet_in, ws.temb_sdr, ws.kv_sdr, ws.eps_sdr, cfg_shared=do_cfg)
+                run_gm = self._unet_runner(("gm", B, h, w), self.gm_unet, ws.gm_in, ws.temb_gm, ws.kv_gm, ws.eps_gm)
             gm_lo, gm_hi = 0, B
         else:
             # CFG-pair mode: this rank's CFG half of the SDR UNet on all B images, and its half of the images for the GM UNet;
@@ -199,13 +218,12 @@ class StableDiffusionDualUNetPipeline(PipelineBase):
                         a_.copy_(b_)
             run_sdr = self._unet_runner(("sdr-pair", B, h, w, pair.rank), self.unet, ws.unet_in, ws.temb_sdr, pw["kv_sdr"], pw["eps_half"])
             run_gm = self._unet_runner(("gm-pair", B, h, w, pair.rank), self.gm_unet, ws.gm_in[gm_lo:gm_hi], ws.temb_gm, pw["kv_gm"], pw["eps_gm_part"])
-        extra = self.prepare_extra_step_kwargs(generator, eta)
         eps_u = ws.eps_sdr[:B].reshape(-1, 4) if do_cfg else None
         eps_c = (ws.eps_sdr[B:] if do_cfg else ws.eps_sdr).reshape(-1, 4)
         eps_g = ws.eps_gm.reshape(-1, 4)
 
         # 7. denoising loop (:1040-1113)
-        with self.progress_bar(total=num_inference_steps) as progress_bar:
+        def denoise_loop(progress_bar):
             for i, t in enumerate(ts):
                 if self.interrupt:
                     continue
@@ -234,6 +252,27 @@ class StableDiffusionDualUNetPipeline(PipelineBase):
                 progress_bar.update()
                 if callback is not None and callback_steps and i % callback_steps == 0:
                     callback(i, t, self._latents_nchw(ws.sdr.x, B, h, w))
+
+        with self.progress_bar(total=num_inference_steps) as progress_bar:
+            if not loop_graph_ok:
+                denoise_loop(progress_bar)
+            else:
+                ent = self._loop_graphs.get(loop_key)
+                if ent is None:
+                    ws.temb_sdr.copy_(table_sdr[0:1]); ws.temb_gm.copy_(table_gm[0:1])
+                    run_sdr(); run_gm()                # eager warm-up: lazily allocated scratch exists before the capture; eps buffers are rewritten
+                    torch.cuda.synchronize()
+                    n0 = L.launch_count()
+                    lg = torch.cuda.CUDAGraph()
+                    with torch.cuda.graph(lg):
+                        denoise_loop(progress_bar)
+                    n_kernels = L.launch_count() - n0      # launches recorded by the capture pass = kernels per replay
+                    L.lib().gmd_add_launch_count(-n_kernels)   # (they did not run)
+                    if len(self._loop_graphs) >= 4:
+                        self._loop_graphs.clear()
+                    self._loop_graphs[loop_key] = ent = (lg, n_kernels, (table_sdr, table_gm))  # (the tables must outlive their cache entry)
+                ent[0].replay()
+                self.graph_launches += ent[1]
 
         sdr_lat = self._latents_nchw(ws.sdr.x, B, h, w)
         gm_lat = self._latents_nchw(ws.gm.x, B, h, w)

@@ -28,13 +28,15 @@
 extern "C" {
 #endif
 
-#define GMD_VERSION 100
+#define GMD_VERSION 200
 
 int gmd_version(void);
 const char* gmd_last_error(void);
 /* number of kernels launched by this library in this process since load / last reset */
 int64_t gmd_launch_count(void);
 void gmd_reset_launch_count(void);
+/* adjust the counter: launches recorded while a CUDA graph was being captured did not run (n < 0); replays of that graph do (n > 0) */
+void gmd_add_launch_count(int64_t n);
 
 /* ------------------------------------------------------------------------------------------ */
 /* (d) Eq.(1) HDR reconstruction + TMO + gamut + min/max                                       */

@@ -85,6 +85,30 @@ def test_dual_pipeline_config0(models, dual_pipe, graph):
     assert np.array_equal(rgbe.cpu().numpy(), RO.save_hdr_pixels(hdr_got.cpu().numpy(), 99))
 
 
+def test_whole_loop_graph_is_bit_identical_to_eager_stepping(dual_pipe):
+    """The denoising loop captured as ONE CUDA graph (all steps, both UNets as child graphs, the fused scheduler kernel with its
+    per-step coefficients baked in) must reproduce eager stepping bit for bit — on the capture call, on replays with new inputs,
+    and with another schedule / guidance scale (a different graph)."""
+    pe, ne, lat, _ = _inputs()
+    lat2 = torch.randn(lat.shape, generator=torch.Generator().manual_seed(77))
+    kw = dict(prompt_embeds=pe, negative_prompt_embeds=ne, height=256, width=256, output_type="latent")
+    dual_pipe.use_cuda_graph = True
+    dual_pipe._loop_graphs.clear()
+    for steps, g in ((4, 7.5), (6, 3.0)):
+        dual_pipe.use_loop_graph = False
+        want = [dual_pipe(latents=x.clone(), num_inference_steps=steps, guidance_scale=g, **kw) for x in (lat, lat2)]
+        dual_pipe.use_loop_graph = True
+        n_graphs = len(dual_pipe._loop_graphs)
+        got = [dual_pipe(latents=x.clone(), num_inference_steps=steps, guidance_scale=g, **kw) for x in (lat, lat2, lat)]
+        assert len(dual_pipe._loop_graphs) == n_graphs + 1, "one loop graph per (schedule, guidance) key"
+        for (gs, gg), (ws_, wg) in zip(got, want + want[:1]):
+            assert torch.equal(gs, ws_) and torch.equal(gg, wg), "loop graph differs from eager stepping"
+    # a callback needs the host between steps: the pipeline must fall back to eager stepping and still call it
+    seen = []
+    dual_pipe(latents=lat.clone(), num_inference_steps=4, guidance_scale=7.5, callback=lambda i, t, x: seen.append((i, t)), callback_steps=1, **kw)
+    assert [t for _, t in seen] == [751, 501, 501, 251, 1]
+
+
 def test_teacher_forced_step_eps(models):
     """Per-step UNet eps, each step fed the ORACLE's inputs: <= 1e-2 relative L2 in bf16."""
     from gm_diffusion_b200 import B200UNet
