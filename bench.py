@@ -11,8 +11,10 @@ NCCL all-gather of the HDR outputs per step.  Synthetic data: random-init SD1.5-
 
 `value`  : images/s with inputs resident in HBM, device-timed (CUDA events), max over ranks.
 `e2e`    : same metric through the public pipeline call with HOST (pinned) inputs and a device->host read of the HDR batch.
-`roofline`: tensor-core kernel family (tcgen05 GEMM + implicit-GEMM conv) measured live with CUDA events on an instrumented
-            eager denoise step after the timed region; algorithmic FLOPs from the layer shapes; peak from MEASURED_PEAKS.json.
+`roofline`: tensor-core kernel family (tcgen05 GEMM + implicit-GEMM conv) measured live after the timed region: the family's calls
+            of one denoise step replayed from a CUDA graph of their own (CUDA events); algorithmic FLOPs from the layer shapes; peak
+            from MEASURED_PEAKS.json.  `gpu_comparator`: torch-eager bf16 (cuDNN / cuBLAS / cuDNN SDPA) on the same box.
+            `extra_configs`: BASELINE.json configs[3] (1024x1024 single pipeline) and configs[4] (4K x 32 Eq.(1) sweep).
 `cpu_baseline` / `--impl reference`: the oracle port of the reference loop on the host cores (diffusers is not installable
             offline, so the reference pipelines cannot run), bounded sample, extrapolated to img/s.
 """
@@ -61,7 +63,7 @@ def load_peaks():
 
 
 def ncu_traffic():
-    """DRAM bytes per launch of the dominant kernel from the committed `ncu --set full` capture (profiles/), or None."""
+    """DRAM bytes of the dominant kernel family from the committed ncu launch list of one warm denoise step (profiles/), or None."""
     p = ROOT / "profiles" / "roofline_traffic.json"
     try:
         return json.loads(p.read_text())
@@ -202,34 +204,57 @@ def build_pipeline(device):
                                              scheduler=G.PNDMScheduler(), device=device)
 
 
-def instrumented_step(pipe, B):
-    """One eager denoise step (SDR UNet 2B + GM UNet B) with CUDA events around every C-ABI call: per-family device time and
-    the tensor-core family's achieved FLOP/s (algorithmic FLOPs from the layer shapes)."""
+def family_times(pipe, B):
+    """Per-kernel-family device time of ONE denoise step (SDR UNet 2B + GM UNet B), measured the way the step really runs: from
+    CUDA-graph replay.  One eager pass records every C-ABI call of the step; then, per family, a graph holding ONLY that family's
+    calls (same tensors, same order) is captured and its replay is timed with CUDA events (3 warm-ups, median of 7).  The three
+    family graphs add up to the step (the step is a serial chain of kernels), so the per-family numbers are no longer upper
+    bounds inflated by eager launch gaps as in round 1.  Also returned: the single hottest GEMM / conv instantiation (its calls
+    of the step in a graph of their own)."""
     from gm_diffusion_b200 import ops
     dev = pipe.device
     fams = {"gemm": "gemm", "conv2d": "gemm", "attention": "attn", "groupnorm_silu": "norm", "layernorm": "norm"}
     orig = {n: getattr(ops, n) for n in fams}
-    records = []
+    calls = []   # (family, flops, signature, closure)
 
-    def flops_of(name, a, k, out):
+    def flops_of(name, a, out):
         if name == "gemm":
             x, w = a[0], a[1]
             return 2.0 * x.shape[-2] * w.shape[-2] * x.shape[-1] * (x.shape[0] if x.dim() == 3 else 1)
         if name == "conv2d":
-            x, w = a[0], a[1]
-            return 2.0 * (out.numel() // out.shape[-1]) * a[2] * w.shape[1]  # output pixels x Cout x (taps * Cin)
+            return 2.0 * (out.numel() // out.shape[-1]) * a[2] * a[1].shape[1]  # output pixels x Cout x (taps * Cin)
         if name == "attention":
-            q, kk, heads = a[0], a[1], a[3]
+            q, kk = a[0], a[1]
             return 4.0 * q.shape[0] * q.shape[1] * kk.shape[1] * q.shape[2]
         return 0.0
 
+    def bytes_of(name, a, k, out):
+        """operands + output of the call once (weights as stored: padded tiles)"""
+        n = out.numel() * out.element_size()
+        for t in list(a) + [k.get("x1"), k.get("residual")]:
+            if isinstance(t, torch.Tensor):
+                n += t.numel() * t.element_size()
+            elif hasattr(t, "data") and isinstance(getattr(t, "data"), torch.Tensor):    # ops.TiledWeight
+                n += t.data.numel() * t.data.element_size()
+        return float(n)
+
+    def sig_of(name, a, k, out):
+        if name == "gemm":
+            f = "".join(t for t, on in (("+geglu", k.get("geglu")), ("+res", k.get("residual") is not None), ("+f32out", out.dtype == torch.float32)) if on)
+            return f"gemm M={a[0].shape[-2]} N={a[1].shape[-2]} K={a[0].shape[-1]}{f}"
+        if name == "conv2d":
+            x = a[0]
+            f = "".join(t for t, on in (("+s2", k.get("stride", 1) == 2), ("+up", k.get("upsample")), ("+2src", k.get("x1") is not None),
+                                        ("+res", k.get("residual") is not None), ("+f32out", out.dtype == torch.float32)) if on)
+            return f"conv{k.get('ksize', 3)} {tuple(x.shape[:3])} Cin={x.shape[3] + (k['x1'].shape[3] if k.get('x1') is not None else 0)} Cout={a[2]}{f}"
+        return name
+
     def wrap(name):
         def f(*a, **k):
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            e0.record()
             out = orig[name](*a, **k)
-            e1.record()
-            records.append((fams[name], flops_of(name, a, k, out), e0, e1))
+            k2 = {kk: vv for kk, vv in k.items() if kk != "out"}     # the replayed call allocates its own output
+            calls.append((fams[name], flops_of(name, a, out), sig_of(name, a, k, out), lambda a=a, k2=k2, name=name: orig[name](*a, **k2),
+                          bytes_of(name, a, k, out)))
             return out
         return f
 
@@ -244,19 +269,205 @@ def instrumented_step(pipe, B):
         xs = torch.randn(B, h, w, 8, device=dev, generator=g).to(torch.bfloat16)  # one copy: the CFG halves share the prefix
         xs[..., 4:] = 0
         xg = torch.randn(B, h, w, 8, device=dev, generator=g).to(torch.bfloat16)
-        records.clear()
-        torch.cuda.synchronize()
+        calls.clear()
         pipe.unet.forward(xs, tb_s, kv_s, cfg_shared=True)
         pipe.gm_unet.forward(xg, tb_g, kv_g)
         torch.cuda.synchronize()
     finally:
         for n in fams:
             setattr(ops, n, orig[n])
+
+    def graph_ms(closures):
+        for c in closures:
+            c()
+        torch.cuda.synchronize()
+        gr = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(gr):
+            for c in closures:
+                c()
+        ts = []
+        for i in range(10):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(); gr.replay(); e1.record(); torch.cuda.synchronize()
+            if i >= 3:
+                ts.append(e0.elapsed_time(e1))
+        del gr
+        return statistics.median(ts)
+
     agg = {}
-    for fam, fl, e0, e1 in records:
-        a = agg.setdefault(fam, {"ms": 0.0, "flop": 0.0, "launches": 0})
-        a["ms"] += e0.elapsed_time(e1); a["flop"] += fl; a["launches"] += 1
-    return agg
+    for fam in ("gemm", "attn", "norm"):
+        sel = [c for c in calls if c[0] == fam]
+        agg[fam] = {"ms": graph_ms([c[3] for c in sel]), "flop": sum(c[1] for c in sel), "launches": len(sel), "bytes": sum(c[4] for c in sel)}
+    # hottest GEMM / conv instantiation by algorithmic work share -> its own graph
+    groups = {}
+    for fam, fl, sg, cl, _ in calls:
+        if fam == "gemm":
+            gp = groups.setdefault(sg, {"flop": 0.0, "calls": []})
+            gp["flop"] += fl; gp["calls"].append(cl)
+    top = sorted(groups.items(), key=lambda kv: -kv[1]["flop"])[:6]
+    hot = []
+    for sg, gp in top:
+        ms = graph_ms(gp["calls"])
+        hot.append({"what": sg, "calls_per_denoise_step": len(gp["calls"]), "ms": round(ms, 4), "tflops": round(gp["flop"] / ms / 1e9, 1)})
+    torch.cuda.empty_cache()
+    return agg, hot
+
+
+def gpu_comparator(B):
+    """The reference's own GPU stack on this box, outside every timed region: ONE SDR UNet forward of the CFG batch
+    (2B samples, 64x64 latents) as torch eager bf16 channels_last on cuDNN / cuBLAS with SDPA attention — what diffusers runs —
+    and cuDNN SDPA on the step's two big self-attention shapes.  The torch network is the oracle's restatement (random init)."""
+    import torch.nn.functional as F
+    from torch.nn.attention import SDPBackend, sdpa_kernel
+    from oracle import unet_oracle as UO      # comparator only: never on the product path
+    dev = torch.device("cuda", torch.cuda.current_device())
+    bf = torch.bfloat16
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+
+    def timeit(fn, n=7, warm=3):
+        for _ in range(warm):
+            fn()
+        ts = []
+        for _ in range(n):
+            flush.zero_()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(); fn(); e1.record(); torch.cuda.synchronize()
+            ts.append(e0.elapsed_time(e1))
+        return statistics.median(ts)
+
+    out = {"what": "torch eager bf16 on cuDNN / cuBLAS / cuDNN-SDPA on the same box, L2 flushed between iterations, median of 7"}
+    g = torch.Generator(device=dev).manual_seed(0)
+    from gm_diffusion_b200 import ops
+    att = []
+    for Bq, N, C in ((2 * B, 4096, 320), (2 * B, 1024, 640)):
+        q, k, v = (torch.randn(Bq, N, C, device=dev, generator=g).to(bf) for _ in range(3))
+        q4, k4, v4 = (t.view(Bq, N, 8, C // 8).transpose(1, 2) for t in (q, k, v))
+        def cudnn():
+            with sdpa_kernel(SDPBackend.CUDNN_ATTENTION):
+                return F.scaled_dot_product_attention(q4, k4, v4)
+        row = {"B": Bq, "N": N, "d": C // 8, "ms_ours": round(timeit(lambda: ops.attention(q, k, v, 8)), 4)}
+        try:
+            row["ms_cudnn_sdpa"] = round(timeit(cudnn), 4)
+        except Exception as e:
+            row["ms_cudnn_sdpa"] = f"unavailable: {type(e).__name__}"
+        att.append(row)
+        del q, k, v
+    out["self_attention"] = att
+
+    def sdpa_forward(self, x, ctx=None):   # diffusers' AttnProcessor2_0
+        ctx = x if ctx is None else ctx
+        b, n, c = x.shape
+        hd, d = self.heads, c // self.heads
+        q = self.to_q(x).view(b, n, hd, d).transpose(1, 2)
+        k = self.to_k(ctx).view(b, -1, hd, d).transpose(1, 2)
+        v = self.to_v(ctx).view(b, -1, hd, d).transpose(1, 2)
+        return self.to_out[0](F.scaled_dot_product_attention(q, k, v).transpose(1, 2).reshape(b, n, c))
+
+    old_fwd, old_bm = UO.Attention.forward, torch.backends.cudnn.benchmark
+    try:
+        UO.Attention.forward = sdpa_forward
+        torch.backends.cudnn.benchmark = True
+        with torch.device(dev):
+            ref = UO.UNet2DConditionOracle(4).eval().to(bf).to(memory_format=torch.channels_last)
+        lat = torch.randn(2 * B, 4, HEIGHT // 8, WIDTH // 8, device=dev, generator=g).to(bf).contiguous(memory_format=torch.channels_last)
+        ctx = torch.randn(2 * B, 77, 768, device=dev, generator=g).to(bf)
+        with torch.no_grad():
+            out["unet_forward_2B_samples_ms_torch_eager"] = round(timeit(lambda: ref(lat, 501, ctx), n=5), 3)
+        del ref
+    finally:
+        UO.Attention.forward, torch.backends.cudnn.benchmark = old_fwd, old_bm
+    torch.cuda.empty_cache()
+    return out
+
+
+def extra_configs(pipe):
+    """BASELINE.json configs[3] and configs[4] as extra keys of the same line (not bench lines of their own)."""
+    import gm_diffusion_b200 as G
+    from gm_diffusion_b200.stage1 import tone_mapping as TM
+    dev = pipe.device
+    out = {}
+    # configs[3]: SDR->HDRTV up-conversion, single pipeline at 1024x1024 (latent 128x128: 16384 tokens at level 0), batch 1, 50 steps, qmax 99
+    single = G.StableDiffusionGMPipeline(vae=pipe.vae, text_encoder=None, tokenizer=None, unet=pipe.gm_unet, scheduler=G.PNDMScheduler(), device=dev)
+    g = torch.Generator().manual_seed(3)
+    pe, ne = torch.randn(1, 77, 768, generator=g).to(dev), torch.randn(1, 77, 768, generator=g).to(dev)
+    sdr_lat = (0.18215 * torch.randn(1, 4, 128, 128, generator=g)).to(dev)
+    call = lambda: single(sdr_lat, prompt_embeds=pe, negative_prompt_embeds=ne, num_inference_steps=STEPS_INFER, guidance_scale=GUIDANCE, output_type="latent")
+    call(); call(); torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(); call(); e1.record(); torch.cuda.synchronize()
+    s = e0.elapsed_time(e1) / 1000.0
+    out["config3_single_pipeline_1024x1024_batch1"] = {"s_per_image_50_steps": round(s, 4), "ms_per_cfg_unet_eval": round(1000 * s / EVALS, 3),
+                                                        "tflops": round(EVALS * 2 * 4674.4 / s / 1000, 1)}
+    del single
+    torch.cuda.empty_cache()
+    # configs[4]: Eq.(1) reconstruction (+ fix_mulog) standalone, 4K frames, batch 32, fp32 planar
+    gg = torch.Generator(device=dev).manual_seed(0)
+    sdr = torch.rand(32, 3, 2160, 3840, device=dev, generator=gg)
+    gm = torch.rand(32, 3, 2160, 3840, device=dev, generator=gg)
+    px = 32 * 2160 * 3840
+    _, hbm, _ = load_peaks()
+    rows = {}
+    for name, bpp, fn in (("eq1 (36 B/px)", 36, lambda: TM.reconstruct_hdr(sdr, gm, QMAX)),
+                          ("eq1 -> fix_mulog -> gamut, one output (36 B/px)", 36, lambda: TM.reconstruct_hdr(sdr, gm, QMAX, tmo="fix_mulog", gamut=True, return_hdr=False)),
+                          ("fix_mulog standalone (24 B/px)", 24, lambda: TM.fix_mulog_tmo(sdr, QMAX))):
+        for _ in range(3):
+            fn()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(5):
+            fn()
+        e1.record(); torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / 5
+        rows[name] = {"ms": round(ms, 3), "GBps": round(px * bpp / ms / 1e6, 1), "frac_of_hbm_peak": round(px * bpp / ms / 1e6 / hbm, 3)}
+    out["config4_eq1_4k_batch32"] = rows
+    del sdr, gm
+    torch.cuda.empty_cache()
+    return out
+
+
+def run_config2(pipe, dev, rank, world, kw):
+    """BASELINE.json configs[2] as written: global batch 64 sharded over the N ranks (32 / 16 / 8 images per GPU), first as plain
+    image sharding, then with the CFG halves split across GPU pairs (ranks 2k, 2k+1 work on the same 64 / (N/2) images; SURVEY.md
+    §8e).  One warm-up batch (graph capture at the new batch size), one timed batch, barrier + synchronize on both sides, max over
+    ranks.  Every rank takes part; rank 0 reports."""
+    import torch.distributed as dist
+    from gm_diffusion_b200 import dist as D
+    G_BATCH = 64
+    out = {"global_batch": G_BATCH}
+
+    def timed_once(fn):
+        fn(); torch.cuda.synchronize()
+        dist.barrier(); torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(); fn(); e1.record()
+        dist.barrier(); torch.cuda.synchronize()
+        return D.max_over_ranks(e0.elapsed_time(e1) / 1000.0, dev)
+
+    def inputs(n, seed):
+        g = torch.Generator().manual_seed(seed)
+        return (torch.randn(n, 77, 768, generator=g).to(dev), torch.randn(n, 77, 768, generator=g).to(dev),
+                torch.randn(n, 4, HEIGHT // 8, WIDTH // 8, generator=g).to(dev))
+
+    if G_BATCH % world == 0:
+        Bl = G_BATCH // world
+        pe, ne, lat = inputs(Bl, 2000 + rank)
+        t = timed_once(lambda: D.gather_outputs(pipe(prompt_embeds=pe, negative_prompt_embeds=ne, latents=lat, **kw)[0], G_BATCH))
+        out["image_sharding"] = {"images_per_gpu": Bl, "img_per_s": G_BATCH / t, "s_per_global_batch": t, "scaling": "strong (total work fixed at 64 images)"}
+        del pe, ne, lat
+    if world % 2 == 0 and G_BATCH % (world // 2) == 0:
+        groups = [dist.new_group([2 * k_, 2 * k_ + 1]) for k_ in range(world // 2)]     # (every rank creates every group)
+        Bp = G_BATCH // (world // 2)
+        pe, ne, lat = inputs(Bp, 3000 + rank // 2)                                      # both ranks of a pair: the same images
+        pipe.enable_cfg_pair(groups[rank // 2])
+        try:
+            t = timed_once(lambda: pipe(prompt_embeds=pe, negative_prompt_embeds=ne, latents=lat, **kw)[0])
+        finally:
+            pipe.cfg_pair = None
+        out["cfg_pair"] = {"images_per_gpu_pair": Bp, "img_per_s": G_BATCH / t, "s_per_global_batch": t,
+                           "note": "CFG halves of the SDR UNet split across each GPU pair, GM UNet split by images, one eps all-gather per UNet per step "
+                                   "(NCCL, eager stepping); both ranks of a pair hold the full result, no output gather timed"}
+    torch.cuda.empty_cache()
+    return out
 
 
 def run_b200(args):
@@ -322,21 +533,33 @@ def run_b200(args):
     value = total * args.steps / t_res
     e2e_value = total * args.steps / t_e2e
     ms_batch = 1000.0 * t_res / args.steps
+    config2 = None
+    if world > 1 and not args.no_config2:
+        try:
+            config2 = run_config2(pipe, dev, rank, world, kw)
+        except Exception as ex:
+            config2 = {"unavailable": f"{type(ex).__name__}: {ex}"}
     if rank != 0:
         if world > 1:
             torch.distributed.barrier()
         return 0
 
-    # ---- roofline of the dominant kernel family, measured live (instrumented eager step, outside the timed region) ----
+    # ---- roofline of the dominant kernel family, measured live from CUDA-graph replay (outside the timed region) ----
     peak_tf, peak_hbm, peak_src = load_peaks()
-    fam = instrumented_step(pipe, B)
+    ms_denoise = 1000.0 * t_lat / EVALS
+    fam, hot = family_times(pipe, B)
     tot_ms = sum(v["ms"] for v in fam.values())
-    gm_ = fam.get("gemm", {"ms": 1e-9, "flop": 0.0, "launches": 1})
+    gm_ = fam.get("gemm", {"ms": 1e-9, "flop": 0.0, "launches": 1, "bytes": 0.0})
     ach_tf = gm_["flop"] / (gm_["ms"] * 1e-3) / 1e12
     roofline = {"bound": "tensor", "kernel": "gmd::gemm_kernel<BN,STAGES> (tcgen05 GEMM + implicit-GEMM conv; all instantiations)",
                 "achieved": ach_tf, "peak": peak_tf, "unit": "TFLOP/s", "frac": ach_tf / peak_tf, "peak_source": peak_src,
-                "traffic": ncu_traffic(), "launches_per_denoise_step": gm_["launches"], "avg_launch_ms": gm_["ms"] / gm_["launches"],
-                "algorithmic_gflop_per_denoise_step": gm_["flop"] / 1e9, "share_of_step": gm_["ms"] / tot_ms}
+                "traffic": (ncu_traffic() or {}).get("dram_bytes_per_launch"), "traffic_detail": ncu_traffic(),
+                "algorithmic_bytes_per_launch": gm_.get("bytes", 0.0) / gm_["launches"],
+                "launches_per_denoise_step": gm_["launches"], "avg_launch_ms": gm_["ms"] / gm_["launches"],
+                "algorithmic_gflop_per_denoise_step": gm_["flop"] / 1e9, "share_of_step": gm_["ms"] / tot_ms,
+                "how": "the family's calls of one denoise step replayed from a CUDA graph of their own (CUDA events, median of 7); the three "
+                       "family graphs sum to families_sum_ms, to be compared with ms_per_denoise_step (whole loop, one graph)",
+                "families_sum_ms": tot_ms, "hottest_instantiations": [dict(h_, frac=round(h_["tflops"] / peak_tf, 3)) for h_ in hot]}
     at = fam.get("attn", {"ms": 1e-9, "flop": 0.0, "launches": 1})
     kernels = {k: {"ms_per_denoise_step": round(v["ms"], 3), "share": round(v["ms"] / tot_ms, 4), "launches": v["launches"],
                    "tflops": round(v["flop"] / (v["ms"] * 1e-3) / 1e12, 1) if v["flop"] else None} for k, v in fam.items()}
@@ -361,6 +584,21 @@ def run_b200(args):
             "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "kernels": kernels,
             "attention": {"achieved_tflops": at["flop"] / (at["ms"] * 1e-3) / 1e12, "note": "true head dims 40/80/160, true Nk; padding not credited"},
             "cpu_baseline": cpu_base}
+    if config2 is not None:
+        line["config2_global_batch_64"] = config2
+    if world == 1 and not args.no_comparator:
+        try:
+            line["gpu_comparator"] = gpu_comparator(B)
+            fwd = line["gpu_comparator"].get("unet_forward_2B_samples_ms_torch_eager")
+            if isinstance(fwd, float):
+                # our SDR forward of the same 2B samples = the SDR share of a denoise step (SDR 2B + GM B samples: 2/3 of the work)
+                line["gpu_comparator"]["unet_forward_2B_samples_ms_ours_in_graph"] = round(ms_denoise * 2.0 / 3.0, 3)
+        except Exception as ex:
+            line["gpu_comparator"] = {"unavailable": f"{type(ex).__name__}: {ex}"}
+        try:
+            line["extra_configs"] = extra_configs(pipe)
+        except Exception as ex:
+            line["extra_configs"] = {"unavailable": f"{type(ex).__name__}: {ex}"}
     emit(line)
     if world > 1:
         torch.distributed.barrier()
@@ -390,6 +628,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-config2", action="store_true", help="N > 1: skip the BASELINE configs[2] block (global batch 64, image sharding and CFG pairs)")
+    ap.add_argument("--no-comparator", action="store_true", help="skip the GPU comparator block and the extra configs (quick runs)")
     ap.add_argument("--comparators", action="store_true",
                     help="GPU-side comparators (SURVEY 8d): torch SDPA / flash_attn / cuDNN / un-fused torch chains / torch-eager UNet "
                          "on the same shapes, next to the hand-written kernels; prints one JSON object")

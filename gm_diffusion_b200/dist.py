@@ -74,5 +74,12 @@ class CfgPair:
         self.rank = dist.get_rank(group)
 
     def gather(self, local: torch.Tensor, out: torch.Tensor) -> None:
-        """out[r] = rank r's `local` (stream-ordered on the current CUDA stream)."""
+        """out[r] = rank r's `local` (NCCL: stream-ordered on the current CUDA stream).  With the gloo backend — two ranks sharing
+        ONE GPU in the single-GPU test leg, where two NCCL ranks cannot coexist and kernels of different processes must never wait
+        on one another — the exchange is staged through the host."""
+        if dist.get_backend(self.group) == "gloo":
+            host = torch.empty(out.shape, dtype=out.dtype)
+            dist.all_gather_into_tensor(host, local.cpu(), group=self.group)
+            out.copy_(host)
+            return
         dist.all_gather_into_tensor(out, local, group=self.group)
