@@ -227,6 +227,20 @@ class PipelineBase:
             if self.tokenizer is None or self.text_encoder is None:
                 raise ValueError("string prompts need `tokenizer` and `text_encoder`; pass `prompt_embeds` / "
                                  "`negative_prompt_embeds` instead")
+            # the text encoder depends on the strings only — the default negative prompt "" (and any repeated prompt,
+            # e.g. the SDR->HDR CLI's prompt=[""], generate_hdr.py:212-218) is encoded once per (text, clip_skip) and reused
+            cache = self.__dict__.setdefault("_text_cache", {})
+            keys = [(t_, clip_skip, id(self.text_encoder)) for t_ in texts]
+            if all(k_ in cache for k_ in keys):
+                return torch.cat([cache[k_] for k_ in keys], 0)
+            out = _encode_uncached(texts)
+            if len(cache) > 256:
+                cache.clear()
+            for k_, row in zip(keys, out):
+                cache[k_] = row[None].detach()
+            return out
+
+        def _encode_uncached(texts):
             ids = self.tokenizer(texts, padding="max_length", max_length=self.tokenizer.model_max_length, truncation=True,
                                  return_tensors="pt").input_ids
             enc_dev = next(self.text_encoder.parameters()).device

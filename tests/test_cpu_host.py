@@ -311,3 +311,34 @@ def test_stale_library_is_refused(lib, monkeypatch):
         lib._check_fresh()
     monkeypatch.setenv("GMD_SKIP_DIGEST_CHECK", "1")
     lib._check_fresh()
+
+
+def test_text_encoder_outputs_are_cached_per_prompt():
+    """the default negative prompt "" (and any repeated prompt) is encoded once, not once per call."""
+    from types import SimpleNamespace
+    from gm_diffusion_b200.pipelines._common import PipelineBase
+
+    class Tok:
+        model_max_length = 77
+
+        def __call__(self, texts, **kw):
+            return SimpleNamespace(input_ids=torch.tensor([[len(t)] * 77 for t in texts]))
+
+    class Enc(torch.nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.emb = torch.nn.Embedding(64, 8)
+            self.calls = 0
+
+        def forward(self, ids, **kw):
+            self.calls += 1
+            return (self.emb(ids),)
+
+    pipe = PipelineBase.__new__(PipelineBase)
+    pipe.tokenizer, pipe.text_encoder = Tok(), Enc()
+    with torch.no_grad():
+        pe1, ne1 = pipe.encode_prompt(["a cat", "a dog"], "cpu", 1, True)
+        assert pipe.text_encoder.calls == 2                       # prompts, then ["", ""]
+        pe2, ne2 = pipe.encode_prompt(["a dog", "a cat"], "cpu", 1, True)
+    assert pipe.text_encoder.calls == 2                           # everything came from the cache
+    assert torch.equal(pe2[0], pe1[1]) and torch.equal(pe2[1], pe1[0]) and torch.equal(ne1, ne2) and ne1.shape == (2, 77, 8)

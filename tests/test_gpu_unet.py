@@ -85,7 +85,14 @@ def test_vae_decoder_parity():
     got = mine.decode(z)
     assert got.shape == want.shape
     r = rel_l2(got, want)
-    assert r < 3e-2, f"VAE decode rel-L2 {r:.3e}"  # ~40 bf16 conv/GN layers at up to 512 channels; the HDR PSNR gate covers the end-to-end effect
+    # Error budget: ~40 bf16 conv / GroupNorm layers at up to 512 channels on random-init weights (no trained contraction of errors).
+    # The yardstick is the SAME decoder executed in bf16 by torch (cuDNN), i.e. the reference's own reduced-precision path: measured
+    # 2.7-3.6e-2 over three seeds against 1.8-2.4e-2 here (fp32 GroupNorm inputs, fp32 residual adds in the epilogues).  The gate is
+    # therefore relative — at least 20 % better than torch-bf16 — plus the absolute 3e-2; the HDR PSNR gate covers the end-to-end effect.
+    with torch.no_grad():
+        bf = ref.to(torch.bfloat16).decode(z.to(torch.bfloat16))
+    r_bf16 = rel_l2(bf, want)
+    assert r < 3e-2 and r < 0.8 * r_bf16, f"VAE decode rel-L2 {r:.3e} (torch bf16 of the same decoder: {r_bf16:.3e})"
 
 
 def test_vae_encoder_parity_and_latent_dist():
@@ -106,7 +113,7 @@ def test_vae_encoder_parity_and_latent_dist():
     assert dist.mean.shape == (2, 4, 16, 24) and dist.parameters.dtype == torch.float32
     r_mean = rel_l2(dist.mean, want[:, :4])
     r_all = rel_l2(dist.parameters.permute(0, 3, 1, 2), want)
-    assert r_mean < 3e-2 and r_all < 3e-2, f"encoder moments rel-L2 mean {r_mean:.3e} all {r_all:.3e}"
+    assert r_mean < 1.5e-2 and r_all < 1.5e-2, f"encoder moments rel-L2 mean {r_mean:.3e} all {r_all:.3e}"   # measured 1.0e-2
     # sample / mode: exact DiagonalGaussianDistribution arithmetic on the product's own moments
     noise = torch.randn(2, 4, 16, 24, generator=g).cuda()
     got = dist.sample(noise=noise)
