@@ -251,11 +251,12 @@ def family_times(pipe, B):
 
     def wrap(name):
         def f(*a, **k):
-            out = orig[name](*a, **k)
+            ret = orig[name](*a, **k)
+            out = ret[0] if isinstance(ret, tuple) else ret            # (conv2d / gemm with gn_stats return (out, statistics))
             k2 = {kk: vv for kk, vv in k.items() if kk != "out"}     # the replayed call allocates its own output
             calls.append((fams[name], flops_of(name, a, out), sig_of(name, a, k, out), lambda a=a, k2=k2, name=name: orig[name](*a, **k2),
                           bytes_of(name, a, k, out)))
-            return out
+            return ret
         return f
 
     h = w = HEIGHT // 8

@@ -54,6 +54,10 @@ struct KernelArgs {
     int64_t split_stride_o;   // elements between the partial-sum planes
     int w_tiled;              // weights pre-tiled as [N tile][k block][BN][64]: every B tile is one contiguous 128*BN-byte read
     const uint8_t* w_bulk;    // non-null: tiles are also PRE-SWIZZLED (smem image) -> one 1-D bulk copy per B tile instead of BN tensor rows
+    // GroupNorm statistics of the output (north_star (b)): per (32-row block, 32-column chunk) 16 pair sums + 16 pair sums of squares
+    float* gn_part;           // [class][128-row block][lane group][N_out / 32][32]; null = none
+    int gn_ncb;               // N_out / 32
+    int gn_tiles;             // 128-row blocks per class (upsample: per output-parity class)
 };
 
 // exact-erf GELU with erf from Abramowitz-Stegun 7.1.26 (|abs err| <= 1.5e-7, two MUFU ops): erff() costs ~60
@@ -539,10 +543,11 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__ 
             ti.fast = ti.tile_full && ptrs_ok && (!args.residual || ti.res_async) && ((ti.zoff_o * out_esize) % 32 == 0);
             return ti;
         };
-        struct RowInfo { bool ok; int64_t out_row, sample; };
+        struct RowInfo { bool ok; int64_t out_row, sample; int blk128; };
         auto row_info = [&](const TileInfo& ti, int s) {
             RowInfo ri;
             int t = PAIR ? ti.mt * (2 * MT) + crank * MT + s : ti.mt * MT + s;
+            ri.blk128 = t;
             if (args.mode == 0) {
                 int64_t m = (int64_t)t * BM + row;
                 ri.ok = m < args.M; ri.out_row = m;
@@ -691,6 +696,27 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__ 
                                         v[8 * j + 4] += bf16_lo(a.z); v[8 * j + 5] += bf16_hi(a.z); v[8 * j + 6] += bf16_lo(a.w); v[8 * j + 7] += bf16_hi(a.w);
                                     }
                                 }
+                            }
+                            if (args.gn_part) {
+                                // GroupNorm statistics of this 32 x 32 block of the output (host: full tiles only, every row valid):
+                                // per thread 16 channel-pair sums + 16 sums of squares, then a warp transpose-reduce (31 shuffles): lane
+                                // L ends up with the block total of value L, and the warp stores 128 contiguous bytes
+                                float sv[32];
+#pragma unroll
+                                for (int j = 0; j < 16; ++j) { sv[j] = v[2 * j] + v[2 * j + 1]; sv[16 + j] = fmaf(v[2 * j], v[2 * j], v[2 * j + 1] * v[2 * j + 1]); }
+#define GMD_GN_STEP(M_, CNT_)                                                                                   \
+                                {                                                                               \
+                                    const bool up = (lane & (M_)) != 0;                                         \
+                                    _Pragma("unroll") for (int i = 0; i < (CNT_) / 2; ++i) {                    \
+                                        const float send = up ? sv[i] : sv[i + (CNT_) / 2];                     \
+                                        const float keep = up ? sv[i + (CNT_) / 2] : sv[i];                     \
+                                        sv[i] = keep + __shfl_xor_sync(0xffffffffu, send, (M_));                \
+                                    }                                                                           \
+                                }
+                                GMD_GN_STEP(16, 32) GMD_GN_STEP(8, 16) GMD_GN_STEP(4, 8) GMD_GN_STEP(2, 4) GMD_GN_STEP(1, 2)
+#undef GMD_GN_STEP
+                                const int64_t blk = ((int64_t)ti.zb * args.gn_tiles + ri.blk128) * 4 + lg;
+                                args.gn_part[(blk * args.gn_ncb + (col0 >> 5)) * 32 + lane] = sv[0];
                             }
                             if (out_f32) {
                                 float* op = reinterpret_cast<float*>(args.out) + zoff_o + orow * args.ldo + col0;
@@ -969,6 +995,14 @@ int launch_finalize(const KernelArgs& a, const float* ws, int ksplit, int64_t ro
 }  // namespace
 }  // namespace gmd
 
+namespace gmd { namespace {
+// the GEMM epilogue can emit GroupNorm statistics when every tile is full and takes the plain (non-GEGLU, unbatched) fast path
+inline bool gemm_gn_ok(const gmd_gemm_params* p, int bn) {
+    const int64_t batch = p->batch > 0 ? p->batch : 1;
+    return batch == 1 && !(p->flags & (GMD_EPI_GEGLU | GMD_EPI_SCALE)) && (bn % 32) == 0 && (p->N % bn) == 0 && (p->M % BM) == 0 && p->ldo == p->N;
+}
+} }
+
 extern "C" int gmd_gemm_fwd(const gmd_gemm_params* p, void* stream) {
     using namespace gmd;
     if (!p || !p->a || !p->w || !p->out) { set_last_error("gmd_gemm_fwd: null pointer"); return kErrInvalid; }
@@ -1045,6 +1079,10 @@ extern "C" int gmd_gemm_fwd(const gmd_gemm_params* p, void* stream) {
     const int64_t tiles_m = (p->M + BM - 1) / BM, tiles_n = (p->N + bn - 1) / bn;
     const bool plain = batch == 1 && !geglu && !(p->flags & GMD_EPI_SCALE) && p->ldo == p->N && (!a.residual || p->ldr == p->N);
     const int ks = plan_splitk(tiles_m * tiles_n, a.num_kb, p->M, (int)p->N, p->workspace, p->workspace_bytes, plain);
+    if (p->gn_part) {
+        if (!gemm_gn_ok(p, bn) || ks > 1) { set_last_error("gmd_gemm_fwd: gn_part is not available for this call (see gmd_gemm_gn_part_floats)"); return kErrUnsupported; }
+        a.gn_part = p->gn_part; a.gn_ncb = (int)(p->N / 32); a.gn_tiles = (int)tiles_m;
+    }
     if (ks > 1) {
         KernelArgs b = a;
         b.ksplit = ks; b.kb_per_split = (a.num_kb + ks - 1) / ks; b.split_stride_o = p->M * p->N;
@@ -1056,6 +1094,38 @@ extern "C" int gmd_gemm_fwd(const gmd_gemm_params* p, void* stream) {
                                p->flags & GMD_EPI_OUT_F32, st);
     }
     return launch_cfg(bn, tiles_m, tiles_n, (unsigned)batch, maps_a, map_w, a, st, false, pair_ok);
+}
+
+extern "C" int64_t gmd_gemm_gn_part_floats(const gmd_gemm_params* p, int64_t rows_per_sample) {
+    using namespace gmd;
+    // whole 128-row tiles per sample: whether statistics come from the epilogue must not depend on how many samples are in the batch
+    if (!p || rows_per_sample <= 0 || (rows_per_sample % BM) || (p->M % rows_per_sample)) return 0;
+    const int bn = pick_bn((int)p->N, (p->flags & GMD_EPI_GEGLU) != 0);
+    if (!gemm_gn_ok(p, bn) || p->workspace) return 0;
+    return p->M / 32 * p->N;      // [M / 32 row blocks][N / 32 column chunks][32]
+}
+
+extern "C" int64_t gmd_conv_gn_part_floats(const gmd_conv_params* p) {
+    using namespace gmd;
+    if (!p || (p->ksize != 3 && p->ksize != 1) || p->N <= 0) return 0;
+    int Wg = p->W, Hg = p->H, Wo = p->W, Ho = p->H;
+    if (p->stride == 2) { Wg = Wo = p->W / 2; Hg = Ho = p->H / 2; }
+    if (p->upsample) { Wo = 2 * p->W; Ho = 2 * p->H; }
+    auto pick = [](int extent, int cap) {          // (as in gmd_conv_fwd)
+        int b = 1;
+        while (b * 2 <= cap && extent % (b * 2) == 0) b *= 2;
+        if (b < 8 && b < cap) { b = 1; while (b < extent && b < cap) b *= 2; }
+        return b;
+    };
+    const int bw = pick(Wg, BM), bh = pick(Hg, BM / bw), bn = BM / (bw * bh);
+    const int C1 = p->x1 ? p->C1 : 0;
+    const int num_kb = p->ksize * p->ksize * ((p->C0 + BK - 1) / BK + (C1 + BK - 1) / BK);
+    const int rows_w = p->w_tiled ? p->Cout : (p->Cout_pad > 0 ? p->Cout_pad : p->Cout);
+    const int bnt = pick_bn(rows_w, false);
+    const int ks = p->workspace ? conv_splitk_rule(Ho, Wo, num_kb, p->Cout, !p->upsample && p->stride == 1) : 1;
+    if (ks > 1 || bn != 1 || (Wg % bw) || (Hg % bh) || (p->Cout % bnt) || (bnt % 32)) return 0;
+    const int64_t tiles_m = (int64_t)(Wg / bw) * (Hg / bh) * p->N;
+    return (p->upsample ? 4 : 1) * tiles_m * 4 * p->Cout;      // [class][128-row block][lane group][Cout / 32][32]
 }
 
 extern "C" int gmd_conv_fwd(const gmd_conv_params* p, void* stream) {
@@ -1207,6 +1277,13 @@ extern "C" int gmd_conv_fwd(const gmd_conv_params* p, void* stream) {
     const int64_t tiles_m = (int64_t)a.tiles_w * a.tiles_h * tiles_img, tiles_nn = (p->Cout + bnt - 1) / bnt;
     const int64_t rows = (int64_t)p->N * Ho * Wo;
     const int ks = p->workspace ? conv_splitk_rule(Ho, Wo, a.num_kb, p->Cout, !p->upsample && p->stride == 1) : 1;
+    if (p->gn_part) {
+        // statistics come out of full 128-row tiles of ONE image each, written by the single-pass epilogue
+        if (ks > 1 || bn != 1 || (Wg % bw) || (Hg % bh) || (p->Cout % bnt) || (bnt % 32)) {
+            set_last_error("gmd_conv_fwd: gn_part is not available for this call (see gmd_conv_gn_part_floats)"); return kErrUnsupported;
+        }
+        a.gn_part = p->gn_part; a.gn_ncb = p->Cout / 32; a.gn_tiles = (int)tiles_m;
+    }
     if (ks > 1) {
         // the fp32 partial planes of the whole batch must fit the workspace; otherwise run the batch in image chunks (whole tiles),
         // which leaves every image's arithmetic unchanged

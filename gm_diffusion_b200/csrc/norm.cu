@@ -168,6 +168,111 @@ __global__ void __launch_bounds__(1024, 1) gn_apply_kernel(const T* __restrict__
 }
 
 // ---------------------------------------------------------------------------------------------
+// GroupNorm with statistics from the PRODUCER's epilogue (north_star (b), include/gmd_b200.h "GroupNorm fused into the producing
+// convolution / GEMM"): gn_fold_kernel adds the epilogue's per-(32 rows x 2 channels) partials per (sample, channel pair) in a fixed
+// order; gn_apply_sums_kernel is one streaming pass (read, scale / shift, SiLU, write) whose statistics are formed from the
+// channel-pair sums of its one or two sources.  No statistics pass over the activation exists any more.
+// ---------------------------------------------------------------------------------------------
+// part: [class][sample][32-row block of the sample within the class][C / 32][32]  (lane L < 16: sum of channel pair cb*16 + L,
+// L >= 16: sum of squares of pair cb*16 + L - 16).  One warp per (sample, 32-channel chunk); lane L walks its column.
+__global__ void __launch_bounds__(256) gn_fold_kernel(const float* __restrict__ part, float* __restrict__ sums, int N, int r32, int ncb, int classes) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int cb = blockIdx.x * 8 + warp, n = blockIdx.y;
+    if (cb >= ncb) return;
+    float acc = 0.0f;
+    for (int z = 0; z < classes; ++z) {
+        const float* src = part + (((int64_t)z * N + n) * r32 * ncb + cb) * 32 + lane;
+        int j = 0;
+        for (; j + 3 < r32; j += 4) {
+            const float a0 = __ldcg(src + (int64_t)j * ncb * 32), a1 = __ldcg(src + (int64_t)(j + 1) * ncb * 32);
+            const float a2 = __ldcg(src + (int64_t)(j + 2) * ncb * 32), a3 = __ldcg(src + (int64_t)(j + 3) * ncb * 32);
+            acc += a0; acc += a1; acc += a2; acc += a3;
+        }
+        for (; j < r32; ++j) acc += __ldcg(src + (int64_t)j * ncb * 32);
+    }
+    sums[(((int64_t)n * ncb + cb) * 16 + (lane & 15)) * 2 + (lane >> 4)] = acc;
+}
+
+template <typename T>
+__global__ void __launch_bounds__(320) gn_apply_sums_kernel(const T* __restrict__ x0, int C0, const float* __restrict__ sums0,
+                                                            const __nv_bfloat16* __restrict__ x1, int C1, const float* __restrict__ sums1,
+                                                            const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                            __nv_bfloat16* __restrict__ out, int HW, int groups, int apply_silu, int px_per_cta, float eps) {
+    __shared__ float s_stat[128];           // [groups][2] mean, rstd
+    const int C = C0 + C1, nvec = C / 8, cg = C / groups;
+    const int n = blockIdx.y;
+    const int P = blockDim.x / nvec;        // blockDim.x == nvec * P: every thread owns a channel vector for its whole life
+    const int cv = threadIdx.x % nvec, pl = threadIdx.x / nvec;
+    const int p0 = blockIdx.x * px_per_cta, p1 = min(p0 + px_per_cta, HW);
+    constexpr int U = 4;
+    // the first batch of activations is requested BEFORE the statistics are formed (their loads hide the prologue's round trips)
+    int p = p0 + pl;
+    float f[U][8];
+    const bool first_full = p + (U - 1) * P < p1;
+    if (first_full) {
+#pragma unroll
+        for (int u = 0; u < U; ++u) gn_load<T>(x0, C0, x1, C1, (int64_t)n * HW + p + u * P, cv * 8, f[u]);
+    }
+    if ((int)threadIdx.x < groups) {
+        // group g = channels [g*cg, (g+1)*cg) = channel pairs [g*cg/2, (g+1)*cg/2) of the concatenation (cg is even); a pair lives
+        // entirely in one source (C0 is even)
+        const int g = threadIdx.x;
+        float s1 = 0.0f, s2 = 0.0f;
+        for (int pr = g * cg / 2; pr < (g + 1) * cg / 2; ++pr) {
+            const float2 v = pr < C0 / 2 ? __ldcg(reinterpret_cast<const float2*>(sums0) + (int64_t)n * (C0 / 2) + pr)
+                                         : __ldcg(reinterpret_cast<const float2*>(sums1) + (int64_t)n * (C1 / 2) + (pr - C0 / 2));
+            s1 += v.x; s2 += v.y;
+        }
+        const float inv_cnt = 1.0f / ((float)cg * (float)HW);
+        const float mean = s1 * inv_cnt;
+        const float var = fmaxf(s2 * inv_cnt - mean * mean, 0.0f);
+        s_stat[g * 2] = mean;
+        s_stat[g * 2 + 1] = rsqrtf(var + eps);
+    }
+    const float4 g0 = __ldg(reinterpret_cast<const float4*>(gamma + cv * 8)), g1 = __ldg(reinterpret_cast<const float4*>(gamma + cv * 8) + 1);
+    const float4 b0 = __ldg(reinterpret_cast<const float4*>(beta + cv * 8)), b1 = __ldg(reinterpret_cast<const float4*>(beta + cv * 8) + 1);
+    __syncthreads();
+    float sc[8], sh[8];
+    {
+        const float ga[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w}, be[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            const int g = (cv * 8 + k) / cg;
+            const float mean = s_stat[g * 2], rstd = s_stat[g * 2 + 1];
+            sc[k] = rstd * ga[k]; sh[k] = fmaf(-mean, rstd * ga[k], be[k]);
+        }
+    }
+    if (first_full) {
+        for (;;) {
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+#pragma unroll
+                for (int k = 0; k < 8; ++k) {
+                    const float y = fmaf(f[u][k], sc[k], sh[k]);
+                    f[u][k] = apply_silu ? silu_f(y) : y;
+                }
+                *reinterpret_cast<uint4*>(out + ((int64_t)n * HW + p + u * P) * C + cv * 8) = pack8(f[u]);
+            }
+            p += U * P;
+            if (!(p + (U - 1) * P < p1)) break;
+#pragma unroll
+            for (int u = 0; u < U; ++u) gn_load<T>(x0, C0, x1, C1, (int64_t)n * HW + p + u * P, cv * 8, f[u]);
+        }
+    }
+    for (; p < p1; p += P) {
+        float g[8];
+        const int64_t px = (int64_t)n * HW + p;
+        gn_load<T>(x0, C0, x1, C1, px, cv * 8, g);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            const float y = fmaf(g[k], sc[k], sh[k]);
+            g[k] = apply_silu ? silu_f(y) : y;
+        }
+        *reinterpret_cast<uint4*>(out + px * C + cv * 8) = pack8(g);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
 // One-pass GroupNorm for everything that fits on chip (all UNet shapes up to 1024^2 images): a thread-block CLUSTER owns
 // (sample, slab of whole groups) and splits the pixels between its CTAs; every CTA parks its part of the input in shared
 // memory, the per-group sums are exchanged through distributed shared memory in rank order (fixed order: deterministic
@@ -585,6 +690,50 @@ extern "C" int gmd_groupnorm_silu(const void* x0, int32_t C0, const void* x1, in
     if (in_dtype == GMD_F32) return gn_launch<float>(x0, C0, x1, C1, gamma, beta, out, N, HW, groups, eps, apply_silu, stats_ws, st);
     set_last_error("gmd_groupnorm_silu: unknown in_dtype %d", in_dtype);
     return kErrInvalid;
+}
+
+extern "C" int gmd_gn_fold(const float* gn_part, float* sums, int32_t N, int64_t rows_per_sample, int32_t C, int32_t classes, void* stream) {
+    using namespace gmd;
+    if (!gn_part || !sums) { set_last_error("gmd_gn_fold: null pointer"); return kErrInvalid; }
+    if (N <= 0 || C <= 0 || (C % 32) || classes <= 0 || rows_per_sample <= 0 || (rows_per_sample % (32 * classes))) {
+        set_last_error("gmd_gn_fold: bad shape N=%d rows_per_sample=%lld C=%d classes=%d", N, (long long)rows_per_sample, C, classes); return kErrInvalid;
+    }
+    const int ncb = C / 32, r32 = (int)(rows_per_sample / classes / 32);
+    gn_fold_kernel<<<dim3((ncb + 7) / 8, N), 256, 0, static_cast<cudaStream_t>(stream)>>>(gn_part, sums, N, r32, ncb, classes);
+    count_launch(1);
+    return check_launch("gn_fold");
+}
+
+extern "C" int gmd_groupnorm_apply(const void* x0, int32_t C0, const float* sums0, const void* x1, int32_t C1, const float* sums1,
+                                   const float* gamma, const float* beta, void* out, int32_t N, int32_t HW, int32_t groups, float eps,
+                                   int32_t apply_silu, int32_t in_dtype, void* stream) {
+    using namespace gmd;
+    if (!x0 || !sums0 || !gamma || !beta || !out) { set_last_error("gmd_groupnorm_apply: null pointer"); return kErrInvalid; }
+    if (!x1) C1 = 0;
+    if (x1 && !sums1) { set_last_error("gmd_groupnorm_apply: second source without statistics"); return kErrInvalid; }
+    const int C = C0 + C1;
+    if (C0 % 8 || C1 % 8 || groups <= 0 || groups > 64 || C % groups || ((C / groups) % 2) || N <= 0 || HW <= 0 || C / 8 > 320) {
+        set_last_error("gmd_groupnorm_apply: bad shape C0=%d C1=%d groups=%d", C0, C1, groups); return kErrInvalid;
+    }
+    if (!al16(x0) || !al16(x1) || !al16(out) || !al16(gamma) || !al16(beta) || (reinterpret_cast<uintptr_t>(sums0) & 7) || (reinterpret_cast<uintptr_t>(sums1) & 7)) {
+        set_last_error("gmd_groupnorm_apply: pointers must be 16-byte aligned (statistics: 8)"); return kErrInvalid;
+    }
+    const int nvec = C / 8;
+    int P = 256 / nvec; if (P < 1) P = 1;
+    const int threads = nvec * P;
+    if (threads < groups) { set_last_error("gmd_groupnorm_apply: C too small for %d groups", groups); return kErrUnsupported; }
+    const int ppc = 16 * P;                                   // four batches of four loads per thread
+    const dim3 grid((HW + ppc - 1) / ppc, N);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (in_dtype == GMD_BF16)
+        gn_apply_sums_kernel<__nv_bfloat16><<<grid, threads, 0, st>>>(static_cast<const __nv_bfloat16*>(x0), C0, sums0, static_cast<const __nv_bfloat16*>(x1), C1, sums1,
+                                                                      gamma, beta, static_cast<__nv_bfloat16*>(out), HW, groups, apply_silu, ppc, eps);
+    else if (in_dtype == GMD_F32)
+        gn_apply_sums_kernel<float><<<grid, threads, 0, st>>>(static_cast<const float*>(x0), C0, sums0, static_cast<const __nv_bfloat16*>(x1), C1, sums1,
+                                                              gamma, beta, static_cast<__nv_bfloat16*>(out), HW, groups, apply_silu, ppc, eps);
+    else { set_last_error("gmd_groupnorm_apply: unknown in_dtype %d", in_dtype); return kErrInvalid; }
+    count_launch(1);
+    return check_launch("groupnorm_apply");
 }
 
 extern "C" int gmd_layernorm(const void* x, const float* gamma, const float* beta, void* out, int64_t M, int32_t C, float eps,

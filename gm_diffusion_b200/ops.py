@@ -77,10 +77,33 @@ def splitk_workspace(device) -> torch.Tensor:
     return ws
 
 
+_GN_PART = {}
+GN_EPILOGUE = __import__("os").environ.get("GMD_GN_EPILOGUE", "1") != "0"   # 0: statistics by the standalone GroupNorm kernel (A/B measurements)
+
+
+def _gn_part_workspace(device, floats: int) -> torch.Tensor:
+    """Scratch for the epilogue's GroupNorm partials (consumed by gmd_gn_fold right behind the producer, in stream order).  Buffers
+    are never freed: a captured CUDA graph may hold their address."""
+    key = torch.device(device).index or 0
+    bufs = _GN_PART.setdefault(key, [])
+    if not bufs or bufs[-1].numel() < floats:
+        bufs.append(torch.empty(max(int(floats), 1 << 20), dtype=torch.float32, device=device))
+    return bufs[-1]
+
+
+def _fold_gn(part: torch.Tensor, n: int, rows_per_sample: int, c: int, classes: int, device) -> torch.Tensor:
+    """Per-(sample, channel pair) sums [N, C/2, 2] (sum, sum of squares) from the producing kernel's partials."""
+    sums = torch.empty((n, c // 2, 2), dtype=torch.float32, device=device)
+    L.check(L.lib().gmd_gn_fold(part.data_ptr(), sums.data_ptr(), n, rows_per_sample, c, classes, L.current_stream()), "gmd_gn_fold")
+    return sums
+
+
 def gemm(a: torch.Tensor, w: torch.Tensor, *, bias: Optional[torch.Tensor] = None, residual: Optional[torch.Tensor] = None,
          row_bias: Optional[torch.Tensor] = None, rows_per_sample: int = 0, geglu: bool = False, out: Optional[torch.Tensor] = None,
-         out_f32: bool = False, alpha: Optional[float] = None, splitk: bool = False) -> torch.Tensor:
-    """out[M,N] = a[M,K] @ w[N,K]^T (+bias +row_bias[sample] +residual | GEGLU).  3-D inputs are batched."""
+         out_f32: bool = False, alpha: Optional[float] = None, splitk: bool = False, gn_rows_per_sample: int = 0):
+    """out[M,N] = a[M,K] @ w[N,K]^T (+bias +row_bias[sample] +residual | GEGLU).  3-D inputs are batched.
+    `gn_rows_per_sample` > 0: also return the GroupNorm statistics of the output, formed in the epilogue (`(out, sums)`; sums is
+    None where the kernel cannot provide them)."""
     tiled = isinstance(w, TiledWeight)
     wt = w.data if tiled else w
     L.require_cuda(a, wt)
@@ -136,16 +159,26 @@ def gemm(a: torch.Tensor, w: torch.Tensor, *, bias: Optional[torch.Tensor] = Non
         # entry point uses a batch-independent rule instead and is on by default, see conv2d.)
         ws = splitk_workspace(a.device)
         p.workspace, p.workspace_bytes = ws.data_ptr(), ws.numel()
+    part = None
+    if gn_rows_per_sample > 0 and GN_EPILOGUE:
+        floats = int(L.lib().gmd_gemm_gn_part_floats(C.byref(p), gn_rows_per_sample))
+        if floats > 0:
+            part = _gn_part_workspace(a.device, floats)
+            p.gn_part = part.data_ptr()
     L.check(L.lib().gmd_gemm_fwd(C.byref(p), L.current_stream()), "gmd_gemm_fwd")
+    if gn_rows_per_sample > 0:
+        return out, (_fold_gn(part, M // gn_rows_per_sample, gn_rows_per_sample, N, 1, a.device) if part is not None else None)
     return out
 
 
 def conv2d(x: torch.Tensor, w: torch.Tensor, cout: int, *, ksize: int = 3, stride: int = 1, upsample: bool = False,
            x1: Optional[torch.Tensor] = None, bias: Optional[torch.Tensor] = None, row_bias: Optional[torch.Tensor] = None,
            residual: Optional[torch.Tensor] = None, out: Optional[torch.Tensor] = None, out_f32: bool = False, splitk: bool = True,
-           pad_end: bool = False) -> torch.Tensor:
+           pad_end: bool = False, gn_stats: bool = False):
     """NHWC bf16 convolution as implicit GEMM (3x3 pad 1 stride 1/2, optional folded nearest-2x upsample).  `pad_end` (stride 2):
-    the AutoencoderKL encoder's asymmetric padding — no leading pad, one zero row/column at the bottom/right."""
+    the AutoencoderKL encoder's asymmetric padding — no leading pad, one zero row/column at the bottom/right.
+    `gn_stats`: also return the GroupNorm statistics of the output, formed in the epilogue (`(out, sums)`; sums is None where the
+    kernel cannot provide them: split-K layers, ragged tiles)."""
     tiled = isinstance(w, TiledWeight)
     wt = w.data if tiled else w
     L.require_cuda(x, wt)
@@ -193,7 +226,15 @@ def conv2d(x: torch.Tensor, w: torch.Tensor, cout: int, *, ksize: int = 3, strid
         # profiles/prof_splitk.py); the rule looks only at the per-image geometry, so results do not depend on the batch
         ws = splitk_workspace(x.device)
         p.workspace, p.workspace_bytes = ws.data_ptr(), ws.numel()
+    part = None
+    if gn_stats and GN_EPILOGUE:
+        floats = int(L.lib().gmd_conv_gn_part_floats(C.byref(p)))
+        if floats > 0:
+            part = _gn_part_workspace(x.device, floats)
+            p.gn_part = part.data_ptr()
     L.check(L.lib().gmd_conv_fwd(C.byref(p), L.current_stream()), "gmd_conv_fwd")
+    if gn_stats:
+        return out, (_fold_gn(part, N, Ho * Wo, cout, 4 if upsample else 1, x.device) if part is not None else None)
     return out
 
 
@@ -203,14 +244,23 @@ def gn_workspace(n_max: int, groups: int, device) -> torch.Tensor:
 
 
 def groupnorm_silu(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, *, x1: Optional[torch.Tensor] = None, groups: int = 32,
-                   eps: float = 1e-5, silu: bool = True, out: Optional[torch.Tensor] = None, stats_ws: Optional[torch.Tensor] = None) -> torch.Tensor:
-    """GroupNorm(+SiLU) over NHWC bf16; with `x1` the channels are [x | x1] and the output is the concatenation."""
+                   eps: float = 1e-5, silu: bool = True, out: Optional[torch.Tensor] = None, stats_ws: Optional[torch.Tensor] = None,
+                   sums: Optional[torch.Tensor] = None, sums1: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """GroupNorm(+SiLU) over NHWC bf16; with `x1` the channels are [x | x1] and the output is the concatenation.
+    `sums` / `sums1`: statistics of x / x1 from their producers' epilogues (conv2d / gemm with gn_stats) — the activation is then
+    read ONCE (gmd_groupnorm_apply) instead of being reduced first."""
     L.require_cuda(x)
     N, C0 = x.shape[0], x.shape[-1]
     HW = x.numel() // (N * C0)
     C1 = x1.shape[-1] if x1 is not None else 0
     if out is None:
         out = torch.empty(x.shape[:-1] + (C0 + C1,), dtype=bf16, device=x.device)
+    if sums is not None and (x1 is None or sums1 is not None) and ((C0 + C1) // groups) % 2 == 0 and (C0 + C1) // 8 <= 320:
+        assert sums.shape == (N, C0 // 2, 2) and (x1 is None or sums1.shape == (N, C1 // 2, 2))
+        L.check(L.lib().gmd_groupnorm_apply(x.data_ptr(), C0, sums.data_ptr(), L.ptr(x1), C1, L.ptr(sums1) if x1 is not None else None,
+                                            gamma.data_ptr(), beta.data_ptr(), out.data_ptr(), N, HW, groups, float(eps), int(silu),
+                                            L.F32 if x.dtype == torch.float32 else L.BF16, L.current_stream()), "gmd_groupnorm_apply")
+        return out
     if stats_ws is None:
         stats_ws = gn_workspace(N, groups, x.device)
     assert stats_ws.numel() >= 1024 + N * 34 * groups * 2, "groupnorm workspace too small"

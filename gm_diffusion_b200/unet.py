@@ -51,18 +51,21 @@ class _Resnet:
             self.wsc = ops.pack_conv_weight_tiled(g("conv_shortcut.weight").to(dev))
             self.bsc = _f32(g("conv_shortcut.bias"), dev)
 
-    def __call__(self, x, skip, temb_all, ws):
+    def __call__(self, x, skip, temb_all, ws, xs=None, skip_s=None):
+        """x / skip: hidden state and (up blocks) the skip tensor; xs / skip_s: their GroupNorm statistics from the epilogues of the
+        kernels that produced them (None: the GroupNorm forms its own).  Returns (output, statistics of the output)."""
         # GN+SiLU also materialises the [hidden | skip] concat, already normalised (dual source read)
-        h = ops.groupnorm_silu(x, *self.n1, x1=skip, eps=self.eps, stats_ws=ws)
+        h = ops.groupnorm_silu(x, *self.n1, x1=skip, eps=self.eps, stats_ws=ws, sums=xs, sums1=skip_s)
         rb = temb_all[:, self.temb_off:self.temb_off + self.cout] if self.temb_off is not None else None
-        # conv1's output only feeds GroupNorm (never an MMA): keep it fp32 so it is not rounded on the way in
-        h = ops.conv2d(h, self.w1, self.cout, bias=self.b1, row_bias=rb, out_f32=True)
-        h = ops.groupnorm_silu(h, *self.n2, eps=self.eps, stats_ws=ws)
+        # conv1's output only feeds GroupNorm (never an MMA): keep it fp32 so it is not rounded on the way in; its epilogue (bias +
+        # time-embedding row already added) also emits the statistics the GroupNorm needs — north_star (b)
+        h, hs = ops.conv2d(h, self.w1, self.cout, bias=self.b1, row_bias=rb, out_f32=True, gn_stats=True)
+        h = ops.groupnorm_silu(h, *self.n2, eps=self.eps, stats_ws=ws, sums=hs)
         if self.wsc is not None:
             res = ops.conv2d(x, self.wsc, self.cout, ksize=1, x1=skip, bias=self.bsc)
         else:
             res = x
-        return ops.conv2d(h, self.w2, self.cout, bias=self.b2, residual=res)
+        return ops.conv2d(h, self.w2, self.cout, bias=self.b2, residual=res, gn_stats=True)
 
 
 class _Transformer:
@@ -89,13 +92,13 @@ class _Transformer:
         """Step-invariant text K/V: Linear(768 -> C) of the CLIP states, fused [K | V]."""
         return ops.gemm(ctx2d, self.w_kv2)
 
-    def __call__(self, x, kv, ws, dup: bool = False):
+    def __call__(self, x, kv, ws, dup: bool = False, xs=None):
         """`dup`: x holds ONE copy of a batch whose two CFG halves are still identical (nothing before the first text
         cross-attention depends on the prompt); everything up to and including self-attention runs once, then the token
         stream and the residual are duplicated (uncond | cond) and the rest runs on 2B samples."""
         B, H, W, c = x.shape
         n, m = H * W, B * H * W
-        y = ops.groupnorm_silu(x, *self.norm, eps=1e-6, silu=False, stats_ws=ws)
+        y = ops.groupnorm_silu(x, *self.norm, eps=1e-6, silu=False, stats_ws=ws, sums=xs)
         # the token stream y is consumed only by LayerNorms and residual adds (never an MMA operand): it stays fp32,
         # which removes 4 of the 5 full-magnitude bf16 roundings per transformer block
         y = ops.gemm(y.view(m, c), self.w_in, bias=self.b_in, out_f32=True)
@@ -118,7 +121,8 @@ class _Transformer:
         h = ops.layernorm(y, *self.ln[2])
         h = ops.gemm(h, self.w_ff1, bias=self.b_ff1, geglu=True)
         y = ops.gemm(h, self.w_ff2, bias=self.b_ff2, residual=y, out_f32=False)  # proj_out's MMA reads it: bf16
-        return ops.gemm(y, self.w_out, bias=self.b_out, residual=x.view(m, c)).view(B, H, W, c)
+        out, os_ = ops.gemm(y, self.w_out, bias=self.b_out, residual=x.view(m, c), gn_rows_per_sample=n)   # the next GroupNorm's statistics
+        return out.view(B, H, W, c), os_
 
 
 class B200UNet:
@@ -238,32 +242,34 @@ class B200UNet:
         temb_all = temb_row if temb_row.shape[0] == full else temb_row.expand(full, -1)
         ws = self._gn_ws
         kv = iter(context_kv)
-        x = ops.conv2d(sample, self.w_in, self.ch0, bias=self.b_in)
-        skips = [torch.cat([x, x], 0) if cfg_shared else x]
+        x, xs = ops.conv2d(sample, self.w_in, self.ch0, bias=self.b_in, gn_stats=True)
+        dup2 = lambda t_: None if t_ is None else torch.cat([t_, t_], 0)
+        skips = [(dup2(x), dup2(xs)) if cfg_shared else (x, xs)]       # every activation travels with its GroupNorm statistics
         pending_dup = cfg_shared
         for res, att, ds in self.down:
             for r, a in zip(res, att):
-                x = r(x, None, temb_all[: x.shape[0]], ws)
+                x, xs = r(x, None, temb_all[: x.shape[0]], ws, xs=xs)
                 if a is not None:
-                    x = a(x, next(kv), ws, dup=pending_dup)
+                    x, xs = a(x, next(kv), ws, dup=pending_dup, xs=xs)
                     pending_dup = False
                 elif pending_dup:
                     raise NotImplementedError("cfg_shared needs an attention block after the first resnet")
-                skips.append(x)
+                skips.append((x, xs))
             if ds is not None:
-                x = ops.conv2d(x, ds[0], ds[0].shape[0], stride=2, bias=ds[1])
-                skips.append(x)
-        x = self.mid_res[0](x, None, temb_all, ws)
-        x = self.mid_att(x, next(kv), ws)
-        x = self.mid_res[1](x, None, temb_all, ws)
+                x, xs = ops.conv2d(x, ds[0], ds[0].shape[0], stride=2, bias=ds[1], gn_stats=True)
+                skips.append((x, xs))
+        x, xs = self.mid_res[0](x, None, temb_all, ws, xs=xs)
+        x, xs = self.mid_att(x, next(kv), ws, xs=xs)
+        x, xs = self.mid_res[1](x, None, temb_all, ws, xs=xs)
         for res, att, us in self.up:
             for r, a in zip(res, att):
-                x = r(x, skips.pop(), temb_all, ws)
+                sk, sks = skips.pop()
+                x, xs = r(x, sk, temb_all, ws, xs=xs, skip_s=sks)
                 if a is not None:
-                    x = a(x, next(kv), ws)
+                    x, xs = a(x, next(kv), ws, xs=xs)
             if us is not None:
-                x = ops.conv2d(x, us[0], us[0].shape[0], upsample=True, bias=us[1])
-        x = ops.groupnorm_silu(x, *self.n_out, eps=1e-5, stats_ws=ws)
+                x, xs = ops.conv2d(x, us[0], us[0].shape[0], upsample=True, bias=us[1], gn_stats=True)
+        x = ops.groupnorm_silu(x, *self.n_out, eps=1e-5, stats_ws=ws, sums=xs)
         return ops.conv2d(x, self.w_out, self.out_channels, bias=self.b_out, out=out, out_f32=True)
 
     __call__ = forward

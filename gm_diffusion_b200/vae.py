@@ -39,10 +39,11 @@ class _VaeAttention:
         self.w_v, self.b_v = sd[a + "to_v.weight"].detach().to(device=dev, dtype=bf16).contiguous(), _f32(sd[a + "to_v.bias"], dev)
         self.w_o, self.b_o = _w(sd[a + "to_out.0.weight"], dev), _f32(sd[a + "to_out.0.bias"], dev)
 
-    def __call__(self, x, ws):
+    def __call__(self, x, ws, xs=None):
+        """xs: GroupNorm statistics of x from its producer's epilogue (or None).  Returns (output, statistics of the output)."""
         B, H, W, c = x.shape
         n, m = H * W, B * H * W
-        y = ops.groupnorm_silu(x, *self.a_norm, eps=1e-6, silu=False, stats_ws=ws).view(m, c)
+        y = ops.groupnorm_silu(x, *self.a_norm, eps=1e-6, silu=False, stats_ws=ws, sums=xs).view(m, c)
         qk = ops.gemm(y, self.w_qk, bias=self.b_qk).view(B, n, 2 * c)
         # V^T per image straight out of a GEMM with swapped operand roles: Vt[c, token] = Wv[c,:] . y[token,:]
         vt = torch.empty((B, c, n), dtype=bf16, device=x.device)
@@ -53,7 +54,8 @@ class _VaeAttention:
         p = ops.softmax_rows(s, c ** -0.5, out=s)
         # rows of P sum to 1, so the V bias passes through the attention average unchanged: add it after P.V
         o = ops.gemm(p, vt, bias=self.b_v).view(m, c)
-        return ops.gemm(o, self.w_o, bias=self.b_o, residual=x.view(m, c)).view(B, H, W, c)
+        out, os_ = ops.gemm(o, self.w_o, bias=self.b_o, residual=x.view(m, c), gn_rows_per_sample=n)
+        return out.view(B, H, W, c), os_
 
 
 class B200VaeDecoder:
@@ -101,8 +103,8 @@ class B200VaeDecoder:
             sf = (cfg.get("scaling_factor") if isinstance(cfg, dict) else getattr(cfg, "scaling_factor", None)) or SCALING_FACTOR
         return cls({k: v for k, v in module.state_dict().items()}, device=device, scaling_factor=sf, **kw)
 
-    def _attention(self, x):
-        return self.mid_attn(x, self._gn_ws)
+    def _attention(self, x, xs=None):
+        return self.mid_attn(x, self._gn_ws, xs)
 
 
     @L.on_own_device
@@ -114,16 +116,17 @@ class B200VaeDecoder:
         L.check(L.lib().gmd_pack_unet_input(latents_px.data_ptr(), None, z.data_ptr(), n_px, 8, L.current_stream()), "gmd_pack_unet_input")
         z = ops.gemm(z, self.w_pq, bias=self.b_pq).view(B, h, w, 8)
         ws = self._gn_ws
-        x = ops.conv2d(z, self.w_in, self.c_mid, bias=self.b_in)
-        x = self.mid_res[0](x, None, None, ws)
-        x = self._attention(x)
-        x = self.mid_res[1](x, None, None, ws)
+        # every activation travels with the GroupNorm statistics its producer's epilogue formed (None where unavailable)
+        x, xs = ops.conv2d(z, self.w_in, self.c_mid, bias=self.b_in, gn_stats=True)
+        x, xs = self.mid_res[0](x, None, None, ws, xs=xs)
+        x, xs = self._attention(x, xs)
+        x, xs = self.mid_res[1](x, None, None, ws, xs=xs)
         for res, us in self.ups:
             for r in res:
-                x = r(x, None, None, ws)
+                x, xs = r(x, None, None, ws, xs=xs)
             if us is not None:
-                x = ops.conv2d(x, us[0], us[0].shape[0], upsample=True, bias=us[1])
-        x = ops.groupnorm_silu(x, *self.n_out, eps=1e-6, stats_ws=ws)
+                x, xs = ops.conv2d(x, us[0], us[0].shape[0], upsample=True, bias=us[1], gn_stats=True)
+        x = ops.groupnorm_silu(x, *self.n_out, eps=1e-6, stats_ws=ws, sums=xs)
         return ops.conv2d(x, self.w_out, self.w_out.shape[0], bias=self.b_out)
 
     @torch.no_grad()
@@ -231,16 +234,16 @@ class B200Vae(B200VaeDecoder):
         x = torch.empty((B, H, W, 8), dtype=bf16, device=self.device)
         L.check(L.lib().gmd_pack_image_nchw(img.data_ptr(), x.data_ptr(), B, H * W, 3, L.current_stream()), "gmd_pack_image_nchw")
         ws = self._gn_ws
-        x = ops.conv2d(x, self.e_w_in, self.e_c0, bias=self.e_b_in)
+        x, xs = ops.conv2d(x, self.e_w_in, self.e_c0, bias=self.e_b_in, gn_stats=True)
         for res, ds in self.e_downs:
             for r in res:
-                x = r(x, None, None, ws)
+                x, xs = r(x, None, None, ws, xs=xs)
             if ds is not None:
-                x = ops.conv2d(x, ds[0], ds[0].shape[0], stride=2, pad_end=True, bias=ds[1])
-        x = self.e_mid_res[0](x, None, None, ws)
-        x = self.e_attn(x, ws)
-        x = self.e_mid_res[1](x, None, None, ws)
-        x = ops.groupnorm_silu(x, *self.e_n_out, eps=1e-6, stats_ws=ws)
+                x, xs = ops.conv2d(x, ds[0], ds[0].shape[0], stride=2, pad_end=True, bias=ds[1], gn_stats=True)
+        x, xs = self.e_mid_res[0](x, None, None, ws, xs=xs)
+        x, xs = self.e_attn(x, ws, xs)
+        x, xs = self.e_mid_res[1](x, None, None, ws, xs=xs)
+        x = ops.groupnorm_silu(x, *self.e_n_out, eps=1e-6, stats_ws=ws, sums=xs)
         return ops.conv2d(x, self.e_w_out, 8, bias=self.e_b_out, out_f32=True)
 
     @torch.no_grad()

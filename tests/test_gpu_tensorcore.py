@@ -314,6 +314,61 @@ def test_attention_large_logits():
     check(got, ref.transpose(1, 2).reshape(B, N, H * d), tol=2e-2, what="peaky softmax (running-max rescale path)")
 
 
+@pytest.mark.parametrize("case", ["conv3", "conv3_f32out_temb", "conv3_2src_res", "conv_up", "conv_s2", "gemm_res"])
+def test_groupnorm_statistics_from_the_producer_epilogue(case):
+    """north_star (b): the convolution / GEMM epilogue emits the GroupNorm statistics of its output; gmd_groupnorm_apply then
+    normalises in one pass.  Checked: the statistics against sums over the stored output, the normalised result against torch's
+    GroupNorm of that output, a two-source consumer whose 32 groups straddle the sources, bit-reproducibility and independence
+    of the batch size."""
+    from gm_diffusion_b200 import ops
+    g = torch.Generator().manual_seed(len(case))
+    N, H, C = 3, 32, 320
+    x = torch.randn(N, H, H, C, generator=g).to(bf).cuda()
+    x1 = torch.randn(N, H, H, 640, generator=g).to(bf).cuda()
+    mk = lambda co, ci: ops.pack_conv_weight_tiled((torch.randn(co, ci, 3, 3, generator=g) / math.sqrt(9 * ci)).cuda())
+    b = torch.randn(640, generator=g).cuda()
+    if case == "conv3":
+        run = lambda xx, n: ops.conv2d(xx, w, 640, bias=b, gn_stats=True); w = mk(640, C)
+    elif case == "conv3_f32out_temb":
+        rb = torch.randn(N, 640, generator=g).cuda(); w = mk(640, C)
+        run = lambda xx, n: ops.conv2d(xx, w, 640, bias=b, row_bias=rb[:n], out_f32=True, gn_stats=True)
+    elif case == "conv3_2src_res":
+        w = mk(640, C + 640); res = torch.randn(N, H, H, 640, generator=g).to(bf).cuda()
+        run = lambda xx, n: ops.conv2d(xx, w, 640, x1=x1[:n], bias=b, residual=res[:n], gn_stats=True)
+    elif case == "conv_up":
+        w = mk(640, C)
+        run = lambda xx, n: ops.conv2d(xx, w, 640, upsample=True, bias=b, gn_stats=True)
+    elif case == "conv_s2":
+        w = mk(640, C)
+        run = lambda xx, n: ops.conv2d(xx, w, 640, stride=2, bias=b, gn_stats=True)
+    else:
+        wl = ops.tile_weight((torch.randn(640, C, generator=g) / math.sqrt(C)).cuda()); res = torch.randn(N * H * H, 640, generator=g).to(bf).cuda()
+        run = lambda xx, n: ops.gemm(xx.reshape(-1, C), wl, bias=b, residual=res[: n * H * H], gn_rows_per_sample=H * H)
+    y, sums = run(x, N)
+    assert sums is not None and sums.shape == (N, 320, 2), "this shape must take the epilogue-statistics path"
+    y3 = y.float().reshape(N, -1, 640)
+    want = torch.stack([y3.reshape(N, -1, 320, 2).sum((1, 3)), (y3 ** 2).reshape(N, -1, 320, 2).sum((1, 3))], -1)
+    err = (sums - want).abs().max() / want.abs().max()
+    assert float(err) < 2e-3, f"{case}: epilogue statistics vs sums over the stored output: {float(err):.2e}"   # (formed before the bf16 rounding of the output)
+    ga, be = torch.randn(640, generator=g).cuda(), torch.randn(640, generator=g).cuda()
+    got = ops.groupnorm_silu(y.reshape(N, -1, 640), ga, be, eps=1e-5, sums=sums)
+    ref = F.silu(F.group_norm(y3.permute(0, 2, 1), 32, ga, be, 1e-5)).permute(0, 2, 1)
+    check(got, ref, what=f"{case}: groupnorm from epilogue statistics")
+    y_, sums_ = run(x, N)
+    assert torch.equal(sums, sums_) and torch.equal(y, y_), "bit-reproducible"
+    y1, s1 = run(x[:1], 1)
+    assert torch.equal(s1, sums[:1]) and torch.equal(y1.reshape(1, -1, 640), y.reshape(N, -1, 640)[:1]), "independent of the batch size"
+    # consumer of a concat whose groups straddle the two sources (640 + 320 channels: groups of 30)
+    n_px = y3.shape[1]
+    z = torch.randn(N, n_px, 320, generator=g).to(bf).cuda()
+    zs = torch.stack([z.float().reshape(N, n_px, 160, 2).sum((1, 3)), (z.float() ** 2).reshape(N, n_px, 160, 2).sum((1, 3))], -1).contiguous()
+    ga2, be2 = torch.randn(960, generator=g).cuda(), torch.randn(960, generator=g).cuda()
+    if y.dtype == bf:
+        got2 = ops.groupnorm_silu(y.reshape(N, n_px, 640), ga2, be2, x1=z, sums=sums, sums1=zs)
+        ref2 = F.silu(F.group_norm(torch.cat([y3, z.float()], -1).permute(0, 2, 1), 32, ga2, be2, 1e-5)).permute(0, 2, 1)
+        check(got2, ref2, what=f"{case}: two-source groupnorm from epilogue statistics")
+
+
 @pytest.mark.parametrize("N,HW,C0,C1", [(2, 4096, 320, 0), (2, 1024, 1280, 640), (3, 64, 1280, 1280), (1, 256, 640, 320), (2, 4096, 128, 0), (1, 100, 512, 0),
                                         (1, 16384, 512, 0), (1, 65536, 128, 0), (2, 4096, 640, 320)])  # 65536: too big for the one-pass cluster kernel -> two-pass
 def test_groupnorm(N, HW, C0, C1):
