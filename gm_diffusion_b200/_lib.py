@@ -49,14 +49,14 @@ class GemmParams(C.Structure):
                 ("bias", _vp), ("row_bias", _vp), ("ld_row_bias", _i64), ("rows_per_sample", _i64),
                 ("residual", _vp), ("ldr", _i64), ("M", _i64), ("N", _i64), ("K", _i64), ("batch", _i64),
                 ("stride_a", _i64), ("stride_w", _i64), ("stride_o", _i64), ("flags", _i32), ("alpha", _f32),
-                ("workspace", _vp), ("workspace_bytes", _i64), ("w_tiled", _i32), ("gn_part", _vp)]
+                ("workspace", _vp), ("workspace_bytes", _i64), ("w_tiled", _i32), ("gn_sums", _vp), ("gn_rows_per_sample", _i64)]
 
 
 class ConvParams(C.Structure):
     _fields_ = [("x0", _vp), ("C0", _i32), ("x1", _vp), ("C1", _i32), ("w", _vp), ("out", _vp), ("bias", _vp),
                 ("row_bias", _vp), ("ld_row_bias", _i64), ("residual", _vp), ("N", _i32), ("H", _i32), ("W", _i32),
                 ("Cout", _i32), ("Cout_pad", _i32), ("ksize", _i32), ("stride", _i32), ("upsample", _i32),
-                ("flags", _i32), ("workspace", _vp), ("workspace_bytes", _i64), ("w_tiled", _i32), ("gn_part", _vp)]
+                ("flags", _i32), ("workspace", _vp), ("workspace_bytes", _i64), ("w_tiled", _i32), ("gn_sums", _vp)]
 
 
 class AttnParams(C.Structure):
@@ -130,11 +130,8 @@ def lib() -> C.CDLL:
     L.gmd_vae_sample.argtypes = [_vp, _vp, _vp, _i64, _f32, _vp]
     L.gmd_gemm_fwd.argtypes = [C.POINTER(GemmParams), _vp]
     L.gmd_conv_fwd.argtypes = [C.POINTER(ConvParams), _vp]
-    L.gmd_conv_gn_part_floats.restype = C.c_int64
-    L.gmd_conv_gn_part_floats.argtypes = [C.POINTER(ConvParams)]
-    L.gmd_gemm_gn_part_floats.restype = C.c_int64
-    L.gmd_gemm_gn_part_floats.argtypes = [C.POINTER(GemmParams), _i64]
-    L.gmd_gn_fold.argtypes = [_vp, _vp, _i32, _i64, _i32, _i32, _vp]
+    L.gmd_conv_gn_sums_ok.argtypes = [C.POINTER(ConvParams)]
+    L.gmd_gemm_gn_sums_ok.argtypes = [C.POINTER(GemmParams), _i64]
     L.gmd_groupnorm_apply.argtypes = [_vp, _i32, _vp, _vp, _i32, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _f32, _i32, _i32, _vp]
     L.gmd_groupnorm_silu.argtypes = [_vp, _i32, _vp, _i32, _vp, _vp, _vp, _i32, _i32, _i32, _f32, _i32, _i32, _vp, _vp]
     L.gmd_layernorm.argtypes = [_vp, _vp, _vp, _vp, _i64, _i32, _f32, _i32, _vp]

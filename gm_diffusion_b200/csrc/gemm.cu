@@ -54,10 +54,12 @@ struct KernelArgs {
     int64_t split_stride_o;   // elements between the partial-sum planes
     int w_tiled;              // weights pre-tiled as [N tile][k block][BN][64]: every B tile is one contiguous 128*BN-byte read
     const uint8_t* w_bulk;    // non-null: tiles are also PRE-SWIZZLED (smem image) -> one 1-D bulk copy per B tile instead of BN tensor rows
-    // GroupNorm statistics of the output (north_star (b)): per (32-row block, 32-column chunk) 16 pair sums + 16 pair sums of squares
-    float* gn_part;           // [class][128-row block][lane group][N_out / 32][32]; null = none
+    // GroupNorm statistics of the output (north_star (b)): per (sample, channel pair) sum and sum of squares, accumulated by the
+    // epilogue as 64-bit FIXED-POINT integers (2^-24 units): integer addition is associative, so the atomics leave the result
+    // bit-reproducible and independent of tile order and batch size; no partial buffer, no fold pass
+    long long* gn_sums;       // [sample][N_out / 2][2]; null = none.  Zeroed by the caller
     int gn_ncb;               // N_out / 32
-    int gn_tiles;             // 128-row blocks per class (upsample: per output-parity class)
+    int64_t gn_rows;          // GEMM mode: output rows per sample
 };
 
 // exact-erf GELU with erf from Abramowitz-Stegun 7.1.26 (|abs err| <= 1.5e-7, two MUFU ops): erff() costs ~60
@@ -697,10 +699,10 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__ 
                                     }
                                 }
                             }
-                            if (args.gn_part) {
+                            if (args.gn_sums) {
                                 // GroupNorm statistics of this 32 x 32 block of the output (host: full tiles only, every row valid):
                                 // per thread 16 channel-pair sums + 16 sums of squares, then a warp transpose-reduce (31 shuffles): lane
-                                // L ends up with the block total of value L, and the warp stores 128 contiguous bytes
+                                // L ends up with the block total of value L, added to the sample's accumulators as a fixed-point integer
                                 float sv[32];
 #pragma unroll
                                 for (int j = 0; j < 16; ++j) { sv[j] = v[2 * j] + v[2 * j + 1]; sv[16 + j] = fmaf(v[2 * j], v[2 * j], v[2 * j + 1] * v[2 * j + 1]); }
@@ -715,8 +717,11 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__ 
                                 }
                                 GMD_GN_STEP(16, 32) GMD_GN_STEP(8, 16) GMD_GN_STEP(4, 8) GMD_GN_STEP(2, 4) GMD_GN_STEP(1, 2)
 #undef GMD_GN_STEP
-                                const int64_t blk = ((int64_t)ti.zb * args.gn_tiles + ri.blk128) * 4 + lg;
-                                args.gn_part[(blk * args.gn_ncb + (col0 >> 5)) * 32 + lane] = sv[0];
+                                // lane L < 16: sum of channel pair (col0/2 + L); L >= 16: sum of squares of pair (col0/2 + L - 16)
+                                const int64_t smp = args.mode == 0 ? orow / args.gn_rows : ri.sample;       // (warp-uniform: 32-row blocks never straddle samples)
+                                unsigned long long* dst = reinterpret_cast<unsigned long long*>(args.gn_sums) +
+                                                          ((smp * args.gn_ncb + (col0 >> 5)) * 16 + (lane & 15)) * 2 + (lane >> 4);
+                                atomicAdd(dst, static_cast<unsigned long long>(__float2ll_rn(sv[0] * 16777216.0f)));
                             }
                             if (out_f32) {
                                 float* op = reinterpret_cast<float*>(args.out) + zoff_o + orow * args.ldo + col0;
@@ -1079,9 +1084,11 @@ extern "C" int gmd_gemm_fwd(const gmd_gemm_params* p, void* stream) {
     const int64_t tiles_m = (p->M + BM - 1) / BM, tiles_n = (p->N + bn - 1) / bn;
     const bool plain = batch == 1 && !geglu && !(p->flags & GMD_EPI_SCALE) && p->ldo == p->N && (!a.residual || p->ldr == p->N);
     const int ks = plan_splitk(tiles_m * tiles_n, a.num_kb, p->M, (int)p->N, p->workspace, p->workspace_bytes, plain);
-    if (p->gn_part) {
-        if (!gemm_gn_ok(p, bn) || ks > 1) { set_last_error("gmd_gemm_fwd: gn_part is not available for this call (see gmd_gemm_gn_part_floats)"); return kErrUnsupported; }
-        a.gn_part = p->gn_part; a.gn_ncb = (int)(p->N / 32); a.gn_tiles = (int)tiles_m;
+    if (p->gn_sums) {
+        if (!gemm_gn_ok(p, bn) || ks > 1 || p->gn_rows_per_sample <= 0 || (p->gn_rows_per_sample % BM) || (p->M % p->gn_rows_per_sample)) {
+            set_last_error("gmd_gemm_fwd: gn_sums is not available for this call (see gmd_gemm_gn_sums_ok)"); return kErrUnsupported;
+        }
+        a.gn_sums = static_cast<long long*>(p->gn_sums); a.gn_ncb = (int)(p->N / 32); a.gn_rows = p->gn_rows_per_sample;
     }
     if (ks > 1) {
         KernelArgs b = a;
@@ -1096,16 +1103,15 @@ extern "C" int gmd_gemm_fwd(const gmd_gemm_params* p, void* stream) {
     return launch_cfg(bn, tiles_m, tiles_n, (unsigned)batch, maps_a, map_w, a, st, false, pair_ok);
 }
 
-extern "C" int64_t gmd_gemm_gn_part_floats(const gmd_gemm_params* p, int64_t rows_per_sample) {
+extern "C" int gmd_gemm_gn_sums_ok(const gmd_gemm_params* p, int64_t rows_per_sample) {
     using namespace gmd;
     // whole 128-row tiles per sample: whether statistics come from the epilogue must not depend on how many samples are in the batch
     if (!p || rows_per_sample <= 0 || (rows_per_sample % BM) || (p->M % rows_per_sample)) return 0;
     const int bn = pick_bn((int)p->N, (p->flags & GMD_EPI_GEGLU) != 0);
-    if (!gemm_gn_ok(p, bn) || p->workspace) return 0;
-    return p->M / 32 * p->N;      // [M / 32 row blocks][N / 32 column chunks][32]
+    return (gemm_gn_ok(p, bn) && !p->workspace) ? 1 : 0;
 }
 
-extern "C" int64_t gmd_conv_gn_part_floats(const gmd_conv_params* p) {
+extern "C" int gmd_conv_gn_sums_ok(const gmd_conv_params* p) {
     using namespace gmd;
     if (!p || (p->ksize != 3 && p->ksize != 1) || p->N <= 0) return 0;
     int Wg = p->W, Hg = p->H, Wo = p->W, Ho = p->H;
@@ -1123,9 +1129,7 @@ extern "C" int64_t gmd_conv_gn_part_floats(const gmd_conv_params* p) {
     const int rows_w = p->w_tiled ? p->Cout : (p->Cout_pad > 0 ? p->Cout_pad : p->Cout);
     const int bnt = pick_bn(rows_w, false);
     const int ks = p->workspace ? conv_splitk_rule(Ho, Wo, num_kb, p->Cout, !p->upsample && p->stride == 1) : 1;
-    if (ks > 1 || bn != 1 || (Wg % bw) || (Hg % bh) || (p->Cout % bnt) || (bnt % 32)) return 0;
-    const int64_t tiles_m = (int64_t)(Wg / bw) * (Hg / bh) * p->N;
-    return (p->upsample ? 4 : 1) * tiles_m * 4 * p->Cout;      // [class][128-row block][lane group][Cout / 32][32]
+    return (ks > 1 || bn != 1 || (Wg % bw) || (Hg % bh) || (p->Cout % bnt) || (bnt % 32)) ? 0 : 1;
 }
 
 extern "C" int gmd_conv_fwd(const gmd_conv_params* p, void* stream) {
@@ -1277,12 +1281,12 @@ extern "C" int gmd_conv_fwd(const gmd_conv_params* p, void* stream) {
     const int64_t tiles_m = (int64_t)a.tiles_w * a.tiles_h * tiles_img, tiles_nn = (p->Cout + bnt - 1) / bnt;
     const int64_t rows = (int64_t)p->N * Ho * Wo;
     const int ks = p->workspace ? conv_splitk_rule(Ho, Wo, a.num_kb, p->Cout, !p->upsample && p->stride == 1) : 1;
-    if (p->gn_part) {
+    if (p->gn_sums) {
         // statistics come out of full 128-row tiles of ONE image each, written by the single-pass epilogue
         if (ks > 1 || bn != 1 || (Wg % bw) || (Hg % bh) || (p->Cout % bnt) || (bnt % 32)) {
-            set_last_error("gmd_conv_fwd: gn_part is not available for this call (see gmd_conv_gn_part_floats)"); return kErrUnsupported;
+            set_last_error("gmd_conv_fwd: gn_sums is not available for this call (see gmd_conv_gn_sums_ok)"); return kErrUnsupported;
         }
-        a.gn_part = p->gn_part; a.gn_ncb = p->Cout / 32; a.gn_tiles = (int)tiles_m;
+        a.gn_sums = static_cast<long long*>(p->gn_sums); a.gn_ncb = p->Cout / 32;
     }
     if (ks > 1) {
         // the fp32 partial planes of the whole batch must fit the workspace; otherwise run the batch in image chunks (whole tiles),

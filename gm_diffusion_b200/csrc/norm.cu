@@ -169,33 +169,13 @@ __global__ void __launch_bounds__(1024, 1) gn_apply_kernel(const T* __restrict__
 
 // ---------------------------------------------------------------------------------------------
 // GroupNorm with statistics from the PRODUCER's epilogue (north_star (b), include/gmd_b200.h "GroupNorm fused into the producing
-// convolution / GEMM"): gn_fold_kernel adds the epilogue's per-(32 rows x 2 channels) partials per (sample, channel pair) in a fixed
-// order; gn_apply_sums_kernel is one streaming pass (read, scale / shift, SiLU, write) whose statistics are formed from the
-// channel-pair sums of its one or two sources.  No statistics pass over the activation exists any more.
+// convolution / GEMM"): the producer's epilogue accumulates per-(sample, channel pair) sums as 64-bit fixed-point integers;
+// gn_apply_sums_kernel is one streaming pass (read, scale / shift, SiLU, write) whose statistics are formed from the channel-pair
+// sums of its one or two sources.  No statistics pass over the activation exists any more.
 // ---------------------------------------------------------------------------------------------
-// part: [class][sample][32-row block of the sample within the class][C / 32][32]  (lane L < 16: sum of channel pair cb*16 + L,
-// L >= 16: sum of squares of pair cb*16 + L - 16).  One warp per (sample, 32-channel chunk); lane L walks its column.
-__global__ void __launch_bounds__(256) gn_fold_kernel(const float* __restrict__ part, float* __restrict__ sums, int N, int r32, int ncb, int classes) {
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int cb = blockIdx.x * 8 + warp, n = blockIdx.y;
-    if (cb >= ncb) return;
-    float acc = 0.0f;
-    for (int z = 0; z < classes; ++z) {
-        const float* src = part + (((int64_t)z * N + n) * r32 * ncb + cb) * 32 + lane;
-        int j = 0;
-        for (; j + 3 < r32; j += 4) {
-            const float a0 = __ldcg(src + (int64_t)j * ncb * 32), a1 = __ldcg(src + (int64_t)(j + 1) * ncb * 32);
-            const float a2 = __ldcg(src + (int64_t)(j + 2) * ncb * 32), a3 = __ldcg(src + (int64_t)(j + 3) * ncb * 32);
-            acc += a0; acc += a1; acc += a2; acc += a3;
-        }
-        for (; j < r32; ++j) acc += __ldcg(src + (int64_t)j * ncb * 32);
-    }
-    sums[(((int64_t)n * ncb + cb) * 16 + (lane & 15)) * 2 + (lane >> 4)] = acc;
-}
-
 template <typename T>
-__global__ void __launch_bounds__(320) gn_apply_sums_kernel(const T* __restrict__ x0, int C0, const float* __restrict__ sums0,
-                                                            const __nv_bfloat16* __restrict__ x1, int C1, const float* __restrict__ sums1,
+__global__ void __launch_bounds__(320) gn_apply_sums_kernel(const T* __restrict__ x0, int C0, const long long* __restrict__ sums0,
+                                                            const __nv_bfloat16* __restrict__ x1, int C1, const long long* __restrict__ sums1,
                                                             const float* __restrict__ gamma, const float* __restrict__ beta,
                                                             __nv_bfloat16* __restrict__ out, int HW, int groups, int apply_silu, int px_per_cta, float eps) {
     __shared__ float s_stat[128];           // [groups][2] mean, rstd
@@ -217,15 +197,16 @@ __global__ void __launch_bounds__(320) gn_apply_sums_kernel(const T* __restrict_
         // group g = channels [g*cg, (g+1)*cg) = channel pairs [g*cg/2, (g+1)*cg/2) of the concatenation (cg is even); a pair lives
         // entirely in one source (C0 is even)
         const int g = threadIdx.x;
-        float s1 = 0.0f, s2 = 0.0f;
+        long long i1 = 0, i2 = 0;       // exact integer sums of the fixed-point accumulators
         for (int pr = g * cg / 2; pr < (g + 1) * cg / 2; ++pr) {
-            const float2 v = pr < C0 / 2 ? __ldcg(reinterpret_cast<const float2*>(sums0) + (int64_t)n * (C0 / 2) + pr)
-                                         : __ldcg(reinterpret_cast<const float2*>(sums1) + (int64_t)n * (C1 / 2) + (pr - C0 / 2));
-            s1 += v.x; s2 += v.y;
+            const longlong2 v = pr < C0 / 2 ? __ldcg(reinterpret_cast<const longlong2*>(sums0) + (int64_t)n * (C0 / 2) + pr)
+                                            : __ldcg(reinterpret_cast<const longlong2*>(sums1) + (int64_t)n * (C1 / 2) + (pr - C0 / 2));
+            i1 += v.x; i2 += v.y;
         }
-        const float inv_cnt = 1.0f / ((float)cg * (float)HW);
-        const float mean = s1 * inv_cnt;
-        const float var = fmaxf(s2 * inv_cnt - mean * mean, 0.0f);
+        const double inv_cnt = 1.0 / ((double)cg * (double)HW * 16777216.0);
+        const double dm = (double)i1 * inv_cnt;
+        const float mean = (float)dm;
+        const float var = fmaxf((float)((double)i2 * inv_cnt - dm * dm), 0.0f);
         s_stat[g * 2] = mean;
         s_stat[g * 2 + 1] = rsqrtf(var + eps);
     }
@@ -692,19 +673,7 @@ extern "C" int gmd_groupnorm_silu(const void* x0, int32_t C0, const void* x1, in
     return kErrInvalid;
 }
 
-extern "C" int gmd_gn_fold(const float* gn_part, float* sums, int32_t N, int64_t rows_per_sample, int32_t C, int32_t classes, void* stream) {
-    using namespace gmd;
-    if (!gn_part || !sums) { set_last_error("gmd_gn_fold: null pointer"); return kErrInvalid; }
-    if (N <= 0 || C <= 0 || (C % 32) || classes <= 0 || rows_per_sample <= 0 || (rows_per_sample % (32 * classes))) {
-        set_last_error("gmd_gn_fold: bad shape N=%d rows_per_sample=%lld C=%d classes=%d", N, (long long)rows_per_sample, C, classes); return kErrInvalid;
-    }
-    const int ncb = C / 32, r32 = (int)(rows_per_sample / classes / 32);
-    gn_fold_kernel<<<dim3((ncb + 7) / 8, N), 256, 0, static_cast<cudaStream_t>(stream)>>>(gn_part, sums, N, r32, ncb, classes);
-    count_launch(1);
-    return check_launch("gn_fold");
-}
-
-extern "C" int gmd_groupnorm_apply(const void* x0, int32_t C0, const float* sums0, const void* x1, int32_t C1, const float* sums1,
+extern "C" int gmd_groupnorm_apply(const void* x0, int32_t C0, const void* sums0, const void* x1, int32_t C1, const void* sums1,
                                    const float* gamma, const float* beta, void* out, int32_t N, int32_t HW, int32_t groups, float eps,
                                    int32_t apply_silu, int32_t in_dtype, void* stream) {
     using namespace gmd;
@@ -715,8 +684,8 @@ extern "C" int gmd_groupnorm_apply(const void* x0, int32_t C0, const float* sums
     if (C0 % 8 || C1 % 8 || groups <= 0 || groups > 64 || C % groups || ((C / groups) % 2) || N <= 0 || HW <= 0 || C / 8 > 320) {
         set_last_error("gmd_groupnorm_apply: bad shape C0=%d C1=%d groups=%d", C0, C1, groups); return kErrInvalid;
     }
-    if (!al16(x0) || !al16(x1) || !al16(out) || !al16(gamma) || !al16(beta) || (reinterpret_cast<uintptr_t>(sums0) & 7) || (reinterpret_cast<uintptr_t>(sums1) & 7)) {
-        set_last_error("gmd_groupnorm_apply: pointers must be 16-byte aligned (statistics: 8)"); return kErrInvalid;
+    if (!al16(x0) || !al16(x1) || !al16(out) || !al16(gamma) || !al16(beta) || !al16(sums0) || !al16(sums1)) {
+        set_last_error("gmd_groupnorm_apply: pointers must be 16-byte aligned"); return kErrInvalid;
     }
     const int nvec = C / 8;
     int P = 256 / nvec; if (P < 1) P = 1;
@@ -726,10 +695,10 @@ extern "C" int gmd_groupnorm_apply(const void* x0, int32_t C0, const float* sums
     const dim3 grid((HW + ppc - 1) / ppc, N);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     if (in_dtype == GMD_BF16)
-        gn_apply_sums_kernel<__nv_bfloat16><<<grid, threads, 0, st>>>(static_cast<const __nv_bfloat16*>(x0), C0, sums0, static_cast<const __nv_bfloat16*>(x1), C1, sums1,
+        gn_apply_sums_kernel<__nv_bfloat16><<<grid, threads, 0, st>>>(static_cast<const __nv_bfloat16*>(x0), C0, static_cast<const long long*>(sums0), static_cast<const __nv_bfloat16*>(x1), C1, static_cast<const long long*>(sums1),
                                                                       gamma, beta, static_cast<__nv_bfloat16*>(out), HW, groups, apply_silu, ppc, eps);
     else if (in_dtype == GMD_F32)
-        gn_apply_sums_kernel<float><<<grid, threads, 0, st>>>(static_cast<const float*>(x0), C0, sums0, static_cast<const __nv_bfloat16*>(x1), C1, sums1,
+        gn_apply_sums_kernel<float><<<grid, threads, 0, st>>>(static_cast<const float*>(x0), C0, static_cast<const long long*>(sums0), static_cast<const __nv_bfloat16*>(x1), C1, static_cast<const long long*>(sums1),
                                                               gamma, beta, static_cast<__nv_bfloat16*>(out), HW, groups, apply_silu, ppc, eps);
     else { set_last_error("gmd_groupnorm_apply: unknown in_dtype %d", in_dtype); return kErrInvalid; }
     count_launch(1);

@@ -77,33 +77,68 @@ def splitk_workspace(device) -> torch.Tensor:
     return ws
 
 
-_GN_PART = {}
 GN_EPILOGUE = __import__("os").environ.get("GMD_GN_EPILOGUE", "1") != "0"   # 0: statistics by the standalone GroupNorm kernel (A/B measurements)
+_GN_ARENA = {}
 
 
-def _gn_part_workspace(device, floats: int) -> torch.Tensor:
-    """Scratch for the epilogue's GroupNorm partials (consumed by gmd_gn_fold right behind the producer, in stream order).  Buffers
-    are never freed: a captured CUDA graph may hold their address."""
-    key = torch.device(device).index or 0
-    bufs = _GN_PART.setdefault(key, [])
-    if not bufs or bufs[-1].numel() < floats:
-        bufs.append(torch.empty(max(int(floats), 1 << 20), dtype=torch.float32, device=device))
-    return bufs[-1]
+class gn_arena:
+    """Zeroed int64 accumulators for the GroupNorm statistics the convolution / GEMM epilogues add into (gmd_b200.h "GroupNorm fused
+    into the producing convolution / GEMM"), bump-allocated from one static buffer per device and zeroed by ONE memset per forward
+    pass instead of one per tensor:
+
+        with ops.gn_arena(device, words_hint) as ar:   # zeroes words_hint words (everything, when the hint is None)
+            ... conv2d(..., gn_stats=True) ...
+        words_hint = ar.used
+
+    Outside such a block every statistics tensor is a fresh torch.zeros.  The buffer is static (CUDA-graph friendly)."""
+    WORDS = 4 << 20
+
+    def __init__(self, device, words_hint=None):
+        self.key = torch.device(device).index or 0
+        self.device, self.hint, self.used = device, words_hint, 0
+
+    def __enter__(self):
+        st = _GN_ARENA.setdefault(self.key, {"buf": None, "active": None})
+        if st["buf"] is None:
+            st["buf"] = torch.zeros(self.WORDS, dtype=torch.int64, device=self.device)
+        self.buf = st["buf"]
+        n = self.WORDS if self.hint is None else min(self.WORDS, int(self.hint))
+        if n > 0:
+            self.buf[:n].zero_()
+        self.zeroed = n
+        self.prev, st["active"] = st["active"], self
+        return self
+
+    def __exit__(self, *exc):
+        _GN_ARENA[self.key]["active"] = self.prev
+        return False
+
+    def alloc(self, n: int, c: int) -> torch.Tensor:
+        words = n * c                       # [n, c/2, 2]
+        if self.used + words > self.zeroed:
+            if self.used + words <= self.WORDS and self.zeroed < self.WORDS:
+                self.buf[self.zeroed:].zero_()          # the hint was too small (first pass at a larger batch): zero the rest
+                self.zeroed = self.WORDS
+            else:
+                return torch.zeros((n, c // 2, 2), dtype=torch.int64, device=self.device)
+        t = self.buf[self.used:self.used + words].view(n, c // 2, 2)
+        self.used += (words + 1) // 2 * 2   # keep 16-byte alignment
+        return t
 
 
-def _fold_gn(part: torch.Tensor, n: int, rows_per_sample: int, c: int, classes: int, device) -> torch.Tensor:
-    """Per-(sample, channel pair) sums [N, C/2, 2] (sum, sum of squares) from the producing kernel's partials."""
-    sums = torch.empty((n, c // 2, 2), dtype=torch.float32, device=device)
-    L.check(L.lib().gmd_gn_fold(part.data_ptr(), sums.data_ptr(), n, rows_per_sample, c, classes, L.current_stream()), "gmd_gn_fold")
-    return sums
+def _gn_sums_alloc(device, n: int, c: int) -> torch.Tensor:
+    st = _GN_ARENA.get(torch.device(device).index or 0)
+    if st is not None and st["active"] is not None:
+        return st["active"].alloc(n, c)
+    return torch.zeros((n, c // 2, 2), dtype=torch.int64, device=device)
 
 
 def gemm(a: torch.Tensor, w: torch.Tensor, *, bias: Optional[torch.Tensor] = None, residual: Optional[torch.Tensor] = None,
          row_bias: Optional[torch.Tensor] = None, rows_per_sample: int = 0, geglu: bool = False, out: Optional[torch.Tensor] = None,
          out_f32: bool = False, alpha: Optional[float] = None, splitk: bool = False, gn_rows_per_sample: int = 0):
     """out[M,N] = a[M,K] @ w[N,K]^T (+bias +row_bias[sample] +residual | GEGLU).  3-D inputs are batched.
-    `gn_rows_per_sample` > 0: also return the GroupNorm statistics of the output, formed in the epilogue (`(out, sums)`; sums is
-    None where the kernel cannot provide them)."""
+    `gn_rows_per_sample` > 0: also return the GroupNorm statistics of the output, accumulated by the epilogue (`(out, sums)`, sums
+    int64 fixed point [samples, N/2, 2]; None where the kernel cannot provide them)."""
     tiled = isinstance(w, TiledWeight)
     wt = w.data if tiled else w
     L.require_cuda(a, wt)
@@ -159,15 +194,13 @@ def gemm(a: torch.Tensor, w: torch.Tensor, *, bias: Optional[torch.Tensor] = Non
         # entry point uses a batch-independent rule instead and is on by default, see conv2d.)
         ws = splitk_workspace(a.device)
         p.workspace, p.workspace_bytes = ws.data_ptr(), ws.numel()
-    part = None
-    if gn_rows_per_sample > 0 and GN_EPILOGUE:
-        floats = int(L.lib().gmd_gemm_gn_part_floats(C.byref(p), gn_rows_per_sample))
-        if floats > 0:
-            part = _gn_part_workspace(a.device, floats)
-            p.gn_part = part.data_ptr()
+    sums = None
+    if gn_rows_per_sample > 0 and GN_EPILOGUE and L.lib().gmd_gemm_gn_sums_ok(C.byref(p), gn_rows_per_sample):
+        sums = _gn_sums_alloc(a.device, M // gn_rows_per_sample, N)
+        p.gn_sums, p.gn_rows_per_sample = sums.data_ptr(), gn_rows_per_sample
     L.check(L.lib().gmd_gemm_fwd(C.byref(p), L.current_stream()), "gmd_gemm_fwd")
     if gn_rows_per_sample > 0:
-        return out, (_fold_gn(part, M // gn_rows_per_sample, gn_rows_per_sample, N, 1, a.device) if part is not None else None)
+        return out, sums
     return out
 
 
@@ -177,8 +210,8 @@ def conv2d(x: torch.Tensor, w: torch.Tensor, cout: int, *, ksize: int = 3, strid
            pad_end: bool = False, gn_stats: bool = False):
     """NHWC bf16 convolution as implicit GEMM (3x3 pad 1 stride 1/2, optional folded nearest-2x upsample).  `pad_end` (stride 2):
     the AutoencoderKL encoder's asymmetric padding — no leading pad, one zero row/column at the bottom/right.
-    `gn_stats`: also return the GroupNorm statistics of the output, formed in the epilogue (`(out, sums)`; sums is None where the
-    kernel cannot provide them: split-K layers, ragged tiles)."""
+    `gn_stats`: also return the GroupNorm statistics of the output, accumulated by the epilogue (`(out, sums)`, sums int64 fixed
+    point [N, Cout/2, 2]; None where the kernel cannot provide them: split-K layers, ragged tiles, images smaller than a tile)."""
     tiled = isinstance(w, TiledWeight)
     wt = w.data if tiled else w
     L.require_cuda(x, wt)
@@ -226,15 +259,13 @@ def conv2d(x: torch.Tensor, w: torch.Tensor, cout: int, *, ksize: int = 3, strid
         # profiles/prof_splitk.py); the rule looks only at the per-image geometry, so results do not depend on the batch
         ws = splitk_workspace(x.device)
         p.workspace, p.workspace_bytes = ws.data_ptr(), ws.numel()
-    part = None
-    if gn_stats and GN_EPILOGUE:
-        floats = int(L.lib().gmd_conv_gn_part_floats(C.byref(p)))
-        if floats > 0:
-            part = _gn_part_workspace(x.device, floats)
-            p.gn_part = part.data_ptr()
+    sums = None
+    if gn_stats and GN_EPILOGUE and L.lib().gmd_conv_gn_sums_ok(C.byref(p)):
+        sums = _gn_sums_alloc(x.device, N, cout)
+        p.gn_sums = sums.data_ptr()
     L.check(L.lib().gmd_conv_fwd(C.byref(p), L.current_stream()), "gmd_conv_fwd")
     if gn_stats:
-        return out, (_fold_gn(part, N, Ho * Wo, cout, 4 if upsample else 1, x.device) if part is not None else None)
+        return out, sums
     return out
 
 

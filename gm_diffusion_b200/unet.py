@@ -242,35 +242,39 @@ class B200UNet:
         temb_all = temb_row if temb_row.shape[0] == full else temb_row.expand(full, -1)
         ws = self._gn_ws
         kv = iter(context_kv)
-        x, xs = ops.conv2d(sample, self.w_in, self.ch0, bias=self.b_in, gn_stats=True)
-        dup2 = lambda t_: None if t_ is None else torch.cat([t_, t_], 0)
-        skips = [(dup2(x), dup2(xs)) if cfg_shared else (x, xs)]       # every activation travels with its GroupNorm statistics
-        pending_dup = cfg_shared
-        for res, att, ds in self.down:
-            for r, a in zip(res, att):
-                x, xs = r(x, None, temb_all[: x.shape[0]], ws, xs=xs)
-                if a is not None:
-                    x, xs = a(x, next(kv), ws, dup=pending_dup, xs=xs)
-                    pending_dup = False
-                elif pending_dup:
-                    raise NotImplementedError("cfg_shared needs an attention block after the first resnet")
-                skips.append((x, xs))
-            if ds is not None:
-                x, xs = ops.conv2d(x, ds[0], ds[0].shape[0], stride=2, bias=ds[1], gn_stats=True)
-                skips.append((x, xs))
-        x, xs = self.mid_res[0](x, None, temb_all, ws, xs=xs)
-        x, xs = self.mid_att(x, next(kv), ws, xs=xs)
-        x, xs = self.mid_res[1](x, None, temb_all, ws, xs=xs)
-        for res, att, us in self.up:
-            for r, a in zip(res, att):
-                sk, sks = skips.pop()
-                x, xs = r(x, sk, temb_all, ws, xs=xs, skip_s=sks)
-                if a is not None:
-                    x, xs = a(x, next(kv), ws, xs=xs)
-            if us is not None:
-                x, xs = ops.conv2d(x, us[0], us[0].shape[0], upsample=True, bias=us[1], gn_stats=True)
-        x = ops.groupnorm_silu(x, *self.n_out, eps=1e-5, stats_ws=ws, sums=xs)
-        return ops.conv2d(x, self.w_out, self.out_channels, bias=self.b_out, out=out, out_f32=True)
+        hints = self.__dict__.setdefault("_gn_words", {})
+        with ops.gn_arena(self.device, hints.get((full, sample.shape[1], sample.shape[2]))) as arena:   # one memset zeroes every GroupNorm accumulator of the pass
+            x, xs = ops.conv2d(sample, self.w_in, self.ch0, bias=self.b_in, gn_stats=True)
+            dup2 = lambda t_: None if t_ is None else torch.cat([t_, t_], 0)
+            skips = [(dup2(x), dup2(xs)) if cfg_shared else (x, xs)]       # every activation travels with its GroupNorm statistics
+            pending_dup = cfg_shared
+            for res, att, ds in self.down:
+                for r, a in zip(res, att):
+                    x, xs = r(x, None, temb_all[: x.shape[0]], ws, xs=xs)
+                    if a is not None:
+                        x, xs = a(x, next(kv), ws, dup=pending_dup, xs=xs)
+                        pending_dup = False
+                    elif pending_dup:
+                        raise NotImplementedError("cfg_shared needs an attention block after the first resnet")
+                    skips.append((x, xs))
+                if ds is not None:
+                    x, xs = ops.conv2d(x, ds[0], ds[0].shape[0], stride=2, bias=ds[1], gn_stats=True)
+                    skips.append((x, xs))
+            x, xs = self.mid_res[0](x, None, temb_all, ws, xs=xs)
+            x, xs = self.mid_att(x, next(kv), ws, xs=xs)
+            x, xs = self.mid_res[1](x, None, temb_all, ws, xs=xs)
+            for res, att, us in self.up:
+                for r, a in zip(res, att):
+                    sk, sks = skips.pop()
+                    x, xs = r(x, sk, temb_all, ws, xs=xs, skip_s=sks)
+                    if a is not None:
+                        x, xs = a(x, next(kv), ws, xs=xs)
+                if us is not None:
+                    x, xs = ops.conv2d(x, us[0], us[0].shape[0], upsample=True, bias=us[1], gn_stats=True)
+            x = ops.groupnorm_silu(x, *self.n_out, eps=1e-5, stats_ws=ws, sums=xs)
+            eps = ops.conv2d(x, self.w_out, self.out_channels, bias=self.b_out, out=out, out_f32=True)
+        hints[(full, sample.shape[1], sample.shape[2])] = max(arena.used, hints.get((full, sample.shape[1], sample.shape[2]), 0))
+        return eps
 
     __call__ = forward
 

@@ -116,18 +116,22 @@ class B200VaeDecoder:
         L.check(L.lib().gmd_pack_unet_input(latents_px.data_ptr(), None, z.data_ptr(), n_px, 8, L.current_stream()), "gmd_pack_unet_input")
         z = ops.gemm(z, self.w_pq, bias=self.b_pq).view(B, h, w, 8)
         ws = self._gn_ws
-        # every activation travels with the GroupNorm statistics its producer's epilogue formed (None where unavailable)
-        x, xs = ops.conv2d(z, self.w_in, self.c_mid, bias=self.b_in, gn_stats=True)
-        x, xs = self.mid_res[0](x, None, None, ws, xs=xs)
-        x, xs = self._attention(x, xs)
-        x, xs = self.mid_res[1](x, None, None, ws, xs=xs)
-        for res, us in self.ups:
-            for r in res:
-                x, xs = r(x, None, None, ws, xs=xs)
-            if us is not None:
-                x, xs = ops.conv2d(x, us[0], us[0].shape[0], upsample=True, bias=us[1], gn_stats=True)
-        x = ops.groupnorm_silu(x, *self.n_out, eps=1e-6, stats_ws=ws, sums=xs)
-        return ops.conv2d(x, self.w_out, self.w_out.shape[0], bias=self.b_out)
+        hints = self.__dict__.setdefault("_gn_words", {})
+        with ops.gn_arena(self.device, hints.get(("dec", B, h, w))) as arena:   # one memset zeroes every GroupNorm accumulator of the pass
+            # every activation travels with the GroupNorm statistics its producer's epilogue formed (None where unavailable)
+            x, xs = ops.conv2d(z, self.w_in, self.c_mid, bias=self.b_in, gn_stats=True)
+            x, xs = self.mid_res[0](x, None, None, ws, xs=xs)
+            x, xs = self._attention(x, xs)
+            x, xs = self.mid_res[1](x, None, None, ws, xs=xs)
+            for res, us in self.ups:
+                for r in res:
+                    x, xs = r(x, None, None, ws, xs=xs)
+                if us is not None:
+                    x, xs = ops.conv2d(x, us[0], us[0].shape[0], upsample=True, bias=us[1], gn_stats=True)
+            x = ops.groupnorm_silu(x, *self.n_out, eps=1e-6, stats_ws=ws, sums=xs)
+            img = ops.conv2d(x, self.w_out, self.w_out.shape[0], bias=self.b_out)
+        hints[("dec", B, h, w)] = max(arena.used, hints.get(("dec", B, h, w), 0))
+        return img
 
     @torch.no_grad()
     @L.on_own_device
@@ -234,17 +238,21 @@ class B200Vae(B200VaeDecoder):
         x = torch.empty((B, H, W, 8), dtype=bf16, device=self.device)
         L.check(L.lib().gmd_pack_image_nchw(img.data_ptr(), x.data_ptr(), B, H * W, 3, L.current_stream()), "gmd_pack_image_nchw")
         ws = self._gn_ws
-        x, xs = ops.conv2d(x, self.e_w_in, self.e_c0, bias=self.e_b_in, gn_stats=True)
-        for res, ds in self.e_downs:
-            for r in res:
-                x, xs = r(x, None, None, ws, xs=xs)
-            if ds is not None:
-                x, xs = ops.conv2d(x, ds[0], ds[0].shape[0], stride=2, pad_end=True, bias=ds[1], gn_stats=True)
-        x, xs = self.e_mid_res[0](x, None, None, ws, xs=xs)
-        x, xs = self.e_attn(x, ws, xs)
-        x, xs = self.e_mid_res[1](x, None, None, ws, xs=xs)
-        x = ops.groupnorm_silu(x, *self.e_n_out, eps=1e-6, stats_ws=ws, sums=xs)
-        return ops.conv2d(x, self.e_w_out, 8, bias=self.e_b_out, out_f32=True)
+        hints = self.__dict__.setdefault("_gn_words", {})
+        with ops.gn_arena(self.device, hints.get(("enc", B, H, W))) as arena:
+            x, xs = ops.conv2d(x, self.e_w_in, self.e_c0, bias=self.e_b_in, gn_stats=True)
+            for res, ds in self.e_downs:
+                for r in res:
+                    x, xs = r(x, None, None, ws, xs=xs)
+                if ds is not None:
+                    x, xs = ops.conv2d(x, ds[0], ds[0].shape[0], stride=2, pad_end=True, bias=ds[1], gn_stats=True)
+            x, xs = self.e_mid_res[0](x, None, None, ws, xs=xs)
+            x, xs = self.e_attn(x, ws, xs)
+            x, xs = self.e_mid_res[1](x, None, None, ws, xs=xs)
+            x = ops.groupnorm_silu(x, *self.e_n_out, eps=1e-6, stats_ws=ws, sums=xs)
+            mom = ops.conv2d(x, self.e_w_out, 8, bias=self.e_b_out, out_f32=True)
+        hints[("enc", B, H, W)] = max(arena.used, hints.get(("enc", B, H, W), 0))
+        return mom
 
     @torch.no_grad()
     @L.on_own_device

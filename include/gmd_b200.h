@@ -206,8 +206,8 @@ typedef struct gmd_gemm_params {
                                           * every operand tile is then one contiguous DRAM read instead of T strided 128-byte rows.
                                           * 1000 + T: the tiles are additionally stored as the SWIZZLE_128B shared-memory image (16-byte chunk c of
                                           * row r at chunk c ^ (r & 7)) and fetched with ONE 1-D bulk copy per tile instead of T tensor rows */
-    float* gn_part;                      /* optional: GroupNorm statistics of the OUTPUT from the epilogue (see gmd_gn_fold); NULL = none.
-                                          * gmd_gemm_gn_part_floats(p) floats, or unsupported (0) for this shape */
+    void* gn_sums;                       /* optional: GroupNorm statistics of the OUTPUT accumulated by the epilogue (see below); NULL = none */
+    int64_t gn_rows_per_sample;          /* with gn_sums: output rows of one sample (a multiple of 128) */
 } gmd_gemm_params;
 
 int gmd_gemm_fwd(const gmd_gemm_params* p, void* stream);
@@ -232,26 +232,24 @@ typedef struct gmd_conv_params {
     void* workspace;                     /* optional fp32 scratch for split-K (8x8-resolution layers); NULL disables it */
     int64_t workspace_bytes;
     int32_t w_tiled;                     /* as gmd_gemm_params.w_tiled; k blocks ordered (tap, 64-channel chunk of x0 then x1), channels zero padded */
-    float* gn_part;                      /* optional: GroupNorm statistics of the OUTPUT from the epilogue (see gmd_gn_fold); NULL = none.
-                                          * gmd_conv_gn_part_floats(p) floats, or unsupported (0) for this shape */
+    void* gn_sums;                       /* optional: GroupNorm statistics of the OUTPUT accumulated by the epilogue (see below); NULL = none */
 } gmd_conv_params;
 
 int gmd_conv_fwd(const gmd_conv_params* p, void* stream);
 
 /* ---- GroupNorm fused into the producing convolution / GEMM (north_star (b); replaces the statistics pass of gmd_groupnorm_silu) ----
- * The epilogue of gmd_conv_fwd / gmd_gemm_fwd, which holds every output value in registers anyway, also emits per-(32 output rows x
- * 2 channels) partial sums and sums of squares into `gn_part` (one 128-byte store per warp and 32-column chunk, warp-shuffle
- * transpose-reduce, no atomics).  gmd_gn_fold adds them per (sample, channel pair) in a fixed order -> `sums` [N][C/2][2] fp32, which
- * any consumer grouping can use (the up-block GroupNorms normalise a concat of two producers whose 32 groups straddle the sources).
- * gmd_groupnorm_apply is then ONE streaming pass: scale / shift (+ SiLU) with statistics formed from the `sums` of its one or two
- * sources.  Deterministic and independent of the batch size like the kernels they replace.
- * The *_gn_part_floats functions return the number of floats `gn_part` must hold, or 0 when this call cannot emit statistics
- * (split-K convolutions, ragged tiles, GEGLU / batched GEMMs): the caller then keeps gmd_groupnorm_silu for that tensor. */
-int64_t gmd_conv_gn_part_floats(const gmd_conv_params* p);
-int64_t gmd_gemm_gn_part_floats(const gmd_gemm_params* p, int64_t rows_per_sample);
-/* classes = 4 for an upsampling convolution (its four output-parity classes), else 1; rows_per_sample = output pixels per sample */
-int gmd_gn_fold(const float* gn_part, float* sums, int32_t N, int64_t rows_per_sample, int32_t C, int32_t classes, void* stream);
-int gmd_groupnorm_apply(const void* x0, int32_t C0, const float* sums0, const void* x1, int32_t C1, const float* sums1,
+ * The epilogue of gmd_conv_fwd / gmd_gemm_fwd, which holds every output value in registers anyway, also accumulates per (sample,
+ * channel pair) the sum and the sum of squares of its output into `gn_sums` [N][C/2][2] int64: each warp transpose-reduces its 32
+ * rows x 32 columns with shuffles and adds 32 totals as FIXED-POINT integers (units of 2^-24) with 64-bit atomics.  Integer addition
+ * is associative, so the result is bit-reproducible and independent of tile order and batch size — no partial buffers, no fold pass.
+ * The caller zeroes `gn_sums` beforehand.  Channel pairs serve any consumer grouping (the up-block GroupNorms normalise a concat of
+ * two producers whose 32 groups straddle the sources).  gmd_groupnorm_apply is then ONE streaming pass over the activation:
+ * scale / shift (+ SiLU) with statistics formed from the sums of its one or two sources.
+ * The *_gn_sums_ok functions say whether a call can emit statistics (no: split-K convolutions, ragged tiles, samples smaller than a
+ * 128-row tile, GEGLU / batched GEMMs); the caller then keeps gmd_groupnorm_silu for that tensor. */
+int gmd_conv_gn_sums_ok(const gmd_conv_params* p);
+int gmd_gemm_gn_sums_ok(const gmd_gemm_params* p, int64_t rows_per_sample);
+int gmd_groupnorm_apply(const void* x0, int32_t C0, const void* sums0, const void* x1, int32_t C1, const void* sums1,
                         const float* gamma, const float* beta, void* out, int32_t N, int32_t HW, int32_t groups, float eps,
                         int32_t apply_silu, int32_t in_dtype, void* stream);
 

@@ -348,7 +348,9 @@ def test_groupnorm_statistics_from_the_producer_epilogue(case):
     assert sums is not None and sums.shape == (N, 320, 2), "this shape must take the epilogue-statistics path"
     y3 = y.float().reshape(N, -1, 640)
     want = torch.stack([y3.reshape(N, -1, 320, 2).sum((1, 3)), (y3 ** 2).reshape(N, -1, 320, 2).sum((1, 3))], -1)
-    err = (sums - want).abs().max() / want.abs().max()
+    assert sums.dtype == torch.int64                     # fixed point, units of 2^-24: integer atomics are order-independent
+    fsums = sums.double().cpu() / 2 ** 24
+    err = (fsums - want.double().cpu()).abs().max() / want.abs().max()
     assert float(err) < 2e-3, f"{case}: epilogue statistics vs sums over the stored output: {float(err):.2e}"   # (formed before the bf16 rounding of the output)
     ga, be = torch.randn(640, generator=g).cuda(), torch.randn(640, generator=g).cuda()
     got = ops.groupnorm_silu(y.reshape(N, -1, 640), ga, be, eps=1e-5, sums=sums)
@@ -361,7 +363,7 @@ def test_groupnorm_statistics_from_the_producer_epilogue(case):
     # consumer of a concat whose groups straddle the two sources (640 + 320 channels: groups of 30)
     n_px = y3.shape[1]
     z = torch.randn(N, n_px, 320, generator=g).to(bf).cuda()
-    zs = torch.stack([z.float().reshape(N, n_px, 160, 2).sum((1, 3)), (z.float() ** 2).reshape(N, n_px, 160, 2).sum((1, 3))], -1).contiguous()
+    zs = (torch.stack([z.double().reshape(N, n_px, 160, 2).sum((1, 3)), (z.double() ** 2).reshape(N, n_px, 160, 2).sum((1, 3))], -1) * 2 ** 24).round().long().contiguous()
     ga2, be2 = torch.randn(960, generator=g).cuda(), torch.randn(960, generator=g).cuda()
     if y.dtype == bf:
         got2 = ops.groupnorm_silu(y.reshape(N, n_px, 640), ga2, be2, x1=z, sums=sums, sums1=zs)
