@@ -641,7 +641,7 @@ struct Cfg2 {
     static constexpr int TM_O = NQT * CH_COLS;
     static constexpr int TMEM_USED = TM_O + NQT * DPV;
     static constexpr uint32_t TMEM_COLS = TMEM_USED <= 128 ? 128 : TMEM_USED <= 256 ? 256 : 512;
-    static constexpr int MIN_CTAS = TMEM_COLS <= 256 ? 2 : 1;
+    static constexpr int MIN_CTAS = TMEM_COLS <= 128 ? 4 : TMEM_COLS <= 256 ? 2 : 1;
     static constexpr int QT_BYTES = NDB * BQ * 128;         // one query tile
     static constexpr int Q_BYTES = NQT * QT_BYTES;
     static constexpr int KV_BLOCK_BYTES = BKV * 128;        // one d block of a K or V tile
@@ -1302,7 +1302,7 @@ extern "C" int gmd_attn_fwd(const gmd_attn_params* p, void* stream) {
     switch (p->d) {
         case 40:
             if (xattn) return launch_x<40>(p, st);
-            if (v2) return g_attn2_cfg40 == 1 ? launch2<40, 64, 2, true, 1, 1, 3>(p, st) : launch2<40, 64, 1, false, 2, 2, 3>(p, st);
+            if (v2) return g_attn2_cfg40 == 1 ? launch2<40, 64, 2, true, 1, 1, 3>(p, st) : g_attn2_cfg40 == 2 ? launch2<40, 64, 1, true, 1, 1, 2>(p, st) : launch2<40, 64, 1, false, 2, 2, 3>(p, st);
             return p->Nk <= 2 * BKV ? launch<40, true>(p, st) : launch<40, false>(p, st);
         case 80:
             if (xattn) return launch_x<80>(p, st);
