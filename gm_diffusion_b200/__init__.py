@@ -12,8 +12,9 @@ from .pipelines import (StableDiffusionDualUNetImprovedPipeline, StableDiffusion
 from .schedulers import DDIMScheduler, DDPMScheduler, DPMSolverMultistepScheduler, PNDMScheduler
 from .unet import B200UNet
 from .vae import B200Vae, B200VaeDecoder
+from .text_encoder import B200ClipTextEncoder
 
 __version__ = "0.1.0"
 __all__ = ["RandomExposureAdjust", "apply_gm_to_sdr", "fix_mulog_tmo", "gamut_compress", "hard_clip_tmo", "linear_scale_tmo", "random_tmo_cuda",
            "tmo_cuda", "reconstruct_hdr", "reconstruct_for_disk", "rgbe_encode", "save_hdr_image", "pack_radiance", "StableDiffusionDualUNetPipeline", "StableDiffusionDualUNetImprovedPipeline",
-           "StableDiffusionGMPipeline", "PNDMScheduler", "DDIMScheduler", "DDPMScheduler", "DPMSolverMultistepScheduler", "B200UNet", "B200VaeDecoder", "B200Vae"]
+           "StableDiffusionGMPipeline", "PNDMScheduler", "DDIMScheduler", "DDPMScheduler", "DPMSolverMultistepScheduler", "B200UNet", "B200VaeDecoder", "B200Vae", "B200ClipTextEncoder"]

@@ -136,6 +136,7 @@ def lib() -> C.CDLL:
     L.gmd_groupnorm_silu.argtypes = [_vp, _i32, _vp, _i32, _vp, _vp, _vp, _i32, _i32, _i32, _f32, _i32, _i32, _vp, _vp]
     L.gmd_layernorm.argtypes = [_vp, _vp, _vp, _vp, _i64, _i32, _f32, _i32, _vp]
     L.gmd_softmax_rows.argtypes = [_vp, _vp, _i64, _i64, _f32, _vp]
+    L.gmd_softmax_rows_masked.argtypes = [_vp, _vp, _i64, _i64, _f32, _i32, _i32, _vp]
     L.gmd_timestep_embedding.argtypes = [_f32, _vp, _i32, _i32, _vp]
     L.gmd_silu.argtypes = [_vp, _vp, _i64, _vp]
     L.gmd_attn_fwd.argtypes = [C.POINTER(AttnParams), _vp]

@@ -523,16 +523,19 @@ __global__ void __launch_bounds__(256) layernorm_f32_exact_kernel(const float* _
 // Row softmax (bf16 in/out, fp32 math): one CTA per row, three passes (the row stays in L1/L2).
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) softmax_rows_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ out,
-                                                           int64_t N, float scale) {
+                                                           int64_t N, float scale, int n_valid, int causal_period) {
+    // columns >= n_valid (padding of the key dimension) and, with causal_period > 0, columns > (row % causal_period) (CLIP's causal
+    // text attention: one causal_period x causal_period matrix per head) get probability 0
     __shared__ float red[32];
     const __nv_bfloat16* xr = x + blockIdx.x * N;
     __nv_bfloat16* orow = out + blockIdx.x * N;
     const int nvec = (int)(N / 8);
+    const int lim = causal_period > 0 ? min(n_valid, (int)(blockIdx.x % causal_period) + 1) : n_valid;
     float mx = -INFINITY;
     for (int i = threadIdx.x; i < nvec; i += blockDim.x) {
         float f[8]; unpack8(__ldg(reinterpret_cast<const uint4*>(xr) + i), f);
 #pragma unroll
-        for (int k = 0; k < 8; ++k) mx = fmaxf(mx, f[k]);
+        for (int k = 0; k < 8; ++k) if (i * 8 + k < lim) mx = fmaxf(mx, f[k]);
     }
     auto block_reduce = [&](float v, bool is_max) {
 #pragma unroll
@@ -550,14 +553,14 @@ __global__ void __launch_bounds__(256) softmax_rows_kernel(const __nv_bfloat16* 
     for (int i = threadIdx.x; i < nvec; i += blockDim.x) {
         float f[8]; unpack8(__ldg(reinterpret_cast<const uint4*>(xr) + i), f);
 #pragma unroll
-        for (int k = 0; k < 8; ++k) sum += exp2f((f[k] - mx) * sl2);
+        for (int k = 0; k < 8; ++k) if (i * 8 + k < lim) sum += exp2f((f[k] - mx) * sl2);
     }
     sum = block_reduce(sum, false);
     const float inv = 1.0f / sum;
     for (int i = threadIdx.x; i < nvec; i += blockDim.x) {
         float f[8]; unpack8(__ldg(reinterpret_cast<const uint4*>(xr) + i), f);
 #pragma unroll
-        for (int k = 0; k < 8; ++k) f[k] = exp2f((f[k] - mx) * sl2) * inv;
+        for (int k = 0; k < 8; ++k) f[k] = i * 8 + k < lim ? exp2f((f[k] - mx) * sl2) * inv : 0.0f;
         reinterpret_cast<uint4*>(orow)[i] = pack8(f);
     }
 }
@@ -736,9 +739,18 @@ extern "C" int gmd_softmax_rows(const void* x, void* out, int64_t M, int64_t N, 
     using namespace gmd;
     if (!x || !out || N % 8 || !al16(x) || !al16(out)) { set_last_error("gmd_softmax_rows: bad arguments"); return kErrInvalid; }
     if (M == 0 || N == 0) return kOk;
-    softmax_rows_kernel<<<(unsigned)M, 256, 0, static_cast<cudaStream_t>(stream)>>>(static_cast<const __nv_bfloat16*>(x), static_cast<__nv_bfloat16*>(out), N, scale);
+    softmax_rows_kernel<<<(unsigned)M, 256, 0, static_cast<cudaStream_t>(stream)>>>(static_cast<const __nv_bfloat16*>(x), static_cast<__nv_bfloat16*>(out), N, scale, (int)N, 0);
     count_launch(1);
     return check_launch("softmax_rows");
+}
+
+extern "C" int gmd_softmax_rows_masked(const void* x, void* out, int64_t M, int64_t N, float scale, int32_t n_valid, int32_t causal_period, void* stream) {
+    using namespace gmd;
+    if (!x || !out || N % 8 || !al16(x) || !al16(out) || n_valid <= 0 || n_valid > N || causal_period < 0) { set_last_error("gmd_softmax_rows_masked: bad arguments"); return kErrInvalid; }
+    if (M == 0 || N == 0) return kOk;
+    softmax_rows_kernel<<<(unsigned)M, 256, 0, static_cast<cudaStream_t>(stream)>>>(static_cast<const __nv_bfloat16*>(x), static_cast<__nv_bfloat16*>(out), N, scale, n_valid, causal_period);
+    count_launch(1);
+    return check_launch("softmax_rows_masked");
 }
 
 extern "C" int gmd_timestep_embedding(float t, void* out, int32_t B, int32_t dim, void* stream) {

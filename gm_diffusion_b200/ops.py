@@ -312,12 +312,18 @@ def layernorm(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, eps: flo
     return out
 
 
-def softmax_rows(x: torch.Tensor, scale: float, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+def softmax_rows(x: torch.Tensor, scale: float, out: Optional[torch.Tensor] = None, n_valid: Optional[int] = None, causal_period: int = 0) -> torch.Tensor:
+    """softmax(scale * x) over the last dim (bf16).  `n_valid`: columns beyond it are key padding (probability 0); `causal_period` > 0:
+    row r additionally sees only columns <= r % causal_period (one causal matrix of that many rows per head)."""
     L.require_cuda(x)
     N = x.shape[-1]
     if out is None:
         out = torch.empty_like(x)
-    L.check(L.lib().gmd_softmax_rows(x.data_ptr(), out.data_ptr(), x.numel() // N, N, float(scale), L.current_stream()), "gmd_softmax_rows")
+    if n_valid is None and causal_period == 0:
+        L.check(L.lib().gmd_softmax_rows(x.data_ptr(), out.data_ptr(), x.numel() // N, N, float(scale), L.current_stream()), "gmd_softmax_rows")
+    else:
+        L.check(L.lib().gmd_softmax_rows_masked(x.data_ptr(), out.data_ptr(), x.numel() // N, N, float(scale), int(n_valid or N), int(causal_period),
+                                                L.current_stream()), "gmd_softmax_rows_masked")
     return out
 
 

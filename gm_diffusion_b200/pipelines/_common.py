@@ -70,6 +70,18 @@ def as_b200_vae(vae, device) -> Optional[B200VaeDecoder]:
     raise TypeError(f"vae must be a B200VaeDecoder or expose a diffusers-style state_dict(), got {type(vae)}")
 
 
+def as_b200_text_encoder(text_encoder, device):
+    """transformers' CLIPTextModel (the only text encoder the reference pipelines are built with, dual_unet.py:19,211) -> the same
+    network on this library's kernels.  Anything else (None, an already converted encoder, a caller's own
+    callable) is kept as it is."""
+    from ..text_encoder import B200ClipTextEncoder
+    if text_encoder is None or isinstance(text_encoder, B200ClipTextEncoder):
+        return text_encoder
+    if type(text_encoder).__name__ == "CLIPTextModel" and hasattr(text_encoder, "state_dict"):
+        return B200ClipTextEncoder.from_module(text_encoder, device=device)
+    return text_encoder
+
+
 def as_b200_scheduler(scheduler):
     """Accept our schedulers, or any object with a diffusers scheduler `config` whose class name we support."""
     if isinstance(scheduler, (S.PNDMScheduler, S.DDIMScheduler, S.DDPMScheduler, S.DPMSolverMultistepScheduler)):
@@ -126,6 +138,15 @@ class PipelineBase:
     # The reference scripts swap the scheduler AFTER construction (`pipeline.scheduler = DPMSolverMultistepScheduler.from_config(
     # pipeline.scheduler.config)`: formal_improved.py:195, rebuttal_r2q2.py:195, formal_improved_ablation.py:195, rebuttal_visual.py:270):
     # every assignment goes through the same conversion as the constructor argument.
+    @property
+    def text_encoder(self):
+        return self._text_encoder
+
+    @text_encoder.setter
+    def text_encoder(self, value):
+        self._text_encoder = as_b200_text_encoder(value, getattr(self, "device", "cuda"))
+        self.__dict__.pop("_text_cache", None)
+
     @property
     def scheduler(self):
         return self._scheduler

@@ -267,6 +267,9 @@ int gmd_timestep_embedding(float t, void* out, int32_t B, int32_t dim, void* str
 int gmd_silu(const void* x, void* out, int64_t n, void* stream);
 /* row softmax over bf16 [M, N] with scale (VAE mid-block attention) */
 int gmd_softmax_rows(const void* x, void* out, int64_t M, int64_t N, float scale, void* stream);
+/* as gmd_softmax_rows with columns >= n_valid (key padding) and, for causal_period > 0, columns > (row % causal_period) masked to 0:
+ * the causal text attention of the CLIP text encoder (one causal_period x causal_period score matrix per head) */
+int gmd_softmax_rows_masked(const void* x, void* out, int64_t M, int64_t N, float scale, int32_t n_valid, int32_t causal_period, void* stream);
 
 /* ------------------------------------------------------------------------------------------ */
 /* (a) attention: softmax(Q K^T * scale) V, tcgen05 + TMEM + TMA, streaming softmax            */
