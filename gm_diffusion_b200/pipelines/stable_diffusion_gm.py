@@ -23,6 +23,8 @@ class StableDiffusionGMPipeline(PipelineBase):
         if self.unet.in_channels != 8:
             raise ValueError(f"StableDiffusionGMPipeline expects the 8-channel GM UNet, got in_channels={self.unet.in_channels}")
         self._ws: Dict[Any, dict] = {}
+        self._loop_graphs: Dict[Any, Any] = {}
+        self.use_loop_graph = True   # capture the whole denoising loop as one CUDA graph when nothing needs the host between steps
 
     @torch.no_grad()
     @L.on_own_device
@@ -122,33 +124,64 @@ class StableDiffusionGMPipeline(PipelineBase):
                 a.copy_(b)
         ts = [int(t) for t in timesteps]
         table = self.unet.timestep_table(ts)
-        run = self._unet_runner(("gm1", B, h, w, do_cfg), self.unet, ws["unet_in"], ws["temb"], ws["kv"], ws["eps"], cfg_shared=do_cfg)
         extra = self.prepare_extra_step_kwargs(generator, eta)
+        # the whole loop as one CUDA graph when nothing needs the host between steps (same rule as the dual pipeline,
+        # stable_diffusion_dual_unet.py here): no callbacks, no per-step ancestral noise
+        stochastic = isinstance(self.scheduler, S.DDPMScheduler) or (isinstance(self.scheduler, S.DDIMScheduler) and extra["eta"] > 0)
+        loop_graph_ok = self.use_cuda_graph and self.use_loop_graph and callback_on_step_end is None and not stochastic
+        if loop_graph_ok:
+            run = lambda: self.unet.forward(ws["unet_in"], ws["temb"], ws["kv"], out=ws["eps"], cfg_shared=do_cfg)
+        else:
+            run = self._unet_runner(("gm1", B, h, w, do_cfg), self.unet, ws["unet_in"], ws["temb"], ws["kv"], ws["eps"], cfg_shared=do_cfg)
         eps_u = ws["eps"][:B].reshape(-1, 4) if do_cfg else None
         eps_c = (ws["eps"][B:] if do_cfg else ws["eps"]).reshape(-1, 4)
-        for i, t in enumerate(ts):  # gm.py:1040-1091
-            if self.interrupt:
-                continue
-            ws["temb"].copy_(table[i:i + 1])
-            run()
-            plan = self.scheduler.plan_step(t, extra["eta"])
-            if plan.needs_noise:
-                z = torch.randn((B, 4, h, w), generator=generator, device=device if generator is None or generator.device.type == "cuda" else "cpu").to(device)
-                st.noise = torch.empty(n_px, 4, dtype=torch.float32, device=device)
-                L.check(L.lib().gmd_latents_nchw_to_px(z.contiguous().data_ptr(), st.noise.data_ptr(), B, h * w, stream))
-            S.fused_step(plan, st, eps_c, eps_u, guidance_scale=guidance_scale, guidance_rescale=guidance_rescale if do_cfg else 0.0,
-                         px_per_sample=h * w, x0_coeffs=self.scheduler.x0_coeffs(t), concat_out=ws["unet_in"], concat_lead=ws["sdr_px"],
-                         concat_self=True, concat_dup=1, rescale_ws=ws["rescale"])
-            if callback_on_step_end is not None:  # gm.py:1073-1081
-                cb_kwargs = {}
-                for k in callback_on_step_end_tensor_inputs:
-                    cb_kwargs[k] = {"latents": self._latents_nchw(st.x, B, h, w), "prompt_embeds": prompt_embeds,
-                                    "negative_prompt_embeds": negative_prompt_embeds}[k]
-                cb_out = callback_on_step_end(self, i, t, cb_kwargs) or {}
-                if "latents" in cb_out:
-                    new = cb_out["latents"].to(device=device, dtype=torch.float32).contiguous()
-                    L.check(L.lib().gmd_latents_nchw_to_px(new.data_ptr(), st.x.data_ptr(), B, h * w, stream))
-                    L.check(L.lib().gmd_pack_unet_input(ws["sdr_px"].data_ptr(), st.x.data_ptr(), ws["unet_in"].data_ptr(), n_px, 8, stream))
+
+        def denoise_loop():
+            for i, t in enumerate(ts):  # gm.py:1040-1091
+                if self.interrupt:
+                    continue
+                ws["temb"].copy_(table[i:i + 1])
+                run()
+                plan = self.scheduler.plan_step(t, extra["eta"])
+                if plan.needs_noise:
+                    z = torch.randn((B, 4, h, w), generator=generator, device=device if generator is None or generator.device.type == "cuda" else "cpu").to(device)
+                    st.noise = torch.empty(n_px, 4, dtype=torch.float32, device=device)
+                    L.check(L.lib().gmd_latents_nchw_to_px(z.contiguous().data_ptr(), st.noise.data_ptr(), B, h * w, stream))
+                S.fused_step(plan, st, eps_c, eps_u, guidance_scale=guidance_scale, guidance_rescale=guidance_rescale if do_cfg else 0.0,
+                             px_per_sample=h * w, x0_coeffs=self.scheduler.x0_coeffs(t), concat_out=ws["unet_in"], concat_lead=ws["sdr_px"],
+                             concat_self=True, concat_dup=1, rescale_ws=ws["rescale"])
+                if callback_on_step_end is not None:  # gm.py:1073-1081
+                    cb_kwargs = {}
+                    for k in callback_on_step_end_tensor_inputs:
+                        cb_kwargs[k] = {"latents": self._latents_nchw(st.x, B, h, w), "prompt_embeds": prompt_embeds,
+                                        "negative_prompt_embeds": negative_prompt_embeds}[k]
+                    cb_out = callback_on_step_end(self, i, t, cb_kwargs) or {}
+                    if "latents" in cb_out:
+                        new = cb_out["latents"].to(device=device, dtype=torch.float32).contiguous()
+                        L.check(L.lib().gmd_latents_nchw_to_px(new.data_ptr(), st.x.data_ptr(), B, h * w, stream))
+                        L.check(L.lib().gmd_pack_unet_input(ws["sdr_px"].data_ptr(), st.x.data_ptr(), ws["unet_in"].data_ptr(), n_px, 8, stream))
+
+        if not loop_graph_ok:
+            denoise_loop()
+        else:
+            loop_key = (B, h, w, do_cfg, type(self.scheduler).__name__, tuple(ts), float(guidance_scale), float(guidance_rescale if do_cfg else 0.0),
+                        table.data_ptr(), tuple(t_.data_ptr() for t_ in ws["kv"]))
+            ent = self._loop_graphs.get(loop_key)
+            if ent is None:
+                ws["temb"].copy_(table[0:1])
+                run()                              # eager warm-up: lazily allocated scratch exists before the capture; eps is rewritten
+                torch.cuda.synchronize()
+                n0 = L.launch_count()
+                lg = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(lg):
+                    denoise_loop()
+                n_kernels = L.launch_count() - n0
+                L.lib().gmd_add_launch_count(-n_kernels)   # (the capture pass recorded them; they did not run)
+                if len(self._loop_graphs) >= 4:
+                    self._loop_graphs.clear()
+                self._loop_graphs[loop_key] = ent = (lg, n_kernels, table)   # (the table must outlive its cache entry)
+            ent[0].replay()
+            self.graph_launches += ent[1]
         image = self._latents_nchw(st.x, B, h, w).to(out_dtype)
         if output_type != "latent":
             if self.vae is None:

@@ -109,6 +109,29 @@ def test_whole_loop_graph_is_bit_identical_to_eager_stepping(dual_pipe):
     assert [t for _, t in seen] == [751, 501, 501, 251, 1]
 
 
+def test_single_pipeline_loop_graph_is_bit_identical_to_eager_stepping(dual_pipe):
+    """Same claim for the SDR-conditioned single pipeline (stable_diffusion_gm.py): one graph per (schedule, guidance) key, replays
+    with new latents / SDR latents / prompts reproduce eager stepping bit for bit; callback_on_step_end falls back to eager."""
+    from gm_diffusion_b200 import DDIMScheduler, PNDMScheduler, StableDiffusionGMPipeline
+    pe, ne, lat, sdr = _inputs()
+    g = torch.Generator().manual_seed(78)
+    lat2, sdr2, pe2 = torch.randn(lat.shape, generator=g), torch.randn(sdr.shape, generator=g), torch.randn(pe.shape, generator=g)
+    for sched in (PNDMScheduler(), DDIMScheduler()):
+        pipe = StableDiffusionGMPipeline(vae=None, text_encoder=None, tokenizer=None, unet=dual_pipe.gm_unet, scheduler=sched)
+        kw = dict(negative_prompt_embeds=ne, num_inference_steps=4, guidance_scale=5.0, output_type="latent")
+        cases = ((sdr, lat, pe), (sdr2, lat2, pe2), (sdr, lat, pe))
+        pipe.use_loop_graph = False
+        want = [pipe(a, latents=b.clone(), prompt_embeds=c, **kw).images for a, b, c in cases]
+        pipe.use_loop_graph = True
+        got = [pipe(a, latents=b.clone(), prompt_embeds=c, **kw).images for a, b, c in cases]
+        assert len(pipe._loop_graphs) == 1 and pipe.graph_launches > 0
+        for x, y in zip(got, want):
+            assert torch.equal(x, y), "loop graph differs from eager stepping"
+        seen = []
+        out = pipe(sdr, latents=lat.clone(), prompt_embeds=pe, callback_on_step_end=lambda p_, i, t, kw_: seen.append(int(t)) or {}, **kw).images
+        assert len(seen) == len(pipe.scheduler.timesteps) and torch.equal(out, want[0]) and len(pipe._loop_graphs) == 1
+
+
 def test_teacher_forced_step_eps(models):
     """Per-step UNet eps, each step fed the ORACLE's inputs: <= 1e-2 relative L2 in bf16."""
     from gm_diffusion_b200 import B200UNet
