@@ -81,17 +81,21 @@ __device__ __forceinline__ float exp2_poly(float x) {
 #endif
 constexpr int POLY = GMD_ATTN2_POLY;
 #ifdef GMD_ATTN2_TRACE
+#ifndef GMD_ATTN2_TRACE_Z
+#define GMD_ATTN2_TRACE_Z 0   // the traced CTA is (0, 0, z)
+#endif
 // debug build only (profiles/trace_attn.py): clock64 timestamps of CTA (0,0,0), 8 event slots per key tile
 __device__ long long g_attn_trace[8 * 1024];
-#define TRACE(slot, j) do { if (blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && (j) < 1024) g_attn_trace[(j) * 8 + (slot)] = clock64(); } while (0)
+#define TRACE(slot, j) do { if (blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == GMD_ATTN2_TRACE_Z && (j) < 1024) g_attn_trace[(j) * 8 + (slot)] = clock64(); } while (0)
+// rows 1000 / 1001: (clock64, globaltimer ns) at the first and after the last tile -> the SM clock the kernel actually ran at
+#define TRACE_CLK(i) do { if (blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == GMD_ATTN2_TRACE_Z) { unsigned long long gt_; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt_)); \
+        g_attn_trace[(1000 + (i)) * 8] = clock64(); g_attn_trace[(1000 + (i)) * 8 + 1] = (long long)gt_; } } while (0)
 #else
 #define TRACE(slot, j) do { } while (0)
-#endif
-#ifndef GMD_ATTN2_SFIRST
-#define GMD_ATTN2_SFIRST 0    // 1: the MMA thread issues S_{j+SB} ahead of P V_j (A/B measurements)
+#define TRACE_CLK(i) do { } while (0)
 #endif
 #ifndef GMD_ATTN2_KO
-#define GMD_ATTN2_KO 0        // timing-only knock-outs of attn2_kernel (wrong results): 1 no MUFU, 2 no P stores, 4 no S loads, 8 no row sums / maxima
+#define GMD_ATTN2_KO 0        // timing-only knock-outs of attn2_kernel (wrong results): 1 no MUFU, 2 no P stores, 4 no S loads, 8 no row sums / maxima, 16 no K / V traffic after the first ring fill
 #endif
 
 template <int D, bool SHORT = false>
@@ -626,20 +630,27 @@ int launch(const gmd_attn_params* p, cudaStream_t st) {
 //     view, profiles/ncu_attn2_r02_summary.txt), so two warps per sub-partition leave the pipe ~35 % idle.  TMEM then only has room
 //     for ALIAS: P_j overwrites S_j in place (stored after the whole tile has been read and the growth check has passed) and
 //     S_{j+1} follows P V_j in the tensor pipe's issue order.
-template <int D, int BKV_, int NQT_, bool ALIAS_, int SB_, int PB_, int KS_>
+//   * HS = 2 (round 2, second pass; profiles/ubench_mma_ts_r02.txt): the TS-form P V MMA runs at the speed of its math (26 cycles
+//     at N = 48) and the whole tile's MMAs need ~260 tensor-pipe cycles, so what is left is keeping the MUFU pipe fed.  Every query
+//     row is worked on by TWO threads, each owning one half of the tile's keys as an independent online-softmax chain (own running
+//     maximum, denominator and O accumulator: P V of keys 0-31 accumulates into O_a, of keys 32-63 into O_b), merged once at the
+//     end of the kernel.  The halves never talk to each other per tile, a thread holds 32 instead of 64 scores (~96 registers), and
+//     two CTAs per SM put FOUR light softmax warps on every sub-partition instead of two heavy ones.
+template <int D, int BKV_, int NQT_, bool ALIAS_, int SB_, int PB_, int KS_, int HS_ = 1>
 struct Cfg2 {
     static constexpr int BKV = BKV_;                        // keys per tile
     static constexpr int NQT = NQT_;                        // 128-row query tiles (chains) per CTA
-    static constexpr bool ALIAS = ALIAS_;                   // P_j is stored over S_j (single buffer per chain)
-    static constexpr int SB = ALIAS ? 1 : SB_, PB = ALIAS ? 1 : PB_;   // S / P buffers per chain in TMEM
+    static constexpr bool ALIAS = ALIAS_;                   // P_j is stored over S_j (by the thread that read those columns of S_j)
+    static constexpr int SB = SB_, PB = ALIAS ? SB_ : PB_;  // S / P buffers per chain in TMEM (ALIAS: the S buffers are the P buffers)
     static constexpr int KS = KS_;                          // K and V ring depth (separate rings, separate barriers)
+    static constexpr int HS = HS_;                          // threads per query row (key halves of a tile as independent chains)
     static constexpr int NDB = (D + 63) / 64;               // 64-wide d blocks
     static constexpr int DP = (D + 15) / 16 * 16;           // K extent of Q K^T
     static constexpr int DPV = (D + 15) / 16 * 16;          // N extent of P V
     static constexpr int PCOLS = BKV / 2;                   // TMEM columns of one bf16 P tile (two keys per 32-bit cell)
-    static constexpr int CH_COLS = ALIAS ? BKV : SB * BKV + PB * PCOLS;   // S (+ P) columns of one chain
+    static constexpr int CH_COLS = ALIAS ? SB * BKV : SB * BKV + PB * PCOLS;   // S (+ P) columns of one chain
     static constexpr int TM_O = NQT * CH_COLS;
-    static constexpr int TMEM_USED = TM_O + NQT * DPV;
+    static constexpr int TMEM_USED = TM_O + NQT * HS * DPV;
     static constexpr uint32_t TMEM_COLS = TMEM_USED <= 128 ? 128 : TMEM_USED <= 256 ? 256 : 512;
     static constexpr int MIN_CTAS = TMEM_COLS <= 128 ? 4 : TMEM_COLS <= 256 ? 2 : 1;
     static constexpr int QT_BYTES = NDB * BQ * 128;         // one query tile
@@ -649,21 +660,30 @@ struct Cfg2 {
     static constexpr int OFF_K = Q_BYTES;
     static constexpr int OFF_V = OFF_K + KS * K_BYTES;
     static constexpr int OFF_BAR = OFF_V + KS * K_BYTES;
-    static constexpr int SMEM = OFF_BAR + 256 + 1024;
-    static constexpr int THREADS = 64 + 128 * NQT;          // warp 0: TMA, warp 1: MMA, then 4 softmax warps per chain (one thread per query row)
+    static constexpr int OFF_MERGE = OFF_BAR + 256;         // (m, l) of every chain half for the final merge (HS > 1)
+    static constexpr int SMEM = OFF_MERGE + (HS > 1 ? NQT * HS * BQ * 8 : 0) + 1024;
+    static constexpr int THREADS = 64 + 128 * NQT * HS;     // warp 0: TMA, warp 1: MMA, then 4 * HS softmax warps per chain (HS threads per query row)
     static constexpr int NBAR = 1 + 4 * KS + NQT * (SB + 2 * PB);
     static constexpr float LAZY_T = 8.0f;
-    static_assert(BKV % 32 == 0 && BKV <= 256, "tile");
+    static_assert(BKV % (32 * HS) == 0 && BKV <= 256, "tile");
     static_assert(KS >= SB, "S_{j+SB} needs its K tile while V_j is still in use");
     static_assert(SMEM * MIN_CTAS <= 227 * 1024, "shared memory");
     static_assert(NBAR * 8 + 4 <= 256, "barrier block");
 };
 
-template <int D, int BKV, int NQT, bool ALIAS, int SB_, int PB_, int KS>
-__global__ void __launch_bounds__(Cfg2<D, BKV, NQT, ALIAS, SB_, PB_, KS>::THREADS, Cfg2<D, BKV, NQT, ALIAS, SB_, PB_, KS>::MIN_CTAS)
+#ifndef GMD_ATTN2_TESTWAIT
+#define GMD_ATTN2_TESTWAIT 1   // hand-offs between the MMA thread and the softmax warps poll with mbarrier.test_wait (0: try_wait, A/B)
+#endif
+#if GMD_ATTN2_TESTWAIT
+#define AWAIT(bar, parity) mbar_wait_poll(bar, parity)
+#else
+#define AWAIT(bar, parity) mbar_wait(bar, parity)
+#endif
+template <int D, int BKV, int NQT, bool ALIAS, int SB_, int PB_, int KS, int HS>
+__global__ void __launch_bounds__(Cfg2<D, BKV, NQT, ALIAS, SB_, PB_, KS, HS>::THREADS, Cfg2<D, BKV, NQT, ALIAS, SB_, PB_, KS, HS>::MIN_CTAS)
 attn2_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_k,
              const __grid_constant__ CUtensorMap map_v, const AttnArgs args) {
-    using C = Cfg2<D, BKV, NQT, ALIAS, SB_, PB_, KS>;
+    using C = Cfg2<D, BKV, NQT, ALIAS, SB_, PB_, KS, HS>;
     constexpr int SB = C::SB, PB = C::PB;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -690,7 +710,7 @@ attn2_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ 
         mbar_init(q_full, 1);
         for (int s = 0; s < KS; ++s) { mbar_init(&k_full[s], 1); mbar_init(&k_empty[s], 1); mbar_init(&v_full[s], 1); mbar_init(&v_empty[s], 1); }
         for (int s = 0; s < NQT * SB; ++s) mbar_init(&s_full[s], 1);
-        for (int s = 0; s < NQT * PB; ++s) { mbar_init(&p_full[s], 128); mbar_init(&pv_done[s], 1); }
+        for (int s = 0; s < NQT * PB; ++s) { mbar_init(&p_full[s], 4 * HS); mbar_init(&pv_done[s], 1); }   // (one arrival per softmax warp)
         fence_barrier_init();
     }
     if (warp == 1) tmem_alloc<C::TMEM_COLS>(tmem_slot);
@@ -700,8 +720,11 @@ attn2_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ 
     const uint32_t tmem_base = *tmem_slot;
     // TMEM columns of chain t: S buffers, then (unless aliased) P buffers; O accumulators of all chains behind
     auto tm_s = [&](int t, int sb) { return tmem_base + t * C::CH_COLS + sb * BKV; };
-    auto tm_p = [&](int t, int pb) { return ALIAS ? tmem_base + t * C::CH_COLS : tmem_base + t * C::CH_COLS + SB * BKV + pb * C::PCOLS; };
-    auto tm_o = [&](int t) { return tmem_base + C::TM_O + t * C::DPV; };
+    // P of key half h: packed behind the S buffers, or (ALIAS) over the first half of the S columns that half's threads own
+    auto tm_p = [&](int t, int pb, int h) {
+        return ALIAS ? tmem_base + t * C::CH_COLS + pb * BKV + h * (BKV / HS) : tmem_base + t * C::CH_COLS + SB * BKV + pb * C::PCOLS + h * (C::PCOLS / HS);
+    };
+    auto tm_o = [&](int t, int h) { return tmem_base + C::TM_O + (t * HS + h) * C::DPV; };
 
     if (warp == 0) {
         if (lane == 0) {
@@ -713,6 +736,7 @@ attn2_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ 
             for (int j = 0; j < T; ++j) {
                 const int st = j % KS;
                 mbar_wait(&k_empty[st], ((j / KS) & 1) ^ 1);
+                if ((GMD_ATTN2_KO & 16) && j >= KS) { mbar_arrive(&k_full[st]); continue; }   // timing only: no K / V traffic after the first ring fill
                 mbar_expect_tx(&k_full[st], C::K_BYTES);
                 for (int b = 0; b < C::NDB; ++b) tma_load_3d(k_smem + st * C::K_BYTES + b * C::KV_BLOCK_BYTES, &map_k, &k_full[st], head * D + b * 64, j * BKV, batch);
                 TRACE(0, j);
@@ -721,6 +745,7 @@ attn2_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ 
             for (int j = 0; j < T; ++j) {
                 const int st = j % KS;
                 mbar_wait(&v_empty[st], ((j / KS) & 1) ^ 1);
+                if ((GMD_ATTN2_KO & 16) && j >= KS) { mbar_arrive(&v_full[st]); continue; }
                 mbar_expect_tx(&v_full[st], C::K_BYTES);
                 for (int b = 0; b < C::NDB; ++b) tma_load_3d(v_smem + st * C::K_BYTES + b * C::KV_BLOCK_BYTES, &map_v, &v_full[st], head * D + b * 64, j * BKV, batch);
             }
@@ -731,9 +756,9 @@ attn2_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ 
             constexpr uint32_t IDESC_O = umma_idesc_bf16(BQ, C::DPV, false, true);   // A = P from TMEM (K-major), B = V is MN-major
             const uint32_t q_addr = smem_u32(q_smem);
             // S_t(j) = Q_t K_j^T.  The K tile is polled once per j (chain 0) and released after the last chain's MMAs.
-            auto issue_s = [&](int t, int j) {
+            auto issue_s = [&](int t, int j, bool polled) {
                 const int st = j % KS;
-                if (t == 0) { mbar_wait(&k_full[st], (j / KS) & 1); tc_fence_after(); TRACE(1, j); }
+                if (t == 0 && !polled) { AWAIT(&k_full[st], (j / KS) & 1); tc_fence_after(); TRACE(1, j); }
                 const uint32_t k_addr = smem_u32(k_smem + st * C::K_BYTES);
 #pragma unroll
                 for (int ks = 0; ks < C::DP / 16; ++ks) {
@@ -746,43 +771,51 @@ attn2_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ 
                 if (t == NQT - 1) umma_commit(&k_empty[st]);
                 if (t == 0) TRACE(2, j);
             };
-            mbar_wait(q_full, 0);
+            AWAIT(q_full, 0);
             for (int i = 0; i < SB && i < T; ++i)
-                for (int t = 0; t < NQT; ++t) issue_s(t, i);
+                for (int t = 0; t < NQT; ++t) issue_s(t, i, false);
             for (int j = 0; j < T; ++j) {
                 const int st = j % KS, pb = j % PB;
                 const uint32_t v_addr = smem_u32(v_smem + st * C::K_BYTES);
+                // The operands of this iteration first — V_j and K_{j+SB} have been in flight for whole tiles, and every poll costs this
+                // thread 100-230 cycles while the softmax warps keep the sub-partition's MIO queue busy (clock64 trace) — so that nothing
+                // but the MMA issue itself stands between "P_j is in TMEM" and S_{j+SB}, the tile the softmax warps will wait for.
+                const bool next_s = j + SB < T;
+                AWAIT(&v_full[st], (j / KS) & 1);
+                TRACE(4, j);
+                // (K_{j+SB} only where it has a ring slot of its own: with KS == SB its load starts when S_j completes and may still be in flight)
+                constexpr bool EARLY_K = KS > SB;
+                if (EARLY_K && next_s) { AWAIT(&k_full[(j + SB) % KS], ((j + SB) / KS) & 1); TRACE(1, j + SB); }
 #pragma unroll
                 for (int t = 0; t < NQT; ++t) {
-                    mbar_wait(&p_full[t * PB + pb], (j / PB) & 1);       // P_t(j) in TMEM; S_t(j) read (its buffer may be overwritten)
-                    if (t == 0) TRACE(3, j);
-                    if (GMD_ATTN2_SFIRST && !ALIAS && j + SB < T) issue_s(t, j + SB);   // the next S ahead of P V_j: it is what the softmax warps wait for
-                    if (t == 0) mbar_wait(&v_full[st], (j / KS) & 1);
+                    AWAIT(&p_full[t * PB + pb], (j / PB) & 1);       // P_t(j) in TMEM; S_t(j) read (its buffer may be overwritten)
                     tc_fence_after();
-                    if (t == 0) TRACE(4, j);
+                    if (t == 0) TRACE(3, j);
 #pragma unroll
                     for (int ks = 0; ks < BKV / 16; ++ks) {
+                        constexpr int KPH = BKV / 16 / HS;   // K steps per key half: half h accumulates into its own O
                         const uint64_t db = umma_desc_mn_sw128(v_addr + ks * 16 * 128, C::KV_BLOCK_BYTES);
-                        umma_bf16_ts(tm_o(t), tm_p(t, pb) + ks * 8, db, IDESC_O, (j != 0 || ks != 0) ? 1u : 0u);
+                        umma_bf16_ts(tm_o(t, ks / KPH), tm_p(t, pb, ks / KPH) + (ks % KPH) * 8, db, IDESC_O, (j != 0 || (ks % KPH) != 0) ? 1u : 0u);
                     }
                     umma_commit(&pv_done[t * PB + pb]);
                     if (t == NQT - 1) umma_commit(&v_empty[st]);
                     if (t == 0) TRACE(5, j);
                     // the chain's next S right behind its P V (ALIAS: it overwrites P_t(j), after P V_t(j) in the pipe's issue order)
-                    if (!(GMD_ATTN2_SFIRST && !ALIAS) && j + SB < T) issue_s(t, j + SB);
+                    if (next_s) issue_s(t, j + SB, EARLY_K);
                 }
             }
         }
     } else {
-        const int lg = warp & 3;
-        const int t = (warp - 2) >> 2;           // chain (query tile) of this softmax warp
+        const int lg = warp & 3;                 // TMEM lane quadrant of this warp (fixed by warp % 4)
+        const int hw = ((warp - 2) >> 2) % HS;   // key half of the tile this thread owns
+        const int t = (warp - 2) / (4 * HS);     // chain (query tile) of this softmax warp
         const int row = lg * 32 + lane;
         const uint32_t lane_off = static_cast<uint32_t>(lg * 32) << 16;
-        const uint32_t my_o = tm_o(t) + lane_off;
+        const uint32_t my_o = tm_o(t, hw) + lane_off;
         const float c = args.scale_log2;
         float m = -INFINITY;     // running (possibly stale) row maximum, scaled log2 units
         float l = 0.0f;          // running denominator, relative to m
-        constexpr int NCH = BKV / 32;
+        constexpr int NCH = BKV / 32 / HS;
         // One pass over the S tile in 32-column TMEM reads.  EXP: probabilities 2^(s*c - m_use) as packed bf16 into pk[] (stored to
         // TMEM by the caller once the growth check has passed), their fp32 sum into `lsum`; the row maximum of the raw logits is
         // formed on the side (never on the exponentials' dependency chain).  MASK: columns >= valid are padding keys (last tile of
@@ -828,11 +861,11 @@ attn2_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ 
         };
         auto do_tile = [&](auto mask_tag, int j) {
             const int sb = j % SB, pb = j % PB;
-            const uint32_t s_addr = tm_s(t, sb) + lane_off, p_addr = tm_p(t, pb) + lane_off;
-            const int valid = args.Nk - j * BKV;
-            mbar_wait(&s_full[t * SB + sb], (j / SB) & 1);
+            const uint32_t s_addr = tm_s(t, sb) + lane_off + hw * (BKV / HS), p_addr = tm_p(t, pb, hw) + lane_off;
+            const int valid = args.Nk - j * BKV - hw * (BKV / HS);
+            AWAIT(&s_full[t * SB + sb], (j / SB) & 1);
             tc_fence_after();
-            if (warp == 2 && lane == 0) TRACE(6, j);
+            if (warp == 2 && lane == 0) { TRACE(6, j); if (j == 0) TRACE_CLK(0); }
             float mx, ls;
             uint32_t pk[NCH * 16];
             if (j == 0) {   // first tile: maximum first
@@ -852,7 +885,7 @@ attn2_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ 
                 m = m_new;
                 l *= alpha;
                 if (j > 0) {
-                    mbar_wait(&pv_done[t * PB + (j - 1) % PB], ((j - 1) / PB) & 1);   // O complete up to tile j-1 (P V_j waits for our p_full arrival)
+                    AWAIT(&pv_done[t * PB + (j - 1) % PB], ((j - 1) / PB) & 1);   // O complete up to tile j-1 (P V_j waits for our p_full arrival)
                     tc_fence_after();
 #pragma unroll
                     for (int oc = 0; oc < C::DPV / 16; ++oc) {
@@ -870,7 +903,7 @@ attn2_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ 
             l += ls;
             // The P buffer was last read by P V_{j-PB}.  ALIAS: P V_{j-1} was issued before S_j by the same thread, so s_full(j) implies
             // it is complete; PB == SB likewise (P V_{j-PB} precedes S_j in the issue order).  Otherwise wait for it.
-            if (!ALIAS && (PB != SB || GMD_ATTN2_SFIRST) && j >= PB) { mbar_wait(&pv_done[t * PB + pb], ((j - PB) / PB) & 1); tc_fence_after(); }
+            if (!ALIAS && PB != SB && j >= PB) { AWAIT(&pv_done[t * PB + pb], ((j - PB) / PB) & 1); tc_fence_after(); }
             if (!(GMD_ATTN2_KO & 2)) {
 #pragma unroll
                 for (int ch = 0; ch < NCH; ++ch) tmem_st_32x16p(p_addr + ch * 16, pk + ch * 16);
@@ -879,31 +912,54 @@ attn2_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ 
                 tmem_st_32x16p(p_addr, pk);
             }
             tc_fence_before();
-            mbar_arrive(&p_full[t * PB + pb]);
-            if (warp == 2 && lane == 0) TRACE(7, j);
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&p_full[t * PB + pb]);
+            if (warp == 2 && lane == 0) { TRACE(7, j); if (j == T - 1) TRACE_CLK(1); }
         };
         const bool ragged = (args.Nk % BKV) != 0;
         for (int j = 0; j < T - 1; ++j) do_tile(std::false_type{}, j);
         if (ragged) do_tile(std::true_type{}, T - 1); else do_tile(std::false_type{}, T - 1);
-        mbar_wait(&pv_done[t * PB + (T - 1) % PB], ((T - 1) / PB) & 1);
+        AWAIT(&pv_done[t * PB + (T - 1) % PB], ((T - 1) / PB) & 1);
         tc_fence_after();
         const int q = q0 + t * BQ + row;
         __nv_bfloat16* op = args.o + batch * args.o_stride_b + (int64_t)q * args.o_stride_n + head * args.o_stride_h;
-        const float inv_l = 1.0f / l;
+        // merge of the row's HS chains: common maximum, weights 2^(m_h - m), one denominator
+        float wgt[HS];
+        float inv_l;
+        if (HS == 1) {
+            wgt[0] = 1.0f;
+            inv_l = 1.0f / l;
+        } else {
+            float2* mg = reinterpret_cast<float2*>(smem + C::OFF_MERGE) + t * HS * BQ;
+            mg[hw * BQ + row] = make_float2(m, l);
+            asm volatile("bar.sync %0, %1;" ::"r"(1 + t), "r"(128 * HS) : "memory");
+            float mf = -INFINITY;
+#pragma unroll
+            for (int h = 0; h < HS; ++h) mf = fmaxf(mf, mg[h * BQ + row].x);
+            float lf = 0.0f;
+#pragma unroll
+            for (int h = 0; h < HS; ++h) { const float2 ml = mg[h * BQ + row]; wgt[h] = ex2(ml.x - mf); lf = fmaf(ml.y, wgt[h], lf); }
+            inv_l = 1.0f / lf;
+        }
 #pragma unroll
         for (int oc = 0; oc < C::DPV / 16; ++oc) {
-            uint32_t o[16];
-            tmem_ld_32x16(my_o + oc * 16, o);
-            tmem_wait_ld();
+            if (oc % HS != hw) continue;     // the row's threads share the output columns
+            float acc[16];
+#pragma unroll
+            for (int h = 0; h < HS; ++h) {
+                uint32_t o[16];
+                tmem_ld_32x16(tm_o(t, h) + lane_off + oc * 16, o);
+                tmem_wait_ld();
+#pragma unroll
+                for (int k = 0; k < 16; ++k) acc[k] = h == 0 ? __uint_as_float(o[k]) * wgt[0] : fmaf(__uint_as_float(o[k]), wgt[h], acc[k]);
+            }
             if (q < args.Nq) {
 #pragma unroll
                 for (int h8 = 0; h8 < 2; ++h8) {
                     const int d0 = oc * 16 + h8 * 8;
                     if (d0 < D) {  // D is a multiple of 8
-                        uint4 v = make_uint4(pack_bf16x2(__uint_as_float(o[h8 * 8 + 0]) * inv_l, __uint_as_float(o[h8 * 8 + 1]) * inv_l),
-                                             pack_bf16x2(__uint_as_float(o[h8 * 8 + 2]) * inv_l, __uint_as_float(o[h8 * 8 + 3]) * inv_l),
-                                             pack_bf16x2(__uint_as_float(o[h8 * 8 + 4]) * inv_l, __uint_as_float(o[h8 * 8 + 5]) * inv_l),
-                                             pack_bf16x2(__uint_as_float(o[h8 * 8 + 6]) * inv_l, __uint_as_float(o[h8 * 8 + 7]) * inv_l));
+                        uint4 v = make_uint4(pack_bf16x2(acc[h8 * 8 + 0] * inv_l, acc[h8 * 8 + 1] * inv_l), pack_bf16x2(acc[h8 * 8 + 2] * inv_l, acc[h8 * 8 + 3] * inv_l),
+                                             pack_bf16x2(acc[h8 * 8 + 4] * inv_l, acc[h8 * 8 + 5] * inv_l), pack_bf16x2(acc[h8 * 8 + 6] * inv_l, acc[h8 * 8 + 7] * inv_l));
                         *reinterpret_cast<uint4*>(op + d0) = v;
                     }
                 }
@@ -919,15 +975,15 @@ attn2_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ 
 }
 
 int g_attn_v1 = -1;     // GMD_ATTN_V1=1 in the environment: keep the round-1 kernel for d = 40 / 80 (A/B measurements)
-int g_attn2_cfg40 = 0;  // GMD_ATTN2_CFG40: 0 = one chain per CTA with double-buffered S and P (default), 1 = two aliased chains per CTA (A/B measurements)
+int g_attn2_cfg40 = 0;  // GMD_ATTN2_CFG40: alternative d = 40 configurations for A/B measurements, see gmd_attn_fwd
 
-template <int D, int BKV, int NQT, bool ALIAS, int SB, int PB, int KS>
+template <int D, int BKV, int NQT, bool ALIAS, int SB, int PB, int KS, int HS = 1>
 int launch2(const gmd_attn_params* p, cudaStream_t st) {
-    using C = Cfg2<D, BKV, NQT, ALIAS, SB, PB, KS>;
+    using C = Cfg2<D, BKV, NQT, ALIAS, SB, PB, KS, HS>;
     static bool configured[kMaxDevices] = {};
     const int dev = device_ordinal();
     if (!configured[dev]) {
-        cudaError_t e = cudaFuncSetAttribute(attn2_kernel<D, BKV, NQT, ALIAS, SB, PB, KS>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM);
+        cudaError_t e = cudaFuncSetAttribute(attn2_kernel<D, BKV, NQT, ALIAS, SB, PB, KS, HS>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM);
         if (e != cudaSuccess) { set_last_error("attn2: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return kErrCuda; }
         configured[dev] = true;
     }
@@ -954,7 +1010,7 @@ int launch2(const gmd_attn_params* p, cudaStream_t st) {
     a.scale_log2 = p->scale * 1.4426950408889634f;
     a.kv_dense = 1;
     dim3 grid((p->Nq + BQ * NQT - 1) / (BQ * NQT), p->H, p->B);
-    attn2_kernel<D, BKV, NQT, ALIAS, SB, PB, KS><<<grid, C::THREADS, C::SMEM, st>>>(mq, mk, mv, a);
+    attn2_kernel<D, BKV, NQT, ALIAS, SB, PB, KS, HS><<<grid, C::THREADS, C::SMEM, st>>>(mq, mk, mv, a);
     count_launch(1);
     return check_launch("attn2_kernel");
 }
@@ -1302,7 +1358,10 @@ extern "C" int gmd_attn_fwd(const gmd_attn_params* p, void* stream) {
     switch (p->d) {
         case 40:
             if (xattn) return launch_x<40>(p, st);
-            if (v2) return g_attn2_cfg40 == 1 ? launch2<40, 64, 2, true, 1, 1, 3>(p, st) : g_attn2_cfg40 == 2 ? launch2<40, 64, 1, true, 1, 1, 2>(p, st) : launch2<40, 64, 1, false, 2, 2, 3>(p, st);
+            // default: one thread per query row, S and P double-buffered; the alternatives are kept for A/B runs: 1 = two
+            // threads per row on independent key halves (P over S, four light softmax warps per sub-partition), 2 = three aliased S buffers
+            if (v2) return g_attn2_cfg40 == 1 ? launch2<40, 64, 1, true, 2, 2, 3, 2>(p, st) : g_attn2_cfg40 == 2 ? launch2<40, 64, 1, true, 3, 3, 4, 1>(p, st)
+                         : launch2<40, 64, 1, false, 2, 2, 3>(p, st);
             return p->Nk <= 2 * BKV ? launch<40, true>(p, st) : launch<40, false>(p, st);
         case 80:
             if (xattn) return launch_x<80>(p, st);

@@ -80,6 +80,31 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
         : "memory");
     return ok != 0;
 }
+__device__ __forceinline__ bool mbar_test_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t"
+        ".reg .pred P;\n\t"
+        "mbarrier.test_wait.parity.shared::cta.b64 P, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, P;\n\t"
+        "}\n"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+// Busy poll with the non-blocking test_wait: try_wait may park the thread, and being woken costs a few hundred cycles — too slow
+// for the hand-offs on the attention kernel's critical path (clock64 trace: ~300 cycles from the last arrival to the waiter running).
+__device__ __forceinline__ void mbar_wait_poll(uint64_t* bar, uint32_t parity) {
+    if (mbar_test_wait(bar, parity)) return;
+    long long t0 = clock64();
+    while (!mbar_test_wait(bar, parity)) {
+        if (clock64() - t0 > 4000000000LL) {
+            printf("gmd: mbarrier watchdog block=(%d,%d,%d) thread=%d parity=%u\n", blockIdx.x, blockIdx.y, blockIdx.z, threadIdx.x, parity);
+            __trap();
+        }
+    }
+}
 // Spin with a watchdog: a pipeline bug must trap (launch failure) instead of hanging the GPU.
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     if (mbar_try_wait(bar, parity)) return;

@@ -35,7 +35,7 @@ def wrap(n):
     def f(*a, **k):
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record(); out = orig[n](*a, **k); e1.record()
-        d, fl = desc(n, a, k, out)
+        d, fl = desc(n, a, k, out[0] if isinstance(out, tuple) else out)
         rec.append((d, fl, e0, e1))
         return out
     return f

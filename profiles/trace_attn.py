@@ -14,9 +14,12 @@ for _ in range(3):
     ops.attention(qkv[..., :C], qkv[..., C:2 * C], qkv[..., 2 * C:], 8)
 torch.cuda.synchronize()
 T = N // 64
-buf = (ctypes.c_longlong * (8 * T))()
-rc = _lib.lib().gmd_attn_trace_dump(buf, 8 * T)
+buf = (ctypes.c_longlong * (8 * 1024))()
+rc = _lib.lib().gmd_attn_trace_dump(buf, 8 * 1024)
 assert rc == 0, rc
+dc, dt = buf[1001 * 8] - buf[1000 * 8], buf[1001 * 8 + 1] - buf[1000 * 8 + 1]
+if dt > 0:
+    print(f"CTA (0,0,0): {dc} cycles in {dt} ns between its first and last tile -> SM clock {dc / dt:.3f} GHz")
 t0 = min(buf[i] for i in range(8 * T) if buf[i] > 0)
 names = ["K_issue", "k_full", "S_issue", "p_full", "v_full", "PV_issue", "s_full", "p_arrive"]
 print("tile " + " ".join(f"{n:>9}" for n in names))
