@@ -636,7 +636,12 @@ int launch(const gmd_attn_params* p, cudaStream_t st) {
 //     maximum, denominator and O accumulator: P V of keys 0-31 accumulates into O_a, of keys 32-63 into O_b), merged once at the
 //     end of the kernel.  The halves never talk to each other per tile, a thread holds 32 instead of 64 scores (~96 registers), and
 //     two CTAs per SM put FOUR light softmax warps on every sub-partition instead of two heavy ones.
-template <int D, int BKV_, int NQT_, bool ALIAS_, int SB_, int PB_, int KS_, int HS_ = 1>
+//   * WG = 1 (128-key tiles, two chains, one CTA per SM): the register file belongs to the sub-partitions (16 K registers each), so a
+//     10-warp CTA is capped at 168 registers per thread like a 12-warp one.  The CTA therefore has three whole warpgroups — {TMA warp,
+//     MMA warp, two idle warps} and one per chain — and re-balances with setmaxnreg: the first gives up all but 40 registers, the
+//     softmax warpgroups grow to 232, enough for a 128-column row with the next 32-column tcgen05.ld in flight under the current
+//     chunk's exponentials.  Twice the keys per barrier hand-off (~850 cycles per tile whatever its size).
+template <int D, int BKV_, int NQT_, bool ALIAS_, int SB_, int PB_, int KS_, int HS_ = 1, int WG_ = 0>
 struct Cfg2 {
     static constexpr int BKV = BKV_;                        // keys per tile
     static constexpr int NQT = NQT_;                        // 128-row query tiles (chains) per CTA
@@ -644,6 +649,8 @@ struct Cfg2 {
     static constexpr int SB = SB_, PB = ALIAS ? SB_ : PB_;  // S / P buffers per chain in TMEM (ALIAS: the S buffers are the P buffers)
     static constexpr int KS = KS_;                          // K and V ring depth (separate rings, separate barriers)
     static constexpr int HS = HS_;                          // threads per query row (key halves of a tile as independent chains)
+    static constexpr int WG = WG_;                          // 1: whole warpgroups + setmaxnreg (see above)
+    static constexpr int SW0 = WG ? 4 : 2;                  // first softmax warp
     static constexpr int NDB = (D + 63) / 64;               // 64-wide d blocks
     static constexpr int DP = (D + 15) / 16 * 16;           // K extent of Q K^T
     static constexpr int DPV = (D + 15) / 16 * 16;          // N extent of P V
@@ -662,7 +669,7 @@ struct Cfg2 {
     static constexpr int OFF_BAR = OFF_V + KS * K_BYTES;
     static constexpr int OFF_MERGE = OFF_BAR + 256;         // (m, l) of every chain half for the final merge (HS > 1)
     static constexpr int SMEM = OFF_MERGE + (HS > 1 ? NQT * HS * BQ * 8 : 0) + 1024;
-    static constexpr int THREADS = 64 + 128 * NQT * HS;     // warp 0: TMA, warp 1: MMA, then 4 * HS softmax warps per chain (HS threads per query row)
+    static constexpr int THREADS = SW0 * 32 + 128 * NQT * HS;   // warp 0: TMA, warp 1: MMA, (WG: two idle warps,) then 4 * HS softmax warps per chain
     static constexpr int NBAR = 1 + 4 * KS + NQT * (SB + 2 * PB);
     static constexpr float LAZY_T = 8.0f;
     static_assert(BKV % (32 * HS) == 0 && BKV <= 256, "tile");
@@ -679,12 +686,12 @@ struct Cfg2 {
 #else
 #define AWAIT(bar, parity) mbar_wait(bar, parity)
 #endif
-template <int D, int BKV, int NQT, bool ALIAS, int SB_, int PB_, int KS, int HS>
-__global__ void __launch_bounds__(Cfg2<D, BKV, NQT, ALIAS, SB_, PB_, KS, HS>::THREADS, Cfg2<D, BKV, NQT, ALIAS, SB_, PB_, KS, HS>::MIN_CTAS)
+template <int D, int BKV, int NQT, bool ALIAS, int SB_, int PB_, int KS, int HS, int WG>
+__global__ void __launch_bounds__(Cfg2<D, BKV, NQT, ALIAS, SB_, PB_, KS, HS, WG>::THREADS, Cfg2<D, BKV, NQT, ALIAS, SB_, PB_, KS, HS, WG>::MIN_CTAS)
 attn2_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_k,
              const __grid_constant__ CUtensorMap map_v, const AttnArgs args) {
-    using C = Cfg2<D, BKV, NQT, ALIAS, SB_, PB_, KS, HS>;
-    constexpr int SB = C::SB, PB = C::PB;
+    using C = Cfg2<D, BKV, NQT, ALIAS, SB_, PB_, KS, HS, WG>;
+    constexpr int SB = C::SB, PB = C::PB, SW0 = C::SW0;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint8_t* q_smem = smem;
@@ -726,6 +733,9 @@ attn2_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ 
     };
     auto tm_o = [&](int t, int h) { return tmem_base + C::TM_O + (t * HS + h) * C::DPV; };
 
+    if (warp < SW0) {
+    // (WG: the whole first warpgroup — TMA warp, MMA warp, two idle warps — hands its registers to the softmax warpgroups)
+    if (WG) asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
     if (warp == 0) {
         if (lane == 0) {
             mbar_expect_tx(q_full, C::Q_BYTES);
@@ -805,10 +815,12 @@ attn2_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ 
                 }
             }
         }
+    }
     } else {
+        if (WG) asm volatile("setmaxnreg.inc.sync.aligned.u32 224;");
         const int lg = warp & 3;                 // TMEM lane quadrant of this warp (fixed by warp % 4)
-        const int hw = ((warp - 2) >> 2) % HS;   // key half of the tile this thread owns
-        const int t = (warp - 2) / (4 * HS);     // chain (query tile) of this softmax warp
+        const int hw = ((warp - SW0) >> 2) % HS;   // key half of the tile this thread owns
+        const int t = (warp - SW0) / (4 * HS);     // chain (query tile) of this softmax warp
         const int row = lg * 32 + lane;
         const uint32_t lane_off = static_cast<uint32_t>(lg * 32) << 16;
         const uint32_t my_o = tm_o(t, hw) + lane_off;
@@ -824,12 +836,19 @@ attn2_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ 
         auto tile_pass = [&](auto exp_tag, auto mask_tag, uint32_t s_addr, int valid, float m_use, uint32_t* pk, float& mx_out, float& lsum) {
             constexpr bool EXP = decltype(exp_tag)::value, MASK = decltype(mask_tag)::value;
             float mx0 = -INFINITY, mx1 = -INFINITY, l0 = 0.0f, l1 = 0.0f, l2 = 0.0f, l3 = 0.0f;
+            // PIPE (one CTA per SM: registers to spare): the next chunk's tcgen05.ld is in flight while this chunk is exponentiated
+            constexpr bool PIPE = WG && NCH > 1 && !(GMD_ATTN2_KO & 4);
+            uint32_t rr[PIPE ? 2 : 1][32];
+            if (PIPE) tmem_ld_32x32(s_addr, rr[0]);
 #pragma unroll
             for (int ch = 0; ch < NCH; ++ch) {
-                uint32_t r[32];
+                uint32_t (&r)[32] = rr[PIPE ? (ch & 1) : 0];
                 if (GMD_ATTN2_KO & 4) {
 #pragma unroll
                     for (int k = 0; k < 32; ++k) r[k] = __float_as_uint(m_use + k);
+                } else if (PIPE) {
+                    tmem_wait_ld_regs(r);
+                    if (ch + 1 < NCH) tmem_ld_32x32(s_addr + (ch + 1) * 32, rr[(ch + 1) & 1]);
                 } else {
                     tmem_ld_32x32(s_addr + ch * 32, r);
                     tmem_wait_ld_regs(r);
@@ -865,7 +884,7 @@ attn2_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ 
             const int valid = args.Nk - j * BKV - hw * (BKV / HS);
             AWAIT(&s_full[t * SB + sb], (j / SB) & 1);
             tc_fence_after();
-            if (warp == 2 && lane == 0) { TRACE(6, j); if (j == 0) TRACE_CLK(0); }
+            if (warp == SW0 && lane == 0) { TRACE(6, j); if (j == 0) TRACE_CLK(0); }
             float mx, ls;
             uint32_t pk[NCH * 16];
             if (j == 0) {   // first tile: maximum first
@@ -914,7 +933,7 @@ attn2_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ 
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&p_full[t * PB + pb]);
-            if (warp == 2 && lane == 0) { TRACE(7, j); if (j == T - 1) TRACE_CLK(1); }
+            if (warp == SW0 && lane == 0) { TRACE(7, j); if (j == T - 1) TRACE_CLK(1); }
         };
         const bool ragged = (args.Nk % BKV) != 0;
         for (int j = 0; j < T - 1; ++j) do_tile(std::false_type{}, j);
@@ -977,13 +996,13 @@ attn2_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ 
 int g_attn_v1 = -1;     // GMD_ATTN_V1=1 in the environment: keep the round-1 kernel for d = 40 / 80 (A/B measurements)
 int g_attn2_cfg40 = 0;  // GMD_ATTN2_CFG40: alternative d = 40 configurations for A/B measurements, see gmd_attn_fwd
 
-template <int D, int BKV, int NQT, bool ALIAS, int SB, int PB, int KS, int HS = 1>
+template <int D, int BKV, int NQT, bool ALIAS, int SB, int PB, int KS, int HS = 1, int WG = 0>
 int launch2(const gmd_attn_params* p, cudaStream_t st) {
-    using C = Cfg2<D, BKV, NQT, ALIAS, SB, PB, KS, HS>;
+    using C = Cfg2<D, BKV, NQT, ALIAS, SB, PB, KS, HS, WG>;
     static bool configured[kMaxDevices] = {};
     const int dev = device_ordinal();
     if (!configured[dev]) {
-        cudaError_t e = cudaFuncSetAttribute(attn2_kernel<D, BKV, NQT, ALIAS, SB, PB, KS, HS>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM);
+        cudaError_t e = cudaFuncSetAttribute(attn2_kernel<D, BKV, NQT, ALIAS, SB, PB, KS, HS, WG>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM);
         if (e != cudaSuccess) { set_last_error("attn2: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return kErrCuda; }
         configured[dev] = true;
     }
@@ -1010,7 +1029,7 @@ int launch2(const gmd_attn_params* p, cudaStream_t st) {
     a.scale_log2 = p->scale * 1.4426950408889634f;
     a.kv_dense = 1;
     dim3 grid((p->Nq + BQ * NQT - 1) / (BQ * NQT), p->H, p->B);
-    attn2_kernel<D, BKV, NQT, ALIAS, SB, PB, KS, HS><<<grid, C::THREADS, C::SMEM, st>>>(mq, mk, mv, a);
+    attn2_kernel<D, BKV, NQT, ALIAS, SB, PB, KS, HS, WG><<<grid, C::THREADS, C::SMEM, st>>>(mq, mk, mv, a);
     count_launch(1);
     return check_launch("attn2_kernel");
 }
@@ -1359,8 +1378,10 @@ extern "C" int gmd_attn_fwd(const gmd_attn_params* p, void* stream) {
         case 40:
             if (xattn) return launch_x<40>(p, st);
             // default: one thread per query row, S and P double-buffered; the alternatives are kept for A/B runs: 1 = two
-            // threads per row on independent key halves (P over S, four light softmax warps per sub-partition), 2 = three aliased S buffers
+            // threads per row on independent key halves (P over S, four light softmax warps per sub-partition), 2 = three aliased S buffers,
+            // 3 = 128-key tiles, two chains per CTA, one CTA per SM with setmaxnreg-rebalanced warpgroups (917 us: slower)
             if (v2) return g_attn2_cfg40 == 1 ? launch2<40, 64, 1, true, 2, 2, 3, 2>(p, st) : g_attn2_cfg40 == 2 ? launch2<40, 64, 1, true, 3, 3, 4, 1>(p, st)
+                         : g_attn2_cfg40 == 3 ? launch2<40, 128, 2, true, 1, 1, 3, 1, 1>(p, st)
                          : launch2<40, 64, 1, false, 2, 2, 3>(p, st);
             return p->Nk <= 2 * BKV ? launch<40, true>(p, st) : launch<40, false>(p, st);
         case 80:
