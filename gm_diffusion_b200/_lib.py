@@ -49,7 +49,8 @@ class GemmParams(C.Structure):
                 ("bias", _vp), ("row_bias", _vp), ("ld_row_bias", _i64), ("rows_per_sample", _i64),
                 ("residual", _vp), ("ldr", _i64), ("M", _i64), ("N", _i64), ("K", _i64), ("batch", _i64),
                 ("stride_a", _i64), ("stride_w", _i64), ("stride_o", _i64), ("flags", _i32), ("alpha", _f32),
-                ("workspace", _vp), ("workspace_bytes", _i64), ("w_tiled", _i32), ("gn_sums", _vp), ("gn_rows_per_sample", _i64)]
+                ("workspace", _vp), ("workspace_bytes", _i64), ("w_tiled", _i32), ("gn_sums", _vp), ("gn_rows_per_sample", _i64),
+                ("ln_out_sums", _vp), ("ln_out_copy", _vp), ("ln_in_sums", _vp), ("ln_in_c", _vp), ("ln_eps", _f32)]
 
 
 class ConvParams(C.Structure):

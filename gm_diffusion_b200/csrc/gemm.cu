@@ -49,6 +49,10 @@ struct KernelArgs {
     float alpha;
     // persistent tile loop: tile -> (super-tile along M, N tile, z)
     int tiles_mt, tiles_n, gz;
+    // K = STAGES * 64 (the K = 320 token GEMMs): every k-block of a tile always lands in the same ring slot, so the weight half of the
+    // slots is left in place while a CTA stays on one N tile — the CTA then owns a CONTIGUOUS range of tiles (M fastest) instead of a
+    // strided one, and a tile costs 80 KB of L2 -> shared-memory traffic instead of 180 KB (these GEMMs ran at the L2's ~9 TB/s)
+    int b_resident;
     // split-K: tile also carries a K slice; partial sums go to an fp32 workspace and are reduced by splitk_finalize_kernel
     int ksplit, kb_per_split;
     int64_t split_stride_o;   // elements between the partial-sum planes
@@ -60,6 +64,12 @@ struct KernelArgs {
     long long* gn_sums;       // [sample][N_out / 2][2]; null = none.  Zeroed by the caller
     int gn_ncb;               // N_out / 32
     int64_t gn_rows;          // GEMM mode: output rows per sample
+    // LayerNorm folding (gmd_b200.h): producer side — row statistics and a bf16 copy of the output; consumer side — normalise in the epilogue
+    long long* ln_out_sums;   // [M][2] fixed point 2^-24, added to
+    __nv_bfloat16* ln_out_copy;   // [M][N_out]
+    const long long* ln_in_sums;  // [M][2]
+    const float* ln_in_c;     // [N]
+    float ln_eps, ln_inv_k;
 };
 
 // exact-erf GELU with erf from Abramowitz-Stegun 7.1.26 (|abs err| <= 1.5e-7, two MUFU ops): erff() costs ~60
@@ -227,6 +237,11 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__ 
     uint8_t* res_s = smem + P::OFF_RES;
     float* bias_s = reinterpret_cast<float*>(smem + P::OFF_BIAS);
     const uint32_t bias_sa = smem_u32(bias_s);
+    // the c vector of a LayerNorm-folding consumer: such a GEMM has no residual (host check), so the private residual rows (>= 2 KB
+    // even with RB = 0) are free to hold its BN floats
+    static_assert(BM * P::RES_ROW >= BN * 4, "residual region too small for the LayerNorm c vector");
+    float* lnc_s = reinterpret_cast<float*>(smem + P::OFF_RES);
+    const uint32_t lnc_sa = smem_u32(lnc_s);
     uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + P::OFF_BARS);
     uint64_t* empty_bar = full_bar + STAGES;
     uint64_t* acc_full = empty_bar + STAGES;   // [3] per accumulator set (or per rotating slot)
@@ -241,8 +256,12 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__ 
     const int lane = threadIdx.x & 31;
     const int crank = CL > 1 ? (int)cluster_ctarank() : 0;
     const int tn_c = PAIR ? args.tiles_n : args.tiles_n / CL;   // N tile groups (a multicast cluster covers CL neighbouring N tiles; a PAIR shares one)
-    const int num_tiles = args.tiles_mt * tn_c * args.gz * args.ksplit;
-    const int tile0 = blockIdx.x / CL, tstride = gridDim.x / CL;
+    const int total_tiles = args.tiles_mt * tn_c * args.gz * args.ksplit;
+    // b_resident: blocked assignment (CTA b owns tiles [b * per, (b + 1) * per)), else strided
+    const int per_cta = (total_tiles + (int)gridDim.x - 1) / (int)gridDim.x;
+    const int tile0 = args.b_resident ? (int)blockIdx.x * per_cta : (int)blockIdx.x / CL;
+    const int tstride = args.b_resident ? 1 : (int)gridDim.x / CL;
+    const int num_tiles = args.b_resident ? min(total_tiles, tile0 + per_cta) : total_tiles;
 
     if (threadIdx.x == 0) {
         tma_prefetch_desc(&map_a0);
@@ -311,6 +330,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__ 
         } else if (!HALO && elect_one()) {
             const int chunks_per_tap = args.chunks0 + args.chunks1;
             uint32_t kbg = 0;  // k-blocks issued so far (ring position carries across tiles)
+            int resident_n0 = -1;   // b_resident: the N tile whose weights the ring slots hold
             for (int tile = tile0; tile < num_tiles; tile += tstride) {
                 const int mt = tile % args.tiles_mt;
                 const int rest = tile / args.tiles_mt;
@@ -319,6 +339,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__ 
                 const int zb = zk % args.gz, ksl = zk / args.gz;
                 const int kb_begin = ksl * args.kb_per_split;
                 const int kb_end = min(args.num_kb, kb_begin + args.kb_per_split);
+                const bool tile_keep_b = !PAIR && CL == 1 && args.b_resident && n0 == resident_n0;
+                resident_n0 = n0;
                 int m0[MT], tw0[MT], th0[MT], tn0[MT];
 #pragma unroll
                 for (int s = 0; s < MT; ++s) {
@@ -342,7 +364,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__ 
                         tma_load_3d_2sm(sb, &map_w, &full_bar[stage], 0, ((n0 / BN) * args.num_kb + kb) * BN + crank * (BN / 2), 0);
                         continue;
                     }
-                    mbar_expect_tx(&full_bar[stage], P::STAGE_BYTES);
+                    const bool keep_b = tile_keep_b;   // slot `stage` already holds W[n0 tile][kb]
+                    mbar_expect_tx(&full_bar[stage], keep_b ? P::A_BYTES : P::STAGE_BYTES);
                     if (args.mode == 0) {
                         if (CL > 1) {
                             // this CTA's sub-tile, multicast into both CTAs of the pair
@@ -354,7 +377,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__ 
                                 else tma_load_3d(sa + s * P::A_SUB, &map_a1, &full_bar[stage], (kb - args.kb_src0) * BK, m0[s], zb);
                             }
                         }
-                        if (args.w_bulk) bulk_copy_g2s(sb, args.w_bulk + (size_t)((n0 / BN) * args.num_kb + kb) * P::B_BYTES, P::B_BYTES, &full_bar[stage]);
+                        if (keep_b) {}
+                        else if (args.w_bulk) bulk_copy_g2s(sb, args.w_bulk + (size_t)((n0 / BN) * args.num_kb + kb) * P::B_BYTES, P::B_BYTES, &full_bar[stage]);
                         else if (args.w_tiled) tma_load_3d(sb, &map_w, &full_bar[stage], 0, ((n0 / BN) * args.num_kb + kb) * BN, 0);
                         else tma_load_3d(sb, &map_w, &full_bar[stage], kb * BK, n0, zb);
                     } else {
@@ -600,13 +624,14 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__ 
             // reload is a dependent global load plus two 256-thread barriers on the epilogue's critical path, ~1 us per tile,
             // which is what bounded the short-K GEMMs (55 tiles per CTA).  The first barrier keeps slow warps of the previous
             // tile from losing their copy.
-            if (args.bias && ti.n0 != bias_n0) {
+            if ((args.bias || args.ln_in_c) && ti.n0 != bias_n0) {
                 bias_n0 = ti.n0;
                 asm volatile("bar.sync 1, 256;" ::: "memory");
                 for (int i = et; i < BN; i += 256) {
                     int col = geglu ? (i < BN / 2 ? ti.out_col_tile + i : args.N_out + ti.out_col_tile + (i - BN / 2)) : ti.n0 + i;
                     int lim = geglu ? 2 * args.N_out : args.N_out;
-                    bias_s[i] = col < lim ? __ldg(args.bias + col) : 0.0f;
+                    if (args.bias) bias_s[i] = col < lim ? __ldg(args.bias + col) : 0.0f;
+                    if (args.ln_in_c) lnc_s[i] = col < lim ? __ldg(args.ln_in_c + col) : 0.0f;
                 }
                 asm volatile("bar.sync 1, 256;" ::: "memory");
             }
@@ -631,6 +656,16 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__ 
                     tc_fence_after();
                 }
                 const uint32_t tsub = P::ROT ? taddr_lane + (rot_u % 3) * BN : taddr_lane + ab * P::ACC_COLS + s * BN;
+                // LayerNorm folding, consumer side: this row's mean / rstd from the producer's exact integer sums (double: E[x^2] - mean^2)
+                float ln_a = 1.0f, ln_b = 0.0f;        // v = acc * ln_a + ln_b * c[n]
+                if (args.ln_in_sums && row_ok) {
+                    const longlong2 sm = *reinterpret_cast<const longlong2*>(args.ln_in_sums + 2 * orow);
+                    const double mean = static_cast<double>(sm.x) * (1.0 / 16777216.0) * args.ln_inv_k;
+                    const double var = static_cast<double>(sm.y) * (1.0 / 16777216.0) * args.ln_inv_k - mean * mean;
+                    ln_a = rsqrtf(static_cast<float>(var) + args.ln_eps);
+                    ln_b = -static_cast<float>(mean) * ln_a;
+                }
+                float ln_s1 = 0.0f, ln_s2 = 0.0f;      // producer side: this thread's part of the row's sum / sum of squares
                 if (fast) {
                     if (geglu) {
 #pragma unroll 1
@@ -673,6 +708,15 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__ 
                                 for (int j = 0; j < 32; ++j) v[j] *= args.alpha;
                             }
                             const int col0 = out_col_tile + c * 32;
+                            if (args.ln_in_sums) {
+                                const uint32_t c4 = lnc_sa + (c * 32) * 4;
+#pragma unroll
+                                for (int j = 0; j < 8; ++j) {
+                                    const float4 cv = lds128(c4 + 16 * j);
+                                    v[4 * j] = fmaf(v[4 * j], ln_a, ln_b * cv.x); v[4 * j + 1] = fmaf(v[4 * j + 1], ln_a, ln_b * cv.y);
+                                    v[4 * j + 2] = fmaf(v[4 * j + 2], ln_a, ln_b * cv.z); v[4 * j + 3] = fmaf(v[4 * j + 3], ln_a, ln_b * cv.w);
+                                }
+                            }
                             if (args.bias) {
                                 const uint32_t b4 = bias_sa + (c * 32) * 4;
 #pragma unroll
@@ -722,6 +766,12 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__ 
                                 unsigned long long* dst = reinterpret_cast<unsigned long long*>(args.gn_sums) +
                                                           ((smp * args.gn_ncb + (col0 >> 5)) * 16 + (lane & 15)) * 2 + (lane >> 4);
                                 atomicAdd(dst, static_cast<unsigned long long>(__float2ll_rn(sv[0] * 16777216.0f)));
+                            }
+                            if (args.ln_out_sums) {
+#pragma unroll
+                                for (int j = 0; j < 32; ++j) { ln_s1 += v[j]; ln_s2 = fmaf(v[j], v[j], ln_s2); }
+                                __nv_bfloat16* cp = args.ln_out_copy + orow * args.N_out + col0;
+                                st_bf16x16(cp, v); st_bf16x16(cp + 16, v + 16);
                             }
                             if (out_f32) {
                                 float* op = reinterpret_cast<float*>(args.out) + zoff_o + orow * args.ldo + col0;
@@ -780,6 +830,12 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__ 
                             for (int j = 0; j < ncol; ++j) op[j] = __float2bfloat16(v[j]);
                         }
                     }
+                }
+                if (args.ln_out_sums && fast && row_ok) {
+                    // (the two warps of a lane group own different column chunks of the row; integer adds commute: order-independent)
+                    unsigned long long* dst = reinterpret_cast<unsigned long long*>(args.ln_out_sums) + 2 * orow;
+                    atomicAdd(dst, static_cast<unsigned long long>(__float2ll_rn(ln_s1 * 16777216.0f)));
+                    atomicAdd(dst + 1, static_cast<unsigned long long>(__float2ll_rn(ln_s2 * 16777216.0f)));
                 }
                 // this thread is done with its private residual row: stream in the next sub-tile's / next tile's chunks
                 if (s + 1 < MT) {
@@ -845,6 +901,7 @@ __global__ void __launch_bounds__(256) splitk_finalize_kernel(const float* __res
 int g_pair_min_kb = 8;            // GMD_PAIR_MIN_KB: shortest K loop (in 64-wide blocks) that takes the CTA-pair path
 bool g_disable_pair = false;      // GMD_NO_PAIR=1: GEMMs stay on single-CTA MMAs (A/B measurements)
 bool g_disable_halo = false;      // GMD_NO_HALO=1: 3x3 convolutions take the one-box-per-tap main loop (A/B measurements)
+bool g_disable_bres = false;      // GMD_NO_BRES=1: no resident-weight ring for the K = 320 GEMMs (A/B measurements)
 bool g_disable_cluster = false;   // GMD_NO_CLUSTER=1 in the environment falls back to single-CTA tiles (A/B measurements)
 
 int sm_count() {
@@ -856,6 +913,8 @@ int sm_count() {
         env_read = true;
         const char* e = getenv("GMD_NO_CLUSTER");
         g_disable_cluster = e && e[0] == '1';
+        e = getenv("GMD_NO_BRES");
+        g_disable_bres = e && e[0] == '1';
         e = getenv("GMD_NO_HALO");
         g_disable_halo = e && e[0] == '1';
         e = getenv("GMD_NO_PAIR");
@@ -912,6 +971,7 @@ int launch_cfg(int bn, int64_t tiles_m, int64_t tiles_n, unsigned gz, const CUte
     const bool mt2 = want_mt2(bn, res_f32, tiles_m, tiles_n, gz, args.num_kb);
     args.tiles_mt = (int)(mt2 ? (tiles_m + 1) / 2 : tiles_m);
     args.tiles_n = (int)tiles_n;
+    args.b_resident = 0;
     args.gz = (int)gz;
     if (args.ksplit < 1) { args.ksplit = 1; args.kb_per_split = args.num_kb; args.split_stride_o = 0; }
     // pair neighbouring N tiles into 2-CTA clusters that share (multicast) the A operand
@@ -945,6 +1005,11 @@ int launch_cfg(int bn, int64_t tiles_m, int64_t tiles_n, unsigned gz, const CUte
         // 128-row tiles: the main loop is bound by the operand bytes in flight (ring capacity / TMA latency — the "40 B/clk/SM" of the
         // 3-stage ring is 108 KB per ~2700 cycles), so everything the residual row buffer does not need goes to more stages
         case 160:
+            // K = 320 (five k-blocks = five ring slots): weights stay resident in the ring while a CTA stays on one N tile
+            if (!mt2 && !res_f32 && args.mode == 0 && args.num_kb == 5 && args.ksplit == 1 && gz == 1 && !g_disable_bres) {
+                args.b_resident = 1;
+                return no_res ? launch<1, 160, 5, 0>(maps_a, map_w, args, st) : launch<1, 160, 5, 2>(maps_a, map_w, args, st);
+            }
             if (no_res) return mt2 ? (cl2 ? launch<2, 160, 4, 0, 2>(maps_a, map_w, args, st) : launch<2, 160, 4, 0>(maps_a, map_w, args, st))
                                    : launch<1, 160, 6, 0>(maps_a, map_w, args, st);
             return mt2 ? (cl2 ? launch<2, 160, 3, 2, 2>(maps_a, map_w, args, st) : launch<2, 160, 3, 2>(maps_a, map_w, args, st))
@@ -1089,6 +1154,18 @@ extern "C" int gmd_gemm_fwd(const gmd_gemm_params* p, void* stream) {
             set_last_error("gmd_gemm_fwd: gn_sums is not available for this call (see gmd_gemm_gn_sums_ok)"); return kErrUnsupported;
         }
         a.gn_sums = static_cast<long long*>(p->gn_sums); a.gn_ncb = (int)(p->N / 32); a.gn_rows = p->gn_rows_per_sample;
+    }
+    if (p->ln_out_sums || p->ln_in_sums) {
+        const int oes = (p->flags & GMD_EPI_OUT_F32) ? 4 : 2;
+        const bool ok = batch == 1 && !geglu && ks == 1 && !(p->ln_in_sums && a.residual) && (p->N % bn) == 0 && (reinterpret_cast<uintptr_t>(p->out) & 31) == 0 && ((p->ldo * oes) % 32) == 0 &&
+                        (!a.residual || ((reinterpret_cast<uintptr_t>(p->residual) & 15) == 0 &&
+                                         ((p->ldr * ((p->flags & GMD_EPI_RESIDUAL_F32) ? 4 : 2)) % 16) == 0)) &&
+                        (!p->ln_out_sums || (p->ln_out_copy && (reinterpret_cast<uintptr_t>(p->ln_out_copy) & 31) == 0 && (reinterpret_cast<uintptr_t>(p->ln_out_sums) & 15) == 0)) &&
+                        (!p->ln_in_sums || (p->ln_in_c && (reinterpret_cast<uintptr_t>(p->ln_in_c) & 15) == 0 && (reinterpret_cast<uintptr_t>(p->ln_in_sums) & 15) == 0));
+        if (!ok) { set_last_error("gmd_gemm_fwd: LayerNorm folding needs batch == 1, no GEGLU, no split-K, full N tiles and 32-byte aligned rows"); return kErrUnsupported; }
+        a.ln_out_sums = static_cast<long long*>(p->ln_out_sums); a.ln_out_copy = static_cast<__nv_bfloat16*>(p->ln_out_copy);
+        a.ln_in_sums = static_cast<const long long*>(p->ln_in_sums); a.ln_in_c = p->ln_in_c;
+        a.ln_eps = p->ln_eps; a.ln_inv_k = 1.0f / static_cast<float>(p->K);
     }
     if (ks > 1) {
         KernelArgs b = a;

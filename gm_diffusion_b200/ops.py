@@ -77,6 +77,7 @@ def splitk_workspace(device) -> torch.Tensor:
     return ws
 
 
+LN_FOLD = __import__("os").environ.get("GMD_LN_FOLD", "0") == "1"   # 1: norm1 / norm2 of the transformer blocks folded into the GEMMs around them (measured neutral: DESIGN.md)
 GN_EPILOGUE = __import__("os").environ.get("GMD_GN_EPILOGUE", "1") != "0"   # 0: statistics by the standalone GroupNorm kernel (A/B measurements)
 _GN_ARENA = {}
 
@@ -91,7 +92,7 @@ class gn_arena:
         words_hint = ar.used
 
     Outside such a block every statistics tensor is a fresh torch.zeros.  The buffer is static (CUDA-graph friendly)."""
-    WORDS = 4 << 20
+    WORDS = 8 << 20
 
     def __init__(self, device, words_hint=None):
         self.key = torch.device(device).index or 0
@@ -135,10 +136,14 @@ def _gn_sums_alloc(device, n: int, c: int) -> torch.Tensor:
 
 def gemm(a: torch.Tensor, w: torch.Tensor, *, bias: Optional[torch.Tensor] = None, residual: Optional[torch.Tensor] = None,
          row_bias: Optional[torch.Tensor] = None, rows_per_sample: int = 0, geglu: bool = False, out: Optional[torch.Tensor] = None,
-         out_f32: bool = False, alpha: Optional[float] = None, splitk: bool = False, gn_rows_per_sample: int = 0):
+         out_f32: bool = False, alpha: Optional[float] = None, splitk: bool = False, gn_rows_per_sample: int = 0,
+         ln_out: bool = False, ln_in=None):
     """out[M,N] = a[M,K] @ w[N,K]^T (+bias +row_bias[sample] +residual | GEGLU).  3-D inputs are batched.
     `gn_rows_per_sample` > 0: also return the GroupNorm statistics of the output, accumulated by the epilogue (`(out, sums)`, sums
-    int64 fixed point [samples, N/2, 2]; None where the kernel cannot provide them)."""
+    int64 fixed point [samples, N/2, 2]; None where the kernel cannot provide them).
+    LayerNorm folding (gmd_b200.h): `ln_out=True` also returns a bf16 copy of the output and its per-row statistics
+    (`(out, copy, sums)`); `ln_in=(sums, c, eps)` makes this GEMM the projection behind that LayerNorm (a = the bf16 copy,
+    w = W * diag(gamma), bias = b + W beta, c = row sums of w)."""
     tiled = isinstance(w, TiledWeight)
     wt = w.data if tiled else w
     L.require_cuda(a, wt)
@@ -194,11 +199,23 @@ def gemm(a: torch.Tensor, w: torch.Tensor, *, bias: Optional[torch.Tensor] = Non
         # entry point uses a batch-independent rule instead and is on by default, see conv2d.)
         ws = splitk_workspace(a.device)
         p.workspace, p.workspace_bytes = ws.data_ptr(), ws.numel()
+    ln_copy = ln_sums = None
+    if ln_out:
+        assert not batched and not geglu
+        ln_copy = torch.empty((M, N), dtype=bf16, device=a.device)
+        ln_sums = _gn_sums_alloc(a.device, M, 2).view(M, 2)
+        p.ln_out_sums, p.ln_out_copy = ln_sums.data_ptr(), ln_copy.data_ptr()
+    if ln_in is not None:
+        s_in, c_in, eps_in = ln_in
+        assert s_in.dtype == torch.int64 and s_in.shape == (M, 2) and s_in.is_contiguous() and c_in.dtype == torch.float32 and c_in.numel() == N
+        p.ln_in_sums, p.ln_in_c, p.ln_eps = s_in.data_ptr(), c_in.data_ptr(), float(eps_in)
     sums = None
     if gn_rows_per_sample > 0 and GN_EPILOGUE and L.lib().gmd_gemm_gn_sums_ok(C.byref(p), gn_rows_per_sample):
         sums = _gn_sums_alloc(a.device, M // gn_rows_per_sample, N)
         p.gn_sums, p.gn_rows_per_sample = sums.data_ptr(), gn_rows_per_sample
     L.check(L.lib().gmd_gemm_fwd(C.byref(p), L.current_stream()), "gmd_gemm_fwd")
+    if ln_out:
+        return out, ln_copy, ln_sums
     if gn_rows_per_sample > 0:
         return out, sums
     return out

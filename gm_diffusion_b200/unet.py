@@ -29,6 +29,15 @@ def _w(t, dev):
     return ops.tile_weight(t.detach().to(device=dev, dtype=bf16))
 
 
+def _w_ln(w, gamma, beta, dev):
+    """Projection behind a LayerNorm, with the LayerNorm folded in (gmd_b200.h "LayerNorm folded into the GEMMs on either side"):
+    W' = W diag(gamma) as the tiled bf16 operand, c = row sums of the ROUNDED W' (what the MMA actually multiplies the mean with),
+    bias = W beta."""
+    w32 = w.detach().to(device=dev, dtype=torch.float32)
+    wg = (w32 * gamma.to(dev, torch.float32)[None, :]).to(bf16)
+    return ops.tile_weight(wg), wg.float().sum(1).contiguous(), (w32 @ beta.to(dev, torch.float32)).contiguous()
+
+
 class _Resnet:
     def __init__(self, sd, prefix, dev, temb_slices: Optional[list], eps=1e-5):
         g = lambda k: sd[prefix + k]
@@ -79,9 +88,17 @@ class _Transformer:
         self.w_in, self.b_in = _w(g("proj_in.weight").reshape(c, c), dev), _f32(g("proj_in.bias"), dev)
         self.w_out, self.b_out = _w(g("proj_out.weight").reshape(c, c), dev), _f32(g("proj_out.bias"), dev)
         self.ln = [(_f32(g(t + f"norm{i}.weight"), dev), _f32(g(t + f"norm{i}.bias"), dev)) for i in (1, 2, 3)]
-        self.w_qkv = _w(torch.cat([g(t + "attn1.to_q.weight"), g(t + "attn1.to_k.weight"), g(t + "attn1.to_v.weight")], 0), dev)
         self.w_o1, self.b_o1 = _w(g(t + "attn1.to_out.0.weight"), dev), _f32(g(t + "attn1.to_out.0.bias"), dev)
-        self.w_q2 = _w(g(t + "attn2.to_q.weight"), dev)
+        # norm1 -> to_q/k/v and norm2 -> to_q with the LayerNorm folded into the projection (norm3 feeds the GEGLU GEMM, whose
+        # epilogue is already the bound of that kernel: it keeps its LayerNorm kernel)
+        self.fold = ops.LN_FOLD
+        if self.fold:
+            wqkv = torch.cat([g(t + "attn1.to_q.weight"), g(t + "attn1.to_k.weight"), g(t + "attn1.to_v.weight")], 0)
+            self.w_qkv_f, self.c_qkv, self.d_qkv = _w_ln(wqkv, *[g(t + f"norm1.{k}") for k in ("weight", "bias")], dev)
+            self.w_q2_f, self.c_q2, self.d_q2 = _w_ln(g(t + "attn2.to_q.weight"), *[g(t + f"norm2.{k}") for k in ("weight", "bias")], dev)
+        else:
+            self.w_qkv = _w(torch.cat([g(t + "attn1.to_q.weight"), g(t + "attn1.to_k.weight"), g(t + "attn1.to_v.weight")], 0), dev)
+            self.w_q2 = _w(g(t + "attn2.to_q.weight"), dev)
         self.w_kv2 = _w(torch.cat([g(t + "attn2.to_k.weight"), g(t + "attn2.to_v.weight")], 0), dev)
         self.w_o2, self.b_o2 = _w(g(t + "attn2.to_out.0.weight"), dev), _f32(g(t + "attn2.to_out.0.bias"), dev)
         wff, bff = ops.pack_geglu_weight_tiled(g(t + "ff.net.0.proj.weight").to(dev), g(t + "ff.net.0.proj.bias").to(dev))
@@ -101,19 +118,34 @@ class _Transformer:
         y = ops.groupnorm_silu(x, *self.norm, eps=1e-6, silu=False, stats_ws=ws, sums=xs)
         # the token stream y is consumed only by LayerNorms and residual adds (never an MMA operand): it stays fp32,
         # which removes 4 of the 5 full-magnitude bf16 roundings per transformer block
-        y = ops.gemm(y.view(m, c), self.w_in, bias=self.b_in, out_f32=True)
+        fold = self.fold
+        if fold:
+            # the GEMMs that write the token stream also emit its bf16 image and row statistics; the projections behind norm1 / norm2
+            # read that image and normalise in their epilogue — no LayerNorm pass over the fp32 stream
+            y, yb, ys = ops.gemm(y.view(m, c), self.w_in, bias=self.b_in, out_f32=True, ln_out=True)
+            qkv = ops.gemm(yb, self.w_qkv_f, bias=self.d_qkv, ln_in=(ys, self.c_qkv, 1e-5)).view(B, n, 3 * c)
+        else:
+            y = ops.gemm(y.view(m, c), self.w_in, bias=self.b_in, out_f32=True)
+            h = ops.layernorm(y, *self.ln[0])
+            qkv = ops.gemm(h, self.w_qkv).view(B, n, 3 * c)
         # self-attention
-        h = ops.layernorm(y, *self.ln[0])
-        qkv = ops.gemm(h, self.w_qkv).view(B, n, 3 * c)
         a = ops.attention(qkv[..., :c], qkv[..., c:2 * c], qkv[..., 2 * c:], self.heads)
-        y = ops.gemm(a.view(m, c), self.w_o1, bias=self.b_o1, residual=y, out_f32=True)
+        if fold:
+            y, yb, ys = ops.gemm(a.view(m, c), self.w_o1, bias=self.b_o1, residual=y, out_f32=True, ln_out=True)
+        else:
+            y = ops.gemm(a.view(m, c), self.w_o1, bias=self.b_o1, residual=y, out_f32=True)
         if dup:
             y = torch.cat([y, y], 0)
             x = torch.cat([x, x], 0)
+            if fold:
+                yb, ys = torch.cat([yb, yb], 0), torch.cat([ys, ys], 0)
             B, m = 2 * B, 2 * m
         # text cross-attention (K/V hoisted)
-        h = ops.layernorm(y, *self.ln[1])
-        q = ops.gemm(h, self.w_q2).view(B, n, c)
+        if fold:
+            q = ops.gemm(yb, self.w_q2_f, bias=self.d_q2, ln_in=(ys, self.c_q2, 1e-5)).view(B, n, c)
+        else:
+            h = ops.layernorm(y, *self.ln[1])
+            q = ops.gemm(h, self.w_q2).view(B, n, c)
         kv3 = kv.view(B, -1, 2 * c)
         a = ops.attention(q, kv3[..., :c], kv3[..., c:], self.heads)
         y = ops.gemm(a.view(m, c), self.w_o2, bias=self.b_o2, residual=y, out_f32=True)

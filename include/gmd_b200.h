@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define GMD_VERSION 200
+#define GMD_VERSION 201
 
 int gmd_version(void);
 const char* gmd_last_error(void);
@@ -208,6 +208,17 @@ typedef struct gmd_gemm_params {
                                           * row r at chunk c ^ (r & 7)) and fetched with ONE 1-D bulk copy per tile instead of T tensor rows */
     void* gn_sums;                       /* optional: GroupNorm statistics of the OUTPUT accumulated by the epilogue (see below); NULL = none */
     int64_t gn_rows_per_sample;          /* with gn_sums: output rows of one sample (a multiple of 128) */
+    /* LayerNorm folded into the GEMMs on either side of it (BasicTransformerBlock norm1 -> to_q/k/v, norm2 -> to_q).  The GEMM that
+     * writes the fp32 token stream x (PRODUCER) also emits a bf16 copy of x and each row's sum / sum of squares; the projection behind
+     * the LayerNorm (CONSUMER) multiplies the bf16 copy with W' = W * diag(gamma) and normalises in its epilogue:
+     *   out[r, n] = rstd_r * (acc[r, n] - mean_r * c[n]) + bias[n],   c[n] = sum_k W'[n, k],   bias = b + W * beta
+     * — the LayerNorm kernel (a read of the fp32 stream and a write of its bf16 image) disappears.  Both sides need full N tiles,
+     * batch == 1, no GEGLU and no split-K (else GMD_ERR_UNSUPPORTED). */
+    void* ln_out_sums;                   /* PRODUCER: int64 [M, 2] (sum, sum of squares of output row r in 2^-24 fixed point), ADDED to: zeroed by the caller.  NULL = none */
+    void* ln_out_copy;                   /* PRODUCER: bf16 [M, N] copy of the output, row stride N */
+    const void* ln_in_sums;              /* CONSUMER: the producer's statistics of the rows of A (K = the producer's N).  NULL = none */
+    const float* ln_in_c;                /* CONSUMER: fp32 [N] */
+    float ln_eps;                        /* CONSUMER */
 } gmd_gemm_params;
 
 int gmd_gemm_fwd(const gmd_gemm_params* p, void* stream);

@@ -15,12 +15,17 @@ SHAPES = {  # name: (M, N, K, kind)
     "geglu_320": (65536, 2560, 320, "geglu"), "ff2_320": (65536, 320, 1280, "res32"),
     "plain_640": (16384, 640, 640, "plain"), "res32_640": (16384, 640, 640, "res32"), "geglu_640": (16384, 5120, 640, "geglu"),
     "plain_1280": (4096, 1280, 1280, "plain"), "res32_1280": (4096, 1280, 1280, "res32"),
+    # LayerNorm folding: producer (fp32 stream + bf16 copy + row statistics), consumer (normalise in the epilogue)
+    "res32_320_lnout": (65536, 320, 320, "res32+lnout"), "qkv_320_lnin": (65536, 960, 320, "plain+lnin"), "plain_320_lnin": (65536, 320, 320, "plain+lnin"),
+    "res32_640_lnout": (16384, 640, 640, "res32+lnout"), "qkv_640_lnin": (16384, 1920, 640, "plain+lnin"),
 }
 only = sys.argv[1] if len(sys.argv) > 1 else None
 reps = int(sys.argv[2]) if len(sys.argv) > 2 else 40
 for name, (M, N, K, kind) in SHAPES.items():
     if only and only != name:
         continue
+    lnout, lnin = kind.endswith("+lnout"), kind.endswith("+lnin")
+    kind = kind.split("+")[0]
     n_out = N // 2 if kind == "geglu" else N
     per_set = M * K * 2 + M * n_out * (4 if kind == "res32" else 2) + (M * N * 4 if kind == "res32" else 0)
     nsets = max(2, int(400e6 // per_set) + 1)
@@ -30,11 +35,14 @@ for name, (M, N, K, kind) in SHAPES.items():
     res = [torch.randn(M, N, device=dev, generator=g) for _ in range(nsets)] if kind == "res32" else None
     out = [torch.empty(M, n_out, device=dev, dtype=torch.float32 if kind == "res32" else bf) for _ in range(nsets)]
 
+    ln_s = torch.zeros(M, 2, dtype=torch.int64, device=dev) + (1 << 24)
+    ln_c = torch.randn(N, device=dev, generator=g)
+
     def call(i):
         if kind == "plain":
-            ops.gemm(a[i], w, bias=b, out=out[i])
+            ops.gemm(a[i], w, bias=b, out=out[i], ln_in=(ln_s, ln_c, 1e-5) if lnin else None)
         elif kind == "res32":
-            ops.gemm(a[i], w, bias=b, residual=res[i], out=out[i], out_f32=True)
+            ops.gemm(a[i], w, bias=b, residual=res[i], out=out[i], out_f32=True, ln_out=lnout)
         else:
             ops.gemm(a[i], w, bias=b, geglu=True, out=out[i])
     for i in range(nsets):

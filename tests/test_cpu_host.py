@@ -27,7 +27,7 @@ def test_library_exports_every_declared_symbol(lib):
     assert len(names) >= 17 and "gmd_attn_fwd" in names and "gmd_hdr_reconstruct" in names
     for n in names:
         assert hasattr(L, n), f"{n} declared in include/gmd_b200.h but not exported"
-    assert L.gmd_version() == 200
+    assert L.gmd_version() == 201
     assert abs(L.gmd_decode_ordered(0x3F800000) - 1.0) == 0.0 and L.gmd_decode_ordered(-2139095041) == float("-inf")
 
 

@@ -406,6 +406,40 @@ def test_layernorm(M, Cc):
     check(ops.layernorm(x32.cuda(), ga.cuda(), be.cuda()), F.layer_norm(x32, (Cc,), ga, be, 1e-5), what=f"layernorm fp32-in {M}x{Cc}")
 
 
+@pytest.mark.parametrize("M,Cc,Nq", [(4096, 320, 960), (1024, 640, 640), (1000, 1280, 1280), (8192, 320, 320)])
+def test_layernorm_folded_into_the_gemms_around_it(M, Cc, Nq):
+    """gmd_b200.h "LayerNorm folded into the GEMMs on either side of it": the GEMM that writes the fp32 token stream also emits a bf16
+    copy and exact per-row sums; the projection behind the LayerNorm multiplies the copy with W diag(gamma) and normalises in its
+    epilogue.  Reference: fp32 torch of  LN(x_out) @ W^T  with x_out = a @ Wo^T + b + residual."""
+    from gm_diffusion_b200 import ops
+    g = torch.Generator().manual_seed(M + Cc + Nq)
+    a = torch.randn(M, Cc, generator=g).to(bf)
+    wo = (torch.randn(Cc, Cc, generator=g) / Cc ** 0.5).to(bf)
+    bo = torch.randn(Cc, generator=g)
+    res = torch.randn(M, Cc, generator=g) * 2 + 0.7            # a mean the normalisation has to remove
+    ga, be = 1 + 0.3 * torch.randn(Cc, generator=g), 0.2 * torch.randn(Cc, generator=g)
+    w = torch.randn(Nq, Cc, generator=g) / Cc ** 0.5
+    x_ref = a.float() @ wo.float().t() + bo + res
+    want = F.layer_norm(x_ref, (Cc,), ga, be, 1e-5) @ w.t()
+    # producer
+    x, xb, xs = ops.gemm(a.cuda(), ops.tile_weight(wo.cuda()), bias=bo.cuda(), residual=res.cuda(), out_f32=True, ln_out=True)
+    check(x, x_ref, tol=3e-3, what="token stream")
+    assert torch.equal(xb, x.to(bf)), "the bf16 copy is the rounded stream"
+    s1 = xs[:, 0].double() / 2 ** 24
+    s2 = xs[:, 1].double() / 2 ** 24
+    assert torch.allclose(s1.cpu(), x.double().sum(1).cpu(), rtol=0, atol=1e-3) and torch.allclose(s2.cpu(), x.double().pow(2).sum(1).cpu(), rtol=1e-6, atol=1e-3)
+    # consumer
+    wg = (w * ga[None, :]).to(bf)
+    got = ops.gemm(xb, ops.tile_weight(wg.cuda()), bias=(w @ be).cuda(), ln_in=(xs, wg.float().sum(1).cuda(), 1e-5))
+    check(got, want, tol=8e-3, what=f"folded LayerNorm {M}x{Cc}->{Nq}")
+    # and it agrees with the unfolded path (LayerNorm kernel, then the plain projection) to bf16 rounding
+    plain = ops.gemm(ops.layernorm(x, ga.cuda(), be.cuda()), ops.tile_weight(w.to(bf).cuda()))
+    assert rel_l2(got, plain) < 8e-3
+    # statistics are accumulated: a second producer call into the same (not re-zeroed) buffer would double them, so every call gets a fresh one
+    _, _, xs2 = ops.gemm(a.cuda(), ops.tile_weight(wo.cuda()), bias=bo.cuda(), residual=res.cuda(), out_f32=True, ln_out=True)
+    assert torch.equal(xs, xs2), "row statistics are bit-reproducible"
+
+
 def test_softmax_silu_temb():
     from gm_diffusion_b200 import ops
     from oracle.unet_oracle import timestep_embedding
