@@ -659,7 +659,7 @@ struct Cfg2 {
     static constexpr int TM_O = NQT * CH_COLS;
     static constexpr int TMEM_USED = TM_O + NQT * HS * DPV;
     static constexpr uint32_t TMEM_COLS = TMEM_USED <= 128 ? 128 : TMEM_USED <= 256 ? 256 : 512;
-    static constexpr int MIN_CTAS = TMEM_COLS <= 128 ? 4 : TMEM_COLS <= 256 ? 2 : 1;
+    static constexpr int MIN_CTAS = TMEM_COLS <= 128 ? 3 : TMEM_COLS <= 256 ? 2 : 1;   // (3, not 4: 192 threads x 3 leaves 112 registers per thread)
     static constexpr int QT_BYTES = NDB * BQ * 128;         // one query tile
     static constexpr int Q_BYTES = NQT * QT_BYTES;
     static constexpr int KV_BLOCK_BYTES = BKV * 128;        // one d block of a K or V tile
