@@ -957,8 +957,10 @@ int launch(const CUtensorMap* maps_a, const CUtensorMap& map_w, const KernelArgs
 
 // tiles_m = number of 128-row tiles; picks the CTA tile and launches
 // 256-row CTA tiles (two accumulators per tile, B tile reused) for long K loops that still fill the 148 SMs
-inline bool want_mt2(int bn, bool res_f32, int64_t tiles_m, int64_t tiles_n, unsigned gz, int num_kb) {
-    return (bn == 160 || bn == 128) && !res_f32 && tiles_m >= 2 && num_kb >= 16 && ((tiles_m + 1) / 2) * tiles_n * gz >= 120;
+// (split-K launches count their K slices as tiles: the 8x8-resolution convolutions of a 16-sample batch are 64 output tiles x 4 slices —
+// as 256-row tiles 128 items of 52 KB per k-block in one wave instead of 256 items of 36 KB in 1.73)
+inline bool want_mt2(int bn, bool res_f32, int64_t tiles_m, int64_t tiles_n, unsigned gz, int num_kb, int ksplit = 1) {
+    return (bn == 160 || bn == 128) && !res_f32 && tiles_m >= 2 && num_kb >= 16 && ((tiles_m + 1) / 2) * tiles_n * gz * (ksplit > 1 ? ksplit : 1) >= 120;
 }
 
 int launch_cfg(int bn, int64_t tiles_m, int64_t tiles_n, unsigned gz, const CUtensorMap* maps_a, const CUtensorMap& map_w,
@@ -968,7 +970,7 @@ int launch_cfg(int bn, int64_t tiles_m, int64_t tiles_n, unsigned gz, const CUte
     // stream needs the larger private-row buffer, which only fits next to the 128-row pipeline.
     const bool res_f32 = args.residual && (args.flags & GMD_EPI_RESIDUAL_F32);
     const bool no_res = !args.residual;
-    const bool mt2 = want_mt2(bn, res_f32, tiles_m, tiles_n, gz, args.num_kb);
+    const bool mt2 = want_mt2(bn, res_f32, tiles_m, tiles_n, gz, args.ksplit > 1 ? args.kb_per_split : args.num_kb, args.ksplit);
     args.tiles_mt = (int)(mt2 ? (tiles_m + 1) / 2 : tiles_m);
     args.tiles_n = (int)tiles_n;
     args.b_resident = 0;
