@@ -79,7 +79,6 @@ __device__ __forceinline__ float exp2_poly(float x) {
 #ifndef GMD_ATTN2_POLY
 #define GMD_ATTN2_POLY 0      // every POLY-th exponential of attn2_kernel on the FMA pipe (0 = all on MUFU)
 #endif
-constexpr int POLY = GMD_ATTN2_POLY;
 #ifdef GMD_ATTN2_TRACE
 #ifndef GMD_ATTN2_TRACE_Z
 #define GMD_ATTN2_TRACE_Z 0   // the traced CTA is (0, 0, z)
@@ -641,7 +640,7 @@ int launch(const gmd_attn_params* p, cudaStream_t st) {
 //     MMA warp, two idle warps} and one per chain — and re-balances with setmaxnreg: the first gives up all but 40 registers, the
 //     softmax warpgroups grow to 232, enough for a 128-column row with the next 32-column tcgen05.ld in flight under the current
 //     chunk's exponentials.  Twice the keys per barrier hand-off (~850 cycles per tile whatever its size).
-template <int D, int BKV_, int NQT_, bool ALIAS_, int SB_, int PB_, int KS_, int HS_ = 1, int WG_ = 0>
+template <int D, int BKV_, int NQT_, bool ALIAS_, int SB_, int PB_, int KS_, int HS_ = 1, int WG_ = 0, int POLY_ = GMD_ATTN2_POLY>
 struct Cfg2 {
     static constexpr int BKV = BKV_;                        // keys per tile
     static constexpr int NQT = NQT_;                        // 128-row query tiles (chains) per CTA
@@ -651,6 +650,7 @@ struct Cfg2 {
     static constexpr int HS = HS_;                          // threads per query row (key halves of a tile as independent chains)
     static constexpr int WG = WG_;                          // 1: whole warpgroups + setmaxnreg (see above)
     static constexpr int SW0 = WG ? 4 : 2;                  // first softmax warp
+    static constexpr int POLY = POLY_;                      // every POLY-th exponential as an FMA-pipe polynomial instead of a MUFU op (0: none)
     static constexpr int NDB = (D + 63) / 64;               // 64-wide d blocks
     static constexpr int DP = (D + 15) / 16 * 16;           // K extent of Q K^T
     static constexpr int DPV = (D + 15) / 16 * 16;          // N extent of P V
@@ -686,12 +686,12 @@ struct Cfg2 {
 #else
 #define AWAIT(bar, parity) mbar_wait(bar, parity)
 #endif
-template <int D, int BKV, int NQT, bool ALIAS, int SB_, int PB_, int KS, int HS, int WG>
-__global__ void __launch_bounds__(Cfg2<D, BKV, NQT, ALIAS, SB_, PB_, KS, HS, WG>::THREADS, Cfg2<D, BKV, NQT, ALIAS, SB_, PB_, KS, HS, WG>::MIN_CTAS)
+template <int D, int BKV, int NQT, bool ALIAS, int SB_, int PB_, int KS, int HS, int WG, int POLY_>
+__global__ void __launch_bounds__(Cfg2<D, BKV, NQT, ALIAS, SB_, PB_, KS, HS, WG, POLY_>::THREADS, Cfg2<D, BKV, NQT, ALIAS, SB_, PB_, KS, HS, WG, POLY_>::MIN_CTAS)
 attn2_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_k,
              const __grid_constant__ CUtensorMap map_v, const AttnArgs args) {
-    using C = Cfg2<D, BKV, NQT, ALIAS, SB_, PB_, KS, HS, WG>;
-    constexpr int SB = C::SB, PB = C::PB, SW0 = C::SW0;
+    using C = Cfg2<D, BKV, NQT, ALIAS, SB_, PB_, KS, HS, WG, POLY_>;
+    constexpr int SB = C::SB, PB = C::PB, SW0 = C::SW0, POLY = C::POLY;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint8_t* q_smem = smem;
@@ -996,13 +996,13 @@ attn2_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ 
 int g_attn_v1 = -1;     // GMD_ATTN_V1=1 in the environment: keep the round-1 kernel for d = 40 / 80 (A/B measurements)
 int g_attn2_cfg40 = 0;  // GMD_ATTN2_CFG40: alternative d = 40 configurations for A/B measurements, see gmd_attn_fwd
 
-template <int D, int BKV, int NQT, bool ALIAS, int SB, int PB, int KS, int HS = 1, int WG = 0>
+template <int D, int BKV, int NQT, bool ALIAS, int SB, int PB, int KS, int HS = 1, int WG = 0, int POLY = GMD_ATTN2_POLY>
 int launch2(const gmd_attn_params* p, cudaStream_t st) {
-    using C = Cfg2<D, BKV, NQT, ALIAS, SB, PB, KS, HS, WG>;
+    using C = Cfg2<D, BKV, NQT, ALIAS, SB, PB, KS, HS, WG, POLY>;
     static bool configured[kMaxDevices] = {};
     const int dev = device_ordinal();
     if (!configured[dev]) {
-        cudaError_t e = cudaFuncSetAttribute(attn2_kernel<D, BKV, NQT, ALIAS, SB, PB, KS, HS, WG>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM);
+        cudaError_t e = cudaFuncSetAttribute(attn2_kernel<D, BKV, NQT, ALIAS, SB, PB, KS, HS, WG, POLY>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM);
         if (e != cudaSuccess) { set_last_error("attn2: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return kErrCuda; }
         configured[dev] = true;
     }
@@ -1029,7 +1029,7 @@ int launch2(const gmd_attn_params* p, cudaStream_t st) {
     a.scale_log2 = p->scale * 1.4426950408889634f;
     a.kv_dense = 1;
     dim3 grid((p->Nq + BQ * NQT - 1) / (BQ * NQT), p->H, p->B);
-    attn2_kernel<D, BKV, NQT, ALIAS, SB, PB, KS, HS, WG><<<grid, C::THREADS, C::SMEM, st>>>(mq, mk, mv, a);
+    attn2_kernel<D, BKV, NQT, ALIAS, SB, PB, KS, HS, WG, POLY><<<grid, C::THREADS, C::SMEM, st>>>(mq, mk, mv, a);
     count_launch(1);
     return check_launch("attn2_kernel");
 }
@@ -1377,12 +1377,12 @@ extern "C" int gmd_attn_fwd(const gmd_attn_params* p, void* stream) {
     switch (p->d) {
         case 40:
             if (xattn) return launch_x<40>(p, st);
-            // default: one thread per query row, S and P double-buffered; the alternatives are kept for A/B runs: 1 = two
-            // threads per row on independent key halves (P over S, four light softmax warps per sub-partition), 2 = three aliased S buffers,
-            // 3 = 128-key tiles, two chains per CTA, one CTA per SM with setmaxnreg-rebalanced warpgroups (917 us: slower)
-            if (v2) return g_attn2_cfg40 == 1 ? launch2<40, 64, 1, true, 2, 2, 3, 2>(p, st) : g_attn2_cfg40 == 2 ? launch2<40, 64, 1, true, 3, 3, 4, 1>(p, st)
-                         : g_attn2_cfg40 == 3 ? launch2<40, 128, 2, true, 1, 1, 3, 1, 1>(p, st)
-                         : launch2<40, 64, 1, false, 2, 2, 3>(p, st);
+            // default (same-box A/B, B=16 N=4096: 688 vs 704 us): two threads per query row on independent key halves (P over S, two S
+            // buffers, four light softmax warps per sub-partition) with every 8th exponential as an FMA-pipe polynomial.  Kept for A/B
+            // runs: 1 = one thread per row, S and P double-buffered (the round's first default), 2 = three aliased S
+            // buffers, 3 = 128-key tiles, two chains per CTA, one CTA per SM with setmaxnreg-rebalanced warpgroups (917 us)
+            if (v2) return g_attn2_cfg40 == 1 ? launch2<40, 64, 1, false, 2, 2, 3>(p, st) : g_attn2_cfg40 == 2 ? launch2<40, 64, 1, true, 3, 3, 4, 1>(p, st)
+                         : g_attn2_cfg40 == 3 ? launch2<40, 128, 2, true, 1, 1, 3, 1, 1>(p, st) : launch2<40, 64, 1, true, 2, 2, 3, 2, 0, 8>(p, st);
             return p->Nk <= 2 * BKV ? launch<40, true>(p, st) : launch<40, false>(p, st);
         case 80:
             if (xattn) return launch_x<80>(p, st);
