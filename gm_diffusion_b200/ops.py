@@ -134,6 +134,16 @@ def _gn_sums_alloc(device, n: int, c: int) -> torch.Tensor:
     return torch.zeros((n, c // 2, 2), dtype=torch.int64, device=device)
 
 
+def dup_rows(t: torch.Tensor) -> torch.Tensor:
+    """[t ; t] along dim 0 (the two CFG halves of a still-shared activation) as two device-to-device memcpys — no copy kernel."""
+    t = t.contiguous()
+    n = t.shape[0]
+    out = torch.empty((2 * n,) + tuple(t.shape[1:]), dtype=t.dtype, device=t.device)
+    out[:n].copy_(t)
+    out[n:].copy_(t)
+    return out
+
+
 def gemm(a: torch.Tensor, w: torch.Tensor, *, bias: Optional[torch.Tensor] = None, residual: Optional[torch.Tensor] = None,
          row_bias: Optional[torch.Tensor] = None, rows_per_sample: int = 0, geglu: bool = False, out: Optional[torch.Tensor] = None,
          out_f32: bool = False, alpha: Optional[float] = None, splitk: bool = False, gn_rows_per_sample: int = 0,

@@ -135,10 +135,10 @@ class _Transformer:
         else:
             y = ops.gemm(a.view(m, c), self.w_o1, bias=self.b_o1, residual=y, out_f32=True)
         if dup:
-            y = torch.cat([y, y], 0)
-            x = torch.cat([x, x], 0)
+            y = ops.dup_rows(y)
+            x = ops.dup_rows(x)
             if fold:
-                yb, ys = torch.cat([yb, yb], 0), torch.cat([ys, ys], 0)
+                yb, ys = ops.dup_rows(yb), ops.dup_rows(ys)
             B, m = 2 * B, 2 * m
         # text cross-attention (K/V hoisted)
         if fold:
@@ -277,7 +277,7 @@ class B200UNet:
         hints = self.__dict__.setdefault("_gn_words", {})
         with ops.gn_arena(self.device, hints.get((full, sample.shape[1], sample.shape[2]))) as arena:   # one memset zeroes every GroupNorm accumulator of the pass
             x, xs = ops.conv2d(sample, self.w_in, self.ch0, bias=self.b_in, gn_stats=True)
-            dup2 = lambda t_: None if t_ is None else torch.cat([t_, t_], 0)
+            dup2 = lambda t_: None if t_ is None else ops.dup_rows(t_)
             skips = [(dup2(x), dup2(xs)) if cfg_shared else (x, xs)]       # every activation travels with its GroupNorm statistics
             pending_dup = cfg_shared
             for res, att, ds in self.down:
