@@ -266,7 +266,8 @@ def test_conv_stride2_pad_end(N, H, W, C, Cout):
 
 @pytest.mark.parametrize("B,H,Nq,Nk,d", [(2, 8, 4096, 4096, 40), (2, 8, 1024, 1024, 80), (2, 8, 256, 256, 160), (3, 8, 64, 64, 160),
                                          (2, 8, 4096, 77, 40), (2, 8, 1024, 77, 80), (2, 8, 256, 77, 160), (1, 8, 200, 130, 40),
-                                         (1, 8, 256, 64, 80), (1, 8, 300, 130, 80), (2, 8, 512, 200, 80), (1, 8, 1000, 448, 80), (1, 8, 256, 128, 80)])
+                                         (1, 8, 256, 64, 80), (1, 8, 300, 130, 80), (2, 8, 512, 200, 80), (1, 8, 1000, 448, 80), (1, 8, 256, 128, 80),
+                                         (1, 8, 300, 170, 40), (2, 8, 640, 1000, 40), (1, 8, 129, 161, 40)])   # ragged key counts through both key halves of a tile
 def test_attention(B, H, Nq, Nk, d):
     from gm_diffusion_b200 import ops
     g = torch.Generator().manual_seed(Nq + Nk + d)
