@@ -76,6 +76,39 @@ __device__ __forceinline__ float exp2_poly(float x) {
     p = fmaf(p, f, 1.0f);
     return __int_as_float(__float_as_int(p) + (__float_as_int(xf) << 23));
 }
+#ifndef GMD_ATTN2_F32X2
+#define GMD_ATTN2_F32X2 1     // scale-and-shift and the row sums of attn2_kernel as packed fp32 pairs (FFMA2 / FADD2: half the issue slots; 0 = scalar, A/B)
+#endif
+// Blackwell's packed fp32 pair arithmetic (fma / add .f32x2 -> FFMA2 / FADD2): one issue slot for two lanes of a 64-bit register pair.
+__device__ __forceinline__ uint64_t f32x2_pack(float a, float b) { uint64_t r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b)); return r; }
+__device__ __forceinline__ void f32x2_unpack(uint64_t v, float& a, float& b) { asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v)); }
+__device__ __forceinline__ uint64_t f32x2_fma(uint64_t a, uint64_t b, uint64_t c) { uint64_t d; asm("fma.rn.ftz.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c)); return d; }
+__device__ __forceinline__ uint64_t f32x2_add(uint64_t a, uint64_t b) { uint64_t d; asm("add.rn.ftz.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
+#ifndef GMD_ATTN2_POLYPAIR
+#define GMD_ATTN2_POLYPAIR 1  // 1: the polynomial exponentials of attn2_kernel come in adjacent pairs (elements 2*POLY-2, 2*POLY-1 of every 2*POLY) on FFMA2 / FADD2
+#endif
+// exp2_poly for a register pair: the same arithmetic, five packed instructions + clamp and exponent insertion per lane.
+__device__ __forceinline__ void exp2_poly2(uint64_t x2, float& p0, float& p1, float& xmax) {
+    float x0, x1;
+    f32x2_unpack(x2, x0, x1);
+    xmax = fmaxf(xmax, fmaxf(x0, x1));   // (exponents >= 128 wrap around in the bit arithmetic below: the caller must notice them)
+    x2 = f32x2_pack(fmaxf(x0, -125.0f), fmaxf(x1, -125.0f));
+    const uint64_t xf = f32x2_add(x2, f32x2_pack(12582912.0f, 12582912.0f));
+    const uint64_t rn = f32x2_add(xf, f32x2_pack(-12582912.0f, -12582912.0f));
+    const uint64_t f = f32x2_fma(rn, f32x2_pack(-1.0f, -1.0f), x2);
+    uint64_t p = f32x2_fma(f, f32x2_pack(0.0555041086f, 0.0555041086f), f32x2_pack(0.2402265069f, 0.2402265069f));
+    p = f32x2_fma(p, f, f32x2_pack(0.6931471806f, 0.6931471806f));
+    p = f32x2_fma(p, f, f32x2_pack(1.0f, 1.0f));
+    float pa, pb, xa, xb;
+    f32x2_unpack(p, pa, pb);
+    f32x2_unpack(xf, xa, xb);
+    p0 = __int_as_float(__float_as_int(pa) + (__float_as_int(xa) << 23));
+    p1 = __int_as_float(__float_as_int(pb) + (__float_as_int(xb) << 23));
+}
+#ifndef GMD_ATTN2_SUMGROW
+#define GMD_ATTN2_SUMGROW 1   // attn2_kernel detects a row maximum leaving the lazy window from the tile's row SUM (> 2^16) instead of forming the maximum of
+                              // every tile: no FMNMX on the fast path; the true maximum is read back from S only on the rare rescale path (0: maximum per tile, A/B)
+#endif
 #ifndef GMD_ATTN2_POLY
 #define GMD_ATTN2_POLY 0      // every POLY-th exponential of attn2_kernel on the FMA pipe (0 = all on MUFU)
 #endif
@@ -92,6 +125,9 @@ __device__ long long g_attn_trace[8 * 1024];
 #else
 #define TRACE(slot, j) do { } while (0)
 #define TRACE_CLK(i) do { } while (0)
+#endif
+#ifndef GMD_ATTN2_POLY40
+#define GMD_ATTN2_POLY40 4     // the d = 40 default: a quarter of the exponentials on the FMA pipe
 #endif
 #ifndef GMD_ATTN2_KO
 #define GMD_ATTN2_KO 0        // timing-only knock-outs of attn2_kernel (wrong results): 1 no MUFU, 2 no P stores, 4 no S loads, 8 no row sums / maxima, 16 no K / V traffic after the first ring fill
@@ -833,9 +869,14 @@ attn2_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ 
         // formed on the side (never on the exponentials' dependency chain).  MASK: columns >= valid are padding keys (last tile of
         // a ragged key count only).  The exponentials are plain (non-volatile) asm behind tmem_wait_ld_regs, so ptxas interleaves the
         // 32 independent fma -> ex2 -> add / pack chains of a chunk freely (one MUFU every ~4 issue slots in the SASS).
-        auto tile_pass = [&](auto exp_tag, auto mask_tag, uint32_t s_addr, int valid, float m_use, uint32_t* pk, float& mx_out, float& lsum) {
+        auto tile_pass = [&](auto exp_tag, auto mask_tag, uint32_t s_addr, int valid, float m_use, uint32_t* pk, float& mx_out, float& lsum, float& px_out) {
             constexpr bool EXP = decltype(exp_tag)::value, MASK = decltype(mask_tag)::value;
             float mx0 = -INFINITY, mx1 = -INFINITY, l0 = 0.0f, l1 = 0.0f, l2 = 0.0f, l3 = 0.0f;
+            float px = -INFINITY;   // largest exponent that went through the polynomial (which wraps around beyond 2^127 instead of returning +inf)
+#if GMD_ATTN2_F32X2
+            uint64_t l01 = f32x2_pack(0.0f, 0.0f), l23 = l01;
+            const uint64_t c2 = f32x2_pack(c, c), nm2 = f32x2_pack(-m_use, -m_use);
+#endif
             // PIPE (one CTA per SM: registers to spare): the next chunk's tcgen05.ld is in flight while this chunk is exponentiated
             constexpr bool PIPE = WG && NCH > 1 && !(GMD_ATTN2_KO & 4);
             uint32_t rr[PIPE ? 2 : 1][32];
@@ -857,26 +898,52 @@ attn2_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ 
 #pragma unroll
                     for (int k = 0; k < 32; ++k) if (ch * 32 + k >= valid) r[k] = 0xff800000u;   // -inf
                 }
+                if (!EXP || !GMD_ATTN2_SUMGROW) {
 #pragma unroll
-                for (int k = 0; k < ((GMD_ATTN2_KO & 8) ? 4 : 32); k += 4) {
-                    mx0 = fmaxf(mx0, fmaxf(__uint_as_float(r[k]), __uint_as_float(r[k + 1])));
-                    mx1 = fmaxf(mx1, fmaxf(__uint_as_float(r[k + 2]), __uint_as_float(r[k + 3])));
+                    for (int k = 0; k < ((GMD_ATTN2_KO & 8) ? 4 : 32); k += 4) {
+                        mx0 = fmaxf(mx0, fmaxf(__uint_as_float(r[k]), __uint_as_float(r[k + 1])));
+                        mx1 = fmaxf(mx1, fmaxf(__uint_as_float(r[k + 2]), __uint_as_float(r[k + 3])));
+                    }
                 }
                 if (EXP) {
                     float pr[32];
+                    constexpr bool PAIR = GMD_ATTN2_F32X2 && GMD_ATTN2_POLYPAIR && POLY > 0;
+                    auto expo = [&](int k, float x) {
+                        if (GMD_ATTN2_KO & 1) return x;
+                        if (!PAIR && POLY > 0 && (k % (POLY > 0 ? POLY : 1)) == POLY - 1) { px = fmaxf(px, x); return exp2_poly(x); }
+                        return ex2(x);
+                    };
+#if GMD_ATTN2_F32X2
 #pragma unroll
-                    for (int k = 0; k < 32; ++k) {
-                        const float x = fmaf(__uint_as_float(r[k]), c, -m_use);
-                        pr[k] = (GMD_ATTN2_KO & 1) ? x : (POLY > 0 && (k % (POLY > 0 ? POLY : 1)) == POLY - 1) ? exp2_poly(x) : ex2(x);
+                    for (int k = 0; k < 32; k += 2) {
+                        const uint64_t x2 = f32x2_fma(f32x2_pack(__uint_as_float(r[k]), __uint_as_float(r[k + 1])), c2, nm2);
+                        if (PAIR && !(GMD_ATTN2_KO & 1) && (k % (2 * (POLY > 0 ? POLY : 1))) == 2 * POLY - 2) {
+                            exp2_poly2(x2, pr[k], pr[k + 1], px);
+                        } else {
+                            float x0, x1;
+                            f32x2_unpack(x2, x0, x1);
+                            pr[k] = expo(k, x0); pr[k + 1] = expo(k + 1, x1);
+                        }
                     }
 #pragma unroll
+                    for (int k = 0; k < ((GMD_ATTN2_KO & 8) ? 4 : 32); k += 4) { l01 = f32x2_add(l01, f32x2_pack(pr[k], pr[k + 1])); l23 = f32x2_add(l23, f32x2_pack(pr[k + 2], pr[k + 3])); }
+#else
+#pragma unroll
+                    for (int k = 0; k < 32; ++k) pr[k] = expo(k, fmaf(__uint_as_float(r[k]), c, -m_use));
+#pragma unroll
                     for (int k = 0; k < ((GMD_ATTN2_KO & 8) ? 4 : 32); k += 4) { l0 += pr[k]; l1 += pr[k + 1]; l2 += pr[k + 2]; l3 += pr[k + 3]; }
+#endif
 #pragma unroll
                     for (int k = 0; k < 16; ++k) pk[ch * 16 + k] = pack_bf16x2(pr[2 * k], pr[2 * k + 1]);
                 }
             }
             mx_out = fmaxf(mx0, mx1);
+#if GMD_ATTN2_F32X2
+            f32x2_unpack(f32x2_add(l01, l23), l0, l1);
+            l2 = l3 = 0.0f;
+#endif
             lsum = (l0 + l1) + (l2 + l3);
+            px_out = px;
         };
         auto do_tile = [&](auto mask_tag, int j) {
             const int sb = j % SB, pb = j % PB;
@@ -885,20 +952,31 @@ attn2_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ 
             AWAIT(&s_full[t * SB + sb], (j / SB) & 1);
             tc_fence_after();
             if (warp == SW0 && lane == 0) { TRACE(6, j); if (j == 0) TRACE_CLK(0); }
-            float mx, ls;
+            float mx, ls, px;
             uint32_t pk[NCH * 16];
             if (j == 0) {   // first tile: maximum first
-                tile_pass(std::false_type{}, mask_tag, s_addr, valid, 0.0f, pk, mx, ls);
+                tile_pass(std::false_type{}, mask_tag, s_addr, valid, 0.0f, pk, mx, ls, px);
                 m = mx * c;
             }
             const float m_use = m == -INFINITY ? 0.0f : m;   // no valid key yet: 2^(-inf) = 0
-            tile_pass(std::true_type{}, mask_tag, s_addr, valid, m_use, pk, mx, ls);
-            const float mt = mx * c;
+            tile_pass(std::true_type{}, mask_tag, s_addr, valid, m_use, pk, mx, ls, px);
+#if GMD_ATTN2_SUMGROW
+            // every probability is positive, so a row sum <= 2^16 proves that no exponent of this thread's keys exceeded 16 (the window is
+            // wide because P is bf16 with fp32's exponent range and O, l are fp32: nothing overflows below 2^100); +inf (an exponent > 128) trips it too
+            bool grow = ls > 65536.0f || px > 16.0f;
+#else
+            float mt = mx * c;
             const bool grow = mt > m + C::LAZY_T;
+#endif
             if (__any_sync(0xffffffffu, grow)) {
                 // rare: a row maximum left the lazy window.  S_j is still intact in TMEM (P_j has not been stored yet and the buffer is
                 // only released by the p_full arrival below): take the new maximum, bring O and l to the new scale and exponentiate
                 // the tile again.
+#if GMD_ATTN2_SUMGROW
+                tile_pass(std::false_type{}, mask_tag, s_addr, valid, 0.0f, pk, mx, ls, px);   // the tile's true maximum, from S
+                const float mt = mx * c;
+                grow = grow && mt > m;
+#endif
                 const float m_new = grow ? mt : m;
                 const float alpha = grow ? ex2(m - m_new) : 1.0f;    // (m is finite here: j > 0 or the maximum-first pass ran)
                 m = m_new;
@@ -917,7 +995,7 @@ attn2_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ 
                     }
                     tmem_wait_st();
                 }
-                tile_pass(std::true_type{}, mask_tag, s_addr, valid, m, pk, mx, ls);
+                tile_pass(std::true_type{}, mask_tag, s_addr, valid, m, pk, mx, ls, px);
             }
             l += ls;
             // The P buffer was last read by P V_{j-PB}.  ALIAS: P V_{j-1} was issued before S_j by the same thread, so s_full(j) implies
@@ -1382,7 +1460,7 @@ extern "C" int gmd_attn_fwd(const gmd_attn_params* p, void* stream) {
             // runs: 1 = one thread per row, S and P double-buffered (the round's first default), 2 = three aliased S
             // buffers, 3 = 128-key tiles, two chains per CTA, one CTA per SM with setmaxnreg-rebalanced warpgroups (917 us)
             if (v2) return g_attn2_cfg40 == 1 ? launch2<40, 64, 1, false, 2, 2, 3>(p, st) : g_attn2_cfg40 == 2 ? launch2<40, 64, 1, true, 3, 3, 4, 1>(p, st)
-                         : g_attn2_cfg40 == 3 ? launch2<40, 128, 2, true, 1, 1, 3, 1, 1>(p, st) : launch2<40, 64, 1, true, 2, 2, 3, 2, 0, 8>(p, st);
+                         : g_attn2_cfg40 == 3 ? launch2<40, 128, 2, true, 1, 1, 3, 1, 1>(p, st) : launch2<40, 64, 1, true, 2, 2, 3, 2, 0, GMD_ATTN2_POLY40>(p, st);
             return p->Nk <= 2 * BKV ? launch<40, true>(p, st) : launch<40, false>(p, st);
         case 80:
             if (xattn) return launch_x<80>(p, st);
