@@ -109,6 +109,9 @@ __device__ __forceinline__ void exp2_poly2(uint64_t x2, float& p0, float& p1, fl
 #define GMD_ATTN2_SUMGROW 1   // attn2_kernel detects a row maximum leaving the lazy window from the tile's row SUM (> 2^16) instead of forming the maximum of
                               // every tile: no FMNMX on the fast path; the true maximum is read back from S only on the rare rescale path (0: maximum per tile, A/B)
 #endif
+#ifndef GMD_ATTN2_UNROLL
+#define GMD_ATTN2_UNROLL 1    // unroll factor of the softmax warps' tile loop
+#endif
 #ifndef GMD_ATTN2_POLY
 #define GMD_ATTN2_POLY 0      // every POLY-th exponential of attn2_kernel on the FMA pipe (0 = all on MUFU)
 #endif
@@ -714,14 +717,33 @@ struct Cfg2 {
     static_assert(NBAR * 8 + 4 <= 256, "barrier block");
 };
 
+// Waits of attn2_kernel.  A waiting warp is not free: every failed poll is an issue slot and an MIO-queue instruction taken from the
+// softmax warps of its sub-partition (a tight inline-asm poll loop cost 6 % at d = 40, the loop with a clock64 watchdog between polls
+// was 4 % FASTER with try_wait than with test_wait), so each role polls as rarely as its latency budget allows:
+//   TMA lanes (ring slots: tiles of slack)  GMD_ATTN2_TMA_SLEEP ns between polls
+//   MMA thread (V / K operands, P hand-off) GMD_ATTN2_MMA_SLEEP ns
+//   softmax warps (S hand-off)              GMD_ATTN2_SM_SLEEP ns            (0: try_wait loop without a sleep)
 #ifndef GMD_ATTN2_TESTWAIT
-#define GMD_ATTN2_TESTWAIT 1   // hand-offs between the MMA thread and the softmax warps poll with mbarrier.test_wait (0: try_wait, A/B)
+#define GMD_ATTN2_TESTWAIT 0   // 1: hand-offs between the MMA thread and the softmax warps poll with mbarrier.test_wait (A/B)
 #endif
-#if GMD_ATTN2_TESTWAIT
-#define AWAIT(bar, parity) mbar_wait_poll(bar, parity)
-#else
-#define AWAIT(bar, parity) mbar_wait(bar, parity)
+#ifndef GMD_ATTN2_TMA_SLEEP
+#define GMD_ATTN2_TMA_SLEEP 0
 #endif
+#ifndef GMD_ATTN2_MMA_SLEEP
+#define GMD_ATTN2_MMA_SLEEP 0
+#endif
+#ifndef GMD_ATTN2_SM_SLEEP
+#define GMD_ATTN2_SM_SLEEP 0
+#endif
+template <int NS>
+__device__ __forceinline__ void attn2_wait(uint64_t* bar, uint32_t parity) {
+    if (NS > 0) mbar_wait_sleep(bar, parity, NS);
+    else if (GMD_ATTN2_TESTWAIT) mbar_wait_poll(bar, parity);
+    else mbar_wait(bar, parity);
+}
+#define AWAIT(bar, parity) attn2_wait<GMD_ATTN2_SM_SLEEP>(bar, parity)
+#define MWAIT(bar, parity) attn2_wait<GMD_ATTN2_MMA_SLEEP>(bar, parity)
+#define TWAIT(bar, parity) attn2_wait<GMD_ATTN2_TMA_SLEEP>(bar, parity)
 template <int D, int BKV, int NQT, bool ALIAS, int SB_, int PB_, int KS, int HS, int WG, int POLY_>
 __global__ void __launch_bounds__(Cfg2<D, BKV, NQT, ALIAS, SB_, PB_, KS, HS, WG, POLY_>::THREADS, Cfg2<D, BKV, NQT, ALIAS, SB_, PB_, KS, HS, WG, POLY_>::MIN_CTAS)
 attn2_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_k,
@@ -781,7 +803,7 @@ attn2_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ 
             // the same tile — one in-order stream would hold K_{j+KS} back behind V_{j+KS-1}, i.e. behind P V_{j-1})
             for (int j = 0; j < T; ++j) {
                 const int st = j % KS;
-                mbar_wait(&k_empty[st], ((j / KS) & 1) ^ 1);
+                TWAIT(&k_empty[st], ((j / KS) & 1) ^ 1);
                 if ((GMD_ATTN2_KO & 16) && j >= KS) { mbar_arrive(&k_full[st]); continue; }   // timing only: no K / V traffic after the first ring fill
                 mbar_expect_tx(&k_full[st], C::K_BYTES);
                 for (int b = 0; b < C::NDB; ++b) tma_load_3d(k_smem + st * C::K_BYTES + b * C::KV_BLOCK_BYTES, &map_k, &k_full[st], head * D + b * 64, j * BKV, batch);
@@ -790,7 +812,7 @@ attn2_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ 
         } else if (lane == 1) {
             for (int j = 0; j < T; ++j) {
                 const int st = j % KS;
-                mbar_wait(&v_empty[st], ((j / KS) & 1) ^ 1);
+                TWAIT(&v_empty[st], ((j / KS) & 1) ^ 1);
                 if ((GMD_ATTN2_KO & 16) && j >= KS) { mbar_arrive(&v_full[st]); continue; }
                 mbar_expect_tx(&v_full[st], C::K_BYTES);
                 for (int b = 0; b < C::NDB; ++b) tma_load_3d(v_smem + st * C::K_BYTES + b * C::KV_BLOCK_BYTES, &map_v, &v_full[st], head * D + b * 64, j * BKV, batch);
@@ -804,7 +826,7 @@ attn2_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ 
             // S_t(j) = Q_t K_j^T.  The K tile is polled once per j (chain 0) and released after the last chain's MMAs.
             auto issue_s = [&](int t, int j, bool polled) {
                 const int st = j % KS;
-                if (t == 0 && !polled) { AWAIT(&k_full[st], (j / KS) & 1); tc_fence_after(); TRACE(1, j); }
+                if (t == 0 && !polled) { MWAIT(&k_full[st], (j / KS) & 1); tc_fence_after(); TRACE(1, j); }
                 const uint32_t k_addr = smem_u32(k_smem + st * C::K_BYTES);
 #pragma unroll
                 for (int ks = 0; ks < C::DP / 16; ++ks) {
@@ -817,7 +839,7 @@ attn2_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ 
                 if (t == NQT - 1) umma_commit(&k_empty[st]);
                 if (t == 0) TRACE(2, j);
             };
-            AWAIT(q_full, 0);
+            MWAIT(q_full, 0);
             for (int i = 0; i < SB && i < T; ++i)
                 for (int t = 0; t < NQT; ++t) issue_s(t, i, false);
             for (int j = 0; j < T; ++j) {
@@ -827,14 +849,14 @@ attn2_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ 
                 // thread 100-230 cycles while the softmax warps keep the sub-partition's MIO queue busy (clock64 trace) — so that nothing
                 // but the MMA issue itself stands between "P_j is in TMEM" and S_{j+SB}, the tile the softmax warps will wait for.
                 const bool next_s = j + SB < T;
-                AWAIT(&v_full[st], (j / KS) & 1);
+                MWAIT(&v_full[st], (j / KS) & 1);
                 TRACE(4, j);
                 // (K_{j+SB} only where it has a ring slot of its own: with KS == SB its load starts when S_j completes and may still be in flight)
                 constexpr bool EARLY_K = KS > SB;
-                if (EARLY_K && next_s) { AWAIT(&k_full[(j + SB) % KS], ((j + SB) / KS) & 1); TRACE(1, j + SB); }
+                if (EARLY_K && next_s) { MWAIT(&k_full[(j + SB) % KS], ((j + SB) / KS) & 1); TRACE(1, j + SB); }
 #pragma unroll
                 for (int t = 0; t < NQT; ++t) {
-                    AWAIT(&p_full[t * PB + pb], (j / PB) & 1);       // P_t(j) in TMEM; S_t(j) read (its buffer may be overwritten)
+                    MWAIT(&p_full[t * PB + pb], (j / PB) & 1);       // P_t(j) in TMEM; S_t(j) read (its buffer may be overwritten)
                     tc_fence_after();
                     if (t == 0) TRACE(3, j);
 #pragma unroll
@@ -945,7 +967,8 @@ attn2_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ 
             lsum = (l0 + l1) + (l2 + l3);
             px_out = px;
         };
-        auto do_tile = [&](auto mask_tag, int j) {
+        auto do_tile = [&](auto mask_tag, auto first_tag, int j) {
+            constexpr bool FIRST = decltype(first_tag)::value;   // j == 0 (its own copy of the tile body: no per-tile branch in the steady state)
             const int sb = j % SB, pb = j % PB;
             const uint32_t s_addr = tm_s(t, sb) + lane_off + hw * (BKV / HS), p_addr = tm_p(t, pb, hw) + lane_off;
             const int valid = args.Nk - j * BKV - hw * (BKV / HS);
@@ -954,7 +977,7 @@ attn2_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ 
             if (warp == SW0 && lane == 0) { TRACE(6, j); if (j == 0) TRACE_CLK(0); }
             float mx, ls, px;
             uint32_t pk[NCH * 16];
-            if (j == 0) {   // first tile: maximum first
+            if (FIRST) {   // first tile: maximum first
                 tile_pass(std::false_type{}, mask_tag, s_addr, valid, 0.0f, pk, mx, ls, px);
                 m = mx * c;
             }
@@ -968,7 +991,7 @@ attn2_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ 
             float mt = mx * c;
             const bool grow = mt > m + C::LAZY_T;
 #endif
-            if (__any_sync(0xffffffffu, grow)) {
+            if (__builtin_expect(__any_sync(0xffffffffu, grow), 0)) {
                 // rare: a row maximum left the lazy window.  S_j is still intact in TMEM (P_j has not been stored yet and the buffer is
                 // only released by the p_full arrival below): take the new maximum, bring O and l to the new scale and exponentiate
                 // the tile again.
@@ -1014,8 +1037,15 @@ attn2_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ 
             if (warp == SW0 && lane == 0) { TRACE(7, j); if (j == T - 1) TRACE_CLK(1); }
         };
         const bool ragged = (args.Nk % BKV) != 0;
-        for (int j = 0; j < T - 1; ++j) do_tile(std::false_type{}, j);
-        if (ragged) do_tile(std::true_type{}, T - 1); else do_tile(std::false_type{}, T - 1);
+        if (T == 1) {
+            if (ragged) do_tile(std::true_type{}, std::true_type{}, 0); else do_tile(std::false_type{}, std::true_type{}, 0);
+        } else {
+            do_tile(std::false_type{}, std::true_type{}, 0);
+            constexpr int UNROLL_J = GMD_ATTN2_UNROLL;
+#pragma unroll UNROLL_J
+            for (int j = 1; j < T - 1; ++j) do_tile(std::false_type{}, std::false_type{}, j);
+            if (ragged) do_tile(std::true_type{}, std::false_type{}, T - 1); else do_tile(std::false_type{}, std::false_type{}, T - 1);
+        }
         AWAIT(&pv_done[t * PB + (T - 1) % PB], ((T - 1) / PB) & 1);
         tc_fence_after();
         const int q = q0 + t * BQ + row;
