@@ -15,6 +15,14 @@
 #include "common.cuh"
 #include "../../include/gmd_b200.h"
 
+#ifndef GMD_GEMM_SVC_SLEEP
+#define GMD_GEMM_SVC_SLEEP 0   // ns between barrier polls of the producer and MMA threads (0: plain try_wait loop); a polling thread takes issue slots from the epilogue warps of its sub-partition
+#endif
+#if GMD_GEMM_SVC_SLEEP > 0
+#define SVC_WAIT(bar, parity) mbar_wait_sleep(bar, parity, GMD_GEMM_SVC_SLEEP)
+#else
+#define SVC_WAIT(bar, parity) mbar_wait(bar, parity)
+#endif
 namespace gmd {
 void count_launch(int n);
 namespace {
@@ -299,7 +307,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__ 
                 for (int sx = 0; sx < 3; ++sx) {
                     for (int cc = 0; cc < chunks; ++cc, ++ag) {
                         const int slot = ag % P::A_SLOTS;
-                        mbar_wait(&a_empty[slot], ((ag / P::A_SLOTS) & 1) ^ 1);
+                        SVC_WAIT(&a_empty[slot], ((ag / P::A_SLOTS) & 1) ^ 1);
                         const CUtensorMap* am = cc < args.chunks0 ? &map_a2 : &map_a3;
                         const int ac = cc < args.chunks0 ? cc * BK : (cc - args.chunks0) * BK;
                         if (PAIR) {
@@ -313,7 +321,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__ 
                         for (int r = 0; r < 3; ++r, ++kbg) {
                             const int kb = (r * 3 + sx) * chunks + cc;
                             const int stage = kbg % STAGES;
-                            mbar_wait(&empty_bar[stage], ((kbg / STAGES) & 1) ^ 1);
+                            SVC_WAIT(&empty_bar[stage], ((kbg / STAGES) & 1) ^ 1);
                             if (PAIR) {
                                 if (crank == 0) mbar_expect_tx(&full_bar[stage], 2 * P::B_BYTES);
                                 tma_load_3d_2sm(smem + P::OFF_B + stage * P::B_BYTES, &map_w, &full_bar[stage], 0,
@@ -353,7 +361,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__ 
                 for (int kb = kb_begin; kb < kb_end; ++kb, ++kbg) {
                     const int stage = kbg % STAGES;
                     const uint32_t phase = (kbg / STAGES) & 1;
-                    mbar_wait(&empty_bar[stage], phase ^ 1);
+                    SVC_WAIT(&empty_bar[stage], phase ^ 1);
                     uint8_t* sa = smem + stage * P::STAGE_BYTES;
                     uint8_t* sb = sa + P::A_BYTES;
                     if (PAIR) {
@@ -437,22 +445,22 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__ 
 #pragma unroll
                     for (int s = 0; s < MT; ++s) {
                         const uint32_t u = 2 * it + s;
-                        mbar_wait(&acc_empty[u % 3], ((u / 3) & 1) ^ 1);
+                        SVC_WAIT(&acc_empty[u % 3], ((u / 3) & 1) ^ 1);
                         tsl[s] = tmem_acc + (u % 3) * BN;
                     }
                 } else {
-                    mbar_wait(&acc_empty[ab], ((it / ACC) & 1) ^ 1);
+                    SVC_WAIT(&acc_empty[ab], ((it / ACC) & 1) ^ 1);
 #pragma unroll
                     for (int s = 0; s < MT; ++s) tsl[s] = tmem_acc + ab * P::ACC_COLS + s * BN;
                 }
                 tc_fence_after();
                 for (int g = 0; g < groups; ++g, ++ag) {
                     const int slot = ag % P::A_SLOTS;
-                    mbar_wait(&a_full[slot], (ag / P::A_SLOTS) & 1);
+                    SVC_WAIT(&a_full[slot], (ag / P::A_SLOTS) & 1);
                     const uint32_t sa = smem_u32(smem + slot * P::A_BYTES);
                     for (int r = 0; r < 3; ++r, ++kbg) {
                         const int stage = kbg % STAGES;
-                        mbar_wait(&full_bar[stage], (kbg / STAGES) & 1);
+                        SVC_WAIT(&full_bar[stage], (kbg / STAGES) & 1);
                         tc_fence_after();
                         const uint64_t db = umma_desc_k_sw128(smem_u32(smem + P::OFF_B + stage * P::B_BYTES));
                         const uint32_t sar = sa + (uint32_t)(r * args.bw) * (BK * 2);   // vertical tap r: r image rows further down
@@ -484,11 +492,11 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__ 
 #pragma unroll
                     for (int s = 0; s < MT; ++s) {
                         const uint32_t u = 2 * it + s;
-                        mbar_wait(&acc_empty[u % 3], ((u / 3) & 1) ^ 1);
+                        SVC_WAIT(&acc_empty[u % 3], ((u / 3) & 1) ^ 1);
                         tsl[s] = tmem_acc + (u % 3) * BN;
                     }
                 } else {
-                    mbar_wait(&acc_empty[ab], ((it / ACC) & 1) ^ 1);   // epilogue has drained this accumulator set
+                    SVC_WAIT(&acc_empty[ab], ((it / ACC) & 1) ^ 1);   // epilogue has drained this accumulator set
 #pragma unroll
                     for (int s = 0; s < MT; ++s) tsl[s] = tmem_acc + ab * P::ACC_COLS + s * BN;
                 }
@@ -499,7 +507,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__ 
                 for (int kb = kb_begin; kb < kb_end; ++kb, ++kbg) {
                     const int stage = kbg % STAGES;
                     const uint32_t phase = (kbg / STAGES) & 1;
-                    mbar_wait(&full_bar[stage], phase);
+                    SVC_WAIT(&full_bar[stage], phase);
                     tc_fence_after();
                     const uint32_t sa = smem_u32(smem + stage * P::STAGE_BYTES);
                     const uint64_t db = umma_desc_k_sw128(sa + P::A_BYTES);

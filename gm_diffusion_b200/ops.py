@@ -67,9 +67,35 @@ def tile_weight(w: torch.Tensor, geglu: bool = False, swizzle: bool = True) -> T
 
 
 
+_SLOT = 0
+
+
+class scratch_slot:
+    """Static scratch (split-K workspace, GroupNorm accumulator arena) is per (device, slot).  Work that runs CONCURRENTLY with other
+    work of this library on the same device — the GM UNet on a side stream beside the SDR UNet of the next step — selects a slot of
+    its own with `with ops.scratch_slot(1): ...`; everything else uses slot 0."""
+
+    def __init__(self, slot: int):
+        self.slot = int(slot)
+
+    def __enter__(self):
+        global _SLOT
+        self.prev, _SLOT = _SLOT, self.slot
+        return self
+
+    def __exit__(self, *exc):
+        global _SLOT
+        _SLOT = self.prev
+        return False
+
+
+def _scratch_key(device):
+    return (torch.device(device).index or 0, _SLOT)
+
+
 def splitk_workspace(device) -> torch.Tensor:
-    """fp32 scratch for the split-K partial sums of the few-tile / long-K layers (allocated once per device, static address)."""
-    key = torch.device(device).index or 0
+    """fp32 scratch for the split-K partial sums of the few-tile / long-K layers (allocated once per device and slot, static address)."""
+    key = _scratch_key(device)
     ws = _WS.get(key)
     if ws is None:
         ws = torch.empty(128 << 20, dtype=torch.uint8, device=device)
@@ -95,7 +121,7 @@ class gn_arena:
     WORDS = 8 << 20
 
     def __init__(self, device, words_hint=None):
-        self.key = torch.device(device).index or 0
+        self.key = _scratch_key(device)
         self.device, self.hint, self.used = device, words_hint, 0
 
     def __enter__(self):
@@ -128,7 +154,7 @@ class gn_arena:
 
 
 def _gn_sums_alloc(device, n: int, c: int) -> torch.Tensor:
-    st = _GN_ARENA.get(torch.device(device).index or 0)
+    st = _GN_ARENA.get(_scratch_key(device))
     if st is not None and st["active"] is not None:
         return st["active"].alloc(n, c)
     return torch.zeros((n, c // 2, 2), dtype=torch.int64, device=device)

@@ -74,6 +74,12 @@ class StableDiffusionDualUNetPipeline(PipelineBase):
         self._pair_ws: Dict[Any, Dict[str, Any]] = {}
         self._loop_graphs: Dict[Any, Any] = {}
         self.use_loop_graph = True   # capture the whole denoising loop as one CUDA graph when nothing needs the host between steps
+        # Inside the loop graph the GM branch of step i (GM UNet + its scheduler step) runs on a side stream beside the SDR UNet of
+        # step i+1: the SDR forward never reads GM state, only the SDR scheduler step does (it writes the GM UNet's input, whose tail is
+        # the GM latents).  Same kernels on the same data — bit-identical to the one-stream order — but the tail of every kernel of one
+        # UNet is filled by CTAs of the other.  GMD_TWO_STREAMS=0 keeps one stream (A/B).
+        self.use_two_streams = __import__("os").environ.get("GMD_TWO_STREAMS", "1") != "0"
+        self._side_stream = None
         self.cfg_pair = None   # gm_diffusion_b200.dist.CfgPair: split the CFG halves / the GM images over two ranks (latency mode)
 
     def enable_cfg_pair(self, group=None):
@@ -189,7 +195,7 @@ class StableDiffusionDualUNetPipeline(PipelineBase):
         loop_graph_ok = (self.use_cuda_graph and self.use_loop_graph and pair is None and callback is None and callback_on_step_end is None
                          and not stochastic)
         loop_key = (B, h, w, do_cfg, type(self.scheduler).__name__, tuple(ts), float(guidance_scale), float(guidance_rescale if do_cfg else 0.0),
-                    table_sdr.data_ptr(), table_gm.data_ptr())
+                    table_sdr.data_ptr(), table_gm.data_ptr(), self.use_two_streams)
         if pair is None:
             ws.set_context("kv_sdr", self.unet.project_context(sdr_ctx))
             ws.set_context("kv_gm", self.gm_unet.project_context(gm_ctx))
@@ -221,6 +227,36 @@ class StableDiffusionDualUNetPipeline(PipelineBase):
         eps_u = ws.eps_sdr[:B].reshape(-1, 4) if do_cfg else None
         eps_c = (ws.eps_sdr[B:] if do_cfg else ws.eps_sdr).reshape(-1, 4)
         eps_g = ws.eps_gm.reshape(-1, 4)
+
+        # 7a. the loop on two streams (loop graph only): stream order within a branch, events between the branches
+        def denoise_loop_two_streams(progress_bar):
+            from .. import ops
+            main = torch.cuda.current_stream()
+            if self._side_stream is None:
+                self._side_stream = torch.cuda.Stream(device=device)
+            side = self._side_stream
+            gm_done = None
+            for i, t in enumerate(ts):
+                ws.temb_sdr.copy_(table_sdr[i:i + 1])
+                run_sdr()                                                       # SDR eps of step i  ||  GM branch of step i-1
+                if gm_done is not None:
+                    main.wait_event(gm_done)                                    # GM latents of step i-1 written, ws.gm_in no longer read
+                S.fused_step(self.scheduler.plan_step(t, extra["eta"]), ws.sdr, eps_c, eps_u, guidance_scale=guidance_scale,
+                             guidance_rescale=guidance_rescale if do_cfg else 0.0, px_per_sample=h * w,
+                             x0_coeffs=self.scheduler.x0_coeffs(t), unet_in_next=ws.unet_in, unet_in_dup=1,
+                             concat_out=ws.gm_in, concat_tail=ws.gm.x, rescale_ws=ws.rescale_ws)
+                sdr_stepped = torch.cuda.Event()
+                sdr_stepped.record(main)
+                side.wait_event(sdr_stepped)
+                with torch.cuda.stream(side), ops.scratch_slot(1):
+                    ws.temb_gm.copy_(table_gm[i:i + 1])
+                    run_gm()
+                    S.fused_step(self.gm_scheduler.plan_step(t, extra["eta"]), ws.gm, eps_g, x0_coeffs=self.gm_scheduler.x0_coeffs(t))
+                    gm_done = torch.cuda.Event()
+                    gm_done.record(side)
+                progress_bar.update()
+            if gm_done is not None:
+                main.wait_event(gm_done)
 
         # 7. denoising loop (:1040-1113)
         def denoise_loop(progress_bar):
@@ -259,13 +295,20 @@ class StableDiffusionDualUNetPipeline(PipelineBase):
             else:
                 ent = self._loop_graphs.get(loop_key)
                 if ent is None:
+                    two = self.use_two_streams and not self.interrupt
                     ws.temb_sdr.copy_(table_sdr[0:1]); ws.temb_gm.copy_(table_gm[0:1])
-                    run_sdr(); run_gm()                # eager warm-up: lazily allocated scratch exists before the capture; eps buffers are rewritten
+                    run_sdr()                          # eager warm-up: lazily allocated scratch exists before the capture; eps buffers are rewritten
+                    if two:
+                        from .. import ops
+                        with ops.scratch_slot(1):
+                            run_gm()
+                    else:
+                        run_gm()
                     torch.cuda.synchronize()
                     n0 = L.launch_count()
                     lg = torch.cuda.CUDAGraph()
                     with torch.cuda.graph(lg):
-                        denoise_loop(progress_bar)
+                        (denoise_loop_two_streams if two else denoise_loop)(progress_bar)
                     n_kernels = L.launch_count() - n0      # launches recorded by the capture pass = kernels per replay
                     L.lib().gmd_add_launch_count(-n_kernels)   # (they did not run)
                     if len(self._loop_graphs) >= 4:

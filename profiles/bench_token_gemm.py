@@ -5,7 +5,10 @@ import sys
 from pathlib import Path
 sys.path.insert(0, str(Path(__file__).resolve().parent.parent))
 import torch
-from gm_diffusion_b200 import ops
+import os
+from gm_diffusion_b200 import _lib, ops
+if os.environ.get('GMD_AB_LIB'):   # A/B runs against an alternative build of the library
+    _lib.LIB_PATH = Path(os.environ['GMD_AB_LIB']).resolve()
 
 dev = torch.device("cuda")
 g = torch.Generator(device=dev).manual_seed(0)

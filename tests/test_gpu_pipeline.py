@@ -94,7 +94,9 @@ def test_whole_loop_graph_is_bit_identical_to_eager_stepping(dual_pipe):
     kw = dict(prompt_embeds=pe, negative_prompt_embeds=ne, height=256, width=256, output_type="latent")
     dual_pipe.use_cuda_graph = True
     dual_pipe._loop_graphs.clear()
-    for steps, g in ((4, 7.5), (6, 3.0)):
+    # (the loop graph runs the GM branch of step i on a side stream beside the SDR UNet of step i+1: use_two_streams; both forms are checked)
+    for steps, g, two in ((4, 7.5, True), (6, 3.0, True), (4, 7.5, False)):
+        dual_pipe.use_two_streams = two
         dual_pipe.use_loop_graph = False
         want = [dual_pipe(latents=x.clone(), num_inference_steps=steps, guidance_scale=g, **kw) for x in (lat, lat2)]
         dual_pipe.use_loop_graph = True
@@ -103,6 +105,7 @@ def test_whole_loop_graph_is_bit_identical_to_eager_stepping(dual_pipe):
         assert len(dual_pipe._loop_graphs) == n_graphs + 1, "one loop graph per (schedule, guidance) key"
         for (gs, gg), (ws_, wg) in zip(got, want + want[:1]):
             assert torch.equal(gs, ws_) and torch.equal(gg, wg), "loop graph differs from eager stepping"
+    dual_pipe.use_two_streams = True
     # a callback needs the host between steps: the pipeline must fall back to eager stepping and still call it
     seen = []
     dual_pipe(latents=lat.clone(), num_inference_steps=4, guidance_scale=7.5, callback=lambda i, t, x: seen.append((i, t)), callback_steps=1, **kw)
