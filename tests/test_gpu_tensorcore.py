@@ -237,16 +237,16 @@ def test_conv_lowres_splitk_is_batch_independent():
             one = ops.conv2d(x[i:i + 1].contiguous(), wt, 1280, bias=b, row_bias=rb[i:i + 1].contiguous(), residual=res[i:i + 1].contiguous())
             assert torch.equal(one, full[i:i + 1]), (hw, cin, i)
         # chunked: a workspace that only fits one tile of images
-        big = ops._WS.get(0)
+        big = ops._WS.get((0, 0))   # (device 0, scratch slot 0)
         try:
             per_img = 4 * hw * hw * 1280 * 4
             imgs_per_tile = 128 // (hw * hw)
-            ops._WS[0] = torch.empty(per_img * imgs_per_tile + 64, dtype=torch.uint8, device="cuda")
+            ops._WS[(0, 0)] = torch.empty(per_img * imgs_per_tile + 64, dtype=torch.uint8, device="cuda")
             L.lib().gmd_reset_launch_count()
             chunked = ops.conv2d(x, wt, 1280, bias=b, row_bias=rb, residual=res)
             assert L.lib().gmd_launch_count() == 2 * -(-5 // imgs_per_tile)
         finally:
-            ops._WS[0] = big
+            ops._WS[(0, 0)] = big
         assert torch.equal(chunked, full), (hw, cin)
 
 
