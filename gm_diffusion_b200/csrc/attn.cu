@@ -132,6 +132,9 @@ __device__ long long g_attn_trace[8 * 1024];
 #ifndef GMD_ATTN2_POLY40
 #define GMD_ATTN2_POLY40 4     // the d = 40 default: a quarter of the exponentials on the FMA pipe
 #endif
+#ifndef GMD_ATTN2_POLY80
+#define GMD_ATTN2_POLY80 4     // d = 80 likewise (B=16 N=1024: 67.6 -> 66.5 us, B=8: 41.0 -> 38.9 us)
+#endif
 #ifndef GMD_ATTN2_KO
 #define GMD_ATTN2_KO 0        // timing-only knock-outs of attn2_kernel (wrong results): 1 no MUFU, 2 no P stores, 4 no S loads, 8 no row sums / maxima, 16 no K / V traffic after the first ring fill
 #endif
@@ -1494,7 +1497,7 @@ extern "C" int gmd_attn_fwd(const gmd_attn_params* p, void* stream) {
             return p->Nk <= 2 * BKV ? launch<40, true>(p, st) : launch<40, false>(p, st);
         case 80:
             if (xattn) return launch_x<80>(p, st);
-            if (v2) return launch2<80, 64, 1, false, 2, 1, 2>(p, st);
+            if (v2) return launch2<80, 64, 1, false, 2, 1, 2, 1, 0, GMD_ATTN2_POLY80>(p, st);
             return launch<80, false>(p, st);   // (the short configuration does not add a third resident CTA at d = 80: measured slightly slower)
         case 160: return launch<160, false>(p, st);
         default: set_last_error("gmd_attn_fwd: head dim %d not instantiated (40, 80, 160)", p->d); return kErrUnsupported;
