@@ -79,11 +79,6 @@ __device__ __forceinline__ float exp2_poly(float x) {
 #ifndef GMD_ATTN2_F32X2
 #define GMD_ATTN2_F32X2 1     // scale-and-shift and the row sums of attn2_kernel as packed fp32 pairs (FFMA2 / FADD2: half the issue slots; 0 = scalar, A/B)
 #endif
-// Blackwell's packed fp32 pair arithmetic (fma / add .f32x2 -> FFMA2 / FADD2): one issue slot for two lanes of a 64-bit register pair.
-__device__ __forceinline__ uint64_t f32x2_pack(float a, float b) { uint64_t r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b)); return r; }
-__device__ __forceinline__ void f32x2_unpack(uint64_t v, float& a, float& b) { asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v)); }
-__device__ __forceinline__ uint64_t f32x2_fma(uint64_t a, uint64_t b, uint64_t c) { uint64_t d; asm("fma.rn.ftz.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c)); return d; }
-__device__ __forceinline__ uint64_t f32x2_add(uint64_t a, uint64_t b) { uint64_t d; asm("add.rn.ftz.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
 #ifndef GMD_ATTN2_POLYPAIR
 #define GMD_ATTN2_POLYPAIR 1  // 1: the polynomial exponentials of attn2_kernel come in adjacent pairs (elements 2*POLY-2, 2*POLY-1 of every 2*POLY) on FFMA2 / FADD2
 #endif

@@ -95,6 +95,40 @@ __device__ __forceinline__ float gelu_fast(float x) {
     return x * (x >= 0.0f ? 1.0f - w : w);
 }
 
+#ifndef GMD_GEMM_F32X2
+#define GMD_GEMM_F32X2 1   // epilogue arithmetic on packed fp32 pairs (FFMA2 / FADD2 / FMUL2: half the issue slots; the K = 320 GEMMs are epilogue-bound); 0: scalar (A/B)
+#endif
+// (a + ba) * gelu(g + bg) for a register pair: the same A&S erf as gelu_fast with the polynomial, the products and the final blend on
+// packed pairs, and x Phi(x) written without a select: 0.5 x + |x| (0.5 - w)  (19 instructions per pair instead of 2 x 17)
+__device__ __forceinline__ void geglu_pair(float a0, float a1, float g0, float g1, float4 ba, float4 bg, int hi, float& o0, float& o1) {
+    const uint64_t av = f32x2_add(f32x2_pack(a0, a1), hi ? f32x2_pack(ba.z, ba.w) : f32x2_pack(ba.x, ba.y));
+    const uint64_t x = f32x2_add(f32x2_pack(g0, g1), hi ? f32x2_pack(bg.z, bg.w) : f32x2_pack(bg.x, bg.y));
+    float x0, x1;
+    f32x2_unpack(x, x0, x1);
+    const float t0 = rcp_ftz(fmaf(fabsf(x0), 0.23164189f, 1.0f)), t1 = rcp_ftz(fmaf(fabsf(x1), 0.23164189f, 1.0f));
+    float q0, q1;
+    f32x2_unpack(f32x2_mul(f32x2_mul(x, x), f32x2_bcast(-0.72134752f)), q0, q1);
+    const uint64_t e = f32x2_pack(ex2_ftz(q0), ex2_ftz(q1)), t = f32x2_pack(t0, t1);
+    uint64_t h = f32x2_fma(t, f32x2_bcast(0.5307027145f), f32x2_bcast(-0.7265760135f));
+    h = f32x2_fma(t, h, f32x2_bcast(0.7107068705f));
+    h = f32x2_fma(t, h, f32x2_bcast(-0.142248368f));
+    h = f32x2_fma(t, h, f32x2_bcast(0.127414796f));
+    const uint64_t w = f32x2_mul(f32x2_mul(h, t), e);
+    const uint64_t hm = f32x2_fma(w, f32x2_bcast(-1.0f), f32x2_bcast(0.5f));                 // 0.5 - w
+    const uint64_t ge = f32x2_fma(f32x2_pack(fabsf(x0), fabsf(x1)), hm, f32x2_mul(x, f32x2_bcast(0.5f)));   // x Phi(x)
+    f32x2_unpack(f32x2_mul(av, ge), o0, o1);
+}
+
+// v[0..3] += a (two FADD2 when the epilogue runs on packed pairs)
+__device__ __forceinline__ void add4(float* v, float4 a) {
+#if GMD_GEMM_F32X2
+    f32x2_unpack(f32x2_add(f32x2_pack(v[0], v[1]), f32x2_pack(a.x, a.y)), v[0], v[1]);
+    f32x2_unpack(f32x2_add(f32x2_pack(v[2], v[3]), f32x2_pack(a.z, a.w)), v[2], v[3]);
+#else
+    v[0] += a.x; v[1] += a.y; v[2] += a.z; v[3] += a.w;
+#endif
+}
+
 // Shared-memory plan of one CTA.  RB = bytes per element of the residual prefetch buffer (4 holds fp32 or bf16 rows).
 template <int MT, int BN, int STAGES, int RB, int HALO = 0, int PAIR = 0>
 struct Plan {
@@ -688,6 +722,11 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__ 
 #pragma unroll
                             for (int j = 0; j < 4; ++j) {
                                 float4 a = args.bias ? lds128(bv + 16 * j) : make_float4(0, 0, 0, 0), g = args.bias ? lds128(bg + 16 * j) : make_float4(0, 0, 0, 0);
+#if GMD_GEMM_F32X2
+                                geglu_pair(__uint_as_float(r0[4 * j + 0]), __uint_as_float(r0[4 * j + 1]), __uint_as_float(r1[4 * j + 0]), __uint_as_float(r1[4 * j + 1]), a, g, 0, v[4 * j + 0], v[4 * j + 1]);
+                                geglu_pair(__uint_as_float(r0[4 * j + 2]), __uint_as_float(r0[4 * j + 3]), __uint_as_float(r1[4 * j + 2]), __uint_as_float(r1[4 * j + 3]), a, g, 1, v[4 * j + 2], v[4 * j + 3]);
+                                continue;
+#endif
                                 v[4 * j + 0] = (__uint_as_float(r0[4 * j + 0]) + a.x) * gelu_fast(__uint_as_float(r1[4 * j + 0]) + g.x);
                                 v[4 * j + 1] = (__uint_as_float(r0[4 * j + 1]) + a.y) * gelu_fast(__uint_as_float(r1[4 * j + 1]) + g.y);
                                 v[4 * j + 2] = (__uint_as_float(r0[4 * j + 2]) + a.z) * gelu_fast(__uint_as_float(r1[4 * j + 2]) + g.z);
@@ -728,7 +767,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__ 
                             if (args.bias) {
                                 const uint32_t b4 = bias_sa + (c * 32) * 4;
 #pragma unroll
-                                for (int j = 0; j < 8; ++j) { float4 a = lds128(b4 + 16 * j); v[4 * j] += a.x; v[4 * j + 1] += a.y; v[4 * j + 2] += a.z; v[4 * j + 3] += a.w; }
+                                for (int j = 0; j < 8; ++j) { float4 a = lds128(b4 + 16 * j); add4(v + 4 * j, a); }
                             }
                             if (rb_row) {
                                 const float4* b4 = reinterpret_cast<const float4*>(rb_row + col0);
@@ -740,7 +779,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__ 
 #pragma unroll
                                     for (int j = 0; j < 8; ++j) {
                                         float4 a = *reinterpret_cast<const float4*>(my_res + (c * 8 + j) * 16);
-                                        v[4 * j] += a.x; v[4 * j + 1] += a.y; v[4 * j + 2] += a.z; v[4 * j + 3] += a.w;
+                                        add4(v + 4 * j, a);
                                     }
                                 } else {
 #pragma unroll
