@@ -99,9 +99,11 @@ def _check_fresh() -> None:
 
 def lib() -> C.CDLL:
     """Load the shared library (once). Raises if it has not been built — there is no CPU path."""
-    global _lib
+    global _lib, LIB_PATH
     if _lib is not None:
         return _lib
+    if os.environ.get("GMD_AB_LIB") and LIB_PATH == _ROOT / "_C" / "libgmd_b200.so":
+        LIB_PATH = Path(os.environ["GMD_AB_LIB"]).resolve()   # an alternative build of the library for A/B measurements (profiles/, bench.py)
     if not LIB_PATH.exists():
         raise RuntimeError(
             f"{LIB_PATH} is missing: build it with `python -m gm_diffusion_b200.build` "
