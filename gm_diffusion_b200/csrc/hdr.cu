@@ -74,8 +74,10 @@ __device__ __forceinline__ float tmo_apply(float x, const HdrConsts& c) {
         case GMD_TMO_HARD_CLIP: return fminf(fmaxf(x, 0.0f), 1.0f);
         case GMD_TMO_MULOG: {
             float y = x * c.inv_hi;
-            float t = log1p_pos(fmaxf(c.mu * y, 0.0f)) * c.inv_log1p_mu;
-            return fminf(fmaxf(t, 0.0f), 1.0f);
+            const float m = c.mu * y;
+            float t = log1p_pos(fmaxf(m, 0.0f)) * c.inv_log1p_mu;       // (-1, 0): a negative logarithm, clamped to 0 below like the reference's
+            t = fminf(fmaxf(t, 0.0f), 1.0f);
+            return m >= -1.0f ? t : __int_as_float(0x7fc00000);         // NaN input or the log of a negative number: NaN, as torch.log gives (tone_mapping.py:33-40)
         }
         case GMD_TMO_CUDA: {
             float y = fminf(fmaxf(x * 0.1f, 0.0f), 1.0f);
@@ -102,9 +104,10 @@ __device__ __forceinline__ int32_t ordered_from_float(float f) {
 
 struct MinMax {
     float lo = INFINITY, hi = -INFINITY;
+    bool nan = false;               // a NaN was seen: the maximum is reported as NaN (ordered code above +inf), as torch.max would
     __device__ __forceinline__ void add(float v) {
         lo = fminf(lo, v); hi = fmaxf(hi, v);
-        if (v != v) hi = INFINITY;  // NaN marker (tmo_cuda's range check, tone_mapping.py:43-45)
+        nan |= v != v;              // (tmo_cuda's range check, tone_mapping.py:43-45, fails exactly for NaN inputs: +-inf are clamped first)
     }
 };
 
@@ -117,7 +120,7 @@ __device__ __forceinline__ void minmax_commit(MinMax mm, int32_t* out) {
     __shared__ float s_lo[32], s_hi[32];
     int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = (blockDim.x + 31) >> 5;
     if (lane == 0) { s_lo[warp] = mm.lo; s_hi[warp] = mm.hi; }
-    __syncthreads();
+    const int any_nan = __syncthreads_or(mm.nan ? 1 : 0);
     if (warp == 0) {
         float lo = lane < nw ? s_lo[lane] : __int_as_float(0x7f800000);
         float hi = lane < nw ? s_hi[lane] : __int_as_float(0xff800000);
@@ -128,7 +131,7 @@ __device__ __forceinline__ void minmax_commit(MinMax mm, int32_t* out) {
         }
         if (lane == 0) {
             atomicMin(out, ordered_from_float(lo));
-            atomicMax(out + 1, ordered_from_float(hi));
+            atomicMax(out + 1, any_nan ? 0x7fc00000 : ordered_from_float(hi));
         }
     }
 }

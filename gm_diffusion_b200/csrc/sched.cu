@@ -55,7 +55,9 @@ __global__ void __launch_bounds__(256) rescale_stats_kernel(const float* __restr
 #define DIV(a, b) __fdiv_rn(a, b)
 
 struct F4 { float v[4]; };
-__device__ __forceinline__ F4 ld(const float* p, int64_t i) { float4 t = ld4(p, i); return {{t.x, t.y, t.z, t.w}}; }
+// (plain loads, not ld.global.nc: x, the history ring and the stash are rewritten in place by the same launch — each thread reads its
+// element before it writes it, but the read-only path is formally undefined for memory the kernel writes)
+__device__ __forceinline__ F4 ld(const float* p, int64_t i) { float4 t = *(reinterpret_cast<const float4*>(p) + i); return {{t.x, t.y, t.z, t.w}}; }
 __device__ __forceinline__ float4 f4(const F4& a) { return make_float4(a.v[0], a.v[1], a.v[2], a.v[3]); }
 
 __global__ void __launch_bounds__(256) sched_kernel(gmd_sched_params p) {

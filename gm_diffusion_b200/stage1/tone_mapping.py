@@ -171,7 +171,7 @@ def tmo_cuda(hdr_img: torch.Tensor) -> torch.Tensor:
     _, out, mm = _run(hdr_img, None, flags=0, tmo=L.TMO_CUDA, qmax=0, eps=0, mu=5000.0, want_hdr=False, want_tmo=True,
                       want_minmax=True)
     lo, hi = _decode_minmax(mm)
-    if hdr_img.numel() and not (hi < float("inf")):  # the kernel flags NaN inputs as max = +inf
+    if hdr_img.numel() and hi != hi:  # the kernel reports the maximum of a tensor with NaNs as NaN; +-inf are clamped into [0, 1] like the reference does
         raise ValueError("HDR image values should be in the range [0, 1]")
     if _needs_grad(hdr_img):
         return _chain(hdr_img, None, flags=0, tmo=L.TMO_CUDA, qmax=0, eps=0, mu=5000.0, which="tmo")
