@@ -133,7 +133,16 @@ class _HdrChainFn(torch.autograd.Function):
 def _chain(sdr, gm, *, flags, tmo, qmax, eps, mu, which, layout=None):
     """One differentiable output of the fused chain (`which` = "hdr" | "tmo")."""
     L.require_cuda(sdr, gm)
-    return _HdrChainFn.apply(sdr, gm, dict(flags=flags, tmo=tmo, qmax=qmax, eps=eps, mu=mu, which=which, layout=layout))
+    # The kernels compute in fp32 on same-shape operands.  Mixed precision (accelerate fp16 / bf16 in train_vqgan_lora.py) and a
+    # broadcast gain map go through differentiable torch casts / expands around the fused launch, and the result comes back in the
+    # dtype torch's own promotion would give the reference expression.
+    out_dtype = sdr.dtype if gm is None else torch.result_type(sdr, gm)
+    if gm is not None and gm.shape != sdr.shape:
+        sdr, gm = torch.broadcast_tensors(sdr, gm)
+    s32 = sdr.to(torch.float32)
+    g32 = gm.to(torch.float32) if gm is not None else None
+    y = _HdrChainFn.apply(s32, g32, dict(flags=flags, tmo=tmo, qmax=qmax, eps=eps, mu=mu, which=which, layout=layout))
+    return y if y.dtype == out_dtype or not out_dtype.is_floating_point else y.to(out_dtype)
 
 
 def _decode_minmax(mm: torch.Tensor) -> Tuple[float, float]:
