@@ -342,3 +342,22 @@ def test_text_encoder_outputs_are_cached_per_prompt():
         pe2, ne2 = pipe.encode_prompt(["a dog", "a cat"], "cpu", 1, True)
     assert pipe.text_encoder.calls == 2                           # everything came from the cache
     assert torch.equal(pe2[0], pe1[1]) and torch.equal(pe2[1], pe1[0]) and torch.equal(ne1, ne2) and ne1.shape == (2, 77, 8)
+
+
+def test_scratch_slots_keep_concurrent_streams_apart():
+    """The library's static scratch (split-K workspace, GroupNorm accumulator arena) is keyed by (device, slot): the loop graph runs
+    the GM branch on a side stream under `ops.scratch_slot(1)` beside the SDR UNet on slot 0 (stable_diffusion_dual_unet.py
+    denoise_loop_two_streams).  Host logic only: keys nest, restore on exit (also on an exception) and never alias across slots."""
+    from gm_diffusion_b200 import ops
+    assert ops._scratch_key("cuda:0") == (0, 0) and ops._scratch_key("cuda:3") == (3, 0)
+    with ops.scratch_slot(1):
+        assert ops._scratch_key("cuda:0") == (0, 1)
+        with ops.scratch_slot(2):
+            assert ops._scratch_key("cuda:0") == (0, 2)
+        assert ops._scratch_key("cuda:0") == (0, 1)
+        assert ops.gn_arena("cuda:0").key == (0, 1)
+    assert ops._scratch_key("cuda:0") == (0, 0)
+    with pytest.raises(RuntimeError):
+        with ops.scratch_slot(5):
+            raise RuntimeError("boom")
+    assert ops._scratch_key("cuda:0") == (0, 0)
