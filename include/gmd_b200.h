@@ -67,7 +67,8 @@ typedef struct gmd_hdr_params {
     const void* gm;    /* gain map; may be NULL when GMD_HDR_EQ1 is not set */
     float* hdr_out;    /* optional: Eq.(1) output */
     float* tmo_out;    /* optional: TMO (+gamut) output */
-    int32_t* minmax;   /* optional: 2 ordered-int32 slots {min,max} of the hdr values; decode with gmd_decode_ordered */
+    int32_t* minmax;   /* optional: 2 ordered-int32 slots {min,max} of the hdr values; decode with gmd_decode_ordered.  A NaN anywhere makes the
+                          maximum decode to NaN (code 0x7fc00000, above +inf), as torch.max would report it */
     int64_t n_px;      /* PLANAR3: H*W per image plane; INTERLEAVED3: pixels; FLAT: elements */
     int64_t batch;     /* PLANAR3: number of images (planes = 3*batch); otherwise 1 */
     int32_t layout;    /* enum gmd_layout */
