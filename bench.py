@@ -6,7 +6,8 @@
 
 One "step" = one batch of 8 images per GPU through the WHOLE path: prompt embeddings -> 51-eval PNDM dual-branch loop
 (SDR UNet under CFG 7.5 + GM UNet, bf16 tensor-core kernels, fp32 latents) -> 2x VAE decode -> Eq.(1) qmax=99 -> HDR fp32
-[B,512,512,3].  Weak scaling: every rank runs its own batch of 8 (global batch 8N), no collective inside the loop, one
+[B,512,512,3].  The loop is one CUDA graph on two streams (GM branch of step i beside the SDR UNet of step i+1; GMD_TWO_STREAMS=0
+keeps one stream).  Weak scaling: every rank runs its own batch of 8 (global batch 8N), no collective inside the loop, one
 NCCL all-gather of the HDR outputs per step.  Synthetic data: random-init SD1.5-architecture weights, N(0,1) embeddings.
 
 `value`  : images/s with inputs resident in HBM, device-timed (CUDA events), max over ranks.
