@@ -173,5 +173,5 @@ def run(TMO, UO, build_pipeline):
     out["unet_forward"] = {"samples": 2 * B, "latent": "64x64", "gflop": round(2 * B * 803.3, 1),
                            "ms": {"gm_diffusion_b200 (eager launches, CFG-shared prefix, cached text K/V and timestep table)": ms_ours,
                                   "torch eager bf16 channels_last, cuDNN benchmark, SDPA (the reference's stack)": ms_ref},
-                           "note": "the bench replays the same forward from a CUDA graph (profiles/bench_r01_1gpu.json: ms_per_denoise_step covers SDR(16) + GM(8) forwards)"}
+                           "note": "the bench replays the same forward from a CUDA graph (the bench line: ms_per_denoise_step covers SDR(16) + GM(8) forwards, gpu_comparator.unet_forward_2B_samples_ms_ours_in_graph is this forward alone)"}
     return out
