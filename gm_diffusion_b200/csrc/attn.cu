@@ -130,6 +130,9 @@ __device__ long long g_attn_trace[8 * 1024];
 #ifndef GMD_ATTN2_POLY80
 #define GMD_ATTN2_POLY80 4     // d = 80 likewise (B=16 N=1024: 67.6 -> 66.5 us, B=8: 41.0 -> 38.9 us)
 #endif
+#ifndef GMD_ATTN2_ALIAS80
+#define GMD_ATTN2_ALIAS80 1    // d = 80 with P stored over S like d = 40 (B=16 N=1024: 67.6 -> 65.6 us; 0: separate single P buffer, A/B)
+#endif
 #ifndef GMD_ATTN2_KO
 #define GMD_ATTN2_KO 0        // timing-only knock-outs of attn2_kernel (wrong results): 1 no MUFU, 2 no P stores, 4 no S loads, 8 no row sums / maxima, 16 no K / V traffic after the first ring fill
 #endif
@@ -1492,7 +1495,7 @@ extern "C" int gmd_attn_fwd(const gmd_attn_params* p, void* stream) {
             return p->Nk <= 2 * BKV ? launch<40, true>(p, st) : launch<40, false>(p, st);
         case 80:
             if (xattn) return launch_x<80>(p, st);
-            if (v2) return launch2<80, 64, 1, false, 2, 1, 2, 1, 0, GMD_ATTN2_POLY80>(p, st);
+            if (v2) return GMD_ATTN2_ALIAS80 ? launch2<80, 64, 1, true, 2, 2, 2, 1, 0, GMD_ATTN2_POLY80>(p, st) : launch2<80, 64, 1, false, 2, 1, 2, 1, 0, GMD_ATTN2_POLY80>(p, st);
             return launch<80, false>(p, st);   // (the short configuration does not add a third resident CTA at d = 80: measured slightly slower)
         case 160: return launch<160, false>(p, st);
         default: set_last_error("gmd_attn_fwd: head dim %d not instantiated (40, 80, 160)", p->d); return kErrUnsupported;
